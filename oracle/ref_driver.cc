@@ -1,0 +1,257 @@
+// oracle/ref_driver.cc -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the UNMODIFIED reference classes (linked from oracle/_ref/libqballref.a, compiled from the sources where
+// they lie under /root/reference) on explicit input arrays and dumps raw arrays, so that the C restatement
+// (oracle/qb_oracle.c) and the CUDA path can be pinned against the reference itself at array level.
+//
+// The reference calls exercised (all on one rank, nprow = npcol = 1):
+//   Basis::resize                         src/qball/Basis.cc:302-700
+//   FourierTransform::backward/forward    src/qball/FourierTransform.cc:529-581 (+ pair forms)
+//   SlaterDet::rs_mul_add                 src/qball/SlaterDet.cc:971-1040
+//   SlaterDet::compute_density            src/qball/SlaterDet.cc:839-932
+//   NonLocalPotential::energy (NC branch) src/qball/NonLocalPotential.cc:1909-2171
+// The kinetic term of EnergyFunctional::energy (EnergyFunctional.cc:1675-1690) lives inside a function that needs a
+// whole Sample; its three-line loop is restated here in the same order (clear -> nonlocal -> kinetic -> local).
+//
+// usage:  ref_driver basis <case.txt>     dump basis / grid tables to <out>.*
+//         ref_driver run   <case.txt>     read <out>.in_c.f64, <out>.in_v.f64, <out>.in_occ.f64 ; dump results
+//
+// case file (one directive per line):
+//   cell a0x a0y a0z a1x a1y a1z a2x a2y a2z     (bohr)
+//   ecut E                                        (hartree)
+//   kpoint kx ky kz                               (crystal units, as the reference's `kpoint` command)
+//   force_complex 0|1
+//   grid np0 np1 np2                              (0 0 0 => ChargeDensity::initialize rule, ChargeDensity.cc:77-99)
+//   nst N
+//   species <name> <file.xml>
+//   atom <name> <species> x y z                   (bohr)
+//   out <prefix>
+
+#include <fstream>
+#include <sstream>
+#include <iostream>
+#include <iomanip>
+#include <vector>
+#include <valarray>
+#include <complex>
+#include <string>
+#include <map>
+#include <list>
+#include <cstdio>
+#include <cstring>
+#include <omp.h>
+#include <qball/Basis.h>
+#include <qball/FourierTransform.h>
+#include <qball/SlaterDet.h>
+#include <qball/AtomSet.h>
+#include <qball/Atom.h>
+#include <qball/Species.h>
+#include <qball/SpeciesReader.h>
+#include <qball/Context.h>
+#include <qball/UnitCell.h>
+#include <qball/Timer.h>
+#include <qball/VectorPotential.h>
+#include <math/matrix.h>
+// the driver needs the projector tables (twnl, wt, lproj), which are private members of NonLocalPotential;
+// every header it includes is already included above, so only that one class is affected.
+#define private public
+#include <qball/NonLocalPotential.h>
+#undef private
+using namespace std;
+
+static void dump(const string& fn, const void* p, size_t bytes)
+{
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f) { perror(fn.c_str()); exit(2); }
+  if (bytes) fwrite(p, 1, bytes, f);
+  fclose(f);
+}
+static void slurp(const string& fn, void* p, size_t bytes)
+{
+  FILE* f = fopen(fn.c_str(), "rb");
+  if (!f) { perror(fn.c_str()); exit(2); }
+  size_t got = fread(p, 1, bytes, f);
+  fclose(f);
+  if (got != bytes) { fprintf(stderr, "%s: short read %zu of %zu\n", fn.c_str(), got, bytes); exit(2); }
+}
+
+struct AtomLine { string name, species; double x, y, z; };
+
+int main(int argc, char** argv)
+{
+  if (argc < 3) { fprintf(stderr, "usage: ref_driver basis|run|time <case.txt> [nrep]\n"); return 1; }
+  const string mode = argv[1];
+  MPI_Init(&argc, &argv);
+  {
+  double a[9] = {0}; double ecut = 0, kp[3] = {0,0,0}; int force_complex = 0; int grid[3] = {0,0,0}; int nst = 1;
+  vector<pair<string,string> > species; vector<AtomLine> atomlines; string out = "case";
+  ifstream in(argv[2]);
+  if (!in) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+  string line;
+  while (getline(in, line)) {
+    istringstream is(line); string key; is >> key;
+    if (key == "cell") for (int i = 0; i < 9; i++) is >> a[i];
+    else if (key == "ecut") is >> ecut;
+    else if (key == "kpoint") is >> kp[0] >> kp[1] >> kp[2];
+    else if (key == "force_complex") is >> force_complex;
+    else if (key == "grid") is >> grid[0] >> grid[1] >> grid[2];
+    else if (key == "nst") is >> nst;
+    else if (key == "species") { string n, f; is >> n >> f; species.push_back(make_pair(n, f)); }
+    else if (key == "atom") { AtomLine al; is >> al.name >> al.species >> al.x >> al.y >> al.z; atomlines.push_back(al); }
+    else if (key == "out") is >> out;
+  }
+
+  Context ctxt(1,1);
+  Context ctxtsq(ctxt,1,1,0,0);
+  Context colctxt(ctxt,1,1,0,0);
+  UnitCell cell(D3vector(a[0],a[1],a[2]), D3vector(a[3],a[4],a[5]), D3vector(a[6],a[7],a[8]));
+  D3vector kpoint(kp[0],kp[1],kp[2]);
+
+  SlaterDet sd(ctxt, colctxt, ctxtsq, kpoint, false, force_complex != 0);
+  sd.set_nblocks(1,1);
+  sd.resize(cell, cell, ecut, nst);
+  const Basis& basis = sd.basis();
+
+  if (grid[0] == 0) {
+    // ChargeDensity::initialize grid rule (ChargeDensity.cc:77-99): density basis at 4*ecut, +2, factorizable
+    Basis vbasis(colctxt, D3vector(0,0,0), false);
+    vbasis.resize(cell, cell, 4.0*ecut);
+    for (int d = 0; d < 3; d++) { grid[d] = vbasis.np(d) + 2; while (!vbasis.factorizable(grid[d])) grid[d] += 2; }
+  }
+  FourierTransform ft(basis, grid[0], grid[1], grid[2]);
+  const int ngw = basis.localsize();
+  const int mloc = sd.c().mloc();
+  const int nrods = basis.nrod_loc();
+  const size_t N = ft.np012loc();
+
+  {
+    int hdr[16] = { grid[0], grid[1], grid[2], ngw, nrods, basis.real() ? 1 : 0, mloc, nst,
+                    basis.np(0), basis.np(1), basis.np(2), basis.idxmin(1), basis.idxmax(1), (int)species.size(), 0, 0 };
+    dump(out + ".hdr.i32", hdr, sizeof(hdr));
+    vector<int> rods(4*nrods);
+    for (int i = 0; i < nrods; i++) { rods[i] = basis.rod_h(i); rods[nrods+i] = basis.rod_k(i);
+      rods[2*nrods+i] = basis.rod_lmin(i); rods[3*nrods+i] = basis.rod_size(i); }
+    dump(out + ".rods.i32", &rods[0], rods.size()*sizeof(int));
+    dump(out + ".idx.i32", basis.idx_ptr(), 3*ngw*sizeof(int));
+    dump(out + ".kpg2.f64", basis.kpg2_ptr(), ngw*sizeof(double));
+    dump(out + ".kpgx.f64", basis.kpgx_ptr(0), 3*ngw*sizeof(double));
+    double om = cell.volume();
+    dump(out + ".omega.f64", &om, sizeof(double));
+  }
+  if (mode == "basis") { MPI_Finalize(); return 0; }
+
+  // ---- atoms / species / projector tables
+  AtomSet atoms(ctxt);
+  atoms.set_cell(cell);
+  for (size_t i = 0; i < species.size(); i++) {
+    SpeciesReader rd(ctxt);
+    Species* sp = new Species(ctxt, species[i].first);
+    rd.readSpecies(*sp, species[i].second);
+    rd.bcastSpecies(*sp);
+    atoms.addSpecies(sp, species[i].first);
+  }
+  for (size_t i = 0; i < atomlines.size(); i++) {
+    Atom* at = new Atom(atomlines[i].name, atomlines[i].species,
+                        D3vector(atomlines[i].x, atomlines[i].y, atomlines[i].z), D3vector(0,0,0));
+    atoms.addAtom(at);
+  }
+  NonLocalPotential* nlp = 0;
+  if (!species.empty()) {
+    nlp = new NonLocalPotential(atoms, ctxt, basis, 0, false);
+    nlp->update_twnl(false);   // as EnergyFunctional does after construction (EnergyFunctional.cc:2036)
+    vector<vector<double> > tau; atoms.get_positions(tau, true);
+    for (int is = 0; is < nlp->nsp; is++) {
+      char tag[32]; snprintf(tag, sizeof tag, ".sp%d", is);
+      int h[4] = { nlp->na[is], nlp->npr[is], 0, 0 };
+      dump(out + tag + ".hdr.i32", h, sizeof h);
+      dump(out + tag + ".lproj.i32", nlp->npr[is] ? &nlp->lproj[is][0] : 0, nlp->npr[is]*sizeof(int));
+      dump(out + tag + ".wt.f64", nlp->npr[is] ? &nlp->wt[is][0] : 0, nlp->npr[is]*sizeof(double));
+      dump(out + tag + ".twnl.f64", nlp->npr[is] ? &nlp->twnl[is][0] : 0, (size_t)nlp->npr[is]*ngw*sizeof(double));
+      dump(out + tag + ".tau.f64", &tau[is][0], 3*nlp->na[is]*sizeof(double));
+    }
+  }
+
+  // ---- inputs
+  vector<complex<double> > cin((size_t)mloc*nst);
+  vector<double> v(N), occ(nst);
+  slurp(out + ".in_c.f64", &cin[0], cin.size()*sizeof(complex<double>));
+  slurp(out + ".in_v.f64", &v[0], N*sizeof(double));
+  slurp(out + ".in_occ.f64", &occ[0], nst*sizeof(double));
+  memcpy(sd.c().valptr(), &cin[0], cin.size()*sizeof(complex<double>));
+  sd.set_occ(occ);
+
+  if (mode == "time") {
+    // CPU baseline: the reference's own per-state loops, wall-clocked (used by bench.py's cpu_baseline leg)
+    const int nrep = argc > 3 ? atoi(argv[3]) : 1;
+    SlaterDet dsd(sd); dsd.c().clear();
+    vector<double> rho(N, 0.0);
+    vector<vector<double> > fion; valarray<double> sigma(6); vector<complex<double> > veff;
+    double t_loc = 0, t_nl = 0, t_rho = 0, t_kin = 0;
+    for (int r = 0; r < nrep; r++) {
+      Timer t0; t0.start(); if (nlp) nlp->energy(sd, true, dsd, false, fion, false, sigma, veff); t0.stop(); t_nl += t0.real();
+      Timer t1; t1.start();
+      { const double* kpg2 = basis.kpg2_ptr(); complex<double>* cp = dsd.c().valptr(); const complex<double>* c = sd.c().cvalptr();
+        for (int n = 0; n < sd.nstloc(); n++) for (int ig = 0; ig < ngw; ig++) cp[ig+mloc*n] += 0.5 * kpg2[ig] * c[ig+mloc*n]; }
+      t1.stop(); t_kin += t1.real();
+      Timer t2; t2.start(); sd.rs_mul_add(ft, &v[0], dsd); t2.stop(); t_loc += t2.real();
+      Timer t3; t3.start(); sd.compute_density(ft, 1.0, &rho[0]); t3.stop(); t_rho += t3.real();
+    }
+    printf("{\"nst\": %d, \"nrep\": %d, \"threads\": %d, \"t_nonlocal\": %.6f, \"t_kinetic\": %.6f, \"t_local\": %.6f, \"t_density\": %.6f}\n",
+           nst, nrep, omp_get_max_threads(), t_nl, t_kin, t_loc, t_rho);
+    MPI_Finalize(); return 0;
+  }
+
+  // ---- single transforms on state 0: f = backward(c0); g = v*f; c' = forward(g)
+  {
+    vector<complex<double> > f(N), cc(mloc);
+    ft.backward(sd.c().cvalptr(0), &f[0]);
+    dump(out + ".bwd0.f64", &f[0], N*sizeof(complex<double>));
+    for (size_t i = 0; i < N; i++) f[i] *= v[i];
+    ft.forward(&f[0], &cc[0]);
+    dump(out + ".fwd0.f64", &cc[0], ngw*sizeof(complex<double>));
+    if (basis.real() && nst >= 2) {
+      vector<complex<double> > c1(mloc), c2(mloc);
+      ft.backward(sd.c().cvalptr(0), sd.c().cvalptr(mloc), &f[0]);
+      dump(out + ".bwdpair01.f64", &f[0], N*sizeof(complex<double>));
+      for (size_t i = 0; i < N; i++) f[i] *= v[i];
+      ft.forward(&f[0], &c1[0], &c2[0]);
+      dump(out + ".fwdpair0.f64", &c1[0], ngw*sizeof(complex<double>));
+      dump(out + ".fwdpair1.f64", &c2[0], ngw*sizeof(complex<double>));
+    }
+  }
+
+  // ---- rs_mul_add alone (sdp starts at zero)
+  {
+    SlaterDet dsd(sd); dsd.c().clear();
+    sd.rs_mul_add(ft, &v[0], dsd);
+    dump(out + ".hloc.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+  }
+  // ---- density
+  {
+    vector<double> rho(N, 0.0);
+    sd.compute_density(ft, 1.0, &rho[0]);
+    dump(out + ".rho.f64", &rho[0], N*sizeof(double));
+  }
+  // ---- nonlocal alone, then the whole H psi in the reference's order: clear -> nonlocal -> kinetic -> local
+  {
+    SlaterDet dsd(sd); dsd.c().clear();
+    vector<vector<double> > fion; valarray<double> sigma(6); vector<complex<double> > veff;
+    double enl = 0.0;
+    if (nlp) {
+      enl = nlp->energy(sd, true, dsd, false, fion, false, sigma, veff);
+      dump(out + ".hnl.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+    }
+    dump(out + ".enl.f64", &enl, sizeof(double));
+    const double* kpg2 = basis.kpg2_ptr();
+    complex<double>* cp = dsd.c().valptr(); const complex<double>* c = sd.c().cvalptr();
+    for (int n = 0; n < sd.nstloc(); n++)
+      for (int ig = 0; ig < ngw; ig++)
+        cp[ig+mloc*n] += 0.5 * kpg2[ig] * c[ig+mloc*n];       // EnergyFunctional.cc:1675-1677
+    sd.rs_mul_add(ft, &v[0], dsd);                               // EnergyFunctional.cc:1695
+    dump(out + ".hpsi.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+  }
+  delete nlp;
+  }
+  MPI_Finalize();
+  return 0;
+}
