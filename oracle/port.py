@@ -1,0 +1,187 @@
+"""oracle/port.py -- TEST INFRASTRUCTURE ONLY: ctypes view of oracle/liboracle.so (the plain-C restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, f) for f in ("qb_oracle.c", "qb_oracle.h")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
+        subprocess.run(["make", "-C", HERE, "-s", "port"], check=True)
+    return LIB
+
+
+class _Basis(C.Structure):
+    _fields_ = [("is_real", C.c_int), ("np", C.c_int * 3), ("idxmin", C.c_int * 3), ("idxmax", C.c_int * 3),
+                ("ngw", C.c_int), ("nrods", C.c_int),
+                ("rod_h", C.POINTER(C.c_int)), ("rod_k", C.POINTER(C.c_int)), ("rod_lmin", C.POINTER(C.c_int)),
+                ("rod_size", C.POINTER(C.c_int)), ("rod_first", C.POINTER(C.c_int)), ("idx", C.POINTER(C.c_int)),
+                ("kpg2", C.POINTER(C.c_double)), ("kpgx", C.POINTER(C.c_double)), ("omega", C.c_double),
+                ("b", C.c_double * 9)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+        L.qbo_factorizable.restype = C.c_int
+        L.qbo_basis_create.restype = C.POINTER(_Basis)
+        L.qbo_basis_create.argtypes = [dp, C.c_double, dp, C.c_int]
+        L.qbo_basis_destroy.argtypes = [C.POINTER(_Basis)]
+        L.qbo_density_grid.argtypes = [dp, C.c_double, ip]
+        L.qbo_ft_create.restype = vp
+        L.qbo_ft_create.argtypes = [C.c_int] * 4 + [ip] * 4 + [C.c_int] * 3
+        L.qbo_ft_destroy.argtypes = [vp]
+        L.qbo_ft_nvec.argtypes = [vp]
+        L.qbo_ft_ntrans0.argtypes = [vp]
+        L.qbo_backward.argtypes = [vp, dp, dp]
+        L.qbo_forward.argtypes = [vp, dp, dp]
+        L.qbo_backward_pair.argtypes = [vp, dp, dp, dp]
+        L.qbo_forward_pair.argtypes = [vp, dp, dp, dp]
+        L.qbo_rs_mul_add.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_compute_density.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_kinetic_add.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_nl_energy_species.restype = C.c_double
+        L.qbo_nl_energy_species.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp,
+                                            dp, C.c_double, C.c_int, C.c_int, dp]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def make_basis(cell, ecut, kpoint=(0.0, 0.0, 0.0), force_complex=False) -> dict:
+    """Basis tables for one rank (same keys as refdrive.read_basis, minus the grid)."""
+    L = lib()
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    kp = np.ascontiguousarray(kpoint, dtype=np.float64)
+    p = L.qbo_basis_create(_d(cell), float(ecut), _d(kp), int(force_complex))
+    b = p.contents
+    ngw, nr = b.ngw, b.nrods
+    out = dict(is_real=bool(b.is_real), basis_np=tuple(b.np), idxmin1=b.idxmin[1], idxmax1=b.idxmax[1], ngw=ngw, nrods=nr,
+               rod_h=np.ctypeslib.as_array(b.rod_h, (nr,)).copy(), rod_k=np.ctypeslib.as_array(b.rod_k, (nr,)).copy(),
+               rod_lmin=np.ctypeslib.as_array(b.rod_lmin, (nr,)).copy(),
+               rod_size=np.ctypeslib.as_array(b.rod_size, (nr,)).copy(),
+               idx=np.ctypeslib.as_array(b.idx, (ngw, 3)).copy(), kpg2=np.ctypeslib.as_array(b.kpg2, (ngw,)).copy(),
+               kpgx=np.ctypeslib.as_array(b.kpgx, (3, ngw)).copy(), omega=b.omega)
+    L.qbo_basis_destroy(p)
+    return out
+
+
+def density_grid(cell, ecut):
+    g = np.zeros(3, dtype=np.int32)
+    lib().qbo_density_grid(_d(np.ascontiguousarray(cell, dtype=np.float64)), float(ecut), _i(g))
+    return tuple(int(x) for x in g)
+
+
+class FT:
+    """FourierTransform restatement bound to basis tables `b` (dict) and a grid."""
+
+    def __init__(self, b: dict, np0: int, np1: int, np2: int):
+        self.L = lib()
+        self.np0, self.np1, self.np2 = np0, np1, np2
+        self.N = np0 * np1 * np2
+        self.ngw = b["ngw"]
+        self.is_real = b["is_real"]
+        keep = [np.ascontiguousarray(b[k], dtype=np.int32) for k in ("rod_h", "rod_k", "rod_lmin", "rod_size")]
+        self.h = self.L.qbo_ft_create(np0, np1, np2, b["nrods"], *[_i(a) for a in keep], int(b["is_real"]),
+                                      int(b["idxmin1"]), int(b["idxmax1"]))
+        self.nvec = self.L.qbo_ft_nvec(self.h)
+        self.ntrans0 = self.L.qbo_ft_ntrans0(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.qbo_ft_destroy(self.h)
+            self.h = None
+
+    def backward(self, c, c2=None):
+        f = np.empty(self.N, dtype=np.complex128)
+        c = np.ascontiguousarray(c, dtype=np.complex128)
+        if c2 is None:
+            self.L.qbo_backward(self.h, _d(c), _d(f))
+        else:
+            c2 = np.ascontiguousarray(c2, dtype=np.complex128)
+            self.L.qbo_backward_pair(self.h, _d(c), _d(c2), _d(f))
+        return f
+
+    def forward(self, f, pair=False):
+        f = np.array(f, dtype=np.complex128, copy=True)
+        c1 = np.zeros(self.ngw, dtype=np.complex128)
+        if not pair:
+            self.L.qbo_forward(self.h, _d(f), _d(c1))
+            return c1
+        c2 = np.zeros(self.ngw, dtype=np.complex128)
+        self.L.qbo_forward_pair(self.h, _d(f), _d(c1), _d(c2))
+        return c1, c2
+
+    def rs_mul_add(self, c, v, cp):
+        """c, cp: (nst, ldc) complex128 C-contiguous; cp updated in place."""
+        nst, ldc = c.shape
+        assert cp.shape == c.shape and c.flags.c_contiguous and cp.flags.c_contiguous
+        self.L.qbo_rs_mul_add(self.h, self.ngw, ldc, nst, _d(c), _d(np.ascontiguousarray(v)), _d(cp))
+        return cp
+
+    def compute_density(self, c, fac, rho):
+        nst, ldc = c.shape
+        fac = np.ascontiguousarray(fac, dtype=np.float64)
+        self.L.qbo_compute_density(self.h, ldc, nst, _d(c), _d(fac), _d(rho))
+        return rho
+
+
+def kinetic_add(kpg2, c, cp):
+    nst, ldc = c.shape
+    lib().qbo_kinetic_add(kpg2.shape[0], ldc, nst, _d(np.ascontiguousarray(kpg2)), _d(c), _d(cp))
+    return cp
+
+
+def nl_energy(b: dict, c, occ, species, compute_hpsi=True, cp=None):
+    """NonLocalPotential::energy NC branch over all species; species = list of dict(na,npr,lproj,wt,twnl,tau)."""
+    nst, ldc = c.shape
+    if cp is None:
+        cp = np.zeros_like(c)
+    namax = max([s["na"] for s in species] + [0])
+    nab = 128 if namax > 128 else namax  # NonLocalPotential.cc:1537-1541
+    kpgx = np.ascontiguousarray(b["kpgx"], dtype=np.float64)
+    occ = np.ascontiguousarray(occ, dtype=np.float64)
+    enl = 0.0
+    for s in species:
+        if s["npr"] == 0 or s["na"] == 0:
+            continue
+        lproj = np.ascontiguousarray(s["lproj"], dtype=np.int32)
+        wt = np.ascontiguousarray(s["wt"], dtype=np.float64)
+        twnl = np.ascontiguousarray(s["twnl"], dtype=np.float64)
+        tau = np.ascontiguousarray(s["tau"], dtype=np.float64)
+        enl += lib().qbo_nl_energy_species(b["ngw"], ldc, nst, _d(c), _d(occ), int(b["is_real"]), s["na"], s["npr"],
+                                           _i(lproj), _d(wt), _d(twnl), _d(tau), _d(kpgx), float(b["omega"]), nab,
+                                           int(compute_hpsi), _d(cp))
+    return enl, cp
+
+
+def hpsi(b: dict, ft: FT, c, v, occ, species):
+    """Whole H psi in the reference's order: clear -> nonlocal -> kinetic -> local (EnergyFunctional.cc:1142-1701)."""
+    cp = np.zeros_like(c)
+    enl, _ = nl_energy(b, c, occ, species, True, cp)
+    kinetic_add(b["kpg2"], c, cp)
+    ft.rs_mul_add(c, v, cp)
+    return enl, cp

@@ -1,0 +1,552 @@
+/* oracle/qb_oracle.c -- TEST INFRASTRUCTURE ONLY (see qb_oracle.h).
+ *
+ * Plain-C restatement of the reference's per-state H psi / density path.  Each function cites the reference
+ * file:line it follows.  Parity is PINNED against the compiled reference (oracle/_ref) and tests/golden/.
+ * The 1-D FFT here is an independent textbook mixed-radix decimation-in-time DFT (the reference delegates to
+ * FFTW/ESSL or its built-in cfftm; only the transform's definition matters: sign, scaling, pruning).
+ */
+#include "qb_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------------------------------------ small vectors */
+typedef struct { double x, y, z; } v3;
+static v3 v3s(double a, v3 b) { v3 r = { b.x * a, b.y * a, b.z * a }; return r; }          /* a*b (D3vector *=)  */
+static v3 v3add(v3 a, v3 b) { v3 r = { a.x + b.x, a.y + b.y, a.z + b.z }; return r; }
+static v3 v3cross(v3 a, v3 b) { v3 r = { a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x }; return r; }
+static double v3dot(v3 a, v3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
+static double v3norm(v3 a) { return a.x*a.x + a.y*a.y + a.z*a.z; }                         /* math/d3vector.h:163 */
+static double v3len(v3 a) { return sqrt(a.x*a.x + a.y*a.y + a.z*a.z); }
+
+/* UnitCell::set (UnitCell.cc:37-94): volume, b_i = 2 pi (fac*a_j) ^ a_k */
+static double cell_recip(const double cell[9], v3 a[3], v3 b[3])
+{
+  for (int i = 0; i < 3; i++) { a[i].x = cell[3*i]; a[i].y = cell[3*i+1]; a[i].z = cell[3*i+2]; }
+  double vol = v3dot(a[0], v3cross(a[1], a[2]));
+  double fac = 1.0 / vol;
+  b[0] = v3s(2.0 * M_PI, v3cross(v3s(fac, a[1]), a[2]));
+  b[1] = v3s(2.0 * M_PI, v3cross(v3s(fac, a[2]), a[0]));
+  b[2] = v3s(2.0 * M_PI, v3cross(v3s(fac, a[0]), a[1]));
+  return vol;
+}
+
+/* ------------------------------------------------------------------------------------------------ Basis */
+int qbo_factorizable(int n)   /* Basis.cc:126-147 */
+{
+  if (n % 11 == 0) n /= 11;
+  if (n % 7 == 0) n /= 7;
+  if (n % 5 == 0) n /= 5;
+  if (n % 3 == 0) n /= 3;
+  if (n % 3 == 0) n /= 3;
+  while (n % 2 == 0) n /= 2;
+  return n == 1;
+}
+
+typedef struct { int h, k, lmin, size, seq; } rod_t;
+static int rod_cmp(const void* pa, const void* pb)
+{
+  /* multiset<Rod> ordered by size (Basis.cc:190-193); equal sizes keep insertion order */
+  const rod_t* a = (const rod_t*)pa; const rod_t* b = (const rod_t*)pb;
+  if (a->size != b->size) return a->size < b->size ? -1 : 1;
+  return a->seq < b->seq ? -1 : (a->seq > b->seq);
+}
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+qbo_basis* qbo_basis_create(const double cell[9], double ecut, const double kpoint[3], int force_complex)
+{
+  qbo_basis* B = (qbo_basis*)calloc(1, sizeof(qbo_basis));
+  v3 a[3], b[3];
+  B->omega = cell_recip(cell, a, b);
+  for (int i = 0; i < 3; i++) { B->b[3*i] = b[i].x; B->b[3*i+1] = b[i].y; B->b[3*i+2] = b[i].z; }
+  B->is_real = (kpoint[0] == 0.0 && kpoint[1] == 0.0 && kpoint[2] == 0.0 && !force_complex);  /* Basis.cc:284 */
+  const double two_ecut = 2.0 * ecut, twopi = 2.0 * M_PI;
+  const double kpx = kpoint[0], kpy = kpoint[1], kpz = kpoint[2];
+  const double b2inv2 = 1.0 / v3norm(b[2]);
+  const double fac = sqrt(two_ecut) / twopi;
+  const int hmax = (int)(0.5 + fac * v3len(a[0])), hmin = -hmax;           /* Basis.cc:397-404 */
+  const int kmax = (int)(0.5 + fac * v3len(a[1])), kmin = -kmax;
+  const int lmax = (int)(0.5 + fac * v3len(a[2])), lmin = -lmax;
+  int cap = (2*hmax + 4) * (2*kmax + 4) + 8, nr = 0;
+  rod_t* rods = (rod_t*)malloc(sizeof(rod_t) * cap);
+  int hmax_u = hmin, hmin_u = hmax, kmax_u = kmin, kmin_u = kmax, lmax_u = lmin, lmin_u = lmax;
+  if (B->is_real) {                                                        /* Basis.cc:417-496 */
+    int lend0 = (int)(sqrt(two_ecut * b2inv2));
+    rod_t r0 = { 0, 0, 0, lend0 + 1, nr }; rods[nr++] = r0;
+    hmax_u = hmin_u = kmin_u = kmax_u = lmin_u = 0; lmax_u = lend0;
+    for (int k = 1; k <= kmax + 1; k++) {
+      int lstart = lmax, lend = lmin, found = 0;
+      for (int l = lmin - 1; l <= lmax + 1; l++) {
+        double two_e = v3norm(v3add(v3s(k, b[1]), v3s(l, b[2])));
+        if (two_e < two_ecut) { lstart = imin(l, lstart); lend = imax(l, lend); found = 1; }
+      }
+      if (found) {
+        rod_t r = { 0, k, lstart, lend - lstart + 1, nr }; rods[nr++] = r;
+        kmax_u = imax(k, kmax_u); kmin_u = imin(k, kmin_u); lmax_u = imax(lend, lmax_u); lmin_u = imin(lstart, lmin_u);
+      }
+    }
+    for (int h = 1; h <= hmax + 1; h++)
+      for (int k = kmin - 1; k <= kmax + 1; k++) {
+        int lstart = lmax, lend = lmin, found = 0;
+        for (int l = lmin - 1; l <= lmax + 1; l++) {
+          double two_e = v3norm(v3add(v3add(v3s(h, b[0]), v3s(k, b[1])), v3s(l, b[2])));
+          if (two_e < two_ecut) { lstart = imin(l, lstart); lend = imax(l, lend); found = 1; }
+        }
+        if (found) {
+          rod_t r = { h, k, lstart, lend - lstart + 1, nr }; rods[nr++] = r;
+          hmax_u = imax(h, hmax_u); hmin_u = imin(h, hmin_u); kmax_u = imax(k, kmax_u); kmin_u = imin(k, kmin_u);
+          lmax_u = imax(lend, lmax_u); lmin_u = imin(lstart, lmin_u);
+        }
+      }
+  } else {                                                                 /* Basis.cc:497-536 */
+    for (int h = hmin - 1; h <= hmax + 1; h++)
+      for (int k = kmin - 1; k <= kmax + 1; k++) {
+        int lstart = lmax, lend = lmin, found = 0;
+        for (int l = lmin - 1; l <= lmax + 1; l++) {
+          double two_e = v3norm(v3add(v3add(v3s(kpx + h, b[0]), v3s(kpy + k, b[1])), v3s(kpz + l, b[2])));
+          if (two_e < two_ecut) { lstart = imin(l, lstart); lend = imax(l, lend); found = 1; }
+        }
+        if (found) {
+          rod_t r = { h, k, lstart, lend - lstart + 1, nr }; rods[nr++] = r;
+          hmax_u = imax(h, hmax_u); hmin_u = imin(h, hmin_u); kmax_u = imax(k, kmax_u); kmin_u = imin(k, kmin_u);
+          lmax_u = imax(lend, lmax_u); lmin_u = imin(lstart, lmin_u);
+        }
+      }
+  }
+  B->idxmax[0] = hmax_u; B->idxmin[0] = hmin_u; B->idxmax[1] = kmax_u; B->idxmin[1] = kmin_u;
+  B->idxmax[2] = lmax_u; B->idxmin[2] = lmin_u;
+  int n;                                                                   /* Basis.cc:563-574 */
+  n = 2*hmax + 2; while (!qbo_factorizable(n)) n += 2; B->np[0] = n;
+  n = 2*kmax + 2; while (!qbo_factorizable(n)) n += 2; B->np[1] = n;
+  n = 2*lmax + 2; while (!qbo_factorizable(n)) n += 2; B->np[2] = n;
+
+  /* one process row: rods in multiset order, then rod(0,0) swapped into slot 0 (Basis.cc:595-651) */
+  qsort(rods, nr, sizeof(rod_t), rod_cmp);
+  int rank0 = -1;
+  for (int i = 0; i < nr; i++) if (rods[i].h == 0 && rods[i].k == 0) rank0 = i;
+  if (rank0 > 0) { rod_t t = rods[0]; rods[0] = rods[rank0]; rods[rank0] = t; }
+  B->nrods = nr;
+  B->rod_h = (int*)malloc(sizeof(int) * nr); B->rod_k = (int*)malloc(sizeof(int) * nr);
+  B->rod_lmin = (int*)malloc(sizeof(int) * nr); B->rod_size = (int*)malloc(sizeof(int) * nr);
+  B->rod_first = (int*)malloc(sizeof(int) * nr);
+  int ngw = 0;
+  for (int i = 0; i < nr; i++) {
+    B->rod_h[i] = rods[i].h; B->rod_k[i] = rods[i].k; B->rod_lmin[i] = rods[i].lmin; B->rod_size[i] = rods[i].size;
+    B->rod_first[i] = ngw; ngw += rods[i].size;
+  }
+  free(rods);
+  B->ngw = ngw;
+  B->idx = (int*)malloc(sizeof(int) * 3 * (size_t)ngw);
+  B->kpg2 = (double*)malloc(sizeof(double) * (size_t)ngw);
+  B->kpgx = (double*)malloc(sizeof(double) * 3 * (size_t)ngw);
+  int i = 0;
+  for (int irod = 0; irod < nr; irod++)
+    for (int l = 0; l < B->rod_size[irod]; l++, i++) {
+      B->idx[3*i] = B->rod_h[irod]; B->idx[3*i+1] = B->rod_k[irod]; B->idx[3*i+2] = B->rod_lmin[irod] + l;
+    }
+  for (i = 0; i < ngw; i++) {                                              /* Basis::update_g, Basis.cc:703-741 */
+    v3 kpgt = v3add(v3add(v3s(kpx + B->idx[3*i], b[0]), v3s(kpy + B->idx[3*i+1], b[1])), v3s(kpz + B->idx[3*i+2], b[2]));
+    B->kpgx[i] = kpgt.x; B->kpgx[ngw + i] = kpgt.y; B->kpgx[2*(size_t)ngw + i] = kpgt.z;
+    B->kpg2[i] = v3norm(kpgt);
+  }
+  return B;
+}
+
+void qbo_basis_destroy(qbo_basis* B)
+{
+  if (!B) return;
+  free(B->rod_h); free(B->rod_k); free(B->rod_lmin); free(B->rod_size); free(B->rod_first);
+  free(B->idx); free(B->kpg2); free(B->kpgx); free(B);
+}
+
+void qbo_density_grid(const double cell[9], double ecut, int grid[3])   /* ChargeDensity.cc:77-99 */
+{
+  /* only np of the Gamma basis at 4*ecut is needed, which depends on hmax/kmax/lmax alone (Basis.cc:394-404,563-574) */
+  v3 a[3], b[3];
+  cell_recip(cell, a, b);
+  const double fac = sqrt(2.0 * 4.0 * ecut) / (2.0 * M_PI);
+  for (int d = 0; d < 3; d++) {
+    int m = (int)(0.5 + fac * v3len(a[d]));
+    int n = 2*m + 2; while (!qbo_factorizable(n)) n += 2;
+    n += 2; while (!qbo_factorizable(n)) n += 2;
+    grid[d] = n;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ 1-D FFT */
+typedef struct { int n; double* w; /* w[2k],w[2k+1] = cos,sin(2 pi k/n) */ } fftplan;
+
+static void fftplan_init(fftplan* p, int n)
+{
+  p->n = n; p->w = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+  for (int k = 0; k < n; k++) {
+    long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+    p->w[2*k] = (double)cosl(ang); p->w[2*k+1] = (double)sinl(ang);
+  }
+}
+static int smallest_factor(int n) { for (int p = 2; p * p <= n; p++) if (n % p == 0) return p; return n; }
+
+/* out[k] = sum_j in[j*is] * exp(sign * 2 pi i jk / n), recursive mixed radix; N = plan length, n divides N */
+static void fft_rec(const fftplan* P, int n, int sign, const double* in, int is, double* out)
+{
+  if (n == 1) { out[0] = in[0]; out[1] = in[1]; return; }
+  const int p = smallest_factor(n), m = n / p, N = P->n, tstride = N / n;
+  for (int r = 0; r < p; r++) fft_rec(P, m, sign, in + 2 * (size_t)r * is, is * p, out + 2 * (size_t)r * m);
+  double tr[16], ti[16];
+  double *tre = tr, *tim = ti;
+  if (p > 16) { tre = (double*)malloc(sizeof(double) * 2 * p); tim = tre + p; }
+  for (int k = 0; k < m; k++) {
+    for (int r = 0; r < p; r++) { tre[r] = out[2*(r*m + k)]; tim[r] = out[2*(r*m + k) + 1]; }
+    for (int q = 0; q < p; q++) {
+      const int kk = k + q * m;
+      double sr = 0.0, si = 0.0;
+      for (int r = 0; r < p; r++) {
+        const int e = (int)(((long long)r * kk) % n) * tstride;
+        const double wr = P->w[2*e], wi = sign > 0 ? P->w[2*e+1] : -P->w[2*e+1];
+        sr += tre[r] * wr - tim[r] * wi;
+        si += tre[r] * wi + tim[r] * wr;
+      }
+      out[2*kk] = sr; out[2*kk+1] = si;
+    }
+  }
+  if (p > 16) free(tre);
+}
+
+/* in-place strided transform of one line: data[j*stride], j<n */
+static void fft_line(const fftplan* P, int sign, double* data, int stride, double* tmp)
+{
+  fft_rec(P, P->n, sign, data, stride, tmp);
+  for (int j = 0; j < P->n; j++) { data[2*(size_t)j*stride] = tmp[2*j]; data[2*(size_t)j*stride+1] = tmp[2*j+1]; }
+}
+
+/* ------------------------------------------------------------------------------------------------ FourierTransform */
+struct qbo_ft {
+  int np0, np1, np2, nvec, ntrans0, ngw, is_real;
+  int *ifftp, *ifftm;      /* sphere -> zvec index (FourierTransform.cc:262-331, 437-454) */
+  int *colxy;              /* column ivec -> hp + np0*kp (the l=0 entry of iunpack_, :361-430, :484-506) */
+  double* zvec;            /* nvec*np2 complex */
+  fftplan P0, P1, P2;
+};
+
+qbo_ft* qbo_ft_create(int np0, int np1, int np2, int nrods, const int* rod_h, const int* rod_k, const int* rod_lmin,
+                      const int* rod_size, int is_real, int idxmin1, int idxmax1)
+{
+  qbo_ft* ft = (qbo_ft*)calloc(1, sizeof(qbo_ft));
+  ft->np0 = np0; ft->np1 = np1; ft->np2 = np2; ft->is_real = is_real;
+  ft->nvec = is_real ? 2 * nrods - 1 : nrods;                                        /* :186-197 */
+  ft->ntrans0 = imax(abs(idxmax1), abs(idxmin1)) + 1;                                /* :202 */
+  int ngw = 0; for (int i = 0; i < nrods; i++) ngw += rod_size[i];
+  ft->ngw = ngw;
+  ft->ifftp = (int*)malloc(sizeof(int) * (size_t)(ngw > 0 ? ngw : 1));
+  ft->ifftm = (int*)malloc(sizeof(int) * (size_t)(ngw > 0 ? ngw : 1));
+  ft->colxy = (int*)malloc(sizeof(int) * (size_t)(ft->nvec > 0 ? ft->nvec : 1));
+  ft->zvec = (double*)malloc(sizeof(double) * 2 * (size_t)ft->nvec * np2 + 16);
+  int ig = 0;
+  if (is_real) {
+    ft->ifftp[0] = 0; ft->ifftm[0] = 0; ig = 1;                                      /* :277-286 */
+    for (int l = 1; l < rod_size[0]; l++, ig++) { ft->ifftp[ig] = l; ft->ifftm[ig] = np2 - l; }
+    ft->colxy[0] = 0;
+    for (int irod = 1; irod < nrods; irod++) {                                       /* :291-305, :372-398 */
+      for (int i = 0; i < rod_size[irod]; i++, ig++) {
+        const int l = i + rod_lmin[irod];
+        int izp = l, izm = -l;
+        if (izp < 0) izp += np2;
+        if (izm < 0) izm += np2;
+        ft->ifftp[ig] = (2*irod - 1) * np2 + izp;
+        ft->ifftm[ig] = (2*irod) * np2 + izm;
+      }
+      int hp = rod_h[irod], kp = rod_k[irod];
+      if (hp < 0) hp += np0;
+      if (kp < 0) kp += np1;
+      int hm = -hp, km = -kp;
+      if (hm < 0) hm += np0;
+      if (km < 0) km += np1;
+      ft->colxy[2*irod - 1] = hp + np0 * kp;
+      ft->colxy[2*irod] = hm + np0 * km;
+    }
+  } else {
+    for (int irod = 0; irod < nrods; irod++) {                                       /* :441-453, :486-506 */
+      for (int i = 0; i < rod_size[irod]; i++, ig++) {
+        int iz = i + rod_lmin[irod];
+        if (iz < 0) iz += np2;
+        ft->ifftp[ig] = irod * np2 + iz;
+      }
+      int h = rod_h[irod], k = rod_k[irod];
+      if (h < 0) h += np0;
+      if (k < 0) k += np1;
+      ft->colxy[irod] = h + np0 * k;
+    }
+  }
+  fftplan_init(&ft->P0, np0); fftplan_init(&ft->P1, np1); fftplan_init(&ft->P2, np2);
+  return ft;
+}
+
+void qbo_ft_destroy(qbo_ft* ft)
+{
+  if (!ft) return;
+  free(ft->ifftp); free(ft->ifftm); free(ft->colxy); free(ft->zvec); free(ft->P0.w); free(ft->P1.w); free(ft->P2.w); free(ft);
+}
+int qbo_ft_nvec(const qbo_ft* ft) { return ft->nvec; }
+int qbo_ft_ntrans0(const qbo_ft* ft) { return ft->ntrans0; }
+
+/* FourierTransform::bwd (FourierTransform.cc:584-980), one rank: z-FFT (+1), zero val, scatter columns, x-FFTs on the
+ * rows j in [0,ntrans0) U [np1-ntrans0,np1), y-FFTs on every column; no scaling. */
+static void bwd(qbo_ft* ft, double* val)
+{
+  const int np0 = ft->np0, np1 = ft->np1, np2 = ft->np2, nvec = ft->nvec;
+  const size_t np01 = (size_t)np0 * np1;
+  #pragma omp parallel
+  {
+    double* tmp = (double*)malloc(sizeof(double) * 2 * (size_t)imax(np0, imax(np1, np2)));
+    #pragma omp for
+    for (int iv = 0; iv < nvec; iv++) fft_line(&ft->P2, +1, ft->zvec + 2 * (size_t)iv * np2, 1, tmp);
+    #pragma omp for
+    for (int k = 0; k < np2; k++) {
+      double* pl = val + 2 * np01 * k;
+      memset(pl, 0, sizeof(double) * 2 * np01);
+      for (int iv = 0; iv < nvec; iv++) {
+        pl[2*ft->colxy[iv]] = ft->zvec[2*((size_t)iv*np2 + k)];
+        pl[2*ft->colxy[iv]+1] = ft->zvec[2*((size_t)iv*np2 + k)+1];
+      }
+      int nlo = ft->ntrans0 < np1 ? ft->ntrans0 : np1;
+      for (int j = 0; j < np1; j++)
+        if (j < nlo || j >= np1 - ft->ntrans0) fft_line(&ft->P0, +1, pl + 2 * (size_t)j * np0, 1, tmp);
+      for (int i = 0; i < np0; i++) fft_line(&ft->P1, +1, pl + 2 * i, np0, tmp);
+    }
+    free(tmp);
+  }
+}
+
+/* FourierTransform::fwd (FourierTransform.cc:983-1361): y-FFTs (-1), x-FFTs on the kept rows, gather columns,
+ * z-FFT (-1), scale 1/(np0*np1*np2) (:1338-1342). val is clobbered, as in the reference. */
+static void fwd(qbo_ft* ft, double* val)
+{
+  const int np0 = ft->np0, np1 = ft->np1, np2 = ft->np2, nvec = ft->nvec;
+  const size_t np01 = (size_t)np0 * np1;
+  const double fac = 1.0 / ((double)np0 * np1 * np2);
+  #pragma omp parallel
+  {
+    double* tmp = (double*)malloc(sizeof(double) * 2 * (size_t)imax(np0, imax(np1, np2)));
+    #pragma omp for
+    for (int k = 0; k < np2; k++) {
+      double* pl = val + 2 * np01 * k;
+      for (int i = 0; i < np0; i++) fft_line(&ft->P1, -1, pl + 2 * i, np0, tmp);
+      int nlo = ft->ntrans0 < np1 ? ft->ntrans0 : np1;
+      for (int j = 0; j < np1; j++)
+        if (j < nlo || j >= np1 - ft->ntrans0) fft_line(&ft->P0, -1, pl + 2 * (size_t)j * np0, 1, tmp);
+      for (int iv = 0; iv < nvec; iv++) {
+        ft->zvec[2*((size_t)iv*np2 + k)] = pl[2*ft->colxy[iv]];
+        ft->zvec[2*((size_t)iv*np2 + k)+1] = pl[2*ft->colxy[iv]+1];
+      }
+    }
+    #pragma omp for
+    for (int iv = 0; iv < nvec; iv++) {
+      double* col = ft->zvec + 2 * (size_t)iv * np2;
+      fft_line(&ft->P2, -1, col, 1, tmp);
+      for (int k = 0; k < 2 * np2; k++) col[k] *= fac;
+    }
+    free(tmp);
+  }
+}
+
+void qbo_backward(qbo_ft* ft, const double* c, double* f)
+{
+  /* vector_to_zvec (FourierTransform.cc:1624-1664) */
+  double* pz = ft->zvec;
+  memset(pz, 0, sizeof(double) * 2 * (size_t)ft->nvec * ft->np2);
+  for (int ig = 0; ig < ft->ngw; ig++) {
+    const double a = c[2*ig], b = c[2*ig+1];
+    const int ip = ft->ifftp[ig];
+    pz[2*ip] = a; pz[2*ip+1] = b;
+    if (ft->is_real) { const int im = ft->ifftm[ig]; pz[2*im] = a; pz[2*im+1] = -b; }
+  }
+  bwd(ft, f);
+}
+
+void qbo_forward(qbo_ft* ft, double* f, double* c)
+{
+  fwd(ft, f);
+  for (int ig = 0; ig < ft->ngw; ig++) {            /* zvec_to_vector (:1666-1681) */
+    const int ip = ft->ifftp[ig];
+    c[2*ig] = ft->zvec[2*ip]; c[2*ig+1] = ft->zvec[2*ip+1];
+  }
+}
+
+void qbo_backward_pair(qbo_ft* ft, const double* c1, const double* c2, double* f)
+{
+  /* doublevector_to_zvec (:1684-1720) */
+  double* pz = ft->zvec;
+  memset(pz, 0, sizeof(double) * 2 * (size_t)ft->nvec * ft->np2);
+  for (int ig = 0; ig < ft->ngw; ig++) {
+    const double a = c1[2*ig], b = c1[2*ig+1], c = c2[2*ig], d = c2[2*ig+1];
+    const int ip = ft->ifftp[ig], im = ft->ifftm[ig];
+    pz[2*ip] = a - d; pz[2*ip+1] = b + c;
+    pz[2*im] = a + d; pz[2*im+1] = c - b;
+  }
+  bwd(ft, f);
+}
+
+void qbo_forward_pair(qbo_ft* ft, double* f, double* c1, double* c2)
+{
+  fwd(ft, f);
+  const double* pz = ft->zvec;                       /* zvec_to_doublevector (:1723-1752) */
+  for (int ig = 0; ig < ft->ngw; ig++) {
+    const int ip = ft->ifftp[ig], im = ft->ifftm[ig];
+    const double a = pz[2*ip], b = pz[2*ip+1], c = pz[2*im], d = pz[2*im+1];
+    c1[2*ig] = 0.5 * (a + c); c1[2*ig+1] = 0.5 * (b - d);
+    c2[2*ig] = 0.5 * (b + d); c2[2*ig+1] = 0.5 * (c - a);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ SlaterDet */
+void qbo_rs_mul_add(qbo_ft* ft, int ngw, int ldc, int nst, const double* c, const double* v, double* cp)
+{
+  /* SlaterDet.cc:971-1040.  ctmp has mloc entries of which only ngw are written by forward(); the reference's
+   * daxpy/zaxpy over mloc adds ctmp's zero-initialised padding, i.e. nothing. */
+  const size_t N = (size_t)ft->np0 * ft->np1 * ft->np2;
+  double* tmp = (double*)malloc(sizeof(double) * 2 * N);
+  double* ct = (double*)calloc(4 * (size_t)ldc, sizeof(double));
+  if (ft->is_real) {
+    int n;
+    for (n = 0; n < nst - 1; n += 2) {
+      qbo_backward_pair(ft, c + 2*(size_t)n*ldc, c + 2*(size_t)(n+1)*ldc, tmp);
+      for (size_t i = 0; i < N; i++) { const double vi = v[i]; tmp[2*i] = vi * tmp[2*i]; tmp[2*i+1] = vi * tmp[2*i+1]; }
+      qbo_forward_pair(ft, tmp, ct, ct + 2*(size_t)ldc);
+      for (int ig = 0; ig < 2*ngw; ig++) { cp[2*(size_t)n*ldc + ig] += ct[ig]; cp[2*(size_t)(n+1)*ldc + ig] += ct[2*(size_t)ldc + ig]; }
+    }
+    if (nst % 2 != 0) {
+      n = nst - 1;
+      qbo_backward(ft, c + 2*(size_t)n*ldc, tmp);
+      for (size_t i = 0; i < N; i++) { tmp[2*i] = v[i] * tmp[2*i]; tmp[2*i+1] = 0.0; }
+      qbo_forward(ft, tmp, ct);
+      for (int ig = 0; ig < 2*ngw; ig++) cp[2*(size_t)n*ldc + ig] += ct[ig];
+    }
+  } else {
+    for (int n = 0; n < nst; n++) {
+      qbo_backward(ft, c + 2*(size_t)n*ldc, tmp);
+      for (size_t i = 0; i < N; i++) { const double vi = v[i]; tmp[2*i] *= vi; tmp[2*i+1] *= vi; }
+      qbo_forward(ft, tmp, ct);
+      for (int ig = 0; ig < 2*ngw; ig++) cp[2*(size_t)n*ldc + ig] += ct[ig];
+    }
+  }
+  free(tmp); free(ct);
+}
+
+void qbo_compute_density(qbo_ft* ft, int ldc, int nst, const double* c, const double* fac, double* rho)
+{
+  /* SlaterDet.cc:905-926 (the pair branch is disabled in the reference, :858) */
+  const size_t N = (size_t)ft->np0 * ft->np1 * ft->np2;
+  double* tmp = (double*)malloc(sizeof(double) * 2 * N);
+  for (int n = 0; n < nst; n++) {
+    if (fac[n] > 0.0) {
+      qbo_backward(ft, c + 2*(size_t)n*ldc, tmp);
+      const double f = fac[n];
+      for (size_t i = 0; i < N; i++) rho[i] += f * (tmp[2*i]*tmp[2*i] + tmp[2*i+1]*tmp[2*i+1]);
+    }
+  }
+  free(tmp);
+}
+
+void qbo_kinetic_add(int ngw, int ldc, int nst, const double* kpg2, const double* c, double* cp)
+{
+  for (int n = 0; n < nst; n++)                       /* EnergyFunctional.cc:1675-1677 */
+    for (int ig = 0; ig < ngw; ig++) {
+      const double h = 0.5 * kpg2[ig];
+      cp[2*((size_t)n*ldc + ig)] += h * c[2*((size_t)n*ldc + ig)];
+      cp[2*((size_t)n*ldc + ig)+1] += h * c[2*((size_t)n*ldc + ig)+1];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ NonLocalPotential */
+double qbo_nl_energy_species(int ngw, int ldc, int nst, const double* c, const double* occ, int is_real, int na, int npr,
+                             const int* lproj, const double* wt, const double* twnl, const double* tau,
+                             const double* kpgx, double omega, int na_block_size, int compute_hpsi, double* cp)
+{
+  if (npr <= 0 || na <= 0) return 0.0;
+  const double omega_inv = 1.0 / omega;
+  double enl = 0.0;
+  const int na_blocks = na / na_block_size + (na % na_block_size == 0 ? 0 : 1);      /* :1920-1921 */
+  double* anl = (double*)malloc(sizeof(double) * 2 * (size_t)npr * na_block_size * ngw);
+  double* fnl = (double*)malloc(sizeof(double) * 2 * (size_t)npr * na_block_size * nst);
+  for (int ib = 0; ib < na_blocks; ib++) {
+    const int iastart = ib * na_block_size;
+    const int iaend = (ib + 1) * na_block_size < na ? (ib + 1) * na_block_size : na;
+    const int nab = iaend - iastart;
+    const int nprnaloc = nab * npr;
+    /* anl[ig + (ia + ipr*nab)*ngw] = twnl * (-i)^l * exp(i*kpgr), kpgr = -(k+G).tau  (:1959-2036) */
+    #pragma omp parallel for collapse(2)
+    for (int ipr = 0; ipr < npr; ipr++)
+      for (int ia = 0; ia < nab; ia++) {
+        const double* t = twnl + (size_t)ngw * ipr;
+        const int l = lproj[ipr];
+        const double* tu = tau + 3 * (size_t)(iastart + ia);
+        double* a = anl + 2 * (size_t)(ia + ipr * nab) * ngw;
+        for (int ig = 0; ig < ngw; ig++) {
+          /* dgemm with alpha=-1 over k=3 (:1969): -(x*tx + y*ty + z*tz) */
+          const double arg = -(kpgx[ig] * tu[0] + kpgx[ngw + ig] * tu[1] + kpgx[2*(size_t)ngw + ig] * tu[2]);
+          const double s = sin(arg), co = cos(arg);
+          if (l == 0) { a[2*ig] = t[ig] * co; a[2*ig+1] = t[ig] * s; }
+          else if (l == 1) { a[2*ig] = t[ig] * s; a[2*ig+1] = -t[ig] * co; }
+          else if (l == 2) { a[2*ig] = -t[ig] * co; a[2*ig+1] = -t[ig] * s; }
+          else { a[2*ig] = -t[ig] * s; a[2*ig+1] = t[ig] * co; }
+        }
+      }
+    /* fnl = anl^H c  (complex, :2064)  or  anl^T c over 2*ngw reals (Gamma, :2053) */
+    #pragma omp parallel for collapse(2)
+    for (int n = 0; n < nst; n++)
+      for (int p = 0; p < nprnaloc; p++) {
+        const double* a = anl + 2 * (size_t)p * ngw;
+        const double* cn = c + 2 * (size_t)n * ldc;
+        double* f = fnl + 2 * ((size_t)p + (size_t)n * nprnaloc);
+        if (is_real) {
+          double s = 0.0;
+          for (int ig = 0; ig < 2*ngw; ig++) s += a[ig] * cn[ig];
+          s += -0.5 * a[0] * cn[0];                 /* dger G=0 double-count fix (:2078-2080) */
+          f[0] = 2.0 * s; f[1] = 0.0;               /* factor 2: G and -G (:2102) */
+        } else {
+          double sr = 0.0, si = 0.0;                /* conj(a)*c */
+          for (int ig = 0; ig < ngw; ig++) {
+            sr += a[2*ig] * cn[2*ig] + a[2*ig+1] * cn[2*ig+1];
+            si += a[2*ig] * cn[2*ig+1] - a[2*ig+1] * cn[2*ig];
+          }
+          f[0] = sr; f[1] = si;
+        }
+      }
+    /* enl and fnl <- wt/omega * fnl (:2106-2148) */
+    for (int ipr = 0; ipr < npr; ipr++) {
+      const double fac = wt[ipr] * omega_inv;
+      for (int n = 0; n < nst; n++) {
+        const double facn = fac * occ[n];
+        for (int ia = 0; ia < nab; ia++) {
+          double* f = fnl + 2 * ((size_t)(ia + ipr * nab) + (size_t)n * nprnaloc);
+          enl += facn * (f[0]*f[0] + f[1]*f[1]);
+          f[0] *= fac; f[1] *= fac;
+        }
+      }
+    }
+    if (compute_hpsi) {                              /* cp += anl * fnl (:2150-2171) */
+      #pragma omp parallel for
+      for (int n = 0; n < nst; n++) {
+        double* cpn = cp + 2 * (size_t)n * ldc;
+        for (int p = 0; p < nprnaloc; p++) {
+          const double* a = anl + 2 * (size_t)p * ngw;
+          const double fr = fnl[2*((size_t)p + (size_t)n*nprnaloc)], fi = fnl[2*((size_t)p + (size_t)n*nprnaloc)+1];
+          if (is_real) { for (int ig = 0; ig < 2*ngw; ig++) cpn[ig] += a[ig] * fr; }
+          else for (int ig = 0; ig < ngw; ig++) {
+            cpn[2*ig] += a[2*ig] * fr - a[2*ig+1] * fi;
+            cpn[2*ig+1] += a[2*ig] * fi + a[2*ig+1] * fr;
+          }
+        }
+      }
+    }
+  }
+  free(anl); free(fnl);
+  return enl;
+}
