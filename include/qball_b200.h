@@ -1,0 +1,107 @@
+/* include/qball_b200.h -- C ABI of libqball_b200.so: Qball's per-state plane-wave H psi / density hot path on B200.
+ *
+ * This is the drop-in boundary.  The reference (LLNL/qball, C++) has no plugin/FFI interface
+ * for this path; the seam is the member functions listed beside each entry point below, which keep their signatures
+ * and forward here (see INTEGRATION.md for the ~10-line shim in each reference class).  Plain pointers and sizes only.
+ *
+ * Conventions (identical to the reference):
+ *   - complex numbers are interleaved (re,im) doubles, i.e. std::complex<double>*.
+ *   - grids are x-fastest: index(i,j,k) = i + np0*(j + np1*k)          (src/qball/FourierTransform.h:165)
+ *   - coefficient blocks are column-major ldc x nst with ldc = ComplexMatrix::mloc() >= ngw; rows ig >= ngw are
+ *     padding, never read or written here                              (src/qball/SlaterDet.cc:2784-2787)
+ *   - backward = sum_G c_G e^{+iGr}, unscaled; forward = (1/N) sum_r f e^{-iGr}  (FourierTransform.cc:1338-1342,1516-1612)
+ *   - every data pointer may be a HOST pointer or a DEVICE pointer on the plan's device (detected with
+ *     cudaPointerGetAttributes); host data is staged through device buffers owned by the plan, device data is used in
+ *     place.  Host scalars/small tables (rod tables, occupations, fac) are always host pointers.
+ *   - one handle per (spin, k-point) per rank, single-threaded callers per handle, one rank <-> one GPU
+ *     (the reference's FourierTransform is stateful and not re-entrant either, FourierTransform.h:87-91).
+ *   - errors: the reference aborts (assert / MPI_Abort, FourierTransform.cc:696-700); here every call returns 0 on
+ *     success or a negative QB200_E* code and qb200_last_error() describes it; the C++ shim turns non-zero into
+ *     message + abort.  There is NO CPU fallback: without a CUDA device every compute call fails with QB200_ENODEV.
+ */
+#ifndef QBALL_B200_H
+#define QBALL_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_OK 0
+#define QB200_EINVAL (-1)   /* bad argument                                   */
+#define QB200_ENODEV (-2)   /* no usable CUDA device / kernel image           */
+#define QB200_ECUDA (-3)    /* CUDA runtime error (see qb200_last_error)      */
+#define QB200_ENOMEM (-4)   /* device allocation failed                       */
+#define QB200_EUNSUPPORTED (-5) /* shape outside what the kernels support     */
+
+typedef struct qb200_plan qb200_plan;
+
+const char* qb200_last_error(void);
+const char* qb200_version(void);
+/* number of CUDA devices visible (0 if none / no driver); never fails */
+int qb200_device_count(void);
+
+/* ---- plan: replaces FourierTransform::FourierTransform(const Basis&, np0, np1, np2)
+ *      (src/qball/FourierTransform.cc:144-526) for one rank (nprow = 1): builds the sphere<->column maps
+ *      (ifftp_/ifftm_/iunpack_), ntrans0 and the FFT tables on the device.
+ *      rod_* = Basis::rod_h/rod_k/rod_lmin/rod_size(irod), irod < nrods = Basis::nrod_loc()  (Basis.h:88-156)
+ *      is_real = Basis::real(); idxmin1/idxmax1 = Basis::idxmin(1)/idxmax(1) (for ntrans0, FourierTransform.cc:202). */
+int qb200_plan_create(qb200_plan** plan, int device, int np0, int np1, int np2, int nrods, const int* rod_h,
+                      const int* rod_k, const int* rod_lmin, const int* rod_size, int is_real, int idxmin1, int idxmax1);
+int qb200_plan_destroy(qb200_plan* plan);
+/* work on this CUDA stream (cudaStream_t as void*); default is the legacy default stream */
+int qb200_plan_set_stream(qb200_plan* plan, void* cuda_stream);
+/* bytes of device scratch for the column-form intermediate (default 96 MiB); bounds the number of states per batch */
+int qb200_plan_set_workspace(qb200_plan* plan, long long bytes);
+/* queries: 0 np0, 1 np1, 2 np2, 3 nvec, 4 ntrans0, 5 ngw, 6 is_real, 7 plane-fused path in use (1) or split path (0),
+ *          8 states per batch, 9 kernels launched since creation (for bench gpu_launches) */
+long long qb200_plan_query(const qb200_plan* plan, int what);
+
+/* ---- FourierTransform::backward(const complex<double>* c, complex<double>* f)       FourierTransform.cc:529-539
+ *      FourierTransform::forward(complex<double>* f, complex<double>* c)              FourierTransform.cc:542-552
+ *      pair forms (Gamma-point two real functions per complex FFT; require is_real)   FourierTransform.cc:555-581
+ *      c: ngw complex, f: np0*np1*np2 complex.  forward leaves f unspecified (the reference clobbers it too). */
+int qb200_fft_backward(qb200_plan* plan, const double* c, double* f);
+int qb200_fft_forward(qb200_plan* plan, double* f, double* c);
+int qb200_fft_backward_pair(qb200_plan* plan, const double* c1, const double* c2, double* f);
+int qb200_fft_forward_pair(qb200_plan* plan, double* f, double* c1, double* c2);
+
+/* ---- SlaterDet::rs_mul_add(FourierTransform& ft, const double* v, SlaterDet& sdp)   SlaterDet.cc:971-1040
+ *      cp[:,n] += FT[ v(r) * FT^-1[ c[:,n] ] ] for n < nst; real bases go by local pairs (n,n+1) + odd tail.
+ *      kpg2 (ngw doubles, Basis::kpg2_ptr(); may be NULL) fuses the kinetic term of EnergyFunctional::energy,
+ *      cp[ig,n] += 0.5*kpg2[ig]*c[ig,n]  (EnergyFunctional.cc:1675-1690; pass kpg2+fstress for confinement :1661-1668). */
+int qb200_rs_mul_add(qb200_plan* plan, int ldc, int nst, const double* c, const double* v, const double* kpg2,
+                     double* cp);
+
+/* ---- SlaterDet::compute_density(FourierTransform& ft, double weight, double* rho)   SlaterDet.cc:839-932
+ *      rho[i] += fac[n]*|psi_n(r_i)|^2 for every n with fac[n] > 0, fac[n] = weight*occ[n]/omega (host array).
+ *      Deterministic: fixed summation order for a given (plan, nst). */
+int qb200_compute_density(qb200_plan* plan, int ldc, int nst, const double* c, const double* fac, double* rho);
+
+/* ---- NonLocalPotential::energy, norm-conserving branch                 NonLocalPotential.cc:1909-2171, 2628-2643
+ *      Projector tables are the outputs of the reference's host setup (NonLocalPotential::init/update_twnl,
+ *      NonLocalPotential.cc:76-1522) and AtomSet::get_positions.  One qb200_nl per NonLocalPotential object. */
+typedef struct qb200_nl qb200_nl;
+int qb200_nl_create(qb200_nl** nl, int device, int ngw, int is_real, double omega, const double* kpgx /* 3*ngw */);
+/* add species: na atoms, npr projectors, lproj[npr], wt[npr], twnl[npr*ngw] (twnl[is][ipr*ngw+ig]), tau[3*na] */
+int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const double* wt, const double* twnl,
+                         const double* tau);
+/* atoms moved: new positions for species is (AtomSet::get_positions order) */
+int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau);
+int qb200_nl_set_stream(qb200_nl* nl, void* cuda_stream);
+int qb200_nl_destroy(qb200_nl* nl);
+/* enl = sum_{n,I,p} occ[n]*wt_p/omega*|F_{Ip,n}|^2 ; if compute_hpsi: cp += anl * (wt/omega * F).
+ * occ: host array of the nst LOCAL states' occupations (occ[c.j(lj,jj)] in the reference, NonLocalPotential.cc:2115).
+ * The row-sum of enl over G-row ranks (NonLocalPotential.cc:2629) is the identity with nprow = 1. */
+int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, int compute_hpsi, double* cp,
+                    double* enl);
+long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched */
+
+/* ---- the whole H psi column block in the reference's order (EnergyFunctional.cc:1142-1153, 1500, 1675-1695):
+ *      hpsi = 0 ; hpsi += V_nl psi ; hpsi += 0.5|k+G|^2 psi ; hpsi += FT[v FT^-1 psi].  nl may be NULL (no projectors).
+ *      hpsi is OUTPUT only (ldc x nst); enl may be NULL. */
+int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,
+               const double* kpg2, double* hpsi, double* enl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+"""ctypes binding of libqball_b200.so (include/qball_b200.h).
+
+Arrays may be numpy arrays (host pointers) or CUDA torch tensors (device pointers, used in place); the C ABI tells
+them apart itself.  The library is required: if it cannot be loaded this module raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+
+class QB200Error(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise QB200Error(f"{path} is missing: run `python -m qball_b200.build` (or __graft_entry__.build()); "
+                         "the CUDA library is the product, there is no fallback")
+    L = C.CDLL(path)
+    vp, ip, dp, i, ll, d = C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_longlong, C.c_double
+    L.qb200_last_error.restype = C.c_char_p
+    L.qb200_version.restype = C.c_char_p
+    L.qb200_device_count.restype = i
+    L.qb200_plan_create.argtypes = [C.POINTER(vp), i, i, i, i, i, ip, ip, ip, ip, i, i, i]
+    L.qb200_plan_destroy.argtypes = [vp]
+    L.qb200_plan_set_stream.argtypes = [vp, vp]
+    L.qb200_plan_set_workspace.argtypes = [vp, ll]
+    L.qb200_plan_query.argtypes = [vp, i]
+    L.qb200_plan_query.restype = ll
+    L.qb200_fft_backward.argtypes = [vp, dp, dp]
+    L.qb200_fft_forward.argtypes = [vp, dp, dp]
+    L.qb200_fft_backward_pair.argtypes = [vp, dp, dp, dp]
+    L.qb200_fft_forward_pair.argtypes = [vp, dp, dp, dp]
+    L.qb200_rs_mul_add.argtypes = [vp, i, i, dp, dp, dp, dp]
+    L.qb200_compute_density.argtypes = [vp, i, i, dp, dp, dp]
+    L.qb200_nl_create.argtypes = [C.POINTER(vp), i, i, i, d, dp]
+    L.qb200_nl_add_species.argtypes = [vp, i, i, ip, dp, dp, dp]
+    L.qb200_nl_set_positions.argtypes = [vp, i, dp]
+    L.qb200_nl_set_stream.argtypes = [vp, vp]
+    L.qb200_nl_destroy.argtypes = [vp]
+    L.qb200_nl_energy.argtypes = [vp, i, i, dp, dp, i, dp, C.POINTER(d)]
+    L.qb200_nl_query.argtypes = [vp, i]
+    L.qb200_nl_query.restype = ll
+    L.qb200_hpsi.argtypes = [vp, vp, i, i, dp, dp, dp, dp, dp, C.POINTER(d)]
+    for name in ("qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace",
+                 "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
+                 "qb200_rs_mul_add", "qb200_compute_density", "qb200_nl_create", "qb200_nl_add_species",
+                 "qb200_nl_set_positions", "qb200_nl_set_stream", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
+        getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise QB200Error(f"{what} failed ({rc}): {load().qb200_last_error().decode()}")
+
+
+def ptr(a):
+    """raw address of a numpy array (host) or torch tensor (host or device); None -> NULL"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags.c_contiguous, "array must be C-contiguous"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous(), "tensor must be contiguous"
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def _iarr(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def device_count() -> int:
+    return load().qb200_device_count()

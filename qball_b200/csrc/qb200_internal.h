@@ -1,0 +1,57 @@
+// qball_b200/csrc/qb200_internal.h -- shared between the translation units of libqball_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/qball_b200.h"
+#include "fft_smem.cuh"
+
+namespace qb200 {
+
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define QB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return qb200::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
+
+bool is_device_ptr(const void* p);
+bool factorize(int n, FftDesc& d);
+std::vector<double> twiddle_table(int n);   // 2n doubles: cos, sin (2 pi j / n), long-double accurate
+
+// device-side view of a plan (passed by value to kernels)
+struct DevPlan {
+  int np0, np1, np2;
+  int nvec, nrods, ngw, is_real;
+  int ntrans0, nkeep, ksplit, kskip;   // kept x-rows: [0,ksplit) and [ksplit+kskip, np1)
+  int pitch0;                          // odd row pitch of a plane in shared memory
+  int rb;                              // rods per z-column CTA
+  int xb;                              // x columns per CTA in the split path
+  FftDesc f0, f1, f2;
+  const cplx *tw0, *tw1, *tw2;
+  const int *rod_first, *rod_size, *rod_lmin;
+  const int *colpos;                   // per column iv: kp*pitch0 + hp
+  const int *colhk;                    // per column iv: hp + np0*kp
+  const int *keepcols, *keeprowstart;  // split path: columns sorted by kept row; start offsets per kept row (nkeep+1)
+};
+
+}  // namespace qb200
+
+struct qb200_plan {
+  int device;
+  cudaStream_t stream;
+  qb200::DevPlan d;
+  std::vector<void*> owned;            // device allocations freed at destroy
+  bool fused;                          // plane fits in shared memory
+  size_t smem_z, smem_plane, smem_rows, smem_ycol;
+  long long ws_bytes;
+  int batch;                           // units per batch
+  double* zt;                          // [batch][np2][nvec] complex
+  size_t zt_units;
+  double* w;                           // split path: [batch][np2][nkeep][np0] complex
+  size_t w_units;
+  double* rho_part; size_t rho_part_elems;
+  double* fac_dev; size_t fac_cap;
+  // staging for host-pointer calls
+  double *st_c, *st_cp, *st_v, *st_f, *st_kpg2; size_t st_c_cap, st_cp_cap, st_v_cap, st_f_cap, st_kpg2_cap;
+  long long launches;
+  int max_smem;
+  int nsm;
+};

@@ -1,0 +1,534 @@
+// qball_b200/csrc/transform.cu -- plan construction and the FourierTransform / rs_mul_add / compute_density entry
+// points of the C ABI (include/qball_b200.h).  Host code only builds tables and launches kernels; all arithmetic on
+// wavefunction data happens in the kernels of transform_kernels.cuh.  There is no CPU fallback.
+#include "transform_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace qb200 {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  g_err = buf;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice) return QB200_ENODEV;
+  if (e == cudaErrorMemoryAllocation) return QB200_ENOMEM;
+  return QB200_ECUDA;
+}
+
+bool is_device_ptr(const void* p)
+{
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// radices ascending so that the last (permuting) step has the largest radix
+bool factorize(int n, FftDesc& d)
+{
+  d.n = n; d.nf = 0;
+  if (n < 1) return false;
+  int m = n;
+  std::vector<int> f;
+  const int primes[3] = { 11, 7, 5 };
+  for (int p : primes) while (m % p == 0) { f.push_back(p); m /= p; }
+  while (m % 9 == 0) { f.push_back(9); m /= 9; }
+  while (m % 3 == 0) { f.push_back(3); m /= 3; }
+  while (m % 16 == 0) { f.push_back(16); m /= 16; }
+  if (m % 8 == 0) { f.push_back(8); m /= 8; }
+  if (m % 4 == 0) { f.push_back(4); m /= 4; }
+  if (m % 2 == 0) { f.push_back(2); m /= 2; }
+  if (m != 1) return false;
+  if (f.empty()) f.push_back(1);
+  if ((int)f.size() > QB200_MAXF) return false;
+  std::sort(f.begin(), f.end());
+  d.nf = (int)f.size();
+  for (int i = 0; i < d.nf; i++) d.r[i] = f[i];
+  return true;
+}
+
+std::vector<double> twiddle_table(int n)
+{
+  std::vector<double> t(2 * (size_t)n);
+  for (int j = 0; j < n; j++) {
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+    t[2 * j] = (double)cosl(a);
+    t[2 * j + 1] = (double)sinl(a);
+  }
+  return t;
+}
+
+template <class T> static int upload(qb200_plan* p, const std::vector<T>& h, const T** dptr)
+{
+  void* d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  QB_CUDA(cudaMalloc(&d, bytes));
+  p->owned.push_back(d);
+  if (!h.empty()) QB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = (const T*)d;
+  return QB200_OK;
+}
+
+static int ensure(double** buf, size_t* cap, size_t elems)
+{
+  if (*cap >= elems && *buf) return QB200_OK;
+  if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+  QB_CUDA(cudaMalloc((void**)buf, std::max<size_t>(elems, 1) * sizeof(double)));
+  *cap = elems;
+  return QB200_OK;
+}
+
+template <class K> static int opt_in_smem(K kernel, size_t bytes)
+{
+  if (bytes > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return QB200_OK;
+}
+
+}  // namespace qb200
+
+using namespace qb200;
+
+extern "C" const char* qb200_last_error(void) { return g_err.c_str(); }
+extern "C" const char* qb200_version(void) { return "qball_b200 0.1 (sm_100a)"; }
+extern "C" int qb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static int configure_batch(qb200_plan* p)
+{
+  const DevPlan& d = p->d;
+  const size_t zt_unit = (size_t)d.nvec * d.np2 * 16;
+  const size_t w_unit = p->fused ? 0 : (size_t)d.nkeep * d.np0 * d.np2 * 16;
+  long long b = p->ws_bytes / (long long)std::max<size_t>(zt_unit + w_unit, 1);
+  if (b < 1) b = 1;
+  if (b > 4096) b = 4096;
+  p->batch = (int)b;
+  return QB200_OK;
+}
+
+static int ensure_work(qb200_plan* p, int units)
+{
+  const DevPlan& d = p->d;
+  if ((size_t)units > p->zt_units) {
+    if (p->zt) cudaFree(p->zt);
+    p->zt = nullptr; p->zt_units = 0;
+    QB_CUDA(cudaMalloc((void**)&p->zt, (size_t)units * d.nvec * d.np2 * 16 + 16));
+    p->zt_units = units;
+  }
+  if (!p->fused && (size_t)units > p->w_units) {
+    if (p->w) cudaFree(p->w);
+    p->w = nullptr; p->w_units = 0;
+    QB_CUDA(cudaMalloc((void**)&p->w, (size_t)units * d.nkeep * d.np0 * d.np2 * 16 + 16));
+    p->w_units = units;
+  }
+  return QB200_OK;
+}
+
+extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1, int np2, int nrods, const int* rod_h,
+                                 const int* rod_k, const int* rod_lmin, const int* rod_size, int is_real, int idxmin1,
+                                 int idxmax1)
+{
+  if (!out || np0 < 1 || np1 < 1 || np2 < 1 || nrods < 1 || !rod_h || !rod_k || !rod_lmin || !rod_size) {
+    set_error("qb200_plan_create: bad argument");
+    return QB200_EINVAL;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  QB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("qb200_plan_create: no such CUDA device"); return QB200_ENODEV; }
+  QB_CUDA(cudaSetDevice(device));
+  qb200_plan* p = new qb200_plan();
+  memset(&p->d, 0, sizeof(p->d));
+  p->device = device; p->stream = 0; p->zt = nullptr; p->zt_units = 0; p->w = nullptr; p->w_units = 0;
+  p->rho_part = nullptr; p->rho_part_elems = 0; p->fac_dev = nullptr; p->fac_cap = 0;
+  p->st_c = p->st_cp = p->st_v = p->st_f = p->st_kpg2 = nullptr;
+  p->st_c_cap = p->st_cp_cap = p->st_v_cap = p->st_f_cap = p->st_kpg2_cap = 0;
+  p->launches = 0;
+  DevPlan& d = p->d;
+  d.np0 = np0; d.np1 = np1; d.np2 = np2; d.nrods = nrods; d.is_real = is_real ? 1 : 0;
+  d.nvec = is_real ? 2 * nrods - 1 : nrods;                       // FourierTransform.cc:186-197
+  d.ntrans0 = std::max(std::abs(idxmax1), std::abs(idxmin1)) + 1;  // FourierTransform.cc:202
+  if (2 * d.ntrans0 >= np1) { d.nkeep = np1; d.ksplit = np1; d.kskip = 0; }
+  else { d.nkeep = 2 * d.ntrans0; d.ksplit = d.ntrans0; d.kskip = np1 - 2 * d.ntrans0; }
+  d.pitch0 = np0 | 1;
+  if (!factorize(np0, d.f0) || !factorize(np1, d.f1) || !factorize(np2, d.f2)) {
+    set_error("qb200_plan_create: grid length not of the form 2^a 3^b 5^c 7^d 11^e"); delete p; return QB200_EUNSUPPORTED;
+  }
+  for (const FftDesc* f : { &d.f0, &d.f1, &d.f2 })
+    if (f->n / f->r[f->nf - 1] > 256) { set_error("qb200_plan_create: grid length too large"); delete p; return QB200_EUNSUPPORTED; }
+  if (is_real && (rod_h[0] != 0 || rod_k[0] != 0 || rod_lmin[0] != 0)) {
+    set_error("qb200_plan_create: real basis requires rod(0,0) first with lmin 0 (Basis.cc:637-651)"); delete p; return QB200_EINVAL;
+  }
+  // tables
+  std::vector<int> first(nrods), size(rod_size, rod_size + nrods), lmin(rod_lmin, rod_lmin + nrods);
+  int ngw = 0;
+  for (int r = 0; r < nrods; r++) {
+    first[r] = ngw; ngw += rod_size[r];
+    const int lo = rod_lmin[r], hi = rod_lmin[r] + rod_size[r] - 1;
+    if (rod_size[r] < 1 || rod_size[r] > np2 || lo <= -np2 || hi >= np2 || std::abs(rod_h[r]) >= np0 || std::abs(rod_k[r]) >= np1) {
+      set_error("qb200_plan_create: rod does not fit the grid"); delete p; return QB200_EINVAL;
+    }
+  }
+  d.ngw = ngw;
+  std::vector<int> colpos(d.nvec), colhk(d.nvec);
+  auto put = [&](int iv, int hp, int kp) { colpos[iv] = kp * d.pitch0 + hp; colhk[iv] = hp + np0 * kp; };
+  for (int r = 0; r < nrods; r++) {                               // FourierTransform.cc:361-430, 484-506
+    int hp = rod_h[r], kp = rod_k[r];
+    if (hp < 0) hp += np0;
+    if (kp < 0) kp += np1;
+    if (!is_real) { put(r, hp, kp); continue; }
+    if (r == 0) { put(0, 0, 0); continue; }
+    int hm = -hp, km = -kp;
+    if (hm < 0) hm += np0;
+    if (km < 0) km += np1;
+    put(2 * r - 1, hp, kp);
+    put(2 * r, hm, km);
+  }
+  // every column must sit on a kept row (true by construction of ntrans0)
+  std::vector<int> keepcols(d.nvec), rowstart(d.nkeep + 1, 0);
+  {
+    std::vector<std::vector<int> > by(d.nkeep);
+    for (int iv = 0; iv < d.nvec; iv++) {
+      const int kp = colhk[iv] / np0;
+      int jr;
+      if (kp < d.ksplit) jr = kp;
+      else if (kp >= d.ksplit + d.kskip) jr = kp - d.kskip;
+      else { set_error("qb200_plan_create: rod outside the kept rows (idxmin1/idxmax1 inconsistent)"); delete p; return QB200_EINVAL; }
+      by[jr].push_back(iv);
+    }
+    int k = 0;
+    for (int jr = 0; jr < d.nkeep; jr++) { rowstart[jr] = k; for (int iv : by[jr]) keepcols[k++] = iv; }
+    rowstart[d.nkeep] = k;
+  }
+  int rc;
+  if ((rc = upload(p, first, &d.rod_first)) || (rc = upload(p, size, &d.rod_size)) || (rc = upload(p, lmin, &d.rod_lmin)) ||
+      (rc = upload(p, colpos, &d.colpos)) || (rc = upload(p, colhk, &d.colhk)) || (rc = upload(p, keepcols, &d.keepcols)) ||
+      (rc = upload(p, rowstart, &d.keeprowstart))) { qb200_plan_destroy(p); return rc; }
+  {
+    const double* t;
+    if ((rc = upload(p, twiddle_table(np0), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw0 = (const cplx*)t;
+    if ((rc = upload(p, twiddle_table(np1), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw1 = (const cplx*)t;
+    if ((rc = upload(p, twiddle_table(np2), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw2 = (const cplx*)t;
+  }
+  // launch geometry
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  p->max_smem = (int)prop.sharedMemPerBlockOptin;
+  p->nsm = prop.multiProcessorCount;
+  const size_t pitch2 = (size_t)(np2 | 1);
+  int ncolmax = (int)std::min<size_t>(32, (80 * 1024) / (pitch2 * 16));
+  if (ncolmax < (is_real ? 2 : 1)) ncolmax = is_real ? 2 : 1;
+  d.rb = is_real ? std::max(1, ncolmax / 2) : ncolmax;
+  const int zcols = is_real ? 2 * d.rb : d.rb;
+  p->smem_z = ((size_t)np2 + (size_t)zcols * pitch2) * 16;
+  p->smem_plane = ((size_t)np0 + np1 + (size_t)np1 * d.pitch0) * 16;
+  const char* force_split = getenv("QB200_FORCE_SPLIT");
+  p->fused = p->smem_plane <= (size_t)p->max_smem && !(force_split && force_split[0] == '1');
+  d.xb = 16;
+  while (d.xb > 1 && ((size_t)np1 + (size_t)np1 * d.xb) * 16 > 96 * 1024) d.xb /= 2;
+  p->smem_ycol = ((size_t)np1 + (size_t)np1 * d.xb) * 16;
+  int rowb = (int)std::max<size_t>(1, (64 * 1024) / ((size_t)d.pitch0 * 16));
+  rowb = std::min(rowb, d.nkeep);
+  p->smem_rows = ((size_t)np0 + (size_t)rowb * d.pitch0) * 16;
+  if (p->smem_z > (size_t)p->max_smem || p->smem_ycol > (size_t)p->max_smem || p->smem_rows > (size_t)p->max_smem) {
+    set_error("qb200_plan_create: grid too large for shared-memory staging"); qb200_plan_destroy(p); return QB200_EUNSUPPORTED;
+  }
+  if ((rc = opt_in_smem(k_zcol_bwd<MODE_SINGLE>, p->smem_z)) || (rc = opt_in_smem(k_zcol_bwd<MODE_PAIR>, p->smem_z)) ||
+      (rc = opt_in_smem(k_zcol_fwd<MODE_SINGLE>, p->smem_z)) || (rc = opt_in_smem(k_zcol_fwd<MODE_PAIR>, p->smem_z))) {
+    qb200_plan_destroy(p); return rc;
+  }
+  if (p->fused) {
+    if ((rc = opt_in_smem(k_plane<OP_HPSI>, p->smem_plane)) || (rc = opt_in_smem(k_plane<OP_DENSITY>, p->smem_plane)) ||
+        (rc = opt_in_smem(k_plane<OP_BWD>, p->smem_plane)) || (rc = opt_in_smem(k_plane<OP_FWD>, p->smem_plane))) {
+      qb200_plan_destroy(p); return rc;
+    }
+  } else {
+    if ((rc = opt_in_smem(k_xrows<+1>, p->smem_rows)) || (rc = opt_in_smem(k_xrows<-1>, p->smem_rows)) ||
+        (rc = opt_in_smem(k_ycols<OP_HPSI>, p->smem_ycol)) || (rc = opt_in_smem(k_ycols<OP_DENSITY>, p->smem_ycol)) ||
+        (rc = opt_in_smem(k_ycols<OP_BWD>, p->smem_ycol)) || (rc = opt_in_smem(k_ycols<OP_FWD>, p->smem_ycol))) {
+      qb200_plan_destroy(p); return rc;
+    }
+  }
+  p->ws_bytes = p->fused ? (96ll << 20) : (3ll << 30);
+  if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
+  configure_batch(p);
+  *out = p;
+  return QB200_OK;
+}
+
+extern "C" int qb200_plan_destroy(qb200_plan* p)
+{
+  if (!p) return QB200_OK;
+  cudaSetDevice(p->device);
+  for (void* q : p->owned) cudaFree(q);
+  for (double* q : { p->zt, p->w, p->rho_part, p->fac_dev, p->st_c, p->st_cp, p->st_v, p->st_f, p->st_kpg2 })
+    if (q) cudaFree(q);
+  delete p;
+  return QB200_OK;
+}
+
+extern "C" int qb200_plan_set_stream(qb200_plan* p, void* s)
+{
+  if (!p) return QB200_EINVAL;
+  p->stream = (cudaStream_t)s;
+  return QB200_OK;
+}
+
+extern "C" int qb200_plan_set_workspace(qb200_plan* p, long long bytes)
+{
+  if (!p || bytes < 0) return QB200_EINVAL;
+  p->ws_bytes = bytes;
+  return configure_batch(p);
+}
+
+extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
+{
+  if (!p) return -1;
+  switch (what) {
+    case 0: return p->d.np0;
+    case 1: return p->d.np1;
+    case 2: return p->d.np2;
+    case 3: return p->d.nvec;
+    case 4: return p->d.ntrans0;
+    case 5: return p->d.ngw;
+    case 6: return p->d.is_real;
+    case 7: return p->fused ? 1 : 0;
+    case 8: return p->batch;
+    case 9: return p->launches;
+    default: return -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+#define QB_LAUNCH_CHECK(p) do { (p)->launches++; cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return qb200::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+
+static int nzblocks(const qb200_plan* p) { return (p->d.nrods + p->d.rb - 1) / p->d.rb; }
+
+static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int nunits)
+{
+  dim3 g(nzblocks(p), nunits);
+  if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
+  else k_zcol_bwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
+  QB_LAUNCH_CHECK(p);
+  return QB200_OK;
+}
+
+static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nunits, int accumulate, const double* kpg2,
+                       const double* cin)
+{
+  dim3 g(nzblocks(p), nunits);
+  const double scale = 1.0 / ((double)p->d.np0 * p->d.np1 * p->d.np2);
+  if (mode == MODE_PAIR)
+    k_zcol_fwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
+  else
+    k_zcol_fwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
+  QB_LAUNCH_CHECK(p);
+  return QB200_OK;
+}
+
+// the xy stage for `nunits` units whose column data sits in p->zt
+template <int OP>
+static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, const double* fac, int ngroups, int zero_imag)
+{
+  const DevPlan& d = p->d;
+  const int upg = (OP == OP_DENSITY) ? (nunits + ngroups - 1) / ngroups : 1;
+  const int ng = (OP == OP_DENSITY) ? ngroups : nunits;
+  if (p->fused) {
+    dim3 g(d.np2, ng);
+    k_plane<OP><<<g, 512, p->smem_plane, p->stream>>>(d, (cplx*)p->zt, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
+    QB_LAUNCH_CHECK(p);
+    return QB200_OK;
+  }
+  const int rowb = (int)((p->smem_rows / 16 - d.np0) / d.pitch0);
+  dim3 gr((d.nkeep + rowb - 1) / rowb, d.np2, nunits);
+  dim3 gy((d.np0 + d.xb - 1) / d.xb, d.np2, ng);
+  if (OP != OP_FWD) {
+    k_xrows<+1><<<gr, 256, p->smem_rows, p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, rowb);
+    QB_LAUNCH_CHECK(p);
+  }
+  k_ycols<OP><<<gy, 256, p->smem_ycol, p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
+  QB_LAUNCH_CHECK(p);
+  if (OP == OP_HPSI || OP == OP_FWD) {
+    k_xrows<-1><<<gr, 256, p->smem_rows, p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, rowb);
+    QB_LAUNCH_CHECK(p);
+  }
+  return QB200_OK;
+}
+
+// host<->device staging
+struct Staged {
+  const double* dev; bool staged;
+};
+static int stage_in(qb200_plan* p, const double* ptr, size_t elems, double** buf, size_t* cap, const double** dev)
+{
+  if (!ptr) { *dev = nullptr; return QB200_OK; }
+  if (is_device_ptr(ptr)) { *dev = ptr; return QB200_OK; }
+  int rc = ensure(buf, cap, elems);
+  if (rc) return rc;
+  QB_CUDA(cudaMemcpyAsync(*buf, ptr, elems * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  *dev = *buf;
+  return QB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single transforms
+static int fft_backward_impl(qb200_plan* p, const double* c1, const double* c2, double* f)
+{
+  if (!p || !c1 || !f) { set_error("qb200_fft_backward: bad argument"); return QB200_EINVAL; }
+  if (c2 && !p->d.is_real) { set_error("qb200_fft_backward_pair: basis is not real (FourierTransform.cc:1688 asserts)"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(p->device));
+  const DevPlan& d = p->d;
+  const size_t N = (size_t)d.np0 * d.np1 * d.np2;
+  int rc = ensure_work(p, 1);
+  if (rc) return rc;
+  // coefficients: gather c1 (and c2) into one ldc = ngw block of 1 or 2 columns on the device
+  rc = ensure(&p->st_c, &p->st_c_cap, 4 * (size_t)d.ngw);
+  if (rc) return rc;
+  const cudaMemcpyKind any = cudaMemcpyDefault;
+  QB_CUDA(cudaMemcpyAsync(p->st_c, c1, 16 * (size_t)d.ngw, any, p->stream));
+  if (c2) QB_CUDA(cudaMemcpyAsync(p->st_c + 2 * (size_t)d.ngw, c2, 16 * (size_t)d.ngw, any, p->stream));
+  double* fdev = f;
+  const bool fhost = !is_device_ptr(f);
+  if (fhost) { rc = ensure(&p->st_f, &p->st_f_cap, 2 * N); if (rc) return rc; fdev = p->st_f; }
+  if ((rc = launch_zbwd(p, c2 ? MODE_PAIR : MODE_SINGLE, p->st_c, d.ngw, 1))) return rc;
+  if ((rc = launch_xy<OP_BWD>(p, 1, nullptr, fdev, nullptr, 1, 0))) return rc;
+  if (fhost) QB_CUDA(cudaMemcpyAsync(f, fdev, 16 * N, cudaMemcpyDeviceToHost, p->stream));
+  QB_CUDA(cudaStreamSynchronize(p->stream));
+  return QB200_OK;
+}
+
+static int fft_forward_impl(qb200_plan* p, double* f, double* c1, double* c2)
+{
+  if (!p || !c1 || !f) { set_error("qb200_fft_forward: bad argument"); return QB200_EINVAL; }
+  if (c2 && !p->d.is_real) { set_error("qb200_fft_forward_pair: basis is not real (FourierTransform.cc:1727 asserts)"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(p->device));
+  const DevPlan& d = p->d;
+  const size_t N = (size_t)d.np0 * d.np1 * d.np2;
+  int rc = ensure_work(p, 1);
+  if (rc) return rc;
+  const double* fdev;
+  if ((rc = stage_in(p, f, 2 * N, &p->st_f, &p->st_f_cap, &fdev))) return rc;
+  rc = ensure(&p->st_c, &p->st_c_cap, 4 * (size_t)d.ngw);
+  if (rc) return rc;
+  if ((rc = launch_xy<OP_FWD>(p, 1, nullptr, (double*)fdev, nullptr, 1, 0))) return rc;
+  if ((rc = launch_zfwd(p, c2 ? MODE_PAIR : MODE_SINGLE, p->st_c, d.ngw, 1, 0, nullptr, nullptr))) return rc;
+  QB_CUDA(cudaMemcpyAsync(c1, p->st_c, 16 * (size_t)d.ngw, cudaMemcpyDefault, p->stream));
+  if (c2) QB_CUDA(cudaMemcpyAsync(c2, p->st_c + 2 * (size_t)d.ngw, 16 * (size_t)d.ngw, cudaMemcpyDefault, p->stream));
+  QB_CUDA(cudaStreamSynchronize(p->stream));
+  return QB200_OK;
+}
+
+extern "C" int qb200_fft_backward(qb200_plan* p, const double* c, double* f) { return fft_backward_impl(p, c, nullptr, f); }
+extern "C" int qb200_fft_backward_pair(qb200_plan* p, const double* c1, const double* c2, double* f)
+{
+  if (!c2) { set_error("qb200_fft_backward_pair: bad argument"); return QB200_EINVAL; }
+  return fft_backward_impl(p, c1, c2, f);
+}
+extern "C" int qb200_fft_forward(qb200_plan* p, double* f, double* c) { return fft_forward_impl(p, f, c, nullptr); }
+extern "C" int qb200_fft_forward_pair(qb200_plan* p, double* f, double* c1, double* c2)
+{
+  if (!c2) { set_error("qb200_fft_forward_pair: bad argument"); return QB200_EINVAL; }
+  return fft_forward_impl(p, f, c1, c2);
+}
+
+// ------------------------------------------------------------------------------------------------ rs_mul_add
+// device pointers only (also used by hpsi.cu)
+int qb200_rs_mul_add_dev(qb200_plan* p, int ldc, int nst, const double* c, const double* v, const double* kpg2, double* cp)
+{
+  const DevPlan& d = p->d;
+  int rc;
+  auto run = [&](int first_state, int nunits, int mode, int zero_imag) -> int {
+    const int spu = mode == MODE_PAIR ? 2 : 1;
+    for (int b0 = 0; b0 < nunits; b0 += p->batch) {
+      const int nb = std::min(p->batch, nunits - b0);
+      int r = ensure_work(p, nb);
+      if (r) return r;
+      const size_t off = 2 * (size_t)(first_state + b0 * spu) * ldc;
+      if ((r = launch_zbwd(p, mode, c + off, ldc, nb))) return r;
+      if ((r = launch_xy<OP_HPSI>(p, nb, v, nullptr, nullptr, 1, zero_imag))) return r;
+      if ((r = launch_zfwd(p, mode, cp + off, ldc, nb, 1, kpg2, kpg2 ? c + off : nullptr))) return r;
+    }
+    return QB200_OK;
+  };
+  if (d.is_real) {                                   // SlaterDet.cc:987-1023: local pairs, then the odd tail with Im := 0
+    const int npair = nst / 2;
+    if (npair && (rc = run(0, npair, MODE_PAIR, 0))) return rc;
+    if (nst % 2 && (rc = run(nst - 1, 1, MODE_SINGLE, 1))) return rc;
+  } else {
+    if ((rc = run(0, nst, MODE_SINGLE, 0))) return rc;  // SlaterDet.cc:1027-1037
+  }
+  return QB200_OK;
+}
+
+extern "C" int qb200_rs_mul_add(qb200_plan* p, int ldc, int nst, const double* c, const double* v, const double* kpg2,
+                                double* cp)
+{
+  if (!p || !c || !v || !cp || nst < 0 || ldc < p->d.ngw) { set_error("qb200_rs_mul_add: bad argument"); return QB200_EINVAL; }
+  if (nst == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(p->device));
+  const DevPlan& d = p->d;
+  const size_t N = (size_t)d.np0 * d.np1 * d.np2, blk = 2 * (size_t)ldc * nst;
+  const double *cd, *vd, *kd, *cpd_c;
+  int rc;
+  if ((rc = stage_in(p, c, blk, &p->st_c, &p->st_c_cap, &cd))) return rc;
+  if ((rc = stage_in(p, v, N, &p->st_v, &p->st_v_cap, &vd))) return rc;
+  if ((rc = stage_in(p, kpg2, d.ngw, &p->st_kpg2, &p->st_kpg2_cap, &kd))) return rc;
+  if ((rc = stage_in(p, cp, blk, &p->st_cp, &p->st_cp_cap, &cpd_c))) return rc;
+  double* cpd = const_cast<double*>(cpd_c);
+  if ((rc = qb200_rs_mul_add_dev(p, ldc, nst, cd, vd, kd, cpd))) return rc;
+  if (cpd != cp) {
+    QB_CUDA(cudaMemcpyAsync(cp, cpd, blk * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    QB_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  return QB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ compute_density
+extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const double* c, const double* fac, double* rho)
+{
+  if (!p || !c || !fac || !rho || nst < 0 || ldc < p->d.ngw) { set_error("qb200_compute_density: bad argument"); return QB200_EINVAL; }
+  if (nst == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(p->device));
+  const DevPlan& d = p->d;
+  const size_t N = (size_t)d.np0 * d.np1 * d.np2, blk = 2 * (size_t)ldc * nst;
+  const double *cd, *rd_c;
+  int rc;
+  if ((rc = stage_in(p, c, blk, &p->st_c, &p->st_c_cap, &cd))) return rc;
+  if ((rc = stage_in(p, rho, N, &p->st_v, &p->st_v_cap, &rd_c))) return rc;
+  double* rd = const_cast<double*>(rd_c);
+  if ((rc = ensure(&p->fac_dev, &p->fac_cap, nst))) return rc;
+  QB_CUDA(cudaMemcpyAsync(p->fac_dev, fac, nst * sizeof(double), cudaMemcpyDefault, p->stream));
+  // groups: exclusive owners of a partial density each; enough CTAs to fill the machine
+  const int nb_max = std::min(p->batch, nst);
+  int ngroups = 1;
+  if (p->fused) ngroups = std::max(1, std::min(nb_max, (2 * p->nsm + d.np2 - 1) / d.np2));
+  if ((rc = ensure(&p->rho_part, &p->rho_part_elems, (size_t)ngroups * N))) return rc;
+  QB_CUDA(cudaMemsetAsync(p->rho_part, 0, (size_t)ngroups * N * sizeof(double), p->stream));
+  for (int b0 = 0; b0 < nst; b0 += p->batch) {
+    const int nb = std::min(p->batch, nst - b0);
+    if ((rc = ensure_work(p, nb))) return rc;
+    if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
+    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, ngroups, 0))) return rc;
+  }
+  k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);
+  QB_LAUNCH_CHECK(p);
+  if (rd != rho) {
+    QB_CUDA(cudaMemcpyAsync(rho, rd, N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    QB_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  return QB200_OK;
+}

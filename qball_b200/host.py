@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's classes on this path, over the C ABI (names and argument meaning follow
+LLNL/qball: FourierTransform.h:144-153, SlaterDet.h:113-115, NonLocalPotential.h:93-96).
+
+The C++ equivalent a Qball maintainer would use is include/qball_b200.hpp; this Python mirror exists so that the
+parity tests and bench.py read like the reference's own drivers (src/tests/testFourierTransform.cc).
+Arrays: numpy (host) or CUDA torch tensors (device, used in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class FourierTransform:
+    """FourierTransform(basis, np0, np1, np2)  (FourierTransform.cc:144-526), one rank.
+
+    `basis` is any object/dict with the reference Basis accessors' values: nrods (nrod_loc), rod_h, rod_k, rod_lmin,
+    rod_size, is_real (Basis::real()), idxmin1/idxmax1 (Basis::idxmin(1)/idxmax(1))."""
+
+    def __init__(self, basis, np0: int, np1: int, np2: int, device: int = 0, stream=None):
+        L = capi.load()
+        g = basis.get if isinstance(basis, dict) else (lambda k: getattr(basis, k))
+        self._keep = [capi._iarr(g(k)) for k in ("rod_h", "rod_k", "rod_lmin", "rod_size")]
+        h = C.c_void_p()
+        capi._check(L.qb200_plan_create(C.byref(h), device, np0, np1, np2, int(g("nrods")), *[k[1] for k in self._keep],
+                                        int(bool(g("is_real"))), int(g("idxmin1")), int(g("idxmax1"))), "qb200_plan_create")
+        self._h, self._L = h, L
+        self.np0_, self.np1_, self.np2_ = np0, np1, np2
+        self.is_real = bool(g("is_real"))
+        if stream is not None:
+            self.set_stream(stream)
+
+    # reference accessors (FourierTransform.h:121-139)
+    def np0(self): return self.np0_
+    def np1(self): return self.np1_
+    def np2(self): return self.np2_
+    def np012(self): return self.np0_ * self.np1_ * self.np2_
+    def np012loc(self): return self.np012()
+    def nvec(self): return int(self._L.qb200_plan_query(self._h, 3))
+    def ntrans0(self): return int(self._L.qb200_plan_query(self._h, 4))
+    def ngw(self): return int(self._L.qb200_plan_query(self._h, 5))
+    def fused(self): return bool(self._L.qb200_plan_query(self._h, 7))
+    def batch(self): return int(self._L.qb200_plan_query(self._h, 8))
+    def launches(self): return int(self._L.qb200_plan_query(self._h, 9))
+
+    def set_stream(self, stream):
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        capi._check(self._L.qb200_plan_set_stream(self._h, s), "qb200_plan_set_stream")
+
+    def set_workspace(self, nbytes: int):
+        capi._check(self._L.qb200_plan_set_workspace(self._h, int(nbytes)), "qb200_plan_set_workspace")
+
+    def backward(self, c, f, c2=None):
+        """backward(c, f) / backward(c1, c2, f): f(r) = sum_G c_G e^{+iGr}  (FourierTransform.cc:529-567)"""
+        if c2 is None:
+            capi._check(self._L.qb200_fft_backward(self._h, capi.ptr(c), capi.ptr(f)), "qb200_fft_backward")
+        else:
+            capi._check(self._L.qb200_fft_backward_pair(self._h, capi.ptr(c), capi.ptr(c2), capi.ptr(f)), "qb200_fft_backward_pair")
+        return f
+
+    def forward(self, f, c, c2=None):
+        """forward(f, c) / forward(f, c1, c2); f is clobbered as in the reference (FourierTransform.cc:542-581)"""
+        if c2 is None:
+            capi._check(self._L.qb200_fft_forward(self._h, capi.ptr(f), capi.ptr(c)), "qb200_fft_forward")
+        else:
+            capi._check(self._L.qb200_fft_forward_pair(self._h, capi.ptr(f), capi.ptr(c), capi.ptr(c2)), "qb200_fft_forward_pair")
+        return c
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qb200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _block_dims(c):
+    """(nst, ldc) of a coefficient block given as a 2-D (nst, ldc) complex array/tensor (== column-major ldc x nst)"""
+    assert len(c.shape) == 2
+    return int(c.shape[0]), int(c.shape[1])
+
+
+def rs_mul_add(ft: FourierTransform, c, v, cp, kpg2=None):
+    """SlaterDet::rs_mul_add(ft, v, sdp): cp += FT[v * FT^-1 c] (SlaterDet.cc:971-1040); kpg2 fuses the kinetic term."""
+    nst, ldc = _block_dims(c)
+    capi._check(ft._L.qb200_rs_mul_add(ft._h, ldc, nst, capi.ptr(c), capi.ptr(v), capi.ptr(kpg2), capi.ptr(cp)), "qb200_rs_mul_add")
+    return cp
+
+
+def compute_density(ft: FourierTransform, c, weight: float, occ, omega: float, rho):
+    """SlaterDet::compute_density(ft, weight, rho): rho += weight*occ_n/omega |psi_n|^2 (SlaterDet.cc:839-932)"""
+    nst, ldc = _block_dims(c)
+    fac = np.ascontiguousarray((weight / omega) * np.asarray(occ, dtype=np.float64))
+    assert fac.shape[0] == nst
+    capi._check(ft._L.qb200_compute_density(ft._h, ldc, nst, capi.ptr(c), capi.ptr(fac), capi.ptr(rho)), "qb200_compute_density")
+    return rho
+
+
+class NonLocalPotential:
+    """NonLocalPotential(atoms, ctxt, basis, ...) norm-conserving branch (NonLocalPotential.cc:76-258, 1909-2171).
+    `species` = list of dict(na, npr, lproj, wt, twnl[npr, ngw], tau[na, 3]) -- the reference's init/update_twnl outputs."""
+
+    def __init__(self, basis, species, device: int = 0, stream=None):
+        L = capi.load()
+        g = basis.get if isinstance(basis, dict) else (lambda k: getattr(basis, k))
+        kpgx = np.ascontiguousarray(g("kpgx"), dtype=np.float64)
+        h = C.c_void_p()
+        capi._check(L.qb200_nl_create(C.byref(h), device, int(g("ngw")), int(bool(g("is_real"))), float(g("omega")),
+                                      capi.ptr(kpgx)), "qb200_nl_create")
+        self._h, self._L = h, L
+        for s in species:
+            lproj, lp = capi._iarr(s["lproj"])
+            wt = np.ascontiguousarray(s["wt"], dtype=np.float64)
+            twnl = np.ascontiguousarray(s["twnl"], dtype=np.float64)
+            tau = np.ascontiguousarray(s["tau"], dtype=np.float64)
+            capi._check(L.qb200_nl_add_species(h, int(s["na"]), int(s["npr"]), lp, capi.ptr(wt), capi.ptr(twnl), capi.ptr(tau)),
+                        "qb200_nl_add_species")
+        if stream is not None:
+            s_ = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+            capi._check(L.qb200_nl_set_stream(h, s_), "qb200_nl_set_stream")
+
+    def launches(self): return int(self._L.qb200_nl_query(self._h, 9))
+
+    def set_positions(self, isp: int, tau):
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        capi._check(self._L.qb200_nl_set_positions(self._h, isp, capi.ptr(tau)), "qb200_nl_set_positions")
+
+    def energy(self, c, occ, compute_hpsi: bool, cp=None) -> float:
+        """energy(sd, compute_hpsi, dsd, ...): returns enl; cp += V_nl psi when compute_hpsi."""
+        nst, ldc = _block_dims(c)
+        occ = np.ascontiguousarray(occ, dtype=np.float64)
+        enl = C.c_double(0.0)
+        capi._check(self._L.qb200_nl_energy(self._h, ldc, nst, capi.ptr(c), capi.ptr(occ), int(compute_hpsi), capi.ptr(cp),
+                                            C.byref(enl)), "qb200_nl_energy")
+        return enl.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qb200_nl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hpsi(ft: FourierTransform, nlp, c, occ, v, kpg2, out) -> float:
+    """The H psi block of EnergyFunctional::energy(compute_hpsi=true) (EnergyFunctional.cc:1142-1153,1500,1675-1695):
+    out = V_nl c + 0.5|k+G|^2 c + FT[v FT^-1 c]; returns enl."""
+    nst, ldc = _block_dims(c)
+    occ = np.ascontiguousarray(occ, dtype=np.float64)
+    enl = C.c_double(0.0)
+    capi._check(ft._L.qb200_hpsi(ft._h, nlp._h if nlp is not None else None, ldc, nst, capi.ptr(c), capi.ptr(occ), capi.ptr(v),
+                                 capi.ptr(kpg2), capi.ptr(out), C.byref(enl)), "qb200_hpsi")
+    return enl.value

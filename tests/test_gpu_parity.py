@@ -1,0 +1,162 @@
+"""GPU: the CUDA path, called through the C ABI (qball_b200.host -> libqball_b200.so), against
+  (1) the committed golden vectors produced by the reference itself (tests/golden/*.npz), and
+  (2) the plain-C oracle on seeded inputs for shapes/paths the fixtures do not cover.
+Tolerance: 1e-10 relative (BASELINE.json north_star) -- FP64 FFT/GEMM results are not bit-identical between
+algorithms; the index tables (integer work) are checked exactly in the CPU tests."""
+import numpy as np
+import pytest
+import torch
+
+import port as P
+import refdrive as R
+from qball_b200 import host as H
+from util import TOL, compare, golden_names, load_golden, regen_inputs, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _run_fixture(name, use_device_ptrs, force_split, monkeypatch):
+    if force_split:
+        monkeypatch.setenv("QB200_FORCE_SPLIT", "1")
+    g = load_golden(name)
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    ngw, N = g["ngw"], g["np0"] * g["np1"] * g["np2"]
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.fused() == (not force_split)
+    assert ft.nvec() == (2 * g["nrods"] - 1 if g["is_real"] else g["nrods"])
+    wrap = _dev if use_device_ptrs else (lambda a: np.ascontiguousarray(a))
+    back = (lambda t: t.cpu().numpy()) if use_device_ptrs else (lambda a: a)
+    # single transforms
+    f = wrap(np.zeros(N, dtype=np.complex128))
+    ft.backward(wrap(c[0, :ngw].copy()), f)
+    compare(g, "bwd0", back(f))
+    fv = wrap(back(f) * v)
+    cc = wrap(np.zeros(ngw, dtype=np.complex128))
+    ft.forward(fv, cc)
+    compare(g, "fwd0", back(cc))
+    if g["is_real"] and g["nst"] >= 2:
+        ft.backward(wrap(c[0, :ngw].copy()), f, c2=wrap(c[1, :ngw].copy()))
+        compare(g, "bwdpair01", back(f))
+        fv = wrap(back(f) * v)
+        c1, c2 = wrap(np.zeros(ngw, dtype=np.complex128)), wrap(np.zeros(ngw, dtype=np.complex128))
+        ft.forward(fv, c1, c2)
+        compare(g, "fwdpair0", back(c1))
+        compare(g, "fwdpair1", back(c2))
+    # rs_mul_add, density, nonlocal, whole H psi
+    cw, vw = wrap(c), wrap(v)
+    cp = wrap(np.zeros_like(c))
+    H.rs_mul_add(ft, cw, vw, cp)
+    compare(g, "hloc", back(cp))
+    rho = wrap(np.zeros(N))
+    H.compute_density(ft, cw, 1.0, occ, g["omega"], rho)
+    compare(g, "rho", back(rho))
+    nlp = H.NonLocalPotential(b, g["species"])
+    cp = wrap(np.zeros_like(c))
+    enl = nlp.energy(cw, occ, True, cp)
+    assert abs(enl - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"])), (enl, g["enl"])
+    if g["nsp"]:
+        compare(g, "hnl", back(cp))
+    out = wrap(np.zeros_like(c))
+    enl2 = H.hpsi(ft, nlp, cw, occ, vw, wrap(b["kpg2"]), out)
+    assert abs(enl2 - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"]))
+    compare(g, "hpsi", back(out))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_vs_reference_fixture_device_pointers(name, monkeypatch):
+    _run_fixture(name, True, False, monkeypatch)
+
+
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_cuda_vs_reference_fixture_host_pointers(name, monkeypatch):
+    _run_fixture(name, False, False, monkeypatch)
+
+
+@pytest.mark.parametrize("name", ["gamma_triclinic_si_h", "kpoint_cubic_au_oncv", "sih4_60cubed"])
+def test_cuda_split_path_vs_reference_fixture(name, monkeypatch):
+    """the split (large-plane) kernels, forced on small grids"""
+    _run_fixture(name, True, True, monkeypatch)
+
+
+@pytest.mark.parametrize("cell,ecut,kpoint,fc,nst,ldpad", [
+    ((11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0, (0, 0, 0), False, 7, 5),         # Gamma, odd tail, padded ldc, 3 pair batches
+    ((11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0, (0.1, 0.2, 0.3), False, 5, 3),  # complex, padded ldc
+    ((16, 0, 0, 0, 9, 0, 0, 0, 9), 9.0, (0, 0, 0.5), False, 3, 0),         # radix mix incl. 5/3/9
+])
+def test_cuda_vs_oracle_seeded(cell, ecut, kpoint, fc, nst, ldpad):
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    grid = P.density_grid(cell, ecut)
+    ldc = b["ngw"] + ldpad
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=5)
+    v = R.synth_potential(*grid, seed=9)
+    occ = R.synth_occ(nst, nst - 1)
+    oft = P.FT(b, *grid)
+    ft = H.FourierTransform(b, *grid)
+    ft.set_workspace(3 * ft.nvec() * grid[2] * 16)  # 3 units per batch -> several batches
+    want = oft.rs_mul_add(c, v, np.zeros_like(c))
+    P.kinetic_add(b["kpg2"], c, want)
+    got = _dev(np.zeros_like(c))
+    H.rs_mul_add(ft, _dev(c), _dev(v), got, kpg2=_dev(b["kpg2"]))
+    got = got.cpu().numpy()
+    assert relerr(got[:, :b["ngw"]], want[:, :b["ngw"]]) < TOL
+    assert np.all(got[:, b["ngw"]:] == 0)  # padding rows untouched (SlaterDet.cc:2784-2787)
+    rho_want = oft.compute_density(c, occ / b["omega"], np.full(oft.N, 0.25))
+    rho = _dev(np.full(oft.N, 0.25))
+    H.compute_density(ft, _dev(c), 1.0, occ, b["omega"], rho)
+    assert relerr(rho.cpu().numpy(), rho_want) < TOL
+
+
+def test_properties_mgo216_full_size():
+    """BASELINE-size shape (MgO216: 112^3, ngw 73447): size-independent properties -- fwd(bwd(c)) = c, Parseval,
+    linearity of H_loc, integral of rho = sum of occupations times norms."""
+    cell, ecut = (23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), 25.0
+    b = P.make_basis(cell, ecut, (0, 0, 0), True)
+    assert b["ngw"] == 73447 and b["nrods"] == 2109
+    grid = P.density_grid(cell, ecut)
+    assert grid == (112, 112, 112)
+    N = 112 ** 3
+    nst = 6
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, seed=21)
+    v = R.synth_potential(*grid, seed=22)
+    ft = H.FourierTransform(b, *grid)
+    cd = _dev(c)
+    f = torch.zeros(N, dtype=torch.complex128, device="cuda")
+    ft.backward(cd[0].contiguous(), f)
+    nrm = float((f.abs() ** 2).sum().item()) / N
+    assert abs(nrm - float(np.vdot(c[0], c[0]).real)) < 1e-10 * nrm       # Parseval
+    back = torch.zeros(b["ngw"], dtype=torch.complex128, device="cuda")
+    ft.forward(f, back)
+    assert relerr(back.cpu().numpy(), c[0]) < 1e-12                        # round trip
+    vd = _dev(v)
+    h = torch.zeros_like(cd)
+    H.rs_mul_add(ft, cd, vd, h)
+    lin = torch.zeros(1, b["ngw"], dtype=torch.complex128, device="cuda")
+    comb = (0.3 * cd[1] - 1.7j * cd[2]).reshape(1, -1).contiguous()
+    H.rs_mul_add(ft, comb, vd, lin)
+    assert relerr(lin[0].cpu().numpy(), (0.3 * h[1] - 1.7j * h[2]).cpu().numpy()) < TOL   # linearity
+    # <c_m| V c_n> is Hermitian for real v
+    m = (cd.conj() @ h.T).cpu().numpy()
+    assert np.abs(m - m.conj().T).max() < 1e-10 * np.abs(m).max()
+    occ = np.array([2, 2, 1.5, 0, 1, 0.25])
+    rho = torch.zeros(N, dtype=torch.float64, device="cuda")
+    H.compute_density(ft, cd, 1.0, occ, b["omega"], rho)
+    nel = float(rho.sum().item()) * b["omega"] / N                          # ChargeDensity.cc:525
+    want = float(sum(occ[n] * np.vdot(c[n], c[n]).real for n in range(nst)))
+    assert abs(nel - want) < 1e-10 * want
+    assert float(rho.min().item()) >= 0.0
+
+
+def test_no_device_fallback_is_an_error():
+    from qball_b200 import capi
+    L = capi.load()
+    import ctypes as C
+    h = C.c_void_p()
+    a = (C.c_int * 1)(0)
+    s = (C.c_int * 1)(3)
+    rc = L.qb200_plan_create(C.byref(h), 99, 8, 8, 8, 1, a, a, a, s, 0, 0, 0)
+    assert rc == -2 and b"device" in L.qb200_last_error()
