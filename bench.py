@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- H psi + density throughput of the B200 path on the reference's headline shapes (BASELINE.json).
+
+A "step" = one pass of the hot path over the rank's state block: the whole H psi block (nonlocal projectors + kinetic
++ local v(r) round trip, EnergyFunctional::energy compute_hpsi=true) followed by one density build
+(ChargeDensity::update_density: compute_density over the block, all-reduce of rho over ranks).
+value = state-applies/s = states through (H psi + density) per second, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mgo216|au992|sih4] [--impl ours|reference]
+
+N>1: launched by torchrun, one rank per GPU; states are sharded by rank (band parallelism, nprow=1); the per-GPU shard is
+fixed (weak scaling); the only collectives are the NCCL all-reduce of rho(r) and of the scalar E_nl.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: cell, ecut (Ha), kpoint, force_complex, nst per GPU, species shape [(name, na, lproj)], note
+    "mgo216": dict(cell=(23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), ecut=25.0, kpoint=(0, 0, 0), force_complex=True, nst=768,
+                   species=[("Mg", 108, [0, 1, 1, 1]), ("O", 108, [0])],
+                   note="examples/MgO216 (timing_nr512.i: 50 Ry, force_complex_wf ON, 768 states, 112^3 grid)"),
+    "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=24,
+                  species=[("Au", 992, [0, 1, 1, 1])],
+                  note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 24 states"),
+    "sih4": dict(cell=(14, 0, 0, 0, 14, 0, 0, 0, 14), ecut=18.0, kpoint=(0, 0, 0), force_complex=False, nst=4,
+                 species=[("Si", 1, [0, 1, 1, 1])], note="examples/sih4 (Gamma, real wavefunctions, 60^3 grid)"),
+}
+
+
+# ------------------------------------------------------------------------------------------------ host-side basis
+def make_basis(cell, ecut, kpoint, force_complex):
+    """G-sphere / rod tables as Basis::resize builds them (host setup, stays on the CPU in the reference too)"""
+    from qball_b200 import basis as B
+    return B.make_basis(cell, ecut, kpoint, force_complex), B.density_grid(cell, ecut)
+
+
+def atom_positions(cell, na_total):
+    """simple cubic filling of the cell (positions only steer the phases e^{-iG.tau}, not the cost)"""
+    a = np.array(cell, dtype=np.float64).reshape(3, 3)
+    n = int(np.ceil(na_total ** (1.0 / 3.0)))
+    pts = []
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                pts.append(((i + 0.25) / n, (j + 0.25) / n, (k + 0.25) / n))
+    pts = np.array(pts[:na_total]) @ a
+    return pts
+
+
+def synth_species(b, wl, seed=11):
+    """Gaussian-times-polynomial stand-in projector tables of the right shape"""
+    rng = np.random.default_rng(seed)
+    na_total = sum(s[1] for s in wl["species"])
+    pos = atom_positions(wl["cell"], na_total)
+    out, o = [], 0
+    kpg = np.sqrt(b["kpg2"])
+    for name, na, lproj in wl["species"]:
+        npr = len(lproj)
+        twnl = np.empty((npr, b["ngw"]))
+        for i, l in enumerate(lproj):
+            ang = 1.0 if l == 0 else b["kpgx"][(i - 1) % 3] / np.maximum(kpg, 1e-12)
+            twnl[i] = (1.5 + 0.1 * i) * kpg ** l * np.exp(-b["kpg2"] / 6.0) * ang
+        out.append(dict(na=na, npr=npr, lproj=np.array(lproj, dtype=np.int32), wt=rng.uniform(0.5, 2.0, npr) * np.where(np.array(lproj) == 0, 1, -1),
+                        twnl=twnl, tau=pos[o:o + na].copy()))
+        o += na
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
+    """times the reference's own SlaterDet::rs_mul_add / compute_density / NonLocalPotential::energy (oracle/_ref, the
+    UNMODIFIED reference compiled serially with its built-in FFT) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdrive as R
+    import synth_species as S
+    wl = WORKLOADS[wl_name]
+    threads = threads or os.cpu_count() or 1
+    if not R.have_ref():
+        return None
+    tmp = tempfile.mkdtemp(prefix="qbbench_")
+    spfiles = {"mgo216": S.mgo_species, "au992": S.au_species}.get(wl_name)
+    species, atoms = [], []
+    if spfiles:
+        species = spfiles(tmp)
+        na_total = sum(s[1] for s in wl["species"])
+        pos = atom_positions(wl["cell"], na_total)
+        o = 0
+        for (nm, _), (_, na, _) in zip(species, wl["species"]):
+            for i in range(na):
+                atoms.append((f"{nm}{i}", nm, float(pos[o + i][0]), float(pos[o + i][1]), float(pos[o + i][2])))
+            o += na
+    case = R.Case(cell=wl["cell"], ecut=wl["ecut"], kpoint=wl["kpoint"], force_complex=wl["force_complex"], nst=nst_sample,
+                  species=species, atoms=atoms)
+    prefix = os.path.join(tmp, "case")
+    cf = os.path.join(tmp, "case.txt")
+    with open(cf, "w") as f:
+        f.write(case.text(prefix))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    subprocess.run([R.REF_DRIVER, "basis", cf], check=True, env=env, stdout=subprocess.DEVNULL)
+    b = R.read_basis(prefix)
+    R.synth_coefficients(b["kpg2"], wl["ecut"], nst_sample, b["mloc"], b["is_real"], 1).tofile(prefix + ".in_c.f64")
+    R.synth_potential(b["np0"], b["np1"], b["np2"], 7).tofile(prefix + ".in_v.f64")
+    R.synth_occ(nst_sample).tofile(prefix + ".in_occ.f64")
+    out = subprocess.run([R.REF_DRIVER, "time", cf, str(nrep)], check=True, env=env, capture_output=True, text=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("{")][-1]
+    t = json.loads(line)
+    per_rep = (t["t_nonlocal"] + t["t_kinetic"] + t["t_local"] + t["t_density"]) / nrep
+    t.update(per_rep_s=per_rep, applies_per_s=nst_sample / per_rep, threads=threads)
+    return t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="mgo216", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nst", type=int, default=0, help="states per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.nst:
+        wl["nst"] = args.nst
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric, unit = "hpsi_density_state_applies_per_s", "state-applies/s"
+    config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}",
+              "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if args.workload == "mgo216" else "L2 flushed by the c/Hpsi block sweep"}
+
+    # ---------------------------------------------------------------- reference arm: the reference's CPU path on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = {"mgo216": 16, "au992": 1, "sih4": 4}[args.workload]
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t = run_reference_cpu(args.workload, sample, 1)
+            if t is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
+                return
+            if i >= args.warmup:
+                ts.append(t)
+            if i == 0 and t["per_rep_s"] > 60:   # keep the whole run within minutes
+                args.warmup, args.steps = 0, max(1, min(args.steps, 2))
+                ts.append(t)
+            if len(ts) >= args.steps:
+                break
+        per = float(np.mean([t["per_rep_s"] for t in ts]))
+        val = sample / per
+        smp = f"{sample} states of the {args.workload} shape (all {sum(s[1] for s in wl['species'])} atoms' projectors), one pass = " \
+              f"NonLocalPotential::energy + kinetic + rs_mul_add + compute_density, built-in FFT (FFT_NOLIB)"
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": len(ts),
+                          "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": unit, "cores": ts[0]["threads"], "kind": "reference", "sample": smp},
+                          "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "breakdown_s": {k: float(np.mean([t[k] for t in ts])) for k in ("t_nonlocal", "t_kinetic", "t_local", "t_density")}}))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from qball_b200 import capi
+    from qball_b200 import host as H
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b, grid = make_basis(wl["cell"], wl["ecut"], wl["kpoint"], wl["force_complex"])
+    np0, np1, np2 = grid
+    N, ngw, nst = np0 * np1 * np2, b["ngw"], wl["nst"]
+    from qball_b200 import synth as R
+    c_host = R.synth_coefficients(b["kpg2"], wl["ecut"], nst, ngw, b["is_real"], seed=1, first_state=rank * nst)
+    v_host = R.synth_potential(np0, np1, np2, 7)
+    occ = R.synth_occ(nst, nst - max(1, nst // 64))
+    species = synth_species(b, wl)
+    stream = torch.cuda.Stream(device=dev)
+    ft = H.FourierTransform(b, np0, np1, np2, device=local_rank, stream=stream)
+    nlp = H.NonLocalPotential(b, species, device=local_rank, stream=stream)
+    with torch.cuda.stream(stream):
+        c = torch.from_numpy(c_host).to(dev)
+        v = torch.from_numpy(v_host).to(dev)
+        kpg2 = torch.from_numpy(b["kpg2"]).to(dev)
+        hpsi = torch.zeros_like(c)
+        rho = torch.zeros(N, dtype=torch.float64, device=dev)
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    omega = b["omega"]
+
+    def step():
+        with torch.cuda.stream(stream):
+            enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
+            rho.zero_()
+            H.compute_density(ft, c, 1.0, occ, omega, rho)
+            if world > 1:
+                scal[0] = enl
+                dist.all_reduce(rho)          # ChargeDensity.cc:309 dsum('r') over state columns
+                dist.all_reduce(scal)         # NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519
+        return enl
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    l0 = ft.launches() + nlp.launches()
+    capi.profile_read()
+    capi.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    for _ in range(args.steps):
+        enl = step()
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    capi.profile_enable(False)
+    prof = capi.profile_read()
+    launches = ft.launches() + nlp.launches() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * nst * args.steps / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- roofline of the dominant kernels (live event times)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+    nvec = ft.nvec()
+    nunits_h = (nst // 2 + nst % 2) if b["is_real"] else nst          # FFT units per H psi sweep
+    xy_ms, xy_n = prof["xy_stage"]
+    # algorithmic bytes of the xy stage per FFT unit: read+write the column-form plane rows, read v (H psi) / rmw rho-partial
+    # is charged once per build: H psi unit 32*nvec*np2 + 8*N ; density unit 16*nvec*np2
+    xy_bytes_step = nunits_h * (32.0 * nvec * np2 + 8.0 * N) + nst * (16.0 * nvec * np2) + 16.0 * N
+    roofline_hbm = None
+    if xy_n:
+        ach = xy_bytes_step * args.steps / (xy_ms * 1e-3) / 1e9
+        roofline_hbm = {"kernel": "k_plane (fused xy stage)" if ft.fused() else "k_xrows+k_ycols (split xy stage)", "bound": "hbm",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
+    nl_flops_step = 0.0
+    for s in species:   # 2 GEMMs x 8 flops per complex MAC (4 per real-basis MAC over 2*ngw reals)
+        nl_flops_step += (16.0 if not b["is_real"] else 8.0) * s["na"] * s["npr"] * ngw * nst
+    nl_ms = prof["k_fnl"][0] + prof["k_back"][0]
+    fp64_peak = 37.0   # TFLOP/s nominal B200 FP64 (vector = DMMA); MEASURED_PEAKS.json has no FP64 entry
+    roofline_fp64 = None
+    if nl_ms > 0:
+        ach = nl_flops_step * args.steps / (nl_ms * 1e-3) / 1e12
+        roofline_fp64 = {"kernel": "k_fnl + k_back (DMMA projector GEMMs)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                         "peak_source": "nominal FP64 37 TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)",
+                         "launches": prof["k_fnl"][1] + prof["k_back"][1]}
+    prof_ms = {k: round(vv[0] / args.steps, 4) for k, vv in prof.items()}
+    dominant = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    roofline = roofline_fp64 if dominant in ("k_fnl", "k_back") and roofline_fp64 else roofline_hbm
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C ABI, copies inside
+    e2e = None
+    if not args.no_e2e:
+        hc = torch.from_numpy(c_host).pin_memory()
+        hv = torch.from_numpy(v_host).pin_memory()
+        hk = torch.from_numpy(b["kpg2"]).pin_memory()
+        hout = torch.empty_like(hc).pin_memory()
+        hrho = torch.zeros(N, dtype=torch.float64).pin_memory()
+
+        def step_host():
+            with torch.cuda.stream(stream):
+                e = H.hpsi(ft, nlp, hc, occ, hv, hk, hout)
+                hrho.zero_()
+                H.compute_density(ft, hc, 1.0, occ, omega, hrho)
+            return e
+
+        ne = max(1, min(args.steps, 3))
+        step_host()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            step_host()
+        sync_all()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        blk = 16 * ngw * nst
+        e2e = {"value": world * nst * ne / float(tt.item()), "unit": unit,
+               "h2d_bytes_per_step": int(2 * blk + 8 * N + 8 * ngw + 8 * N), "d2h_bytes_per_step": int(blk + 8 * N + 8),
+               "steps": ne, "api": "qb200_hpsi + qb200_compute_density with pinned HOST pointers (staged inside the call)"}
+
+    # ---------------------------------------------------------------- cpu baseline (rank 0, N=1): the compiled reference
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = {"mgo216": 16, "au992": 1, "sih4": 4}[args.workload]
+        try:
+            tcpu = run_reference_cpu(args.workload, sample, 1)
+        except Exception as ex:  # noqa: BLE001
+            tcpu = None
+            sys.stderr.write(f"cpu baseline failed: {ex}\n")
+        if tcpu:
+            cpu_baseline = {"value": tcpu["applies_per_s"], "unit": unit, "cores": tcpu["threads"], "kind": "reference",
+                            "sample": f"{sample} states of the {args.workload} shape, all projectors, one H psi + density pass; "
+                                      f"reference compiled serially with its built-in FFT (oracle/_ref), OMP threads = cores",
+                            "breakdown_s": {k: tcpu[k] for k in ("t_nonlocal", "t_kinetic", "t_local", "t_density")}}
+
+    if rank == 0:
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+               "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
+               "kernel_ms_per_step": prof_ms, "enl": enl,
+               "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
+                         "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

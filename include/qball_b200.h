@@ -101,6 +101,14 @@ long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched *
 int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,
                const double* kpg2, double* hpsi, double* enl);
 
+/* ---- optional per-kernel timing (CUDA events on the launching stream, recorded around every launch while enabled).
+ *      categories: 0 k_zcol_bwd, 1 xy stage (k_plane, or k_xrows+k_ycols), 2 k_zcol_fwd, 3 k_fnl, 4 k_fnl_finish+sum,
+ *      5 k_back, 6 k_rho_reduce.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the
+ *      recorded launches into ms[ncat]/count[ncat] and clears the record. */
+#define QB200_NCAT 7
+int qb200_profile_enable(int on);
+int qb200_profile_read(double* ms, long long* count, int ncat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,9 @@ def load():
     L.qb200_nl_query.argtypes = [vp, i]
     L.qb200_nl_query.restype = ll
     L.qb200_hpsi.argtypes = [vp, vp, i, i, dp, dp, dp, dp, dp, C.POINTER(d)]
-    for name in ("qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace",
+    L.qb200_profile_enable.argtypes = [i]
+    L.qb200_profile_read.argtypes = [C.POINTER(d), C.POINTER(ll), i]
+    for name in ("qb200_profile_enable", "qb200_profile_read", "qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace",
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_nl_create", "qb200_nl_add_species",
                  "qb200_nl_set_positions", "qb200_nl_set_stream", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
@@ -91,3 +93,19 @@ def _iarr(a):
 
 def device_count() -> int:
     return load().qb200_device_count()
+
+
+PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce")
+
+
+def profile_enable(on: bool):
+    load().qb200_profile_enable(int(on))
+
+
+def profile_read():
+    """{category: (total_ms, launches)} for the launches recorded since the last read"""
+    n = len(PROFILE_CATEGORIES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    load().qb200_profile_read(ms, cnt, n)
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(PROFILE_CATEGORIES)}

@@ -427,18 +427,24 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     const int nblk = (int)((total + 255) / 256);
     if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
     dim3 g1(mt, nt, ksplit);
+    prof_begin(3, nl->stream);
     if (nl->is_real) k_fnl<1><<<g1, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
     else k_fnl<0><<<g1, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
+    prof_begin(4, nl->stream);
     if (nl->is_real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(S, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
     else k_fnl_finish<0><<<nblk, 256, 0, nl->stream>>>(S, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
     NL_LAUNCH_CHECK(nl);
     k_sum_blocks<<<1, 32, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
+    prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
     if (compute_hpsi) {
       dim3 g2((nl->ngw + 63) / 64, (nst + 63) / 64);
+      prof_begin(5, nl->stream);
       if (nl->is_real) k_back<1><<<g2, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
       else k_back<0><<<g2, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
+      prof_end(nl->stream);
       NL_LAUNCH_CHECK(nl);
     }
   }

@@ -13,6 +13,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 #define QB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return qb200::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
 
 bool is_device_ptr(const void* p);
+// per-launch event timing (transform.cu)
+void prof_begin(int cat, cudaStream_t s);
+void prof_end(cudaStream_t s);
 bool factorize(int n, FftDesc& d);
 std::vector<double> twiddle_table(int n);   // 2n doubles: cos, sin (2 pi j / n), long-double accurate
 

@@ -66,6 +66,23 @@ std::vector<double> twiddle_table(int n)
   return t;
 }
 
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+void prof_begin(int cat, cudaStream_t s)
+{
+  if (!g_prof_on) return;
+  ProfRec r; r.cat = cat;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t s)
+{
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, s);
+}
+
 template <class T> static int upload(qb200_plan* p, const std::vector<T>& h, const T** dptr)
 {
   void* d = nullptr;
@@ -103,6 +120,22 @@ extern "C" int qb200_device_count(void)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+extern "C" int qb200_profile_enable(int on) { g_prof_on = on != 0; return QB200_OK; }
+extern "C" int qb200_profile_read(double* ms, long long* count, int ncat)
+{
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cat < ncat) {
+      if (ms) ms[r.cat] += t;
+      if (count) count[r.cat] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  cudaGetLastError();
+  return QB200_OK;
 }
 
 static int configure_batch(qb200_plan* p)
@@ -322,8 +355,10 @@ static int nzblocks(const qb200_plan* p) { return (p->d.nrods + p->d.rb - 1) / p
 static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int nunits)
 {
   dim3 g(nzblocks(p), nunits);
+  prof_begin(0, p->stream);
   if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
   else k_zcol_bwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
+  prof_end(p->stream);
   QB_LAUNCH_CHECK(p);
   return QB200_OK;
 }
@@ -333,10 +368,12 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
 {
   dim3 g(nzblocks(p), nunits);
   const double scale = 1.0 / ((double)p->d.np0 * p->d.np1 * p->d.np2);
+  prof_begin(2, p->stream);
   if (mode == MODE_PAIR)
     k_zcol_fwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
   else
     k_zcol_fwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
+  prof_end(p->stream);
   QB_LAUNCH_CHECK(p);
   return QB200_OK;
 }
@@ -350,13 +387,16 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
   const int ng = (OP == OP_DENSITY) ? ngroups : nunits;
   if (p->fused) {
     dim3 g(d.np2, ng);
+    prof_begin(1, p->stream);
     k_plane<OP><<<g, 512, p->smem_plane, p->stream>>>(d, (cplx*)p->zt, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
+    prof_end(p->stream);
     QB_LAUNCH_CHECK(p);
     return QB200_OK;
   }
   const int rowb = (int)((p->smem_rows / 16 - d.np0) / d.pitch0);
   dim3 gr((d.nkeep + rowb - 1) / rowb, d.np2, nunits);
   dim3 gy((d.np0 + d.xb - 1) / d.xb, d.np2, ng);
+  prof_begin(1, p->stream);
   if (OP != OP_FWD) {
     k_xrows<+1><<<gr, 256, p->smem_rows, p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, rowb);
     QB_LAUNCH_CHECK(p);
@@ -367,6 +407,7 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
     k_xrows<-1><<<gr, 256, p->smem_rows, p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, rowb);
     QB_LAUNCH_CHECK(p);
   }
+  prof_end(p->stream);
   return QB200_OK;
 }
 
@@ -524,7 +565,9 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
     if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
     if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, ngroups, 0))) return rc;
   }
+  prof_begin(6, p->stream);
   k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);
+  prof_end(p->stream);
   QB_LAUNCH_CHECK(p);
   if (rd != rho) {
     QB_CUDA(cudaMemcpyAsync(rho, rd, N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));

@@ -44,8 +44,10 @@ def regen_inputs(g, kpg2):
     c = R.synth_coefficients(kpg2, g["ecut"], g["nst"], g["mloc"], g["is_real"], g["seed"])
     v = R.synth_potential(g["np0"], g["np1"], g["np2"], g["seed"] + 6)
     occ = R.synth_occ(g["nst"], None if g["nocc"] < 0 else g["nocc"])
-    cs = np.array([checksum(c), checksum(v), checksum(occ)])
-    assert np.allclose(cs, g["in_checksum"], rtol=1e-12, atol=1e-12), "synthetic input generator drifted"
+    # libm/SIMD exp and cos may differ in the last ulp between hosts: compare the checksums relative to the L1 mass
+    for a, want in zip((c, v, occ), g["in_checksum"]):
+        l1 = float(np.abs(np.ascontiguousarray(a).view(np.float64)).sum())
+        assert abs(checksum(a) - float(want)) <= 1e-13 * max(l1, 1.0), "synthetic input generator drifted"
     return c, v, occ
 
 
