@@ -34,6 +34,22 @@ struct LineMap {
   __device__ __forceinline__ int off(int l) const { return (l < lsplit ? l : l + lskip) * lstride; }
 };
 
+// division by a loop-invariant positive divisor without the ~40-instruction integer divide: float reciprocal + fix-up
+// (exact for 0 <= n < 2^24)
+struct FastDiv {
+  int d;
+  float r;
+  __device__ __forceinline__ explicit FastDiv(int dd) : d(dd), r(1.0f / (float)dd) {}
+  __device__ __forceinline__ int div(int n, int& rem) const
+  {
+    int q = __float2int_rz(__int2float_rn(n) * r);
+    rem = n - q * d;
+    if (rem < 0) { q--; rem += d; }
+    else if (rem >= d) { q++; rem -= d; }
+    return q;
+  }
+};
+
 template <int R, int S>
 __device__ __noinline__ void dif_tasks(cplx* sm, int nlines, LineMap lm, int estride, int n, int len,
                                           const cplx* __restrict__ tw)
@@ -42,11 +58,11 @@ __device__ __noinline__ void dif_tasks(cplx* sm, int nlines, LineMap lm, int est
   const int per_line = n / R;                 // (n/len) segments * m offsets
   const int ntask = nlines * per_line;
   const int twmul = n / len;
+  const FastDiv dl(nlines), dm(m);
   for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-    const int line = task % nlines;
-    const int q = task / nlines;
-    const int t = q % m;
-    const int seg = q / m;
+    int line, t;
+    const int q = dl.div(task, line);
+    const int seg = dm.div(q, t);
     cplx* p = sm + lm.off(line) + (seg * len + t) * estride;
     const int step = m * estride;
     cplx x[R];
@@ -64,15 +80,15 @@ __device__ __noinline__ void dif_tasks(cplx* sm, int nlines, LineMap lm, int est
 }
 
 template <int R, int S>
-__device__ __noinline__ void last_tasks(cplx* sm, int nlines, LineMap lm, int estride, const FftDesc d)
+__device__ __noinline__ void last_tasks(cplx* sm, int nlines, LineMap lm, int estride, const FftDesc& d)
 {
   const int n = d.n;
   const int tpl = n / R;                       // tasks per line
   int lpr = blockDim.x / tpl;                  // lines per round
   if (lpr < 1) lpr = 1;                        // (tpl > blockDim.x is rejected on the host)
   if (lpr > nlines) lpr = nlines;
-  const int lr = threadIdx.x % lpr;
-  const int u = threadIdx.x / lpr;
+  int lr;
+  const int u = FastDiv(lpr).div(threadIdx.x, lr);
   // natural position of run u: digits of u (most significant = first radix) reversed
   int rev = 0;
   {
@@ -85,16 +101,17 @@ __device__ __noinline__ void last_tasks(cplx* sm, int nlines, LineMap lm, int es
       mul *= d.r[i];
     }
   }
+  // inactive threads (u >= tpl, or past the last line) work on clamped indices and simply do not store: keeping the
+  // loads and the butterfly unconditional keeps x[] in registers across the barrier
+  const int uc = min(u, tpl - 1);
   for (int line0 = 0; line0 < nlines; line0 += lpr) {
     const int line = line0 + lr;
     const bool act = (u < tpl) && (line < nlines);
     cplx x[R];
-    cplx* base = sm + (act ? lm.off(line) : 0);
-    if (act) {
+    cplx* base = sm + lm.off(min(line, nlines - 1));
 #pragma unroll
-      for (int k = 0; k < R; k++) x[k] = base[(u * R + k) * estride];
-      Dft<R, S>::run(x);
-    }
+    for (int k = 0; k < R; k++) x[k] = base[(uc * R + k) * estride];
+    Dft<R, S>::run(x);
     __syncthreads();
     if (act) {
 #pragma unroll

@@ -57,4 +57,5 @@ struct qb200_plan {
   long long launches;
   int max_smem;
   int nsm;
+  int plane_threads;
 };

@@ -31,7 +31,8 @@ bool is_device_ptr(const void* p)
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// radices ascending so that the last (permuting) step has the largest radix
+// radices descending: the twiddled DIF passes take the big radices (no spills at 112 registers), the last
+// (permuting) pass the smallest
 bool factorize(int n, FftDesc& d)
 {
   d.n = n; d.nf = 0;
@@ -49,7 +50,10 @@ bool factorize(int n, FftDesc& d)
   if (m != 1) return false;
   if (f.empty()) f.push_back(1);
   if ((int)f.size() > QB200_MAXF) return false;
-  std::sort(f.begin(), f.end());
+  std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
+  // the last pass needs n/r tasks per line in one round of <= 256 threads: take the smallest radix that allows it
+  for (int i = (int)f.size() - 1; i >= 0; i--)
+    if (n / f[i] <= 256) { const int r = f[i]; f.erase(f.begin() + i); f.push_back(r); break; }
   d.nf = (int)f.size();
   for (int i = 0; i < d.nf; i++) d.r[i] = f[i];
   return true;
@@ -296,6 +300,29 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       qb200_plan_destroy(p); return rc;
     }
   }
+  // plane kernel block size: the per-pass task counts rarely divide the block; pick the size (multiple of 32, <= 416 so
+  // that the radix-16 pass keeps its ~112 registers) that wastes the fewest FP64-pipe slots over one plane
+  {
+    auto cost = [&](int b) {
+      double c = 0.0;
+      const FftDesc* fd[2] = { &d.f0, &d.f1 };
+      const int nl[2] = { d.nkeep, np0 };
+      for (int a = 0; a < 2; a++) {
+        const FftDesc& f = *fd[a];
+        for (int i = 0; i < f.nf; i++) {
+          const double w = f.r[i] * std::log2((double)std::max(f.r[i], 2));
+          long rounds;
+          if (i < f.nf - 1) rounds = ((long)nl[a] * (f.n / f.r[i]) + b - 1) / b;
+          else { const int tpl = f.n / f.r[i]; const int lpr = std::max(1, std::min(b / tpl, nl[a])); rounds = (nl[a] + lpr - 1) / lpr; }
+          c += rounds * w * b;
+        }
+      }
+      return c;
+    };
+    int best = 384;
+    for (int b = 256; b <= 416; b += 32) if (cost(b) < cost(best)) best = b;
+    p->plane_threads = best;
+  }
   p->ws_bytes = p->fused ? (96ll << 20) : (3ll << 30);
   if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
   configure_batch(p);
@@ -388,7 +415,7 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
   if (p->fused) {
     dim3 g(d.np2, ng);
     prof_begin(1, p->stream);
-    k_plane<OP><<<g, 512, p->smem_plane, p->stream>>>(d, (cplx*)p->zt, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
+    k_plane<OP><<<g, p->plane_threads, p->smem_plane, p->stream>>>(d, (cplx*)p->zt, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
     prof_end(p->stream);
     QB_LAUNCH_CHECK(p);
     return QB200_OK;

@@ -31,7 +31,7 @@ __device__ __forceinline__ void load_tw(cplx* dst, const cplx* __restrict__ src,
 // ------------------------------------------------------------------------------------------------ z columns, backward
 // grid (ceil(nrods/rb), nunits); dynamic smem: np2 + ncolmax*pitch complex
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_zcol_bwd(DevPlan P, const cplx* __restrict__ c, size_t ldc, cplx* __restrict__ zt)
+__global__ void __launch_bounds__(256, 2) k_zcol_bwd(const __grid_constant__ DevPlan P, const cplx* __restrict__ c, size_t ldc, cplx* __restrict__ zt)
 {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx* tw = reinterpret_cast<cplx*>(smraw);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 2) k_zcol_bwd(DevPlan P, const cplx* __re
 // ------------------------------------------------------------------------------------------------ z columns, forward
 // out1/out2 (+ unit offsets) receive the coefficients; accumulate: out += ; kpg2/cin: add 0.5*kpg2*c
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_zcol_fwd(DevPlan P, const cplx* __restrict__ zt, cplx* __restrict__ out, size_t ldc,
+__global__ void __launch_bounds__(256, 2) k_zcol_fwd(const __grid_constant__ DevPlan P, const cplx* __restrict__ zt, cplx* __restrict__ out, size_t ldc,
                                                   int accumulate, const double* __restrict__ kpg2,
                                                   const cplx* __restrict__ cin, double scale)
 {
@@ -144,13 +144,13 @@ __global__ void __launch_bounds__(256, 2) k_zcol_fwd(DevPlan P, const cplx* __re
 }
 
 // ------------------------------------------------------------------------------------------------ fused xy plane
-// grid (np2, ngroups); block 512; dynamic smem: np0 + np1 + np1*pitch0 complex.
+// grid (np2, ngroups); block plan->plane_threads (<= 416); dynamic smem: np0 + np1 + np1*pitch0 complex.
 //   OP_HPSI    : zt plane -> psi(r) -> * v -> zt plane (in place).  zero_imag: the Gamma odd-tail rule (SlaterDet.cc:1015)
 //   OP_DENSITY : CTA walks the units of its group; rho_part[group][i] += fac[unit]*|psi|^2 (exclusive owner, no atomics)
 //   OP_BWD     : zt plane -> f[unit] plane
 //   OP_FWD     : f[unit] plane -> zt plane
 template <int OP>
-__global__ void __launch_bounds__(512, 1) k_plane(DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
+__global__ void __launch_bounds__(416, 1) k_plane(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
                                                    cplx* __restrict__ f, double* __restrict__ rho_part,
                                                    const double* __restrict__ fac, int nunits, int units_per_group,
                                                    int zero_imag)
@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(512, 1) k_plane(DevPlan P, cplx* __restrict__ 
   const LineMap cols = { 1, np0, 0 };
   const int u0 = blockIdx.y * units_per_group;
   const int u1 = min(u0 + units_per_group, nunits);
+  const FastDiv d0(np0);
+  constexpr int U = 8;                       // loads in flight per thread in the global-memory phases
   for (int unit = u0; unit < u1; unit++) {
     double facu = 0.0;
     if (OP == OP_DENSITY) { facu = fac[unit]; if (!(facu > 0.0)) continue; }
@@ -176,40 +178,69 @@ __global__ void __launch_bounds__(512, 1) k_plane(DevPlan P, cplx* __restrict__ 
     if (OP != OP_FWD) {
       for (int i = threadIdx.x; i < np1 * pitch; i += blockDim.x) pl[i] = make_double2(0.0, 0.0);
       __syncthreads();
-      for (int i = threadIdx.x; i < P.nvec; i += blockDim.x) pl[P.colpos[i]] = ztrow[i];
+      for (int i0 = threadIdx.x; i0 < P.nvec; i0 += U * blockDim.x) {
+        cplx val[U]; int pos[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int i = min(i0 + u * (int)blockDim.x, P.nvec - 1); val[u] = ztrow[i]; pos[u] = P.colpos[i]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int i = i0 + u * blockDim.x; if (i < P.nvec) pl[pos[u]] = val[u]; }
+      }
       __syncthreads();
       fft_lines<+1>(pl, P.nkeep, rows, 1, P.f0, tw0);
       fft_lines<+1>(pl, np0, cols, pitch, P.f1, tw1);
     }
     if (OP == OP_HPSI) {
       const double* vz = v + (size_t)z * np01;
-      for (int e = threadIdx.x; e < np01; e += blockDim.x) {
-        const int x = e % np0, y = e / np0;
-        const double vv = vz[e];
-        cplx t = pl[y * pitch + x];
-        t.x *= vv;
-        t.y = zero_imag ? 0.0 : t.y * vv;
-        pl[y * pitch + x] = t;
+      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
+        double vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) vv[u] = vz[min(e0 + u * (int)blockDim.x, np01 - 1)];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int e = e0 + u * blockDim.x;
+          if (e < np01) {
+            int x; const int y = d0.div(e, x);
+            cplx t = pl[y * pitch + x];
+            t.x *= vv[u];
+            t.y = zero_imag ? 0.0 : t.y * vv[u];
+            pl[y * pitch + x] = t;
+          }
+        }
       }
       __syncthreads();
     } else if (OP == OP_DENSITY) {
       double* rz = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01;
-      for (int e = threadIdx.x; e < np01; e += blockDim.x) {
-        const int x = e % np0, y = e / np0;
-        const cplx t = pl[y * pitch + x];
-        rz[e] += facu * (t.x * t.x + t.y * t.y);
+      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
+        double rr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) rr[u] = rz[min(e0 + u * (int)blockDim.x, np01 - 1)];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int e = e0 + u * blockDim.x;
+          if (e < np01) {
+            int x; const int y = d0.div(e, x);
+            const cplx t = pl[y * pitch + x];
+            rz[e] = rr[u] + facu * (t.x * t.x + t.y * t.y);
+          }
+        }
       }
     } else if (OP == OP_BWD) {
       cplx* fz = f + (size_t)unit * N + (size_t)z * np01;
       for (int e = threadIdx.x; e < np01; e += blockDim.x) {
-        const int x = e % np0, y = e / np0;
+        int x; const int y = d0.div(e, x);
         fz[e] = pl[y * pitch + x];
       }
     } else if (OP == OP_FWD) {
       const cplx* fz = f + (size_t)unit * N + (size_t)z * np01;
-      for (int e = threadIdx.x; e < np01; e += blockDim.x) {
-        const int x = e % np0, y = e / np0;
-        pl[y * pitch + x] = fz[e];
+      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
+        cplx val[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) val[u] = fz[min(e0 + u * (int)blockDim.x, np01 - 1)];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int e = e0 + u * blockDim.x;
+          if (e < np01) { int x; const int y = d0.div(e, x); pl[y * pitch + x] = val[u]; }
+        }
       }
       __syncthreads();
     }
@@ -226,7 +257,7 @@ __device__ __forceinline__ int keptrow_to_row(const DevPlan& P, int jr) { return
 
 // grid (ceil(nkeep/rowb), np2, nunits); smem: np0 + rowb*pitch0 complex
 template <int DIR>
-__global__ void __launch_bounds__(256, 2) k_xrows(DevPlan P, cplx* __restrict__ zt, cplx* __restrict__ w, int rowb)
+__global__ void __launch_bounds__(256, 2) k_xrows(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, cplx* __restrict__ w, int rowb)
 {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx* tw0 = reinterpret_cast<cplx*>(smraw);
@@ -269,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) k_xrows(DevPlan P, cplx* __restrict__ 
 // ------------------------------------------------------------------------------------------------ split path: y columns
 // grid (ceil(np0/xb), np2, ngroups); smem: np1 + np1*xb complex
 template <int OP>
-__global__ void __launch_bounds__(256, 2) k_ycols(DevPlan P, cplx* __restrict__ w, const double* __restrict__ v,
+__global__ void __launch_bounds__(256, 2) k_ycols(const __grid_constant__ DevPlan P, cplx* __restrict__ w, const double* __restrict__ v,
                                                cplx* __restrict__ f, double* __restrict__ rho_part,
                                                const double* __restrict__ fac, int nunits, int units_per_group,
                                                int zero_imag)
