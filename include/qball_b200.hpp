@@ -1,0 +1,143 @@
+// include/qball_b200.hpp -- C++ host-side mirror of the reference's classes on the H psi / density path, over the C ABI
+// (include/qball_b200.h).  Header only.  Same names, argument meaning and error behaviour as LLNL/qball:
+//
+//   qb200::FourierTransform   <->  FourierTransform        (src/qball/FourierTransform.h:57-189)
+//   qb200::rs_mul_add         <->  SlaterDet::rs_mul_add    (src/qball/SlaterDet.h:115, SlaterDet.cc:971-1040)
+//   qb200::compute_density    <->  SlaterDet::compute_density (src/qball/SlaterDet.h:113, SlaterDet.cc:839-932)
+//   qb200::NonLocalPotential  <->  NonLocalPotential::energy, norm-conserving branch (NonLocalPotential.h:93-96)
+//
+// The reference signals errors on this path with assert / cout + MPI_Abort / exit (FourierTransform.cc:696-700,
+// Messages.h:41-50); the wrappers below do the same: a non-zero status prints qb200_last_error() and aborts.
+// INTEGRATION.md shows the few lines each reference class needs to forward to these.
+#ifndef QBALL_B200_HPP
+#define QBALL_B200_HPP
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "qball_b200.h"
+
+namespace qb200 {
+
+inline void check(int rc, const char* what)
+{
+  if (rc != QB200_OK) {
+    std::fprintf(stderr, " qb200: %s failed (%d): %s\n", what, rc, qb200_last_error());
+    std::abort();   // the reference: MPI_Abort(MPI_COMM_WORLD, 2)
+  }
+}
+
+// What the plan needs from the reference's Basis (Basis.h:88-156); fill it from a `const Basis&` with from_basis().
+struct BasisTables {
+  int nrods = 0;
+  std::vector<int> rod_h, rod_k, rod_lmin, rod_size;
+  bool real = false;
+  int idxmin1 = 0, idxmax1 = 0;
+  // Works with any type exposing the reference's accessors: nrod_loc(), rod_h(i), rod_k(i), rod_lmin(i), rod_size(i),
+  // real(), idxmin(1), idxmax(1).
+  template <class BasisT> static BasisTables from_basis(const BasisT& b)
+  {
+    BasisTables t;
+    t.nrods = b.nrod_loc();
+    for (int i = 0; i < t.nrods; i++) {
+      t.rod_h.push_back(b.rod_h(i)); t.rod_k.push_back(b.rod_k(i));
+      t.rod_lmin.push_back(b.rod_lmin(i)); t.rod_size.push_back(b.rod_size(i));
+    }
+    t.real = b.real(); t.idxmin1 = b.idxmin(1); t.idxmax1 = b.idxmax(1);
+    return t;
+  }
+};
+
+class FourierTransform {
+ public:
+  // FourierTransform(const Basis& basis, int np0, int np1, int np2)   (FourierTransform.cc:144)
+  FourierTransform(const BasisTables& b, int np0, int np1, int np2, int device = 0) : np0_(np0), np1_(np1), np2_(np2)
+  {
+    check(qb200_plan_create(&plan_, device, np0, np1, np2, b.nrods, b.rod_h.data(), b.rod_k.data(), b.rod_lmin.data(),
+                            b.rod_size.data(), b.real ? 1 : 0, b.idxmin1, b.idxmax1), "qb200_plan_create");
+  }
+  ~FourierTransform() { qb200_plan_destroy(plan_); }
+  FourierTransform(const FourierTransform&) = delete;
+  FourierTransform& operator=(const FourierTransform&) = delete;
+
+  // backward: Fourier synthesis, c -> f(r); forward: Fourier analysis, f is clobbered (FourierTransform.h:144-153)
+  void backward(const std::complex<double>* c, std::complex<double>* f)
+  { check(qb200_fft_backward(plan_, reinterpret_cast<const double*>(c), reinterpret_cast<double*>(f)), "backward"); }
+  void forward(std::complex<double>* f, std::complex<double>* c)
+  { check(qb200_fft_forward(plan_, reinterpret_cast<double*>(f), reinterpret_cast<double*>(c)), "forward"); }
+  void backward(const std::complex<double>* c1, const std::complex<double>* c2, std::complex<double>* f)
+  { check(qb200_fft_backward_pair(plan_, reinterpret_cast<const double*>(c1), reinterpret_cast<const double*>(c2), reinterpret_cast<double*>(f)), "backward(pair)"); }
+  void forward(std::complex<double>* f, std::complex<double>* c1, std::complex<double>* c2)
+  { check(qb200_fft_forward_pair(plan_, reinterpret_cast<double*>(f), reinterpret_cast<double*>(c1), reinterpret_cast<double*>(c2)), "forward(pair)"); }
+
+  int np0() const { return np0_; }
+  int np1() const { return np1_; }
+  int np2() const { return np2_; }
+  int np2_loc() const { return np2_; }                       // nprow = 1
+  int np012() const { return np0_ * np1_ * np2_; }
+  int np012loc() const { return np012(); }
+  int index(int i, int j, int k) const { return i + np0_ * (j + np1_ * k); }   // FourierTransform.h:165
+  qb200_plan* plan() const { return plan_; }
+  void set_stream(void* cuda_stream) { check(qb200_plan_set_stream(plan_, cuda_stream), "set_stream"); }
+
+ private:
+  qb200_plan* plan_ = nullptr;
+  int np0_, np1_, np2_;
+};
+
+// sd.rs_mul_add(ft, v, sdp):  c = sd.c().cvalptr(), cp = sdp.c().valptr(), mloc = sd.c().mloc(), nstloc = sd.nstloc()
+inline void rs_mul_add(FourierTransform& ft, int mloc, int nstloc, const std::complex<double>* c, const double* v,
+                       std::complex<double>* cp, const double* kpg2 = nullptr)
+{
+  check(qb200_rs_mul_add(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), v, kpg2, reinterpret_cast<double*>(cp)), "rs_mul_add");
+}
+
+// sd.compute_density(ft, weight, rho):  occ_local[n] = occ_[c_.j(lj,jj)] of the n-th local state (SlaterDet.cc:912)
+inline void compute_density(FourierTransform& ft, int mloc, int nstloc, const std::complex<double>* c, double weight,
+                            const double* occ_local, double omega, double* rho)
+{
+  std::vector<double> fac(nstloc);
+  const double prefac = weight / omega;                      // SlaterDet.cc:848
+  for (int n = 0; n < nstloc; n++) fac[n] = prefac * occ_local[n];
+  check(qb200_compute_density(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), fac.data(), rho), "compute_density");
+}
+
+class NonLocalPotential {
+ public:
+  // kpgx = basis.kpgx_ptr(0) (3*ngw, component-major), omega = basis.cell().volume()
+  NonLocalPotential(int ngw, bool real, double omega, const double* kpgx, int device = 0)
+  { check(qb200_nl_create(&nl_, device, ngw, real ? 1 : 0, omega, kpgx), "qb200_nl_create"); }
+  ~NonLocalPotential() { qb200_nl_destroy(nl_); }
+  NonLocalPotential(const NonLocalPotential&) = delete;
+  NonLocalPotential& operator=(const NonLocalPotential&) = delete;
+  // one call per species with npr[is] > 0, in species order: na[is], npr[is], lproj[is], wt[is], twnl[is], tau[is]
+  void add_species(int na, int npr, const int* lproj, const double* wt, const double* twnl, const double* tau)
+  { check(qb200_nl_add_species(nl_, na, npr, lproj, wt, twnl, tau), "qb200_nl_add_species"); }
+  void set_positions(int is, const double* tau) { check(qb200_nl_set_positions(nl_, is, tau), "qb200_nl_set_positions"); }
+  // double energy(SlaterDet& sd, bool compute_hpsi, SlaterDet& dsd, ...) without forces/stress
+  double energy(int mloc, int nstloc, const std::complex<double>* c, const double* occ_local, bool compute_hpsi,
+                std::complex<double>* cp)
+  {
+    double enl = 0.0;
+    check(qb200_nl_energy(nl_, mloc, nstloc, reinterpret_cast<const double*>(c), occ_local, compute_hpsi ? 1 : 0,
+                          reinterpret_cast<double*>(cp), &enl), "qb200_nl_energy");
+    return enl;
+  }
+  qb200_nl* handle() const { return nl_; }
+
+ private:
+  qb200_nl* nl_ = nullptr;
+};
+
+// the H psi block of EnergyFunctional::energy(compute_hpsi = true) in one call (EnergyFunctional.cc:1142-1153,1500,1675-1695)
+inline double hpsi(FourierTransform& ft, NonLocalPotential* nlp, int mloc, int nstloc, const std::complex<double>* c,
+                   const double* occ_local, const double* v, const double* kpg2, std::complex<double>* dwf)
+{
+  double enl = 0.0;
+  check(qb200_hpsi(ft.plan(), nlp ? nlp->handle() : nullptr, mloc, nstloc, reinterpret_cast<const double*>(c), occ_local, v,
+                   kpg2, reinterpret_cast<double*>(dwf), &enl), "qb200_hpsi");
+  return enl;
+}
+
+}  // namespace qb200
+#endif

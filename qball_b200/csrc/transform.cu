@@ -320,7 +320,8 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       return c;
     };
     int best = 384;
-    for (int b = 256; b <= 416; b += 32) if (cost(b) < cost(best)) best = b;
+    for (int b = 256; b <= 512; b += 32) if (cost(b) < cost(best)) best = b;
+    if (const char* e = getenv("QB200_PLANE_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) best = t; }
     p->plane_threads = best;
   }
   p->ws_bytes = p->fused ? (96ll << 20) : (3ll << 30);

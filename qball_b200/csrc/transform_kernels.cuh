@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256, 2) k_zcol_fwd(const __grid_constant__ Dev
 //   OP_BWD     : zt plane -> f[unit] plane
 //   OP_FWD     : f[unit] plane -> zt plane
 template <int OP>
-__global__ void __launch_bounds__(416, 1) k_plane(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
+__global__ void __launch_bounds__(512, 1) k_plane(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
                                                    cplx* __restrict__ f, double* __restrict__ rho_part,
                                                    const double* __restrict__ fac, int nunits, int units_per_group,
                                                    int zero_imag)

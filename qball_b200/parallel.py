@@ -1,0 +1,32 @@
+"""Band (state) parallelism across the GPUs of one box: the reference's process grid with nprow = 1, npcol = #GPUs
+(Wavefunction.cc:262-271).  States are split in contiguous blocks of nb = ceil(nst/npcol) (SlaterDet.cc:228-231 with the
+default blocking); v(r), projector tables and plan tables are replicated; H psi needs no exchange; the density needs ONE
+all-reduce of rho(r) (ChargeDensity.cc:309, BLACS dsum over state columns) and the scalars (E_nl, NonLocalPotential.cc:2629;
+integral of rho, ChargeDensity.cc:528) one small all-reduce.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is
+the plumbing."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def state_block(nst: int, rank: int, world: int):
+    """(first, count) of the states owned by `rank`: block size nb = ceil(nst/world); trailing ranks may own fewer or none"""
+    nb = nst // world + (1 if nst % world else 0)
+    first = min(rank * nb, nst)
+    return first, max(0, min(nb, nst - first))
+
+
+def allreduce_density(rho: torch.Tensor, group=None) -> torch.Tensor:
+    """wfcontext->dsum('r', np012loc, 1, rhor) over the state-column ranks"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(rho, op=dist.ReduceOp.SUM, group=group)
+    return rho
+
+
+def allreduce_scalars(values, device=None, group=None):
+    """sum a short list of python floats over ranks (E_nl partials, integral of rho, ...)"""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [float(x) for x in t.cpu()]
