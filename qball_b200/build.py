@@ -1,14 +1,17 @@
-"""Builds libqball_b200.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc."""
+"""Builds libqball_b200.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc: one object per source, compiled
+in parallel, then linked."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libqball_b200.so")
-SOURCES = ["transform.cu", "nonlocal.cu", "hpsi.cu"]
+SOURCES = ["transform.cu", "plane.cu", "nonlocal.cu", "hpsi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 
@@ -25,16 +28,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or _stale()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc, "-shared", "-o", LIB] + NVCC_FLAGS + srcs + ["-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+    def compile_one(s):
+        o = os.path.join(OBJ, s.replace(".cu", ".o"))
+        cmd = [nvcc, "-c", "-o", o] + NVCC_FLAGS + [os.path.join(CSRC, s)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return s, o, cmd, r
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        results = list(ex.map(compile_one, srcs))
     log = os.path.join(PKG, "build.log")
+    failed = False
     with open(log, "w") as f:
+        for s, o, cmd, r in results:
+            f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            failed = failed or r.returncode != 0
+            if verbose or r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+    if failed:
+        raise RuntimeError(f"nvcc failed; see {log}")
+    cmd = [nvcc, "-shared", "-o", LIB] + [o for _, o, _, _ in results] + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(log, "a") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError(f"nvcc failed ({r.returncode}); see {log}")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"link failed; see {log}")
     return LIB
 
 

@@ -24,6 +24,7 @@ struct FftDesc {
   int n;
   int nf;
   int r[QB200_MAXF];
+  int len[QB200_MAXF];   // sub-transform length entering pass s: n / (r[0]*...*r[s-1])
 };
 
 // where line `l` starts: lines may be split in two blocks (kept rows [0,nt) and [np1-nt,np1) of a plane)

@@ -30,12 +30,27 @@ struct DevPlan {
   FftDesc f0, f1, f2;
   const cplx *tw0, *tw1, *tw2;
   const int *rod_first, *rod_size, *rod_lmin;
-  const int *colpos;                   // per column iv: kp*pitch0 + hp
+  int gthreads;                        // threads per group in the plane kernel (fft_group.cuh)
+  int nyrev_c;                         // 16-byte slots reserved for the yrev table in shared memory
+  int ncolpos_c;                       // 16-byte slots for the colpos table in shared memory (0: read it from global)
+  int stage_per;                       // plane kernel: column values per group staged ahead in dead rows (0: off)
+  const int *yrev;                     // natural y index of the first element of segment seg of the y mid pass
+  const int *colpos;                   // per column iv: kp*pitch0 + (digit-reversed x position of hp)
   const int *colhk;                    // per column iv: hp + np0*kp
   const int *keepcols, *keeprowstart;  // split path: columns sorted by kept row; start offsets per kept row (nkeep+1)
 };
 
+enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
+enum { OP_HPSI = 0, OP_DENSITY = 1, OP_BWD = 2, OP_FWD = 3 };
+
 }  // namespace qb200
+
+struct qb200_plan;
+namespace qb200 {
+// plane.cu: the plane-fused xy stage (own translation unit: its register budget is 144, the other kernels' is 128)
+int plane_opt_in(qb200_plan* p);
+int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, const double* fac, int nunits, int zero_imag);
+}
 
 struct qb200_plan {
   int device;

@@ -55,8 +55,22 @@ bool factorize(int n, FftDesc& d)
   for (int i = (int)f.size() - 1; i >= 0; i--)
     if (n / f[i] <= 256) { const int r = f[i]; f.erase(f.begin() + i); f.push_back(r); break; }
   d.nf = (int)f.size();
-  for (int i = 0; i < d.nf; i++) d.r[i] = f[i];
+  for (int i = 0, len = n; i < d.nf; i++) { d.r[i] = f[i]; d.len[i] = len; len /= f[i]; }
   return true;
+}
+
+// natural index held by in-place position q after a DIF transform with d's radices (fft_group.cuh)
+int digit_reverse(const FftDesc& d, int q)
+{
+  int div = d.n, nat = 0, mul = 1;
+  for (int i = 0; i < d.nf; i++) {
+    div /= d.r[i];
+    const int dig = q / div;
+    q -= dig * div;
+    nat += dig * mul;
+    mul *= d.r[i];
+  }
+  return nat;
 }
 
 std::vector<double> twiddle_table(int n)
@@ -154,6 +168,26 @@ static int configure_batch(qb200_plan* p)
   return QB200_OK;
 }
 
+// fused path: how many of the `remaining` units to take in the next batch (<= p->batch) and over how many persistent
+// CTAs per plane (grid.y = G <= maxG) to spread them, so that the np2*G CTAs fill whole waves of the nsm SMs (one CTA
+// per SM) and every CTA gets the same number of units
+static void plan_split(const qb200_plan* p, int remaining, int maxG, int* nb_out, int* G_out)
+{
+  const int np2 = p->d.np2, nsm = std::max(1, p->nsm);
+  const int nbmax = std::min(p->batch, remaining);
+  if (!p->fused) { *nb_out = nbmax; *G_out = 1; return; }
+  double best = -1.0; int bnb = nbmax, bG = 1;
+  const int nbmin = (nbmax == remaining) ? nbmax : std::max(1, (3 * nbmax) / 4);   // the last batch takes what is left
+  for (int nb = nbmax; nb >= nbmin; nb--)
+    for (int G = 1; G <= std::min(maxG, nb); G++) {
+      const long rounds = ((long)np2 * G + nsm - 1) / nsm;
+      const long upg = (nb + G - 1) / G;
+      const double eff = ((double)nb * np2 / nsm) / (double)(rounds * upg);
+      if (eff > best * (1.0 + 1e-9)) { best = eff; bnb = nb; bG = G; }
+    }
+  *nb_out = bnb; *G_out = bG;
+}
+
 static int ensure_work(qb200_plan* p, int units)
 {
   const DevPlan& d = p->d;
@@ -218,8 +252,14 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     }
   }
   d.ngw = ngw;
-  std::vector<int> colpos(d.nvec), colhk(d.nvec);
-  auto put = [&](int iv, int hp, int kp) { colpos[iv] = kp * d.pitch0 + hp; colhk[iv] = hp + np0 * kp; };
+  std::vector<int> colpos(d.nvec), colhk(d.nvec), xpos(np0), yrev;
+  for (int q = 0; q < np0; q++) xpos[digit_reverse(d.f0, q)] = q;   // x-rows are transformed DIT: scatter to digit-reversed x
+  {
+    const int rl = d.f1.r[d.f1.nf - 1];
+    for (int seg = 0; seg < np1 / rl; seg++) yrev.push_back(digit_reverse(d.f1, seg * rl));
+    d.nyrev_c = ((int)yrev.size() * 4 + 15) / 16;
+  }
+  auto put = [&](int iv, int hp, int kp) { colpos[iv] = kp * d.pitch0 + xpos[hp]; colhk[iv] = hp + np0 * kp; };
   for (int r = 0; r < nrods; r++) {                               // FourierTransform.cc:361-430, 484-506
     int hp = rod_h[r], kp = rod_k[r];
     if (hp < 0) hp += np0;
@@ -250,7 +290,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   }
   int rc;
   if ((rc = upload(p, first, &d.rod_first)) || (rc = upload(p, size, &d.rod_size)) || (rc = upload(p, lmin, &d.rod_lmin)) ||
-      (rc = upload(p, colpos, &d.colpos)) || (rc = upload(p, colhk, &d.colhk)) || (rc = upload(p, keepcols, &d.keepcols)) ||
+      (rc = upload(p, colpos, &d.colpos)) || (rc = upload(p, yrev, &d.yrev)) || (rc = upload(p, colhk, &d.colhk)) || (rc = upload(p, keepcols, &d.keepcols)) ||
       (rc = upload(p, rowstart, &d.keeprowstart))) { qb200_plan_destroy(p); return rc; }
   {
     const double* t;
@@ -272,7 +312,12 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   d.rb = is_real ? std::max(1, ncolmax / 2) : ncolmax;
   const int zcols = is_real ? 2 * d.rb : d.rb;
   p->smem_z = ((size_t)np2 + (size_t)zcols * pitch2) * 16;
-  p->smem_plane = ((size_t)np0 + np1 + (size_t)np1 * d.pitch0) * 16;
+  d.ncolpos_c = (d.nvec * 4 + 15) / 16;
+  p->smem_plane = ((size_t)np0 + np1 + d.nyrev_c + d.ncolpos_c + (size_t)np1 * d.pitch0) * 16;
+  if (p->smem_plane > (size_t)p->max_smem) {      // colpos stays in global memory
+    d.ncolpos_c = 0;
+    p->smem_plane = ((size_t)np0 + np1 + d.nyrev_c + (size_t)np1 * d.pitch0) * 16;
+  }
   const char* force_split = getenv("QB200_FORCE_SPLIT");
   p->fused = p->smem_plane <= (size_t)p->max_smem && !(force_split && force_split[0] == '1');
   d.xb = 16;
@@ -289,10 +334,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     qb200_plan_destroy(p); return rc;
   }
   if (p->fused) {
-    if ((rc = opt_in_smem(k_plane<OP_HPSI>, p->smem_plane)) || (rc = opt_in_smem(k_plane<OP_DENSITY>, p->smem_plane)) ||
-        (rc = opt_in_smem(k_plane<OP_BWD>, p->smem_plane)) || (rc = opt_in_smem(k_plane<OP_FWD>, p->smem_plane))) {
-      qb200_plan_destroy(p); return rc;
-    }
+    if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
   } else {
     if ((rc = opt_in_smem(k_xrows<+1>, p->smem_rows)) || (rc = opt_in_smem(k_xrows<-1>, p->smem_rows)) ||
         (rc = opt_in_smem(k_ycols<OP_HPSI>, p->smem_ycol)) || (rc = opt_in_smem(k_ycols<OP_DENSITY>, p->smem_ycol)) ||
@@ -300,31 +342,29 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       qb200_plan_destroy(p); return rc;
     }
   }
-  // plane kernel block size: the per-pass task counts rarely divide the block; pick the size (multiple of 32, <= 416 so
-  // that the radix-16 pass keeps its ~112 registers) that wastes the fewest FP64-pipe slots over one plane
+  // plane kernel geometry: groups of gthreads threads own blocks of 8 rows / 8 columns (fft_group.cuh); pick the number of
+  // groups (<= 7 x 64 = 448 threads so that the radix-16 pass keeps its ~112 registers) that needs the fewest rounds
   {
-    auto cost = [&](int b) {
-      double c = 0.0;
-      const FftDesc* fd[2] = { &d.f0, &d.f1 };
-      const int nl[2] = { d.nkeep, np0 };
-      for (int a = 0; a < 2; a++) {
-        const FftDesc& f = *fd[a];
-        for (int i = 0; i < f.nf; i++) {
-          const double w = f.r[i] * std::log2((double)std::max(f.r[i], 2));
-          long rounds;
-          if (i < f.nf - 1) rounds = ((long)nl[a] * (f.n / f.r[i]) + b - 1) / b;
-          else { const int tpl = f.n / f.r[i]; const int lpr = std::max(1, std::min(b / tpl, nl[a])); rounds = (nl[a] + lpr - 1) / lpr; }
-          c += rounds * w * b;
-        }
-      }
-      return c;
-    };
-    int best = 384;
-    for (int b = 256; b <= 512; b += 32) if (cost(b) < cost(best)) best = b;
-    if (const char* e = getenv("QB200_PLANE_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) best = t; }
-    p->plane_threads = best;
+    d.gthreads = 64;
+    if (const char* e = getenv("QB200_GROUP_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= 256 && t % 32 == 0) d.gthreads = t; }
+    const int maxg = std::max(1, std::min(15, 448 / d.gthreads));
+    const int by = (np0 + 7) / 8, bx = (d.nkeep + 7) / 8 + ((d.nkeep < np1 && d.ksplit % 8) ? 1 : 0);
+    const double wy = (double)np1, wx = (double)np0;
+    auto cost = [&](int g) { return ((by + g - 1) / g) * wy * 8 + ((bx + g - 1) / g) * wx * 8; };
+    int best = maxg;
+    for (int g = maxg; g >= 1; g--) if (cost(g) < cost(best) * (1.0 - 1e-9)) best = g;
+    p->plane_threads = best * d.gthreads;
+    if (const char* e = getenv("QB200_PLANE_THREADS")) {
+      const int t = atoi(e);
+      if (t >= d.gthreads && t <= 448 && t % d.gthreads == 0 && t / d.gthreads <= 15) p->plane_threads = t;
+    }
+    // staging of the next unit's column values in the dead (not kept) rows of each group's first column block
+    const int ngrp = p->plane_threads / d.gthreads;
+    const int per = (((d.nvec + ngrp - 1) / ngrp) + 7) / 8 * 8;
+    d.stage_per = (per <= d.kskip * 8 && ngrp * 8 <= np0) ? per : 0;
+    if (const char* e = getenv("QB200_NO_STAGE")) if (e[0] == '1') d.stage_per = 0;
   }
-  p->ws_bytes = p->fused ? (96ll << 20) : (3ll << 30);
+  p->ws_bytes = p->fused ? (256ll << 20) : (3ll << 30);
   if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
   configure_batch(p);
   *out = p;
@@ -414,11 +454,12 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
   const int upg = (OP == OP_DENSITY) ? (nunits + ngroups - 1) / ngroups : 1;
   const int ng = (OP == OP_DENSITY) ? ngroups : nunits;
   if (p->fused) {
-    dim3 g(d.np2, ng);
+    dim3 g(d.np2, std::max(1, std::min(ngroups, nunits)));
     prof_begin(1, p->stream);
-    k_plane<OP><<<g, p->plane_threads, p->smem_plane, p->stream>>>(d, (cplx*)p->zt, v, (cplx*)f, p->rho_part, fac, nunits, upg, zero_imag);
+    const int rc = launch_plane(p, OP, g, v, f, fac, nunits, zero_imag);
     prof_end(p->stream);
-    QB_LAUNCH_CHECK(p);
+    if (rc) return rc;
+    p->launches++;
     return QB200_OK;
   }
   const int rowb = (int)((p->smem_rows / 16 - d.np0) / d.pitch0);
@@ -522,14 +563,16 @@ int qb200_rs_mul_add_dev(qb200_plan* p, int ldc, int nst, const double* c, const
   int rc;
   auto run = [&](int first_state, int nunits, int mode, int zero_imag) -> int {
     const int spu = mode == MODE_PAIR ? 2 : 1;
-    for (int b0 = 0; b0 < nunits; b0 += p->batch) {
-      const int nb = std::min(p->batch, nunits - b0);
+    for (int b0 = 0; b0 < nunits;) {
+      int nb, G;
+      plan_split(p, nunits - b0, 64, &nb, &G);
       int r = ensure_work(p, nb);
       if (r) return r;
       const size_t off = 2 * (size_t)(first_state + b0 * spu) * ldc;
       if ((r = launch_zbwd(p, mode, c + off, ldc, nb))) return r;
-      if ((r = launch_xy<OP_HPSI>(p, nb, v, nullptr, nullptr, 1, zero_imag))) return r;
+      if ((r = launch_xy<OP_HPSI>(p, nb, v, nullptr, nullptr, G, zero_imag))) return r;
       if ((r = launch_zfwd(p, mode, cp + off, ldc, nb, 1, kpg2, kpg2 ? c + off : nullptr))) return r;
+      b0 += nb;
     }
     return QB200_OK;
   };
@@ -582,16 +625,18 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   if ((rc = ensure(&p->fac_dev, &p->fac_cap, nst))) return rc;
   QB_CUDA(cudaMemcpyAsync(p->fac_dev, fac, nst * sizeof(double), cudaMemcpyDefault, p->stream));
   // groups: exclusive owners of a partial density each; enough CTAs to fill the machine
-  const int nb_max = std::min(p->batch, nst);
+  const int maxG = 16;
   int ngroups = 1;
-  if (p->fused) ngroups = std::max(1, std::min(nb_max, (2 * p->nsm + d.np2 - 1) / d.np2));
+  for (int b0 = 0; b0 < nst;) { int nb, G; plan_split(p, nst - b0, maxG, &nb, &G); ngroups = std::max(ngroups, G); b0 += nb; }
   if ((rc = ensure(&p->rho_part, &p->rho_part_elems, (size_t)ngroups * N))) return rc;
   QB_CUDA(cudaMemsetAsync(p->rho_part, 0, (size_t)ngroups * N * sizeof(double), p->stream));
-  for (int b0 = 0; b0 < nst; b0 += p->batch) {
-    const int nb = std::min(p->batch, nst - b0);
+  for (int b0 = 0; b0 < nst;) {
+    int nb, G;
+    plan_split(p, nst - b0, maxG, &nb, &G);
     if ((rc = ensure_work(p, nb))) return rc;
     if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
-    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, ngroups, 0))) return rc;
+    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, p->fused ? G : 1, 0))) return rc;
+    b0 += nb;
   }
   prof_begin(6, p->stream);
   k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);

@@ -5,9 +5,7 @@
 //   k_zcol_bwd   sphere scatter (vector_to_zvec / doublevector_to_zvec, FourierTransform.cc:1624-1720) + z-FFT(+1);
 //                writes the column-form intermediate TRANSPOSED, zt[unit][z][iv], so that the xy stage reads each
 //                plane's nvec values contiguously.  Zero columns of the grid are never touched.
-//   k_plane<OP>  (plane-fused path: one xy-plane in shared memory)  fill -> pruned x-FFT -> y-FFT -> OP ->
-//                y-FFT -> pruned x-FFT -> gather, OP = v(r) multiply (SlaterDet.cc:993-1031), |psi|^2 accumulate
-//                (SlaterDet.cc:919-921), or plain backward / forward.
+//   k_plane2<OP> (plane-fused path: one xy-plane in shared memory) lives in plane_kernels.cuh / plane.cu.
 //   k_xrows_*, k_ycols<OP>  (split path for planes larger than shared memory, e.g. Au 252x252): the same three
 //                phases as separate kernels with a compact kept-rows intermediate w[unit][z][jr][x].
 //   k_zcol_fwd   z-FFT(-1), 1/N scale (FourierTransform.cc:1338-1342), sphere gather (zvec_to_vector /
@@ -17,9 +15,6 @@
 #include "qb200_internal.h"
 
 namespace qb200 {
-
-enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
-enum { OP_HPSI = 0, OP_DENSITY = 1, OP_BWD = 2, OP_FWD = 3 };
 
 __device__ __forceinline__ int colfirst(const DevPlan& P, int r) { return P.is_real ? (r == 0 ? 0 : 2 * r - 1) : r; }
 
@@ -139,115 +134,6 @@ __global__ void __launch_bounds__(256, 2) k_zcol_fwd(const __grid_constant__ Dev
       }
       o1[ig] = v1;
       if (MODE == MODE_PAIR) o2[ig] = v2;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ fused xy plane
-// grid (np2, ngroups); block plan->plane_threads (<= 416); dynamic smem: np0 + np1 + np1*pitch0 complex.
-//   OP_HPSI    : zt plane -> psi(r) -> * v -> zt plane (in place).  zero_imag: the Gamma odd-tail rule (SlaterDet.cc:1015)
-//   OP_DENSITY : CTA walks the units of its group; rho_part[group][i] += fac[unit]*|psi|^2 (exclusive owner, no atomics)
-//   OP_BWD     : zt plane -> f[unit] plane
-//   OP_FWD     : f[unit] plane -> zt plane
-template <int OP>
-__global__ void __launch_bounds__(512, 1) k_plane(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
-                                                   cplx* __restrict__ f, double* __restrict__ rho_part,
-                                                   const double* __restrict__ fac, int nunits, int units_per_group,
-                                                   int zero_imag)
-{
-  extern __shared__ __align__(16) unsigned char smraw[];
-  cplx* tw0 = reinterpret_cast<cplx*>(smraw);
-  cplx* tw1 = tw0 + P.np0;
-  cplx* pl = tw1 + P.np1;
-  const int np0 = P.np0, np1 = P.np1, pitch = P.pitch0, np01 = np0 * np1;
-  const int z = blockIdx.x;
-  const size_t N = (size_t)np01 * P.np2;
-  load_tw(tw0, P.tw0, np0);
-  load_tw(tw1, P.tw1, np1);
-  const LineMap rows = { pitch, P.ksplit, P.kskip };
-  const LineMap cols = { 1, np0, 0 };
-  const int u0 = blockIdx.y * units_per_group;
-  const int u1 = min(u0 + units_per_group, nunits);
-  const FastDiv d0(np0);
-  constexpr int U = 8;                       // loads in flight per thread in the global-memory phases
-  for (int unit = u0; unit < u1; unit++) {
-    double facu = 0.0;
-    if (OP == OP_DENSITY) { facu = fac[unit]; if (!(facu > 0.0)) continue; }
-    cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * P.nvec;
-    __syncthreads();   // previous unit's readers are done with the plane
-    if (OP != OP_FWD) {
-      for (int i = threadIdx.x; i < np1 * pitch; i += blockDim.x) pl[i] = make_double2(0.0, 0.0);
-      __syncthreads();
-      for (int i0 = threadIdx.x; i0 < P.nvec; i0 += U * blockDim.x) {
-        cplx val[U]; int pos[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) { const int i = min(i0 + u * (int)blockDim.x, P.nvec - 1); val[u] = ztrow[i]; pos[u] = P.colpos[i]; }
-#pragma unroll
-        for (int u = 0; u < U; u++) { const int i = i0 + u * blockDim.x; if (i < P.nvec) pl[pos[u]] = val[u]; }
-      }
-      __syncthreads();
-      fft_lines<+1>(pl, P.nkeep, rows, 1, P.f0, tw0);
-      fft_lines<+1>(pl, np0, cols, pitch, P.f1, tw1);
-    }
-    if (OP == OP_HPSI) {
-      const double* vz = v + (size_t)z * np01;
-      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
-        double vv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) vv[u] = vz[min(e0 + u * (int)blockDim.x, np01 - 1)];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int e = e0 + u * blockDim.x;
-          if (e < np01) {
-            int x; const int y = d0.div(e, x);
-            cplx t = pl[y * pitch + x];
-            t.x *= vv[u];
-            t.y = zero_imag ? 0.0 : t.y * vv[u];
-            pl[y * pitch + x] = t;
-          }
-        }
-      }
-      __syncthreads();
-    } else if (OP == OP_DENSITY) {
-      double* rz = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01;
-      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
-        double rr[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) rr[u] = rz[min(e0 + u * (int)blockDim.x, np01 - 1)];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int e = e0 + u * blockDim.x;
-          if (e < np01) {
-            int x; const int y = d0.div(e, x);
-            const cplx t = pl[y * pitch + x];
-            rz[e] = rr[u] + facu * (t.x * t.x + t.y * t.y);
-          }
-        }
-      }
-    } else if (OP == OP_BWD) {
-      cplx* fz = f + (size_t)unit * N + (size_t)z * np01;
-      for (int e = threadIdx.x; e < np01; e += blockDim.x) {
-        int x; const int y = d0.div(e, x);
-        fz[e] = pl[y * pitch + x];
-      }
-    } else if (OP == OP_FWD) {
-      const cplx* fz = f + (size_t)unit * N + (size_t)z * np01;
-      for (int e0 = threadIdx.x; e0 < np01; e0 += U * blockDim.x) {
-        cplx val[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) val[u] = fz[min(e0 + u * (int)blockDim.x, np01 - 1)];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int e = e0 + u * blockDim.x;
-          if (e < np01) { int x; const int y = d0.div(e, x); pl[y * pitch + x] = val[u]; }
-        }
-      }
-      __syncthreads();
-    }
-    if (OP == OP_HPSI || OP == OP_FWD) {
-      fft_lines<-1>(pl, np0, cols, pitch, P.f1, tw1);
-      fft_lines<-1>(pl, P.nkeep, rows, 1, P.f0, tw0);
-      for (int i = threadIdx.x; i < P.nvec; i += blockDim.x) ztrow[i] = pl[P.colpos[i]];
     }
   }
 }
