@@ -49,10 +49,11 @@ int qb200_plan_create(qb200_plan** plan, int device, int np0, int np1, int np2, 
 int qb200_plan_destroy(qb200_plan* plan);
 /* work on this CUDA stream (cudaStream_t as void*); default is the legacy default stream */
 int qb200_plan_set_stream(qb200_plan* plan, void* cuda_stream);
-/* bytes of device scratch for the column-form intermediate (default 96 MiB); bounds the number of states per batch */
+/* bytes of device scratch for the column-form intermediate (default 256 MiB); bounds the number of states per batch */
 int qb200_plan_set_workspace(qb200_plan* plan, long long bytes);
 /* queries: 0 np0, 1 np1, 2 np2, 3 nvec, 4 ntrans0, 5 ngw, 6 is_real, 7 plane-fused path in use (1) or split path (0),
- *          8 states per batch, 9 kernels launched since creation (for bench gpu_launches) */
+ *          8 states per batch, 9 kernels launched since creation (for bench gpu_launches),
+ *          10 plane kernel in use: 0 generic, > 0 index of the compiled grid shape (plane.cu) */
 long long qb200_plan_query(const qb200_plan* plan, int what);
 
 /* ---- FourierTransform::backward(const complex<double>* c, complex<double>* f)       FourierTransform.cc:529-539

@@ -14,6 +14,7 @@
 //     accumulate, first DIT butterfly -- all in registers), and scatter/gather tables absorb the permutation at the
 //     sphere side.  Position q = d0*(n/r0) + d1*(n/(r0 r1)) + ... + d_{f-1} holds natural index
 //     d0 + r0*(d1 + r1*(d2 + ...)).
+//   * twiddles come from a packed per-pass table (fft_desc.h): the r-1 factors of a task are contiguous;
 //   * the first DIF pass / last DIT pass can skip rows known to be zero / not needed (the reference's ntrans0 pruning,
 //     FourierTransform.cc:202, 772-819, applied to the y direction as well).
 #pragma once
@@ -47,7 +48,6 @@ __device__ __noinline__ void radix_pass(Grp g, cplx* base, int nlines, int nlpad
 {
   const int m = len / R;
   const int ntask = (n / R) * nlpad;
-  const int twmul = n / len;
   const FastDiv dm(m), dl(nlpad);
   const int step = m * estride;
   for (int task = g.tid; task < ntask; task += g.nthr) {
@@ -64,11 +64,11 @@ __device__ __noinline__ void radix_pass(Grp g, cplx* base, int nlines, int nlpad
 #pragma unroll
       for (int k = 0; k < R; k++) x[k] = p[k * step];
     }
-    const int tws = t * twmul;
+    const cplx* twt = tw + t * (R - 1) - 1;      // packed: entry (t, k) at t*(R-1) + k-1
     if (DIT && m > 1) {
 #pragma unroll
       for (int k = 1; k < R; k++) {
-        const cplx w = tw[k * tws];
+        const cplx w = twt[k];
         x[k] = cmul_s<S>(x[k], w.x, w.y);
       }
     }
@@ -76,7 +76,7 @@ __device__ __noinline__ void radix_pass(Grp g, cplx* base, int nlines, int nlpad
     if (!DIT && m > 1) {
 #pragma unroll
       for (int k = 1; k < R; k++) {
-        const cplx w = tw[k * tws];
+        const cplx w = twt[k];
         x[k] = cmul_s<S>(x[k], w.x, w.y);
       }
     }
@@ -116,7 +116,7 @@ __device__ __forceinline__ void fft_block_dif(Grp g, cplx* base, int nlines, int
 {
   for (int s = first_pass; s < first_pass + npass; s++) {
     if (s > first_pass) g.sync();
-    radix_pass_any<S, false>(d.r[s], g, base, nlines, nlpad, lm, estride, d.n, d.len[s], tw, prune && s == 0, kp);
+    radix_pass_any<S, false>(d.r[s], g, base, nlines, nlpad, lm, estride, d.n, d.len[s], tw + d.twoff[s], prune && s == 0, kp);
   }
 }
 
@@ -127,7 +127,7 @@ __device__ __forceinline__ void fft_block_dit(Grp g, cplx* base, int nlines, int
 {
   for (int s = last_pass; s >= 0; s--) {
     if (s < last_pass) g.sync();
-    radix_pass_any<S, true>(d.r[s], g, base, nlines, nlpad, lm, estride, d.n, d.len[s], tw, prune && s == 0, kp);
+    radix_pass_any<S, true>(d.r[s], g, base, nlines, nlpad, lm, estride, d.n, d.len[s], tw + d.twoff[s], prune && s == 0, kp);
   }
 }
 

@@ -15,17 +15,9 @@
 // columns staged x-fastest) every quarter-warp touches 8 distinct 16-byte bank groups -> conflict-free LDS/STS.128.
 #pragma once
 #include "fft_radix.cuh"
+#include "fft_desc.h"
 
 namespace qb200 {
-
-#define QB200_MAXF 8
-
-struct FftDesc {
-  int n;
-  int nf;
-  int r[QB200_MAXF];
-  int len[QB200_MAXF];   // sub-transform length entering pass s: n / (r[0]*...*r[s-1])
-};
 
 // where line `l` starts: lines may be split in two blocks (kept rows [0,nt) and [np1-nt,np1) of a plane)
 struct LineMap {

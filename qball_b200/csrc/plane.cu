@@ -1,14 +1,40 @@
 // qball_b200/csrc/plane.cu -- instantiation and launch of the plane-fused xy kernels (plane_kernels.cuh).
 // Own translation unit: the __noinline__ radix passes are shared by all kernels of a translation unit and compiled
 // for the tightest register budget among them; here that is 65536/448 = 144 registers (128 elsewhere).
-#include "plane_kernels.cuh"
+#include "plane_static.cuh"
+#include <cstdlib>
 
 namespace qb200 {
+
+// shapes compiled in (PlaneShape<np0, np1, xsplit, xskip, ysplit, yskip, groups, threads per group>)
+typedef PlaneShape<112, 112, 26, 60, 26, 60, 7, 64> ShapeMgO216;   // examples/MgO216: 112^3 grid, |h|,|k| <= 25
+
+// 0: generic kernel; > 0: index of the compiled shape that matches the plan (hmax = max |rod_h|)
+int plane_select_static(const qb200_plan* p, int hmax)
+{
+  if (const char* e = getenv("QB200_NO_STATIC")) if (e[0] == '1') return 0;
+  const DevPlan& d = p->d;
+  typedef ShapeMgO216 S;
+  if (d.np0 == S::NP0 && d.np1 == S::NP1 && d.ksplit == S::YSPLIT && d.kskip == S::YSKIP && hmax < S::XSPLIT &&
+      p->plane_threads == S::NTHR && d.gthreads == S::GT) return 1;
+  return 0;
+}
+
+template <class K> static int opt_in(K kernel, int bytes)
+{
+  QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return QB200_OK;
+}
 
 int plane_opt_in(qb200_plan* p)
 {
   const int bytes = (int)p->smem_plane;
   if (bytes <= 48 * 1024) return QB200_OK;
+  if (p->static_shape == 1) {
+    int rc;
+    if ((rc = opt_in(k_plane_s<OP_HPSI, ShapeMgO216>, bytes)) || (rc = opt_in(k_plane_s<OP_DENSITY, ShapeMgO216>, bytes)) ||
+        (rc = opt_in(k_plane_s<OP_BWD, ShapeMgO216>, bytes)) || (rc = opt_in(k_plane_s<OP_FWD, ShapeMgO216>, bytes))) return rc;
+  }
   QB_CUDA(cudaFuncSetAttribute(k_plane2<OP_HPSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   QB_CUDA(cudaFuncSetAttribute(k_plane2<OP_DENSITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   QB_CUDA(cudaFuncSetAttribute(k_plane2<OP_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -20,6 +46,18 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
 {
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
+  if (p->static_shape == 1) {
+    typedef ShapeMgO216 S;
+    switch (op) {
+      case OP_HPSI: k_plane_s<OP_HPSI, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      case OP_DENSITY: k_plane_s<OP_DENSITY, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      case OP_BWD: k_plane_s<OP_BWD, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      default: k_plane_s<OP_FWD, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_plane_s launch", __FILE__, __LINE__);
+    return QB200_OK;
+  }
   switch (op) {
     case OP_HPSI: k_plane2<OP_HPSI><<<grid, p->plane_threads, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
     case OP_DENSITY: k_plane2<OP_DENSITY><<<grid, p->plane_threads, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;

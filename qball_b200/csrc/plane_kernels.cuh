@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(448, 1) k_plane2(const __grid_constant__ DevPl
 {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx* tw0 = reinterpret_cast<cplx*>(smraw);
-  cplx* tw1 = tw0 + P.np0;
-  int* yrev = reinterpret_cast<int*>(tw1 + P.np1);
-  int* colpos_s = reinterpret_cast<int*>(tw1 + P.np1 + P.nyrev_c);
-  cplx* pl = tw1 + P.np1 + P.nyrev_c + P.ncolpos_c;
+  cplx* tw1 = tw0 + P.f0.twsize;
+  int* yrev = reinterpret_cast<int*>(tw1 + P.f1.twsize);
+  int* colpos_s = reinterpret_cast<int*>(tw1 + P.f1.twsize + P.nyrev_c);
+  cplx* pl = tw1 + P.f1.twsize + P.nyrev_c + P.ncolpos_c;
   const int np0 = P.np0, np1 = P.np1, pitch = P.pitch0, np01 = np0 * np1, nvec = P.nvec;
   const int z = blockIdx.x;
   const size_t N = (size_t)np01 * P.np2;
-  for (int i = threadIdx.x; i < np0; i += blockDim.x) tw0[i] = P.tw0[i];
-  for (int i = threadIdx.x; i < np1; i += blockDim.x) tw1[i] = P.tw1[i];
+  for (int i = threadIdx.x; i < P.f0.twsize; i += blockDim.x) tw0[i] = P.tw0p[i];
+  for (int i = threadIdx.x; i < P.f1.twsize; i += blockDim.x) tw1[i] = P.tw1p[i];
   const int rl = P.f1.r[P.f1.nf - 1];
   for (int i = threadIdx.x; i < np1 / rl; i += blockDim.x) yrev[i] = P.yrev[i];
   if (P.ncolpos_c) for (int i = threadIdx.x; i < nvec; i += blockDim.x) colpos_s[i] = P.colpos[i];

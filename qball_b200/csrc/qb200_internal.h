@@ -17,6 +17,7 @@ bool is_device_ptr(const void* p);
 void prof_begin(int cat, cudaStream_t s);
 void prof_end(cudaStream_t s);
 bool factorize(int n, FftDesc& d);
+std::vector<double> packed_twiddle_table(const FftDesc& d);
 std::vector<double> twiddle_table(int n);   // 2n doubles: cos, sin (2 pi j / n), long-double accurate
 
 // device-side view of a plan (passed by value to kernels)
@@ -28,7 +29,8 @@ struct DevPlan {
   int rb;                              // rods per z-column CTA
   int xb;                              // x columns per CTA in the split path
   FftDesc f0, f1, f2;
-  const cplx *tw0, *tw1, *tw2;
+  const cplx *tw0, *tw1, *tw2;         // natural twiddle tables w_n^j (first-generation engine)
+  const cplx *tw0p, *tw1p, *tw2p;      // packed per-pass twiddle tables (fft_desc.h)
   const int *rod_first, *rod_size, *rod_lmin;
   int gthreads;                        // threads per group in the plane kernel (fft_group.cuh)
   int nyrev_c;                         // 16-byte slots reserved for the yrev table in shared memory
@@ -49,6 +51,7 @@ struct qb200_plan;
 namespace qb200 {
 // plane.cu: the plane-fused xy stage (own translation unit: its register budget is 144, the other kernels' is 128)
 int plane_opt_in(qb200_plan* p);
+int plane_select_static(const qb200_plan* p, int hmax);
 int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, const double* fac, int nunits, int zero_imag);
 }
 
@@ -73,4 +76,5 @@ struct qb200_plan {
   int max_smem;
   int nsm;
   int plane_threads;
+  int static_shape;                    // plane.cu: 0 generic kernel, > 0 compiled shape index
 };

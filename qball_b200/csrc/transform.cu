@@ -31,46 +31,29 @@ bool is_device_ptr(const void* p)
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// radices descending: the twiddled DIF passes take the big radices (no spills at 112 registers), the last
-// (permuting) pass the smallest
 bool factorize(int n, FftDesc& d)
 {
-  d.n = n; d.nf = 0;
-  if (n < 1) return false;
-  int m = n;
-  std::vector<int> f;
-  const int primes[3] = { 11, 7, 5 };
-  for (int p : primes) while (m % p == 0) { f.push_back(p); m /= p; }
-  while (m % 9 == 0) { f.push_back(9); m /= 9; }
-  while (m % 3 == 0) { f.push_back(3); m /= 3; }
-  while (m % 16 == 0) { f.push_back(16); m /= 16; }
-  if (m % 8 == 0) { f.push_back(8); m /= 8; }
-  if (m % 4 == 0) { f.push_back(4); m /= 4; }
-  if (m % 2 == 0) { f.push_back(2); m /= 2; }
-  if (m != 1) return false;
-  if (f.empty()) f.push_back(1);
-  if ((int)f.size() > QB200_MAXF) return false;
-  std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
-  // the last pass needs n/r tasks per line in one round of <= 256 threads: take the smallest radix that allows it
-  for (int i = (int)f.size() - 1; i >= 0; i--)
-    if (n / f[i] <= 256) { const int r = f[i]; f.erase(f.begin() + i); f.push_back(r); break; }
-  d.nf = (int)f.size();
-  for (int i = 0, len = n; i < d.nf; i++) { d.r[i] = f[i]; d.len[i] = len; len /= f[i]; }
-  return true;
+  d = make_fft_desc(n);
+  return d.nf > 0;
 }
 
-// natural index held by in-place position q after a DIF transform with d's radices (fft_group.cuh)
-int digit_reverse(const FftDesc& d, int q)
+// packed per-pass twiddles (fft_desc.h): entry (t, k) of pass s = (cos, sin)(2 pi k t / len_s)
+std::vector<double> packed_twiddle_table(const FftDesc& d)
 {
-  int div = d.n, nat = 0, mul = 1;
-  for (int i = 0; i < d.nf; i++) {
-    div /= d.r[i];
-    const int dig = q / div;
-    q -= dig * div;
-    nat += dig * mul;
-    mul *= d.r[i];
+  std::vector<double> t(2 * (size_t)d.twsize, 0.0);
+  t[0] = 1.0;
+  for (int s = 0; s < d.nf; s++) {
+    const int r = d.r[s], len = d.len[s], m = len / r;
+    if (m <= 1) continue;
+    for (int tt = 0; tt < m; tt++)
+      for (int k = 1; k < r; k++) {
+        const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)((long)k * tt % len) / (long double)len;
+        const size_t i = (size_t)d.twoff[s] + (size_t)tt * (r - 1) + (k - 1);
+        t[2 * i] = (double)cosl(a);
+        t[2 * i + 1] = (double)sinl(a);
+      }
   }
-  return nat;
+  return t;
 }
 
 std::vector<double> twiddle_table(int n)
@@ -182,7 +165,8 @@ static void plan_split(const qb200_plan* p, int remaining, int maxG, int* nb_out
     for (int G = 1; G <= std::min(maxG, nb); G++) {
       const long rounds = ((long)np2 * G + nsm - 1) / nsm;
       const long upg = (nb + G - 1) / G;
-      const double eff = ((double)nb * np2 / nsm) / (double)(rounds * upg);
+      // a CTA pays ~0.4 unit-times of prologue (tables, first exposed fill) before its first unit
+      const double eff = ((double)nb * np2 / nsm) / ((double)rounds * (upg + 0.4));
       if (eff > best * (1.0 + 1e-9)) { best = eff; bnb = nb; bG = G; }
     }
   *nb_out = bnb; *G_out = bG;
@@ -300,6 +284,12 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     d.tw1 = (const cplx*)t;
     if ((rc = upload(p, twiddle_table(np2), &t))) { qb200_plan_destroy(p); return rc; }
     d.tw2 = (const cplx*)t;
+    if ((rc = upload(p, packed_twiddle_table(d.f0), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw0p = (const cplx*)t;
+    if ((rc = upload(p, packed_twiddle_table(d.f1), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw1p = (const cplx*)t;
+    if ((rc = upload(p, packed_twiddle_table(d.f2), &t))) { qb200_plan_destroy(p); return rc; }
+    d.tw2p = (const cplx*)t;
   }
   // launch geometry
   cudaDeviceProp prop;
@@ -313,10 +303,10 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   const int zcols = is_real ? 2 * d.rb : d.rb;
   p->smem_z = ((size_t)np2 + (size_t)zcols * pitch2) * 16;
   d.ncolpos_c = (d.nvec * 4 + 15) / 16;
-  p->smem_plane = ((size_t)np0 + np1 + d.nyrev_c + d.ncolpos_c + (size_t)np1 * d.pitch0) * 16;
+  p->smem_plane = ((size_t)d.f0.twsize + d.f1.twsize + d.nyrev_c + d.ncolpos_c + (size_t)np1 * d.pitch0) * 16;
   if (p->smem_plane > (size_t)p->max_smem) {      // colpos stays in global memory
     d.ncolpos_c = 0;
-    p->smem_plane = ((size_t)np0 + np1 + d.nyrev_c + (size_t)np1 * d.pitch0) * 16;
+    p->smem_plane = ((size_t)d.f0.twsize + d.f1.twsize + d.nyrev_c + (size_t)np1 * d.pitch0) * 16;
   }
   const char* force_split = getenv("QB200_FORCE_SPLIT");
   p->fused = p->smem_plane <= (size_t)p->max_smem && !(force_split && force_split[0] == '1');
@@ -334,7 +324,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     qb200_plan_destroy(p); return rc;
   }
   if (p->fused) {
-    if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
+    // (opt-in for the plane kernels happens after the thread geometry is chosen, below)
   } else {
     if ((rc = opt_in_smem(k_xrows<+1>, p->smem_rows)) || (rc = opt_in_smem(k_xrows<-1>, p->smem_rows)) ||
         (rc = opt_in_smem(k_ycols<OP_HPSI>, p->smem_ycol)) || (rc = opt_in_smem(k_ycols<OP_DENSITY>, p->smem_ycol)) ||
@@ -363,6 +353,13 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     const int per = (((d.nvec + ngrp - 1) / ngrp) + 7) / 8 * 8;
     d.stage_per = (per <= d.kskip * 8 && ngrp * 8 <= np0) ? per : 0;
     if (const char* e = getenv("QB200_NO_STAGE")) if (e[0] == '1') d.stage_per = 0;
+  }
+  p->static_shape = 0;
+  if (p->fused) {
+    int hmax = 0;
+    for (int r = 0; r < nrods; r++) hmax = std::max(hmax, std::abs(rod_h[r]));
+    p->static_shape = plane_select_static(p, hmax);
+    if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
   }
   p->ws_bytes = p->fused ? (256ll << 20) : (3ll << 30);
   if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
@@ -410,6 +407,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 7: return p->fused ? 1 : 0;
     case 8: return p->batch;
     case 9: return p->launches;
+    case 10: return p->static_shape;
     default: return -1;
   }
 }

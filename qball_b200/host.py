@@ -45,6 +45,7 @@ class FourierTransform:
     def fused(self): return bool(self._L.qb200_plan_query(self._h, 7))
     def batch(self): return int(self._L.qb200_plan_query(self._h, 8))
     def launches(self): return int(self._L.qb200_plan_query(self._h, 9))
+    def query(self, what): return int(self._L.qb200_plan_query(self._h, int(what)))
 
     def set_stream(self, stream):
         s = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)

@@ -77,6 +77,22 @@ def test_cuda_vs_reference_fixture_host_pointers(name, monkeypatch):
     _run_fixture(name, False, False, monkeypatch)
 
 
+def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
+    """the MgO216 grid runs the shape-specialised plane kernel; the generic kernel must give the same answers there"""
+    g = load_golden("mgo216_shape_112cubed")
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(10) == 1, "MgO216 plan did not select the compiled shape"
+    del ft
+    monkeypatch.setenv("QB200_NO_STATIC", "1")
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(10) == 0
+    del ft
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+    monkeypatch.setenv("QB200_NO_STAGE", "1")
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+
+
 @pytest.mark.parametrize("name", ["gamma_triclinic_si_h", "kpoint_cubic_au_oncv", "sih4_60cubed"])
 def test_cuda_split_path_vs_reference_fixture(name, monkeypatch):
     """the split (large-plane) kernels, forced on small grids"""
