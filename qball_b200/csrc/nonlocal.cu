@@ -6,7 +6,7 @@
 // cp += anl (wt/omega fnl) (:2150-2171).  Here anl is never stored: both GEMM kernels regenerate their anl tiles on the
 // fly (one FP64 sincos per (atom, G) per tile, shared by the atom's projectors) straight into shared memory and feed
 // mma.sync.m8n8k4.f64 (DMMA -- tcgen05 has no FP64 kind).  Complex arithmetic is mapped on real DMMA:
-//   k_fnl : out[p, (n,re|im)] = sum_k A[p][k] B[k][(n,re|im)],  k over the 2*ngw reals, B = [c_n, J c_n]
+//   k_fnl : out[(p,re|im), n] = sum_k A[(p,.)][k] B[k][n],  k over the 2*ngw reals (g,re),(g,im), B = c as stored
 //   k_back: cp[(g,re|im), n] += sum_{(p,re|im)} A2[(g,.)][(p,.)] f'[(p,.), n]
 // At the Gamma point both are plain real GEMMs over the 2*ngw reals with the G=0 half weight (:2070-2082) folded
 // into k_fnl's tile generation and the factor 2 (:2102) into the epilogue.
@@ -19,15 +19,38 @@
 
 namespace qb200 {
 
-#define NL_PITCH 36            // doubles per shared-memory tile row: 32 + 4 -> conflict-free DMMA fragment loads
-#define NL_KSTEP 32            // reals of the reduction dimension per stage
-#define NL_SMEM_BYTES (192 * NL_PITCH * 8)
+// Tile geometry of both GEMM kernels: CTA = 512 threads = 16 warps (4 x 4), warp tile 32 x 32 (16 m8n8 accumulators),
+// CTA tile 128 x 128 reals, 32 reals of the reduction dimension per stage, two stages of shared memory:
+// while the tensor pipe works on stage s, the FP64 pipe generates the anl tile of stage s+1 (sincos) and cp.async
+// brings in its B tile -- one __syncthreads per stage.
+#define NL_TM 128
+#define NL_TN 128
+#define NL_KSTEP 32
+#define NL_THREADS 512
+#define NL_PITCH 36            // doubles per row of a [row][k] tile: 32 + 4 -> conflict-free DMMA fragment loads
+#define NL_PITCH_KR 132        // doubles per k-row of a [k][row] tile: 128 + 4 (same property, k-major)
+#define NL_NPRMAX 32           // projectors per atom whose twnl values are staged in shared memory (more: read from global)
+#define NL_TAUMAX 1024         // atoms whose positions are staged in shared memory by k_back (more: read from global)
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// 16/8-byte asynchronous copies global -> shared; !valid copies nothing and writes zeros
+__device__ __forceinline__ void nl_cp16(void* smem, const void* gmem, bool valid)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void nl_cp8(void* smem, const void* gmem, bool valid)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void nl_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // anl = t * (-i)^l * (c + i s)     (NonLocalPotential.cc:2002-2034)
 __device__ __forceinline__ double2 anl_value(int l, double t, double s, double c)
@@ -48,17 +71,21 @@ struct NlSpecies {
   const double* tau;              // [na][3]
 };
 
-// warp-level 32x32 tile: acc[i][j] is the m8n8 tile (i,j); As rows = M index, Bs rows = N index, both k-contiguous
-__device__ __forceinline__ void warp_mma_32x32(const double* As, const double* Bs, double (&acc)[4][4][2], int lane)
+// one stage of the warp tile: acc[i][j] += A(32 x 32 reals) * B(32 x 32 reals)
+template <bool A_KMAJOR>
+__device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][4][2],
+                                               int lane, int wm, int wn)
 {
   const int r = lane >> 2, kq = lane & 3;
+  const double* a0 = A_KMAJOR ? As + kq * NL_PITCH_KR + wm * 32 + r : As + (wm * 32 + r) * NL_PITCH + kq;
+  const double* b0 = Bs + (wn * 32 + r) * NL_PITCH + kq;
 #pragma unroll
   for (int k4 = 0; k4 < NL_KSTEP / 4; k4++) {
     double a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = As[(i * 8 + r) * NL_PITCH + k4 * 4 + kq];
+    for (int i = 0; i < 4; i++) a[i] = A_KMAJOR ? a0[k4 * 4 * NL_PITCH_KR + i * 8] : a0[i * 8 * NL_PITCH + k4 * 4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) b[j] = Bs[(j * 8 + r) * NL_PITCH + k4 * 4 + kq];
+    for (int j = 0; j < 4; j++) b[j] = b0[j * 8 * NL_PITCH + k4 * 4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -66,79 +93,120 @@ __device__ __forceinline__ void warp_mma_32x32(const double* As, const double* B
   }
 }
 
+// shared-memory layout of k_fnl (doubles)
+#define FNL_AS 0
+#define FNL_BS (FNL_AS + 2 * NL_TM * NL_PITCH)
+#define FNL_STG (FNL_BS + 2 * NL_TN * NL_PITCH)                 // 2 x [(3 + NL_NPRMAX)][16]: kpgx and twnl of a stage
+#define FNL_TAU (FNL_STG + 2 * (3 + NL_NPRMAX) * 16)            // [128][3]
+#define FNL_SMEM_BYTES ((FNL_TAU + 3 * 128) * 8)
+
 // ------------------------------------------------------------------------------------------------ fnl = anl^H c
-// grid (ceil(M/64), ceil(ncols/128), ksplit); block 256 (8 warps as 2 x 4 of 32x32).
-// part[(ks*ncols + col)*Mp + p], ncols = IS_REAL ? nst : 2*nst, col = n or 2n+{re,im}
+// grid (ceil(M/PT), ceil(nst/128), ksplit), PT = 64 projectors (complex: rows (p,re),(p,im)) or 128 (Gamma: real).
+// part[(ks*ncols + col)*Mp + p], ncols = IS_REAL ? nst : 2*nst, col = n or 2n+{re,im}.
+// Reduction over the reals (g,re),(g,im) of the plane waves of this CTA's chunk, 16 plane waves per stage:
+//   A[(p,re)][(g,.)] = ( a.x, a.y),  A[(p,im)][(g,.)] = (-a.y, a.x),  B[(g,.)][n] = c[g,n]   (a = anl[g,p]; fnl = conj(a) c)
 template <int IS_REAL>
-__global__ void __launch_bounds__(256, 2) k_fnl(NlSpecies S, int ngw, const double* __restrict__ kpgx,
-                                                const double2* __restrict__ c, size_t ldc, int nst, int gchunk,
-                                                double* __restrict__ part, int Mp)
+__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, const double* __restrict__ kpgx,
+                                                         const double2* __restrict__ c, size_t ldc, int nst, int gchunk,
+                                                         double* __restrict__ part, int Mp)
 {
   extern __shared__ __align__(16) double nl_smem[];
-  double* As = nl_smem;                      // [64][NL_PITCH]
-  double* Bs = nl_smem + 64 * NL_PITCH;      // [128][NL_PITCH]
+  double* As = nl_smem + FNL_AS;
+  double* Bs = nl_smem + FNL_BS;
+  double* stg = nl_smem + FNL_STG;
+  double* taus = nl_smem + FNL_TAU;
+  constexpr int PT = IS_REAL ? NL_TM : NL_TM / 2;
+  constexpr int STG = (3 + NL_NPRMAX) * 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int p0 = blockIdx.x * 64, col0 = blockIdx.y * 128;
+  const int p0 = blockIdx.x * PT, n0 = blockIdx.y * NL_TN;
   const int ncols = IS_REAL ? nst : 2 * nst;
   const int g0 = blockIdx.z * gchunk, g1 = min(g0 + gchunk, ngw);
-  const int ia0 = p0 / S.npr;
-  const int ia1 = min((p0 + 63) / S.npr, S.na - 1);
+  const int npr = S.npr;
+  const int ia0 = p0 / npr;
+  const int ia1 = min((p0 + PT - 1) / npr, S.na - 1);
   const int nat = ia1 - ia0 + 1;
+  const int nstage = (g1 - g0 + 15) / 16;
+  const bool tw_staged = npr <= NL_NPRMAX;
+
+  for (int i = tid; i < 2 * NL_TM * NL_PITCH; i += NL_THREADS) As[i] = 0.0;     // rows no projector maps to stay zero
+  for (int i = tid; i < 3 * nat; i += NL_THREADS) taus[i] = S.tau[3 * ia0 + i];
+
+  auto issue_stg = [&](int st) {                 // kpgx and twnl values of stage st -> stg[st & 1]
+    if (st >= nstage) return;
+    double* dst = stg + (st & 1) * STG;
+    const int gs = g0 + st * 16;
+    const int nrow = 3 + (tw_staged ? npr : 0);
+    for (int i = tid; i < nrow * 16; i += NL_THREADS) {
+      const int row = i >> 4, gl = i & 15, g = gs + gl;
+      const bool ok = g < g1;
+      const double* src = row < 3 ? kpgx + (size_t)row * ngw + (ok ? g : 0) : S.twnl + (size_t)(row - 3) * ngw + (ok ? g : 0);
+      nl_cp8(dst + i, src, ok);
+    }
+  };
+  auto issue_b = [&](int st) {                   // c[g, n] of stage st -> Bs[st & 1][n][(g,re),(g,im)]
+    if (st >= nstage) return;
+    double* dst = Bs + (st & 1) * NL_TN * NL_PITCH;
+    const int gs = g0 + st * 16;
+    for (int i = tid; i < NL_TN * 16; i += NL_THREADS) {
+      const int nl = i >> 4, gl = i & 15, n = n0 + nl, g = gs + gl;
+      const bool ok = n < nst && g < g1;
+      nl_cp16(dst + nl * NL_PITCH + 2 * gl, c + (ok ? (size_t)n * ldc + g : 0), ok);
+    }
+  };
+  auto generate = [&](int st) {                  // anl tile of stage st -> As[st & 1]
+    if (st >= nstage) return;
+    double* A = As + (st & 1) * NL_TM * NL_PITCH;
+    const double* sg = stg + (st & 1) * STG;
+    const int gs = g0 + st * 16;
+    for (int w = tid; w < nat * 16; w += NL_THREADS) {
+      const int gl = w & 15, ai = w >> 4, g = gs + gl;
+      const bool ok = g < g1;
+      double sn = 0.0, cs = 0.0;
+      if (ok) {
+        const double arg = -(sg[gl] * taus[3 * ai] + sg[16 + gl] * taus[3 * ai + 1] + sg[32 + gl] * taus[3 * ai + 2]);
+        sincos(arg, &sn, &cs);
+      }
+      for (int ipr = 0; ipr < npr; ipr++) {
+        const int pl = (ia0 + ai) * npr + ipr - p0;
+        if (pl < 0 || pl >= PT || p0 + pl >= S.M) continue;
+        double2 a = make_double2(0.0, 0.0);
+        if (ok) {
+          const double t = tw_staged ? sg[(3 + ipr) * 16 + gl] : S.twnl[(size_t)ipr * ngw + g];
+          a = anl_value(S.lproj[ipr], t, sn, cs);
+          if (IS_REAL && g == 0) a.x *= 0.5;       // G=0 counted once: dger fix, NonLocalPotential.cc:2078-2080
+        }
+        if (IS_REAL) {
+          *reinterpret_cast<double2*>(A + pl * NL_PITCH + 2 * gl) = a;
+        } else {
+          *reinterpret_cast<double2*>(A + (2 * pl) * NL_PITCH + 2 * gl) = a;
+          *reinterpret_cast<double2*>(A + (2 * pl + 1) * NL_PITCH + 2 * gl) = make_double2(-a.y, a.x);
+        }
+      }
+    }
+  };
+
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int gs = g0; gs < g1; gs += NL_KSTEP / 2) {
+  issue_stg(0);
+  issue_b(0);
+  nl_cp_wait();
+  __syncthreads();
+  issue_stg(1);
+  generate(0);
+  nl_cp_wait();
+  __syncthreads();
+  for (int st = 0; st < nstage; st++) {
+    issue_b(st + 1);
+    issue_stg(st + 2);
+    warp_mma_stage<false>(As + (st & 1) * NL_TM * NL_PITCH, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
+    generate(st + 1);
+    nl_cp_wait();
     __syncthreads();
-    // A tile: 64 projector columns x 16 plane waves
-    for (int i = tid; i < 64 * (NL_KSTEP / 2); i += blockDim.x) {       // clear (tile edges, atoms cut by the tile)
-      As[(i >> 4) * NL_PITCH + 2 * (i & 15)] = 0.0;
-      As[(i >> 4) * NL_PITCH + 2 * (i & 15) + 1] = 0.0;
-    }
-    __syncthreads();
-    for (int w = tid; w < nat * (NL_KSTEP / 2); w += blockDim.x) {
-      const int gl = w & 15, ia = ia0 + (w >> 4), g = gs + gl;
-      if (g < g1) {
-        const double arg = -(kpgx[g] * S.tau[3 * ia] + kpgx[ngw + g] * S.tau[3 * ia + 1] + kpgx[2 * (size_t)ngw + g] * S.tau[3 * ia + 2]);
-        double sn, cs;
-        sincos(arg, &sn, &cs);
-        for (int ipr = 0; ipr < S.npr; ipr++) {
-          const int pl = ia * S.npr + ipr - p0;
-          if (pl >= 0 && pl < 64) {
-            double2 a = anl_value(S.lproj[ipr], S.twnl[(size_t)ipr * ngw + g], sn, cs);
-            if (IS_REAL && g == 0) a.x *= 0.5;       // G=0 counted once: dger fix, NonLocalPotential.cc:2078-2080
-            As[pl * NL_PITCH + 2 * gl] = a.x;
-            As[pl * NL_PITCH + 2 * gl + 1] = a.y;
-          }
-        }
-      }
-    }
-    // B tile: 128 real columns x 16 plane waves
-    if (IS_REAL) {
-      for (int w = tid; w < 128 * (NL_KSTEP / 2); w += blockDim.x) {
-        const int gl = w & 15, nl = w >> 4, n = col0 + nl, g = gs + gl;
-        double2 v = make_double2(0.0, 0.0);
-        if (n < nst && g < g1) v = c[(size_t)n * ldc + g];
-        Bs[nl * NL_PITCH + 2 * gl] = v.x;
-        Bs[nl * NL_PITCH + 2 * gl + 1] = v.y;
-      }
-    } else {
-      for (int w = tid; w < 64 * (NL_KSTEP / 2); w += blockDim.x) {
-        const int gl = w & 15, nl = w >> 4, n = (col0 >> 1) + nl, g = gs + gl;
-        double2 v = make_double2(0.0, 0.0);
-        if (n < nst && g < g1) v = c[(size_t)n * ldc + g];
-        // Re fnl = sum a_re c_re + a_im c_im ; Im fnl = sum a_re c_im - a_im c_re   (conj(a) * c)
-        Bs[(2 * nl) * NL_PITCH + 2 * gl] = v.x;
-        Bs[(2 * nl) * NL_PITCH + 2 * gl + 1] = v.y;
-        Bs[(2 * nl + 1) * NL_PITCH + 2 * gl] = v.y;
-        Bs[(2 * nl + 1) * NL_PITCH + 2 * gl + 1] = -v.x;
-      }
-    }
-    __syncthreads();
-    warp_mma_32x32(As + wm * 32 * NL_PITCH, Bs + wn * 32 * NL_PITCH, acc, lane);
   }
   const int r = lane >> 2, cq = lane & 3;
 #pragma unroll
@@ -147,9 +215,11 @@ __global__ void __launch_bounds__(256, 2) k_fnl(NlSpecies S, int ngw, const doub
     for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        const int p = p0 + wm * 32 + i * 8 + r;
-        const int col = col0 + wn * 32 + j * 8 + 2 * cq + e;
-        if (p < S.M && col < ncols) part[((size_t)blockIdx.z * ncols + col) * Mp + p] = acc[i][j][e];
+        const int row = wm * 32 + i * 8 + r;
+        const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
+        const int p = p0 + (IS_REAL ? row : (row >> 1));
+        const int col = IS_REAL ? n : 2 * n + (row & 1);
+        if (p < S.M && n < nst) part[((size_t)blockIdx.z * ncols + col) * Mp + p] = acc[i][j][e];
       }
 }
 
@@ -203,69 +273,113 @@ __global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __r
   }
 }
 
+// shared-memory layout of k_back (doubles)
+#define BK_AS 0
+#define BK_BS (BK_AS + 2 * NL_KSTEP * NL_PITCH_KR)
+#define BK_KP (BK_BS + 2 * NL_TN * NL_PITCH)                    // [3][64] kpgx of the CTA's plane waves
+#define BK_TW (BK_KP + 3 * 64)                                  // [NL_NPRMAX][64] twnl of the CTA's plane waves
+#define BK_TAU (BK_TW + NL_NPRMAX * 64)                         // [NL_TAUMAX][3]
+#define BK_SMEM_BYTES ((BK_TAU + 3 * NL_TAUMAX) * 8)
+
 // ------------------------------------------------------------------------------------------------ cp += anl * fs
-// grid (ceil(ngw/64), ceil(nst/64)); block 256 (8 warps as 4 x 2 of 32x32): 128 output reals (64 G) x 64 states
+// grid (ceil(ngw/64), ceil(nst/128)): 128 output reals (64 plane waves x re/im) x 128 states per CTA.
+// Reduction over the projectors, PSTEP = 16 complex (Gamma: 32 real) per stage; A is stored k-major ([k][row]) so that
+// the generating thread of (atom, g) writes (re,im) row pairs with one 16-byte store, conflict-free:
+//   complex: A[(g,re)][(p,re)] = a.x  A[(g,re)][(p,im)] = -a.y  A[(g,im)][(p,re)] = a.y  A[(g,im)][(p,im)] = a.x
+//   Gamma:   A[(g,re)][p] = a.x  A[(g,im)][p] = a.y            B[k][n] = fs[n][k]  (fs = wt/omega * fnl)
 template <int IS_REAL>
-__global__ void __launch_bounds__(256, 2) k_back(NlSpecies S, int ngw, const double* __restrict__ kpgx,
-                                                 const double* __restrict__ fs, int Mp, double2* __restrict__ cp, size_t ldc,
-                                                 int nst)
+__global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, const double* __restrict__ kpgx,
+                                                          const double* __restrict__ fs, int Mp, double2* __restrict__ cp,
+                                                          size_t ldc, int nst)
 {
   extern __shared__ __align__(16) double nl_smem[];
-  double* As = nl_smem;                      // [128][NL_PITCH]
-  double* Bs = nl_smem + 128 * NL_PITCH;     // [64][NL_PITCH]
+  double* As = nl_smem + BK_AS;
+  double* Bs = nl_smem + BK_BS;
+  double* kps = nl_smem + BK_KP;
+  double* tws = nl_smem + BK_TW;
+  double* taus = nl_smem + BK_TAU;
+  constexpr int PSTEP = IS_REAL ? NL_KSTEP : NL_KSTEP / 2;   // projectors per stage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;
-  const int g0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  constexpr int PSTEP = IS_REAL ? NL_KSTEP : NL_KSTEP / 2;   // projector columns per stage
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g0 = blockIdx.x * 64, n0 = blockIdx.y * NL_TN;
+  const int npr = S.npr;
+  const int nstage = (S.M + PSTEP - 1) / PSTEP;
+  const bool tw_staged = npr <= NL_NPRMAX, tau_staged = S.na <= NL_TAUMAX;
+
+  for (int i = tid; i < 3 * 64; i += NL_THREADS) { const int g = g0 + (i & 63); kps[i] = g < ngw ? kpgx[(size_t)(i >> 6) * ngw + g] : 0.0; }
+  if (tw_staged)
+    for (int i = tid; i < npr * 64; i += NL_THREADS) { const int g = g0 + (i & 63); tws[i] = g < ngw ? S.twnl[(size_t)(i >> 6) * ngw + g] : 0.0; }
+  if (tau_staged) for (int i = tid; i < 3 * S.na; i += NL_THREADS) taus[i] = S.tau[i];
+  for (int i = tid; i < 2 * NL_KSTEP * NL_PITCH_KR; i += NL_THREADS) As[i] = 0.0;
+
+  auto issue_b = [&](int st) {                   // fs of stage st -> Bs[st & 1][n][k]
+    if (st >= nstage) return;
+    double* dst = Bs + (st & 1) * NL_TN * NL_PITCH;
+    const int ps = st * PSTEP;
+    for (int i = tid; i < NL_TN * 16; i += NL_THREADS) {
+      const int nl = i >> 4, ch = i & 15, n = n0 + nl;          // chunk ch = doubles 2ch, 2ch+1 of the stage's 32
+      bool ok;
+      const double* src;
+      if (IS_REAL) { ok = n < nst && ps + 2 * ch < Mp; src = fs + (ok ? (size_t)n * Mp + ps + 2 * ch : 0); }
+      else { ok = n < nst && ps + ch < S.M; src = fs + (ok ? 2 * ((size_t)n * Mp + ps + ch) : 0); }
+      nl_cp16(dst + nl * NL_PITCH + 2 * ch, src, ok);
+    }
+  };
+  auto generate = [&](int st) {                  // anl tile of stage st -> As[st & 1], k-major
+    if (st >= nstage) return;
+    double* A = As + (st & 1) * NL_KSTEP * NL_PITCH_KR;
+    const int ps = st * PSTEP;
+    const int ia0 = ps / npr;
+    const int ia1 = min((ps + PSTEP - 1) / npr, S.na - 1);
+    const int nat = ia1 - ia0 + 1;
+    if (ps + PSTEP > S.M) {                      // last stage: projector slots past M must read as zero
+      const int k0 = (IS_REAL ? 1 : 2) * (S.M - ps);
+      for (int i = tid; i < (NL_KSTEP - k0) * NL_PITCH_KR; i += NL_THREADS) A[k0 * NL_PITCH_KR + i] = 0.0;
+    }
+    for (int w = tid; w < nat * 64; w += NL_THREADS) {
+      const int gl = w & 63, ia = ia0 + (w >> 6), g = g0 + gl;
+      const bool ok = g < ngw;
+      double sn = 0.0, cs = 0.0;
+      if (ok) {
+        const double* t3 = tau_staged ? taus + 3 * ia : S.tau + 3 * ia;
+        const double arg = -(kps[gl] * t3[0] + kps[64 + gl] * t3[1] + kps[128 + gl] * t3[2]);
+        sincos(arg, &sn, &cs);
+      }
+      for (int ipr = 0; ipr < npr; ipr++) {
+        const int pl = ia * npr + ipr - ps;
+        if (pl < 0 || pl >= PSTEP || ps + pl >= S.M) continue;
+        double2 a = make_double2(0.0, 0.0);
+        if (ok) {
+          const double t = tw_staged ? tws[ipr * 64 + gl] : S.twnl[(size_t)ipr * ngw + g];
+          a = anl_value(S.lproj[ipr], t, sn, cs);
+        }
+        if (IS_REAL) {
+          *reinterpret_cast<double2*>(A + pl * NL_PITCH_KR + 2 * gl) = a;
+        } else {
+          *reinterpret_cast<double2*>(A + (2 * pl) * NL_PITCH_KR + 2 * gl) = a;
+          *reinterpret_cast<double2*>(A + (2 * pl + 1) * NL_PITCH_KR + 2 * gl) = make_double2(-a.y, a.x);
+        }
+      }
+    }
+  };
+
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int ps = 0; ps < S.M; ps += PSTEP) {
+  issue_b(0);
+  __syncthreads();            // tables and the zeroed A buffers are visible
+  generate(0);
+  nl_cp_wait();
+  __syncthreads();
+  for (int st = 0; st < nstage; st++) {
+    issue_b(st + 1);
+    warp_mma_stage<true>(As + (st & 1) * NL_KSTEP * NL_PITCH_KR, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
+    generate(st + 1);
+    nl_cp_wait();
     __syncthreads();
-    for (int i = tid; i < 128 * NL_KSTEP; i += blockDim.x) As[(i >> 5) * NL_PITCH + (i & 31)] = 0.0;
-    __syncthreads();
-    const int ia0 = ps / S.npr;
-    const int ia1 = min((ps + PSTEP - 1) / S.npr, S.na - 1);
-    const int nat = ia1 - ia0 + 1;
-    for (int w = tid; w < nat * 64; w += blockDim.x) {
-      const int gl = w & 63, ia = ia0 + (w >> 6), g = g0 + gl;
-      if (g < ngw) {
-        const double arg = -(kpgx[g] * S.tau[3 * ia] + kpgx[ngw + g] * S.tau[3 * ia + 1] + kpgx[2 * (size_t)ngw + g] * S.tau[3 * ia + 2]);
-        double sn, cs;
-        sincos(arg, &sn, &cs);
-        for (int ipr = 0; ipr < S.npr; ipr++) {
-          const int pl = ia * S.npr + ipr - ps;
-          if (pl >= 0 && pl < PSTEP && ps + pl < S.M) {
-            const double2 a = anl_value(S.lproj[ipr], S.twnl[(size_t)ipr * ngw + g], sn, cs);
-            if (IS_REAL) {
-              As[(2 * gl) * NL_PITCH + pl] = a.x;
-              As[(2 * gl + 1) * NL_PITCH + pl] = a.y;
-            } else {
-              // (a_re + i a_im)(f_re + i f_im): rows (g,re),(g,im) ; reduction index (p,re),(p,im)
-              As[(2 * gl) * NL_PITCH + 2 * pl] = a.x;
-              As[(2 * gl) * NL_PITCH + 2 * pl + 1] = -a.y;
-              As[(2 * gl + 1) * NL_PITCH + 2 * pl] = a.y;
-              As[(2 * gl + 1) * NL_PITCH + 2 * pl + 1] = a.x;
-            }
-          }
-        }
-      }
-    }
-    // B tile: 64 states x NL_KSTEP reduction entries, fs is [n][p] (complex interleaved, or real at Gamma)
-    for (int w = tid; w < 64 * NL_KSTEP; w += blockDim.x) {
-      const int kk = w & 31, nl = w >> 5, n = n0 + nl;
-      double v = 0.0;
-      if (n < nst) {
-        if (IS_REAL) { if (ps + kk < S.M) v = fs[(size_t)n * Mp + ps + kk]; }
-        else { if (ps + (kk >> 1) < S.M) v = fs[2 * ((size_t)n * Mp + ps) + kk]; }
-      }
-      Bs[nl * NL_PITCH + kk] = v;
-    }
-    __syncthreads();
-    warp_mma_32x32(As + wm * 32 * NL_PITCH, Bs + wn * 32 * NL_PITCH, acc, lane);
   }
   const int r = lane >> 2, cq = lane & 3;
   double* cpd = reinterpret_cast<double*>(cp);
@@ -340,10 +454,10 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   if (rc) { qb200_nl_destroy(nl); return rc; }
   nl->kpgx = const_cast<double*>(d);
   QB_CUDA(cudaMalloc((void**)&nl->enl_dev, sizeof(double)));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
   *out = nl;
   return QB200_OK;
 }
@@ -413,23 +527,34 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   const int ncols = nl->is_real ? nst : 2 * nst;
   for (const NlSpecies& S : nl->sp) {
     if (S.M <= 0) continue;
-    const int Mp = S.M;
-    const int mt = (S.M + 63) / 64, nt = (ncols + 127) / 128;
-    // split K so that ~4 waves of CTAs exist; chunks are multiples of 16 plane waves
-    int ksplit = std::max(1, (4 * 2 * nl->nsm + mt * nt - 1) / (mt * nt));
-    ksplit = std::min(ksplit, std::max(1, nl->ngw / 256));
+    const int Mp = (S.M + 1) & ~1;               // even pitch: 16-byte cp.async chunks of fs stay aligned; the pad is zero
+    const int PT = nl->is_real ? NL_TM : NL_TM / 2;
+    const int mt = (S.M + PT - 1) / PT, nt = (nst + NL_TN - 1) / NL_TN;
+    // split K so that the CTAs fill whole waves of the SMs (one CTA per SM); chunks are multiples of 16 plane waves
+    int ksplit = 1;
+    {
+      const int maxk = std::max(1, nl->ngw / 512);
+      double best = -1.0;
+      for (int k = 1; k <= std::min(maxk, 64); k++) {
+        const long ctas = (long)mt * nt * k;
+        const long waves = (ctas + nl->nsm - 1) / nl->nsm;
+        const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;   // mild preference for fewer partials
+        if (eff > best) { best = eff; ksplit = k; }
+      }
+    }
     int gchunk = (nl->ngw + ksplit - 1) / ksplit;
     gchunk = ((gchunk + 15) / 16) * 16;
     ksplit = (nl->ngw + gchunk - 1) / gchunk;
     if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * ncols * Mp))) return rc;
     if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, 2 * (size_t)nst * Mp))) return rc;
+    if (Mp != S.M) QB_CUDA(cudaMemsetAsync(nl->fs, 0, 2 * (size_t)nst * Mp * sizeof(double), nl->stream));
     const size_t total = (size_t)nst * S.M;
     const int nblk = (int)((total + 255) / 256);
     if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
     dim3 g1(mt, nt, ksplit);
     prof_begin(3, nl->stream);
-    if (nl->is_real) k_fnl<1><<<g1, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
-    else k_fnl<0><<<g1, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    if (nl->is_real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
     prof_begin(4, nl->stream);
@@ -440,10 +565,10 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
     if (compute_hpsi) {
-      dim3 g2((nl->ngw + 63) / 64, (nst + 63) / 64);
+      dim3 g2((nl->ngw + 63) / 64, (nst + NL_TN - 1) / NL_TN);
       prof_begin(5, nl->stream);
-      if (nl->is_real) k_back<1><<<g2, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
-      else k_back<0><<<g2, 256, NL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
+      if (nl->is_real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
+      else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
       prof_end(nl->stream);
       NL_LAUNCH_CHECK(nl);
     }
