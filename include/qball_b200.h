@@ -85,6 +85,14 @@ int qb200_nl_create(qb200_nl** nl, int device, int ngw, int is_real, double omeg
 /* add species: na atoms, npr projectors, lproj[npr], wt[npr], twnl[npr*ngw] (twnl[is][ipr*ngw+ig]), tau[3*na] */
 int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const double* wt, const double* twnl,
                          const double* tau);
+/* optional, before the first energy call: the integer description of the plane waves.
+ *   idx    = Basis::idx_ptr(): 3*ngw ints, (h,k,l) of plane wave ig at idx[3*ig + 0..2]      (Basis.cc:672-674)
+ *   b      = reciprocal lattice vectors UnitCell::b(0), b(1), b(2) as 9 doubles (b[3*i + xyz]) (Basis.cc:711-713)
+ *   kpoint = Basis::kpoint(), in units of b0,b1,b2                                             (Basis.h:51)
+ * With k+G = kpoint + h b0 + k b1 + l b2 the structure-factor phase exp(-i (k+G).tau) (comp_eigr / comp_anl,
+ * NonLocalPotential.cc:1959-2036) factorises per direction; the kernels then read three small per-atom tables instead
+ * of evaluating one FP64 sincos per (atom, G) and tile.  Same results to rounding (~1e-13 absolute in the phase). */
+int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* b, const double* kpoint);
 /* atoms moved: new positions for species is (AtomSet::get_positions order) */
 int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau);
 int qb200_nl_set_stream(qb200_nl* nl, void* cuda_stream);

@@ -84,7 +84,8 @@ def make_basis(cell, ecut, kpoint=(0.0, 0.0, 0.0), force_complex=False) -> dict:
                rod_lmin=np.ctypeslib.as_array(b.rod_lmin, (nr,)).copy(),
                rod_size=np.ctypeslib.as_array(b.rod_size, (nr,)).copy(),
                idx=np.ctypeslib.as_array(b.idx, (ngw, 3)).copy(), kpg2=np.ctypeslib.as_array(b.kpg2, (ngw,)).copy(),
-               kpgx=np.ctypeslib.as_array(b.kpgx, (3, ngw)).copy(), omega=b.omega)
+               kpgx=np.ctypeslib.as_array(b.kpgx, (3, ngw)).copy(), omega=b.omega,
+               cell=np.array(cell, dtype=np.float64).copy(), kpoint=np.array(kp, dtype=np.float64).copy())
     L.qbo_basis_destroy(p)
     return out
 

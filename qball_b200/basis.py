@@ -30,6 +30,11 @@ def _next_fact(n: int) -> int:
     return n
 
 
+def reciprocal_vectors(cell):
+    """rows b0, b1, b2 of the reciprocal lattice (UnitCell::b(i)), 2 pi / a convention"""
+    return _recip(cell)[1]
+
+
 def _recip(cell):
     a = np.asarray(cell, dtype=np.float64).reshape(3, 3)
 
@@ -117,4 +122,5 @@ def make_basis(cell, ecut: float, kpoint=(0.0, 0.0, 0.0), force_complex: bool = 
     kpg2 = kpgx[0] * kpgx[0] + kpgx[1] * kpgx[1] + kpgx[2] * kpgx[2]
     return dict(is_real=is_real, basis_np=(_next_fact(2 * hmax + 2), _next_fact(2 * kmax + 2), _next_fact(2 * lmax + 2)),
                 idxmin1=int(idxmin1), idxmax1=int(idxmax1), ngw=ngw, nrods=len(rods), rod_h=rod_h, rod_k=rod_k, rod_lmin=rod_lmin,
-                rod_size=rod_size, idx=idx, kpg2=kpg2, kpgx=kpgx, omega=vol)
+                rod_size=rod_size, idx=idx, kpg2=kpg2, kpgx=kpgx, omega=vol,
+                cell=np.array(cell, dtype=np.float64).reshape(9).copy(), kpoint=np.array(kp, dtype=np.float64).copy())

@@ -51,6 +51,7 @@ def load():
     L.qb200_nl_create.argtypes = [C.POINTER(vp), i, i, i, d, dp]
     L.qb200_nl_add_species.argtypes = [vp, i, i, ip, dp, dp, dp]
     L.qb200_nl_set_positions.argtypes = [vp, i, dp]
+    L.qb200_nl_set_lattice.argtypes = [vp, ip, dp, dp]
     L.qb200_nl_set_stream.argtypes = [vp, vp]
     L.qb200_nl_destroy.argtypes = [vp]
     L.qb200_nl_energy.argtypes = [vp, i, i, dp, dp, i, dp, C.POINTER(d)]
@@ -62,7 +63,7 @@ def load():
     for name in ("qb200_profile_enable", "qb200_profile_read", "qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace",
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_nl_create", "qb200_nl_add_species",
-                 "qb200_nl_set_positions", "qb200_nl_set_stream", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
+                 "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
         getattr(L, name).restype = i
     _lib = L
     return L

@@ -50,6 +50,12 @@ __device__ __forceinline__ void nl_cp8(void* smem, const void* gmem, bool valid)
   const int n = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
 }
+__device__ __forceinline__ void nl_cp4(void* smem, const void* gmem, bool valid)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
 __device__ __forceinline__ void nl_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // anl = t * (-i)^l * (c + i s)     (NonLocalPotential.cc:2002-2034)
@@ -69,7 +75,49 @@ struct NlSpecies {
   const double* wt;               // [npr]
   const double* twnl;             // [npr][ngw]
   const double* tau;              // [na][3]
+  const double2* ph;              // [na][JT] separable phase tables (NlLattice), or null
 };
+
+// Optional integer description of the plane waves (qb200_nl_set_lattice): k+G = kpoint + h b0 + k b1 + l b2, so
+//   exp(-i (k+G).tau) = [exp(-i kpoint.tau) exp(-i h b0.tau)] * exp(-i k b1.tau) * exp(-i l b2.tau)
+// and the FP64 sincos per (atom, G) of the tile generation (which runs on the same FP64 units as DMMA) becomes three
+// table look-ups and two complex multiplications.  Tables: per atom JT = J0+J1+J2 entries, Jd = 2*jmax[d]+1.
+struct NlLattice {
+  const int* idx;                 // [3][ngw] (h, k, l planes), null: sincos path
+  int jmax[3];
+  int JT;
+};
+
+__device__ __forceinline__ double2 nl_phase(const NlLattice& L, const double2* __restrict__ T, int h, int k, int l)
+{
+  const double2 a = __ldg(T + h + L.jmax[0]);
+  const double2 b = __ldg(T + 2 * L.jmax[0] + 1 + k + L.jmax[1]);
+  const double2 c = __ldg(T + 2 * L.jmax[0] + 1 + 2 * L.jmax[1] + 1 + l + L.jmax[2]);
+  const double2 ab = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return make_double2(ab.x * c.x - ab.y * c.y, ab.x * c.y + ab.y * c.x);
+}
+
+// grid (na), block 128: tables of one species.  bt[d] = b_d . tau, kt = kpoint . tau
+__global__ void k_phase_tables(NlSpecies S, NlLattice L, double b00, double b01, double b02, double b10, double b11, double b12,
+                               double b20, double b21, double b22, double k0, double k1, double k2, double2* __restrict__ out)
+{
+  const int ia = blockIdx.x;
+  const double tx = S.tau[3 * ia], ty = S.tau[3 * ia + 1], tz = S.tau[3 * ia + 2];
+  const double bt[3] = { b00 * tx + b01 * ty + b02 * tz, b10 * tx + b11 * ty + b12 * tz, b20 * tx + b21 * ty + b22 * tz };
+  const double kt = k0 * tx + k1 * ty + k2 * tz;
+  double2* T = out + (size_t)ia * L.JT;
+  int off = 0;
+  for (int d = 0; d < 3; d++) {
+    const int J = 2 * L.jmax[d] + 1;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      const double arg = -((double)(j - L.jmax[d]) * bt[d] + (d == 0 ? kt : 0.0));
+      double sn, cs;
+      sincos(arg, &sn, &cs);
+      T[off + j] = make_double2(cs, sn);
+    }
+    off += J;
+  }
+}
 
 // one stage of the warp tile: acc[i][j] += A(32 x 32 reals) * B(32 x 32 reals)
 template <bool A_KMAJOR>
@@ -98,7 +146,9 @@ __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, co
 #define FNL_BS (FNL_AS + 2 * NL_TM * NL_PITCH)
 #define FNL_STG (FNL_BS + 2 * NL_TN * NL_PITCH)                 // 2 x [(3 + NL_NPRMAX)][16]: kpgx and twnl of a stage
 #define FNL_TAU (FNL_STG + 2 * (3 + NL_NPRMAX) * 16)            // [128][3]
-#define FNL_SMEM_BYTES ((FNL_TAU + 3 * 128) * 8)
+#define FNL_IDX (FNL_TAU + 3 * 128)                             // 2 x [3][16] ints: (h,k,l) of a stage's plane waves
+#define FNL_LPR (FNL_IDX + 2 * 3 * 16 / 2)                      // [NL_NPRMAX] ints: lproj
+#define FNL_SMEM_BYTES ((FNL_LPR + NL_NPRMAX / 2) * 8)
 
 // ------------------------------------------------------------------------------------------------ fnl = anl^H c
 // grid (ceil(M/PT), ceil(nst/128), ksplit), PT = 64 projectors (complex: rows (p,re),(p,im)) or 128 (Gamma: real).
@@ -106,7 +156,7 @@ __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, co
 // Reduction over the reals (g,re),(g,im) of the plane waves of this CTA's chunk, 16 plane waves per stage:
 //   A[(p,re)][(g,.)] = ( a.x, a.y),  A[(p,im)][(g,.)] = (-a.y, a.x),  B[(g,.)][n] = c[g,n]   (a = anl[g,p]; fnl = conj(a) c)
 template <int IS_REAL>
-__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, const double* __restrict__ kpgx,
+__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
                                                          const double2* __restrict__ c, size_t ldc, int nst, int gchunk,
                                                          double* __restrict__ part, int Mp)
 {
@@ -115,6 +165,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
   double* Bs = nl_smem + FNL_BS;
   double* stg = nl_smem + FNL_STG;
   double* taus = nl_smem + FNL_TAU;
+  int* istg = reinterpret_cast<int*>(nl_smem + FNL_IDX);
+  int* lprs = reinterpret_cast<int*>(nl_smem + FNL_LPR);
+  const bool tables = L.idx != nullptr && S.ph != nullptr;
   constexpr int PT = IS_REAL ? NL_TM : NL_TM / 2;
   constexpr int STG = (3 + NL_NPRMAX) * 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,6 +184,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
 
   for (int i = tid; i < 2 * NL_TM * NL_PITCH; i += NL_THREADS) As[i] = 0.0;     // rows no projector maps to stay zero
   for (int i = tid; i < 3 * nat; i += NL_THREADS) taus[i] = S.tau[3 * ia0 + i];
+  for (int i = tid; i < min(npr, NL_NPRMAX); i += NL_THREADS) lprs[i] = S.lproj[i];     // no global load inside the stage loop
 
   auto issue_stg = [&](int st) {                 // kpgx and twnl values of stage st -> stg[st & 1]
     if (st >= nstage) return;
@@ -142,6 +196,11 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
       const bool ok = g < g1;
       const double* src = row < 3 ? kpgx + (size_t)row * ngw + (ok ? g : 0) : S.twnl + (size_t)(row - 3) * ngw + (ok ? g : 0);
       nl_cp8(dst + i, src, ok);
+    }
+    if (tables && tid >= NL_THREADS - 48) {
+      const int i = tid - (NL_THREADS - 48), g = gs + (i & 15);
+      const bool ok = g < g1;
+      nl_cp4(istg + (st & 1) * 48 + i, L.idx + (size_t)(i >> 4) * ngw + (ok ? g : 0), ok);
     }
   };
   auto issue_b = [&](int st) {                   // c[g, n] of stage st -> Bs[st & 1][n][(g,re),(g,im)]
@@ -164,8 +223,14 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
       const bool ok = g < g1;
       double sn = 0.0, cs = 0.0;
       if (ok) {
-        const double arg = -(sg[gl] * taus[3 * ai] + sg[16 + gl] * taus[3 * ai + 1] + sg[32 + gl] * taus[3 * ai + 2]);
-        sincos(arg, &sn, &cs);
+        if (tables) {
+          const int* ig = istg + (st & 1) * 48;
+          const double2 e = nl_phase(L, S.ph + (size_t)(ia0 + ai) * L.JT, ig[gl], ig[16 + gl], ig[32 + gl]);
+          cs = e.x; sn = e.y;
+        } else {
+          const double arg = -(sg[gl] * taus[3 * ai] + sg[16 + gl] * taus[3 * ai + 1] + sg[32 + gl] * taus[3 * ai + 2]);
+          sincos(arg, &sn, &cs);
+        }
       }
       for (int ipr = 0; ipr < npr; ipr++) {
         const int pl = (ia0 + ai) * npr + ipr - p0;
@@ -173,7 +238,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
         double2 a = make_double2(0.0, 0.0);
         if (ok) {
           const double t = tw_staged ? sg[(3 + ipr) * 16 + gl] : S.twnl[(size_t)ipr * ngw + g];
-          a = anl_value(S.lproj[ipr], t, sn, cs);
+          a = anl_value(tw_staged ? lprs[ipr] : S.lproj[ipr], t, sn, cs);
           if (IS_REAL && g == 0) a.x *= 0.5;       // G=0 counted once: dger fix, NonLocalPotential.cc:2078-2080
         }
         if (IS_REAL) {
@@ -201,10 +266,13 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, int ngw, con
   nl_cp_wait();
   __syncthreads();
   for (int st = 0; st < nstage; st++) {
+    // generation first: before this stage's DMMAs (the warps that hold work items start multiplying late, the others
+    // keep the FP64/DMMA pipe full meanwhile -- one warp per sub-partition saturates it) and before the cp.async
+    // issue (otherwise the phase-table loads share a scoreboard with the copies and wait for HBM)
+    generate(st + 1);
     issue_b(st + 1);
     issue_stg(st + 2);
     warp_mma_stage<false>(As + (st & 1) * NL_TM * NL_PITCH, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
-    generate(st + 1);
     nl_cp_wait();
     __syncthreads();
   }
@@ -279,7 +347,9 @@ __global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __r
 #define BK_KP (BK_BS + 2 * NL_TN * NL_PITCH)                    // [3][64] kpgx of the CTA's plane waves
 #define BK_TW (BK_KP + 3 * 64)                                  // [NL_NPRMAX][64] twnl of the CTA's plane waves
 #define BK_TAU (BK_TW + NL_NPRMAX * 64)                         // [NL_TAUMAX][3]
-#define BK_SMEM_BYTES ((BK_TAU + 3 * NL_TAUMAX) * 8)
+#define BK_IDX (BK_TAU + 3 * NL_TAUMAX)                         // [3][64] ints: (h,k,l) of the CTA's plane waves
+#define BK_LPR (BK_IDX + 3 * 64 / 2)                            // [NL_NPRMAX] ints: lproj
+#define BK_SMEM_BYTES ((BK_LPR + NL_NPRMAX / 2) * 8)
 
 // ------------------------------------------------------------------------------------------------ cp += anl * fs
 // grid (ceil(ngw/64), ceil(nst/128)): 128 output reals (64 plane waves x re/im) x 128 states per CTA.
@@ -288,7 +358,7 @@ __global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __r
 //   complex: A[(g,re)][(p,re)] = a.x  A[(g,re)][(p,im)] = -a.y  A[(g,im)][(p,re)] = a.y  A[(g,im)][(p,im)] = a.x
 //   Gamma:   A[(g,re)][p] = a.x  A[(g,im)][p] = a.y            B[k][n] = fs[n][k]  (fs = wt/omega * fnl)
 template <int IS_REAL>
-__global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, const double* __restrict__ kpgx,
+__global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
                                                           const double* __restrict__ fs, int Mp, double2* __restrict__ cp,
                                                           size_t ldc, int nst)
 {
@@ -298,6 +368,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, co
   double* kps = nl_smem + BK_KP;
   double* tws = nl_smem + BK_TW;
   double* taus = nl_smem + BK_TAU;
+  int* idxs = reinterpret_cast<int*>(nl_smem + BK_IDX);
+  int* lprs = reinterpret_cast<int*>(nl_smem + BK_LPR);
+  const bool tables = L.idx != nullptr && S.ph != nullptr;
   constexpr int PSTEP = IS_REAL ? NL_KSTEP : NL_KSTEP / 2;   // projectors per stage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
@@ -309,7 +382,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, co
   for (int i = tid; i < 3 * 64; i += NL_THREADS) { const int g = g0 + (i & 63); kps[i] = g < ngw ? kpgx[(size_t)(i >> 6) * ngw + g] : 0.0; }
   if (tw_staged)
     for (int i = tid; i < npr * 64; i += NL_THREADS) { const int g = g0 + (i & 63); tws[i] = g < ngw ? S.twnl[(size_t)(i >> 6) * ngw + g] : 0.0; }
-  if (tau_staged) for (int i = tid; i < 3 * S.na; i += NL_THREADS) taus[i] = S.tau[i];
+  for (int i = tid; i < min(npr, NL_NPRMAX); i += NL_THREADS) lprs[i] = S.lproj[i];
+  if (tau_staged && !tables) for (int i = tid; i < 3 * S.na; i += NL_THREADS) taus[i] = S.tau[i];
+  if (tables) for (int i = tid; i < 3 * 64; i += NL_THREADS) { const int g = g0 + (i & 63); idxs[i] = g < ngw ? L.idx[(size_t)(i >> 6) * ngw + g] : 0; }
   for (int i = tid; i < 2 * NL_KSTEP * NL_PITCH_KR; i += NL_THREADS) As[i] = 0.0;
 
   auto issue_b = [&](int st) {                   // fs of stage st -> Bs[st & 1][n][k]
@@ -341,9 +416,14 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, co
       const bool ok = g < ngw;
       double sn = 0.0, cs = 0.0;
       if (ok) {
-        const double* t3 = tau_staged ? taus + 3 * ia : S.tau + 3 * ia;
-        const double arg = -(kps[gl] * t3[0] + kps[64 + gl] * t3[1] + kps[128 + gl] * t3[2]);
-        sincos(arg, &sn, &cs);
+        if (tables) {
+          const double2 e = nl_phase(L, S.ph + (size_t)ia * L.JT, idxs[gl], idxs[64 + gl], idxs[128 + gl]);
+          cs = e.x; sn = e.y;
+        } else {
+          const double* t3 = tau_staged ? taus + 3 * ia : S.tau + 3 * ia;
+          const double arg = -(kps[gl] * t3[0] + kps[64 + gl] * t3[1] + kps[128 + gl] * t3[2]);
+          sincos(arg, &sn, &cs);
+        }
       }
       for (int ipr = 0; ipr < npr; ipr++) {
         const int pl = ia * npr + ipr - ps;
@@ -351,7 +431,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, co
         double2 a = make_double2(0.0, 0.0);
         if (ok) {
           const double t = tw_staged ? tws[ipr * 64 + gl] : S.twnl[(size_t)ipr * ngw + g];
-          a = anl_value(S.lproj[ipr], t, sn, cs);
+          a = anl_value(tw_staged ? lprs[ipr] : S.lproj[ipr], t, sn, cs);
         }
         if (IS_REAL) {
           *reinterpret_cast<double2*>(A + pl * NL_PITCH_KR + 2 * gl) = a;
@@ -375,9 +455,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, int ngw, co
   nl_cp_wait();
   __syncthreads();
   for (int st = 0; st < nstage; st++) {
+    generate(st + 1);
     issue_b(st + 1);
     warp_mma_stage<true>(As + (st & 1) * NL_KSTEP * NL_PITCH_KR, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
-    generate(st + 1);
     nl_cp_wait();
     __syncthreads();
   }
@@ -412,6 +492,11 @@ struct qb200_nl {
   double *st_c, *st_cp; size_t st_c_cap, st_cp_cap;
   long long launches;
   int nsm;
+  // optional lattice description (qb200_nl_set_lattice)
+  NlLattice lat;
+  double bvec[9], kcart[3];
+  std::vector<double2*> ph;                    // per species phase tables
+  bool ph_dirty;
 };
 
 static int nl_ensure(double** buf, size_t* cap, size_t elems)
@@ -446,6 +531,8 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   nl->part = nl->fs = nl->eblk = nl->occ_dev = nl->enl_dev = nl->st_c = nl->st_cp = nullptr;
   nl->part_cap = nl->fs_cap = nl->eblk_cap = nl->occ_cap = nl->st_c_cap = nl->st_cp_cap = 0;
   nl->launches = 0;
+  nl->lat.idx = nullptr; nl->lat.jmax[0] = nl->lat.jmax[1] = nl->lat.jmax[2] = 0; nl->lat.JT = 0;
+  nl->ph_dirty = true;
   cudaDeviceProp prop;
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
   nl->nsm = prop.multiProcessorCount;
@@ -469,7 +556,7 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   QB_CUDA(cudaSetDevice(nl->device));
   NlSpecies s;
   s.na = na; s.npr = npr; s.M = na * npr;
-  s.lproj = nullptr; s.wt = nullptr; s.twnl = nullptr; s.tau = nullptr;
+  s.lproj = nullptr; s.wt = nullptr; s.twnl = nullptr; s.tau = nullptr; s.ph = nullptr;
   if (s.M > 0) {
     if (!lproj || !wt || !twnl || !tau) { set_error("qb200_nl_add_species: null table"); return QB200_EINVAL; }
     for (int i = 0; i < npr; i++) if (lproj[i] < 0 || lproj[i] > 3) { set_error("qb200_nl_add_species: l > 3 unsupported (as in the reference)"); return QB200_EUNSUPPORTED; }
@@ -478,6 +565,57 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
         (rc = nl_upload(nl, twnl, (size_t)npr * nl->ngw, &s.twnl)) || (rc = nl_upload(nl, tau, 3 * (size_t)na, &s.tau))) return rc;
   }
   nl->sp.push_back(s);
+  nl->ph.push_back(nullptr);
+  nl->ph_dirty = true;
+  return QB200_OK;
+}
+
+extern "C" int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* b, const double* kpoint)
+{
+  if (!nl || !idx || !b || !kpoint) { set_error("qb200_nl_set_lattice: bad argument"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(nl->device));
+  const int ngw = nl->ngw;
+  std::vector<int> planes(3 * (size_t)ngw);
+  int jmax[3] = { 0, 0, 0 };
+  for (int i = 0; i < ngw; i++)
+    for (int d = 0; d < 3; d++) {
+      const int v = idx[3 * (size_t)i + d];
+      planes[(size_t)d * ngw + i] = v;
+      jmax[d] = std::max(jmax[d], std::abs(v));
+    }
+  const int* dev;
+  int rc = nl_upload(nl, planes.data(), planes.size(), &dev);
+  if (rc) return rc;
+  nl->lat.idx = dev;
+  for (int d = 0; d < 3; d++) nl->lat.jmax[d] = jmax[d];
+  nl->lat.JT = 2 * (jmax[0] + jmax[1] + jmax[2]) + 3;
+  for (int i = 0; i < 9; i++) nl->bvec[i] = b[i];
+  for (int d = 0; d < 3; d++) nl->kcart[d] = kpoint[0] * b[d] + kpoint[1] * b[3 + d] + kpoint[2] * b[6 + d];
+  nl->ph_dirty = true;
+  return QB200_OK;
+}
+
+// (re)build the separable phase tables after a change of positions or lattice
+static int nl_refresh_tables(qb200_nl* nl)
+{
+  if (!nl->ph_dirty) return QB200_OK;
+  nl->ph_dirty = false;
+  if (!nl->lat.idx) return QB200_OK;
+  for (size_t is = 0; is < nl->sp.size(); is++) {
+    NlSpecies& S = nl->sp[is];
+    if (S.M <= 0) continue;
+    if (!nl->ph[is]) {
+      QB_CUDA(cudaMalloc((void**)&nl->ph[is], (size_t)S.na * nl->lat.JT * sizeof(double2)));
+      nl->owned.push_back(nl->ph[is]);
+    }
+    const double* b = nl->bvec;
+    k_phase_tables<<<S.na, 128, 0, nl->stream>>>(S, nl->lat, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8],
+                                                 nl->kcart[0], nl->kcart[1], nl->kcart[2], nl->ph[is]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return qb200::cuda_fail(e, "k_phase_tables launch", __FILE__, __LINE__);
+    nl->launches++;
+    S.ph = nl->ph[is];
+  }
   return QB200_OK;
 }
 
@@ -487,6 +625,7 @@ extern "C" int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau)
   QB_CUDA(cudaSetDevice(nl->device));
   if (nl->sp[is].na > 0 && nl->sp[is].tau)
     QB_CUDA(cudaMemcpy(const_cast<double*>(nl->sp[is].tau), tau, 3 * (size_t)nl->sp[is].na * sizeof(double), cudaMemcpyHostToDevice));
+  nl->ph_dirty = true;
   return QB200_OK;
 }
 
@@ -525,6 +664,7 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   QB_CUDA(cudaMemcpyAsync(nl->occ_dev, occ_host, nst * sizeof(double), cudaMemcpyDefault, nl->stream));
   QB_CUDA(cudaMemsetAsync(nl->enl_dev, 0, sizeof(double), nl->stream));
   const int ncols = nl->is_real ? nst : 2 * nst;
+  if ((rc = nl_refresh_tables(nl))) return rc;
   for (const NlSpecies& S : nl->sp) {
     if (S.M <= 0) continue;
     const int Mp = (S.M + 1) & ~1;               // even pitch: 16-byte cp.async chunks of fs stay aligned; the pad is zero
@@ -553,8 +693,8 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
     dim3 g1(mt, nt, ksplit);
     prof_begin(3, nl->stream);
-    if (nl->is_real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
-    else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    if (nl->is_real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
     prof_begin(4, nl->stream);
@@ -567,8 +707,8 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     if (compute_hpsi) {
       dim3 g2((nl->ngw + 63) / 64, (nst + NL_TN - 1) / NL_TN);
       prof_begin(5, nl->stream);
-      if (nl->is_real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
-      else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
+      if (nl->is_real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
+      else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
       prof_end(nl->stream);
       NL_LAUNCH_CHECK(nl);
     }

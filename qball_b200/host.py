@@ -108,14 +108,22 @@ class NonLocalPotential:
     """NonLocalPotential(atoms, ctxt, basis, ...) norm-conserving branch (NonLocalPotential.cc:76-258, 1909-2171).
     `species` = list of dict(na, npr, lproj, wt, twnl[npr, ngw], tau[na, 3]) -- the reference's init/update_twnl outputs."""
 
-    def __init__(self, basis, species, device: int = 0, stream=None):
+    def __init__(self, basis, species, device: int = 0, stream=None, use_lattice: bool = True):
         L = capi.load()
-        g = basis.get if isinstance(basis, dict) else (lambda k: getattr(basis, k))
+        g = basis.get if isinstance(basis, dict) else (lambda k, d=None: getattr(basis, k, d))
         kpgx = np.ascontiguousarray(g("kpgx"), dtype=np.float64)
         h = C.c_void_p()
         capi._check(L.qb200_nl_create(C.byref(h), device, int(g("ngw")), int(bool(g("is_real"))), float(g("omega")),
                                       capi.ptr(kpgx)), "qb200_nl_create")
         self._h, self._L = h, L
+        if use_lattice and g("idx") is not None and g("cell") is not None and g("kpoint") is not None:
+            # integer (h,k,l) + reciprocal lattice: separable phase tables instead of one sincos per (atom, G)
+            from . import basis as _B
+            idx = np.ascontiguousarray(g("idx"), dtype=np.int32)
+            bvec = np.ascontiguousarray(_B.reciprocal_vectors(g("cell")), dtype=np.float64)
+            kp = np.ascontiguousarray(g("kpoint"), dtype=np.float64)
+            capi._check(L.qb200_nl_set_lattice(h, idx.ctypes.data_as(C.POINTER(C.c_int)), capi.ptr(bvec), capi.ptr(kp)),
+                        "qb200_nl_set_lattice")
         for s in species:
             lproj, lp = capi._iarr(s["lproj"])
             wt = np.ascontiguousarray(s["wt"], dtype=np.float64)

@@ -19,7 +19,7 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def _run_fixture(name, use_device_ptrs, force_split, monkeypatch):
+def _run_fixture(name, use_device_ptrs, force_split, monkeypatch, use_lattice=True):
     if force_split:
         monkeypatch.setenv("QB200_FORCE_SPLIT", "1")
     g = load_golden(name)
@@ -55,7 +55,7 @@ def _run_fixture(name, use_device_ptrs, force_split, monkeypatch):
     rho = wrap(np.zeros(N))
     H.compute_density(ft, cw, 1.0, occ, g["omega"], rho)
     compare(g, "rho", back(rho))
-    nlp = H.NonLocalPotential(b, g["species"])
+    nlp = H.NonLocalPotential(b, g["species"], use_lattice=use_lattice)
     cp = wrap(np.zeros_like(c))
     enl = nlp.energy(cw, occ, True, cp)
     assert abs(enl - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"])), (enl, g["enl"])
@@ -75,6 +75,12 @@ def test_cuda_vs_reference_fixture_device_pointers(name, monkeypatch):
 @pytest.mark.parametrize("name", golden_names("full"))
 def test_cuda_vs_reference_fixture_host_pointers(name, monkeypatch):
     _run_fixture(name, False, False, monkeypatch)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_projectors_sincos_path(name, monkeypatch):
+    """without qb200_nl_set_lattice the projector tiles evaluate exp(-i (k+G).tau) with sincos per (atom, G)"""
+    _run_fixture(name, True, False, monkeypatch, use_lattice=False)
 
 
 def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
