@@ -96,13 +96,18 @@ int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* b, const do
 /* atoms moved: new positions for species is (AtomSet::get_positions order) */
 int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau);
 int qb200_nl_set_stream(qb200_nl* nl, void* cuda_stream);
+/* bytes of device memory the materialised anl block may take (default 8 GiB).  anl for all projectors and a chunk of
+ * plane waves is written once per energy call (the reference's comp_anl) in the layout both GEMMs read; when the whole
+ * sphere does not fit (Au992: 181 GB) the call sweeps over chunks of plane waves instead of blocks of atoms. */
+int qb200_nl_set_workspace(qb200_nl* nl, long long bytes);
 int qb200_nl_destroy(qb200_nl* nl);
 /* enl = sum_{n,I,p} occ[n]*wt_p/omega*|F_{Ip,n}|^2 ; if compute_hpsi: cp += anl * (wt/omega * F).
  * occ: host array of the nst LOCAL states' occupations (occ[c.j(lj,jj)] in the reference, NonLocalPotential.cc:2115).
  * The row-sum of enl over G-row ranks (NonLocalPotential.cc:2629) is the identity with nprow = 1. */
 int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, int compute_hpsi, double* cp,
                     double* enl);
-long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched */
+long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call,
+                                                           12: bytes of the anl block, 13: projectors in total */
 
 /* ---- the whole H psi column block in the reference's order (EnergyFunctional.cc:1142-1153, 1500, 1675-1695):
  *      hpsi = 0 ; hpsi += V_nl psi ; hpsi += 0.5|k+G|^2 psi ; hpsi += FT[v FT^-1 psi].  nl may be NULL (no projectors).
@@ -112,9 +117,9 @@ int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c
 
 /* ---- optional per-kernel timing (CUDA events on the launching stream, recorded around every launch while enabled).
  *      categories: 0 k_zcol_bwd, 1 xy stage (k_plane, or k_xrows+k_ycols), 2 k_zcol_fwd, 3 k_fnl, 4 k_fnl_finish+sum,
- *      5 k_back, 6 k_rho_reduce.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the
+ *      5 k_back, 6 k_rho_reduce, 7 k_anl_gen.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the
  *      recorded launches into ms[ncat]/count[ncat] and clears the record. */
-#define QB200_NCAT 7
+#define QB200_NCAT 8
 int qb200_profile_enable(int on);
 int qb200_profile_read(double* ms, long long* count, int ncat);
 

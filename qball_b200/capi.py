@@ -53,6 +53,7 @@ def load():
     L.qb200_nl_set_positions.argtypes = [vp, i, dp]
     L.qb200_nl_set_lattice.argtypes = [vp, ip, dp, dp]
     L.qb200_nl_set_stream.argtypes = [vp, vp]
+    L.qb200_nl_set_workspace.argtypes = [vp, ll]
     L.qb200_nl_destroy.argtypes = [vp]
     L.qb200_nl_energy.argtypes = [vp, i, i, dp, dp, i, dp, C.POINTER(d)]
     L.qb200_nl_query.argtypes = [vp, i]
@@ -63,7 +64,7 @@ def load():
     for name in ("qb200_profile_enable", "qb200_profile_read", "qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace",
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_nl_create", "qb200_nl_add_species",
-                 "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
+                 "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_set_workspace", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -96,7 +97,7 @@ def device_count() -> int:
     return load().qb200_device_count()
 
 
-PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce")
+PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce", "k_anl_gen")
 
 
 def profile_enable(on: bool):

@@ -1,62 +1,61 @@
 // qball_b200/csrc/nonlocal.cu -- NonLocalPotential::energy, norm-conserving branch
-// (/root/reference/src/qball/NonLocalPotential.cc:1909-2171, 2628-2643) as two fused FP64 tensor-core GEMMs.
+// (/root/reference/src/qball/NonLocalPotential.cc:1909-2171, 2628-2643) as two FP64 tensor-core GEMMs.
 //
 // The reference materialises anl[ig,(ia,ipr)] = twnl[ipr][ig] * (-i)^l * exp(-i (k+G).tau_ia)  (:1959-2036) for blocks
 // of <=128 atoms and calls BLAS:  fnl = anl^H c (:2050-2068),  E_nl += occ wt/omega |fnl|^2 (:2106-2148),
-// cp += anl (wt/omega fnl) (:2150-2171).  Here anl is never stored: both GEMM kernels regenerate their anl tiles on the
-// fly (one FP64 sincos per (atom, G) per tile, shared by the atom's projectors) straight into shared memory and feed
-// mma.sync.m8n8k4.f64 (DMMA -- tcgen05 has no FP64 kind).  Complex arithmetic is mapped on real DMMA:
-//   k_fnl : out[(p,re|im), n] = sum_k A[(p,.)][k] B[k][n],  k over the 2*ngw reals (g,re),(g,im), B = c as stored
-//   k_back: cp[(g,re|im), n] += sum_{(p,re|im)} A2[(g,.)][(p,.)] f'[(p,.), n]
-// At the Gamma point both are plain real GEMMs over the 2*ngw reals with the G=0 half weight (:2070-2082) folded
-// into k_fnl's tile generation and the factor 2 (:2102) into the epilogue.
-// Internal projector order is atom-major, p = ia*npr + ipr (the reference's ia + ipr*nab is never exposed).
-// Summation is deterministic: split-K partials are reduced in fixed order, E_nl by a fixed tree.
+// cp += anl (wt/omega fnl) (:2150-2171).  Here:
+//   * k_anl_gen writes anl for ALL projectors (species concatenated, atom-major p = ia*npr + ipr within a species) and a
+//     CHUNK of plane waves into one real matrix W in the form both GEMMs consume,
+//        complex:  W[2p  ][2g..2g+1] = ( a.x, a.y)     W[2p+1][2g..2g+1] = (-a.y, a.x)        (a = anl[g,p])
+//        Gamma:    W[p][2g..2g+1]    = ( a.x, a.y)     (a.x halved at G=0: the dger fix :2070-2082)
+//     The chunk is the whole sphere when W fits the workspace (MgO216: 1.3 GB; written once per call like the
+//     reference's comp_anl, or kept until the atoms move with QB200_ANL_CACHE=1); otherwise (Au992: 181 GB for
+//     everything) the two sweeps below regenerate it chunk by chunk.
+//   * k_fnl : part[(p,re|im), n] (+)= sum_k W[row][k] c[k, n]      k over the reals (g,re),(g,im) of the chunk
+//   * k_back: cp[(g,re|im), n]  += sum_row W[row][(g,.)] fs[row, n]    (W used k-major: the same matrix, transposed role)
+//     are pure cp.async -> shared memory -> mma.sync.m8n8k4.f64 (DMMA) pipelines, three stages deep, one barrier per
+//     stage.  tcgen05 has no FP64 kind, so this is the tensor path there is for this contraction.
+// Why anl is not generated inside the GEMMs (as an earlier version did): on B200 DMMA and plain FP64 instructions
+// share one pipe (tools/microbench/dmma_peak.cu: 37.0 TF/s DMMA alone, 34 TF/s DFMA alone, the sum stays ~35 when
+// mixed), and a warp that evaluates phase factors while others multiply finds its handful of DMUL/DFMA starved behind
+// their DMMAs (measured: 4400 cycles for two DMULs) -- the tile generation could not be overlapped and cost 20 %.
+// Summation is deterministic: split-K partials and chunks are reduced in fixed order, E_nl by a fixed tree.
 #include "qb200_internal.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace qb200 {
 
-// Tile geometry of both GEMM kernels: CTA = 512 threads = 16 warps (4 x 4), warp tile 32 x 32 (16 m8n8 accumulators),
-// CTA tile 128 x 128 reals, 32 reals of the reduction dimension per stage, two stages of shared memory:
-// while the tensor pipe works on stage s, the FP64 pipe generates the anl tile of stage s+1 (sincos) and cp.async
-// brings in its B tile -- one __syncthreads per stage.
+// GEMM tile geometry: CTA = 512 threads = 16 warps (4 x 4), warp tile 32 x 32 (16 m8n8 accumulators),
+// CTA tile 128 x 128 reals, 32 reals of the reduction dimension per stage, 3 stages of shared memory.
 #define NL_TM 128
 #define NL_TN 128
 #define NL_KSTEP 32
 #define NL_THREADS 512
+#define NL_NSTAGE 3
 #define NL_PITCH 36            // doubles per row of a [row][k] tile: 32 + 4 -> conflict-free DMMA fragment loads
 #define NL_PITCH_KR 132        // doubles per k-row of a [k][row] tile: 128 + 4 (same property, k-major)
-#define NL_NPRMAX 32           // projectors per atom whose twnl values are staged in shared memory (more: read from global)
-#define NL_TAUMAX 1024         // atoms whose positions are staged in shared memory by k_back (more: read from global)
+#define NL_STAGE_RK (NL_TM * NL_PITCH + NL_TN * NL_PITCH)          // doubles per stage, A row-major (k_fnl)
+#define NL_STAGE_KR (NL_KSTEP * NL_PITCH_KR + NL_TN * NL_PITCH)    // doubles per stage, A k-major (k_back)
+#define FNL_SMEM_BYTES (NL_NSTAGE * NL_STAGE_RK * 8)
+#define BK_SMEM_BYTES (NL_NSTAGE * NL_STAGE_KR * 8)
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// 16/8-byte asynchronous copies global -> shared; !valid copies nothing and writes zeros
+// 16-byte asynchronous copy global -> shared; !valid copies nothing and writes zeros
 __device__ __forceinline__ void nl_cp16(void* smem, const void* gmem, bool valid)
 {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   const int n = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
 }
-__device__ __forceinline__ void nl_cp8(void* smem, const void* gmem, bool valid)
-{
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  const int n = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
-}
-__device__ __forceinline__ void nl_cp4(void* smem, const void* gmem, bool valid)
-{
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  const int n = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
-}
-__device__ __forceinline__ void nl_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void nl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void nl_cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // anl = t * (-i)^l * (c + i s)     (NonLocalPotential.cc:2002-2034)
 __device__ __forceinline__ double2 anl_value(int l, double t, double s, double c)
@@ -71,6 +70,7 @@ __device__ __forceinline__ double2 anl_value(int l, double t, double s, double c
 
 struct NlSpecies {
   int na, npr, M;                 // M = na*npr
+  int poff;                       // first projector of the species in the concatenated list
   const int* lproj;               // [npr]
   const double* wt;               // [npr]
   const double* twnl;             // [npr][ngw]
@@ -80,8 +80,8 @@ struct NlSpecies {
 
 // Optional integer description of the plane waves (qb200_nl_set_lattice): k+G = kpoint + h b0 + k b1 + l b2, so
 //   exp(-i (k+G).tau) = [exp(-i kpoint.tau) exp(-i h b0.tau)] * exp(-i k b1.tau) * exp(-i l b2.tau)
-// and the FP64 sincos per (atom, G) of the tile generation (which runs on the same FP64 units as DMMA) becomes three
-// table look-ups and two complex multiplications.  Tables: per atom JT = J0+J1+J2 entries, Jd = 2*jmax[d]+1.
+// and the FP64 sincos per (atom, G) becomes three table look-ups and two complex multiplications.
+// Tables: per atom JT = J0+J1+J2 entries, Jd = 2*jmax[d]+1.
 struct NlLattice {
   const int* idx;                 // [3][ngw] (h, k, l planes), null: sincos path
   int jmax[3];
@@ -119,6 +119,43 @@ __global__ void k_phase_tables(NlSpecies S, NlLattice L, double b00, double b01,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ anl chunk -> W
+// grid (ceil(gpad/128), na), block 128: one atom x 128 plane waves of the chunk [gbeg, gbeg+gcount), columns up to gpad
+// (a multiple of 16) zero-filled.  W row pitch WP doubles.
+template <int IS_REAL>
+__global__ void __launch_bounds__(128) k_anl_gen(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx, int gbeg,
+                                                 int gcount, int gpad, double* __restrict__ W, size_t WP)
+{
+  const int gl = blockIdx.x * 128 + threadIdx.x;
+  if (gl >= gpad) return;
+  const int ia = blockIdx.y, g = gbeg + gl;
+  const bool ok = gl < gcount;
+  double sn = 0.0, cs = 0.0;
+  if (ok) {
+    if (L.idx != nullptr && S.ph != nullptr) {
+      const double2 e = nl_phase(L, S.ph + (size_t)ia * L.JT, L.idx[g], L.idx[(size_t)ngw + g], L.idx[2 * (size_t)ngw + g]);
+      cs = e.x; sn = e.y;
+    } else {
+      const double arg = -(kpgx[g] * S.tau[3 * ia] + kpgx[(size_t)ngw + g] * S.tau[3 * ia + 1] + kpgx[2 * (size_t)ngw + g] * S.tau[3 * ia + 2]);
+      sincos(arg, &sn, &cs);
+    }
+  }
+  for (int ipr = 0; ipr < S.npr; ipr++) {
+    const size_t p = (size_t)S.poff + (size_t)ia * S.npr + ipr;
+    double2 a = make_double2(0.0, 0.0);
+    if (ok) {
+      a = anl_value(S.lproj[ipr], S.twnl[(size_t)ipr * ngw + g], sn, cs);
+      if (IS_REAL && g == 0) a.x *= 0.5;           // G=0 counted once: dger fix, NonLocalPotential.cc:2078-2080
+    }
+    if (IS_REAL) {
+      *reinterpret_cast<double2*>(W + p * WP + 2 * gl) = a;
+    } else {
+      *reinterpret_cast<double2*>(W + (2 * p) * WP + 2 * gl) = a;
+      *reinterpret_cast<double2*>(W + (2 * p + 1) * WP + 2 * gl) = make_double2(-a.y, a.x);
+    }
+  }
+}
+
 // one stage of the warp tile: acc[i][j] += A(32 x 32 reals) * B(32 x 32 reals)
 template <bool A_KMAJOR>
 __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][4][2],
@@ -141,141 +178,54 @@ __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, co
   }
 }
 
-// shared-memory layout of k_fnl (doubles)
-#define FNL_AS 0
-#define FNL_BS (FNL_AS + 2 * NL_TM * NL_PITCH)
-#define FNL_STG (FNL_BS + 2 * NL_TN * NL_PITCH)                 // 2 x [(3 + NL_NPRMAX)][16]: kpgx and twnl of a stage
-#define FNL_TAU (FNL_STG + 2 * (3 + NL_NPRMAX) * 16)            // [128][3]
-#define FNL_IDX (FNL_TAU + 3 * 128)                             // 2 x [3][16] ints: (h,k,l) of a stage's plane waves
-#define FNL_LPR (FNL_IDX + 2 * 3 * 16 / 2)                      // [NL_NPRMAX] ints: lproj
-#define FNL_SMEM_BYTES ((FNL_LPR + NL_NPRMAX / 2) * 8)
-
 // ------------------------------------------------------------------------------------------------ fnl = anl^H c
-// grid (ceil(M/PT), ceil(nst/128), ksplit), PT = 64 projectors (complex: rows (p,re),(p,im)) or 128 (Gamma: real).
-// part[(ks*ncols + col)*Mp + p], ncols = IS_REAL ? nst : 2*nst, col = n or 2n+{re,im}.
-// Reduction over the reals (g,re),(g,im) of the plane waves of this CTA's chunk, 16 plane waves per stage:
-//   A[(p,re)][(g,.)] = ( a.x, a.y),  A[(p,im)][(g,.)] = (-a.y, a.x),  B[(g,.)][n] = c[g,n]   (a = anl[g,p]; fnl = conj(a) c)
+// grid (ceil(RW/128), ceil(nst/128), ksplit).  Rows = rows of W (complex: (p,re),(p,im); Gamma: p), columns = states,
+// reduction over the chunk's reals k = 2*(g-gbeg)+{re,im}; this CTA takes [blockIdx.z*kper, +kper) of them.
+// part[(ks*ncols + col)*Mp + p] (=, or += when accumulate), ncols = IS_REAL ? nst : 2*nst, col = n or 2n+{re,im}.
 template <int IS_REAL>
-__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
-                                                         const double2* __restrict__ c, size_t ldc, int nst, int gchunk,
-                                                         double* __restrict__ part, int Mp)
+__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
+                                                         int kper, const double2* __restrict__ c, size_t ldc, int nst,
+                                                         double* __restrict__ part, int Mp, int Mtot, int accumulate)
 {
   extern __shared__ __align__(16) double nl_smem[];
-  double* As = nl_smem + FNL_AS;
-  double* Bs = nl_smem + FNL_BS;
-  double* stg = nl_smem + FNL_STG;
-  double* taus = nl_smem + FNL_TAU;
-  int* istg = reinterpret_cast<int*>(nl_smem + FNL_IDX);
-  int* lprs = reinterpret_cast<int*>(nl_smem + FNL_LPR);
-  const bool tables = L.idx != nullptr && S.ph != nullptr;
-  constexpr int PT = IS_REAL ? NL_TM : NL_TM / 2;
-  constexpr int STG = (3 + NL_NPRMAX) * 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int p0 = blockIdx.x * PT, n0 = blockIdx.y * NL_TN;
-  const int ncols = IS_REAL ? nst : 2 * nst;
-  const int g0 = blockIdx.z * gchunk, g1 = min(g0 + gchunk, ngw);
-  const int npr = S.npr;
-  const int ia0 = p0 / npr;
-  const int ia1 = min((p0 + PT - 1) / npr, S.na - 1);
-  const int nat = ia1 - ia0 + 1;
-  const int nstage = (g1 - g0 + 15) / 16;
-  const bool tw_staged = npr <= NL_NPRMAX;
-
-  for (int i = tid; i < 2 * NL_TM * NL_PITCH; i += NL_THREADS) As[i] = 0.0;     // rows no projector maps to stay zero
-  for (int i = tid; i < 3 * nat; i += NL_THREADS) taus[i] = S.tau[3 * ia0 + i];
-  for (int i = tid; i < min(npr, NL_NPRMAX); i += NL_THREADS) lprs[i] = S.lproj[i];     // no global load inside the stage loop
-
-  auto issue_stg = [&](int st) {                 // kpgx and twnl values of stage st -> stg[st & 1]
-    if (st >= nstage) return;
-    double* dst = stg + (st & 1) * STG;
-    const int gs = g0 + st * 16;
-    const int nrow = 3 + (tw_staged ? npr : 0);
-    for (int i = tid; i < nrow * 16; i += NL_THREADS) {
-      const int row = i >> 4, gl = i & 15, g = gs + gl;
-      const bool ok = g < g1;
-      const double* src = row < 3 ? kpgx + (size_t)row * ngw + (ok ? g : 0) : S.twnl + (size_t)(row - 3) * ngw + (ok ? g : 0);
-      nl_cp8(dst + i, src, ok);
-    }
-    if (tables && tid >= NL_THREADS - 48) {
-      const int i = tid - (NL_THREADS - 48), g = gs + (i & 15);
-      const bool ok = g < g1;
-      nl_cp4(istg + (st & 1) * 48 + i, L.idx + (size_t)(i >> 4) * ngw + (ok ? g : 0), ok);
-    }
-  };
-  auto issue_b = [&](int st) {                   // c[g, n] of stage st -> Bs[st & 1][n][(g,re),(g,im)]
-    if (st >= nstage) return;
-    double* dst = Bs + (st & 1) * NL_TN * NL_PITCH;
-    const int gs = g0 + st * 16;
-    for (int i = tid; i < NL_TN * 16; i += NL_THREADS) {
-      const int nl = i >> 4, gl = i & 15, n = n0 + nl, g = gs + gl;
-      const bool ok = n < nst && g < g1;
-      nl_cp16(dst + nl * NL_PITCH + 2 * gl, c + (ok ? (size_t)n * ldc + g : 0), ok);
-    }
-  };
-  auto generate = [&](int st) {                  // anl tile of stage st -> As[st & 1]
-    if (st >= nstage) return;
-    double* A = As + (st & 1) * NL_TM * NL_PITCH;
-    const double* sg = stg + (st & 1) * STG;
-    const int gs = g0 + st * 16;
-    for (int w = tid; w < nat * 16; w += NL_THREADS) {
-      const int gl = w & 15, ai = w >> 4, g = gs + gl;
-      const bool ok = g < g1;
-      double sn = 0.0, cs = 0.0;
-      if (ok) {
-        if (tables) {
-          const int* ig = istg + (st & 1) * 48;
-          const double2 e = nl_phase(L, S.ph + (size_t)(ia0 + ai) * L.JT, ig[gl], ig[16 + gl], ig[32 + gl]);
-          cs = e.x; sn = e.y;
-        } else {
-          const double arg = -(sg[gl] * taus[3 * ai] + sg[16 + gl] * taus[3 * ai + 1] + sg[32 + gl] * taus[3 * ai + 2]);
-          sincos(arg, &sn, &cs);
-        }
-      }
-      for (int ipr = 0; ipr < npr; ipr++) {
-        const int pl = (ia0 + ai) * npr + ipr - p0;
-        if (pl < 0 || pl >= PT || p0 + pl >= S.M) continue;
-        double2 a = make_double2(0.0, 0.0);
-        if (ok) {
-          const double t = tw_staged ? sg[(3 + ipr) * 16 + gl] : S.twnl[(size_t)ipr * ngw + g];
-          a = anl_value(tw_staged ? lprs[ipr] : S.lproj[ipr], t, sn, cs);
-          if (IS_REAL && g == 0) a.x *= 0.5;       // G=0 counted once: dger fix, NonLocalPotential.cc:2078-2080
-        }
-        if (IS_REAL) {
-          *reinterpret_cast<double2*>(A + pl * NL_PITCH + 2 * gl) = a;
-        } else {
-          *reinterpret_cast<double2*>(A + (2 * pl) * NL_PITCH + 2 * gl) = a;
-          *reinterpret_cast<double2*>(A + (2 * pl + 1) * NL_PITCH + 2 * gl) = make_double2(-a.y, a.x);
-        }
+  const int r0 = blockIdx.x * NL_TM, n0 = blockIdx.y * NL_TN;
+  const int kbeg = blockIdx.z * kper, kend = min(kbeg + kper, 2 * gcount);
+  const int nstage = (kend - kbeg + NL_KSTEP - 1) / NL_KSTEP;
+  // this thread's 4+4 copies per stage: row (tid>>4) + 32 i, 16-byte chunk (tid & 15) of the stage's 32 reals
+  const int crow = tid >> 4, cch = tid & 15;
+  auto issue = [&](int st) {
+    if (st < nstage) {
+      double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_RK;
+      double* Bs = As + NL_TM * NL_PITCH;
+      const int k = kbeg + st * NL_KSTEP + 2 * cch;               // chunk-local real index of this copy
+      const bool kok = k < kend;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int row = crow + 32 * i;
+        const bool aok = kok && r0 + row < RW;
+        nl_cp16(As + row * NL_PITCH + 2 * cch, W + (aok ? (size_t)(r0 + row) * WP + k : 0), aok);
+        const bool bok = kok && n0 + row < nst;
+        nl_cp16(Bs + row * NL_PITCH + 2 * cch, c + (bok ? (size_t)(n0 + row) * ldc + gbeg + (k >> 1) : 0), bok);
       }
     }
+    nl_cp_commit();
   };
-
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  issue_stg(0);
-  issue_b(0);
-  nl_cp_wait();
-  __syncthreads();
-  issue_stg(1);
-  generate(0);
-  nl_cp_wait();
-  __syncthreads();
+  for (int s = 0; s < NL_NSTAGE - 1; s++) issue(s);
   for (int st = 0; st < nstage; st++) {
-    // generation first: before this stage's DMMAs (the warps that hold work items start multiplying late, the others
-    // keep the FP64/DMMA pipe full meanwhile -- one warp per sub-partition saturates it) and before the cp.async
-    // issue (otherwise the phase-table loads share a scoreboard with the copies and wait for HBM)
-    generate(st + 1);
-    issue_b(st + 1);
-    issue_stg(st + 2);
-    warp_mma_stage<false>(As + (st & 1) * NL_TM * NL_PITCH, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
-    nl_cp_wait();
-    __syncthreads();
+    nl_cp_wait_group<NL_NSTAGE - 2>();
+    __syncthreads();                   // stage st has landed for everybody; everybody is done with stage st-1's buffer
+    issue(st + NL_NSTAGE - 1);
+    const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_RK;
+    warp_mma_stage<false>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
   }
+  const int ncols = IS_REAL ? nst : 2 * nst;
   const int r = lane >> 2, cq = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -283,29 +233,32 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(NlSpecies S, NlLattice L,
     for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        const int row = wm * 32 + i * 8 + r;
+        const int row = r0 + wm * 32 + i * 8 + r;
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
-        const int p = p0 + (IS_REAL ? row : (row >> 1));
+        const int p = IS_REAL ? row : (row >> 1);
         const int col = IS_REAL ? n : 2 * n + (row & 1);
-        if (p < S.M && n < nst) part[((size_t)blockIdx.z * ncols + col) * Mp + p] = acc[i][j][e];
+        if (p < Mtot && n < nst) {
+          double* dst = part + ((size_t)blockIdx.z * ncols + col) * Mp + p;
+          *dst = accumulate ? *dst + acc[i][j][e] : acc[i][j][e];
+        }
       }
 }
 
 // ------------------------------------------------------------------------------------------------ E_nl, fnl <- wt/omega fnl
 // one thread per (n, p); fs[n][p] complex (or real at Gamma); block partial sums of E_nl to eblk
 template <int IS_REAL>
-__global__ void __launch_bounds__(256) k_fnl_finish(NlSpecies S, const double* __restrict__ part, int Mp, int nst, int ksplit,
-                                                    const double* __restrict__ occ, double omega_inv,
+__global__ void __launch_bounds__(256) k_fnl_finish(const double* __restrict__ wtp, int Mtot, const double* __restrict__ part, int Mp,
+                                                    int nst, int ksplit, const double* __restrict__ occ, double omega_inv,
                                                     double* __restrict__ fs, double* __restrict__ eblk)
 {
   __shared__ double red[256];
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t total = (size_t)nst * S.M;
+  const size_t total = (size_t)nst * Mtot;
   double e = 0.0;
   if (idx < total) {
-    const int n = (int)(idx / S.M), p = (int)(idx % S.M);
+    const int n = (int)(idx / Mtot), p = (int)(idx % Mtot);
     const int ncols = IS_REAL ? nst : 2 * nst;
-    const double fac = S.wt[p % S.npr] * omega_inv;
+    const double fac = wtp[p] * omega_inv;
     if (IS_REAL) {
       double f = 0.0;
       for (int ks = 0; ks < ksplit; ks++) f += part[((size_t)ks * ncols + n) * Mp + p];
@@ -341,125 +294,51 @@ __global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __r
   }
 }
 
-// shared-memory layout of k_back (doubles)
-#define BK_AS 0
-#define BK_BS (BK_AS + 2 * NL_KSTEP * NL_PITCH_KR)
-#define BK_KP (BK_BS + 2 * NL_TN * NL_PITCH)                    // [3][64] kpgx of the CTA's plane waves
-#define BK_TW (BK_KP + 3 * 64)                                  // [NL_NPRMAX][64] twnl of the CTA's plane waves
-#define BK_TAU (BK_TW + NL_NPRMAX * 64)                         // [NL_TAUMAX][3]
-#define BK_IDX (BK_TAU + 3 * NL_TAUMAX)                         // [3][64] ints: (h,k,l) of the CTA's plane waves
-#define BK_LPR (BK_IDX + 3 * 64 / 2)                            // [NL_NPRMAX] ints: lproj
-#define BK_SMEM_BYTES ((BK_LPR + NL_NPRMAX / 2) * 8)
-
 // ------------------------------------------------------------------------------------------------ cp += anl * fs
-// grid (ceil(ngw/64), ceil(nst/128)): 128 output reals (64 plane waves x re/im) x 128 states per CTA.
-// Reduction over the projectors, PSTEP = 16 complex (Gamma: 32 real) per stage; A is stored k-major ([k][row]) so that
-// the generating thread of (atom, g) writes (re,im) row pairs with one 16-byte store, conflict-free:
-//   complex: A[(g,re)][(p,re)] = a.x  A[(g,re)][(p,im)] = -a.y  A[(g,im)][(p,re)] = a.y  A[(g,im)][(p,im)] = a.x
-//   Gamma:   A[(g,re)][p] = a.x  A[(g,im)][p] = a.y            B[k][n] = fs[n][k]  (fs = wt/omega * fnl)
+// grid (ceil(gcount/64), ceil(nst/128)): 128 output reals (64 plane waves of the chunk x re/im) x 128 states per CTA.
+// Reduction over the rows of W (32 per stage), read k-major: A[k = W row][row = 2*(g-gbeg)+{re,im}];
+// B[k][n] = fs[n][k], fs = wt/omega * fnl with row pitch FP = (IS_REAL ? Mp : 2*Mp) doubles, zero beyond RW.
 template <int IS_REAL>
-__global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
-                                                          const double* __restrict__ fs, int Mp, double2* __restrict__ cp,
+__global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
+                                                          const double* __restrict__ fs, int FP, double2* __restrict__ cp,
                                                           size_t ldc, int nst)
 {
   extern __shared__ __align__(16) double nl_smem[];
-  double* As = nl_smem + BK_AS;
-  double* Bs = nl_smem + BK_BS;
-  double* kps = nl_smem + BK_KP;
-  double* tws = nl_smem + BK_TW;
-  double* taus = nl_smem + BK_TAU;
-  int* idxs = reinterpret_cast<int*>(nl_smem + BK_IDX);
-  int* lprs = reinterpret_cast<int*>(nl_smem + BK_LPR);
-  const bool tables = L.idx != nullptr && S.ph != nullptr;
-  constexpr int PSTEP = IS_REAL ? NL_KSTEP : NL_KSTEP / 2;   // projectors per stage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int g0 = blockIdx.x * 64, n0 = blockIdx.y * NL_TN;
-  const int npr = S.npr;
-  const int nstage = (S.M + PSTEP - 1) / PSTEP;
-  const bool tw_staged = npr <= NL_NPRMAX, tau_staged = S.na <= NL_TAUMAX;
-
-  for (int i = tid; i < 3 * 64; i += NL_THREADS) { const int g = g0 + (i & 63); kps[i] = g < ngw ? kpgx[(size_t)(i >> 6) * ngw + g] : 0.0; }
-  if (tw_staged)
-    for (int i = tid; i < npr * 64; i += NL_THREADS) { const int g = g0 + (i & 63); tws[i] = g < ngw ? S.twnl[(size_t)(i >> 6) * ngw + g] : 0.0; }
-  for (int i = tid; i < min(npr, NL_NPRMAX); i += NL_THREADS) lprs[i] = S.lproj[i];
-  if (tau_staged && !tables) for (int i = tid; i < 3 * S.na; i += NL_THREADS) taus[i] = S.tau[i];
-  if (tables) for (int i = tid; i < 3 * 64; i += NL_THREADS) { const int g = g0 + (i & 63); idxs[i] = g < ngw ? L.idx[(size_t)(i >> 6) * ngw + g] : 0; }
-  for (int i = tid; i < 2 * NL_KSTEP * NL_PITCH_KR; i += NL_THREADS) As[i] = 0.0;
-
-  auto issue_b = [&](int st) {                   // fs of stage st -> Bs[st & 1][n][k]
-    if (st >= nstage) return;
-    double* dst = Bs + (st & 1) * NL_TN * NL_PITCH;
-    const int ps = st * PSTEP;
-    for (int i = tid; i < NL_TN * 16; i += NL_THREADS) {
-      const int nl = i >> 4, ch = i & 15, n = n0 + nl;          // chunk ch = doubles 2ch, 2ch+1 of the stage's 32
-      bool ok;
-      const double* src;
-      if (IS_REAL) { ok = n < nst && ps + 2 * ch < Mp; src = fs + (ok ? (size_t)n * Mp + ps + 2 * ch : 0); }
-      else { ok = n < nst && ps + ch < S.M; src = fs + (ok ? 2 * ((size_t)n * Mp + ps + ch) : 0); }
-      nl_cp16(dst + nl * NL_PITCH + 2 * ch, src, ok);
-    }
-  };
-  auto generate = [&](int st) {                  // anl tile of stage st -> As[st & 1], k-major
-    if (st >= nstage) return;
-    double* A = As + (st & 1) * NL_KSTEP * NL_PITCH_KR;
-    const int ps = st * PSTEP;
-    const int ia0 = ps / npr;
-    const int ia1 = min((ps + PSTEP - 1) / npr, S.na - 1);
-    const int nat = ia1 - ia0 + 1;
-    if (ps + PSTEP > S.M) {                      // last stage: projector slots past M must read as zero
-      const int k0 = (IS_REAL ? 1 : 2) * (S.M - ps);
-      for (int i = tid; i < (NL_KSTEP - k0) * NL_PITCH_KR; i += NL_THREADS) A[k0 * NL_PITCH_KR + i] = 0.0;
-    }
-    for (int w = tid; w < nat * 64; w += NL_THREADS) {
-      const int gl = w & 63, ia = ia0 + (w >> 6), g = g0 + gl;
-      const bool ok = g < ngw;
-      double sn = 0.0, cs = 0.0;
-      if (ok) {
-        if (tables) {
-          const double2 e = nl_phase(L, S.ph + (size_t)ia * L.JT, idxs[gl], idxs[64 + gl], idxs[128 + gl]);
-          cs = e.x; sn = e.y;
-        } else {
-          const double* t3 = tau_staged ? taus + 3 * ia : S.tau + 3 * ia;
-          const double arg = -(kps[gl] * t3[0] + kps[64 + gl] * t3[1] + kps[128 + gl] * t3[2]);
-          sincos(arg, &sn, &cs);
-        }
-      }
-      for (int ipr = 0; ipr < npr; ipr++) {
-        const int pl = ia * npr + ipr - ps;
-        if (pl < 0 || pl >= PSTEP || ps + pl >= S.M) continue;
-        double2 a = make_double2(0.0, 0.0);
-        if (ok) {
-          const double t = tw_staged ? tws[ipr * 64 + gl] : S.twnl[(size_t)ipr * ngw + g];
-          a = anl_value(tw_staged ? lprs[ipr] : S.lproj[ipr], t, sn, cs);
-        }
-        if (IS_REAL) {
-          *reinterpret_cast<double2*>(A + pl * NL_PITCH_KR + 2 * gl) = a;
-        } else {
-          *reinterpret_cast<double2*>(A + (2 * pl) * NL_PITCH_KR + 2 * gl) = a;
-          *reinterpret_cast<double2*>(A + (2 * pl + 1) * NL_PITCH_KR + 2 * gl) = make_double2(-a.y, a.x);
-        }
+  const int gl0 = blockIdx.x * 64, n0 = blockIdx.y * NL_TN;
+  const int nstage = (RW + NL_KSTEP - 1) / NL_KSTEP;
+  auto issue = [&](int st) {
+    if (st < nstage) {
+      double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_KR;
+      double* Bs = As + NL_KSTEP * NL_PITCH_KR;
+      const int k0 = st * NL_KSTEP;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        // A: 32 k-rows x 64 chunks (one plane wave = (re,im) each)
+        const int ci = tid + i * NL_THREADS, kr = ci >> 6, gc = ci & 63;
+        const bool aok = k0 + kr < RW && gl0 + gc < gcount;
+        nl_cp16(As + kr * NL_PITCH_KR + 2 * gc, W + (aok ? (size_t)(k0 + kr) * WP + 2 * (size_t)(gl0 + gc) : 0), aok);
+        // B: 128 states x 16 chunks of 2 reals
+        const int nl = ci >> 4, ch = ci & 15;
+        const bool bok = n0 + nl < nst && k0 + 2 * ch < FP;
+        nl_cp16(Bs + nl * NL_PITCH + 2 * ch, fs + (bok ? (size_t)(n0 + nl) * FP + k0 + 2 * ch : 0), bok);
       }
     }
+    nl_cp_commit();
   };
-
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  issue_b(0);
-  __syncthreads();            // tables and the zeroed A buffers are visible
-  generate(0);
-  nl_cp_wait();
-  __syncthreads();
+  for (int s = 0; s < NL_NSTAGE - 1; s++) issue(s);
   for (int st = 0; st < nstage; st++) {
-    generate(st + 1);
-    issue_b(st + 1);
-    warp_mma_stage<true>(As + (st & 1) * NL_KSTEP * NL_PITCH_KR, Bs + (st & 1) * NL_TN * NL_PITCH, acc, lane, wm, wn);
-    nl_cp_wait();
+    nl_cp_wait_group<NL_NSTAGE - 2>();
     __syncthreads();
+    issue(st + NL_NSTAGE - 1);
+    const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_KR;
+    warp_mma_stage<true>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
   }
   const int r = lane >> 2, cq = lane & 3;
   double* cpd = reinterpret_cast<double*>(cp);
@@ -470,9 +349,12 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(NlSpecies S, NlLattice L
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int row = wm * 32 + i * 8 + r;                 // real row within the tile: 2*gl + (re|im)
-        const int g = g0 + (row >> 1);
+        const int gl = gl0 + (row >> 1);
+        const int g = gbeg + gl;
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
-        if (g < ngw && n < nst) cpd[2 * ((size_t)n * ldc + g) + (row & 1)] += acc[i][j][e];
+        double v = acc[i][j][e];
+        if (IS_REAL && g == 0 && (row & 1) == 0) v *= 2.0;    // W holds half of Re anl at G=0 (k_anl_gen)
+        if (gl < gcount && n < nst) cpd[2 * ((size_t)n * ldc + g) + (row & 1)] += v;
       }
 }
 
@@ -497,6 +379,15 @@ struct qb200_nl {
   double bvec[9], kcart[3];
   std::vector<double2*> ph;                    // per species phase tables
   bool ph_dirty;
+  // concatenated projector list and the materialised anl chunk
+  int Mtot;
+  double* wtp; size_t wtp_cap;                 // [Mtot] weight of every projector
+  bool wtp_dirty;
+  double* W; size_t W_cap;                     // anl chunk, RW rows x WP doubles
+  long long anl_budget;                        // bytes W may take
+  bool W_valid;                                // W holds the whole sphere for the current positions
+  bool cache_anl;                              // keep a whole-sphere W between energy calls until the atoms move
+  int nchunks_last;
 };
 
 static int nl_ensure(double** buf, size_t* cap, size_t elems)
@@ -533,6 +424,13 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   nl->launches = 0;
   nl->lat.idx = nullptr; nl->lat.jmax[0] = nl->lat.jmax[1] = nl->lat.jmax[2] = 0; nl->lat.JT = 0;
   nl->ph_dirty = true;
+  nl->Mtot = 0; nl->wtp = nullptr; nl->wtp_cap = 0; nl->wtp_dirty = true;
+  nl->W = nullptr; nl->W_cap = 0; nl->W_valid = false; nl->nchunks_last = 0;
+  nl->anl_budget = 8ll << 30;
+  if (const char* e = getenv("QB200_ANL_BYTES")) nl->anl_budget = std::max(1ll << 20, atoll(e));
+  // off by default: like the reference (comp_anl in every energy call) each call regenerates anl (~1 % of the call)
+  nl->cache_anl = false;
+  if (const char* e = getenv("QB200_ANL_CACHE")) nl->cache_anl = e[0] == '1';
   cudaDeviceProp prop;
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
   nl->nsm = prop.multiProcessorCount;
@@ -555,7 +453,7 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   if (!nl || na < 0 || npr < 0) { set_error("qb200_nl_add_species: bad argument"); return QB200_EINVAL; }
   QB_CUDA(cudaSetDevice(nl->device));
   NlSpecies s;
-  s.na = na; s.npr = npr; s.M = na * npr;
+  s.na = na; s.npr = npr; s.M = na * npr; s.poff = nl->Mtot;
   s.lproj = nullptr; s.wt = nullptr; s.twnl = nullptr; s.tau = nullptr; s.ph = nullptr;
   if (s.M > 0) {
     if (!lproj || !wt || !twnl || !tau) { set_error("qb200_nl_add_species: null table"); return QB200_EINVAL; }
@@ -566,7 +464,8 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   }
   nl->sp.push_back(s);
   nl->ph.push_back(nullptr);
-  nl->ph_dirty = true;
+  nl->Mtot += s.M;
+  nl->ph_dirty = true; nl->wtp_dirty = true; nl->W_valid = false;
   return QB200_OK;
 }
 
@@ -591,13 +490,30 @@ extern "C" int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* 
   nl->lat.JT = 2 * (jmax[0] + jmax[1] + jmax[2]) + 3;
   for (int i = 0; i < 9; i++) nl->bvec[i] = b[i];
   for (int d = 0; d < 3; d++) nl->kcart[d] = kpoint[0] * b[d] + kpoint[1] * b[3 + d] + kpoint[2] * b[6 + d];
-  nl->ph_dirty = true;
+  nl->ph_dirty = true; nl->W_valid = false;
   return QB200_OK;
 }
 
-// (re)build the separable phase tables after a change of positions or lattice
+#define NL_LAUNCH_CHECK(nl) do { (nl)->launches++; cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return qb200::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+
+// (re)build the separable phase tables and the projector weight list after a change of positions, lattice or species
 static int nl_refresh_tables(qb200_nl* nl)
 {
+  if (nl->wtp_dirty) {
+    nl->wtp_dirty = false;
+    int rc = nl_ensure(&nl->wtp, &nl->wtp_cap, std::max(nl->Mtot, 1));
+    if (rc) return rc;
+    std::vector<double> w(std::max(nl->Mtot, 1), 0.0);
+    for (const NlSpecies& S : nl->sp) {
+      if (S.M <= 0) continue;
+      std::vector<double> wt(S.npr);
+      QB_CUDA(cudaMemcpy(wt.data(), S.wt, S.npr * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int ia = 0; ia < S.na; ia++) for (int ipr = 0; ipr < S.npr; ipr++) w[S.poff + ia * S.npr + ipr] = wt[ipr];
+    }
+    QB_CUDA(cudaMemcpyAsync(nl->wtp, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
+    QB_CUDA(cudaStreamSynchronize(nl->stream));
+  }
   if (!nl->ph_dirty) return QB200_OK;
   nl->ph_dirty = false;
   if (!nl->lat.idx) return QB200_OK;
@@ -611,9 +527,7 @@ static int nl_refresh_tables(qb200_nl* nl)
     const double* b = nl->bvec;
     k_phase_tables<<<S.na, 128, 0, nl->stream>>>(S, nl->lat, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8],
                                                  nl->kcart[0], nl->kcart[1], nl->kcart[2], nl->ph[is]);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return qb200::cuda_fail(e, "k_phase_tables launch", __FILE__, __LINE__);
-    nl->launches++;
+    NL_LAUNCH_CHECK(nl);
     S.ph = nl->ph[is];
   }
   return QB200_OK;
@@ -625,7 +539,7 @@ extern "C" int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau)
   QB_CUDA(cudaSetDevice(nl->device));
   if (nl->sp[is].na > 0 && nl->sp[is].tau)
     QB_CUDA(cudaMemcpy(const_cast<double*>(nl->sp[is].tau), tau, 3 * (size_t)nl->sp[is].na * sizeof(double), cudaMemcpyHostToDevice));
-  nl->ph_dirty = true;
+  nl->ph_dirty = true; nl->W_valid = false;
   return QB200_OK;
 }
 
@@ -636,12 +550,20 @@ extern "C" int qb200_nl_set_stream(qb200_nl* nl, void* s)
   return QB200_OK;
 }
 
+extern "C" int qb200_nl_set_workspace(qb200_nl* nl, long long bytes)
+{
+  if (!nl || bytes < (1ll << 20)) { set_error("qb200_nl_set_workspace: bad argument"); return QB200_EINVAL; }
+  nl->anl_budget = bytes;
+  nl->W_valid = false;
+  return QB200_OK;
+}
+
 extern "C" int qb200_nl_destroy(qb200_nl* nl)
 {
   if (!nl) return QB200_OK;
   cudaSetDevice(nl->device);
   for (void* p : nl->owned) cudaFree(p);
-  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp }) if (p) cudaFree(p);
+  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W }) if (p) cudaFree(p);
   delete nl;
   return QB200_OK;
 }
@@ -649,12 +571,29 @@ extern "C" int qb200_nl_destroy(qb200_nl* nl)
 extern "C" long long qb200_nl_query(const qb200_nl* nl, int what)
 {
   if (!nl) return -1;
-  if (what == 9) return nl->launches;
-  return -1;
+  switch (what) {
+    case 9: return nl->launches;
+    case 11: return nl->nchunks_last;
+    case 12: return (long long)(nl->W_cap * sizeof(double));
+    case 13: return nl->Mtot;
+    default: return -1;
+  }
 }
 
-#define NL_LAUNCH_CHECK(nl) do { (nl)->launches++; cudaError_t e__ = cudaGetLastError(); \
-    if (e__ != cudaSuccess) return qb200::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+// anl for the plane waves [gbeg, gbeg+gcount) of every species -> W (columns up to gpad zero-filled)
+static int nl_generate_chunk(qb200_nl* nl, int gbeg, int gcount, int gpad, size_t WP)
+{
+  prof_begin(7, nl->stream);
+  for (const NlSpecies& S : nl->sp) {
+    if (S.M <= 0) continue;
+    dim3 g((gpad + 127) / 128, S.na);
+    if (nl->is_real) k_anl_gen<1><<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
+    else k_anl_gen<0><<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
+    NL_LAUNCH_CHECK(nl);
+  }
+  prof_end(nl->stream);
+  return QB200_OK;
+}
 
 // device pointers; enl accumulated into nl->enl_dev (zeroed here)
 int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp)
@@ -663,55 +602,79 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   if ((rc = nl_ensure(&nl->occ_dev, &nl->occ_cap, nst))) return rc;
   QB_CUDA(cudaMemcpyAsync(nl->occ_dev, occ_host, nst * sizeof(double), cudaMemcpyDefault, nl->stream));
   QB_CUDA(cudaMemsetAsync(nl->enl_dev, 0, sizeof(double), nl->stream));
-  const int ncols = nl->is_real ? nst : 2 * nst;
+  const int Mtot = nl->Mtot;
+  if (Mtot <= 0) return QB200_OK;
   if ((rc = nl_refresh_tables(nl))) return rc;
-  for (const NlSpecies& S : nl->sp) {
-    if (S.M <= 0) continue;
-    const int Mp = (S.M + 1) & ~1;               // even pitch: 16-byte cp.async chunks of fs stay aligned; the pad is zero
-    const int PT = nl->is_real ? NL_TM : NL_TM / 2;
-    const int mt = (S.M + PT - 1) / PT, nt = (nst + NL_TN - 1) / NL_TN;
-    // split K so that the CTAs fill whole waves of the SMs (one CTA per SM); chunks are multiples of 16 plane waves
-    int ksplit = 1;
-    {
-      const int maxk = std::max(1, nl->ngw / 512);
-      double best = -1.0;
-      for (int k = 1; k <= std::min(maxk, 64); k++) {
-        const long ctas = (long)mt * nt * k;
-        const long waves = (ctas + nl->nsm - 1) / nl->nsm;
-        const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;   // mild preference for fewer partials
-        if (eff > best) { best = eff; ksplit = k; }
-      }
+  const int real = nl->is_real;
+  const int ncols = real ? nst : 2 * nst;
+  const int RW = real ? Mtot : 2 * Mtot;          // rows of W
+  const int Mp = (Mtot + 1) & ~1;                  // even pitch: 16-byte copies of fs stay aligned; the pad is zero
+  const int FP = real ? Mp : 2 * Mp;
+  // chunking of the plane waves: W = RW x 2*gchunk doubles within the budget
+  const int ngw = nl->ngw;
+  long long gmax = nl->anl_budget / ((long long)RW * 16);
+  gmax = std::max(512ll, (gmax / 512) * 512);
+  const int gchunk = (int)std::min<long long>(gmax, ((long long)ngw + 15) / 16 * 16);
+  const int nchunks = (ngw + gchunk - 1) / gchunk;
+  nl->nchunks_last = nchunks;
+  const size_t WP = 2 * (size_t)gchunk;
+  if (nl->W_cap < (size_t)RW * WP) nl->W_valid = false;
+  if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
+  const bool cacheable = nchunks == 1 && nl->cache_anl;
+  // split K of k_fnl so that the CTAs fill whole waves of the SMs (one CTA per SM)
+  const int mt = (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
+  int ksplit = 1;
+  {
+    const int maxk = std::max(1, std::min(gchunk, ngw) / 512);
+    double best = -1.0;
+    for (int k = 1; k <= std::min(maxk, 64); k++) {
+      const long ctas = (long)mt * nt * k;
+      const long waves = (ctas + nl->nsm - 1) / nl->nsm;
+      const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;   // mild preference for fewer partials
+      if (eff > best) { best = eff; ksplit = k; }
     }
-    int gchunk = (nl->ngw + ksplit - 1) / ksplit;
-    gchunk = ((gchunk + 15) / 16) * 16;
-    ksplit = (nl->ngw + gchunk - 1) / gchunk;
-    if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * ncols * Mp))) return rc;
-    if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, 2 * (size_t)nst * Mp))) return rc;
-    if (Mp != S.M) QB_CUDA(cudaMemsetAsync(nl->fs, 0, 2 * (size_t)nst * Mp * sizeof(double), nl->stream));
-    const size_t total = (size_t)nst * S.M;
-    const int nblk = (int)((total + 255) / 256);
-    if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
-    dim3 g1(mt, nt, ksplit);
+  }
+  if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * ncols * Mp))) return rc;
+  if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, (size_t)nst * FP))) return rc;
+  if (Mp != Mtot) QB_CUDA(cudaMemsetAsync(nl->fs, 0, (size_t)nst * FP * sizeof(double), nl->stream));
+  const size_t total = (size_t)nst * Mtot;
+  const int nblk = (int)((total + 255) / 256);
+  if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
+  // sweep 1: fnl partials, chunk by chunk
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (!(cacheable && nl->W_valid)) {
+      if ((rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;
+      nl->W_valid = cacheable;
+    }
+    int kper = (2 * gcount + ksplit - 1) / ksplit;
+    kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
+    dim3 g1(mt, nt, ksplit);          // a split beyond the chunk's end has no stages and stores zeros
     prof_begin(3, nl->stream);
-    if (nl->is_real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
-    else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, (const double2*)c, ldc, nst, gchunk, nl->part, Mp);
+    if (real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
-    prof_begin(4, nl->stream);
-    if (nl->is_real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(S, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
-    else k_fnl_finish<0><<<nblk, 256, 0, nl->stream>>>(S, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
-    NL_LAUNCH_CHECK(nl);
-    k_sum_blocks<<<1, 32, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
+  }
+  prof_begin(4, nl->stream);
+  if (real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
+  else k_fnl_finish<0><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
+  NL_LAUNCH_CHECK(nl);
+  k_sum_blocks<<<1, 32, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
+  prof_end(nl->stream);
+  NL_LAUNCH_CHECK(nl);
+  if (!compute_hpsi) return QB200_OK;
+  // sweep 2: back-projection, chunk by chunk (the last chunk of sweep 1 is still in W)
+  for (int i = 0; i < nchunks; i++) {
+    const int ch = nchunks - 1 - i;
+    const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (i > 0 && (rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;   // (i == 0: still in W from sweep 1)
+    dim3 g2((gcount + 63) / 64, nt);
+    prof_begin(5, nl->stream);
+    if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
+    else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
-    if (compute_hpsi) {
-      dim3 g2((nl->ngw + 63) / 64, (nst + NL_TN - 1) / NL_TN);
-      prof_begin(5, nl->stream);
-      if (nl->is_real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
-      else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, nl->fs, Mp, (double2*)cp, ldc, nst);
-      prof_end(nl->stream);
-      NL_LAUNCH_CHECK(nl);
-    }
   }
   return QB200_OK;
 }

@@ -136,6 +136,10 @@ class NonLocalPotential:
             capi._check(L.qb200_nl_set_stream(h, s_), "qb200_nl_set_stream")
 
     def launches(self): return int(self._L.qb200_nl_query(self._h, 9))
+    def query(self, what): return int(self._L.qb200_nl_query(self._h, int(what)))
+
+    def set_workspace(self, nbytes: int):
+        capi._check(self._L.qb200_nl_set_workspace(self._h, int(nbytes)), "qb200_nl_set_workspace")
 
     def set_positions(self, isp: int, tau):
         tau = np.ascontiguousarray(tau, dtype=np.float64)

@@ -19,7 +19,7 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def _run_fixture(name, use_device_ptrs, force_split, monkeypatch, use_lattice=True):
+def _run_fixture(name, use_device_ptrs, force_split, monkeypatch, use_lattice=True, anl_bytes=None):
     if force_split:
         monkeypatch.setenv("QB200_FORCE_SPLIT", "1")
     g = load_golden(name)
@@ -56,6 +56,8 @@ def _run_fixture(name, use_device_ptrs, force_split, monkeypatch, use_lattice=Tr
     H.compute_density(ft, cw, 1.0, occ, g["omega"], rho)
     compare(g, "rho", back(rho))
     nlp = H.NonLocalPotential(b, g["species"], use_lattice=use_lattice)
+    if anl_bytes is not None:
+        nlp.set_workspace(anl_bytes)
     cp = wrap(np.zeros_like(c))
     enl = nlp.energy(cw, occ, True, cp)
     assert abs(enl - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"])), (enl, g["enl"])
@@ -65,6 +67,8 @@ def _run_fixture(name, use_device_ptrs, force_split, monkeypatch, use_lattice=Tr
     enl2 = H.hpsi(ft, nlp, cw, occ, vw, wrap(b["kpg2"]), out)
     assert abs(enl2 - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"]))
     compare(g, "hpsi", back(out))
+    if anl_bytes is not None and g["nsp"] and g["ngw"] > 512:
+        assert nlp.query(11) > 1, "expected the projector sweep to run in several plane-wave chunks"
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -75,6 +79,12 @@ def test_cuda_vs_reference_fixture_device_pointers(name, monkeypatch):
 @pytest.mark.parametrize("name", golden_names("full"))
 def test_cuda_vs_reference_fixture_host_pointers(name, monkeypatch):
     _run_fixture(name, False, False, monkeypatch)
+
+
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_cuda_projectors_chunked_sweep(name, monkeypatch):
+    """a workspace too small for the whole anl block: the two GEMM sweeps run chunk by chunk (the Au992 regime)"""
+    _run_fixture(name, True, False, monkeypatch, anl_bytes=1 << 20)
 
 
 @pytest.mark.parametrize("name", golden_names())
