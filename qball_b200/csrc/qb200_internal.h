@@ -40,6 +40,10 @@ struct DevPlan {
   const int *colpos;                   // per column iv: kp*pitch0 + (digit-reversed x position of hp)
   const int *colhk;                    // per column iv: hp + np0*kp
   const int *keepcols, *keeprowstart;  // split path: columns sorted by kept row; start offsets per kept row (nkeep+1)
+  // second-generation z-column kernels (zcol_kernels.cuh); zb_*: backward, zf_*: forward
+  const int *zq, *zqm;                 // per coefficient: digit-reversed z position | column << 12 (zqm: the -G image, real bases)
+  int zb_rb, zb_cb, zb_cmax;           // rods per CTA, columns per tile, max coefficients per rod block
+  int zf_rb, zf_cb, zf_cmax;
 };
 
 enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
@@ -62,6 +66,9 @@ struct qb200_plan {
   std::vector<void*> owned;            // device allocations freed at destroy
   bool fused;                          // plane fits in shared memory
   size_t smem_z, smem_plane, smem_rows, smem_ycol;
+  bool z2;                             // second-generation z-column kernels in use
+  size_t smem_zb[2], smem_zf[2];       // their dynamic shared memory, [MODE_SINGLE], [MODE_PAIR]
+  int zslots_b[2], zslots_f[2];        // resident CTAs on the whole device
   long long ws_bytes;
   int batch;                           // units per batch
   double* zt;                          // [batch][np2][nvec] complex

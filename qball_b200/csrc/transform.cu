@@ -2,6 +2,7 @@
 // points of the C ABI (include/qball_b200.h).  Host code only builds tables and launches kernels; all arithmetic on
 // wavefunction data happens in the kernels of transform_kernels.cuh.  There is no CPU fallback.
 #include "transform_kernels.cuh"
+#include "zcol_kernels.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -190,6 +191,82 @@ static int ensure_work(qb200_plan* p, int units)
   return QB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ z-column kernels v2
+// Picks, for each direction, the number of columns per tile (cb; rb = rods per CTA) so that the persistent grid
+// (rod blocks x G) fills the resident-CTA slots of the device as evenly as possible, and records shared-memory sizes.
+namespace {
+struct Z2Choice { int cb, rb, cmax, ctas; size_t smem[2]; double cost; };
+
+int z2_cmax(const std::vector<int>& first, int ngw, int nrods, int rb)
+{
+  int cmax = 1;
+  for (int r0 = 0; r0 < nrods; r0 += rb) {
+    const int r1 = std::min(r0 + rb, nrods);
+    cmax = std::max(cmax, (r1 < nrods ? first[r1] : ngw) - first[r0]);
+  }
+  return (cmax + 3) & ~3;
+}
+
+bool z2_pick(const qb200_plan* p, const std::vector<int>& first, bool fwd, size_t smem_sm, int force_cb, Z2Choice* out)
+{
+  const DevPlan& d = p->d;
+  const int per = d.is_real ? 2 : 1;
+  bool found = false;
+  Z2Choice best = {};
+  for (int cb = 32; cb >= 8; cb--) {
+    if (cb % per) continue;
+    if (force_cb > 0 && cb != force_cb) continue;
+    Z2Choice c;
+    c.cb = cb; c.rb = cb / per;
+    c.cmax = z2_cmax(first, d.ngw, d.nrods, c.rb);
+    const size_t pitch = (size_t)(cb | 1), tile = (size_t)d.np2 * pitch * 16, tw = (size_t)d.f2.twsize * 16;
+    for (int mode = 0; mode < 2; mode++) {
+      const size_t cper = mode == MODE_PAIR ? 2 : 1;
+      c.smem[mode] = fwd ? tw + 2 * tile + (size_t)c.cmax * (8 + 4 + 4)
+                         : tw + tile + 2 * cper * (size_t)c.cmax * 16 + (size_t)c.cmax * 8;
+    }
+    const size_t need = c.smem[d.is_real ? MODE_PAIR : MODE_SINGLE];
+    if (need > (size_t)p->max_smem) continue;
+    c.ctas = (int)std::min<size_t>(2, smem_sm / (need + 1024));
+    if (c.ctas < 1) continue;
+    const long slots = (long)p->nsm * c.ctas;
+    const long nzb = (d.nrods + c.rb - 1) / c.rb;
+    const long G = std::max(1l, slots / nzb);
+    const long waves = (nzb * G + slots - 1) / slots;
+    c.cost = (double)c.rb * c.ctas * waves / (double)G * (c.ctas == 1 ? 1.15 : 1.0) * (cb < 16 ? 1.25 : 1.0);
+    if (!found || c.cost < best.cost * (1.0 - 1e-9)) { best = c; found = true; }
+  }
+  if (found) *out = best;
+  return found;
+}
+}  // namespace
+
+static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t smem_sm)
+{
+  DevPlan& d = p->d;
+  p->z2 = false;
+  if (const char* e = getenv("QB200_Z2")) if (e[0] == '0') return QB200_OK;
+  if (d.np2 > 4095) return QB200_OK;
+  int fb = 0, ff = 0;
+  if (const char* e = getenv("QB200_ZB_COLS")) fb = atoi(e);
+  if (const char* e = getenv("QB200_ZF_COLS")) ff = atoi(e);
+  Z2Choice b, f;
+  if (!z2_pick(p, first, false, smem_sm, fb, &b) || !z2_pick(p, first, true, smem_sm, ff, &f)) return QB200_OK;
+  d.zb_cb = b.cb; d.zb_rb = b.rb; d.zb_cmax = b.cmax;
+  d.zf_cb = f.cb; d.zf_rb = f.rb; d.zf_cmax = f.cmax;
+  int rc;
+  for (int mode = 0; mode < 2; mode++) { p->smem_zb[mode] = b.smem[mode]; p->smem_zf[mode] = f.smem[mode]; }
+  if ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_bwd2<MODE_PAIR>, p->smem_zb[1])) ||
+      (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE>, p->smem_zf[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_PAIR>, p->smem_zf[1]))) return rc;
+  int n = 0;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_SINGLE>, 256, p->smem_zb[0])); p->zslots_b[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_PAIR>, 256, p->smem_zb[1])); p->zslots_b[1] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_SINGLE>, 256, p->smem_zf[0])); p->zslots_f[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_PAIR>, 256, p->smem_zf[1])); p->zslots_f[1] = std::max(1, n) * p->nsm;
+  p->z2 = true;
+  return QB200_OK;
+}
+
 extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1, int np2, int nrods, const int* rod_h,
                                  const int* rod_k, const int* rod_lmin, const int* rod_size, int is_real, int idxmin1,
                                  int idxmax1)
@@ -296,6 +373,22 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
   p->max_smem = (int)prop.sharedMemPerBlockOptin;
   p->nsm = prop.multiProcessorCount;
+  {
+    // second-generation z-column kernels: shared-memory position of every coefficient (digit-reversed z | column << 12)
+    std::vector<int> zpos(np2), zq(ngw), zqm(is_real ? ngw : 0);
+    for (int q = 0; q < np2; q++) zpos[digit_reverse(d.f2, q)] = q;
+    for (int r = 0; r < nrods; r++) {
+      const int col = is_real ? (r == 0 ? 0 : 2 * r - 1) : r, colm = r == 0 ? col : col + 1;
+      for (int i = 0; i < size[r]; i++) {
+        const int l = lmin[r] + i;
+        const int izp = l < 0 ? l + np2 : l, izm = l > 0 ? np2 - l : -l;
+        zq[first[r] + i] = zpos[izp] | (col << 12);
+        if (is_real) zqm[first[r] + i] = zpos[izm] | (colm << 12);
+      }
+    }
+    if ((rc = upload(p, zq, &d.zq)) || (rc = upload(p, zqm, &d.zqm))) { qb200_plan_destroy(p); return rc; }
+    if ((rc = configure_z2(p, first, prop.sharedMemPerMultiprocessor))) { qb200_plan_destroy(p); return rc; }
+  }
   const size_t pitch2 = (size_t)(np2 | 1);
   int ncolmax = (int)std::min<size_t>(32, (80 * 1024) / (pitch2 * 16));
   if (ncolmax < (is_real ? 2 : 1)) ncolmax = is_real ? 2 : 1;
@@ -408,6 +501,9 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 8: return p->batch;
     case 9: return p->launches;
     case 10: return p->static_shape;
+    case 11: return p->z2 ? 1 : 0;
+    case 12: return p->d.zb_cb;
+    case 13: return p->d.zf_cb;
     default: return -1;
   }
 }
@@ -418,11 +514,23 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
 
 static int nzblocks(const qb200_plan* p) { return (p->d.nrods + p->d.rb - 1) / p->d.rb; }
 
+// persistent grid of the v2 z kernels: (rod blocks, G) filling the resident-CTA slots
+static dim3 z2_grid(const qb200_plan* p, int rb, int slots, int nunits)
+{
+  const int nzb = (p->d.nrods + rb - 1) / rb;
+  return dim3(nzb, std::max(1, std::min(nunits, slots / nzb)));
+}
+
 static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int nunits)
 {
   dim3 g(nzblocks(p), nunits);
   prof_begin(0, p->stream);
-  if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
+  if (p->z2) {
+    const dim3 g2 = z2_grid(p, p->d.zb_rb, p->zslots_b[mode], nunits);
+    if (mode == MODE_PAIR) k_zcol_bwd2<MODE_PAIR><<<g2, 256, p->smem_zb[1], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else k_zcol_bwd2<MODE_SINGLE><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+  }
+  else if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
   else k_zcol_bwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
   prof_end(p->stream);
   QB_LAUNCH_CHECK(p);
@@ -435,7 +543,14 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
   dim3 g(nzblocks(p), nunits);
   const double scale = 1.0 / ((double)p->d.np0 * p->d.np1 * p->d.np2);
   prof_begin(2, p->stream);
-  if (mode == MODE_PAIR)
+  if (p->z2) {
+    const dim3 g2 = z2_grid(p, p->d.zf_rb, p->zslots_f[mode], nunits);
+    if (mode == MODE_PAIR)
+      k_zcol_fwd2<MODE_PAIR><<<g2, 256, p->smem_zf[1], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+    else
+      k_zcol_fwd2<MODE_SINGLE><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+  }
+  else if (mode == MODE_PAIR)
     k_zcol_fwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
   else
     k_zcol_fwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
