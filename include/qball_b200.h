@@ -51,9 +51,20 @@ int qb200_plan_destroy(qb200_plan* plan);
 int qb200_plan_set_stream(qb200_plan* plan, void* cuda_stream);
 /* bytes of device scratch for the column-form intermediate (default 256 MiB); bounds the number of states per batch */
 int qb200_plan_set_workspace(qb200_plan* plan, long long bytes);
+/* Host coefficient blocks and residency.  When `c` is a HOST pointer, qb200_hpsi and qb200_compute_density upload it
+ * in blocks of states on a copy stream while earlier blocks are being computed (and qb200_hpsi downloads finished
+ * blocks of H psi on a second copy stream), so PCIe time hides behind the kernels; register the arrays with
+ * cudaHostRegister (ComplexMatrix::val) -- pageable memory still works but serialises.  The device copy stays in the
+ * plan.  tag != 0 declares the CONTENT VERSION of the host blocks passed from now on: a later call with the same
+ * (pointer, ldc, nst) under the same tag skips the upload.  The reference evaluates rho and H psi on the same
+ * wavefunction between two stepper updates (BOSampleStepper.cc: cd_.update_density(); ef_.update_vhxc(); ef_.energy()),
+ * so the SlaterDet shim bumps a counter in its non-const c() accessor and passes it here.
+ * tag == 0 (default): every call uploads. */
+int qb200_plan_set_coefficient_tag(qb200_plan* plan, long long tag);
 /* queries: 0 np0, 1 np1, 2 np2, 3 nvec, 4 ntrans0, 5 ngw, 6 is_real, 7 plane-fused path in use (1) or split path (0),
  *          8 states per batch, 9 kernels launched since creation (for bench gpu_launches),
- *          10 plane kernel in use: 0 generic, > 0 index of the compiled grid shape (plane.cu) */
+ *          10 plane kernel in use: 0 generic, > 0 index of the compiled grid shape (plane.cu),
+ *          11 second-generation z-column kernels in use, 12/13 their columns per tile (backward/forward) */
 long long qb200_plan_query(const qb200_plan* plan, int what);
 
 /* ---- FourierTransform::backward(const complex<double>* c, complex<double>* f)       FourierTransform.cc:529-539

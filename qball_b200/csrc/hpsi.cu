@@ -5,7 +5,8 @@
 #include <algorithm>
 
 int qb200_rs_mul_add_dev(qb200_plan* p, int ldc, int nst, const double* c, const double* v, const double* kpg2, double* cp);
-int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp);
+int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int cont);
+int qb200_nl_chunks(const qb200_nl* nl, int nst);
 double* qb200_nl_enl_dev(qb200_nl* nl);
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s);
 
@@ -20,6 +21,17 @@ static int ensure_buf(double** buf, size_t* cap, size_t elems)
   return QB200_OK;
 }
 
+// states per pipeline block of the host-pointer path: whole GEMM tiles (128 states), an even count (real bases pair
+// local states (n, n+1), SlaterDet.cc:987), at most 8 blocks; one block when the projector sweep is chunked (each
+// block would regenerate every anl chunk)
+static int hpsi_block_states(int nst, bool single)
+{
+  if (single || nst <= 128) return nst;
+  const int nblk = std::min(8, (nst + 127) / 128);
+  const int per = (nst + nblk - 1) / nblk;
+  return (per + 127) / 128 * 128;
+}
+
 extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,
                           const double* kpg2, double* hpsi, double* enl)
 {
@@ -32,10 +44,12 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
   int rc;
   const double *cd = c, *vd = v, *kd = kpg2;
   double* od = hpsi;
-  if (!is_device_ptr(c)) {
+  const bool chost = !is_device_ptr(c), ohost = !is_device_ptr(hpsi);
+  const bool upload_c = chost && !plan_resident(p, c, ldc, nst);
+  if (chost) {
     if ((rc = ensure_buf(&p->st_c, &p->st_c_cap, blk))) return rc;
-    QB_CUDA(cudaMemcpyAsync(p->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     cd = p->st_c;
+    if (upload_c) p->res_ptr = nullptr;
   }
   if (!is_device_ptr(v)) {
     if ((rc = ensure_buf(&p->st_v, &p->st_v_cap, N))) return rc;
@@ -47,23 +61,58 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
     QB_CUDA(cudaMemcpyAsync(p->st_kpg2, kpg2, d.ngw * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     kd = p->st_kpg2;
   }
-  if (!is_device_ptr(hpsi)) {
+  if (ohost) {
     if ((rc = ensure_buf(&p->st_cp, &p->st_cp_cap, blk))) return rc;
     od = p->st_cp;
   }
-  QB_CUDA(cudaMemsetAsync(od, 0, blk * sizeof(double), p->stream));           // dwf.c().clear()
-  cudaStream_t saved = 0;
-  if (nl) {
-    saved = qb200_nl_swap_stream(nl, p->stream);
-    rc = qb200_nl_energy_dev(nl, ldc, nst, cd, occ, 1, od);                    // nlp->energy(sd, true, dsd, ...)
-    qb200_nl_swap_stream(nl, saved);
-    if (rc) return rc;
+  // Host blocks are pipelined by blocks of states: block b+1 is uploaded (copy stream s_in) and block b-1 downloaded
+  // (s_out) while block b is computed on the plan's stream; device-resident blocks are one "block".
+  const bool pipelined = upload_c || ohost;
+  const int SB = pipelined ? hpsi_block_states(nst, nl && qb200_nl_chunks(nl, nst) > 1) : nst;
+  const int nblk = (nst + SB - 1) / SB;
+  if (pipelined && (rc = plan_copy_streams(p))) return rc;
+  if (upload_c) {
+    cudaEvent_t ev;
+    if ((rc = plan_event(p, 0, &ev))) return rc;
+    QB_CUDA(cudaEventRecord(ev, p->stream));
+    QB_CUDA(cudaStreamWaitEvent(p->s_in, ev, 0));
+    for (int b = 0; b < nblk; b++) {
+      const int n0 = b * SB, nb = std::min(SB, nst - n0);
+      const size_t off = 2 * (size_t)n0 * ldc;
+      QB_CUDA(cudaMemcpyAsync(p->st_c + off, c + off, 2 * (size_t)nb * ldc * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+      if ((rc = plan_event(p, 1 + b, &ev))) return rc;
+      QB_CUDA(cudaEventRecord(ev, p->s_in));
+    }
   }
-  if ((rc = qb200_rs_mul_add_dev(p, ldc, nst, cd, vd, kd, od))) return rc;     // kinetic + sd.rs_mul_add(...)
-  if (od != hpsi) QB_CUDA(cudaMemcpyAsync(hpsi, od, blk * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  cudaStream_t saved = 0;
+  if (nl) saved = qb200_nl_swap_stream(nl, p->stream);
+  for (int b = 0; b < nblk; b++) {
+    const int n0 = b * SB, nb = std::min(SB, nst - n0);
+    const size_t off = 2 * (size_t)n0 * ldc;
+    if (upload_c) QB_CUDA(cudaStreamWaitEvent(p->stream, p->evs[1 + b], 0));
+    QB_CUDA(cudaMemsetAsync(od + off, 0, 2 * (size_t)nb * ldc * sizeof(double), p->stream));      // dwf.c().clear()
+    if (nl && (rc = qb200_nl_energy_dev(nl, ldc, nb, cd + off, occ + n0, 1, od + off, b > 0))) {      // nlp->energy(sd, true, dsd, ...)
+      qb200_nl_swap_stream(nl, saved);
+      return rc;
+    }
+    if ((rc = qb200_rs_mul_add_dev(p, ldc, nb, cd + off, vd, kd, od + off))) {                       // kinetic + sd.rs_mul_add(...)
+      if (nl) qb200_nl_swap_stream(nl, saved);
+      return rc;
+    }
+    if (ohost) {
+      cudaEvent_t ev;
+      if ((rc = plan_event(p, 1 + nblk + b, &ev))) return rc;
+      QB_CUDA(cudaEventRecord(ev, p->stream));
+      QB_CUDA(cudaStreamWaitEvent(p->s_out, ev, 0));
+      QB_CUDA(cudaMemcpyAsync(hpsi + off, od + off, 2 * (size_t)nb * ldc * sizeof(double), cudaMemcpyDeviceToHost, p->s_out));
+    }
+  }
+  if (nl) qb200_nl_swap_stream(nl, saved);
   double e = 0.0;
   if (nl && enl) QB_CUDA(cudaMemcpyAsync(&e, qb200_nl_enl_dev(nl), sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  if (od != hpsi || (nl && enl)) QB_CUDA(cudaStreamSynchronize(p->stream));
+  if (pipelined || chost || (nl && enl)) QB_CUDA(cudaStreamSynchronize(p->stream));
+  if (ohost) QB_CUDA(cudaStreamSynchronize(p->s_out));
+  if (upload_c) plan_mark_resident(p, c, ldc, nst);
   if (enl) *enl = e;
   return QB200_OK;
 }

@@ -595,13 +595,26 @@ static int nl_generate_chunk(qb200_nl* nl, int gbeg, int gcount, int gpad, size_
   return QB200_OK;
 }
 
-// device pointers; enl accumulated into nl->enl_dev (zeroed here)
-int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp)
+// plane-wave chunks the projector sweep of a call takes (1: anl for the whole sphere fits the workspace)
+static void nl_chunking(const qb200_nl* nl, int* gchunk_out, int* nchunks_out)
+{
+  const int RW = nl->is_real ? nl->Mtot : 2 * nl->Mtot;
+  long long gmax = nl->anl_budget / ((long long)std::max(RW, 1) * 16);
+  gmax = std::max(512ll, (gmax / 512) * 512);
+  const int gchunk = (int)std::min<long long>(gmax, ((long long)nl->ngw + 15) / 16 * 16);
+  *gchunk_out = gchunk;
+  *nchunks_out = (nl->ngw + gchunk - 1) / gchunk;
+}
+int qb200_nl_chunks(const qb200_nl* nl, int) { int g, n; nl_chunking(nl, &g, &n); return nl->Mtot > 0 ? n : 1; }
+
+// device pointers; enl accumulated into nl->enl_dev.  cont == 0: a new call (enl zeroed, anl regenerated unless cached);
+// cont != 0: a further block of states of the same call (enl keeps accumulating, a whole-sphere anl in W is reused).
+int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int cont)
 {
   int rc;
   if ((rc = nl_ensure(&nl->occ_dev, &nl->occ_cap, nst))) return rc;
   QB_CUDA(cudaMemcpyAsync(nl->occ_dev, occ_host, nst * sizeof(double), cudaMemcpyDefault, nl->stream));
-  QB_CUDA(cudaMemsetAsync(nl->enl_dev, 0, sizeof(double), nl->stream));
+  if (!cont) QB_CUDA(cudaMemsetAsync(nl->enl_dev, 0, sizeof(double), nl->stream));
   const int Mtot = nl->Mtot;
   if (Mtot <= 0) return QB200_OK;
   if ((rc = nl_refresh_tables(nl))) return rc;
@@ -612,15 +625,15 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   const int FP = real ? Mp : 2 * Mp;
   // chunking of the plane waves: W = RW x 2*gchunk doubles within the budget
   const int ngw = nl->ngw;
-  long long gmax = nl->anl_budget / ((long long)RW * 16);
-  gmax = std::max(512ll, (gmax / 512) * 512);
-  const int gchunk = (int)std::min<long long>(gmax, ((long long)ngw + 15) / 16 * 16);
-  const int nchunks = (ngw + gchunk - 1) / gchunk;
+  int gchunk, nchunks;
+  nl_chunking(nl, &gchunk, &nchunks);
   nl->nchunks_last = nchunks;
   const size_t WP = 2 * (size_t)gchunk;
   if (nl->W_cap < (size_t)RW * WP) nl->W_valid = false;
   if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
-  const bool cacheable = nchunks == 1 && nl->cache_anl;
+  // W_valid: W holds anl of the whole sphere for the current positions; reused by later blocks of one call, and
+  // across calls when caching is on
+  const bool reuse = nchunks == 1 && nl->W_valid && (nl->cache_anl || cont);
   // split K of k_fnl so that the CTAs fill whole waves of the SMs (one CTA per SM)
   const int mt = (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
   int ksplit = 1;
@@ -643,9 +656,9 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   // sweep 1: fnl partials, chunk by chunk
   for (int ch = 0; ch < nchunks; ch++) {
     const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
-    if (!(cacheable && nl->W_valid)) {
+    if (!reuse) {
       if ((rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;
-      nl->W_valid = cacheable;
+      nl->W_valid = nchunks == 1;
     }
     int kper = (2 * gcount + ksplit - 1) / ksplit;
     kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
@@ -700,7 +713,7 @@ extern "C" int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, 
     QB_CUDA(cudaMemcpyAsync(nl->st_cp, cp, blk * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
     cpd = nl->st_cp;
   }
-  if ((rc = qb200_nl_energy_dev(nl, ldc, nst, cd, occ, compute_hpsi, cpd))) return rc;
+  if ((rc = qb200_nl_energy_dev(nl, ldc, nst, cd, occ, compute_hpsi, cpd, 0))) return rc;
   if (compute_hpsi && cpd != cp) QB_CUDA(cudaMemcpyAsync(cp, cpd, blk * sizeof(double), cudaMemcpyDeviceToHost, nl->stream));
   double e = 0.0;
   QB_CUDA(cudaMemcpyAsync(&e, nl->enl_dev, sizeof(double), cudaMemcpyDeviceToHost, nl->stream));

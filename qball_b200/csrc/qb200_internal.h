@@ -84,4 +84,16 @@ struct qb200_plan {
   int nsm;
   int plane_threads;
   int static_shape;                    // plane.cu: 0 generic kernel, > 0 compiled shape index
+  // pipelined host-pointer paths (hpsi.cu, qb200_compute_density): copy streams + events, and the identity of the host
+  // coefficient block whose device copy sits in st_c (qb200_plan_set_coefficient_tag)
+  cudaStream_t s_in, s_out;
+  std::vector<cudaEvent_t> evs;
+  const void* res_ptr; int res_ldc, res_nst; long long res_tag, next_tag;
 };
+
+namespace qb200 {
+int plan_copy_streams(qb200_plan* p);                 // create s_in/s_out on first use
+int plan_event(qb200_plan* p, size_t i, cudaEvent_t* ev);   // i-th event of the plan's pool (timing disabled)
+bool plan_resident(const qb200_plan* p, const void* c, int ldc, int nst);
+void plan_mark_resident(qb200_plan* p, const void* c, int ldc, int nst);
+}

@@ -105,6 +105,31 @@ static int ensure(double** buf, size_t* cap, size_t elems)
   return QB200_OK;
 }
 
+int plan_copy_streams(qb200_plan* p)
+{
+  if (!p->s_in) QB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  if (!p->s_out) QB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  return QB200_OK;
+}
+int plan_event(qb200_plan* p, size_t i, cudaEvent_t* ev)
+{
+  while (p->evs.size() <= i) {
+    cudaEvent_t e;
+    QB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->evs.push_back(e);
+  }
+  *ev = p->evs[i];
+  return QB200_OK;
+}
+bool plan_resident(const qb200_plan* p, const void* c, int ldc, int nst)
+{
+  return p->next_tag != 0 && p->res_tag == p->next_tag && p->res_ptr == c && p->res_ldc == ldc && p->res_nst == nst && p->st_c;
+}
+void plan_mark_resident(qb200_plan* p, const void* c, int ldc, int nst)
+{
+  p->res_ptr = c; p->res_ldc = ldc; p->res_nst = nst; p->res_tag = p->next_tag;
+}
+
 template <class K> static int opt_in_smem(K kernel, size_t bytes)
 {
   if (bytes > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -287,6 +312,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   p->st_c = p->st_cp = p->st_v = p->st_f = p->st_kpg2 = nullptr;
   p->st_c_cap = p->st_cp_cap = p->st_v_cap = p->st_f_cap = p->st_kpg2_cap = 0;
   p->launches = 0;
+  p->s_in = p->s_out = nullptr; p->res_ptr = nullptr; p->res_ldc = p->res_nst = 0; p->res_tag = p->next_tag = 0;
   DevPlan& d = p->d;
   d.np0 = np0; d.np1 = np1; d.np2 = np2; d.nrods = nrods; d.is_real = is_real ? 1 : 0;
   d.nvec = is_real ? 2 * nrods - 1 : nrods;                       // FourierTransform.cc:186-197
@@ -466,6 +492,9 @@ extern "C" int qb200_plan_destroy(qb200_plan* p)
   if (!p) return QB200_OK;
   cudaSetDevice(p->device);
   for (void* q : p->owned) cudaFree(q);
+  for (cudaEvent_t e : p->evs) cudaEventDestroy(e);
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
   for (double* q : { p->zt, p->w, p->rho_part, p->fac_dev, p->st_c, p->st_cp, p->st_v, p->st_f, p->st_kpg2 })
     if (q) cudaFree(q);
   delete p;
@@ -476,6 +505,13 @@ extern "C" int qb200_plan_set_stream(qb200_plan* p, void* s)
 {
   if (!p) return QB200_EINVAL;
   p->stream = (cudaStream_t)s;
+  return QB200_OK;
+}
+
+extern "C" int qb200_plan_set_coefficient_tag(qb200_plan* p, long long tag)
+{
+  if (!p) return QB200_EINVAL;
+  p->next_tag = tag;
   return QB200_OK;
 }
 
@@ -601,6 +637,7 @@ static int stage_in(qb200_plan* p, const double* ptr, size_t elems, double** buf
 {
   if (!ptr) { *dev = nullptr; return QB200_OK; }
   if (is_device_ptr(ptr)) { *dev = ptr; return QB200_OK; }
+  if (buf == &p->st_c) p->res_ptr = nullptr;            // st_c no longer holds a tagged coefficient block
   int rc = ensure(buf, cap, elems);
   if (rc) return rc;
   QB_CUDA(cudaMemcpyAsync(*buf, ptr, elems * sizeof(double), cudaMemcpyHostToDevice, p->stream));
@@ -619,6 +656,7 @@ static int fft_backward_impl(qb200_plan* p, const double* c1, const double* c2, 
   int rc = ensure_work(p, 1);
   if (rc) return rc;
   // coefficients: gather c1 (and c2) into one ldc = ngw block of 1 or 2 columns on the device
+  p->res_ptr = nullptr;
   rc = ensure(&p->st_c, &p->st_c_cap, 4 * (size_t)d.ngw);
   if (rc) return rc;
   const cudaMemcpyKind any = cudaMemcpyDefault;
@@ -645,6 +683,7 @@ static int fft_forward_impl(qb200_plan* p, double* f, double* c1, double* c2)
   if (rc) return rc;
   const double* fdev;
   if ((rc = stage_in(p, f, 2 * N, &p->st_f, &p->st_f_cap, &fdev))) return rc;
+  p->res_ptr = nullptr;
   rc = ensure(&p->st_c, &p->st_c_cap, 4 * (size_t)d.ngw);
   if (rc) return rc;
   if ((rc = launch_xy<OP_FWD>(p, 1, nullptr, (double*)fdev, nullptr, 1, 0))) return rc;
@@ -730,23 +769,49 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   QB_CUDA(cudaSetDevice(p->device));
   const DevPlan& d = p->d;
   const size_t N = (size_t)d.np0 * d.np1 * d.np2, blk = 2 * (size_t)ldc * nst;
-  const double *cd, *rd_c;
+  const double *cd = c, *rd_c;
   int rc;
-  if ((rc = stage_in(p, c, blk, &p->st_c, &p->st_c_cap, &cd))) return rc;
+  // a host coefficient block is uploaded batch by batch on the copy stream while earlier batches are transformed
+  // (or not at all when the caller tagged it as unchanged since the upload that left it in st_c)
+  const bool chost = !is_device_ptr(c);
+  const bool upload_c = chost && !plan_resident(p, c, ldc, nst);
+  if (chost) {
+    if ((rc = ensure(&p->st_c, &p->st_c_cap, blk))) return rc;
+    cd = p->st_c;
+    if (upload_c) { p->res_ptr = nullptr; if ((rc = plan_copy_streams(p))) return rc; }
+  }
   if ((rc = stage_in(p, rho, N, &p->st_v, &p->st_v_cap, &rd_c))) return rc;
   double* rd = const_cast<double*>(rd_c);
   if ((rc = ensure(&p->fac_dev, &p->fac_cap, nst))) return rc;
   QB_CUDA(cudaMemcpyAsync(p->fac_dev, fac, nst * sizeof(double), cudaMemcpyDefault, p->stream));
   // groups: exclusive owners of a partial density each; enough CTAs to fill the machine
   const int maxG = 16;
-  int ngroups = 1;
-  for (int b0 = 0; b0 < nst;) { int nb, G; plan_split(p, nst - b0, maxG, &nb, &G); ngroups = std::max(ngroups, G); b0 += nb; }
+  int ngroups = 1, nbatches = 0;
+  for (int b0 = 0; b0 < nst;) { int nb, G; plan_split(p, nst - b0, maxG, &nb, &G); ngroups = std::max(ngroups, G); b0 += nb; nbatches++; }
+  if (upload_c) {
+    cudaEvent_t ev;
+    if ((rc = plan_event(p, 0, &ev))) return rc;
+    QB_CUDA(cudaEventRecord(ev, p->stream));              // st_c may still be read by earlier work on the plan's stream
+    QB_CUDA(cudaStreamWaitEvent(p->s_in, ev, 0));
+    int ib = 0;
+    for (int b0 = 0; b0 < nst; ib++) {
+      int nb, G;
+      plan_split(p, nst - b0, maxG, &nb, &G);
+      const size_t off = 2 * (size_t)b0 * ldc, cnt = 2 * (size_t)nb * ldc;
+      QB_CUDA(cudaMemcpyAsync(p->st_c + off, c + off, cnt * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+      if ((rc = plan_event(p, 1 + ib, &ev))) return rc;
+      QB_CUDA(cudaEventRecord(ev, p->s_in));
+      b0 += nb;
+    }
+  }
   if ((rc = ensure(&p->rho_part, &p->rho_part_elems, (size_t)ngroups * N))) return rc;
   QB_CUDA(cudaMemsetAsync(p->rho_part, 0, (size_t)ngroups * N * sizeof(double), p->stream));
-  for (int b0 = 0; b0 < nst;) {
+  int ib = 0;
+  for (int b0 = 0; b0 < nst; ib++) {
     int nb, G;
     plan_split(p, nst - b0, maxG, &nb, &G);
     if ((rc = ensure_work(p, nb))) return rc;
+    if (upload_c) QB_CUDA(cudaStreamWaitEvent(p->stream, p->evs[1 + ib], 0));
     if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
     if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, p->fused ? G : 1, 0))) return rc;
     b0 += nb;
@@ -755,9 +820,8 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);
   prof_end(p->stream);
   QB_LAUNCH_CHECK(p);
-  if (rd != rho) {
-    QB_CUDA(cudaMemcpyAsync(rho, rd, N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    QB_CUDA(cudaStreamSynchronize(p->stream));
-  }
+  if (rd != rho) QB_CUDA(cudaMemcpyAsync(rho, rd, N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (rd != rho || chost) QB_CUDA(cudaStreamSynchronize(p->stream));
+  if (upload_c) plan_mark_resident(p, c, ldc, nst);
   return QB200_OK;
 }

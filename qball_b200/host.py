@@ -54,6 +54,10 @@ class FourierTransform:
     def set_workspace(self, nbytes: int):
         capi._check(self._L.qb200_plan_set_workspace(self._h, int(nbytes)), "qb200_plan_set_workspace")
 
+    def set_coefficient_tag(self, tag: int):
+        """content version of the HOST coefficient blocks passed from now on (0: always upload); see qball_b200.h"""
+        capi._check(self._L.qb200_plan_set_coefficient_tag(self._h, int(tag)), "qb200_plan_set_coefficient_tag")
+
     def backward(self, c, f, c2=None):
         """backward(c, f) / backward(c1, c2, f): f(r) = sum_G c_G e^{+iGr}  (FourierTransform.cc:529-567)"""
         if c2 is None:

@@ -192,3 +192,57 @@ def test_no_device_fallback_is_an_error():
     s = (C.c_int * 1)(3)
     rc = L.qb200_plan_create(C.byref(h), 99, 8, 8, 8, 1, a, a, a, s, 0, 0, 0)
     assert rc == -2 and b"device" in L.qb200_last_error()
+
+
+@pytest.mark.parametrize("kpoint,nst", [((0, 0, 0), 259), ((0.1, 0.2, 0.3), 300)])
+def test_cuda_host_blocks_pipelined_and_resident(kpoint, nst):
+    """HOST coefficient blocks: qb200_hpsi / qb200_compute_density pipeline them in blocks of 128 states (upload,
+    compute, download overlapped); results must equal the device-pointer path and the oracle, for a real basis with an
+    odd tail in the last block and a complex one.  With a coefficient tag the second call reuses the device copy."""
+    cell, ecut = (11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0
+    b = P.make_basis(cell, ecut, kpoint, False)
+    grid = P.density_grid(cell, ecut)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 2, b["is_real"], seed=31)
+    v = R.synth_potential(*grid, seed=32)
+    occ = R.synth_occ(nst, nst - 7)
+    rng = np.random.default_rng(33)
+    species = [dict(na=5, npr=4, lproj=np.array([0, 1, 1, 1], dtype=np.int32), wt=np.array([1.3, -0.6, -0.6, -0.6]),
+                    twnl=rng.standard_normal((4, ngw)) * np.exp(-b["kpg2"] / 4.0)[None, :], tau=rng.uniform(0, 11, (5, 3)))]
+    ft = H.FourierTransform(b, *grid)
+    nlp = H.NonLocalPotential(b, species)
+    # device pointers: one block
+    out_d = _dev(np.zeros_like(c))
+    enl_d = H.hpsi(ft, nlp, _dev(c), occ, _dev(v), _dev(b["kpg2"]), out_d)
+    rho_d = _dev(np.zeros(grid[0] * grid[1] * grid[2]))
+    H.compute_density(ft, _dev(c), 1.0, occ, b["omega"], rho_d)
+    # host pointers (pinned): blocks of 128 states
+    hc = torch.from_numpy(c.copy()).pin_memory()
+    hout = torch.zeros_like(hc).pin_memory()
+    hrho = torch.zeros(grid[0] * grid[1] * grid[2], dtype=torch.float64).pin_memory()
+    ft.set_coefficient_tag(1)
+    enl_h = H.hpsi(ft, nlp, hc, occ, v, b["kpg2"], hout)
+    H.compute_density(ft, hc, 1.0, occ, b["omega"], hrho)          # same tag: no second upload
+    assert abs(enl_h - enl_d) <= 1e-12 * max(1.0, abs(enl_d))
+    assert relerr(hout.numpy(), out_d.cpu().numpy()) < 1e-12
+    assert relerr(hrho.numpy(), rho_d.cpu().numpy()) < 1e-12
+    assert np.all(hout.numpy()[:, ngw:] == 0)
+    # oracle on a few states of the first and the last block
+    sel = [0, 1, nst - 2, nst - 1] if not b["is_real"] else [0, 1]
+    oft = P.FT(b, *grid)
+    _, h_ref = P.hpsi(b, oft, np.ascontiguousarray(c[sel]), v, occ[sel], species)
+    assert relerr(hout.numpy()[sel][:, :ngw], h_ref[:, :ngw]) < TOL
+    # residency semantics: same tag -> the device copy is used; a new tag -> the host block is uploaded again
+    hc[:, :ngw] *= 2.0
+    hrho.zero_()
+    H.compute_density(ft, hc, 1.0, occ, b["omega"], hrho)
+    assert relerr(hrho.numpy(), rho_d.cpu().numpy()) < 1e-12
+    ft.set_coefficient_tag(2)
+    hrho.zero_()
+    H.compute_density(ft, hc, 1.0, occ, b["omega"], hrho)
+    assert relerr(hrho.numpy(), 4.0 * rho_d.cpu().numpy()) < 1e-12
+    ft.set_coefficient_tag(0)
+    hc[:, :ngw] *= 0.5
+    hrho.zero_()
+    H.compute_density(ft, hc, 1.0, occ, b["omega"], hrho)        # tag 0: always uploaded
+    assert relerr(hrho.numpy(), rho_d.cpu().numpy()) < 1e-12
