@@ -360,6 +360,8 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
 
 }  // namespace qb200
 
+#include "nonlocal_3m.cuh"
+
 using namespace qb200;
 
 struct qb200_nl {
@@ -388,6 +390,7 @@ struct qb200_nl {
   bool W_valid;                                // W holds the whole sphere for the current positions
   bool cache_anl;                              // keep a whole-sphere W between energy calls until the atoms move
   int nchunks_last;
+  bool use3m;                                  // complex bases: Karatsuba 3-GEMM form (nonlocal_3m.cuh)
 };
 
 static int nl_ensure(double** buf, size_t* cap, size_t elems)
@@ -431,6 +434,8 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   // off by default: like the reference (comp_anl in every energy call) each call regenerates anl (~1 % of the call)
   nl->cache_anl = false;
   if (const char* e = getenv("QB200_ANL_CACHE")) nl->cache_anl = e[0] == '1';
+  nl->use3m = !is_real;
+  if (const char* e = getenv("QB200_NL_3M")) if (e[0] == '0') nl->use3m = false;
   cudaDeviceProp prop;
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
   nl->nsm = prop.multiProcessorCount;
@@ -443,6 +448,8 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl3, cudaFuncAttributeMaxDynamicSharedMemorySize, N3_FNL_SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_back3, cudaFuncAttributeMaxDynamicSharedMemorySize, N3_BK_SMEM));
   *out = nl;
   return QB200_OK;
 }
@@ -587,7 +594,8 @@ static int nl_generate_chunk(qb200_nl* nl, int gbeg, int gcount, int gpad, size_
   for (const NlSpecies& S : nl->sp) {
     if (S.M <= 0) continue;
     dim3 g((gpad + 127) / 128, S.na);
-    if (nl->is_real) k_anl_gen<1><<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
+    if (nl->use3m) k_anl_gen3<<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
+    else if (nl->is_real) k_anl_gen<1><<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
     else k_anl_gen<0><<<g, 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
     NL_LAUNCH_CHECK(nl);
   }
@@ -598,8 +606,9 @@ static int nl_generate_chunk(qb200_nl* nl, int gbeg, int gcount, int gpad, size_
 // plane-wave chunks the projector sweep of a call takes (1: anl for the whole sphere fits the workspace)
 static void nl_chunking(const qb200_nl* nl, int* gchunk_out, int* nchunks_out)
 {
-  const int RW = nl->is_real ? nl->Mtot : 2 * nl->Mtot;
-  long long gmax = nl->anl_budget / ((long long)std::max(RW, 1) * 16);
+  // bytes of W per plane wave: Gamma Mtot rows x 2 doubles; complex 2*Mtot rows x 2 doubles, or (3M) 24*ceil(Mtot/8) x 1
+  const long long per_g = nl->is_real ? 16ll * nl->Mtot : (nl->use3m ? 8ll * 24 * ((nl->Mtot + 7) / 8) : 32ll * nl->Mtot);
+  long long gmax = nl->anl_budget / std::max(per_g, 1ll);
   gmax = std::max(512ll, (gmax / 512) * 512);
   const int gchunk = (int)std::min<long long>(gmax, ((long long)nl->ngw + 15) / 16 * 16);
   *gchunk_out = gchunk;
@@ -620,22 +629,23 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   if ((rc = nl_refresh_tables(nl))) return rc;
   const int real = nl->is_real;
   const int ncols = real ? nst : 2 * nst;
-  const int RW = real ? Mtot : 2 * Mtot;          // rows of W
+  const bool m3 = nl->use3m && !real;              // Karatsuba form (nonlocal_3m.cuh)
+  const int RW = real ? Mtot : (m3 ? 24 * ((Mtot + 7) / 8) : 2 * Mtot);          // rows of W
   const int Mp = (Mtot + 1) & ~1;                  // even pitch: 16-byte copies of fs stay aligned; the pad is zero
-  const int FP = real ? Mp : 2 * Mp;
+  const int FP = real ? Mp : (m3 ? RW : 2 * Mp);
   // chunking of the plane waves: W = RW x 2*gchunk doubles within the budget
   const int ngw = nl->ngw;
   int gchunk, nchunks;
   nl_chunking(nl, &gchunk, &nchunks);
   nl->nchunks_last = nchunks;
-  const size_t WP = 2 * (size_t)gchunk;
+  const size_t WP = m3 ? (size_t)gchunk : 2 * (size_t)gchunk;
   if (nl->W_cap < (size_t)RW * WP) nl->W_valid = false;
   if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
   // W_valid: W holds anl of the whole sphere for the current positions; reused by later blocks of one call, and
   // across calls when caching is on
   const bool reuse = nchunks == 1 && nl->W_valid && (nl->cache_anl || cont);
   // split K of k_fnl so that the CTAs fill whole waves of the SMs (one CTA per SM)
-  const int mt = (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
+  const int mt = m3 ? (Mtot + N3_MP - 1) / N3_MP : (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
   int ksplit = 1;
   {
     const int maxk = std::max(1, std::min(gchunk, ngw) / 512);
@@ -649,7 +659,7 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   }
   if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * ncols * Mp))) return rc;
   if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, (size_t)nst * FP))) return rc;
-  if (Mp != Mtot) QB_CUDA(cudaMemsetAsync(nl->fs, 0, (size_t)nst * FP * sizeof(double), nl->stream));
+  if (Mp != Mtot || (m3 && RW != 3 * Mtot)) QB_CUDA(cudaMemsetAsync(nl->fs, 0, (size_t)nst * FP * sizeof(double), nl->stream));
   const size_t total = (size_t)nst * Mtot;
   const int nblk = (int)((total + 255) / 256);
   if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
@@ -660,17 +670,19 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
       if ((rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;
       nl->W_valid = nchunks == 1;
     }
-    int kper = (2 * gcount + ksplit - 1) / ksplit;
-    kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
+    int kper = ((m3 ? 1 : 2) * gcount + ksplit - 1) / ksplit;      // reduction index: plane waves (3M) or their reals
+    kper = m3 ? (kper + N3_KS - 1) / N3_KS * N3_KS : (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
     dim3 g1(mt, nt, ksplit);          // a split beyond the chunk's end has no stages and stores zeros
     prof_begin(3, nl->stream);
-    if (real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    if (m3) k_fnl3<<<g1, NL_THREADS, N3_FNL_SMEM, nl->stream>>>(nl->W, WP, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    else if (real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
   }
   prof_begin(4, nl->stream);
-  if (real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
+  if (m3) k_fnl_finish3<<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, FP, nl->eblk);
+  else if (real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
   else k_fnl_finish<0><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
   NL_LAUNCH_CHECK(nl);
   k_sum_blocks<<<1, 32, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
@@ -684,7 +696,8 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     if (i > 0 && (rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;   // (i == 0: still in W from sweep 1)
     dim3 g2((gcount + 63) / 64, nt);
     prof_begin(5, nl->stream);
-    if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
+    if (m3) k_back3<<<dim3(nt, (gcount + N3_GT - 1) / N3_GT), NL_THREADS, N3_BK_SMEM, nl->stream>>>(nl->W, WP, RW, Mtot, gbeg, gcount, gpad, nl->fs, FP, (double2*)cp, ldc, nst);
+    else if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);

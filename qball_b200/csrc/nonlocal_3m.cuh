@@ -1,0 +1,286 @@
+// qball_b200/csrc/nonlocal_3m.cuh -- the projector contractions of complex bases as THREE real DMMA GEMMs each
+// (Karatsuba / "3M" complex product) instead of the four of the straightforward real embedding: 25 % fewer FP64
+// tensor flops for the path's one FP64-pipe-bound stage (NonLocalPotential.cc:2050-2068 fnl = anl^H c and
+// :2150-2171 cp += anl (wt/omega fnl), both zgemm in the reference).
+//
+// With anl = A + iB (A, B real), c = X + iY, fs = F + iH:
+//   fnl = anl^* . c :  P1 = sum A X,  P2 = sum B Y,  P3 = sum (A+B)(Y-X)   ->  Re = P1 + P2,  Im = P3 + P1 - P2
+//   cp += anl . fs  :  R1 = sum A F,  R2 = sum B H,  R3 = sum (A+B)(F+H)   ->  Re = R1 - R2,  Im = R3 - R1 - R2
+// The three "kinds" of the anl operand (A, B, A+B) are materialised per plane-wave chunk by k_anl_gen3 into one real
+// matrix W3: rows grouped by blocks of 8 projectors, row(p, kind) = (p/8)*24 + kind*8 + p%8, one double per plane wave,
+// so that 8 consecutive rows are one m8 (k_fnl3) or two k4 (k_back3) DMMA operand slices of ONE kind.  fs is written in
+// the same row order (F, H, F+H) by k_fnl_finish3.  The c operand stays interleaved (re,im): one LDS.128 yields X and Y
+// of a fragment element, Y-X is one DADD per fragment element (2 % of the DMMA pipe time).
+// Error: the Karatsuba imaginary part is accurate to eps * sum |anl||c| (normwise like the 4-product form; not
+// componentwise) -- far inside the 1e-10 parity tolerance; summation stays deterministic (fixed split-K order).
+#pragma once
+
+namespace qb200 {
+
+#define N3_MP 64                      // projectors per CTA tile of k_fnl3 (x 3 kinds = 192 W3 rows)
+#define N3_NT 128                     // states per CTA tile
+#define N3_KS 16                      // complex plane waves per stage of k_fnl3
+#define N3_APITCH 20                  // doubles per A row in k_fnl3 (16 + 4: conflict-free LDS.64 fragments)
+#define N3_BPITCH 40                  // doubles per B row in k_fnl3 (32 + 8: conflict-free LDS.128 fragments)
+#define N3_ASTAGE (3 * N3_MP * N3_APITCH)
+#define N3_BSTAGE (N3_NT * N3_BPITCH)
+#define N3_FNL_STAGE (N3_ASTAGE + N3_BSTAGE)
+#define N3_FNL_NSTAGE 3
+#define N3_FNL_SMEM (N3_FNL_NSTAGE * N3_FNL_STAGE * 8)
+
+#define N3_GT 64                      // plane waves per CTA tile of k_back3
+#define N3_BK_KROWS 24                // W3 rows per stage of k_back3: one block of 8 projectors x 3 kinds
+#define N3_BK_APITCH 68               // doubles per k-row of the A tile (64 + 4)
+#define N3_BK_BPITCH 36               // doubles per state row of the B tile (24 + 12, = 4 mod 16)
+#define N3_BK_STAGE (N3_BK_KROWS * N3_BK_APITCH + N3_NT * N3_BK_BPITCH)
+#define N3_BK_NSTAGE 4
+#define N3_BK_SMEM (N3_BK_NSTAGE * N3_BK_STAGE * 8)
+
+// grid (ceil(gpad/128), na), block 128: as k_anl_gen, three rows (A, B, A+B) of one double per plane wave
+__global__ void __launch_bounds__(128) k_anl_gen3(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx, int gbeg,
+                                                  int gcount, int gpad, double* __restrict__ W3, size_t WP)
+{
+  const int gl = blockIdx.x * 128 + threadIdx.x;
+  if (gl >= gpad) return;
+  const int ia = blockIdx.y, g = gbeg + gl;
+  const bool ok = gl < gcount;
+  double sn = 0.0, cs = 0.0;
+  if (ok) {
+    if (L.idx != nullptr && S.ph != nullptr) {
+      const double2 e = nl_phase(L, S.ph + (size_t)ia * L.JT, L.idx[g], L.idx[(size_t)ngw + g], L.idx[2 * (size_t)ngw + g]);
+      cs = e.x; sn = e.y;
+    } else {
+      const double arg = -(kpgx[g] * S.tau[3 * ia] + kpgx[(size_t)ngw + g] * S.tau[3 * ia + 1] + kpgx[2 * (size_t)ngw + g] * S.tau[3 * ia + 2]);
+      sincos(arg, &sn, &cs);
+    }
+  }
+  for (int ipr = 0; ipr < S.npr; ipr++) {
+    const int p = S.poff + ia * S.npr + ipr;
+    double2 a = make_double2(0.0, 0.0);
+    if (ok) a = anl_value(S.lproj[ipr], S.twnl[(size_t)ipr * ngw + g], sn, cs);
+    double* row = W3 + ((size_t)(p >> 3) * 24 + (p & 7)) * WP + gl;
+    row[0] = a.x;
+    row[8 * WP] = a.y;
+    row[16 * WP] = a.x + a.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fnl = anl^H c  (3M)
+// grid (ceil(Mtot/64), ceil(nst/128), ksplit), block 512 = 16 warps (4 x 4); warp tile 16 projectors x 3 kinds x 32 states.
+// Reduction over the chunk's plane waves [blockIdx.z*kper, +kper) (kper a multiple of 16).
+// part[(ks*2*nst + 2n+{re,im})*Mp + p]  (=, or += when accumulate) -- the layout k_fnl writes.
+__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper,
+                                                        const double2* __restrict__ c, size_t ldc, int nst,
+                                                        double* __restrict__ part, int Mp, int Mtot, int accumulate)
+{
+  extern __shared__ __align__(16) double nl_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int p0 = blockIdx.x * N3_MP, n0 = blockIdx.y * N3_NT;
+  const int kbeg = blockIdx.z * kper, kend = min(kbeg + kper, gcount);
+  const int nstage = kend > kbeg ? (kend - kbeg + N3_KS - 1) / N3_KS : 0;
+  // A copies: 192 rows x 8 chunks (2 plane waves each) = 3 per thread; B copies: 128 states x 16 plane waves = 4 per thread
+  const int arow = tid >> 3, ach = tid & 7;              // copy i: row arow + 64 i = 24 (8 i / 3 ...) -> recomputed per copy
+  const int bn = tid >> 4, bch = tid & 15;
+  const double* wbase = W3 + (size_t)(p0 / 8) * 24 * WP + 2 * ach;
+  auto issue = [&](int st) {
+    if (st < nstage) {
+      double* As = nl_smem + (st % N3_FNL_NSTAGE) * N3_FNL_STAGE;
+      double* Bs = As + N3_ASTAGE;
+      const int k0 = kbeg + st * N3_KS;
+      const bool kok = k0 + 2 * ach < kend;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int row = arow + 64 * i;
+        const int p = p0 + (row / 24) * 8 + (row & 7);
+        const bool ok = kok && p < Mtot;
+        nl_cp16(As + row * N3_APITCH + 2 * ach, ok ? wbase + (size_t)row * WP + k0 : W3, ok);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int n = bn + 32 * i;
+        const bool ok = n0 + n < nst && k0 + bch < kend;
+        nl_cp16(Bs + n * N3_BPITCH + 2 * bch, ok ? c + (size_t)(n0 + n) * ldc + gbeg + k0 + bch : c, ok);
+      }
+    }
+    nl_cp_commit();
+  };
+  double acc[3][2][4][2];
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
+  const int r = lane >> 2, kq = lane & 3;
+  for (int s = 0; s < N3_FNL_NSTAGE - 1; s++) issue(s);
+  for (int st = 0; st < nstage; st++) {
+    nl_cp_wait_group<N3_FNL_NSTAGE - 2>();
+    __syncthreads();
+    issue(st + N3_FNL_NSTAGE - 1);
+    const double* As = nl_smem + (st % N3_FNL_NSTAGE) * N3_FNL_STAGE;
+    const double* Bs = As + N3_ASTAGE;
+    const double* a0 = As + ((wm * 2) * 24 + r) * N3_APITCH + kq;
+    const double* b0 = Bs + (wn * 32 + r) * N3_BPITCH + 2 * kq;
+#pragma unroll
+    for (int k4 = 0; k4 < N3_KS / 4; k4++) {
+      double a[3][2];
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[q][i] = a0[(i * 24 + q * 8) * N3_APITCH + k4 * 4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double2 v = *reinterpret_cast<const double2*>(b0 + j * 8 * N3_BPITCH + k4 * 8);
+        const double z = v.y - v.x;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          dmma(acc[0][i][j][0], acc[0][i][j][1], a[0][i], v.x);
+          dmma(acc[1][i][j][0], acc[1][i][j][1], a[1][i], v.y);
+          dmma(acc[2][i][j][0], acc[2][i][j][1], a[2][i], z);
+        }
+      }
+    }
+  }
+  const int ncols = 2 * nst;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int p = p0 + wm * 16 + i * 8 + r;
+        const int n = n0 + wn * 32 + j * 8 + 2 * kq + e;
+        if (p < Mtot && n < nst) {
+          const double P1 = acc[0][i][j][e], P2 = acc[1][i][j][e], P3 = acc[2][i][j][e];
+          const double re = P1 + P2, im = P3 + (P1 - P2);
+          double* dr = part + ((size_t)blockIdx.z * ncols + 2 * n) * Mp + p;
+          double* di = dr + Mp;
+          *dr = accumulate ? *dr + re : re;
+          *di = accumulate ? *di + im : im;
+        }
+      }
+}
+
+// one thread per (n, p): split-K reduce, E_nl block partials, fs3[n][row(p,kind)] = wt/omega * (F, H, F+H)
+__global__ void __launch_bounds__(256) k_fnl_finish3(const double* __restrict__ wtp, int Mtot, const double* __restrict__ part, int Mp,
+                                                     int nst, int ksplit, const double* __restrict__ occ, double omega_inv,
+                                                     double* __restrict__ fs3, int FP3, double* __restrict__ eblk)
+{
+  __shared__ double red[256];
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nst * Mtot;
+  double e = 0.0;
+  if (idx < total) {
+    const int n = (int)(idx / Mtot), p = (int)(idx % Mtot);
+    const int ncols = 2 * nst;
+    const double fac = wtp[p] * omega_inv;
+    double fr = 0.0, fi = 0.0;
+    for (int ks = 0; ks < ksplit; ks++) {
+      fr += part[((size_t)ks * ncols + 2 * n) * Mp + p];
+      fi += part[((size_t)ks * ncols + 2 * n + 1) * Mp + p];
+    }
+    e = fac * occ[n] * (fr * fr + fi * fi);
+    double* o = fs3 + (size_t)n * FP3 + (p >> 3) * 24 + (p & 7);
+    const double F = fac * fr, Hh = fac * fi;
+    o[0] = F; o[8] = Hh; o[16] = F + Hh;
+  }
+  red[threadIdx.x] = e;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) eblk[blockIdx.x] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------ cp += anl * fs  (3M)
+// grid (ceil(nst/128), ceil(gcount/64)) -- state tiles fastest, so the CTAs that share a W3 tile run together and W3
+// streams from HBM once; block 512 = 16 warps (4 x 4), warp tile 16 plane waves x 32 states x 3 kinds.
+// Reduction over the RW3 = 24*ceil(Mtot/8) rows of W3, 24 (one projector block, all kinds) per stage.
+__global__ void __launch_bounds__(NL_THREADS, 1) k_back3(const double* __restrict__ W3, size_t WP, int RW3, int Mtot, int gbeg,
+                                                         int gcount, int gpad, const double* __restrict__ fs3, int FP3,
+                                                         double2* __restrict__ cp, size_t ldc, int nst)
+{
+  extern __shared__ __align__(16) double nl_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int n0 = blockIdx.x * N3_NT, gl0 = blockIdx.y * N3_GT;
+  const int nstage = RW3 / N3_BK_KROWS;
+  auto issue = [&](int st) {
+    if (st < nstage) {
+      double* As = nl_smem + (st % N3_BK_NSTAGE) * N3_BK_STAGE;
+      double* Bs = As + N3_BK_KROWS * N3_BK_APITCH;
+      const int k0 = st * N3_BK_KROWS;
+      // A: 24 k-rows x 32 chunks (2 plane waves each) = 768 copies
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int ci = tid + i * NL_THREADS;
+        if (ci < N3_BK_KROWS * 32) {
+          const int kr = ci >> 5, gc = ci & 31;
+          const bool ok = st * 8 + (kr & 7) < Mtot && gl0 + 2 * gc < gpad;
+          nl_cp16(As + kr * N3_BK_APITCH + 2 * gc, ok ? W3 + (size_t)(k0 + kr) * WP + gl0 + 2 * gc : W3, ok);
+        }
+      }
+      // B: 128 states x 12 chunks (2 rows of fs3 each) = 1536 copies
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int ci = tid + i * NL_THREADS, nl = ci / 12, ch = ci - nl * 12;
+        const bool ok = n0 + nl < nst;
+        nl_cp16(Bs + nl * N3_BK_BPITCH + 2 * ch, ok ? fs3 + (size_t)(n0 + nl) * FP3 + k0 + 2 * ch : fs3, ok);
+      }
+    }
+    nl_cp_commit();
+  };
+  double acc[3][2][4][2];
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
+  const int r = lane >> 2, kq = lane & 3;
+  for (int s = 0; s < N3_BK_NSTAGE - 1; s++) issue(s);
+  for (int st = 0; st < nstage; st++) {
+    nl_cp_wait_group<N3_BK_NSTAGE - 2>();
+    __syncthreads();
+    issue(st + N3_BK_NSTAGE - 1);
+    const double* As = nl_smem + (st % N3_BK_NSTAGE) * N3_BK_STAGE;
+    const double* Bs = As + N3_BK_KROWS * N3_BK_APITCH;
+    const double* a0 = As + kq * N3_BK_APITCH + wm * 16 + r;
+    const double* b0 = Bs + (wn * 32 + r) * N3_BK_BPITCH + kq;
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+#pragma unroll
+      for (int k4 = 0; k4 < 2; k4++) {
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[i] = a0[(q * 8 + k4 * 4) * N3_BK_APITCH + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = b0[j * 8 * N3_BK_BPITCH + q * 8 + k4 * 4];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma(acc[q][i][j][0], acc[q][i][j][1], a[i], b[j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int gl = gl0 + wm * 16 + i * 8 + r;
+        const int n = n0 + wn * 32 + j * 8 + 2 * kq + e;
+        if (gl < gcount && n < nst) {
+          const double R1 = acc[0][i][j][e], R2 = acc[1][i][j][e], R3 = acc[2][i][j][e];
+          double2* dst = cp + (size_t)n * ldc + gbeg + gl;
+          double2 v = *dst;
+          v.x += R1 - R2;
+          v.y += R3 - (R1 + R2);
+          *dst = v;
+        }
+      }
+}
+
+}  // namespace qb200
