@@ -391,6 +391,8 @@ struct qb200_nl {
   bool cache_anl;                              // keep a whole-sphere W between energy calls until the atoms move
   int nchunks_last;
   bool use3m;                                  // complex bases: Karatsuba 3-GEMM form (nonlocal_3m.cuh)
+  int tile3m;                                  // 0: 512-thread CTAs (one per SM), 1: 256-thread CTAs (two per SM)
+  size_t W_WP;                                 // row pitch W was last zero-filled for (3M pad rows must be zero)
 };
 
 static int nl_ensure(double** buf, size_t* cap, size_t elems)
@@ -436,6 +438,8 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   if (const char* e = getenv("QB200_ANL_CACHE")) nl->cache_anl = e[0] == '1';
   nl->use3m = !is_real;
   if (const char* e = getenv("QB200_NL_3M")) if (e[0] == '0') nl->use3m = false;
+  nl->tile3m = 1; nl->W_WP = 0;
+  if (const char* e = getenv("QB200_NL_TILE")) nl->tile3m = atoi(e);
   cudaDeviceProp prop;
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
   nl->nsm = prop.multiProcessorCount;
@@ -448,8 +452,10 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl3, cudaFuncAttributeMaxDynamicSharedMemorySize, N3_FNL_SMEM));
-  QB_CUDA(cudaFuncSetAttribute(k_back3, cudaFuncAttributeMaxDynamicSharedMemorySize, N3_BK_SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 4, 3>::SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 2, 2>::SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_back3<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 4, 4>::SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_back3<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 2, 3>::SMEM));
   *out = nl;
   return QB200_OK;
 }
@@ -607,7 +613,7 @@ static int nl_generate_chunk(qb200_nl* nl, int gbeg, int gcount, int gpad, size_
 static void nl_chunking(const qb200_nl* nl, int* gchunk_out, int* nchunks_out)
 {
   // bytes of W per plane wave: Gamma Mtot rows x 2 doubles; complex 2*Mtot rows x 2 doubles, or (3M) 24*ceil(Mtot/8) x 1
-  const long long per_g = nl->is_real ? 16ll * nl->Mtot : (nl->use3m ? 8ll * 24 * ((nl->Mtot + 7) / 8) : 32ll * nl->Mtot);
+  const long long per_g = nl->is_real ? 16ll * nl->Mtot : (nl->use3m ? 8ll * 192 * ((nl->Mtot + 63) / 64) : 32ll * nl->Mtot);
   long long gmax = nl->anl_budget / std::max(per_g, 1ll);
   gmax = std::max(512ll, (gmax / 512) * 512);
   const int gchunk = (int)std::min<long long>(gmax, ((long long)nl->ngw + 15) / 16 * 16);
@@ -639,21 +645,30 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   nl_chunking(nl, &gchunk, &nchunks);
   nl->nchunks_last = nchunks;
   const size_t WP = m3 ? (size_t)gchunk : 2 * (size_t)gchunk;
-  if (nl->W_cap < (size_t)RW * WP) nl->W_valid = false;
-  if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
+  // 3M: W3 is allocated for whole k_fnl3 tiles (64 projectors) plus one k_back3 tile of slack past the last row; rows
+  // that hold no projector stay zero from the fill below
+  const size_t Welems = m3 ? (size_t)192 * ((Mtot + 63) / 64) * WP + 128 : (size_t)RW * WP;
+  if (nl->W_cap < Welems) { nl->W_valid = false; nl->W_WP = 0; }
+  if ((rc = nl_ensure(&nl->W, &nl->W_cap, Welems))) return rc;
+  if (m3 && nl->W_WP != WP) {
+    QB_CUDA(cudaMemsetAsync(nl->W, 0, nl->W_cap * sizeof(double), nl->stream));
+    nl->W_WP = WP; nl->W_valid = false;
+  }
   // W_valid: W holds anl of the whole sphere for the current positions; reused by later blocks of one call, and
   // across calls when caching is on
   const bool reuse = nchunks == 1 && nl->W_valid && (nl->cache_anl || cont);
   // split K of k_fnl so that the CTAs fill whole waves of the SMs (one CTA per SM)
-  const int mt = m3 ? (Mtot + N3_MP - 1) / N3_MP : (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
+  const int nt3 = nl->tile3m == 1 ? 64 : 128;      // states per CTA tile of the 3M kernels
+  const int mt = m3 ? (Mtot + 63) / 64 : (RW + NL_TM - 1) / NL_TM, nt = m3 ? (nst + nt3 - 1) / nt3 : (nst + NL_TN - 1) / NL_TN;
+  const int slots = (m3 && nl->tile3m == 1) ? 2 * nl->nsm : nl->nsm;   // resident CTAs
   int ksplit = 1;
   {
     const int maxk = std::max(1, std::min(gchunk, ngw) / 512);
     double best = -1.0;
     for (int k = 1; k <= std::min(maxk, 64); k++) {
       const long ctas = (long)mt * nt * k;
-      const long waves = (ctas + nl->nsm - 1) / nl->nsm;
-      const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;   // mild preference for fewer partials
+      const long waves = (ctas + slots - 1) / slots;
+      const double eff = (double)ctas / (double)(waves * slots) - 0.002 * k;   // mild preference for fewer partials
       if (eff > best) { best = eff; ksplit = k; }
     }
   }
@@ -674,7 +689,8 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     kper = m3 ? (kper + N3_KS - 1) / N3_KS * N3_KS : (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
     dim3 g1(mt, nt, ksplit);          // a split beyond the chunk's end has no stages and stores zeros
     prof_begin(3, nl->stream);
-    if (m3) k_fnl3<<<g1, NL_THREADS, N3_FNL_SMEM, nl->stream>>>(nl->W, WP, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    if (m3 && nl->tile3m == 1) k_fnl3<4, 2, 2><<<g1, 256, Fnl3Cfg<4, 2, 2>::SMEM, nl->stream>>>(nl->W, WP, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    else if (m3) k_fnl3<4, 4, 3><<<g1, 512, Fnl3Cfg<4, 4, 3>::SMEM, nl->stream>>>(nl->W, WP, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     else if (real) k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     else k_fnl<0><<<g1, NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
     prof_end(nl->stream);
@@ -696,7 +712,8 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     if (i > 0 && (rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;   // (i == 0: still in W from sweep 1)
     dim3 g2((gcount + 63) / 64, nt);
     prof_begin(5, nl->stream);
-    if (m3) k_back3<<<dim3(nt, (gcount + N3_GT - 1) / N3_GT), NL_THREADS, N3_BK_SMEM, nl->stream>>>(nl->W, WP, RW, Mtot, gbeg, gcount, gpad, nl->fs, FP, (double2*)cp, ldc, nst);
+    if (m3 && nl->tile3m == 1) k_back3<4, 2, 3><<<dim3(nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
+    else if (m3) k_back3<4, 4, 4><<<dim3(nt, (gcount + 63) / 64), 512, Back3Cfg<4, 4, 4>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     else if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
     prof_end(nl->stream);

@@ -17,24 +17,23 @@
 
 namespace qb200 {
 
-#define N3_MP 64                      // projectors per CTA tile of k_fnl3 (x 3 kinds = 192 W3 rows)
-#define N3_NT 128                     // states per CTA tile
 #define N3_KS 16                      // complex plane waves per stage of k_fnl3
 #define N3_APITCH 20                  // doubles per A row in k_fnl3 (16 + 4: conflict-free LDS.64 fragments)
 #define N3_BPITCH 40                  // doubles per B row in k_fnl3 (32 + 8: conflict-free LDS.128 fragments)
-#define N3_ASTAGE (3 * N3_MP * N3_APITCH)
-#define N3_BSTAGE (N3_NT * N3_BPITCH)
-#define N3_FNL_STAGE (N3_ASTAGE + N3_BSTAGE)
-#define N3_FNL_NSTAGE 3
-#define N3_FNL_SMEM (N3_FNL_NSTAGE * N3_FNL_STAGE * 8)
-
-#define N3_GT 64                      // plane waves per CTA tile of k_back3
 #define N3_BK_KROWS 24                // W3 rows per stage of k_back3: one block of 8 projectors x 3 kinds
-#define N3_BK_APITCH 68               // doubles per k-row of the A tile (64 + 4)
-#define N3_BK_BPITCH 36               // doubles per state row of the B tile (24 + 12, = 4 mod 16)
-#define N3_BK_STAGE (N3_BK_KROWS * N3_BK_APITCH + N3_NT * N3_BK_BPITCH)
-#define N3_BK_NSTAGE 4
-#define N3_BK_SMEM (N3_BK_NSTAGE * N3_BK_STAGE * 8)
+#define N3_BK_BPITCH 36               // doubles per state row of the B tile of k_back3 (24 + 12, = 4 mod 16)
+
+// Tile geometry: NWM x NWN warps; a warp owns 16 projectors (k_fnl3) or 16 plane waves (k_back3) x 32 states x 3 kinds
+// (24 m8n8 accumulators).  <4,4>: 512 threads, one CTA per SM, 3-4 stages; <4,2>: 256 threads, two CTAs per SM whose
+// stage barriers and pipeline fills overlap each other.
+template <int NWM, int NWN, int NSTG> struct Fnl3Cfg {
+  static constexpr int NTHR = 32 * NWM * NWN, MP = 16 * NWM, NT = 32 * NWN;
+  static constexpr int ASTAGE = 3 * MP * N3_APITCH, STAGE = ASTAGE + NT * N3_BPITCH, SMEM = NSTG * STAGE * 8;
+};
+template <int NWM, int NWN, int NSTG> struct Back3Cfg {
+  static constexpr int NTHR = 32 * NWM * NWN, GT = 16 * NWM, NT = 32 * NWN;
+  static constexpr int APITCH = GT + 4, ASTAGE = N3_BK_KROWS * APITCH, STAGE = ASTAGE + NT * N3_BK_BPITCH, SMEM = NSTG * STAGE * 8;
+};
 
 // grid (ceil(gpad/128), na), block 128: as k_anl_gen, three rows (A, B, A+B) of one double per plane wave
 __global__ void __launch_bounds__(128) k_anl_gen3(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx, int gbeg,
@@ -66,41 +65,39 @@ __global__ void __launch_bounds__(128) k_anl_gen3(NlSpecies S, NlLattice L, int 
 }
 
 // ------------------------------------------------------------------------------------------------ fnl = anl^H c  (3M)
-// grid (ceil(Mtot/64), ceil(nst/128), ksplit), block 512 = 16 warps (4 x 4); warp tile 16 projectors x 3 kinds x 32 states.
-// Reduction over the chunk's plane waves [blockIdx.z*kper, +kper) (kper a multiple of 16).
-// part[(ks*2*nst + 2n+{re,im})*Mp + p]  (=, or += when accumulate) -- the layout k_fnl writes.
-__global__ void __launch_bounds__(NL_THREADS, 1) k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper,
-                                                        const double2* __restrict__ c, size_t ldc, int nst,
-                                                        double* __restrict__ part, int Mp, int Mtot, int accumulate)
+// grid (ceil(Mtot/MP), ceil(nst/NT), ksplit).  Reduction over the chunk's plane waves [blockIdx.z*kper, +kper) (kper a
+// multiple of 16).  W3 needs no bounds checks: its pad rows (projectors >= Mtot of the last block of 8) and pad columns
+// (plane waves gcount..gpad) are zero.  part[(ks*2*nst + 2n+{re,im})*Mp + p]  (=, or += when accumulate).
+template <int NWM, int NWN, int NSTG>
+__global__ void __launch_bounds__(32 * NWM * NWN, 512 / (32 * NWM * NWN))
+k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper, const double2* __restrict__ c, size_t ldc, int nst,
+       double* __restrict__ part, int Mp, int Mtot, int accumulate)
 {
+  typedef Fnl3Cfg<NWM, NWN, NSTG> C;
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int p0 = blockIdx.x * N3_MP, n0 = blockIdx.y * N3_NT;
+  const int wm = warp / NWN, wn = warp - wm * NWN;
+  const int p0 = blockIdx.x * C::MP, n0 = blockIdx.y * C::NT;
   const int kbeg = blockIdx.z * kper, kend = min(kbeg + kper, gcount);
   const int nstage = kend > kbeg ? (kend - kbeg + N3_KS - 1) / N3_KS : 0;
-  // A copies: 192 rows x 8 chunks (2 plane waves each) = 3 per thread; B copies: 128 states x 16 plane waves = 4 per thread
-  const int arow = tid >> 3, ach = tid & 7;              // copy i: row arow + 64 i = 24 (8 i / 3 ...) -> recomputed per copy
-  const int bn = tid >> 4, bch = tid & 15;
-  const double* wbase = W3 + (size_t)(p0 / 8) * 24 * WP + 2 * ach;
+  // A copies: 3*MP rows x 8 chunks (2 plane waves each); B copies: NT states x 16 plane waves
+  constexpr int ACOP = 3 * C::MP * 8 / C::NTHR, BCOP = C::NT * 16 / C::NTHR, AROWS = C::NTHR / 8, BROWS = C::NTHR / 16;
+  const int arow = tid >> 3, ach = tid & 7, bn = tid >> 4, bch = tid & 15;
+  const double* wsrc = W3 + ((size_t)(p0 / 8) * 24 + arow) * WP + 2 * ach;
+  const double2* csrc = c + (size_t)(n0 + bn) * ldc + gbeg + bch;
   auto issue = [&](int st) {
     if (st < nstage) {
-      double* As = nl_smem + (st % N3_FNL_NSTAGE) * N3_FNL_STAGE;
-      double* Bs = As + N3_ASTAGE;
+      double* As = nl_smem + (st % NSTG) * C::STAGE;
+      double* Bs = As + C::ASTAGE;
       const int k0 = kbeg + st * N3_KS;
-      const bool kok = k0 + 2 * ach < kend;
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const int row = arow + 64 * i;
-        const int p = p0 + (row / 24) * 8 + (row & 7);
-        const bool ok = kok && p < Mtot;
-        nl_cp16(As + row * N3_APITCH + 2 * ach, ok ? wbase + (size_t)row * WP + k0 : W3, ok);
-      }
+      for (int i = 0; i < ACOP; i++)
+        nl_cp16(As + (arow + AROWS * i) * N3_APITCH + 2 * ach, wsrc + (size_t)(AROWS * i) * WP + k0, true);
+      const bool kok = k0 + bch < kend;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int n = bn + 32 * i;
-        const bool ok = n0 + n < nst && k0 + bch < kend;
-        nl_cp16(Bs + n * N3_BPITCH + 2 * bch, ok ? c + (size_t)(n0 + n) * ldc + gbeg + k0 + bch : c, ok);
+      for (int i = 0; i < BCOP; i++) {
+        const bool ok = kok && n0 + bn + BROWS * i < nst;
+        nl_cp16(Bs + (bn + BROWS * i) * N3_BPITCH + 2 * bch, ok ? csrc + (size_t)(BROWS * i) * ldc + k0 : c, ok);
       }
     }
     nl_cp_commit();
@@ -113,15 +110,14 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl3(const double* __restrict
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
   const int r = lane >> 2, kq = lane & 3;
-  for (int s = 0; s < N3_FNL_NSTAGE - 1; s++) issue(s);
+  for (int s = 0; s < NSTG - 1; s++) issue(s);
   for (int st = 0; st < nstage; st++) {
-    nl_cp_wait_group<N3_FNL_NSTAGE - 2>();
+    nl_cp_wait_group<NSTG - 2>();
     __syncthreads();
-    issue(st + N3_FNL_NSTAGE - 1);
-    const double* As = nl_smem + (st % N3_FNL_NSTAGE) * N3_FNL_STAGE;
-    const double* Bs = As + N3_ASTAGE;
+    issue(st + NSTG - 1);
+    const double* As = nl_smem + (st % NSTG) * C::STAGE;
     const double* a0 = As + ((wm * 2) * 24 + r) * N3_APITCH + kq;
-    const double* b0 = Bs + (wn * 32 + r) * N3_BPITCH + 2 * kq;
+    const double* b0 = As + C::ASTAGE + (wn * 32 + r) * N3_BPITCH + 2 * kq;
 #pragma unroll
     for (int k4 = 0; k4 < N3_KS / 4; k4++) {
       double a[3][2];
@@ -195,37 +191,37 @@ __global__ void __launch_bounds__(256) k_fnl_finish3(const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ cp += anl * fs  (3M)
-// grid (ceil(nst/128), ceil(gcount/64)) -- state tiles fastest, so the CTAs that share a W3 tile run together and W3
-// streams from HBM once; block 512 = 16 warps (4 x 4), warp tile 16 plane waves x 32 states x 3 kinds.
-// Reduction over the RW3 = 24*ceil(Mtot/8) rows of W3, 24 (one projector block, all kinds) per stage.
-__global__ void __launch_bounds__(NL_THREADS, 1) k_back3(const double* __restrict__ W3, size_t WP, int RW3, int Mtot, int gbeg,
-                                                         int gcount, int gpad, const double* __restrict__ fs3, int FP3,
-                                                         double2* __restrict__ cp, size_t ldc, int nst)
+// grid (ceil(nst/NT), ceil(gcount/GT)) -- state tiles fastest, so the CTAs that share a W3 tile run together and W3
+// streams from HBM once.  Reduction over the RW3 = 24*ceil(Mtot/8) rows of W3, 24 (one projector block, all kinds) per
+// stage; pad rows/columns of W3 and pad rows of fs3 are zero.
+template <int NWM, int NWN, int NSTG>
+__global__ void __launch_bounds__(32 * NWM * NWN, 512 / (32 * NWM * NWN))
+k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount, const double* __restrict__ fs3, int FP3,
+        double2* __restrict__ cp, size_t ldc, int nst)
 {
+  typedef Back3Cfg<NWM, NWN, NSTG> C;
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int n0 = blockIdx.x * N3_NT, gl0 = blockIdx.y * N3_GT;
+  const int wm = warp / NWN, wn = warp - wm * NWN;
+  const int n0 = blockIdx.x * C::NT, gl0 = blockIdx.y * C::GT;
   const int nstage = RW3 / N3_BK_KROWS;
+  constexpr int ACH = C::GT / 2, ATOT = N3_BK_KROWS * ACH, BTOT = C::NT * 12;   // 16-byte copies per stage
   auto issue = [&](int st) {
     if (st < nstage) {
-      double* As = nl_smem + (st % N3_BK_NSTAGE) * N3_BK_STAGE;
-      double* Bs = As + N3_BK_KROWS * N3_BK_APITCH;
+      double* As = nl_smem + (st % NSTG) * C::STAGE;
+      double* Bs = As + C::ASTAGE;
       const int k0 = st * N3_BK_KROWS;
-      // A: 24 k-rows x 32 chunks (2 plane waves each) = 768 copies
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        const int ci = tid + i * NL_THREADS;
-        if (ci < N3_BK_KROWS * 32) {
-          const int kr = ci >> 5, gc = ci & 31;
-          const bool ok = st * 8 + (kr & 7) < Mtot && gl0 + 2 * gc < gpad;
-          nl_cp16(As + kr * N3_BK_APITCH + 2 * gc, ok ? W3 + (size_t)(k0 + kr) * WP + gl0 + 2 * gc : W3, ok);
+      for (int i = 0; i < (ATOT + C::NTHR - 1) / C::NTHR; i++) {
+        const int ci = tid + i * C::NTHR;
+        if (ATOT % C::NTHR == 0 || ci < ATOT) {
+          const int kr = ci / ACH, gc = ci - kr * ACH;
+          nl_cp16(As + kr * C::APITCH + 2 * gc, W3 + (size_t)(k0 + kr) * WP + gl0 + 2 * gc, true);
         }
       }
-      // B: 128 states x 12 chunks (2 rows of fs3 each) = 1536 copies
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const int ci = tid + i * NL_THREADS, nl = ci / 12, ch = ci - nl * 12;
+      for (int i = 0; i < BTOT / C::NTHR; i++) {
+        const int ci = tid + i * C::NTHR, nl = ci / 12, ch = ci - nl * 12;
         const bool ok = n0 + nl < nst;
         nl_cp16(Bs + nl * N3_BK_BPITCH + 2 * ch, ok ? fs3 + (size_t)(n0 + nl) * FP3 + k0 + 2 * ch : fs3, ok);
       }
@@ -240,22 +236,21 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back3(const double* __restric
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
   const int r = lane >> 2, kq = lane & 3;
-  for (int s = 0; s < N3_BK_NSTAGE - 1; s++) issue(s);
+  for (int s = 0; s < NSTG - 1; s++) issue(s);
   for (int st = 0; st < nstage; st++) {
-    nl_cp_wait_group<N3_BK_NSTAGE - 2>();
+    nl_cp_wait_group<NSTG - 2>();
     __syncthreads();
-    issue(st + N3_BK_NSTAGE - 1);
-    const double* As = nl_smem + (st % N3_BK_NSTAGE) * N3_BK_STAGE;
-    const double* Bs = As + N3_BK_KROWS * N3_BK_APITCH;
-    const double* a0 = As + kq * N3_BK_APITCH + wm * 16 + r;
-    const double* b0 = Bs + (wn * 32 + r) * N3_BK_BPITCH + kq;
+    issue(st + NSTG - 1);
+    const double* As = nl_smem + (st % NSTG) * C::STAGE;
+    const double* a0 = As + kq * C::APITCH + wm * 16 + r;
+    const double* b0 = As + C::ASTAGE + (wn * 32 + r) * N3_BK_BPITCH + kq;
 #pragma unroll
     for (int q = 0; q < 3; q++)
 #pragma unroll
       for (int k4 = 0; k4 < 2; k4++) {
         double a[2], b[4];
 #pragma unroll
-        for (int i = 0; i < 2; i++) a[i] = a0[(q * 8 + k4 * 4) * N3_BK_APITCH + i * 8];
+        for (int i = 0; i < 2; i++) a[i] = a0[(q * 8 + k4 * 4) * C::APITCH + i * 8];
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = b0[j * 8 * N3_BK_BPITCH + q * 8 + k4 * 4];
 #pragma unroll
