@@ -44,6 +44,9 @@ struct DevPlan {
   const int *zq, *zqm;                 // per coefficient: digit-reversed z position | column << 12 (zqm: the -G image, real bases)
   int zb_rb, zb_cb, zb_cmax;           // rods per CTA, columns per tile, max coefficients per rod block
   int zf_rb, zf_cb, zf_cmax;
+  // second-generation split xy stage (split_kernels.cuh)
+  const int *xs_jr, *xs_x;             // per entry of keepcols: kept-row index, digit-reversed x position
+  const int *yq;                       // natural y index held by position q after the y DIF transform
 };
 
 enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
@@ -66,6 +69,10 @@ struct qb200_plan {
   std::vector<void*> owned;            // device allocations freed at destroy
   bool fused;                          // plane fits in shared memory
   size_t smem_z, smem_plane, smem_rows, smem_ycol;
+  bool split2;                         // second-generation split xy kernels in use (planes larger than shared memory)
+  int split_static;                    // 0 generic engine, 1 compiled 252 x 252 shape (gold benchmark)
+  int xr_rowb, xr_smax;                // k_xrows2: rows per CTA, max column values per row block
+  size_t smem_xr[2], smem_yc[4];       // dynamic shared memory of k_xrows2<+1/-1>, k_ycols2<OP>
   bool z2;                             // second-generation z-column kernels in use
   size_t smem_zb[2], smem_zf[2];       // their dynamic shared memory, [MODE_SINGLE], [MODE_PAIR]
   int zslots_b[2], zslots_f[2];        // resident CTAs on the whole device

@@ -3,6 +3,7 @@
 // wavefunction data happens in the kernels of transform_kernels.cuh.  There is no CPU fallback.
 #include "transform_kernels.cuh"
 #include "zcol_kernels.cuh"
+#include "split_kernels.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -216,6 +217,8 @@ static int ensure_work(qb200_plan* p, int units)
   return QB200_OK;
 }
 
+typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;   // examples/gold_benchmark: 252 x 252 x 896 grid
+
 // ------------------------------------------------------------------------------------------------ z-column kernels v2
 // Picks, for each direction, the number of columns per tile (cb; rb = rods per CTA) so that the persistent grid
 // (rod blocks x G) fills the resident-CTA slots of the device as evenly as possible, and records shared-memory sizes.
@@ -375,7 +378,12 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     for (int jr = 0; jr < d.nkeep; jr++) { rowstart[jr] = k; for (int iv : by[jr]) keepcols[k++] = iv; }
     rowstart[d.nkeep] = k;
   }
+  std::vector<int> xs_jr(d.nvec), xs_x(d.nvec), yq(np1);
+  for (int jr = 0; jr < d.nkeep; jr++)
+    for (int i = rowstart[jr]; i < rowstart[jr + 1]; i++) { xs_jr[i] = jr; xs_x[i] = xpos[colhk[keepcols[i]] % np0]; }
+  for (int q = 0; q < np1; q++) yq[q] = digit_reverse(d.f1, q);
   int rc;
+  if ((rc = upload(p, xs_jr, &d.xs_jr)) || (rc = upload(p, xs_x, &d.xs_x)) || (rc = upload(p, yq, &d.yq))) { qb200_plan_destroy(p); return rc; }
   if ((rc = upload(p, first, &d.rod_first)) || (rc = upload(p, size, &d.rod_size)) || (rc = upload(p, lmin, &d.rod_lmin)) ||
       (rc = upload(p, colpos, &d.colpos)) || (rc = upload(p, yrev, &d.yrev)) || (rc = upload(p, colhk, &d.colhk)) || (rc = upload(p, keepcols, &d.keepcols)) ||
       (rc = upload(p, rowstart, &d.keeprowstart))) { qb200_plan_destroy(p); return rc; }
@@ -442,6 +450,48 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       (rc = opt_in_smem(k_zcol_fwd<MODE_SINGLE>, p->smem_z)) || (rc = opt_in_smem(k_zcol_fwd<MODE_PAIR>, p->smem_z))) {
     qb200_plan_destroy(p); return rc;
   }
+  p->split2 = false;
+  if (!p->fused) {
+    // second-generation split kernels: rows per x CTA sized for two resident CTAs, shared-memory budgets per kernel
+    const size_t rowbytes = (size_t)d.pitch0 * 16;
+    int rowb = (int)std::min<size_t>(d.nkeep, std::max<size_t>(1, (40 * 1024) / rowbytes));
+    if (rowb > 8) rowb = 8;
+    int smax = 4;
+    for (int jr0 = 0; jr0 < d.nkeep; jr0 += rowb) smax = std::max(smax, rowstart[std::min(jr0 + rowb, d.nkeep)] - rowstart[jr0]);
+    smax = (smax + 3) & ~3;
+    p->xr_rowb = rowb; p->xr_smax = smax;
+    p->smem_xr[0] = (size_t)d.f0.twsize * 16 + (size_t)rowb * rowbytes + (size_t)smax * (16 + 8);
+    p->smem_xr[1] = (size_t)d.f0.twsize * 16 + 2 * (size_t)rowb * rowbytes + (size_t)smax * 8;
+    const size_t ybase = (size_t)d.f1.twsize * 16 + (size_t)((np1 + 3) & ~3) * 4 + (size_t)np1 * (d.xb | 1) * 16 + (size_t)d.nkeep * d.xb * 16;
+    for (int op = 0; op < 4; op++) p->smem_yc[op] = ybase + (op == OP_DENSITY ? (size_t)np1 * d.xb * 8 : 0);
+    const char* e2 = getenv("QB200_SPLIT2");
+    size_t need = std::max(p->smem_xr[0], p->smem_xr[1]);
+    for (int op = 0; op < 4; op++) need = std::max(need, p->smem_yc[op]);
+    p->split2 = !(e2 && e2[0] == '0') && need <= (size_t)p->max_smem;
+    if (p->split2 &&
+        ((rc = opt_in_smem(k_xrows2<+1, DynSplit>, p->smem_xr[0])) || (rc = opt_in_smem(k_xrows2<-1, DynSplit>, p->smem_xr[1])) ||
+         (rc = opt_in_smem(k_ycols2<OP_HPSI, DynSplit>, p->smem_yc[OP_HPSI])) || (rc = opt_in_smem(k_ycols2<OP_DENSITY, DynSplit>, p->smem_yc[OP_DENSITY])) ||
+         (rc = opt_in_smem(k_ycols2<OP_BWD, DynSplit>, p->smem_yc[OP_BWD])) || (rc = opt_in_smem(k_ycols2<OP_FWD, DynSplit>, p->smem_yc[OP_FWD])))) {
+      qb200_plan_destroy(p); return rc;
+    }
+    // compiled shape: the gold benchmark's 252 x 252 planes (examples/gold_benchmark, |h|,|k| <= 55)
+    p->split_static = 0;
+    {
+      typedef ShapeAu992 S;
+      int hmax = 0;
+      for (int r = 0; r < nrods; r++) hmax = std::max(hmax, std::abs(rod_h[r]));
+      const char* ns = getenv("QB200_NO_STATIC");
+      if (p->split2 && !(ns && ns[0] == '1') && np0 == S::NP0 && np1 == S::NP1 && d.ksplit == S::YSPLIT && d.kskip == S::YSKIP &&
+          hmax < S::XSPLIT && d.xb == S::XB && rowb == S::ROWB) {
+        p->split_static = 1;
+        if ((rc = opt_in_smem(k_xrows2<+1, S>, p->smem_xr[0])) || (rc = opt_in_smem(k_xrows2<-1, S>, p->smem_xr[1])) ||
+            (rc = opt_in_smem(k_ycols2<OP_HPSI, S>, p->smem_yc[OP_HPSI])) || (rc = opt_in_smem(k_ycols2<OP_DENSITY, S>, p->smem_yc[OP_DENSITY])) ||
+            (rc = opt_in_smem(k_ycols2<OP_BWD, S>, p->smem_yc[OP_BWD])) || (rc = opt_in_smem(k_ycols2<OP_FWD, S>, p->smem_yc[OP_FWD]))) {
+          qb200_plan_destroy(p); return rc;
+        }
+      }
+    }
+  }
   if (p->fused) {
     // (opt-in for the plane kernels happens after the thread geometry is chosen, below)
   } else {
@@ -480,7 +530,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     p->static_shape = plane_select_static(p, hmax);
     if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
   }
-  p->ws_bytes = p->fused ? (256ll << 20) : (3ll << 30);
+  p->ws_bytes = p->fused ? (256ll << 20) : (8ll << 30);
   if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
   configure_batch(p);
   *out = p;
@@ -538,6 +588,8 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 9: return p->launches;
     case 10: return p->static_shape;
     case 11: return p->z2 ? 1 : 0;
+    case 14: return p->split2 ? 1 : 0;
+    case 15: return p->split_static;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;
@@ -609,6 +661,30 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
     prof_end(p->stream);
     if (rc) return rc;
     p->launches++;
+    return QB200_OK;
+  }
+  if (p->split2) {
+    // persistent CTAs per (block, plane); G spreads the units of the batch only when the planes alone cannot fill the SMs
+    const int nrb = (d.nkeep + p->xr_rowb - 1) / p->xr_rowb, nxb = (d.np0 + d.xb - 1) / d.xb;
+    auto spread = [&](long ctas) { return (int)std::max(1l, std::min<long>(nunits, (4l * p->nsm + ctas - 1) / ctas)); };
+    const dim3 gr(nrb, d.np2, spread((long)nrb * d.np2));
+    const dim3 gy(nxb, d.np2, OP == OP_DENSITY ? std::max(1, std::min(ngroups, nunits)) : spread((long)nxb * d.np2));
+    prof_begin(1, p->stream);
+    const bool st = p->split_static == 1;
+    if (OP != OP_FWD) {
+      if (st) k_xrows2<+1, ShapeAu992><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+      else k_xrows2<+1, DynSplit><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+      QB_LAUNCH_CHECK(p);
+    }
+    if (st) k_ycols2<OP, ShapeAu992><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
+    else k_ycols2<OP, DynSplit><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
+    QB_LAUNCH_CHECK(p);
+    if (OP == OP_HPSI || OP == OP_FWD) {
+      if (st) k_xrows2<-1, ShapeAu992><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+      else k_xrows2<-1, DynSplit><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+      QB_LAUNCH_CHECK(p);
+    }
+    prof_end(p->stream);
     return QB200_OK;
   }
   const int rowb = (int)((p->smem_rows / 16 - d.np0) / d.pitch0);

@@ -246,3 +246,46 @@ def test_cuda_host_blocks_pipelined_and_resident(kpoint, nst):
     hrho.zero_()
     H.compute_density(ft, hc, 1.0, occ, b["omega"], hrho)        # tag 0: always uploaded
     assert relerr(hrho.numpy(), rho_d.cpu().numpy()) < 1e-12
+
+
+def test_properties_au992_full_size_split_path(monkeypatch):
+    """BASELINE-size shape (gold benchmark: 252 x 252 x 896 grid, ngw 2.84 M, planes larger than shared memory): the
+    compiled-shape split kernels against the run-time-shape split kernels (which the forced-split fixtures tie to the
+    reference), plus size-independent properties: Parseval, fwd(bwd(c)) = c, integral of rho."""
+    cell, ecut, kpoint = (30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), 65.0, (1e-7, 0, 0)
+    b = P.make_basis(cell, ecut, kpoint, False)
+    grid = P.density_grid(cell, ecut)
+    assert grid == (252, 252, 896) and not b["is_real"]
+    N, ngw, nst = grid[0] * grid[1] * grid[2], b["ngw"], 3
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw, False, seed=41)
+    v = R.synth_potential(*grid, seed=42)
+    occ = np.array([2.0, 1.0, 0.5])
+    cd, vd = _dev(c), _dev(v)
+    res = {}
+    for mode in ("static", "generic"):
+        if mode == "generic":
+            monkeypatch.setenv("QB200_NO_STATIC", "1")
+        ft = H.FourierTransform(b, *grid)
+        ft.set_workspace(2 << 30)
+        assert not ft.fused() and ft.query(14) == 1 and ft.query(15) == (1 if mode == "static" else 0)
+        h = torch.zeros_like(cd)
+        H.rs_mul_add(ft, cd, vd, h, kpg2=_dev(b["kpg2"]))
+        rho = torch.zeros(N, dtype=torch.float64, device="cuda")
+        H.compute_density(ft, cd, 1.0, occ, b["omega"], rho)
+        res[mode] = (h.cpu().numpy(), rho.cpu().numpy())
+        if mode == "static":
+            f = torch.zeros(N, dtype=torch.complex128, device="cuda")
+            ft.backward(cd[0].contiguous(), f)
+            nrm = float((f.abs() ** 2).sum().item()) / N
+            assert abs(nrm - float(np.vdot(c[0], c[0]).real)) < 1e-10 * nrm          # Parseval
+            back = torch.zeros(ngw, dtype=torch.complex128, device="cuda")
+            ft.forward(f, back)
+            assert relerr(back.cpu().numpy(), c[0]) < 1e-12                           # round trip
+            del f, back
+            nel = float(rho.sum().item()) * b["omega"] / N
+            want = float(sum(occ[n] * np.vdot(c[n], c[n]).real for n in range(nst)))
+            assert abs(nel - want) < 1e-10 * want
+        del ft, h, rho
+        torch.cuda.empty_cache()
+    assert relerr(res["static"][0], res["generic"][0]) < 1e-12
+    assert relerr(res["static"][1], res["generic"][1]) < 1e-12
