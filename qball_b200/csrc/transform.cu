@@ -217,7 +217,9 @@ static int ensure_work(qb200_plan* p, int units)
   return QB200_OK;
 }
 
-typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;   // examples/gold_benchmark: 252 x 252 x 896 grid
+typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;
+typedef qb200::ZShape<112, 29, 26, 60> ZbMgO216;   // examples/MgO216: 112 planes, |l| <= 25; 29 / 22 columns per tile fill one wave
+typedef qb200::ZShape<112, 22, 26, 60> ZfMgO216;   // examples/gold_benchmark: 252 x 252 x 896 grid
 
 // ------------------------------------------------------------------------------------------------ z-column kernels v2
 // Picks, for each direction, the number of columns per tile (cb; rb = rods per CTA) so that the persistent grid
@@ -269,7 +271,7 @@ bool z2_pick(const qb200_plan* p, const std::vector<int>& first, bool fwd, size_
 }
 }  // namespace
 
-static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t smem_sm)
+static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t smem_sm, int lmax)
 {
   DevPlan& d = p->d;
   p->z2 = false;
@@ -278,19 +280,29 @@ static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t sme
   int fb = 0, ff = 0;
   if (const char* e = getenv("QB200_ZB_COLS")) fb = atoi(e);
   if (const char* e = getenv("QB200_ZF_COLS")) ff = atoi(e);
+  // compiled shape (MgO216's 112 planes): its tile widths are fixed at compile time
+  p->z_static = 0;
+  {
+    const char* ns = getenv("QB200_NO_STATIC");
+    if (!(ns && ns[0] == '1') && !d.is_real && d.np2 == ZbMgO216::NP2 && lmax < ZbMgO216::ZSPLIT && fb == 0 && ff == 0) {
+      p->z_static = 1; fb = ZbMgO216::CB; ff = ZfMgO216::CB;
+    }
+  }
   Z2Choice b, f;
-  if (!z2_pick(p, first, false, smem_sm, fb, &b) || !z2_pick(p, first, true, smem_sm, ff, &f)) return QB200_OK;
+  if (!z2_pick(p, first, false, smem_sm, fb, &b) || !z2_pick(p, first, true, smem_sm, ff, &f)) { p->z_static = 0; return QB200_OK; }
   d.zb_cb = b.cb; d.zb_rb = b.rb; d.zb_cmax = b.cmax;
   d.zf_cb = f.cb; d.zf_rb = f.rb; d.zf_cmax = f.cmax;
   int rc;
   for (int mode = 0; mode < 2; mode++) { p->smem_zb[mode] = b.smem[mode]; p->smem_zf[mode] = f.smem[mode]; }
-  if ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_bwd2<MODE_PAIR>, p->smem_zb[1])) ||
-      (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE>, p->smem_zf[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_PAIR>, p->smem_zf[1]))) return rc;
+  if ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, DynZ>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_bwd2<MODE_PAIR, DynZ>, p->smem_zb[1])) ||
+      (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, DynZ>, p->smem_zf[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_PAIR, DynZ>, p->smem_zf[1]))) return rc;
+  if (p->z_static == 1 &&
+      ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, ZbMgO216>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, ZfMgO216>, p->smem_zf[0])))) return rc;
   int n = 0;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_SINGLE>, 256, p->smem_zb[0])); p->zslots_b[0] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_PAIR>, 256, p->smem_zb[1])); p->zslots_b[1] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_SINGLE>, 256, p->smem_zf[0])); p->zslots_f[0] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_PAIR>, 256, p->smem_zf[1])); p->zslots_f[1] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_SINGLE, DynZ>, 256, p->smem_zb[0])); p->zslots_b[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_PAIR, DynZ>, 256, p->smem_zb[1])); p->zslots_b[1] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_SINGLE, DynZ>, 256, p->smem_zf[0])); p->zslots_f[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_PAIR, DynZ>, 256, p->smem_zf[1])); p->zslots_f[1] = std::max(1, n) * p->nsm;
   p->z2 = true;
   return QB200_OK;
 }
@@ -421,7 +433,9 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       }
     }
     if ((rc = upload(p, zq, &d.zq)) || (rc = upload(p, zqm, &d.zqm))) { qb200_plan_destroy(p); return rc; }
-    if ((rc = configure_z2(p, first, prop.sharedMemPerMultiprocessor))) { qb200_plan_destroy(p); return rc; }
+    int lmax = 0;
+    for (int r = 0; r < nrods; r++) lmax = std::max(lmax, std::max(std::abs(lmin[r]), std::abs(lmin[r] + size[r] - 1)));
+    if ((rc = configure_z2(p, first, prop.sharedMemPerMultiprocessor, lmax))) { qb200_plan_destroy(p); return rc; }
   }
   const size_t pitch2 = (size_t)(np2 | 1);
   int ncolmax = (int)std::min<size_t>(32, (80 * 1024) / (pitch2 * 16));
@@ -590,6 +604,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 11: return p->z2 ? 1 : 0;
     case 14: return p->split2 ? 1 : 0;
     case 15: return p->split_static;
+    case 16: return p->z_static;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;
@@ -615,8 +630,9 @@ static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int
   prof_begin(0, p->stream);
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zb_rb, p->zslots_b[mode], nunits);
-    if (mode == MODE_PAIR) k_zcol_bwd2<MODE_PAIR><<<g2, 256, p->smem_zb[1], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
-    else k_zcol_bwd2<MODE_SINGLE><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    if (mode == MODE_PAIR) k_zcol_bwd2<MODE_PAIR, DynZ><<<g2, 256, p->smem_zb[1], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else if (p->z_static == 1) k_zcol_bwd2<MODE_SINGLE, ZbMgO216><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else k_zcol_bwd2<MODE_SINGLE, DynZ><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
   }
   else if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
   else k_zcol_bwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
@@ -634,9 +650,11 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zf_rb, p->zslots_f[mode], nunits);
     if (mode == MODE_PAIR)
-      k_zcol_fwd2<MODE_PAIR><<<g2, 256, p->smem_zf[1], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+      k_zcol_fwd2<MODE_PAIR, DynZ><<<g2, 256, p->smem_zf[1], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+    else if (p->z_static == 1)
+      k_zcol_fwd2<MODE_SINGLE, ZfMgO216><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
     else
-      k_zcol_fwd2<MODE_SINGLE><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+      k_zcol_fwd2<MODE_SINGLE, DynZ><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
   }
   else if (mode == MODE_PAIR)
     k_zcol_fwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);

@@ -19,8 +19,18 @@
 #pragma once
 #include "qb200_internal.h"
 #include "fft_group.cuh"
+#include "plane_static.cuh"
 
 namespace qb200 {
+
+// ZS selects the transform engine: DynZ = run-time shapes (group engine); ZShape<np2, columns per tile, zsplit, zskip> =
+// compiled shape (pass_s of plane_static.cuh): the sphere only reaches |l| < zsplit, so the first backward pass knows
+// which inputs are zero and the last forward pass which outputs are never gathered.
+struct DynZ { static constexpr bool STATIC = false; };
+template <int NP2_, int CB_, int ZSPLIT_, int ZSKIP_> struct ZShape {
+  static constexpr bool STATIC = true;
+  static constexpr int NP2 = NP2_, CB = CB_, PITCH = CB_ | 1, ZSPLIT = ZSPLIT_, ZSKIP = ZSKIP_;
+};
 
 __device__ __forceinline__ void zc_cp16(void* smem, const void* gmem)
 {
@@ -48,7 +58,7 @@ __device__ __forceinline__ int ztile_pos(int m, int pitch, int col0) { return (m
 
 // ------------------------------------------------------------------------------------------------ backward
 // grid (ceil(nrods/rb), G), block 256.  smem: tw[f2.twsize] | lines[np2*pitch] | stage[2][cper*cmax] | pos[cmax] (| posm[cmax])
-template <int MODE>
+template <int MODE, class ZS>
 __global__ void __launch_bounds__(256, 2) k_zcol_bwd2(const __grid_constant__ DevPlan P, const cplx* __restrict__ c, size_t ldc,
                                                       cplx* __restrict__ zt, int nunits)
 {
@@ -105,7 +115,12 @@ __global__ void __launch_bounds__(256, 2) k_zcol_bwd2(const __grid_constant__ De
       if (P.is_real) lines[posm[e]] = mv;          // same thread, later: the conjugate wins at G=0, as in the reference
     }
     __syncthreads();
-    fft_block_dit<+1>(g, lines, b.ncol, CB, lm, pitch, P.f2, tw, P.f2.nf - 1, false, nokeep);
+    if constexpr (ZS::STATIC) {
+      constexpr FftDesc FZ = make_fft_desc(ZS::NP2);
+      dit_s<+1, ZS::NP2, ZS::PITCH, ZS::CB, ColsOff, ZS::ZSPLIT, ZS::ZSKIP, true, false, FZ.nf - 1>(tid, nthr, lines, tw, [] { __syncthreads(); });
+    } else {
+      fft_block_dit<+1>(g, lines, b.ncol, CB, lm, pitch, P.f2, tw, P.f2.nf - 1, false, nokeep);
+    }
     __syncthreads();
     cplx* out = zt + (size_t)unit * np2 * P.nvec + b.col0;
     for (int e = tid; e < b.ncol * np2; e += nthr) {
@@ -119,7 +134,7 @@ __global__ void __launch_bounds__(256, 2) k_zcol_bwd2(const __grid_constant__ De
 
 // ------------------------------------------------------------------------------------------------ forward
 // grid (ceil(nrods/rb), G), block 256.  smem: tw | lines[2][np2*pitch] | kpg2h[cmax] | pos[cmax] (| posm[cmax])
-template <int MODE>
+template <int MODE, class ZS>
 __global__ void __launch_bounds__(256, 2) k_zcol_fwd2(const __grid_constant__ DevPlan P, const cplx* __restrict__ zt, cplx* __restrict__ out,
                                                       size_t ldc, int accumulate, const double* __restrict__ kpg2,
                                                       const cplx* __restrict__ cin, double scale, int nunits)
@@ -162,7 +177,12 @@ __global__ void __launch_bounds__(256, 2) k_zcol_fwd2(const __grid_constant__ De
     __syncthreads();          // this unit's tile has landed; everybody has finished the previous unit's gather (other buffer)
     if (unit + G < nunits) issue(unit + G, buf ^ 1);
     cplx* lines = lines0 + (size_t)buf * np2 * pitch;
-    fft_block_dif<-1>(g, lines, b.ncol, CB, lm, pitch, P.f2, tw, 0, P.f2.nf, false, nokeep);
+    if constexpr (ZS::STATIC) {
+      constexpr FftDesc FZ = make_fft_desc(ZS::NP2);
+      dif_s<-1, ZS::NP2, ZS::PITCH, ZS::CB, ColsOff, ZS::ZSPLIT, ZS::ZSKIP, false, true, 0, FZ.nf - 1>(tid, nthr, lines, tw, [] { __syncthreads(); });
+    } else {
+      fft_block_dif<-1>(g, lines, b.ncol, CB, lm, pitch, P.f2, tw, 0, P.f2.nf, false, nokeep);
+    }
     __syncthreads();
     const size_t s1 = (size_t)unit * CPER * ldc + b.ig0;
     cplx* o1 = out + s1;
