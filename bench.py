@@ -32,9 +32,9 @@ WORKLOADS = {
     "mgo216": dict(cell=(23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), ecut=25.0, kpoint=(0, 0, 0), force_complex=True, nst=768,
                    species=[("Mg", 108, [0, 1, 1, 1]), ("O", 108, [0])],
                    note="examples/MgO216 (timing_nr512.i: 50 Ry, force_complex_wf ON, 768 states, 112^3 grid)"),
-    "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=24,
+    "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=64,
                   species=[("Au", 992, [0, 1, 1, 1])],
-                  note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 24 states"),
+                  note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 64 states (the full 10118-state job holds ~1265 per GPU on 8)"),
     "sih4": dict(cell=(14, 0, 0, 0, 14, 0, 0, 0, 14), ecut=18.0, kpoint=(0, 0, 0), force_complex=False, nst=4,
                  species=[("Si", 1, [0, 1, 1, 1])], note="examples/sih4 (Gamma, real wavefunctions, 60^3 grid)"),
 }
@@ -310,16 +310,33 @@ def main():
         roofline_hbm = {"kernel": "k_plane (fused xy stage)" if ft.fused() else "k_xrows+k_ycols (split xy stage)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                         "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
-    nl_flops_step = 0.0
-    for s in species:   # 2 GEMMs x 8 flops per complex MAC (4 per real-basis MAC over 2*ngw reals)
-        nl_flops_step += (16.0 if not b["is_real"] else 8.0) * s["na"] * s["npr"] * ngw * nst
+    # the whole local path (z columns + xy stage, both directions) against the HBM roofline with SURVEY.md section 8d's
+    # per-unit algorithmic bytes: B_Hpsi = 48*ngw*cper + 64*nvec*np2 + 8*N, B_rho = 16*ngw + 32*nvec*np2 (+16*N per build)
+    cper = 2 if b["is_real"] else 1
+    local_bytes_step = nunits_h * (48.0 * ngw * cper + 64.0 * nvec * np2 + 8.0 * N) + nst * (16.0 * ngw + 32.0 * nvec * np2) + 16.0 * N
+    local_ms = prof["k_zcol_bwd"][0] + prof["xy_stage"][0] + prof["k_zcol_fwd"][0] + prof["k_rho_reduce"][0]
+    roofline_local = None
+    if local_ms > 0:
+        ach = local_bytes_step * args.steps / (local_ms * 1e-3) / 1e9
+        roofline_local = {"kernel": "local path: k_zcol_bwd + xy stage + k_zcol_fwd (H psi local term + density)", "bound": "hbm",
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                          "note": "xy stage is bound by the shared-memory and FP64 pipes (ncu: smem wavefronts 65%, FP64 45%, DRAM 7% of peak), not by HBM"}
+    nl_flops_step = 0.0     # flops EXECUTED on the FP64 tensor pipe
+    nl_zgemm_flops_step = 0.0   # the same contraction counted as the reference's zgemm/dgemm (8 / 2 flops per MAC)
+    m3 = (not b["is_real"]) and os.environ.get("QB200_NL_3M", "1") != "0"
+    for s in species:   # 2 GEMMs; complex MAC = 3 real MACs in the Karatsuba form (nonlocal_3m.cuh), 4 in the plain embedding
+        per_mac = 8.0 if b["is_real"] else (12.0 if m3 else 16.0)
+        nl_flops_step += per_mac * s["na"] * s["npr"] * ngw * nst
+        nl_zgemm_flops_step += (8.0 if b["is_real"] else 16.0) * s["na"] * s["npr"] * ngw * nst
     nl_ms = prof["k_fnl"][0] + prof["k_back"][0]
     fp64_peak = 37.0   # TFLOP/s nominal B200 FP64 (vector = DMMA); MEASURED_PEAKS.json has no FP64 entry
     roofline_fp64 = None
     if nl_ms > 0:
         ach = nl_flops_step * args.steps / (nl_ms * 1e-3) / 1e12
-        roofline_fp64 = {"kernel": "k_fnl + k_back (DMMA projector GEMMs)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
+        roofline_fp64 = {"kernel": ("k_fnl3 + k_back3 (DMMA projector GEMMs, 3-product complex form: 12 flops per complex MAC)" if m3
+                                    else "k_fnl + k_back (DMMA projector GEMMs)"), "bound": "tensor", "achieved": ach, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                         "zgemm_equivalent_tflops": nl_zgemm_flops_step * args.steps / (nl_ms * 1e-3) / 1e12,
                          "peak_source": "nominal FP64 37 TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)",
                          "launches": prof["k_fnl"][1] + prof["k_back"][1]}
     prof_ms = {k: round(vv[0] / args.steps, 4) for k, vv in prof.items()}
@@ -386,7 +403,7 @@ def main():
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-               "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
+               "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
                "kernel_ms_per_step": prof_ms, "enl": enl,
                "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
                          "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
