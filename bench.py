@@ -165,6 +165,15 @@ def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: keep a private handle to the real stdout and point fd 1 at stderr, so that
+    # library chatter (NCCL prints its version banner to stdout) cannot get in front of it
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -194,7 +203,7 @@ def main():
         for i in range(args.warmup + args.steps):
             t = run_reference_cpu(args.workload, sample, 1)
             if t is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
+                emit({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"})
                 return
             if i >= args.warmup:
                 ts.append(t)
@@ -207,7 +216,7 @@ def main():
         val = sample / per
         smp = f"{sample} states of the {args.workload} shape (all {sum(s[1] for s in wl['species'])} atoms' projectors), one pass = " \
               f"NonLocalPotential::energy + kinetic + rs_mul_add + compute_density, built-in FFT (FFT_NOLIB)"
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": len(ts),
+        emit(({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": len(ts),
                           "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": unit, "cores": ts[0]["threads"], "kind": "reference", "sample": smp},
@@ -407,7 +416,7 @@ def main():
                "kernel_ms_per_step": prof_ms, "enl": enl,
                "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
                          "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
