@@ -79,6 +79,8 @@ class FourierTransform {
   int index(int i, int j, int k) const { return i + np0_ * (j + np1_ * k); }   // FourierTransform.h:165
   qb200_plan* plan() const { return plan_; }
   void set_stream(void* cuda_stream) { check(qb200_plan_set_stream(plan_, cuda_stream), "set_stream"); }
+  // content version of the HOST coefficient blocks passed from now on (0: always upload); see qball_b200.h
+  void set_coefficient_tag(long long tag) { check(qb200_plan_set_coefficient_tag(plan_, tag), "set_coefficient_tag"); }
 
  private:
   qb200_plan* plan_ = nullptr;
