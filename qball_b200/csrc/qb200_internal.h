@@ -59,6 +59,7 @@ namespace qb200 {
 // plane.cu: the plane-fused xy stage (own translation unit: its register budget is 144, the other kernels' is 128)
 int plane_opt_in(qb200_plan* p);
 int plane_select_static(const qb200_plan* p, int hmax);
+int plane_preferred_gthreads(int np0, int np1, int ksplit, int kskip);
 int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, const double* fac, int nunits, int zero_imag);
 }
 

@@ -518,7 +518,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   // plane kernel geometry: groups of gthreads threads own blocks of 8 rows / 8 columns (fft_group.cuh); pick the number of
   // groups (<= 7 x 64 = 448 threads so that the radix-16 pass keeps its ~112 registers) that needs the fewest rounds
   {
-    d.gthreads = 64;
+    d.gthreads = plane_preferred_gthreads(np0, np1, d.ksplit, d.kskip);
     if (const char* e = getenv("QB200_GROUP_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= 256 && t % 32 == 0) d.gthreads = t; }
     const int maxg = std::max(1, std::min(15, 448 / d.gthreads));
     const int by = (np0 + 7) / 8, bx = (d.nkeep + 7) / 8 + ((d.nkeep < np1 && d.ksplit % 8) ? 1 : 0);
