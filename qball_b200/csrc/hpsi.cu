@@ -3,6 +3,7 @@
 // in the reference's order, on one stream, with host blocks staged in and out when host pointers are given.
 #include "qb200_internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 int qb200_rs_mul_add_dev(qb200_plan* p, int ldc, int nst, const double* c, const double* v, const double* kpg2, double* cp);
 int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int cont);
@@ -21,15 +22,17 @@ static int ensure_buf(double** buf, size_t* cap, size_t elems)
   return QB200_OK;
 }
 
-// states per pipeline block of the host-pointer path: whole GEMM tiles (128 states), an even count (real bases pair
-// local states (n, n+1), SlaterDet.cc:987), at most 8 blocks; one block when the projector sweep is chunked (each
-// block would regenerate every anl chunk)
+// states per pipeline slice of the host-pointer path: whole GEMM tiles (64 states), an even count (real bases pair
+// local states (n, n+1), SlaterDet.cc:987), at most 16 slices -- small slices keep the exposed first upload and last
+// download short; one slice when the projector sweep is chunked (each slice would regenerate every anl chunk)
 static int hpsi_block_states(int nst, bool single)
 {
-  if (single || nst <= 128) return nst;
-  const int nblk = std::min(8, (nst + 127) / 128);
+  int unit = 64;
+  if (const char* e = getenv("QB200_HOST_SLICE")) { const int v = atoi(e); if (v >= 2 && v % 2 == 0) unit = v; }
+  if (single || nst <= unit) return nst;
+  const int nblk = std::min(16, (nst + unit - 1) / unit);
   const int per = (nst + nblk - 1) / nblk;
-  return (per + 127) / 128 * 128;
+  return (per + unit - 1) / unit * unit;
 }
 
 extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,

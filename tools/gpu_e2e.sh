@@ -1,7 +1,8 @@
-set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/e2e_pytest.log
-cat gpurun_out/e2e_pytest.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/e2e_bench.json 2> gpurun_out/e2e_err.log
-python -c "
-import json; d=json.load(open('gpurun_out/e2e_bench.json')); print(d['ms_per_step'], d['value'], d['e2e'], d['kernel_ms_per_step'])"
-tail -5 gpurun_out/e2e_err.log
+rm -f gpurun_out/e2e_var.log
+for V in "$@"; do
+  echo "== $V" >> gpurun_out/e2e_var.log
+  env $V timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>>gpurun_out/e2e_err.log | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'])" >> gpurun_out/e2e_var.log
+done
+cat gpurun_out/e2e_var.log
