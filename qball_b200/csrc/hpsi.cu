@@ -8,6 +8,7 @@
 int qb200_rs_mul_add_dev(qb200_plan* p, int ldc, int nst, const double* c, const double* v, const double* kpg2, double* cp);
 int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int cont);
 int qb200_nl_chunks(const qb200_nl* nl, int nst);
+int qb200_nl_projectors(const qb200_nl* nl);
 double* qb200_nl_enl_dev(qb200_nl* nl);
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s);
 
@@ -93,8 +94,13 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
     const int n0 = b * SB, nb = std::min(SB, nst - n0);
     const size_t off = 2 * (size_t)n0 * ldc;
     if (upload_c) QB_CUDA(cudaStreamWaitEvent(p->stream, p->evs[1 + b], 0));
-    QB_CUDA(cudaMemsetAsync(od + off, 0, 2 * (size_t)nb * ldc * sizeof(double), p->stream));      // dwf.c().clear()
-    if (nl && (rc = qb200_nl_energy_dev(nl, ldc, nb, cd + off, occ + n0, 1, od + off, b > 0))) {      // nlp->energy(sd, true, dsd, ...)
+    // dwf.c().clear(): with projectors the back-projection WRITES rows [0, ngw) (first term of H psi), so only the
+    // padding rows need clearing; without projectors the whole slice is cleared
+    const bool nlw = nl && qb200_nl_projectors(nl) > 0;
+    if (!nlw) QB_CUDA(cudaMemsetAsync(od + off, 0, 2 * (size_t)nb * ldc * sizeof(double), p->stream));
+    else if (ldc > d.ngw)
+      QB_CUDA(cudaMemset2DAsync(od + off + 2 * (size_t)d.ngw, (size_t)ldc * 16, 0, (size_t)(ldc - d.ngw) * 16, nb, p->stream));
+    if (nl && (rc = qb200_nl_energy_dev(nl, ldc, nb, cd + off, occ + n0, 1, od + off, (b > 0 ? 1 : 0) | (nlw ? 2 : 0)))) {   // nlp->energy(sd, true, dsd, ...)
       qb200_nl_swap_stream(nl, saved);
       return rc;
     }

@@ -301,7 +301,7 @@ __global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __r
 template <int IS_REAL>
 __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
                                                           const double* __restrict__ fs, int FP, double2* __restrict__ cp,
-                                                          size_t ldc, int nst)
+                                                          size_t ldc, int nst, int overwrite)
 {
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -354,7 +354,10 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
         double v = acc[i][j][e];
         if (IS_REAL && g == 0 && (row & 1) == 0) v *= 2.0;    // W holds half of Re anl at G=0 (k_anl_gen)
-        if (gl < gcount && n < nst) cpd[2 * ((size_t)n * ldc + g) + (row & 1)] += v;
+        if (gl < gcount && n < nst) {
+          double* dst = cpd + 2 * ((size_t)n * ldc + g) + (row & 1);
+          *dst = overwrite ? v : *dst + v;
+        }
       }
 }
 
@@ -620,12 +623,15 @@ static void nl_chunking(const qb200_nl* nl, int* gchunk_out, int* nchunks_out)
   *gchunk_out = gchunk;
   *nchunks_out = (nl->ngw + gchunk - 1) / gchunk;
 }
+int qb200_nl_projectors(const qb200_nl* nl) { return nl->Mtot; }
 int qb200_nl_chunks(const qb200_nl* nl, int) { int g, n; nl_chunking(nl, &g, &n); return nl->Mtot > 0 ? n : 1; }
 
-// device pointers; enl accumulated into nl->enl_dev.  cont == 0: a new call (enl zeroed, anl regenerated unless cached);
-// cont != 0: a further block of states of the same call (enl keeps accumulating, a whole-sphere anl in W is reused).
-int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int cont)
+// device pointers; enl accumulated into nl->enl_dev.  flags bit 0 clear: a new call (enl zeroed, anl regenerated unless
+// cached); bit 0 set: a further block of states of the same call (enl keeps accumulating, a whole-sphere anl in W is
+// reused).  Bit 1: cp rows [0, ngw) are known to be zero and are WRITTEN instead of accumulated (H psi: first term).
+int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ_host, int compute_hpsi, double* cp, int flags)
 {
+  const int cont = flags & 1, overwrite = (flags >> 1) & 1;
   int rc;
   if ((rc = nl_ensure(&nl->occ_dev, &nl->occ_cap, nst))) return rc;
   QB_CUDA(cudaMemcpyAsync(nl->occ_dev, occ_host, nst * sizeof(double), cudaMemcpyDefault, nl->stream));
@@ -712,10 +718,10 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     if (i > 0 && (rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;   // (i == 0: still in W from sweep 1)
     dim3 g2((gcount + 63) / 64, nt);
     prof_begin(5, nl->stream);
-    if (m3 && nl->tile3m == 1) k_back3<4, 2, 3><<<dim3(nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
-    else if (m3) k_back3<4, 4, 4><<<dim3(nt, (gcount + 63) / 64), 512, Back3Cfg<4, 4, 4>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
-    else if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
-    else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst);
+    if (m3 && nl->tile3m == 1) k_back3<4, 2, 3><<<dim3(nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);
+    else if (m3) k_back3<4, 4, 4><<<dim3(nt, (gcount + 63) / 64), 512, Back3Cfg<4, 4, 4>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);
+    else if (real) k_back<1><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);
+    else k_back<0><<<g2, NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);
     prof_end(nl->stream);
     NL_LAUNCH_CHECK(nl);
   }

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) k_fnl_finish3(const double* __restrict__ 
 template <int NWM, int NWN, int NSTG>
 __global__ void __launch_bounds__(32 * NWM * NWN, 512 / (32 * NWM * NWN))
 k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount, const double* __restrict__ fs3, int FP3,
-        double2* __restrict__ cp, size_t ldc, int nst)
+        double2* __restrict__ cp, size_t ldc, int nst, int overwrite)
 {
   typedef Back3Cfg<NWM, NWN, NSTG> C;
   extern __shared__ __align__(16) double nl_smem[];
@@ -270,7 +270,7 @@ k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount,
         if (gl < gcount && n < nst) {
           const double R1 = acc[0][i][j][e], R2 = acc[1][i][j][e], R3 = acc[2][i][j][e];
           double2* dst = cp + (size_t)n * ldc + gbeg + gl;
-          double2 v = *dst;
+          double2 v = overwrite ? make_double2(0.0, 0.0) : *dst;     // overwrite: cp is known to be zero (H psi: first term)
           v.x += R1 - R2;
           v.y += R3 - (R1 + R2);
           *dst = v;
