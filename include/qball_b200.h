@@ -88,6 +88,12 @@ int qb200_rs_mul_add(qb200_plan* plan, int ldc, int nst, const double* c, const 
  *      Deterministic: fixed summation order for a given (plan, nst). */
 int qb200_compute_density(qb200_plan* plan, int ldc, int nst, const double* c, const double* fac, double* rho);
 
+/* ---- tail of ChargeDensity::update_density after the sum over ranks                    ChargeDensity.cc:516-551
+ *      nelectrons = sum_i rho[i] * omega / N ; rhog = FT_v[ omega * rho ]  (vft_->forward, density basis).
+ *      vplan: the plan of the DENSITY basis (vbasis_: k = 0, ecut 4*ecut_wf or ecutden, ChargeDensity.cc:77-81) on the same
+ *      grid; rho: N doubles; rhog: vbasis ngw complex; nelectrons may be NULL. */
+int qb200_density_finish(qb200_plan* vplan, const double* rho, double omega, double* rhog, double* nelectrons);
+
 /* ---- NonLocalPotential::energy, norm-conserving branch                 NonLocalPotential.cc:1909-2171, 2628-2643
  *      Projector tables are the outputs of the reference's host setup (NonLocalPotential::init/update_twnl,
  *      NonLocalPotential.cc:76-1522) and AtomSet::get_positions.  One qb200_nl per NonLocalPotential object. */

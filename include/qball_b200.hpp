@@ -104,6 +104,14 @@ inline void compute_density(FourierTransform& ft, int mloc, int nstloc, const st
   check(qb200_compute_density(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), fac.data(), rho), "compute_density");
 }
 
+// tail of ChargeDensity::update_density (ChargeDensity.cc:516-551): returns nelectrons_, fills rhog = vft.forward(omega*rho)
+inline double density_finish(FourierTransform& vft, const double* rho, double omega, std::complex<double>* rhog)
+{
+  double nel = 0.0;
+  check(qb200_density_finish(vft.plan(), rho, omega, reinterpret_cast<double*>(rhog), &nel), "density_finish");
+  return nel;
+}
+
 class NonLocalPotential {
  public:
   // kpgx = basis.kpgx_ptr(0) (3*ngw, component-major), omega = basis.cell().volume()

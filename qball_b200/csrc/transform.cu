@@ -919,3 +919,30 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   if (upload_c) plan_mark_resident(p, c, ldc, nst);
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ update_density tail
+// ChargeDensity::update_density after the row sum (ChargeDensity.cc:516-551): nelectrons = sum(rho)*omega/N,
+// rhotmp = omega*rho, rhog = vft->forward(rhotmp).  `pv` is the plan of the DENSITY basis (vbasis_, ChargeDensity.cc:77-81).
+extern "C" int qb200_density_finish(qb200_plan* pv, const double* rho, double omega, double* rhog, double* nelectrons)
+{
+  if (!pv || !rho || !rhog || !(omega > 0.0)) { set_error("qb200_density_finish: bad argument"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(pv->device));
+  const DevPlan& d = pv->d;
+  const size_t N = (size_t)d.np0 * d.np1 * d.np2;
+  const double* rd;
+  int rc;
+  if ((rc = stage_in(pv, rho, N, &pv->st_v, &pv->st_v_cap, &rd))) return rc;
+  const int nblk = 148 * 4;
+  if ((rc = ensure(&pv->st_f, &pv->st_f_cap, 2 * N + nblk + 2))) return rc;
+  double* f = pv->st_f;
+  double* bs = f + 2 * N;
+  k_rho_expand<<<nblk, 256, 0, pv->stream>>>(rd, N, omega, (cplx*)f, bs);
+  QB_LAUNCH_CHECK(pv);
+  k_sum_fixed<<<1, 32, 0, pv->stream>>>(bs, nblk, omega / (double)N, bs + nblk);
+  QB_LAUNCH_CHECK(pv);
+  double nel = 0.0;
+  QB_CUDA(cudaMemcpyAsync(&nel, bs + nblk, sizeof(double), cudaMemcpyDeviceToHost, pv->stream));
+  if ((rc = fft_forward_impl(pv, f, rhog, nullptr))) return rc;          // synchronises the stream
+  if (nelectrons) *nelectrons = nel;
+  return QB200_OK;
+}

@@ -269,4 +269,32 @@ __global__ void k_rho_reduce(double* __restrict__ rho, const double* __restrict_
   }
 }
 
+// rhotmp[i] = (omega*rho[i], 0) and per-block partial sums of rho (ChargeDensity.cc:520-528); fixed grid -> fixed order
+__global__ void __launch_bounds__(256) k_rho_expand(const double* __restrict__ rho, size_t N, double omega, cplx* __restrict__ f,
+                                                    double* __restrict__ blocksum)
+{
+  __shared__ double red[256];
+  double s = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+    const double r = rho[i];
+    s += r;
+    f[i] = make_double2(omega * r, 0.0);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = red[0];
+}
+__global__ void k_sum_fixed(const double* __restrict__ blocksum, int n, double scale, double* __restrict__ out)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += blocksum[i];
+    *out = s * scale;
+  }
+}
+
 }  // namespace qb200

@@ -108,6 +108,35 @@ def compute_density(ft: FourierTransform, c, weight: float, occ, omega: float, r
     return rho
 
 
+class ChargeDensity:
+    """ChargeDensity (ChargeDensity.cc:66-151, 276-556), norm-conserving, one spin / one k-point per object:
+    update_density() = zero rho; SlaterDet::compute_density; sum over the ranks that share the states (:309);
+    nelectrons = sum(rho)*omega/N (:520-528); rhog = vft->forward(omega*rho) (:550).
+    `ft` transforms the wavefunction basis, `vbasis` is the density basis (k = 0, 4*ecut) on the same grid."""
+
+    def __init__(self, ft: FourierTransform, vbasis, omega: float, device: int = 0, stream=None):
+        self.ft = ft
+        self.vft = FourierTransform(vbasis, ft.np0(), ft.np1(), ft.np2(), device=device, stream=stream)
+        self.omega = float(omega)
+        self.nelectrons = 0.0
+
+    def update_density(self, c, occ, rhor, rhog, weight: float = 1.0, group=None) -> float:
+        """rhor (N doubles) and rhog (vbasis ngw complex) are outputs; returns nelectrons (total_electronic_charge)"""
+        from . import parallel as _par
+        if hasattr(rhor, "zero_"):
+            rhor.zero_()
+        else:
+            rhor[...] = 0.0
+        compute_density(self.ft, c, weight, occ, self.omega, rhor)
+        if hasattr(rhor, "is_cuda"):
+            _par.allreduce_density(rhor, group)
+        nel = C.c_double(0.0)
+        capi._check(self.ft._L.qb200_density_finish(self.vft._h, capi.ptr(rhor), self.omega, capi.ptr(rhog), C.byref(nel)),
+                    "qb200_density_finish")
+        self.nelectrons = nel.value
+        return nel.value
+
+
 class NonLocalPotential:
     """NonLocalPotential(atoms, ctxt, basis, ...) norm-conserving branch (NonLocalPotential.cc:76-258, 1909-2171).
     `species` = list of dict(na, npr, lproj, wt, twnl[npr, ngw], tau[na, 3]) -- the reference's init/update_twnl outputs."""

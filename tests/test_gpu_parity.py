@@ -297,3 +297,65 @@ def test_properties_au992_full_size_split_path(monkeypatch):
         torch.cuda.empty_cache()
     assert relerr(res["static"][0], res["generic"][0]) < 1e-12
     assert relerr(res["static"][1], res["generic"][1]) < 1e-12
+
+
+def test_cuda_vs_oracle_si54p_shape_gamma_real():
+    """examples/si54p as a Gamma-point real-wavefunction case (fcc-type cell 2 x 15.525, 65 Ry, 126^3 grid,
+    ngw 33114): planes of 126 x 127 x 16 B exceed shared memory, so this runs the real-basis pair path (+ odd tail)
+    through the run-time-shape z-column and split xy kernels; checked against the oracle on the same seeded inputs."""
+    a = 15.525
+    cell, ecut = (0, a, a, a, 0, a, a, a, 0), 32.5
+    b = P.make_basis(cell, ecut, (0, 0, 0), False)
+    grid = P.density_grid(cell, ecut)
+    assert b["is_real"] and grid == (126, 126, 126) and b["ngw"] == 33114
+    nst = 5
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"] + 3, True, seed=51)
+    v = R.synth_potential(*grid, seed=52)
+    occ = np.array([2.0, 2.0, 1.0, 0.0, 0.5])
+    oft = P.FT(b, *grid)
+    ft = H.FourierTransform(b, *grid)
+    assert not ft.fused() and ft.query(14) == 1 and ft.query(11) == 1
+    want = oft.rs_mul_add(c, v, np.zeros_like(c))
+    P.kinetic_add(b["kpg2"], c, want)
+    got = _dev(np.zeros_like(c))
+    H.rs_mul_add(ft, _dev(c), _dev(v), got, kpg2=_dev(b["kpg2"]))
+    got = got.cpu().numpy()
+    assert relerr(got[:, :b["ngw"]], want[:, :b["ngw"]]) < TOL
+    assert np.all(got[:, b["ngw"]:] == 0)
+    rho_want = oft.compute_density(c, occ / b["omega"], np.zeros(oft.N))
+    rho = _dev(np.zeros(oft.N))
+    H.compute_density(ft, _dev(c), 1.0, occ, b["omega"], rho)
+    assert relerr(rho.cpu().numpy(), rho_want) < TOL
+
+
+@pytest.mark.parametrize("kpoint,host", [((0, 0, 0), False), ((0.25, 0, 0.5), True)])
+def test_cuda_update_density_tail_vs_oracle(kpoint, host):
+    """ChargeDensity::update_density (ChargeDensity.cc:276-551, norm-conserving, one k-point): rho(r), the integral
+    nelectrons = sum(rho)*omega/N and rho(G) = vft->forward(omega*rho) on the density basis (k = 0, 4*ecut), against the
+    oracle restatement (compute_density + forward transform, both pinned to the reference)."""
+    cell, ecut, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 5.0, 6
+    b = P.make_basis(cell, ecut, kpoint, False)
+    vb = P.make_basis(cell, 4.0 * ecut, (0, 0, 0), False)          # ChargeDensity.cc:77-81
+    grid = P.density_grid(cell, ecut)
+    N = grid[0] * grid[1] * grid[2]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=61)
+    occ = np.array([2, 2, 2, 1, 0.5, 0.0])
+    oft, ovft = P.FT(b, *grid), P.FT(vb, *grid)
+    rho_ref = oft.compute_density(c, occ / b["omega"], np.zeros(N))
+    nel_ref = rho_ref.sum() * b["omega"] / N
+    rhog_ref = ovft.forward((b["omega"] * rho_ref).astype(np.complex128))
+    ft = H.FourierTransform(b, *grid)
+    cd = H.ChargeDensity(ft, vb, b["omega"])
+    if host:
+        rhor, rhog, cc = np.zeros(N), np.zeros(vb["ngw"], dtype=np.complex128), c
+    else:
+        rhor = torch.zeros(N, dtype=torch.float64, device="cuda")
+        rhog = torch.zeros(vb["ngw"], dtype=torch.complex128, device="cuda")
+        cc = _dev(c)
+    nel = cd.update_density(cc, occ, rhor, rhog)
+    back = (lambda a: a) if host else (lambda t: t.cpu().numpy())
+    assert relerr(back(rhor), rho_ref) < TOL
+    assert abs(nel - nel_ref) < 1e-12 * abs(nel_ref)
+    assert relerr(back(rhog), rhog_ref) < TOL
+    # the G = 0 coefficient is the electron count (vbasis is real: G = 0 sits at index 0, SlaterDet.cc:2776-2779)
+    assert abs(back(rhog)[0].real - nel) < 1e-10 * abs(nel)
