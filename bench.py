@@ -352,6 +352,25 @@ def main():
     dominant = max(prof.items(), key=lambda kv: kv[1][0])[0]
     roofline = roofline_fp64 if dominant in ("k_fnl", "k_back") and roofline_fp64 else roofline_hbm
 
+    # ---------------------------------------------------------------- TDDFT propagation (configs[3]): one 4th-order Taylor
+    # exponential exp(-i dt H) on the resident block = 4 H psi applications + axpy chain (ExponentialWavefunctionStepper.cc:51-149)
+    tddft = None
+    if not b["is_real"] and not args.no_e2e:
+        with torch.cuda.stream(stream):
+            cprop = c.clone()
+            H.exponential(ft, nlp, cprop, occ, v, kpg2, 0.02)        # warm-up (allocates the two work blocks)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record(stream)
+            nrep = 2
+            for _ in range(nrep):
+                H.exponential(ft, nlp, cprop, occ, v, kpg2, 0.02)
+            t1e.record(stream)
+        sync_all()
+        ms_exp = t0e.elapsed_time(t1e) / nrep
+        tddft = {"exponential_order4_ms": ms_exp, "hpsi_state_applies_per_s": world * nst * 4 / (ms_exp * 1e-3),
+                 "what": "qb200_exponential, order 4, Hamiltonian frozen, block resident in HBM (per rank)"}
+        del cprop
+
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI, copies inside
     e2e = None
     if not args.no_e2e:
@@ -413,7 +432,7 @@ def main():
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
-               "kernel_ms_per_step": prof_ms, "enl": enl,
+               "kernel_ms_per_step": prof_ms, "tddft": tddft, "enl": enl,
                "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
                          "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
         emit(out)

@@ -132,6 +132,15 @@ long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 
 int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,
                const double* kpg2, double* hpsi, double* enl);
 
+/* ---- TDDFT propagator glue: ExponentialWavefunctionStepper::exponential(num_exp, dt1, dt2)
+ *      (ExponentialWavefunctionStepper.cc:51-149) with the Hamiltonian frozen at v (the caller updates v between the
+ *      exponentials of an ETRS/AETRS step): c <- sum_{N=0..order} (-i dt1 H)^N / N! c  (order 4 in the reference, :45);
+ *      if c2 != NULL (num_exp == 2): c2 <- the same series with dt2, from the same H^N c.  H = qb200_hpsi.
+ *      Complex bases only (the reference requires force_complex_wf for wf_dyn ETRS, vars/WfDyn.h:82-92).
+ *      The H^N c chain stays on the device; work space: two blocks of ldc x nst complex owned by the plan. */
+int qb200_exponential(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, double* c, const double* occ, const double* v,
+                      const double* kpg2, int order, double dt1, double dt2, double* c2);
+
 /* ---- optional per-kernel timing (CUDA events on the launching stream, recorded around every launch while enabled).
  *      categories: 0 k_zcol_bwd, 1 xy stage (k_plane, or k_xrows+k_ycols), 2 k_zcol_fwd, 3 k_fnl, 4 k_fnl_finish+sum,
  *      5 k_back, 6 k_rho_reduce, 7 k_anl_gen.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the

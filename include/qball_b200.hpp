@@ -112,6 +112,13 @@ inline double density_finish(FourierTransform& vft, const double* rho, double om
   return nel;
 }
 
+class NonLocalPotential;
+// ExponentialWavefunctionStepper::exponential with a frozen Hamiltonian (ExponentialWavefunctionStepper.cc:51-149); see
+// qb200_exponential.  Defined after NonLocalPotential below.
+inline void exponential(FourierTransform& ft, NonLocalPotential* nlp, int mloc, int nstloc, std::complex<double>* c,
+                        const double* occ_local, const double* v, const double* kpg2, double dt1, double dt2 = 0.0,
+                        std::complex<double>* c2 = 0, int order = 4);
+
 class NonLocalPotential {
  public:
   // kpgx = basis.kpgx_ptr(0) (3*ngw, component-major), omega = basis.cell().volume()
@@ -147,6 +154,14 @@ inline double hpsi(FourierTransform& ft, NonLocalPotential* nlp, int mloc, int n
   check(qb200_hpsi(ft.plan(), nlp ? nlp->handle() : nullptr, mloc, nstloc, reinterpret_cast<const double*>(c), occ_local, v,
                    kpg2, reinterpret_cast<double*>(dwf), &enl), "qb200_hpsi");
   return enl;
+}
+
+inline void exponential(FourierTransform& ft, NonLocalPotential* nlp, int mloc, int nstloc, std::complex<double>* c,
+                        const double* occ_local, const double* v, const double* kpg2, double dt1, double dt2,
+                        std::complex<double>* c2, int order)
+{
+  check(qb200_exponential(ft.plan(), nlp ? nlp->handle() : nullptr, mloc, nstloc, reinterpret_cast<double*>(c), occ_local, v, kpg2,
+                          order, dt1, dt2, reinterpret_cast<double*>(c2)), "qb200_exponential");
 }
 
 }  // namespace qb200

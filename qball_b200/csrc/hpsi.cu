@@ -125,3 +125,81 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
   if (enl) *enl = e;
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ TDDFT propagator glue
+// y1 += f1*x ; y2 += f2*x (complex factors), one pass over the block (ComplexMatrix::axpy, ExponentialWavefunctionStepper.cc:124-133)
+__global__ void __launch_bounds__(256) k_zaxpy2(size_t n, double2 f1, const double2* __restrict__ x, double2* __restrict__ y1,
+                                                double2 f2, double2* __restrict__ y2)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 a = x[i];
+    double2 b = y1[i];
+    b.x += f1.x * a.x - f1.y * a.y;
+    b.y += f1.x * a.y + f1.y * a.x;
+    y1[i] = b;
+    if (y2) {
+      double2 c = y2[i];
+      c.x += f2.x * a.x - f2.y * a.y;
+      c.y += f2.x * a.y + f2.y * a.x;
+      y2[i] = c;
+    }
+  }
+}
+
+extern "C" int qb200_exponential(qb200_plan* p, qb200_nl* nl, int ldc, int nst, double* c, const double* occ, const double* v,
+                                 const double* kpg2, int order, double dt1, double dt2, double* c2)
+{
+  if (!p || !c || !v || nst < 0 || ldc < p->d.ngw || order < 1 || order > 16 || (nl && !occ)) { set_error("qb200_exponential: bad argument"); return QB200_EINVAL; }
+  if (nst == 0) return QB200_OK;
+  if (p->d.is_real) { set_error("qb200_exponential: the propagator needs complex wavefunctions (the reference requires force_complex_wf, vars/WfDyn.h:82-92)"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(p->device));
+  const size_t blk = 2 * (size_t)ldc * nst, nel = (size_t)ldc * nst;
+  int rc;
+  // device views of c (in/out) and c2 (out)
+  const bool chost = !is_device_ptr(c), c2host = c2 && !is_device_ptr(c2);
+  double *cd = c, *c2d = c2;
+  if ((rc = ensure_buf(&p->ex_a, &p->ex_a_cap, blk)) || (rc = ensure_buf(&p->ex_b, &p->ex_b_cap, blk))) return rc;
+  if (chost) {
+    p->res_ptr = nullptr;
+    if ((rc = ensure_buf(&p->st_c, &p->st_c_cap, blk))) return rc;
+    QB_CUDA(cudaMemcpyAsync(p->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    cd = p->st_c;
+  }
+  if (c2host) {
+    if ((rc = ensure_buf(&p->ex_c2, &p->ex_c2_cap, blk))) return rc;
+    c2d = p->ex_c2;
+  }
+  // device copies of v and kpg2 once for all applications of H
+  const double *vd = v, *kd = kpg2;
+  const size_t N = (size_t)p->d.np0 * p->d.np1 * p->d.np2;
+  if (!is_device_ptr(v)) {
+    if ((rc = ensure_buf(&p->st_v, &p->st_v_cap, N))) return rc;
+    QB_CUDA(cudaMemcpyAsync(p->st_v, v, N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    vd = p->st_v;
+  }
+  if (kpg2 && !is_device_ptr(kpg2)) {
+    if ((rc = ensure_buf(&p->st_kpg2, &p->st_kpg2_cap, p->d.ngw))) return rc;
+    QB_CUDA(cudaMemcpyAsync(p->st_kpg2, kpg2, p->d.ngw * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    kd = p->st_kpg2;
+  }
+  double2 f1 = make_double2(1.0, 0.0), f2 = make_double2(1.0, 0.0);
+  const double* operand = cd;
+  double* out = p->ex_b;
+  for (int n = 1; n <= order; n++) {
+    // factor *= -i dt / n   (ExponentialWavefunctionStepper.cc:100-103)
+    f1 = make_double2(f1.y * dt1 / n, -f1.x * dt1 / n);
+    f2 = make_double2(f2.y * dt2 / n, -f2.x * dt2 / n);
+    if ((rc = qb200_hpsi(p, nl, ldc, nst, operand, occ, vd, kd, out, nullptr))) return rc;      // ef_.energy(wf_, true, dwf, ...)
+    if (n == 1 && c2d) QB_CUDA(cudaMemcpyAsync(c2d, cd, blk * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));   // newwf_ = wf_
+    k_zaxpy2<<<148 * 8, 256, 0, p->stream>>>(nel, f1, (const double2*)out, (double2*)cd, f2, (double2*)c2d);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_zaxpy2 launch", __FILE__, __LINE__);
+    p->launches++;
+    operand = out;                                                                                // wf_ = dwf
+    out = (out == p->ex_b) ? p->ex_a : p->ex_b;
+  }
+  if (chost) QB_CUDA(cudaMemcpyAsync(c, cd, blk * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (c2host) QB_CUDA(cudaMemcpyAsync(c2, c2d, blk * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  QB_CUDA(cudaStreamSynchronize(p->stream));
+  return QB200_OK;
+}

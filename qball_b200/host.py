@@ -208,3 +208,13 @@ def hpsi(ft: FourierTransform, nlp, c, occ, v, kpg2, out) -> float:
     capi._check(ft._L.qb200_hpsi(ft._h, nlp._h if nlp is not None else None, ldc, nst, capi.ptr(c), capi.ptr(occ), capi.ptr(v),
                                  capi.ptr(kpg2), capi.ptr(out), C.byref(enl)), "qb200_hpsi")
     return enl.value
+
+
+def exponential(ft: FourierTransform, nlp, c, occ, v, kpg2, dt1: float, dt2: float = 0.0, c2=None, order: int = 4):
+    """ExponentialWavefunctionStepper::exponential(num_exp, dt1, dt2) with a frozen Hamiltonian
+    (ExponentialWavefunctionStepper.cc:51-149): c <- sum_N (-i dt1 H)^N/N! c in place; c2 (optional) <- the dt2 series."""
+    nst, ldc = _block_dims(c)
+    occ = np.ascontiguousarray(occ, dtype=np.float64)
+    capi._check(ft._L.qb200_exponential(ft._h, nlp._h if nlp is not None else None, ldc, nst, capi.ptr(c), capi.ptr(occ), capi.ptr(v),
+                                        capi.ptr(kpg2), int(order), float(dt1), float(dt2), capi.ptr(c2)), "qb200_exponential")
+    return c

@@ -359,3 +359,49 @@ def test_cuda_update_density_tail_vs_oracle(kpoint, host):
     assert relerr(back(rhog), rhog_ref) < TOL
     # the G = 0 coefficient is the electron count (vbasis is real: G = 0 sits at index 0, SlaterDet.cc:2776-2779)
     assert abs(back(rhog)[0].real - nel) < 1e-10 * abs(nel)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_cuda_exponential_propagator_vs_oracle(host):
+    """ExponentialWavefunctionStepper::exponential(2, dt1, dt2) with a frozen Hamiltonian
+    (ExponentialWavefunctionStepper.cc:51-149): 4th-order Taylor series of exp(-i dt H) applied to the block, both time
+    steps from one chain of H applications; oracle = the same recurrence over the oracle's H psi."""
+    cell, ecut, kpoint, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 5.0, (0.0, 0.0, 0.0), 5
+    b = P.make_basis(cell, ecut, kpoint, True)                       # force_complex_wf ON (vars/WfDyn.h:82-92)
+    assert not b["is_real"]
+    grid = P.density_grid(cell, ecut)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 1, False, seed=71)
+    v = 0.3 * R.synth_potential(*grid, seed=72)
+    occ = R.synth_occ(nst, nst)
+    rng = np.random.default_rng(73)
+    species = [dict(na=2, npr=4, lproj=np.array([0, 1, 1, 1], dtype=np.int32), wt=np.array([0.9, -0.4, -0.4, -0.4]),
+                    twnl=rng.standard_normal((4, ngw)) * np.exp(-b["kpg2"] / 4.0)[None, :], tau=rng.uniform(0, 10, (2, 3)))]
+    dt1, dt2, order = 0.05, 0.1, 4
+    oft = P.FT(b, *grid)
+    exp1, exp2, op = c.copy(), c.copy(), c.copy()
+    f1 = f2 = 1.0 + 0.0j
+    for n in range(1, order + 1):
+        f1 *= -1j * dt1 / n
+        f2 *= -1j * dt2 / n
+        _, op = P.hpsi(b, oft, np.ascontiguousarray(op), v, occ, species)
+        exp1 += f1 * op
+        exp2 += f2 * op
+    ft = H.FourierTransform(b, *grid)
+    nlp = H.NonLocalPotential(b, species)
+    if host:
+        cw, c2w, back = c.copy(), np.zeros_like(c), (lambda a: a)
+        H.exponential(ft, nlp, cw, occ, v, b["kpg2"], dt1, dt2, c2w, order)
+    else:
+        cw, c2w, back = _dev(c), _dev(np.zeros_like(c)), (lambda t: t.cpu().numpy())
+        H.exponential(ft, nlp, cw, occ, _dev(v), _dev(b["kpg2"]), dt1, dt2, c2w, order)
+    assert relerr(back(cw), exp1) < TOL
+    assert relerr(back(c2w), exp2) < TOL
+    # norm conservation to the order of the truncated series (the reference's own accuracy check for ETRS)
+    n0 = np.vdot(c[0], c[0]).real
+    n1 = np.vdot(back(cw)[0], back(cw)[0]).real
+    assert abs(n1 - n0) < 1e-4 * n0
+    # single-exponential form (num_exp == 1)
+    cw1 = _dev(c)
+    H.exponential(ft, nlp, cw1, occ, _dev(v), _dev(b["kpg2"]), dt1, order=order)
+    assert relerr(cw1.cpu().numpy(), exp1) < TOL
