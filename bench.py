@@ -313,11 +313,26 @@ def main():
     # algorithmic bytes of the xy stage per FFT unit: read+write the column-form plane rows, read v (H psi) / rmw rho-partial
     # is charged once per build: H psi unit 32*nvec*np2 + 8*N ; density unit 16*nvec*np2
     xy_bytes_step = nunits_h * (32.0 * nvec * np2 + 8.0 * N) + nst * (16.0 * nvec * np2) + 16.0 * N
+    # DRAM traffic per launch from the committed ncu --set full capture of this same command (tools/ncu_traffic.py)
+    ncu_traffic = {}
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+
+    def traffic_of(*keys):
+        """launch-weighted mean DRAM bytes per launch over the kernels `keys` (None unless every one was captured)"""
+        if args.workload != "mgo216" or not all(k in ncu_traffic for k in keys):
+            return None
+        return sum(ncu_traffic[k]["dram_bytes_per_launch"] for k in keys) / len(keys)
+
     roofline_hbm = None
     if xy_n:
         ach = xy_bytes_step * args.steps / (xy_ms * 1e-3) / 1e9
         roofline_hbm = {"kernel": "k_plane (fused xy stage)" if ft.fused() else "k_xrows+k_ycols (split xy stage)", "bound": "hbm",
-                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": traffic_of("k_plane_s<0>", "k_plane_s<1>") if ft.fused() else None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": xy_bytes_step * args.steps / xy_n,
                         "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
     # the whole local path (z columns + xy stage, both directions) against the HBM roofline with SURVEY.md section 8d's
     # per-unit algorithmic bytes: B_Hpsi = 48*ngw*cper + 64*nvec*np2 + 8*N, B_rho = 16*ngw + 32*nvec*np2 (+16*N per build)
@@ -344,7 +359,7 @@ def main():
         ach = nl_flops_step * args.steps / (nl_ms * 1e-3) / 1e12
         roofline_fp64 = {"kernel": ("k_fnl3 + k_back3 (DMMA projector GEMMs, 3-product complex form: 12 flops per complex MAC)" if m3
                                     else "k_fnl + k_back (DMMA projector GEMMs)"), "bound": "tensor", "achieved": ach, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic_of("k_fnl3<4>", "k_back3<4>") if m3 else None,
                          "zgemm_equivalent_tflops": nl_zgemm_flops_step * args.steps / (nl_ms * 1e-3) / 1e12,
                          "peak_source": "nominal FP64 37 TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)",
                          "launches": prof["k_fnl"][1] + prof["k_back"][1]}
