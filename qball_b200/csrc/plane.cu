@@ -8,7 +8,8 @@ namespace qb200 {
 
 // shapes compiled in (PlaneShape<np0, np1, xsplit, xskip, ysplit, yskip, groups, threads per group>)
 typedef PlaneShape<112, 112, 26, 60, 26, 60, 7, 64> ShapeMgO216;   // examples/MgO216: 112^3 grid, |h|,|k| <= 25
-typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32> ShapeMgO216w; // same, one warp per 8-column block (QB200_GROUP_THREADS=32)
+typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32> ShapeMgO216w;     // one warp per 8-column block (default)
+typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32, 114> ShapeMgO216ww; // + warp-owned x phase (k_plane_w, QB200_PLANE_W=1) // same, one warp per 8-column block (QB200_GROUP_THREADS=32)
 
 // threads per group the plan should use when nothing else is requested: the compiled MgO216 shape runs one warp per
 // 8-column block (14 blocks, all in one round, warps drift out of phase: 4 % faster than 7 groups of 64)
@@ -19,6 +20,20 @@ int plane_preferred_gthreads(int np0, int np1, int ksplit, int kskip)
   return (np0 == W::NP0 && np1 == W::NP1 && ksplit == W::YSPLIT && kskip == W::YSKIP) ? W::GT : 64;
 }
 
+// row pitch of the shared-memory plane: np0 | 1 (odd: conflict-free whole-CTA row passes) unless the warp-owned MgO216
+// geometry will run, whose 4-row passes need a pitch of 2 (mod 8) slots
+int plane_preferred_pitch(int np0, int np1, int ksplit, int kskip)
+{
+  typedef ShapeMgO216w W;
+  int gt = plane_preferred_gthreads(np0, np1, ksplit, kskip);
+  if (const char* e = getenv("QB200_GROUP_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= 256 && t % 32 == 0) gt = t; }
+  // opt-in (QB200_PLANE_W=1): measured 14.8 ms against 14.6 ms for k_plane_s on the same 14 x 32 geometry -- the x phase is
+  // too short for the warps to drift apart between the remaining barriers, so removing five of eight barriers bought nothing
+  const char* ew = getenv("QB200_PLANE_W");
+  const bool want_w = ew && ew[0] == '1';
+  return (want_w && np0 == W::NP0 && np1 == W::NP1 && ksplit == W::YSPLIT && kskip == W::YSKIP && gt == W::GT) ? ShapeMgO216ww::PITCH : (np0 | 1);
+}
+
 // 0: generic kernel; > 0: index of the compiled shape that matches the plan (hmax = max |rod_h|)
 int plane_select_static(const qb200_plan* p, int hmax)
 {
@@ -26,10 +41,13 @@ int plane_select_static(const qb200_plan* p, int hmax)
   const DevPlan& d = p->d;
   typedef ShapeMgO216 S;
   if (d.np0 == S::NP0 && d.np1 == S::NP1 && d.ksplit == S::YSPLIT && d.kskip == S::YSKIP && hmax < S::XSPLIT &&
-      p->plane_threads == S::NTHR && d.gthreads == S::GT) return 1;
+      p->plane_threads == S::NTHR && d.gthreads == S::GT && d.pitch0 == S::PITCH) return 1;
   typedef ShapeMgO216w W;
   if (d.np0 == W::NP0 && d.np1 == W::NP1 && d.ksplit == W::YSPLIT && d.kskip == W::YSKIP && hmax < W::XSPLIT &&
-      p->plane_threads == W::NTHR && d.gthreads == W::GT) return 2;
+      p->plane_threads == W::NTHR && d.gthreads == W::GT && d.pitch0 == W::PITCH) return 2;
+  typedef ShapeMgO216ww WW;
+  if (d.np0 == WW::NP0 && d.np1 == WW::NP1 && d.ksplit == WW::YSPLIT && d.kskip == WW::YSKIP && hmax < WW::XSPLIT &&
+      p->plane_threads == WW::NTHR && d.gthreads == WW::GT && d.pitch0 == WW::PITCH) return 3;
   return 0;
 }
 
@@ -47,6 +65,11 @@ int plane_opt_in(qb200_plan* p)
     int rc;
     if ((rc = opt_in(k_plane_s<OP_HPSI, ShapeMgO216>, bytes)) || (rc = opt_in(k_plane_s<OP_DENSITY, ShapeMgO216>, bytes)) ||
         (rc = opt_in(k_plane_s<OP_BWD, ShapeMgO216>, bytes)) || (rc = opt_in(k_plane_s<OP_FWD, ShapeMgO216>, bytes))) return rc;
+  }
+  if (p->static_shape == 3) {
+    int rc;
+    if ((rc = opt_in(k_plane_w<OP_HPSI, ShapeMgO216ww>, bytes)) || (rc = opt_in(k_plane_w<OP_DENSITY, ShapeMgO216ww>, bytes)) ||
+        (rc = opt_in(k_plane_w<OP_BWD, ShapeMgO216ww>, bytes)) || (rc = opt_in(k_plane_w<OP_FWD, ShapeMgO216ww>, bytes))) return rc;
   }
   if (p->static_shape == 2) {
     int rc;
@@ -74,6 +97,18 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_plane_s launch", __FILE__, __LINE__);
+    return QB200_OK;
+  }
+  if (p->static_shape == 3) {
+    typedef ShapeMgO216ww S;
+    switch (op) {
+      case OP_HPSI: k_plane_w<OP_HPSI, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      case OP_DENSITY: k_plane_w<OP_DENSITY, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      case OP_BWD: k_plane_w<OP_BWD, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+      default: k_plane_w<OP_FWD, S><<<grid, S::NTHR, p->smem_plane, p->stream>>>(d, zt, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_plane_w launch", __FILE__, __LINE__);
     return QB200_OK;
   }
   if (p->static_shape == 2) {

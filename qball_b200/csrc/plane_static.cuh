@@ -15,9 +15,9 @@
 
 namespace qb200 {
 
-template <int NP0_, int NP1_, int XSPLIT_, int XSKIP_, int YSPLIT_, int YSKIP_, int NGRP_, int GT_>
+template <int NP0_, int NP1_, int XSPLIT_, int XSKIP_, int YSPLIT_, int YSKIP_, int NGRP_, int GT_, int PITCH_ = (NP0_ | 1)>
 struct PlaneShape {
-  static constexpr int NP0 = NP0_, NP1 = NP1_, PITCH = NP0_ | 1;
+  static constexpr int NP0 = NP0_, NP1 = NP1_, PITCH = PITCH_;
   static constexpr int XSPLIT = XSPLIT_, XSKIP = XSKIP_;     // non-zero x: [0,XSPLIT) and [XSPLIT+XSKIP, NP0)
   static constexpr int YSPLIT = YSPLIT_, YSKIP = YSKIP_;     // kept rows:  [0,YSPLIT) and [YSPLIT+YSKIP, NP1)
   static constexpr int NKEEP = NP1_ - YSKIP_;
@@ -72,13 +72,14 @@ enum { Z_NONE = 0, Z_IN = 1, Z_OUT = 2 };
 
 // one radix-R pass, everything but the data known at compile time.  tw: packed twiddle table of the direction.
 template <int R, int S, bool DIT, int N, int LEN, int TWOFF, int ESTRIDE, int NLPAD, int ZMODE, int SPLIT, int SKIP, class LINEOFF>
-__device__ __forceinline__ void pass_s(int tid, int nthr, cplx* base, const cplx* tw)
+__device__ __forceinline__ void pass_s(int tid, int nthr, cplx* base, const cplx* tw, int nlv = NLPAD)
 {
   constexpr int M = LEN / R, NTASK = (N / R) * NLPAD;
   constexpr int STEP = (M == 1) ? N / R : M;   // natural-index distance of a task's elements in a pruned pass
   constexpr unsigned MASK = ZMODE == Z_IN ? zmask(R, STEP, SPLIT, SKIP) : ((1u << R) - 1u);
   for (int task = tid; task < NTASK; task += nthr) {
     const int line = task % NLPAD, q = task / NLPAD;
+    if (line >= nlv) continue;                  // (nlv == NLPAD unless the caller owns fewer lines: folds away)
     const int seg = q / M, t = q - seg * M;
     cplx* p = base + LINEOFF::off(line) + (seg * LEN + t) * ESTRIDE;
     const int u = (M == 1) ? revseg<N, R>(seg) : t;
@@ -131,27 +132,27 @@ __device__ __forceinline__ void pass_s(int tid, int nthr, cplx* base, const cplx
 
 // passes first..last (inclusive, ascending) of a DIF transform of length N; `sync` between passes
 template <int S, int N, int ESTRIDE, int NLPAD, class LINEOFF, int SPLIT, int SKIP, bool ZIN0, bool ZOUTLAST, int s, int last, class SYNC>
-__device__ __forceinline__ void dif_s(int tid, int nthr, cplx* base, const cplx* tw, SYNC sync)
+__device__ __forceinline__ void dif_s(int tid, int nthr, cplx* base, const cplx* tw, SYNC sync, int nlv = NLPAD)
 {
   constexpr FftDesc F = make_fft_desc(N);
   constexpr int Z = (s == 0 && ZIN0) ? Z_IN : ((s == F.nf - 1 && ZOUTLAST) ? Z_OUT : Z_NONE);
-  pass_s<F.r[s], S, false, N, F.len[s], F.twoff[s], ESTRIDE, NLPAD, Z, SPLIT, SKIP, LINEOFF>(tid, nthr, base, tw);
+  pass_s<F.r[s], S, false, N, F.len[s], F.twoff[s], ESTRIDE, NLPAD, Z, SPLIT, SKIP, LINEOFF>(tid, nthr, base, tw, nlv);
   if constexpr (s < last) {
     sync();
-    dif_s<S, N, ESTRIDE, NLPAD, LINEOFF, SPLIT, SKIP, ZIN0, ZOUTLAST, s + 1, last, SYNC>(tid, nthr, base, tw, sync);
+    dif_s<S, N, ESTRIDE, NLPAD, LINEOFF, SPLIT, SKIP, ZIN0, ZOUTLAST, s + 1, last, SYNC>(tid, nthr, base, tw, sync, nlv);
   }
 }
 
 // passes first..0 (descending) of a DIT transform of length N
 template <int S, int N, int ESTRIDE, int NLPAD, class LINEOFF, int SPLIT, int SKIP, bool ZINFIRST, bool ZOUT0, int s, class SYNC>
-__device__ __forceinline__ void dit_s(int tid, int nthr, cplx* base, const cplx* tw, SYNC sync)
+__device__ __forceinline__ void dit_s(int tid, int nthr, cplx* base, const cplx* tw, SYNC sync, int nlv = NLPAD)
 {
   constexpr FftDesc F = make_fft_desc(N);
   constexpr int Z = (s == F.nf - 1 && ZINFIRST) ? Z_IN : ((s == 0 && ZOUT0) ? Z_OUT : Z_NONE);
-  pass_s<F.r[s], S, true, N, F.len[s], F.twoff[s], ESTRIDE, NLPAD, Z, SPLIT, SKIP, LINEOFF>(tid, nthr, base, tw);
+  pass_s<F.r[s], S, true, N, F.len[s], F.twoff[s], ESTRIDE, NLPAD, Z, SPLIT, SKIP, LINEOFF>(tid, nthr, base, tw, nlv);
   if constexpr (s > 0) {
     sync();
-    dit_s<S, N, ESTRIDE, NLPAD, LINEOFF, SPLIT, SKIP, ZINFIRST, ZOUT0, s - 1, SYNC>(tid, nthr, base, tw, sync);
+    dit_s<S, N, ESTRIDE, NLPAD, LINEOFF, SPLIT, SKIP, ZINFIRST, ZOUT0, s - 1, SYNC>(tid, nthr, base, tw, sync, nlv);
   }
 }
 
@@ -315,6 +316,117 @@ __global__ void __launch_bounds__(SH::NTHR, 1) k_plane_s(const __grid_constant__
       dif_s<-1, np0, 1, SH::NKEEP, ROWS, SH::XSPLIT, SH::XSKIP, false, true, 0, FX.nf - 1>(tid, SH::NTHR, pl, tw0, csync);
       __syncthreads();
       for (int i = tid; i < nvec; i += SH::NTHR) ztrow[i] = pl[colpos[i]];
+    }
+    unit = nxt;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ warp-owned variant
+// k_plane_w<OP, SH>: k_plane_s with one WARP per group (SH::GT == 32) and the x phase made warp-local as well: warp g owns
+// RBX kept rows (low half for g < NGRP/2, high half above) and, through a table sorted by owner (P.wown: staged address |
+// plane position << 16, P.wown_iv: column index), zero-fills, scatters, x-transforms and finally gathers ITS rows without
+// any CTA barrier -- three CTA barriers per unit remain (staged data landed, x -> y, y -> x) instead of eight, and the
+// warps drift out of phase so that one warp's shared-memory traffic overlaps another's FP64 butterflies in the x phase
+// too.  The row pitch is 2 (mod 8) 16-byte slots, which keeps the 4-row x passes bank-conflict free.
+template <int PITCH> struct DenseRowsW {
+  static __device__ __forceinline__ int off(int line) { return line * PITCH; }
+};
+
+template <int OP, class SH>
+__global__ void __launch_bounds__(SH::NTHR, 1) k_plane_w(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
+                                                         cplx* __restrict__ f, double* __restrict__ rho_part,
+                                                         const double* __restrict__ fac, int nunits, int zero_imag)
+{
+  static_assert(SH::GT == 32 && SH::NGRP % 2 == 0 && SH::NP1 - SH::YSPLIT - SH::YSKIP == SH::YSPLIT, "warp-owned geometry");
+  static_assert(SH::NGRP * QB200_BLOCK_LINES == SH::NP0, "one column block per warp");
+  constexpr FftDesc FX = make_fft_desc(SH::NP0), FY = make_fft_desc(SH::NP1);
+  constexpr int np0 = SH::NP0, np1 = SH::NP1, pitch = SH::PITCH, np01 = np0 * np1;
+  constexpr int HALF = SH::NGRP / 2, RBX = (SH::YSPLIT + HALF - 1) / HALF;       // kept rows per warp
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx* tw0 = reinterpret_cast<cplx*>(smraw);
+  cplx* tw1 = tw0 + FX.twsize;
+  int* own_s = reinterpret_cast<int*>(tw1 + FY.twsize + P.nyrev_c);
+  int* owniv_s = own_s + 4 * P.ncolpos_c;
+  cplx* pl = tw1 + FY.twsize + P.nyrev_c + 2 * P.ncolpos_c;
+  const int nvec = P.nvec;
+  const int z = blockIdx.x;
+  const size_t N = (size_t)np01 * P.np2;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FX.twsize; i += SH::NTHR) tw0[i] = P.tw0p[i];
+  for (int i = tid; i < FY.twsize; i += SH::NTHR) tw1[i] = P.tw1p[i];
+  for (int i = tid; i < nvec; i += SH::NTHR) { own_s[i] = P.wown[i]; owniv_s[i] = P.wown_iv[i]; }
+  const int gid = tid >> 5, lane = tid & 31;
+  auto wsync = []() { __syncwarp(); };
+  // this warp's kept rows and its entries of the owner-sorted table
+  const int rlo = (gid < HALF) ? gid * RBX : (gid - HALF) * RBX;
+  const int nrow = max(0, min(RBX, SH::YSPLIT - rlo));
+  const int row0 = (gid < HALF) ? rlo : SH::YSPLIT + SH::YSKIP + rlo;
+  const int e0 = P.wown_start[gid], e1 = P.wown_start[gid + 1];
+  cplx* myrows = pl + row0 * pitch;
+  const int per = (OP == OP_FWD) ? 0 : P.stage_per;
+  const int G = gridDim.y;
+  auto stage = [&](int unit) {
+    const cplx* src = zt + ((size_t)unit * P.np2 + z) * nvec + gid * per;
+    const int cnt = min(per, nvec - gid * per);
+    cplx* dst = pl + SH::YSPLIT * pitch + gid * QB200_BLOCK_LINES;
+    for (int j = lane; j < cnt; j += 32) cp_async16(dst + (j >> 3) * pitch + (j & 7), src + j);
+  };
+  auto next_unit = [&](int u) {
+    u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    return u;
+  };
+  int unit = next_unit((int)blockIdx.y - G);
+  if (per && unit < nunits) stage(unit);
+  for (; unit < nunits;) {
+    const int nxt = next_unit(unit);
+    double facu = 0.0;
+    if (OP == OP_DENSITY) facu = fac[unit];
+    cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
+    if (per) cp_async_wait_all();
+    __syncthreads();                 // tables / every warp's staged values visible; the plane is free
+    if (OP != OP_FWD) {
+      for (int i = lane; i < nrow * pitch; i += 32) myrows[i] = make_double2(0.0, 0.0);
+      __syncwarp();
+      if (per) {
+        for (int e = e0 + lane; e < e1; e += 32) { const int w = own_s[e]; pl[w >> 16] = pl[w & 0xffff]; }
+      } else {
+        for (int e = e0 + lane; e < e1; e += 32) pl[own_s[e] >> 16] = ztrow[owniv_s[e]];
+      }
+      __syncwarp();
+      // x direction: this warp's rows, digit-reversed (zeros outside the sphere's h range) -> natural
+      dit_s<+1, np0, 1, RBX, DenseRowsW<pitch>, SH::XSPLIT, SH::XSKIP, true, false, FX.nf - 1>(lane, 32, myrows, tw0, wsync, nrow);
+      __syncthreads();
+    }
+    // y direction: the warp's block of 8 columns
+    {
+      const int c0 = gid * QB200_BLOCK_LINES;
+      cplx* blk = pl + c0;
+      if constexpr (OP != OP_FWD && FY.nf > 1) {
+        dif_s<+1, np1, pitch, QB200_BLOCK_LINES, ColsOff, SH::YSPLIT, SH::YSKIP, true, false, 0, FY.nf - 2>(lane, 32, blk, tw1, wsync);
+        __syncwarp();
+      }
+      MidArgs a;
+      a.v = v + (size_t)z * np01 + c0;
+      a.rho = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + c0;
+      a.f = f + (size_t)unit * N + (size_t)z * np01 + c0;
+      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag;
+      mid_s<OP, SH>(lane, 32, blk, QB200_BLOCK_LINES, a);
+      if constexpr ((OP == OP_HPSI || OP == OP_FWD) && FY.nf > 1) {
+        __syncwarp();
+        dit_s<-1, np1, pitch, QB200_BLOCK_LINES, ColsOff, SH::YSPLIT, SH::YSKIP, false, true, FY.nf - 2>(lane, 32, blk, tw1, wsync);
+      }
+      if (per && nxt < nunits) {
+        __syncwarp();                // the warp is done with its block before the block's dead rows are overwritten
+        stage(nxt);
+      }
+    }
+    if (OP == OP_HPSI || OP == OP_FWD) {
+      __syncthreads();
+      dif_s<-1, np0, 1, RBX, DenseRowsW<pitch>, SH::XSPLIT, SH::XSKIP, false, true, 0, FX.nf - 1>(lane, 32, myrows, tw0, wsync, nrow);
+      __syncwarp();
+      for (int e = e0 + lane; e < e1; e += 32) ztrow[owniv_s[e]] = pl[own_s[e] >> 16];
     }
     unit = nxt;
   }

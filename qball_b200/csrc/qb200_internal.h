@@ -47,6 +47,8 @@ struct DevPlan {
   // second-generation split xy stage (split_kernels.cuh)
   const int *xs_jr, *xs_x;             // per entry of keepcols: kept-row index, digit-reversed x position
   const int *yq;                       // natural y index held by position q after the y DIF transform
+  // warp-owned plane kernel (k_plane_w): columns sorted by owner warp: staged address | plane position << 16, column index
+  const int *wown, *wown_iv, *wown_start;
 };
 
 enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
@@ -60,6 +62,7 @@ namespace qb200 {
 int plane_opt_in(qb200_plan* p);
 int plane_select_static(const qb200_plan* p, int hmax);
 int plane_preferred_gthreads(int np0, int np1, int ksplit, int kskip);
+int plane_preferred_pitch(int np0, int np1, int ksplit, int kskip);
 int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, const double* fac, int nunits, int zero_imag);
 }
 

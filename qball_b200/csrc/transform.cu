@@ -335,7 +335,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   d.ntrans0 = std::max(std::abs(idxmax1), std::abs(idxmin1)) + 1;  // FourierTransform.cc:202
   if (2 * d.ntrans0 >= np1) { d.nkeep = np1; d.ksplit = np1; d.kskip = 0; }
   else { d.nkeep = 2 * d.ntrans0; d.ksplit = d.ntrans0; d.kskip = np1 - 2 * d.ntrans0; }
-  d.pitch0 = np0 | 1;
+  d.pitch0 = plane_preferred_pitch(np0, np1, d.ksplit, d.kskip);
   if (!factorize(np0, d.f0) || !factorize(np1, d.f1) || !factorize(np2, d.f2)) {
     set_error("qb200_plan_create: grid length not of the form 2^a 3^b 5^c 7^d 11^e"); delete p; return QB200_EUNSUPPORTED;
   }
@@ -543,6 +543,29 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     int hmax = 0;
     for (int r = 0; r < nrods; r++) hmax = std::max(hmax, std::abs(rod_h[r]));
     p->static_shape = plane_select_static(p, hmax);
+    // warp-owned variant of the compiled MgO216 geometry: tables sorted by the warp that owns a column's kept row
+    if (p->static_shape == 3 && !(p->smem_plane + (size_t)d.ncolpos_c * 16 <= (size_t)p->max_smem && d.ncolpos_c > 0 && d.stage_per >= 0)) p->static_shape = 0;
+    if (p->static_shape == 3 && p->smem_plane + (size_t)d.ncolpos_c * 16 <= (size_t)p->max_smem && d.ncolpos_c > 0) {
+      const int ngrp = p->plane_threads / d.gthreads, half = ngrp / 2, rbx = (d.ksplit + half - 1) / half, per = d.stage_per;
+      std::vector<std::vector<int> > by(ngrp);
+      for (int iv = 0; iv < d.nvec; iv++) {
+        const int kp = colhk[iv] / np0;
+        by[kp < d.ksplit ? kp / rbx : half + (kp - d.ksplit - d.kskip) / rbx].push_back(iv);
+      }
+      std::vector<int> wown, wiv, wstart(ngrp + 1, 0);
+      for (int g = 0; g < ngrp; g++) {
+        wstart[g] = (int)wown.size();
+        for (int iv : by[g]) {
+          int src = 0;
+          if (per) { const int sh = iv / per, j = iv % per; src = (d.ksplit + (j >> 3)) * d.pitch0 + sh * 8 + (j & 7); }
+          wown.push_back(src | (colpos[iv] << 16));
+          wiv.push_back(iv);
+        }
+      }
+      wstart[ngrp] = (int)wown.size();
+      if ((rc = upload(p, wown, &d.wown)) || (rc = upload(p, wiv, &d.wown_iv)) || (rc = upload(p, wstart, &d.wown_start))) { qb200_plan_destroy(p); return rc; }
+      p->smem_plane += (size_t)d.ncolpos_c * 16;
+    }
     if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
   }
   p->ws_bytes = p->fused ? (256ll << 20) : (8ll << 30);

@@ -98,7 +98,7 @@ def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
     g = load_golden("mgo216_shape_112cubed")
     b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
-    assert ft.query(10) >= 1, "MgO216 plan did not select a compiled shape"
+    assert ft.query(10) == 2, "MgO216 plan did not select the compiled shape (one warp per column block)"
     del ft
     monkeypatch.setenv("QB200_NO_STATIC", "1")
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
@@ -113,6 +113,13 @@ def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
     monkeypatch.setenv("QB200_GROUP_THREADS", "64")
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
     assert ft.query(10) == 1
+    del ft
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+    # ... and the warp-owned x phase (k_plane_w, opt-in)
+    monkeypatch.delenv("QB200_GROUP_THREADS")
+    monkeypatch.setenv("QB200_PLANE_W", "1")
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(10) == 3
     del ft
     _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
 
