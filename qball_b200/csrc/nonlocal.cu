@@ -285,13 +285,19 @@ __global__ void __launch_bounds__(256) k_fnl_finish(const double* __restrict__ w
   if (threadIdx.x == 0) eblk[blockIdx.x] = red[0];
 }
 
-__global__ void k_sum_blocks(const double* __restrict__ eblk, int n, double* __restrict__ acc)
+// *acc += sum of eblk[0..n): one block of 256 threads, fixed assignment and fixed tree -> deterministic
+__global__ void __launch_bounds__(256) k_sum_blocks(const double* __restrict__ eblk, int n, double* __restrict__ acc)
 {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < n; i++) s += eblk[i];
-    *acc += s;
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += eblk[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) *acc += red[0];
 }
 
 // ------------------------------------------------------------------------------------------------ cp += anl * fs
@@ -707,7 +713,7 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   else if (real) k_fnl_finish<1><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
   else k_fnl_finish<0><<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
   NL_LAUNCH_CHECK(nl);
-  k_sum_blocks<<<1, 32, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
+  k_sum_blocks<<<1, 256, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
   prof_end(nl->stream);
   NL_LAUNCH_CHECK(nl);
   if (!compute_hpsi) return QB200_OK;
