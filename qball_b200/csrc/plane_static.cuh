@@ -182,10 +182,6 @@ __device__ __forceinline__ void mid_s(int tid, int nthr, cplx* blk, int nlines, 
         const double* vp = a.v + g0;
 #pragma unroll
         for (int j = 0; j < R; j++) vv[j] = __ldg(vp + j * YSTEP);
-      } else if (OP == OP_DENSITY) {
-        const double* rp = a.rho + g0;
-#pragma unroll
-        for (int j = 0; j < R; j++) vv[j] = rp[j * YSTEP];
       }
 #pragma unroll
       for (int k = 0; k < R; k++) if (mask_bit(MASK, k)) x[k] = p[k * SH::PITCH];
@@ -195,8 +191,14 @@ __device__ __forceinline__ void mid_s(int tid, int nthr, cplx* blk, int nlines, 
         for (int j = 0; j < R; j++) { x[j].x *= vv[j]; x[j].y = a.zero_imag ? 0.0 : x[j].y * vv[j]; }
       } else if (OP == OP_DENSITY) {
         double* rp = a.rho + g0;
+        // fire-and-forget reduction at the L2 (red.global.add.f64) instead of load / add / store: no load latency in the
+        // pass and half the LSU instructions (xy stage 14.6 -> 14.3 ms).  Every address is owned by one thread of one CTA,
+        // whose reductions to it are applied in program (= unit) order: deterministic.
 #pragma unroll
-        for (int j = 0; j < R; j++) rp[j * YSTEP] = vv[j] + a.facu * (x[j].x * x[j].x + x[j].y * x[j].y);
+        for (int j = 0; j < R; j++) {
+          const double val = a.facu * (x[j].x * x[j].x + x[j].y * x[j].y);
+          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rp + j * YSTEP), "d"(val) : "memory");
+        }
       } else if (OP == OP_BWD) {
         cplx* fp = a.f + g0;
 #pragma unroll
