@@ -35,6 +35,9 @@ WORKLOADS = {
     "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=64,
                   species=[("Au", 992, [0, 1, 1, 1])],
                   note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 64 states (the full 10118-state job holds ~1265 per GPU on 8)"),
+    "si54p": dict(cell=(0, 15.525, 15.525, 15.525, 0, 15.525, 15.525, 15.525, 0), ecut=32.5, kpoint=(0, 0, 0), force_complex=False, nst=109,
+                  species=[("Si", 54, [0, 1, 1, 1])],
+                  note="examples/si54p as a Gamma-point real-wavefunction case (65 Ry, 126^3 grid, 109 states, 216 projectors; SURVEY.md 8d)"),
     "sih4": dict(cell=(14, 0, 0, 0, 14, 0, 0, 0, 14), ecut=18.0, kpoint=(0, 0, 0), force_complex=False, nst=4,
                  species=[("Si", 1, [0, 1, 1, 1])], note="examples/sih4 (Gamma, real wavefunctions, 60^3 grid)"),
 }
@@ -133,7 +136,7 @@ def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
     if not R.have_ref():
         return None
     tmp = tempfile.mkdtemp(prefix="qbbench_")
-    spfiles = {"mgo216": S.mgo_species, "au992": S.au_species}.get(wl_name)
+    spfiles = {"mgo216": S.mgo_species, "au992": S.au_species, "si54p": S.si_species}.get(wl_name)
     species, atoms = [], []
     if spfiles:
         species = spfiles(tmp)
@@ -198,7 +201,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = {"mgo216": 16, "au992": 1, "sih4": 4}[args.workload]
+        sample = {"mgo216": 16, "au992": 1, "sih4": 4, "si54p": 16}[args.workload]
         ts = []
         for i in range(args.warmup + args.steps):
             t = run_reference_cpu(args.workload, sample, 1)
@@ -443,7 +446,7 @@ def main():
     # ---------------------------------------------------------------- cpu baseline (rank 0, N=1): the compiled reference
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {"mgo216": 16, "au992": 1, "sih4": 4}[args.workload]
+        sample = {"mgo216": 16, "au992": 1, "sih4": 4, "si54p": 16}[args.workload]
         try:
             tcpu = run_reference_cpu(args.workload, sample, 1)
         except Exception as ex:  # noqa: BLE001

@@ -24,7 +24,6 @@ struct SplitShape {
   static constexpr bool STATIC = true;
   static constexpr int NP0 = NP0_, NP1 = NP1_, XSPLIT = XSPLIT_, XSKIP = XSKIP_, YSPLIT = YSPLIT_, YSKIP = YSKIP_;
   static constexpr int XB = XB_, ROWB = ROWB_, PITCH0 = NP0_ | 1, YPITCH = XB_ | 1, NKEEP = NP1_ - YSKIP_;
-  static_assert(NKEEP % ROWB_ == 0, "row blocks must be whole");
 };
 template <int PITCH> struct DenseRows {
   static __device__ __forceinline__ int off(int line) { return line * PITCH; }
@@ -79,7 +78,7 @@ __global__ void __launch_bounds__(256, 2) k_xrows2(const __grid_constant__ DevPl
       if (unit + G < nunits) issue(unit + G);
       if constexpr (SH::STATIC) {
         constexpr FftDesc FX = make_fft_desc(SH::NP0);
-        dit_s<+1, SH::NP0, 1, SH::ROWB, DenseRows<SH::PITCH0>, SH::XSPLIT, SH::XSKIP, true, false, FX.nf - 1>(tid, nthr, rows0, tw, [] { __syncthreads(); });
+        dit_s<+1, SH::NP0, 1, SH::ROWB, DenseRows<SH::PITCH0>, SH::XSPLIT, SH::XSKIP, true, false, FX.nf - 1>(tid, nthr, rows0, tw, [] { __syncthreads(); }, nr);
       } else {
         fft_block_dit<+1>(g, rows0, nr, rowb, lm, 1, P.f0, tw, P.f0.nf - 1, false, nokeep);
       }
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(256, 2) k_xrows2(const __grid_constant__ DevPl
       cplx* rows = rows0 + (size_t)buf * rowb * pitch;
       if constexpr (SH::STATIC) {
         constexpr FftDesc FX = make_fft_desc(SH::NP0);
-        dif_s<-1, SH::NP0, 1, SH::ROWB, DenseRows<SH::PITCH0>, SH::XSPLIT, SH::XSKIP, false, true, 0, FX.nf - 1>(tid, nthr, rows, tw, [] { __syncthreads(); });
+        dif_s<-1, SH::NP0, 1, SH::ROWB, DenseRows<SH::PITCH0>, SH::XSPLIT, SH::XSKIP, false, true, 0, FX.nf - 1>(tid, nthr, rows, tw, [] { __syncthreads(); }, nr);
       } else {
         fft_block_dif<-1>(g, rows, nr, rowb, lm, 1, P.f0, tw, 0, P.f0.nf, false, nokeep);
       }

@@ -218,8 +218,24 @@ static int ensure_work(qb200_plan* p, int units)
 }
 
 typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;
+typedef qb200::SplitShape<126, 126, 29, 68, 29, 68, 16, 8> ShapeSi54p;    // examples/si54p at 65 Ry: 126^3 grid, |h|,|k| <= 28
 typedef qb200::ZShape<112, 29, 26, 60> ZbMgO216;   // examples/MgO216: 112 planes, |l| <= 25; 29 / 22 columns per tile fill one wave
 typedef qb200::ZShape<112, 22, 26, 60> ZfMgO216;   // examples/gold_benchmark: 252 x 252 x 896 grid
+
+template <class S> static bool split_shape_matches(const qb200::DevPlan& d, int hmax, int rowb)
+{
+  return d.np0 == S::NP0 && d.np1 == S::NP1 && d.ksplit == S::YSPLIT && d.kskip == S::YSKIP && hmax < S::XSPLIT && d.xb == S::XB &&
+         rowb == S::ROWB;
+}
+
+template <class S> static int split_opt_in(qb200_plan* p)
+{
+  int rc;
+  if ((rc = opt_in_smem(k_xrows2<+1, S>, p->smem_xr[0])) || (rc = opt_in_smem(k_xrows2<-1, S>, p->smem_xr[1])) ||
+      (rc = opt_in_smem(k_ycols2<OP_HPSI, S>, p->smem_yc[OP_HPSI])) || (rc = opt_in_smem(k_ycols2<OP_DENSITY, S>, p->smem_yc[OP_DENSITY])) ||
+      (rc = opt_in_smem(k_ycols2<OP_BWD, S>, p->smem_yc[OP_BWD])) || (rc = opt_in_smem(k_ycols2<OP_FWD, S>, p->smem_yc[OP_FWD]))) return rc;
+  return QB200_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ z-column kernels v2
 // Picks, for each direction, the number of columns per tile (cb; rb = rods per CTA) so that the persistent grid
@@ -489,21 +505,16 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
          (rc = opt_in_smem(k_ycols2<OP_BWD, DynSplit>, p->smem_yc[OP_BWD])) || (rc = opt_in_smem(k_ycols2<OP_FWD, DynSplit>, p->smem_yc[OP_FWD])))) {
       qb200_plan_destroy(p); return rc;
     }
-    // compiled shape: the gold benchmark's 252 x 252 planes (examples/gold_benchmark, |h|,|k| <= 55)
+    // compiled shapes: the gold benchmark's 252 x 252 planes and si54p's 126 x 126 planes
     p->split_static = 0;
     {
-      typedef ShapeAu992 S;
       int hmax = 0;
       for (int r = 0; r < nrods; r++) hmax = std::max(hmax, std::abs(rod_h[r]));
       const char* ns = getenv("QB200_NO_STATIC");
-      if (p->split2 && !(ns && ns[0] == '1') && np0 == S::NP0 && np1 == S::NP1 && d.ksplit == S::YSPLIT && d.kskip == S::YSKIP &&
-          hmax < S::XSPLIT && d.xb == S::XB && rowb == S::ROWB) {
-        p->split_static = 1;
-        if ((rc = opt_in_smem(k_xrows2<+1, S>, p->smem_xr[0])) || (rc = opt_in_smem(k_xrows2<-1, S>, p->smem_xr[1])) ||
-            (rc = opt_in_smem(k_ycols2<OP_HPSI, S>, p->smem_yc[OP_HPSI])) || (rc = opt_in_smem(k_ycols2<OP_DENSITY, S>, p->smem_yc[OP_DENSITY])) ||
-            (rc = opt_in_smem(k_ycols2<OP_BWD, S>, p->smem_yc[OP_BWD])) || (rc = opt_in_smem(k_ycols2<OP_FWD, S>, p->smem_yc[OP_FWD]))) {
-          qb200_plan_destroy(p); return rc;
-        }
+      if (p->split2 && !(ns && ns[0] == '1')) {
+        if (split_shape_matches<ShapeAu992>(d, hmax, rowb)) { p->split_static = 1; rc = split_opt_in<ShapeAu992>(p); }
+        else if (split_shape_matches<ShapeSi54p>(d, hmax, rowb)) { p->split_static = 2; rc = split_opt_in<ShapeSi54p>(p); }
+        if (rc) { qb200_plan_destroy(p); return rc; }
       }
     }
   }
@@ -689,6 +700,24 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
   return QB200_OK;
 }
 
+// the three kernels of the split xy stage for one engine / compiled shape
+template <int OP, class SH>
+static int launch_split(qb200_plan* p, dim3 gr, dim3 gy, const double* v, double* f, const double* fac, int nunits, int zero_imag)
+{
+  const DevPlan& d = p->d;
+  if (OP != OP_FWD) {
+    k_xrows2<+1, SH><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+    QB_LAUNCH_CHECK(p);
+  }
+  k_ycols2<OP, SH><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
+  QB_LAUNCH_CHECK(p);
+  if (OP == OP_HPSI || OP == OP_FWD) {
+    k_xrows2<-1, SH><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
+    QB_LAUNCH_CHECK(p);
+  }
+  return QB200_OK;
+}
+
 // the xy stage for `nunits` units whose column data sits in p->zt
 template <int OP>
 static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, const double* fac, int ngroups, int zero_imag)
@@ -712,22 +741,14 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
     const dim3 gr(nrb, d.np2, spread((long)nrb * d.np2));
     const dim3 gy(nxb, d.np2, OP == OP_DENSITY ? std::max(1, std::min(ngroups, nunits)) : spread((long)nxb * d.np2));
     prof_begin(1, p->stream);
-    const bool st = p->split_static == 1;
-    if (OP != OP_FWD) {
-      if (st) k_xrows2<+1, ShapeAu992><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
-      else k_xrows2<+1, DynSplit><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
-      QB_LAUNCH_CHECK(p);
-    }
-    if (st) k_ycols2<OP, ShapeAu992><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
-    else k_ycols2<OP, DynSplit><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
-    QB_LAUNCH_CHECK(p);
-    if (OP == OP_HPSI || OP == OP_FWD) {
-      if (st) k_xrows2<-1, ShapeAu992><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
-      else k_xrows2<-1, DynSplit><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
-      QB_LAUNCH_CHECK(p);
+    int rc;
+    switch (p->split_static) {
+      case 1: rc = launch_split<OP, ShapeAu992>(p, gr, gy, v, f, fac, nunits, zero_imag); break;
+      case 2: rc = launch_split<OP, ShapeSi54p>(p, gr, gy, v, f, fac, nunits, zero_imag); break;
+      default: rc = launch_split<OP, DynSplit>(p, gr, gy, v, f, fac, nunits, zero_imag); break;
     }
     prof_end(p->stream);
-    return QB200_OK;
+    return rc;
   }
   const int rowb = (int)((p->smem_rows / 16 - d.np0) / d.pitch0);
   dim3 gr((d.nkeep + rowb - 1) / rowb, d.np2, nunits);

@@ -306,10 +306,14 @@ def test_properties_au992_full_size_split_path(monkeypatch):
     assert relerr(res["static"][1], res["generic"][1]) < 1e-12
 
 
-def test_cuda_vs_oracle_si54p_shape_gamma_real():
+@pytest.mark.parametrize("compiled", [True, False])
+def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     """examples/si54p as a Gamma-point real-wavefunction case (fcc-type cell 2 x 15.525, 65 Ry, 126^3 grid,
     ngw 33114): planes of 126 x 127 x 16 B exceed shared memory, so this runs the real-basis pair path (+ odd tail)
-    through the run-time-shape z-column and split xy kernels; checked against the oracle on the same seeded inputs."""
+    through the z-column and split xy kernels -- with the compiled 126 x 126 shape and with the run-time-shape engine;
+    checked against the oracle on the same seeded inputs."""
+    if not compiled:
+        monkeypatch.setenv("QB200_NO_STATIC", "1")
     a = 15.525
     cell, ecut = (0, a, a, a, 0, a, a, a, 0), 32.5
     b = P.make_basis(cell, ecut, (0, 0, 0), False)
@@ -321,7 +325,7 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real():
     occ = np.array([2.0, 2.0, 1.0, 0.0, 0.5])
     oft = P.FT(b, *grid)
     ft = H.FourierTransform(b, *grid)
-    assert not ft.fused() and ft.query(14) == 1 and ft.query(11) == 1
+    assert not ft.fused() and ft.query(14) == 1 and ft.query(11) == 1 and ft.query(15) == (2 if compiled else 0)
     want = oft.rs_mul_add(c, v, np.zeros_like(c))
     P.kinetic_add(b["kpg2"], c, want)
     got = _dev(np.zeros_like(c))
