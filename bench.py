@@ -402,6 +402,50 @@ def main():
                  "what": "qb200_exponential, order 4, Hamiltonian frozen, block resident in HBM (per rank)"}
         del cprop
 
+    # ---------------------------------------------------------------- subspace dense LA on the resident block:
+    # the PSD/PSDA descent direction a = c^H Hc, Hc -= c a (with band sharding: after an NCCL all-gather of the state
+    # blocks -- the path's one exchange step) and SlaterDet::gram on this rank's block
+    subspace = None
+    if not args.no_e2e:
+        try:
+            la = H.SubspaceLA(b, device=local_rank, stream=stream)
+            from qball_b200 import parallel as PAR
+
+            def la_step(do_gram):
+                with torch.cuda.stream(stream):
+                    call = PAR.allgather_states(c, world * nst) if world > 1 else c
+                    la.residual(call, hres)
+                    if do_gram:
+                        la.gram(cg)
+
+            with torch.cuda.stream(stream):
+                hres = hpsi.clone()
+                cg = c.clone()
+            la_step(True)
+            sync_all()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            with torch.cuda.stream(stream):
+                ev[0].record(stream)
+            la_step(False)
+            with torch.cuda.stream(stream):
+                ev[1].record(stream)
+                cg.copy_(c)
+                la.gram(cg)
+                ev[2].record(stream)
+            sync_all()
+            ms_res, ms_gram = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+            cx = 1.0 if b["is_real"] else 4.0            # real flops per (real | complex) multiply-add pair / 2
+            fl_res = 2 * 2.0 * cx * (world * nst) * nst * ngw * (2 if b["is_real"] else 1)
+            fl_gram = 2 * 2.0 * cx * nst * nst * ngw * (2 if b["is_real"] else 1)
+            subspace = {"residual_ms": ms_res, "residual_tflops_gemm_equivalent": fl_res / (ms_res * 1e-3) / 1e12,
+                        "gram_ms": ms_gram, "gram_tflops_gemm_equivalent": fl_gram / (ms_gram * 1e-3) / 1e12,
+                        "nall": world * nst, "nst": nst,
+                        "what": "qb200_residual (incl. the all-gather of c when sharded) and qb200_gram (incl. the copy of c) on the "
+                                "resident block; flops counted as the two zgemm/dgemm calls of the reference (full S for gram)"}
+            del hres, cg, la
+        except Exception as ex:  # noqa: BLE001
+            subspace = {"error": str(ex)[:200]}
+
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI, copies inside
     e2e = None
     if not args.no_e2e:
@@ -463,7 +507,7 @@ def main():
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
-               "kernel_ms_per_step": prof_ms, "tddft": tddft, "enl": enl,
+               "kernel_ms_per_step": prof_ms, "tddft": tddft, "subspace_la": subspace, "enl": enl,
                "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
                          "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
         emit(out)

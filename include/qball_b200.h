@@ -141,6 +141,32 @@ int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c
 int qb200_exponential(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, double* c, const double* occ, const double* v,
                       const double* kpg2, int order, double dt1, double dt2, double* c2);
 
+/* ---- subspace dense linear algebra between two H psi evaluations, on the same FP64
+ *      tensor-core GEMM kernels as the projector contractions.  One qb200_la per (spin, k-point) wavefunction block.
+ *      Blocks are ComplexMatrix::val as everywhere else (column-major ldc x n, rows >= ngw padding); real bases are read
+ *      through the reference's DoubleMatrix proxy view (2*ldc real rows, PSDAWavefunctionStepper.cc:67-69). */
+typedef struct qb200_la qb200_la;
+int qb200_la_create(qb200_la** la, int device, int ngw, int is_real);
+int qb200_la_set_stream(qb200_la* la, void* cuda_stream);
+/* bytes the packed copy of the wavefunction block may take (default 8 GiB); larger blocks are swept in plane-wave chunks */
+int qb200_la_set_workspace(qb200_la* la, long long bytes);
+int qb200_la_destroy(qb200_la* la);
+long long qb200_la_query(const qb200_la* la, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call */
+/* descent direction of the SD / PSD / PSDA wavefunction steppers:
+ *   complex:  a.gemm('c','n',1.0,c,cp,0.0); cp.gemm('n','n',-1.0,c,a,1.0)       PSDAWavefunctionStepper.cc:264-277
+ *   real:     a.gemm('t','n',2.0,c,cp,0.0); a.ger(-1.0,c,0,cp,0); cp.gemm('n','n',-1.0,c,a,1.0)          :65-84
+ *   (PSDWavefunctionStepper.cc:62-90 is the same sequence)
+ * c:  ldc x nall, ALL states of the Slater determinant (with band sharding: the gathered block, qball_b200/parallel.py);
+ * hc: ldc x nst, this rank's columns of H psi, replaced by H psi - c a;
+ * a:  optional output, nall x nst column-major (complex, or real for real bases) = this rank's columns of a. */
+int qb200_residual(qb200_la* la, int ldc, int nall, const double* c, int nst, double* hc, double* a);
+/* SlaterDet::gram(), norm-conserving branch                                               SlaterDet.cc:1043-1143
+ *   complex: s.herk('l','c',1.0,c,0.0); s.potrf('l'); c.trsm('r','l','c','n',1.0,s)
+ *   real:    s.syrk('l','t',2.0,c,0.0); s.syr('l',-1.0,c,0,'r'); s.potrf('l'); c.trsm('r','l','t','n',1.0,s)
+ * c: ldc x nst (all states on this rank), orthonormalised in place.  info (may be NULL): LAPACK potrf's info; a
+ * non-positive-definite overlap returns QB200_EINVAL with *info = order of the failing minor and leaves c unchanged. */
+int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info);
+
 /* ---- optional per-kernel timing (CUDA events on the launching stream, recorded around every launch while enabled).
  *      categories: 0 k_zcol_bwd, 1 xy stage (k_plane, or k_xrows+k_ycols), 2 k_zcol_fwd, 3 k_fnl, 4 k_fnl_finish+sum,
  *      5 k_back, 6 k_rho_reduce, 7 k_anl_gen.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the

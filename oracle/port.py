@@ -59,6 +59,9 @@ def lib():
         L.qbo_nl_energy_species.restype = C.c_double
         L.qbo_nl_energy_species.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp,
                                             dp, C.c_double, C.c_int, C.c_int, dp]
+        L.qbo_residual.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_gram.restype = C.c_int
+        L.qbo_gram.argtypes = [C.c_int, C.c_int, C.c_int, dp]
         _lib = L
     return _lib
 
@@ -186,3 +189,23 @@ def hpsi(b: dict, ft: FT, c, v, occ, species):
     kinetic_add(b["kpg2"], c, cp)
     ft.rs_mul_add(c, v, cp)
     return enl, cp
+
+
+def residual(c, hc, is_real):
+    """PSD/PSDA descent direction (PSDAWavefunctionStepper.cc:65-84, 264-277): returns (hc - c a, a) with a = c^H hc;
+    c: (nall, ldc), hc: (nst, ldc) complex128; a: (nst, nall) (row n = column n of the reference's matrix a)."""
+    nall, ldc = c.shape
+    nst = hc.shape[0]
+    out = np.array(hc, dtype=np.complex128, copy=True)
+    a = np.zeros((nst, nall), dtype=np.float64 if is_real else np.complex128)
+    lib().qbo_residual(ldc, nall, nst, int(is_real), _d(np.ascontiguousarray(c)), _d(out), _d(a))
+    return out, a
+
+
+def gram(c, is_real):
+    """SlaterDet::gram (SlaterDet.cc:1043-1143): Cholesky orthonormalisation, returns the new (nst, ldc) block"""
+    nst, ldc = c.shape
+    out = np.array(c, dtype=np.complex128, copy=True)
+    info = lib().qbo_gram(ldc, nst, int(is_real), _d(out))
+    assert info == 0, f"gram: leading minor {info} not positive definite"
+    return out

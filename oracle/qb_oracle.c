@@ -550,3 +550,116 @@ double qbo_nl_energy_species(int ngw, int ldc, int nst, const double* c, const d
   free(anl); free(fnl);
   return enl;
 }
+
+/* ------------------------------------------------------------------------------------------------ subspace dense LA (f1)
+ * Storage as ComplexMatrix::val (math/matrix.h:294-340): column-major ldc x nst complex; real bases are read through the
+ * DoubleMatrix proxy (2*ldc real rows).  nall = columns of c (all states), hc holds nst columns (the local shard). */
+void qbo_residual(int ldc, int nall, int nst, int is_real, const double* c, double* hc, double* a)
+{
+  /* PSDAWavefunctionStepper.cc:65-84 (real) / :264-277 (complex); PSDWavefunctionStepper.cc:62-90 is identical */
+  const size_t m2 = 2 * (size_t)ldc;
+  if (is_real) {
+    /* a = 2 c^T cp (gemm 't','n', 2.0) ; a -= c(row 0)^T cp(row 0) (ger -1.0) ; cp -= c a (gemm 'n','n', -1.0) */
+    #pragma omp parallel for collapse(2)
+    for (int n = 0; n < nst; n++)
+      for (int m = 0; m < nall; m++) {
+        const double* cm = c + m2 * m; const double* hn = hc + m2 * n;
+        double s = 0.0;
+        for (size_t i = 0; i < m2; i++) s += cm[i] * hn[i];
+        a[(size_t)n * nall + m] = 2.0 * s - cm[0] * hn[0];
+      }
+    #pragma omp parallel for
+    for (int n = 0; n < nst; n++) {
+      double* hn = hc + m2 * n;
+      for (int m = 0; m < nall; m++) {
+        const double* cm = c + m2 * m; const double am = a[(size_t)n * nall + m];
+        for (size_t i = 0; i < m2; i++) hn[i] -= cm[i] * am;
+      }
+    }
+  } else {
+    /* a = c^H cp (gemm 'c','n') ; cp -= c a */
+    #pragma omp parallel for collapse(2)
+    for (int n = 0; n < nst; n++)
+      for (int m = 0; m < nall; m++) {
+        const double* cm = c + m2 * m; const double* hn = hc + m2 * n;
+        double sr = 0.0, si = 0.0;
+        for (int i = 0; i < ldc; i++) {
+          sr += cm[2*i] * hn[2*i] + cm[2*i+1] * hn[2*i+1];
+          si += cm[2*i] * hn[2*i+1] - cm[2*i+1] * hn[2*i];
+        }
+        a[2*((size_t)n * nall + m)] = sr; a[2*((size_t)n * nall + m)+1] = si;
+      }
+    #pragma omp parallel for
+    for (int n = 0; n < nst; n++) {
+      double* hn = hc + m2 * n;
+      for (int m = 0; m < nall; m++) {
+        const double* cm = c + m2 * m;
+        const double ar = a[2*((size_t)n * nall + m)], ai = a[2*((size_t)n * nall + m)+1];
+        for (int i = 0; i < ldc; i++) {
+          hn[2*i] -= cm[2*i] * ar - cm[2*i+1] * ai;
+          hn[2*i+1] -= cm[2*i] * ai + cm[2*i+1] * ar;
+        }
+      }
+    }
+  }
+}
+
+int qbo_gram(int ldc, int nst, int is_real, double* c)
+{
+  /* SlaterDet::gram, norm-conserving branch (SlaterDet.cc:1043-1143):
+   *   real:    s = 2 c^T c (syrk 'l','t') - c(row 0)^T c(row 0) (syr) ; potrf 'l' ; c <- c L^-T  (trsm 'r','l','t','n')
+   *   complex: s = c^H c (herk 'l','c') ; potrf 'l' ; c <- c L^-H (trsm 'r','l','c','n')
+   * s, L: nst x nst, lower triangle, here complex for both (imaginary parts stay 0 for real bases). */
+  const size_t m2 = 2 * (size_t)ldc;
+  const int n = nst;
+  double* s = (double*)calloc(2 * (size_t)n * n, sizeof(double));
+  #pragma omp parallel for schedule(dynamic)
+  for (int j = 0; j < n; j++)
+    for (int i = j; i < n; i++) {                               /* s[i,j] = sum conj(c_i) c_j, i >= j */
+      const double* ci = c + m2 * i; const double* cj = c + m2 * j;
+      double sr = 0.0, si = 0.0;
+      if (is_real) {
+        for (size_t k = 0; k < m2; k++) sr += ci[k] * cj[k];
+        sr = 2.0 * sr - ci[0] * cj[0];
+      } else
+        for (int k = 0; k < ldc; k++) {
+          sr += ci[2*k] * cj[2*k] + ci[2*k+1] * cj[2*k+1];
+          si += ci[2*k] * cj[2*k+1] - ci[2*k+1] * cj[2*k];
+        }
+      s[2*((size_t)j * n + i)] = sr; s[2*((size_t)j * n + i)+1] = si;
+    }
+  /* Cholesky s = L L^H, lower, column by column (LAPACK xPOTRF's definition) */
+  for (int j = 0; j < n; j++) {
+    double d = s[2*((size_t)j * n + j)];
+    for (int k = 0; k < j; k++) { const double* l = s + 2*((size_t)k * n + j); d -= l[0]*l[0] + l[1]*l[1]; }
+    if (!(d > 0.0)) { free(s); return j + 1; }
+    d = sqrt(d);
+    s[2*((size_t)j * n + j)] = d; s[2*((size_t)j * n + j)+1] = 0.0;
+    for (int i = j + 1; i < n; i++) {
+      double vr = s[2*((size_t)j * n + i)], vi = s[2*((size_t)j * n + i)+1];
+      for (int k = 0; k < j; k++) {                              /* - L[i,k] conj(L[j,k]) */
+        const double* li = s + 2*((size_t)k * n + i); const double* lj = s + 2*((size_t)k * n + j);
+        vr -= li[0]*lj[0] + li[1]*lj[1];
+        vi -= li[1]*lj[0] - li[0]*lj[1];
+      }
+      s[2*((size_t)j * n + i)] = vr / d; s[2*((size_t)j * n + i)+1] = vi / d;
+    }
+  }
+  /* X L^H = C  ->  X[:,j] = ( C[:,j] - sum_{k<j} X[:,k] conj(L[j,k]) ) / L[j,j], columns in increasing order */
+  for (int j = 0; j < n; j++) {
+    double* xj = c + m2 * j;
+    for (int k = 0; k < j; k++) {
+      const double* xk = c + m2 * k;
+      const double lr = s[2*((size_t)k * n + j)], li = -s[2*((size_t)k * n + j)+1];
+      #pragma omp parallel for
+      for (int i = 0; i < ldc; i++) {
+        xj[2*i] -= xk[2*i] * lr - xk[2*i+1] * li;
+        xj[2*i+1] -= xk[2*i] * li + xk[2*i+1] * lr;
+      }
+    }
+    const double dinv = 1.0 / s[2*((size_t)j * n + j)];
+    for (size_t i = 0; i < m2; i++) xj[i] *= dinv;
+  }
+  free(s);
+  return 0;
+}

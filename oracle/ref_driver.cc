@@ -10,6 +10,8 @@
 //   SlaterDet::rs_mul_add                 src/qball/SlaterDet.cc:971-1040
 //   SlaterDet::compute_density            src/qball/SlaterDet.cc:839-932
 //   NonLocalPotential::energy (NC branch) src/qball/NonLocalPotential.cc:1909-2171
+//   DoubleMatrix/ComplexMatrix gemm, ger  as called by PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:65-84, 264-277)
+//   SlaterDet::gram                       src/qball/SlaterDet.cc:1043-1143
 // The kinetic term of EnergyFunctional::energy (EnergyFunctional.cc:1675-1690) lives inside a function that needs a
 // whole Sample; its three-line loop is restated here in the same order (clear -> nonlocal -> kinetic -> local).
 //
@@ -249,6 +251,31 @@ int main(int argc, char** argv)
         cp[ig+mloc*n] += 0.5 * kpg2[ig] * c[ig+mloc*n];       // EnergyFunctional.cc:1675-1677
     sd.rs_mul_add(ft, &v[0], dsd);                               // EnergyFunctional.cc:1695
     dump(out + ".hpsi.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+    // ---- descent direction of the PSD/PSDA steppers on (psi, H psi): the reference's own matrix calls, in the order of
+    //      PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:65-84 real, :264-277 complex)
+    if (basis.real()) {
+      DoubleMatrix c_proxy(sd.c());
+      DoubleMatrix cp_proxy(dsd.c());
+      DoubleMatrix am(c_proxy.context(), c_proxy.n(), c_proxy.n(), c_proxy.nb(), c_proxy.nb());
+      am.gemm('t','n',2.0,c_proxy,cp_proxy,0.0);
+      am.ger(-1.0,c_proxy,0,cp_proxy,0);
+      cp_proxy.gemm('n','n',-1.0,c_proxy,am,1.0);
+      dump(out + ".resid_a.f64", am.cvalptr(), (size_t)nst*nst*sizeof(double));
+    } else {
+      ComplexMatrix& c_proxy = sd.c();
+      ComplexMatrix& cpm = dsd.c();
+      ComplexMatrix am(c_proxy.context(), c_proxy.n(), c_proxy.n(), c_proxy.nb(), c_proxy.nb());
+      am.gemm('c','n',1.0,c_proxy,cpm,0.0);
+      cpm.gemm('n','n',-1.0,c_proxy,am,1.0);
+      dump(out + ".resid_a.f64", am.cvalptr(), (size_t)nst*nst*sizeof(complex<double>));
+    }
+    dump(out + ".resid.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+  }
+  // ---- SlaterDet::gram (SlaterDet.cc:1043-1143) on the input coefficients
+  {
+    SlaterDet gsd(sd);
+    gsd.gram();
+    dump(out + ".gram.f64", gsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
   }
   delete nlp;
   }

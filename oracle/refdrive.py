@@ -104,6 +104,9 @@ def run_reference(case: Case, seed: int = 1, nocc: int | None = None, workdir: s
     r["rho"] = _load(prefix, "rho.f64", np.float64)
     r["hpsi"] = _load(prefix, "hpsi.f64", np.complex128).reshape(case.nst, b["mloc"])
     r["enl"] = float(_load(prefix, "enl.f64", np.float64)[0])
+    r["resid"] = _load(prefix, "resid.f64", np.complex128).reshape(case.nst, b["mloc"])
+    r["resid_a"] = _load(prefix, "resid_a.f64", np.float64 if b["is_real"] else np.complex128).reshape(case.nst, case.nst)
+    r["gram"] = _load(prefix, "gram.f64", np.complex128).reshape(case.nst, b["mloc"])
     sp = []
     for i in range(b["nsp"]):
         h = _load(prefix, f"sp{i}.hdr.i32", np.int32)

@@ -766,3 +766,6 @@ extern "C" int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, 
 
 double* qb200_nl_enl_dev(qb200_nl* nl) { return nl->enl_dev; }
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s) { cudaStream_t o = nl->stream; nl->stream = s; return o; }
+
+// the subspace dense linear algebra on the same GEMM kernels (qb200_residual, qb200_gram)
+#include "subspace_la.cuh"

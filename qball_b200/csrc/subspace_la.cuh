@@ -1,0 +1,549 @@
+// qball_b200/csrc/subspace_la.cuh -- SURVEY section 8 row f1: the subspace dense linear algebra that sits between two
+// H psi evaluations of a ground-state iteration, on the device and on the same FP64 tensor-core GEMM kernels as the
+// projector contractions (this file is included at the end of nonlocal.cu and reuses k_fnl3 / k_back3 / k_fnl / k_back):
+//
+//   qb200_residual : A = C^H (HC) ; HC -= C A          PSDAWavefunctionStepper.cc:65-84 (real), :264-277 (complex);
+//                                                       PSDWavefunctionStepper.cc:62-90 is the same sequence
+//   qb200_gram     : S = C^H C ; S = L L^H ; C <- C L^-H   SlaterDet::gram, SlaterDet.cc:1043-1143 (norm-conserving)
+//
+// Both are "projector contractions with the wavefunctions as projectors": the block C plays the role of anl.
+//   complex bases: C is packed per chunk of plane waves into the three-kind real matrix W3 of nonlocal_3m.cuh
+//                  (rows grouped by 8 states: Re, Im, Re+Im), k_fnl3 forms C^H X as three real DMMA GEMMs, a finish
+//                  kernel reduces the split-K partials in fixed order and writes the second operand in k_back3's row order
+//   real bases   : the DoubleMatrix proxy of the reference (2*mloc real rows) is the block itself, so k_fnl<1> / k_back<0>
+//                  read it in place as their W operand (residual) or a per-chunk copy (gram: C is overwritten);
+//                  the factor 2 (G and -G) and the rank-1 term of real row 0 (ger / syr) are applied in the finish kernel.
+// gram: the nst x nst Cholesky factorisation runs on the device as a blocked right-looking algorithm (32 x 32 diagonal
+// blocks factorised and inverted in shared memory, panel and trailing updates as tile kernels), then L^-1 is formed by
+// block forward substitution and C <- C L^-H is one more k_back3 / k_back GEMM (overwrite form) from the packed copy.
+// Rows ig >= ngw of the blocks are padding (zero in the reference, SlaterDet.cc:2784-2787) and are neither read nor written.
+#pragma once
+
+namespace qb200 {
+
+#define LA_NB 32
+
+// ------------------------------------------------------------------------------------------------ packing
+// grid (ceil(gpad/128), nall), block 128: state m, plane waves [gbeg, gbeg+gcount) of the chunk -> W3 rows (Re, Im, Re+Im)
+__global__ void __launch_bounds__(128) k_pack_w3(const double2* __restrict__ c, size_t ldc, int gbeg, int gcount, int gpad,
+                                                 double* __restrict__ W3, size_t WP)
+{
+  const int gl = blockIdx.x * 128 + threadIdx.x;
+  if (gl >= gpad) return;
+  const int m = blockIdx.y;
+  double2 a = make_double2(0.0, 0.0);
+  if (gl < gcount) a = c[(size_t)m * ldc + gbeg + gl];
+  double* row = W3 + ((size_t)(m >> 3) * 24 + (m & 7)) * WP + gl;
+  row[0] = a.x;
+  row[8 * WP] = a.y;
+  row[16 * WP] = a.x + a.y;
+}
+// real bases: W[m][2g..2g+1] = c[g, m] for the chunk (a copy, because gram overwrites c)
+__global__ void __launch_bounds__(128) k_pack_wr(const double2* __restrict__ c, size_t ldc, int gbeg, int gcount, int gpad,
+                                                 double* __restrict__ W, size_t WP)
+{
+  const int gl = blockIdx.x * 128 + threadIdx.x;
+  if (gl >= gpad) return;
+  const int m = blockIdx.y;
+  double2 a = make_double2(0.0, 0.0);
+  if (gl < gcount) a = c[(size_t)m * ldc + gbeg + gl];
+  *reinterpret_cast<double2*>(W + (size_t)m * WP + 2 * gl) = a;
+}
+
+// ------------------------------------------------------------------------------------------------ finish: partials -> A or S
+// one thread per (n, m), m < nall rows, n < nst columns.  part as written by k_fnl3 / k_fnl<1>.
+//   RESIDUAL: a_out[n*nall + m] = A[m,n] (optional), second operand of the back GEMM = -A
+//   GRAM    : S[n*nS + m] = S[m,n] as complex (both triangles; potrf reads the lower one)
+// real bases: value = 2*sum - c(row 0, m) * x(row 0, n)   (gemm alpha 2.0 + ger/syr -1.0 on real row 0)
+template <int IS_REAL, int GRAM>
+__global__ void __launch_bounds__(256) k_la_finish(const double* __restrict__ part, int Mp, int nall, int nst, int ksplit,
+                                                   const double2* __restrict__ c, const double2* __restrict__ x, size_t ldc,
+                                                   double* __restrict__ a_out, double* __restrict__ fs, int FP,
+                                                   double2* __restrict__ S, int nS)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nst * nall) return;
+  const int n = (int)(idx / nall), m = (int)(idx % nall);
+  const int ncols = IS_REAL ? nst : 2 * nst;
+  double fr = 0.0, fi = 0.0;
+  if (IS_REAL) {
+    for (int ks = 0; ks < ksplit; ks++) fr += part[((size_t)ks * ncols + n) * Mp + m];
+    fr = 2.0 * fr - c[(size_t)m * ldc].x * x[(size_t)n * ldc].x;
+  } else {
+    for (int ks = 0; ks < ksplit; ks++) {
+      fr += part[((size_t)ks * ncols + 2 * n) * Mp + m];
+      fi += part[((size_t)ks * ncols + 2 * n + 1) * Mp + m];
+    }
+  }
+  if (GRAM) {
+    S[(size_t)n * nS + m] = make_double2(fr, fi);
+  } else if (IS_REAL) {
+    if (a_out) a_out[(size_t)n * nall + m] = fr;
+    fs[(size_t)n * FP + m] = -fr;
+  } else {
+    if (a_out) { a_out[2 * ((size_t)n * nall + m)] = fr; a_out[2 * ((size_t)n * nall + m) + 1] = fi; }
+    double* o = fs + (size_t)n * FP + (m >> 3) * 24 + (m & 7);
+    o[0] = -fr; o[8] = -fi; o[16] = -(fr + fi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ blocked Cholesky
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a conj(b)
+
+// one CTA (32 x 32): factorise the diagonal block at k0 in shared memory (unblocked, LAPACK zpotf2's recurrence),
+// write L_kk back and its inverse (lower triangular) to Dinv (32 x 32 column-major, zero upper part).
+// info (device int): first non-positive pivot + 1, as LAPACK.
+__global__ void __launch_bounds__(1024) k_potrf_diag(double2* __restrict__ S, int n, int k0, double2* __restrict__ Dinv,
+                                                     int* __restrict__ info)
+{
+  __shared__ double2 A[LA_NB][LA_NB + 1];     // A[col][row]
+  __shared__ double2 X[LA_NB][LA_NB + 1];
+  const int i = threadIdx.x, j = threadIdx.y;
+  const int nb = min(LA_NB, n - k0);
+  double2 v = make_double2(i == j ? 1.0 : 0.0, 0.0);          // identity padding beyond the matrix
+  if (i < nb && j < nb) v = i >= j ? S[(size_t)(k0 + j) * n + k0 + i] : make_double2(0.0, 0.0);
+  A[j][i] = v;
+  X[j][i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int p = 0; p < LA_NB; p++) {
+    if (i == p && j == p) {
+      double d = A[p][p].x;
+      if (!(d > 0.0)) { atomicCAS(info, 0, k0 + p + 1); d = 1.0; }
+      A[p][p] = make_double2(sqrt(d), 0.0);
+    }
+    __syncthreads();
+    if (j == p && i > p) { const double dinv = 1.0 / A[p][p].x; A[p][i] = make_double2(A[p][i].x * dinv, A[p][i].y * dinv); }
+    __syncthreads();
+    if (j > p && i >= j) { const double2 t = cmulc(A[p][i], A[p][j]); A[j][i].x -= t.x; A[j][i].y -= t.y; }
+    __syncthreads();
+  }
+  if (i < nb && j < nb && i >= j) S[(size_t)(k0 + j) * n + k0 + i] = A[j][i];
+  // inverse of the lower triangular block by forward substitution, one thread per column
+  if (j == 0) {
+    const int col = i;
+    for (int r = col; r < LA_NB; r++) {
+      double2 s = make_double2(r == col ? 1.0 : 0.0, 0.0);
+      for (int k = col; k < r; k++) { const double2 t = cmul(A[k][r], X[col][k]); s.x -= t.x; s.y -= t.y; }
+      const double dinv = 1.0 / A[r][r].x;
+      X[col][r] = make_double2(s.x * dinv, s.y * dinv);
+    }
+  }
+  __syncthreads();
+  Dinv[j * LA_NB + i] = i >= j ? X[j][i] : make_double2(0.0, 0.0);
+}
+
+// grid (row blocks below the diagonal block): A[r0.., k0..] <- A[r0.., k0..] * L_kk^-H = A * Dinv^H
+__global__ void __launch_bounds__(1024) k_potrf_panel(double2* __restrict__ S, int n, int k0, const double2* __restrict__ Dinv)
+{
+  __shared__ double2 A[LA_NB][LA_NB + 1];     // A[col][row]
+  __shared__ double2 D[LA_NB][LA_NB + 1];     // D[col][row] = Dinv
+  const int i = threadIdx.x, j = threadIdx.y;
+  const int r = k0 + LA_NB + blockIdx.x * LA_NB + i;
+  A[j][i] = (r < n && k0 + j < n) ? S[(size_t)(k0 + j) * n + r] : make_double2(0.0, 0.0);
+  D[j][i] = Dinv[j * LA_NB + i];
+  __syncthreads();
+  double2 s = make_double2(0.0, 0.0);
+  for (int p = 0; p <= j; p++) { const double2 t = cmulc(A[p][i], D[p][j]); s.x += t.x; s.y += t.y; }   // sum_p A[i,p] conj(Dinv[j,p])
+  if (r < n && k0 + j < n) S[(size_t)(k0 + j) * n + r] = s;
+}
+
+// grid (nt, nt), nt = trailing row blocks: S[bi, bj] -= P_bi P_bj^H for bi >= bj (P = the panel just computed)
+__global__ void __launch_bounds__(1024) k_potrf_trail(double2* __restrict__ S, int n, int k0)
+{
+  if (blockIdx.x < blockIdx.y) return;
+  __shared__ double2 Pi[LA_NB][LA_NB + 1];    // [p][row]
+  __shared__ double2 Pj[LA_NB][LA_NB + 1];
+  const int i = threadIdx.x, j = threadIdx.y;
+  const int t0 = k0 + LA_NB;
+  const int ri = t0 + blockIdx.x * LA_NB + i, rj = t0 + blockIdx.y * LA_NB + i;
+  const bool pok = k0 + j < n;
+  Pi[j][i] = (ri < n && pok) ? S[(size_t)(k0 + j) * n + ri] : make_double2(0.0, 0.0);
+  Pj[j][i] = (rj < n && pok) ? S[(size_t)(k0 + j) * n + rj] : make_double2(0.0, 0.0);
+  __syncthreads();
+  double2 s = make_double2(0.0, 0.0);
+#pragma unroll 8
+  for (int p = 0; p < LA_NB; p++) { const double2 t = cmulc(Pi[p][i], Pj[p][j]); s.x += t.x; s.y += t.y; }
+  const int cj = t0 + blockIdx.y * LA_NB + j;
+  if (ri < n && cj < n && ri >= cj) {
+    double2* d = S + (size_t)cj * n + ri;
+    d->x -= s.x; d->y -= s.y;
+  }
+}
+
+// grid (nblk): block column k of X = L^-1 by block forward substitution:
+//   X[k,k] = Dinv_k ; X[i,k] = -Dinv_i * sum_{j=k}^{i-1} L[i,j] X[j,k]      (X zero above the diagonal, pre-cleared)
+__global__ void __launch_bounds__(1024) k_trtri_cols(const double2* __restrict__ L, int n, const double2* __restrict__ Dinv,
+                                                     double2* __restrict__ X)
+{
+  __shared__ double2 Acc[LA_NB][LA_NB + 1];   // [col][row]
+  __shared__ double2 D[LA_NB][LA_NB + 1];
+  const int r = threadIdx.x, cc = threadIdx.y;
+  const int k = blockIdx.x, nblk = (n + LA_NB - 1) / LA_NB;
+  const int col = k * LA_NB + cc;
+  if (col < n && k * LA_NB + r < n) X[(size_t)col * n + k * LA_NB + r] = Dinv[(size_t)k * LA_NB * LA_NB + cc * LA_NB + r];
+  for (int i = k + 1; i < nblk; i++) {
+    __syncthreads();                            // X[j,k] of the previous steps visible; Acc / D free
+    const int row = i * LA_NB + r;
+    double2 s = make_double2(0.0, 0.0);
+    if (row < n && col < n)
+      for (int q = k * LA_NB; q < i * LA_NB; q++) {
+        const double2 t = cmul(L[(size_t)q * n + row], X[(size_t)col * n + q]);
+        s.x += t.x; s.y += t.y;
+      }
+    Acc[cc][r] = s;
+    D[cc][r] = Dinv[(size_t)i * LA_NB * LA_NB + cc * LA_NB + r];
+    __syncthreads();
+    double2 o = make_double2(0.0, 0.0);
+    for (int p = 0; p <= r; p++) { const double2 t = cmul(D[p][r], Acc[cc][p]); o.x -= t.x; o.y -= t.y; }
+    if (row < n && col < n) X[(size_t)col * n + row] = o;
+  }
+}
+
+// second operand of the back GEMM of gram: T = L^-H, T[m,n] = conj(X[n,m]) (upper triangular)
+template <int IS_REAL>
+__global__ void __launch_bounds__(256) k_gram_operand(const double2* __restrict__ X, int n, double* __restrict__ fs, int FP)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const int col = (int)(idx / n), m = (int)(idx % n);
+  double2 t = make_double2(0.0, 0.0);
+  if (m <= col) { const double2 x = X[(size_t)m * n + col]; t = make_double2(x.x, -x.y); }
+  if (IS_REAL) fs[(size_t)col * FP + m] = t.x;
+  else {
+    double* o = fs + (size_t)col * FP + (m >> 3) * 24 + (m & 7);
+    o[0] = t.x; o[8] = t.y; o[16] = t.x + t.y;
+  }
+}
+
+}  // namespace qb200
+
+using namespace qb200;
+
+struct qb200_la {
+  int device;
+  cudaStream_t stream;
+  int ngw, is_real;
+  long long budget;                             // bytes the packed copy W may take
+  double *W, *part, *fs; size_t W_cap, part_cap, fs_cap;
+  size_t W_WP;                                  // pitch W was last zero-filled for (3M pad rows must be zero)
+  double *S, *X, *Dinv; size_t S_cap, X_cap, Dinv_cap;
+  double *st_c, *st_x, *st_a; size_t st_c_cap, st_x_cap, st_a_cap;
+  int* info_dev;
+  long long launches;
+  int nsm;
+  int nchunks_last;
+};
+
+extern "C" int qb200_la_create(qb200_la** out, int device, int ngw, int is_real)
+{
+  if (!out || ngw < 1) { set_error("qb200_la_create: bad argument"); return QB200_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  QB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("qb200_la_create: no such CUDA device"); return QB200_ENODEV; }
+  QB_CUDA(cudaSetDevice(device));
+  qb200_la* la = new qb200_la();
+  la->device = device; la->stream = 0; la->ngw = ngw; la->is_real = is_real ? 1 : 0;
+  la->budget = 8ll << 30;
+  if (const char* e = getenv("QB200_LA_BYTES")) la->budget = std::max(1ll << 20, atoll(e));
+  la->W = la->part = la->fs = la->S = la->X = la->Dinv = la->st_c = la->st_x = la->st_a = nullptr;
+  la->W_cap = la->part_cap = la->fs_cap = la->S_cap = la->X_cap = la->Dinv_cap = la->st_c_cap = la->st_x_cap = la->st_a_cap = 0;
+  la->W_WP = 0; la->launches = 0; la->nchunks_last = 0; la->info_dev = nullptr;
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  la->nsm = prop.multiProcessorCount;
+  QB_CUDA(cudaMalloc((void**)&la->info_dev, sizeof(int)));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 2, 2>::SMEM));
+  QB_CUDA(cudaFuncSetAttribute(k_back3<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 2, 3>::SMEM));
+  *out = la;
+  return QB200_OK;
+}
+
+extern "C" int qb200_la_set_stream(qb200_la* la, void* s)
+{
+  if (!la) return QB200_EINVAL;
+  la->stream = (cudaStream_t)s;
+  return QB200_OK;
+}
+
+extern "C" int qb200_la_set_workspace(qb200_la* la, long long bytes)
+{
+  if (!la || bytes < (1ll << 20)) { set_error("qb200_la_set_workspace: bad argument"); return QB200_EINVAL; }
+  la->budget = bytes;
+  return QB200_OK;
+}
+
+extern "C" int qb200_la_destroy(qb200_la* la)
+{
+  if (!la) return QB200_OK;
+  cudaSetDevice(la->device);
+  for (double* p : { la->W, la->part, la->fs, la->S, la->X, la->Dinv, la->st_c, la->st_x, la->st_a }) if (p) cudaFree(p);
+  if (la->info_dev) cudaFree(la->info_dev);
+  delete la;
+  return QB200_OK;
+}
+
+extern "C" long long qb200_la_query(const qb200_la* la, int what)
+{
+  if (!la) return -1;
+  switch (what) {
+    case 9: return la->launches;
+    case 11: return la->nchunks_last;
+    case 12: return (long long)(la->W_cap * sizeof(double));
+    default: return -1;
+  }
+}
+
+namespace {
+
+struct LaGeom {
+  bool m3;                 // complex: three-kind packed copy + k_fnl3 / k_back3
+  int nall, RW, Mp, FP;    // rows of W, even pitch of part, pitch of the second operand
+  int gchunk, nchunks;
+  size_t WP, Welems;
+  int mt, nt, ksplit;
+};
+
+// nall "projector" rows, nst columns; in_place: real bases read the block itself as W (no copy, one chunk)
+LaGeom la_geometry(const qb200_la* la, int nall, int nst, bool in_place, size_t ldc)
+{
+  LaGeom g;
+  g.m3 = !la->is_real;
+  g.nall = nall;
+  g.RW = g.m3 ? 24 * ((nall + 7) / 8) : nall;
+  g.Mp = (nall + 1) & ~1;
+  g.FP = g.m3 ? g.RW : g.Mp;
+  const int ngw = la->ngw;
+  if (in_place) {
+    g.gchunk = (ngw + 15) / 16 * 16; g.nchunks = 1; g.WP = 2 * ldc; g.Welems = 0;
+  } else {
+    const long long per_g = g.m3 ? 8ll * 192 * ((nall + 63) / 64) : 16ll * nall;
+    long long gmax = la->budget / std::max(per_g, 1ll);
+    gmax = std::max(512ll, (gmax / 512) * 512);
+    g.gchunk = (int)std::min<long long>(gmax, ((long long)ngw + 15) / 16 * 16);
+    g.nchunks = (ngw + g.gchunk - 1) / g.gchunk;
+    g.WP = g.m3 ? (size_t)g.gchunk : 2 * (size_t)g.gchunk;
+    g.Welems = g.m3 ? (size_t)192 * ((nall + 63) / 64) * g.WP + 128 : (size_t)g.RW * g.WP;
+  }
+  g.mt = g.m3 ? (nall + 63) / 64 : (g.RW + NL_TM - 1) / NL_TM;
+  g.nt = g.m3 ? (nst + 63) / 64 : (nst + NL_TN - 1) / NL_TN;
+  const int slots = g.m3 ? 2 * la->nsm : la->nsm;
+  g.ksplit = 1;
+  const int maxk = std::max(1, std::min(g.gchunk, ngw) / 512);
+  double best = -1.0;
+  for (int k = 1; k <= std::min(maxk, 64); k++) {
+    const long ctas = (long)g.mt * g.nt * k;
+    const long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots) - 0.002 * k;
+    if (eff > best) { best = eff; g.ksplit = k; }
+  }
+  return g;
+}
+
+#define LA_LAUNCH_CHECK(la) do { (la)->launches++; cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return qb200::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+
+int la_prepare_W(qb200_la* la, const LaGeom& g)
+{
+  int rc;
+  if (g.Welems == 0) return QB200_OK;
+  if (la->W_cap < g.Welems) la->W_WP = 0;
+  if ((rc = nl_ensure(&la->W, &la->W_cap, g.Welems))) return rc;
+  if (g.m3 && la->W_WP != g.WP) {                    // pad rows of the last block of 8 / tile of 64 must be zero
+    QB_CUDA(cudaMemsetAsync(la->W, 0, la->W_cap * sizeof(double), la->stream));
+    la->W_WP = g.WP;
+  }
+  return QB200_OK;
+}
+
+int la_pack(qb200_la* la, const LaGeom& g, const double* c, size_t ldc, int gbeg, int gcount, int gpad)
+{
+  dim3 grid((gpad + 127) / 128, g.nall);
+  prof_begin(7, la->stream);
+  if (g.m3) k_pack_w3<<<grid, 128, 0, la->stream>>>((const double2*)c, ldc, gbeg, gcount, gpad, la->W, g.WP);
+  else k_pack_wr<<<grid, 128, 0, la->stream>>>((const double2*)c, ldc, gbeg, gcount, gpad, la->W, g.WP);
+  prof_end(la->stream);
+  LA_LAUNCH_CHECK(la);
+  return QB200_OK;
+}
+
+// part (+)= W^H x over one chunk
+int la_fnl(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, const double* x, size_t ldc, int nst, bool accumulate)
+{
+  int kper = ((g.m3 ? 1 : 2) * gcount + g.ksplit - 1) / g.ksplit;
+  kper = g.m3 ? (kper + N3_KS - 1) / N3_KS * N3_KS : (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
+  dim3 g1(g.mt, g.nt, g.ksplit);
+  prof_begin(3, la->stream);
+  if (g.m3) k_fnl3<4, 2, 2><<<g1, 256, Fnl3Cfg<4, 2, 2>::SMEM, la->stream>>>(W, g.WP, gbeg, gcount, kper, (const double2*)x, ldc, nst, la->part, g.Mp, g.nall, accumulate);
+  else k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, kper, (const double2*)x, ldc, nst, la->part, g.Mp, g.nall, accumulate);
+  prof_end(la->stream);
+  LA_LAUNCH_CHECK(la);
+  return QB200_OK;
+}
+
+// y[rows of the chunk, :] (+)= W * fs
+int la_back(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, double* y, size_t ldc, int nst, int overwrite)
+{
+  prof_begin(5, la->stream);
+  if (g.m3) k_back3<4, 2, 3><<<dim3(g.nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
+  else k_back<0><<<dim3((gcount + 63) / 64, g.nt), NL_THREADS, BK_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
+  prof_end(la->stream);
+  LA_LAUNCH_CHECK(la);
+  return QB200_OK;
+}
+
+}  // namespace
+
+// device pointers
+static int la_residual_dev(qb200_la* la, int ldc, int nall, const double* c, int nst, double* hc, double* a)
+{
+  int rc;
+  const bool in_place = la->is_real != 0;            // real bases: the block is its own W operand
+  const LaGeom g = la_geometry(la, nall, nst, in_place, ldc);
+  la->nchunks_last = g.nchunks;
+  if ((rc = la_prepare_W(la, g))) return rc;
+  const int ncols = la->is_real ? nst : 2 * nst;
+  if ((rc = nl_ensure(&la->part, &la->part_cap, (size_t)g.ksplit * ncols * g.Mp))) return rc;
+  if ((rc = nl_ensure(&la->fs, &la->fs_cap, (size_t)nst * g.FP))) return rc;
+  if (g.FP != (g.m3 ? 3 * nall : nall)) QB_CUDA(cudaMemsetAsync(la->fs, 0, (size_t)nst * g.FP * sizeof(double), la->stream));
+  const int ngw = la->ngw;
+  for (int ch = 0; ch < g.nchunks; ch++) {
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (!in_place && (rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_fnl(la, g, in_place ? c : la->W, gbeg, gcount, hc, ldc, nst, ch > 0))) return rc;
+  }
+  const size_t total = (size_t)nst * nall;
+  const int nblk = (int)((total + 255) / 256);
+  prof_begin(4, la->stream);
+  if (la->is_real) k_la_finish<1, 0><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, nall, nst, g.ksplit, (const double2*)c, (const double2*)hc, ldc, a, la->fs, g.FP, nullptr, 0);
+  else k_la_finish<0, 0><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, nall, nst, g.ksplit, (const double2*)c, (const double2*)hc, ldc, a, la->fs, g.FP, nullptr, 0);
+  prof_end(la->stream);
+  LA_LAUNCH_CHECK(la);
+  for (int i = 0; i < g.nchunks; i++) {
+    const int ch = g.nchunks - 1 - i;
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (!in_place && i > 0 && (rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;   // i == 0: still packed
+    if ((rc = la_back(la, g, in_place ? c : la->W, gbeg, gcount, hc, ldc, nst, 0))) return rc;
+  }
+  return QB200_OK;
+}
+
+static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
+{
+  int rc;
+  const int n = nst;
+  const LaGeom g = la_geometry(la, n, n, false, ldc);
+  la->nchunks_last = g.nchunks;
+  if ((rc = la_prepare_W(la, g))) return rc;
+  const int ncols = la->is_real ? n : 2 * n;
+  const int nblkd = (n + LA_NB - 1) / LA_NB;
+  if ((rc = nl_ensure(&la->part, &la->part_cap, (size_t)g.ksplit * ncols * g.Mp))) return rc;
+  if ((rc = nl_ensure(&la->fs, &la->fs_cap, (size_t)n * g.FP))) return rc;
+  if ((rc = nl_ensure(&la->S, &la->S_cap, 2 * (size_t)n * n))) return rc;
+  if ((rc = nl_ensure(&la->X, &la->X_cap, 2 * (size_t)n * n))) return rc;
+  if ((rc = nl_ensure(&la->Dinv, &la->Dinv_cap, 2 * (size_t)nblkd * LA_NB * LA_NB))) return rc;
+  QB_CUDA(cudaMemsetAsync(la->fs, 0, (size_t)n * g.FP * sizeof(double), la->stream));
+  QB_CUDA(cudaMemsetAsync(la->X, 0, 2 * (size_t)n * n * sizeof(double), la->stream));
+  QB_CUDA(cudaMemsetAsync(la->info_dev, 0, sizeof(int), la->stream));
+  const int ngw = la->ngw;
+  // S = C^H C
+  for (int ch = 0; ch < g.nchunks; ch++) {
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, c, ldc, n, ch > 0))) return rc;
+  }
+  const size_t total = (size_t)n * n;
+  const int nblk = (int)((total + 255) / 256);
+  prof_begin(4, la->stream);
+  if (la->is_real) k_la_finish<1, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)c, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
+  else k_la_finish<0, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)c, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
+  LA_LAUNCH_CHECK(la);
+  // S = L L^H (lower), blocked right-looking; Dinv[k] = L_kk^-1
+  double2* S = (double2*)la->S; double2* Dinv = (double2*)la->Dinv;
+  const dim3 tb(LA_NB, LA_NB);
+  for (int k = 0; k < nblkd; k++) {
+    const int k0 = k * LA_NB;
+    k_potrf_diag<<<1, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB, la->info_dev);
+    LA_LAUNCH_CHECK(la);
+    const int nt = nblkd - k - 1;
+    if (nt > 0) {
+      k_potrf_panel<<<nt, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB);
+      LA_LAUNCH_CHECK(la);
+      k_potrf_trail<<<dim3(nt, nt), tb, 0, la->stream>>>(S, n, k0);
+      LA_LAUNCH_CHECK(la);
+    }
+  }
+  // X = L^-1, then the GEMM operand T = L^-H
+  k_trtri_cols<<<nblkd, tb, 0, la->stream>>>(S, n, Dinv, (double2*)la->X);
+  LA_LAUNCH_CHECK(la);
+  if (la->is_real) k_gram_operand<1><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, la->fs, g.FP);
+  else k_gram_operand<0><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, la->fs, g.FP);
+  prof_end(la->stream);
+  LA_LAUNCH_CHECK(la);
+  int h_info = 0;
+  QB_CUDA(cudaMemcpyAsync(&h_info, la->info_dev, sizeof(int), cudaMemcpyDeviceToHost, la->stream));
+  QB_CUDA(cudaStreamSynchronize(la->stream));
+  if (info) *info = h_info;
+  if (h_info != 0) { set_error("qb200_gram: overlap matrix not positive definite (potrf info > 0)"); return QB200_EINVAL; }
+  // C <- C L^-H from the packed copy, chunk by chunk (a chunk's rows of C are overwritten only after they were packed)
+  for (int i = 0; i < g.nchunks; i++) {
+    const int ch = g.nchunks - 1 - i;
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (i > 0 && (rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_back(la, g, la->W, gbeg, gcount, c, ldc, n, 1))) return rc;
+  }
+  return QB200_OK;
+}
+
+extern "C" int qb200_residual(qb200_la* la, int ldc, int nall, const double* c, int nst, double* hc, double* a)
+{
+  if (!la || !c || !hc || nall < 0 || nst < 0 || ldc < la->ngw) { set_error("qb200_residual: bad argument"); return QB200_EINVAL; }
+  if (nall == 0 || nst == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(la->device));
+  int rc;
+  const size_t cb = 2 * (size_t)ldc * nall, xb = 2 * (size_t)ldc * nst, ab = (la->is_real ? 1 : 2) * (size_t)nall * nst;
+  const double* cd = c; double* xd = hc; double* ad = a;
+  if (!is_device_ptr(c)) {
+    if ((rc = nl_ensure(&la->st_c, &la->st_c_cap, cb))) return rc;
+    QB_CUDA(cudaMemcpyAsync(la->st_c, c, cb * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    cd = la->st_c;
+  }
+  if (!is_device_ptr(hc)) {
+    if ((rc = nl_ensure(&la->st_x, &la->st_x_cap, xb))) return rc;
+    QB_CUDA(cudaMemcpyAsync(la->st_x, hc, xb * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    xd = la->st_x;
+  }
+  if (a && !is_device_ptr(a)) {
+    if ((rc = nl_ensure(&la->st_a, &la->st_a_cap, ab))) return rc;
+    ad = la->st_a;
+  }
+  if ((rc = la_residual_dev(la, ldc, nall, cd, nst, xd, ad))) return rc;
+  if (xd != hc) QB_CUDA(cudaMemcpyAsync(hc, xd, xb * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+  if (a && ad != a) QB_CUDA(cudaMemcpyAsync(a, ad, ab * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+  if (xd != hc || (a && ad != a)) QB_CUDA(cudaStreamSynchronize(la->stream));
+  return QB200_OK;
+}
+
+extern "C" int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info)
+{
+  if (info) *info = 0;
+  if (!la || !c || nst < 0 || ldc < la->ngw) { set_error("qb200_gram: bad argument"); return QB200_EINVAL; }
+  if (nst == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(la->device));
+  int rc;
+  const size_t cb = 2 * (size_t)ldc * nst;
+  double* cd = c;
+  if (!is_device_ptr(c)) {
+    if ((rc = nl_ensure(&la->st_c, &la->st_c_cap, cb))) return rc;
+    QB_CUDA(cudaMemcpyAsync(la->st_c, c, cb * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    cd = la->st_c;
+  }
+  if ((rc = la_gram_dev(la, ldc, nst, cd, info))) return rc;
+  if (cd != c) {
+    QB_CUDA(cudaMemcpyAsync(c, cd, cb * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+    QB_CUDA(cudaStreamSynchronize(la->stream));
+  }
+  return QB200_OK;
+}

@@ -218,3 +218,53 @@ def exponential(ft: FourierTransform, nlp, c, occ, v, kpg2, dt1: float, dt2: flo
     capi._check(ft._L.qb200_exponential(ft._h, nlp._h if nlp is not None else None, ldc, nst, capi.ptr(c), capi.ptr(occ), capi.ptr(v),
                                         capi.ptr(kpg2), int(order), float(dt1), float(dt2), capi.ptr(c2)), "qb200_exponential")
     return c
+
+
+class SubspaceLA:
+    """The dense linear algebra the ground-state steppers run between two H psi evaluations:
+    residual() = the descent direction of PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:65-84, 264-277),
+    gram() = SlaterDet::gram (SlaterDet.cc:1043-1143).  Blocks are (nst, ldc) complex arrays/tensors as elsewhere."""
+
+    def __init__(self, basis, device: int = 0, stream=None):
+        L = capi.load()
+        g = basis.get if isinstance(basis, dict) else (lambda k: getattr(basis, k))
+        h = C.c_void_p()
+        capi._check(L.qb200_la_create(C.byref(h), device, int(g("ngw")), int(bool(g("is_real")))), "qb200_la_create")
+        self._h, self._L = h, L
+        self.is_real = bool(g("is_real"))
+        if stream is not None:
+            s_ = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+            capi._check(L.qb200_la_set_stream(h, s_), "qb200_la_set_stream")
+
+    def launches(self): return int(self._L.qb200_la_query(self._h, 9))
+    def query(self, what): return int(self._L.qb200_la_query(self._h, int(what)))
+
+    def set_workspace(self, nbytes: int):
+        capi._check(self._L.qb200_la_set_workspace(self._h, int(nbytes)), "qb200_la_set_workspace")
+
+    def residual(self, c, hc, a=None):
+        """hc <- hc - c (c^H hc); c holds ALL states (nall, ldc), hc this rank's (nst, ldc) columns of H psi;
+        a (optional output): (nst, nall), row n = column n of the reference's matrix a."""
+        nall, ldc = _block_dims(c)
+        nst, ldh = _block_dims(hc)
+        assert ldh == ldc
+        capi._check(self._L.qb200_residual(self._h, ldc, nall, capi.ptr(c), nst, capi.ptr(hc), capi.ptr(a)), "qb200_residual")
+        return hc
+
+    def gram(self, c):
+        """c <- c L^-H with c^H c = L L^H, in place"""
+        nst, ldc = _block_dims(c)
+        info = C.c_int(0)
+        capi._check(self._L.qb200_gram(self._h, ldc, nst, capi.ptr(c), C.byref(info)), "qb200_gram")
+        return c
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qb200_la_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

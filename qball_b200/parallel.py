@@ -3,7 +3,10 @@
 default blocking); v(r), projector tables and plan tables are replicated; H psi needs no exchange; the density needs ONE
 all-reduce of rho(r) (ChargeDensity.cc:309, BLACS dsum over state columns) and the scalars (E_nl, NonLocalPotential.cc:2629;
 integral of rho, ChargeDensity.cc:528) one small all-reduce.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is
-the plumbing."""
+the plumbing.
+The subspace linear algebra (qb200_residual) is the one place with a real exchange step: every
+rank needs ALL columns of c to form its columns of a = c^H (H c) and of c a -- allgather_states (NCCL all-gather over
+NVLink) replaces the reference's pzgemm communication over process columns."""
 from __future__ import annotations
 
 import torch
@@ -30,3 +33,21 @@ def allreduce_scalars(values, device=None, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [float(x) for x in t.cpu()]
+
+
+def allgather_states(c_local: torch.Tensor, nst: int, group=None) -> torch.Tensor:
+    """(nst, ldc) block of ALL states from the per-rank blocks of state_block(); ranks that own fewer than nb states
+    contribute zero columns that are trimmed again (the blocks are contiguous and in rank order)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return c_local
+    nb = nst // world + (1 if nst % world else 0)
+    ldc = c_local.shape[1]
+    send = c_local
+    if c_local.shape[0] != nb:
+        send = torch.zeros((nb, ldc), dtype=c_local.dtype, device=c_local.device)
+        send[:c_local.shape[0]] = c_local
+    out = torch.empty((world * nb, ldc), dtype=c_local.dtype, device=c_local.device)
+    # complex tensors travel as their (re, im) doubles
+    dist.all_gather_into_tensor(torch.view_as_real(out), torch.view_as_real(send.contiguous()), group=group)
+    return out[:nst]

@@ -67,3 +67,45 @@ def test_band_sharded_density_and_enl_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] < 1e-12 and res[1] < 1e-12 and res[2] < 1e-10, res
+
+
+def _worker_la(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import port as P
+    import refdrive as R
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cell, ecut, nst = (9, 0, 0, 0, 9, 0, 0, 0, 10), 4.0, 5           # 5 states on 2 ranks: blocks of 3 and 2
+    b = P.make_basis(cell, ecut, (0.25, 0, 0))
+    first, n = PAR.state_block(nst, rank, world)
+    c = R.synth_coefficients(b["kpg2"], ecut, n, b["ngw"], b["is_real"], seed=3, first_state=first)
+    hc = R.synth_coefficients(b["kpg2"], ecut, n, b["ngw"], b["is_real"], seed=4, first_state=first)
+    call = PAR.allgather_states(torch.from_numpy(c), nst).numpy()    # the exchange step
+    res, a = P.residual(np.ascontiguousarray(call), hc, b["is_real"])  # (the oracle stands in for qb200_residual)
+    gathered = PAR.allgather_states(torch.from_numpy(res), nst).numpy()
+    if rank == 0:
+        c_all = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=3)
+        h_all = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=4)
+        res_all, _ = P.residual(c_all, h_all, b["is_real"])
+        q.put((float(np.abs(call - c_all).max()), float(np.abs(gathered - res_all).max() / np.abs(res_all).max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_sharded_residual_world2():
+    """a = c^H (Hc)_local needs every column of c: all-gather of the state blocks, then each rank's columns of the
+    descent direction equal the single-rank result"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker_la, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == 0.0 and res[1] < 1e-13, res

@@ -1,0 +1,147 @@
+"""Subspace dense linear algebra: the PSD/PSDA descent direction (a = c^H Hc, Hc -= c a;
+PSDAWavefunctionStepper.cc:65-84, 264-277) and SlaterDet::gram (SlaterDet.cc:1043-1143).
+CPU: the plain-C oracle against the golden vectors produced by the reference's own matrix classes (tests/golden/la/) and
+against the compiled reference run live.  GPU: the CUDA path through the C ABI against the same vectors and, on seeded
+inputs at sizes that cross the GEMM tile boundaries, against the oracle.  Tolerance 1e-10 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import port as P
+import refdrive as R
+from util import GOLDEN, TOL, golden_names, load_golden, regen_inputs, relerr, checksum
+
+
+def _la_golden(name):
+    z = np.load(os.path.join(GOLDEN, "la", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _inputs(name):
+    g = load_golden(name)
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    return g, b, c
+
+
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_oracle_la_matches_reference_fixture(name):
+    g, b, c = _inputs(name)
+    la = _la_golden(name)
+    hpsi = g["hpsi"].reshape(c.shape)
+    assert abs(checksum(hpsi) - float(la["hpsi_checksum"])) <= 1e-12 * np.abs(hpsi).sum()
+    res, a = P.residual(c, hpsi, g["is_real"])
+    assert relerr(res, la["resid"]) < TOL
+    assert relerr(a, la["resid_a"]) < TOL
+    assert relerr(P.gram(c, g["is_real"]), la["gram"]) < TOL
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref/ref_driver not built (needs /root/reference)")
+@pytest.mark.parametrize("cell,ecut,kpoint,fc,nst", [
+    ((10, 0, 0, 0, 10, 0, 0, 0, 10), 6.0, (0, 0, 0), False, 9),
+    ((10, 0, 0, 0, 10, 0, 0, 0, 10), 6.0, (0, 0, 0), True, 7),
+    ((8, 0, 0, 2.0, 9, 0, -1.0, 0.5, 12), 5.0, (0.5, 0.5, 0.5), False, 5),
+])
+def test_oracle_la_vs_live_reference(cell, ecut, kpoint, fc, nst):
+    r = R.run_reference(R.Case(cell=cell, ecut=ecut, kpoint=kpoint, force_complex=fc, nst=nst), seed=5)
+    res, a = P.residual(r["c"], r["hpsi"], r["is_real"])
+    assert relerr(res, r["resid"]) < TOL and relerr(a, r["resid_a"]) < TOL
+    g = P.gram(r["c"], r["is_real"])
+    assert relerr(g, r["gram"]) < TOL
+    # the property gram exists for: orthonormal columns (real bases: with the G/-G weighting of the proxy)
+    ngw = r["ngw"]
+    s = g[:, :ngw].conj() @ g[:, :ngw].T
+    if r["is_real"]:
+        s = 2.0 * s.real - np.outer(g[:, 0].real, g[:, 0].real)
+    assert np.abs(s - np.eye(nst)).max() < 1e-12
+
+
+def test_oracle_gram_reports_singular_overlap():
+    b = P.make_basis((9, 0, 0, 0, 9, 0, 0, 0, 9), 4.0, (0.2, 0, 0), False)
+    c = R.synth_coefficients(b["kpg2"], 4.0, 3, b["ngw"], False, 2)
+    c[2] = 0.0      # a zero state: the third leading minor is exactly singular
+    out = np.array(c, copy=True)
+    info = P.lib().qbo_gram(c.shape[1], 3, 0, P._d(out))
+    assert info == 3
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_ptrs", [True, False])
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_cuda_la_vs_reference_fixture(name, device_ptrs):
+    from qball_b200 import host as H
+    g, b, c = _inputs(name)
+    la = _la_golden(name)
+    wrap = _dev if device_ptrs else (lambda x: np.ascontiguousarray(x).copy())
+    back = (lambda t: t.cpu().numpy()) if device_ptrs else (lambda x: x)
+    L = H.SubspaceLA(b)
+    hc = wrap(g["hpsi"].reshape(c.shape))
+    a = wrap(np.zeros((g["nst"], g["nst"]), dtype=np.float64 if g["is_real"] else np.complex128))
+    L.residual(wrap(c), hc, a)
+    assert relerr(back(hc), la["resid"]) < TOL
+    assert relerr(back(a), la["resid_a"]) < TOL
+    cg = wrap(c)
+    L.gram(cg)
+    assert relerr(back(cg), la["gram"]) < TOL
+    assert L.launches() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kpoint,fc,nst,nloc,ldpad,ws", [
+    ((0, 0, 0), False, 70, 70, 0, None),          # real basis, one partial tile
+    ((0, 0, 0), False, 200, 67, 3, None),         # real basis, band shard of 67 of 200 states, padded rows
+    ((0, 0, 0), True, 77, 77, 0, None),           # complex, nst not a multiple of 8
+    ((0.25, 0, 0.5), False, 150, 150, 5, None),   # complex k-point, several 64-state tiles, padded rows
+    ((0.25, 0, 0.5), False, 150, 40, 0, 1 << 20), # band shard + a workspace that forces plane-wave chunks
+])
+def test_cuda_la_vs_oracle(kpoint, fc, nst, nloc, ldpad, ws):
+    from qball_b200 import host as H
+    cell, ecut = (11, 0, 0, 0, 10, 0, 0, 0, 12), 7.0
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    ldc = b["ngw"] + ldpad
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], 21)
+    # a stand-in for H psi with the same structure (Im = 0 at G = 0 for real bases, zero padding rows)
+    hc = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], 22) * (1.0 + b["kpg2"].max() * 0.1)
+    first = (nst - nloc) // 2
+    hloc = np.ascontiguousarray(hc[first:first + nloc])
+    res_ref, a_ref = P.residual(c, hloc, b["is_real"])
+    L = H.SubspaceLA(b)
+    if ws:
+        L.set_workspace(ws)
+    hd = _dev(hloc)
+    ad = _dev(np.zeros_like(a_ref))
+    L.residual(_dev(c), hd, ad)
+    assert relerr(hd.cpu().numpy(), res_ref) < TOL
+    assert relerr(ad.cpu().numpy(), a_ref) < TOL
+    if ws and not b["is_real"]:
+        assert L.query(11) > 1, "expected the sweep to run in several plane-wave chunks"
+    assert np.all(hd.cpu().numpy()[:, b["ngw"]:] == 0.0), "padding rows must stay zero"
+    # gram on the whole block
+    g_ref = P.gram(c, b["is_real"])
+    cd = _dev(c)
+    L.gram(cd)
+    got = cd.cpu().numpy()
+    assert relerr(got, g_ref) < TOL
+    # a second call on the orthonormal block is the identity to rounding (idempotence)
+    L.gram(cd)
+    assert relerr(cd.cpu().numpy(), got) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_gram_singular_overlap_fails_loudly():
+    from qball_b200 import capi, host as H
+    b = P.make_basis((9, 0, 0, 0, 9, 0, 0, 0, 9), 4.0, (0.2, 0, 0), False)
+    c = R.synth_coefficients(b["kpg2"], 4.0, 40, b["ngw"], False, 2)
+    c[35] = 0.0
+    L = H.SubspaceLA(b)
+    cd = _dev(c)
+    with pytest.raises(capi.QB200Error):
+        L.gram(cd)
+    assert np.array_equal(cd.cpu().numpy(), c), "a failed factorisation must leave the block unchanged"
