@@ -398,7 +398,19 @@ def main():
             t1e.record(stream)
         sync_all()
         ms_exp = t0e.elapsed_time(t1e) / nrep
-        tddft = {"exponential_order4_ms": ms_exp, "hpsi_state_applies_per_s": world * nst * 4 / (ms_exp * 1e-3),
+        # current density of the block: 3 directions x 2 fused density passes (qb200_compute_current)
+        with torch.cuda.stream(stream):
+            kpgx_d = torch.from_numpy(np.ascontiguousarray(b["kpgx"])).to(dev)
+            cur = torch.zeros((3, N), dtype=torch.float64, device=dev)
+            H.compute_current(ft, c, 1.0, occ, omega, kpgx_d, cur)
+            t0c, t1c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0c.record(stream)
+            H.compute_current(ft, c, 1.0, occ, omega, kpgx_d, cur)
+            t1c.record(stream)
+        sync_all()
+        ms_cur = t0c.elapsed_time(t1c)
+        del cur, kpgx_d
+        tddft = {"exponential_order4_ms": ms_exp, "current_density_ms": ms_cur, "hpsi_state_applies_per_s": world * nst * 4 / (ms_exp * 1e-3),
                  "what": "qb200_exponential, order 4, Hamiltonian frozen, block resident in HBM (per rank)"}
         del cprop
 

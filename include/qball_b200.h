@@ -141,6 +141,16 @@ int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c
 int qb200_exponential(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, double* c, const double* occ, const double* v,
                       const double* kpg2, int order, double dt1, double dt2, double* c2);
 
+/* ---- CurrentDensity::update_current (CurrentDensity.cc:52-86) for one spin / k-point: the pair density of
+ *      SlaterDet::compute_density(FourierTransform&, double weight, complex<double>* rho, const SlaterDet& sd2)
+ *      (SlaterDet.cc:935-968) with sd2 = i*kpgx[idir]*c (:72-76), reduced to what the caller keeps:
+ *        cur[idir*N + r] += -Im sum_n fac[n] conj(psi_n(r)) FT^-1[i kpgx_idir c_n](r)      for fac[n] > 0, idir = 0,1,2
+ *      kpgx = Basis::kpgx_ptr(0) (3*ngw doubles, component-major), fac[n] = weight*occ[n]/omega (host array, as in
+ *      qb200_compute_density), cur: 3*N doubles, ACCUMULATED (the caller clears it and sums over k-points and ranks,
+ *      CurrentDensity.cc:60-62, 90).  Real bases add nothing (real wavefunctions carry no current). */
+int qb200_compute_current(qb200_plan* plan, int ldc, int nst, const double* c, const double* fac, const double* kpgx,
+                          double* cur);
+
 /* ---- subspace dense linear algebra between two H psi evaluations, on the same FP64
  *      tensor-core GEMM kernels as the projector contractions.  One qb200_la per (spin, k-point) wavefunction block.
  *      Blocks are ComplexMatrix::val as everywhere else (column-major ldc x n, rows >= ngw padding); real bases are read

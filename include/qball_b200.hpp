@@ -5,6 +5,8 @@
 //   qb200::rs_mul_add         <->  SlaterDet::rs_mul_add    (src/qball/SlaterDet.h:115, SlaterDet.cc:971-1040)
 //   qb200::compute_density    <->  SlaterDet::compute_density (src/qball/SlaterDet.h:113, SlaterDet.cc:839-932)
 //   qb200::NonLocalPotential  <->  NonLocalPotential::energy, norm-conserving branch (NonLocalPotential.h:93-96)
+//   qb200::SubspaceLA         <->  the gemm/ger calls of PSD(A)WavefunctionStepper::update (PSDAWavefunctionStepper.cc:65-84,
+//                                  264-277) and SlaterDet::gram (SlaterDet.cc:1043-1143)
 //
 // The reference signals errors on this path with assert / cout + MPI_Abort / exit (FourierTransform.cc:696-700,
 // Messages.h:41-50); the wrappers below do the same: a non-zero status prints qb200_last_error() and aborts.
@@ -104,6 +106,15 @@ inline void compute_density(FourierTransform& ft, int mloc, int nstloc, const st
   check(qb200_compute_density(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), fac.data(), rho), "compute_density");
 }
 
+// CurrentDensity::update_current, body of the (ispin, ikp) loop (CurrentDensity.cc:64-88): cur[idir*N + r] accumulated
+inline void compute_current(FourierTransform& ft, int mloc, int nstloc, const std::complex<double>* c, double weight,
+                            const double* occ_local, double omega, const double* kpgx, double* cur)
+{
+  std::vector<double> fac(nstloc);
+  for (int n = 0; n < nstloc; n++) fac[n] = weight / omega * occ_local[n];
+  check(qb200_compute_current(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), fac.data(), kpgx, cur), "compute_current");
+}
+
 // tail of ChargeDensity::update_density (ChargeDensity.cc:516-551): returns nelectrons_, fills rhog = vft.forward(omega*rho)
 inline double density_finish(FourierTransform& vft, const double* rho, double omega, std::complex<double>* rhog)
 {
@@ -163,6 +174,26 @@ inline void exponential(FourierTransform& ft, NonLocalPotential* nlp, int mloc, 
   check(qb200_exponential(ft.plan(), nlp ? nlp->handle() : nullptr, mloc, nstloc, reinterpret_cast<double*>(c), occ_local, v, kpg2,
                           order, dt1, dt2, reinterpret_cast<double*>(c2)), "qb200_exponential");
 }
+
+// Subspace dense linear algebra of the ground-state steppers, one object per SlaterDet.
+class SubspaceLA {
+ public:
+  SubspaceLA(int ngw, bool real, int device = 0) { check(qb200_la_create(&la_, device, ngw, real ? 1 : 0), "qb200_la_create"); }
+  ~SubspaceLA() { qb200_la_destroy(la_); }
+  SubspaceLA(const SubspaceLA&) = delete;
+  SubspaceLA& operator=(const SubspaceLA&) = delete;
+  // PSDAWavefunctionStepper::update: a = c^H cp (real: 2 c^T cp - row-0 rank-1 term); cp -= c a.
+  // c: mloc x n (all states), cp: mloc x nstloc (this rank's columns of H psi); a (optional): n x nstloc.
+  void residual(int mloc, int n, const std::complex<double>* c, int nstloc, std::complex<double>* cp, double* a = 0)
+  { check(qb200_residual(la_, mloc, n, reinterpret_cast<const double*>(c), nstloc, reinterpret_cast<double*>(cp), a), "qb200_residual"); }
+  // SlaterDet::gram(): c <- c L^-H with c^H c = L L^H.  A singular overlap aborts like the reference's potrf.
+  void gram(int mloc, int n, std::complex<double>* c)
+  { int info = 0; check(qb200_gram(la_, mloc, n, reinterpret_cast<double*>(c), &info), "qb200_gram"); }
+  qb200_la* handle() const { return la_; }
+
+ private:
+  qb200_la* la_ = nullptr;
+};
 
 }  // namespace qb200
 #endif

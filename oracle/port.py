@@ -59,6 +59,7 @@ def lib():
         L.qbo_nl_energy_species.restype = C.c_double
         L.qbo_nl_energy_species.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp,
                                             dp, C.c_double, C.c_int, C.c_int, dp]
+        L.qbo_compute_current.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
         L.qbo_residual.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp]
         L.qbo_gram.restype = C.c_int
         L.qbo_gram.argtypes = [C.c_int, C.c_int, C.c_int, dp]
@@ -151,6 +152,17 @@ class FT:
         fac = np.ascontiguousarray(fac, dtype=np.float64)
         self.L.qbo_compute_density(self.h, ldc, nst, _d(c), _d(fac), _d(rho))
         return rho
+
+
+def compute_current(ft: "FT", c, fac, kpgx, cur=None):
+    """CurrentDensity::update_current (CurrentDensity.cc:52-86): returns cur (3, N), accumulated"""
+    nst, ldc = c.shape
+    if cur is None:
+        cur = np.zeros((3, ft.N))
+    fac = np.ascontiguousarray(fac, dtype=np.float64)
+    kpgx = np.ascontiguousarray(kpgx, dtype=np.float64)
+    lib().qbo_compute_current(ft.h, ft.ngw, ldc, nst, _d(c), _d(fac), _d(kpgx), _d(cur))
+    return cur
 
 
 def kinetic_add(kpg2, c, cp):

@@ -454,6 +454,36 @@ void qbo_compute_density(qbo_ft* ft, int ldc, int nst, const double* c, const do
   free(tmp);
 }
 
+void qbo_compute_current(qbo_ft* ft, int ngw, int ldc, int nst, const double* c, const double* fac, const double* kpgx, double* cur)
+{
+  /* CurrentDensity::update_current (CurrentDensity.cc:52-86) around SlaterDet::compute_density(ft, weight, complex* rho, sd2)
+   * (SlaterDet.cc:935-968): per direction rwf = i*kpgx[idir]*c (:72-76), tmp = sum_n fac_n conj(psi_n(r)) rwf_n(r) over
+   * the states with fac_n > 0, current[idir][r] += -Im tmp (:85-87).  cur: 3*N doubles, accumulated. */
+  const size_t N = (size_t)ft->np0 * ft->np1 * ft->np2;
+  double* t1 = (double*)malloc(sizeof(double) * 2 * N);
+  double* t2 = (double*)malloc(sizeof(double) * 2 * N);
+  double* acc = (double*)malloc(sizeof(double) * 2 * N);
+  double* rw = (double*)malloc(sizeof(double) * 2 * (size_t)ngw);
+  for (int idir = 0; idir < 3; idir++) {
+    const double* k = kpgx + (size_t)idir * ngw;
+    memset(acc, 0, sizeof(double) * 2 * N);
+    for (int n = 0; n < nst; n++) {
+      if (!(fac[n] > 0.0)) continue;
+      const double* cn = c + 2 * (size_t)n * ldc;
+      for (int ig = 0; ig < ngw; ig++) { rw[2*ig] = -k[ig] * cn[2*ig+1]; rw[2*ig+1] = k[ig] * cn[2*ig]; }   /* (0,1)*k*c */
+      qbo_backward(ft, cn, t1);
+      qbo_backward(ft, rw, t2);
+      const double f = fac[n];
+      for (size_t i = 0; i < N; i++) {               /* rho[i] += fac*conj(tmp1[i])*tmp2[i] */
+        acc[2*i] += f * (t1[2*i] * t2[2*i] + t1[2*i+1] * t2[2*i+1]);
+        acc[2*i+1] += f * (t1[2*i] * t2[2*i+1] - t1[2*i+1] * t2[2*i]);
+      }
+    }
+    for (size_t i = 0; i < N; i++) cur[(size_t)idir * N + i] += -acc[2*i+1];
+  }
+  free(t1); free(t2); free(acc); free(rw);
+}
+
 void qbo_kinetic_add(int ngw, int ldc, int nst, const double* kpg2, const double* c, double* cp)
 {
   for (int n = 0; n < nst; n++)                       /* EnergyFunctional.cc:1675-1677 */

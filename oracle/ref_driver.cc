@@ -271,6 +271,23 @@ int main(int argc, char** argv)
     }
     dump(out + ".resid.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
   }
+  // ---- current density: SlaterDet::compute_density(ft, weight, complex* rho, sd2) (SlaterDet.cc:935-968) driven as
+  //      CurrentDensity::update_current does (CurrentDensity.cc:52-86; that class needs a whole Sample, its loop is restated)
+  {
+    vector<double> cur(3*N, 0.0);
+    vector<complex<double> > tmp(N);
+    SlaterDet rsd(sd);
+    for (int idir = 0; idir < 3; idir++) {
+      const double* kx = basis.kpgx_ptr(idir);
+      for (int n = 0; n < sd.nstloc(); n++)
+        for (int ig = 0; ig < ngw; ig++)
+          rsd.c()[ig + mloc*n] = complex<double>(0.0, 1.0) * kx[ig] * sd.c()[ig + mloc*n];   // CurrentDensity.cc:72-76
+      for (size_t i = 0; i < N; i++) tmp[i] = 0.0;
+      sd.compute_density(ft, 1.0, &tmp[0], rsd);
+      for (size_t i = 0; i < N; i++) cur[idir*N + i] += -imag(tmp[i]);                        // CurrentDensity.cc:85-87
+    }
+    dump(out + ".cur.f64", &cur[0], 3*N*sizeof(double));
+  }
   // ---- SlaterDet::gram (SlaterDet.cc:1043-1143) on the input coefficients
   {
     SlaterDet gsd(sd);

@@ -49,6 +49,7 @@ def load():
     L.qb200_fft_forward_pair.argtypes = [vp, dp, dp, dp]
     L.qb200_rs_mul_add.argtypes = [vp, i, i, dp, dp, dp, dp]
     L.qb200_compute_density.argtypes = [vp, i, i, dp, dp, dp]
+    L.qb200_compute_current.argtypes = [vp, i, i, dp, dp, dp, dp]
     L.qb200_density_finish.argtypes = [vp, dp, d, dp, C.POINTER(d)]
     L.qb200_nl_create.argtypes = [C.POINTER(vp), i, i, i, d, dp]
     L.qb200_nl_add_species.argtypes = [vp, i, i, ip, dp, dp, dp]
@@ -76,7 +77,7 @@ def load():
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_density_finish", "qb200_nl_create", "qb200_nl_add_species",
                  "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_set_workspace", "qb200_nl_destroy", "qb200_nl_energy", "qb200_hpsi", "qb200_exponential",
-                 "qb200_la_create", "qb200_la_set_stream", "qb200_la_set_workspace", "qb200_la_destroy", "qb200_residual", "qb200_gram"):
+                 "qb200_compute_current", "qb200_la_create", "qb200_la_set_stream", "qb200_la_set_workspace", "qb200_la_destroy", "qb200_residual", "qb200_gram"):
         getattr(L, name).restype = i
     _lib = L
     return L

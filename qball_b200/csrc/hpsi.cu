@@ -203,3 +203,102 @@ extern "C" int qb200_exponential(qb200_plan* p, qb200_nl* nl, int ldc, int nst, 
   QB_CUDA(cudaStreamSynchronize(p->stream));
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ current density
+// CurrentDensity::update_current (CurrentDensity.cc:52-86) with SlaterDet::compute_density(ft, w, complex* rho, sd2)
+// (SlaterDet.cc:935-968): per direction d, eta = FT^-1[kpgx_d c] (so that rwf = i*kpgx_d*c transforms to i*eta) and
+//   current_d(r) += -Im sum_n fac_n conj(psi_n) (i eta_n) = -sum_n fac_n Re(conj(psi_n) eta_n).
+// The reference transforms psi and rwf to the whole grid for every state and direction (6 FFTs per state) and multiplies
+// there.  Here the product is taken through the polarisation identity
+//   4 s Re(conj(psi) eta) = |psi + s eta|^2 - |psi - s eta|^2 ,        psi +- s eta = FT^-1[(1 +- s kpgx_d) c] ,
+// so each direction is TWO runs of the fused density path (z columns -> plane kernel -> |.|^2 accumulation, nothing
+// written to the grid per state) on the block scaled per plane wave: the same 6 transforms per state, none of them
+// leaving the chip.  s = 1/max|kpgx_d| keeps both weights in [0, 2]; the rounding error is that of two density builds
+// (~1e-16 * rho * max|k|, the size of the reference's own rounding).  Real (Gamma) bases: the current of real
+// wavefunctions vanishes identically (the reference accumulates rounding noise ~1e-17); nothing is added.
+__global__ void __launch_bounds__(1024) k_kmax(const double* __restrict__ kpgx, int ngw, double* __restrict__ kmax)
+{
+  __shared__ double red[1024];
+  const double* k = kpgx + (size_t)blockIdx.x * ngw;
+  double m = 0.0;
+  for (int i = threadIdx.x; i < ngw; i += 1024) m = fmax(m, fabs(k[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) kmax[blockIdx.x] = red[0];
+}
+// out[g, n] = (1 + sign * k[g] / kmax) * c[g, n]; grid (ceil(ngw/256), nst)
+__global__ void __launch_bounds__(256) k_scale_k(const double2* __restrict__ c, size_t ldc, int ngw, const double* __restrict__ k,
+                                                 const double* __restrict__ kmax, double sign, double2* __restrict__ out)
+{
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  if (g >= ngw) return;
+  const double km = *kmax;
+  const double w = 1.0 + sign * (km > 0.0 ? k[g] / km : 0.0);
+  const double2 a = c[(size_t)blockIdx.y * ldc + g];
+  out[(size_t)blockIdx.y * ldc + g] = make_double2(w * a.x, w * a.y);
+}
+// cur += sign * kmax/4 * rho
+__global__ void __launch_bounds__(256) k_cur_acc(double* __restrict__ cur, const double* __restrict__ rho, size_t N,
+                                                 const double* __restrict__ kmax, double sign)
+{
+  const double f = sign * 0.25 * *kmax;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) cur[i] += f * rho[i];
+}
+
+extern "C" int qb200_compute_current(qb200_plan* p, int ldc, int nst, const double* c, const double* fac, const double* kpgx,
+                                     double* cur)
+{
+  if (!p || !c || !fac || !kpgx || !cur || nst < 0 || ldc < p->d.ngw) { set_error("qb200_compute_current: bad argument"); return QB200_EINVAL; }
+  if (nst == 0 || p->d.is_real) return QB200_OK;            // real wavefunctions carry no current
+  QB_CUDA(cudaSetDevice(p->device));
+  const int ngw = p->d.ngw;
+  const size_t N = (size_t)p->d.np0 * p->d.np1 * p->d.np2, blk = 2 * (size_t)ldc * nst;
+  int rc;
+  // work: the scaled block (ex_a); one grid of density + kmax[3] (+ the device copy of cur and kpgx if they are host arrays)
+  const bool chost = !is_device_ptr(c), khost = !is_device_ptr(kpgx), curhost = !is_device_ptr(cur);
+  if ((rc = ensure_buf(&p->ex_a, &p->ex_a_cap, blk))) return rc;
+  const size_t need = N + 4 + (curhost ? 3 * N : 0) + (khost ? 3 * (size_t)ngw : 0);
+  if ((rc = ensure_buf(&p->ex_b, &p->ex_b_cap, need))) return rc;
+  double* tmp = p->ex_b;
+  double* kmax = tmp + N;
+  double* curd = curhost ? tmp + N + 4 : cur;
+  const double* kd = kpgx;
+  if (khost) {
+    double* kbuf = tmp + N + 4 + (curhost ? 3 * N : 0);
+    QB_CUDA(cudaMemcpyAsync(kbuf, kpgx, 3 * (size_t)ngw * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    kd = kbuf;
+  }
+  if (curhost) QB_CUDA(cudaMemcpyAsync(curd, cur, 3 * N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  const double* cd = c;
+  if (chost) {
+    p->res_ptr = nullptr;
+    if ((rc = ensure_buf(&p->st_c, &p->st_c_cap, blk))) return rc;
+    QB_CUDA(cudaMemcpyAsync(p->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    cd = p->st_c;
+  }
+  // rows >= ngw of the scaled block are padding: cleared once so the block is a valid coefficient block
+  if (ldc > ngw) QB_CUDA(cudaMemsetAsync(p->ex_a, 0, blk * sizeof(double), p->stream));
+  k_kmax<<<3, 1024, 0, p->stream>>>(kd, ngw, kmax);
+  p->launches++;
+  const dim3 gs((ngw + 255) / 256, nst);
+  for (int d = 0; d < 3; d++)
+    for (int pass = 0; pass < 2; pass++) {
+      const double sign = pass == 0 ? 1.0 : -1.0;             // |psi + s eta|^2 enters with -, |psi - s eta|^2 with +
+      k_scale_k<<<gs, 256, 0, p->stream>>>((const double2*)cd, ldc, ngw, kd + (size_t)d * ngw, kmax + d, sign, (double2*)p->ex_a);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_scale_k launch", __FILE__, __LINE__);
+      QB_CUDA(cudaMemsetAsync(tmp, 0, N * sizeof(double), p->stream));
+      if ((rc = qb200_compute_density(p, ldc, nst, p->ex_a, fac, tmp))) return rc;
+      k_cur_acc<<<148 * 4, 256, 0, p->stream>>>(curd + (size_t)d * N, tmp, N, kmax + d, -sign);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_cur_acc launch", __FILE__, __LINE__);
+      p->launches += 2;
+    }
+  if (curhost) QB_CUDA(cudaMemcpyAsync(cur, curd, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (curhost || chost) QB_CUDA(cudaStreamSynchronize(p->stream));
+  return QB200_OK;
+}

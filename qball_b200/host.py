@@ -137,6 +137,40 @@ class ChargeDensity:
         return nel.value
 
 
+def compute_current(ft: FourierTransform, c, weight: float, occ, omega: float, kpgx, cur):
+    """the per-(spin, k-point) body of CurrentDensity::update_current (CurrentDensity.cc:64-88):
+    cur[idir] += -Im sum_n weight*occ_n/omega conj(psi_n) FT^-1[i kpgx_idir c_n]; cur: (3, N) doubles, accumulated."""
+    nst, ldc = _block_dims(c)
+    fac = np.ascontiguousarray((weight / omega) * np.asarray(occ, dtype=np.float64))
+    assert fac.shape[0] == nst
+    capi._check(ft._L.qb200_compute_current(ft._h, ldc, nst, capi.ptr(c), capi.ptr(fac), capi.ptr(kpgx), capi.ptr(cur)),
+                "qb200_compute_current")
+    return cur
+
+
+class CurrentDensity:
+    """CurrentDensity::update_current (CurrentDensity.cc:40-102), one spin / one k-point, without the vector-potential
+    term (energy_functional.vp, :96): current[idir][r] and total_current[idir] = volume_element * sum_r current."""
+
+    def __init__(self, ft: FourierTransform, omega: float):
+        self.ft, self.omega = ft, float(omega)
+        self.total_current = [0.0, 0.0, 0.0]
+
+    def update_current(self, c, occ, kpgx, cur, weight: float = 1.0, group=None):
+        from . import parallel as _par
+        if hasattr(cur, "zero_"):
+            cur.zero_()
+        else:
+            cur[...] = 0.0
+        compute_current(self.ft, c, weight, occ, self.omega, kpgx, cur)
+        if hasattr(cur, "is_cuda"):
+            _par.allreduce_density(cur, group)                     # wfcontext()->dsum('r', ...) (:90)
+        dv = self.omega / self.ft.np012()
+        tot = cur.sum(dim=1) if hasattr(cur, "is_cuda") else cur.sum(axis=1)
+        self.total_current = [float(dv * t) for t in tot]
+        return self.total_current
+
+
 class NonLocalPotential:
     """NonLocalPotential(atoms, ctxt, basis, ...) norm-conserving branch (NonLocalPotential.cc:76-258, 1909-2171).
     `species` = list of dict(na, npr, lproj, wt, twnl[npr, ngw], tau[na, 3]) -- the reference's init/update_twnl outputs."""

@@ -40,8 +40,14 @@ int main(int argc, char** argv)
   ft.backward(&c[0], &fr[0]);
   qb200::rs_mul_add(ft, ldc, nst, c.data(), v.data(), cp.data(), kpg2.data());
   qb200::compute_density(ft, ldc, nst, c.data(), 1.0, occ.data(), omega, rho.data());
+  // the stepper's descent direction on (c, cp) and SlaterDet::gram on c, as PSDAWavefunctionStepper / SlaterDet would call
+  std::vector<std::complex<double> > res(cp), cg(c);
+  qb200::SubspaceLA la(ngw, b.real());
+  la.residual(ldc, nst, c.data(), nst, res.data());
+  la.gram(ldc, nst, cg.data());
   FILE* o = fopen(argv[2], "wb");
   fwrite(fr.data(), 16, N, o); fwrite(cp.data(), 16, cp.size(), o); fwrite(rho.data(), 8, N, o);
+  fwrite(res.data(), 16, res.size(), o); fwrite(cg.data(), 16, cg.size(), o);
   fclose(o);
   return 0;
 }

@@ -50,10 +50,14 @@ def test_cpp_mirror_matches_oracle():
         raw = np.fromfile(fout, dtype=np.float64)
         fr = raw[:2 * N].view(np.complex128)
         cp = raw[2 * N:2 * N + 2 * ldc * nst].view(np.complex128).reshape(nst, ldc)
-        rho = raw[2 * N + 2 * ldc * nst:]
+        rho = raw[2 * N + 2 * ldc * nst:3 * N + 2 * ldc * nst]
+        tail = raw[3 * N + 2 * ldc * nst:].view(np.complex128).reshape(2, nst, ldc)
     oft = P.FT(b, *grid)
     assert relerr(fr, oft.backward(c[0, :b["ngw"]])) < TOL
     want = oft.rs_mul_add(c, v, np.zeros_like(c))
     P.kinetic_add(b["kpg2"], c, want)
     assert relerr(cp, want) < TOL
     assert relerr(rho, oft.compute_density(c, occ / b["omega"], np.zeros(N))) < TOL
+    res_ref, _ = P.residual(c, want, b["is_real"])
+    assert relerr(tail[0], res_ref) < TOL
+    assert relerr(tail[1], P.gram(c, b["is_real"])) < TOL
