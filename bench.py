@@ -414,6 +414,47 @@ def main():
                  "what": "qb200_exponential, order 4, Hamiltonian frozen, block resident in HBM (per rank)"}
         del cprop
 
+    # ---------------------------------------------------------------- cuFFT as a timing comparison (north_star): the same
+    # local operator cp += FT[v FT^-1 c] per state on dense grids through torch.fft (cuFFT Z2Z 3-D, batched), coefficients
+    # already scattered to the grid and no gather timed -- i.e. cuFFT is given LESS work than the fused path does
+    cufft = None
+    if rank == 0 and not args.no_e2e:
+        try:
+            nb_c = max(1, min(nst, int((2 << 30) // (16 * N))))          # states per cuFFT batch (<= 2 GiB per buffer)
+            with torch.cuda.stream(stream):
+                xg = torch.zeros((nb_c, np2, np1, np0), dtype=torch.complex128, device=dev)
+                xg.view(torch.float64).normal_()
+                v3 = v.view(1, np2, np1, np0)
+
+                def cufft_step():
+                    y = torch.fft.ifftn(xg, dim=(1, 2, 3), norm="forward")     # backward: unscaled synthesis
+                    y.mul_(v3)
+                    return torch.fft.fftn(y, dim=(1, 2, 3), norm="forward")     # forward: 1/N analysis
+
+                cufft_step(); cufft_step()
+                ta, tb, tc_, td = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+                ta.record(stream)
+                for _ in range(3):
+                    cufft_step()
+                tb.record(stream)
+                cpl = torch.zeros_like(c)
+                H.rs_mul_add(ft, c, v, cpl, kpg2)
+                tc_.record(stream)
+                for _ in range(3):
+                    H.rs_mul_add(ft, c, v, cpl, kpg2)
+                td.record(stream)
+            sync_all()
+            units = nst / 2 if b["is_real"] else nst                    # cuFFT would also pack two real states per FFT
+            us_cufft = ta.elapsed_time(tb) / 3 / nb_c * 1e3
+            us_ours = tc_.elapsed_time(td) / 3 / units * 1e3
+            cufft = {"cufft_us_per_transform_pair": us_cufft, "ours_us_per_unit": us_ours, "speedup": us_cufft / us_ours,
+                     "what": f"torch.fft (cuFFT) ifftn + v multiply + fftn on {nb_c} dense {np0}x{np1}x{np2} complex128 grids per batch "
+                             "(no sphere scatter/gather, no kinetic term) against qb200_rs_mul_add per FFT unit (scatter, pruned "
+                             "transforms, v multiply, gather and kinetic term fused)"}
+            del xg, cpl
+        except Exception as ex:  # noqa: BLE001
+            cufft = {"error": str(ex)[:200]}
+
     # ---------------------------------------------------------------- subspace dense LA on the resident block:
     # the PSD/PSDA descent direction a = c^H Hc, Hc -= c a (with band sharding: after an NCCL all-gather of the state
     # blocks -- the path's one exchange step) and SlaterDet::gram on this rank's block
@@ -519,7 +560,7 @@ def main():
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
-               "kernel_ms_per_step": prof_ms, "tddft": tddft, "subspace_la": subspace, "enl": enl,
+               "kernel_ms_per_step": prof_ms, "tddft": tddft, "subspace_la": subspace, "cufft_comparison": cufft, "enl": enl,
                "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
                          "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
         emit(out)
