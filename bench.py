@@ -365,9 +365,10 @@ def main():
                           "note": "xy stage is bound by the shared-memory and FP64 pipes (ncu: smem wavefronts 65%, FP64 45%, DRAM 7% of peak), not by HBM"}
     nl_flops_step = 0.0     # flops EXECUTED on the FP64 tensor pipe
     nl_zgemm_flops_step = 0.0   # the same contraction counted as the reference's zgemm/dgemm (8 / 2 flops per MAC)
-    m3 = (not b["is_real"]) and os.environ.get("QB200_NL_3M", "1") != "0"
-    for s in species:   # 2 GEMMs; complex MAC = 3 real MACs in the Karatsuba form (nonlocal_3m.cuh), 4 in the plain embedding
-        per_mac = 8.0 if b["is_real"] else (12.0 if m3 else 16.0)
+    nl_mode = nlp.query(14)   # 0 real basis, 1 four-product, 2 three-product (Karatsuba), 3 Gamma-point half sphere (real-function split)
+    m3 = nl_mode == 2
+    for s in species:   # 2 GEMMs; real MACs per complex MAC: 4 plain embedding, 3 Karatsuba (nonlocal_3m.cuh), 2 at Gamma (two real functions)
+        per_mac = {0: 8.0, 1: 16.0, 2: 12.0, 3: 8.0}[nl_mode]
         nl_flops_step += per_mac * s["na"] * s["npr"] * ngw * nst
         nl_zgemm_flops_step += (8.0 if b["is_real"] else 16.0) * s["na"] * s["npr"] * ngw * nst
     nl_ms = prof["k_fnl"][0] + prof["k_back"][0]
@@ -376,7 +377,9 @@ def main():
     if nl_ms > 0:
         ach = nl_flops_step * args.steps / (nl_ms * 1e-3) / 1e12
         roofline_fp64 = {"kernel": ("k_fnl3 + k_back3 (DMMA projector GEMMs, 3-product complex form: 12 flops per complex MAC)" if m3
-                                    else "k_fnl + k_back (DMMA projector GEMMs)"), "bound": "tensor", "achieved": ach, "peak": fp64_peak,
+                                    else "k_split_pm + k_fnl<1> + k_back<0> + k_merge_pm (DMMA projector GEMMs over the half sphere: complex states "
+                                         "at Gamma projected as two real functions, 8 flops per complex MAC; split/merge passes included in the time)"
+                                    if nl_mode == 3 else "k_fnl + k_back (DMMA projector GEMMs)"), "bound": "tensor", "achieved": ach, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic_of("k_fnl3<4>", "k_back3<4>") if m3 else None,
                          "zgemm_equivalent_tflops": nl_zgemm_flops_step * args.steps / (nl_ms * 1e-3) / 1e12,
                          "peak_source": "nominal FP64 37 TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)",

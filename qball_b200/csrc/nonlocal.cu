@@ -367,6 +367,134 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
       }
 }
 
+// ------------------------------------------------------------------------------------------------ Gamma point, complex states
+// Complex wavefunctions at k = 0 (force_complex_wf, the TDDFT configuration; MgO216): the projectors are transforms of
+// REAL functions, anl(-G) = conj(anl(G)), and the sphere holds every G together with -G.  With a = c(G), b = c(-G),
+// anl(G) = A + iB:   conj(anl(G)) a + conj(anl(-G)) b = A (a+b) - iB (a-b), so over the half sphere G > 0 (G = 0 as an
+// unpaired entry, b = 0)
+//   Re fnl = sum_G [A,B].[Re(a+b),  Im(a-b)]          Im fnl = sum_G [A,B].[Im(a+b), -Re(a-b)]
+// -- two REAL dot products with the same real row (A_G, B_G): psi = psi_R + i psi_I is projected as two real functions,
+// 2 real MACs per (projector, state, plane wave) instead of the 3 of the Karatsuba form.  The back-projection is the
+// transposed statement.  k_split_pm / k_merge_pm convert between the sphere and the half-sphere blocks; the GEMMs are the
+// real-basis kernels k_fnl<1> / k_back<0> on 2*nst real "states" and ngw reals (= 2 * half sphere) per state.
+// grid (ceil(hpad/128), na): anl of the half sphere, W[p][2g'..2g'+1] = (A, B), g = ghalf[g']; columns >= nhalf zero
+__global__ void __launch_bounds__(128) k_anl_gen_half(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
+                                                      const int* __restrict__ ghalf, int nhalf, int hpad, double* __restrict__ W, size_t WP)
+{
+  const int gl = blockIdx.x * 128 + threadIdx.x;
+  if (gl >= hpad) return;
+  const int ia = blockIdx.y;
+  const bool ok = gl < nhalf;
+  const int g = ok ? ghalf[gl] : 0;
+  double sn = 0.0, cs = 0.0;
+  if (ok) {
+    if (L.idx != nullptr && S.ph != nullptr) {
+      const double2 e = nl_phase(L, S.ph + (size_t)ia * L.JT, L.idx[g], L.idx[(size_t)ngw + g], L.idx[2 * (size_t)ngw + g]);
+      cs = e.x; sn = e.y;
+    } else {
+      const double arg = -(kpgx[g] * S.tau[3 * ia] + kpgx[(size_t)ngw + g] * S.tau[3 * ia + 1] + kpgx[2 * (size_t)ngw + g] * S.tau[3 * ia + 2]);
+      sincos(arg, &sn, &cs);
+    }
+  }
+  for (int ipr = 0; ipr < S.npr; ipr++) {
+    const size_t p = (size_t)S.poff + (size_t)ia * S.npr + ipr;
+    double2 a = make_double2(0.0, 0.0);
+    if (ok) a = anl_value(S.lproj[ipr], S.twnl[(size_t)ipr * ngw + g], sn, cs);
+    *reinterpret_cast<double2*>(W + p * WP + 2 * gl) = a;
+  }
+}
+// The half-sphere form needs twnl(-G) = (-1)^l twnl(G) (true of the reference's tables, NonLocalPotential.cc:261-1522: real
+// spherical harmonics times a radial function); the ABI accepts any table, so the property is CHECKED on the device
+// whenever the tables change and the general path is used if it does not hold.
+// grid (ceil(nhalf/256), npr): out[0] = max |twnl(-G) - (-1)^l twnl(G)|, out[1] = max |twnl| (non-negative doubles
+// compare like their bit patterns)
+__global__ void __launch_bounds__(256) k_twnl_parity(NlSpecies S, int ngw, const int* __restrict__ ghalf, const int* __restrict__ gminus,
+                                                     int nhalf, unsigned long long* __restrict__ out)
+{
+  const int gl = blockIdx.x * 256 + threadIdx.x;
+  double dev = 0.0, mag = 0.0;
+  if (gl < nhalf) {
+    const int ipr = blockIdx.y;
+    const double tp = S.twnl[(size_t)ipr * ngw + ghalf[gl]], tm = S.twnl[(size_t)ipr * ngw + gminus[gl]];
+    const double sgn = (S.lproj[ipr] & 1) ? -1.0 : 1.0;
+    dev = fabs(tm - sgn * tp);
+    mag = fmax(fabs(tp), fabs(tm));
+    if (gl == 0 && (S.lproj[ipr] & 1)) dev = fabs(tp);        // odd l at G = 0 must vanish
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    mag = fmax(mag, __shfl_xor_sync(0xffffffffu, mag, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(dev));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(mag));
+  }
+}
+// grid (ceil(nhalf/256), nst): U[2n][g'] = (Re(a+b), Im(a-b)), U[2n+1][g'] = (Im(a+b), -Re(a-b)); g' = 0 is G = 0 (b = 0)
+__global__ void __launch_bounds__(256) k_split_pm(const double2* __restrict__ c, size_t ldc, const int* __restrict__ ghalf,
+                                                  const int* __restrict__ gminus, int nhalf, double2* __restrict__ U, size_t ldu)
+{
+  const int gl = blockIdx.x * 256 + threadIdx.x;
+  if (gl >= nhalf) return;
+  const size_t n = blockIdx.y;
+  const double2 a = c[n * ldc + ghalf[gl]];
+  double2 b = make_double2(0.0, 0.0);
+  if (gl > 0) b = c[n * ldc + gminus[gl]];
+  U[(2 * n) * ldu + gl] = make_double2(a.x + b.x, a.y - b.y);
+  U[(2 * n + 1) * ldu + gl] = make_double2(a.y + b.y, b.x - a.x);
+}
+// grid (ceil(nhalf/256), nst): O[2n][g'] = (P, T) = (sum A f_r, sum B f_r), O[2n+1][g'] = (R, Q) = (sum A f_i, sum B f_i)
+//   cp(G) (+)= (P - Q) + i (R + T) ;  cp(-G) (+)= (P + Q) + i (R - T)
+__global__ void __launch_bounds__(256) k_merge_pm(const double2* __restrict__ O, size_t ldu, const int* __restrict__ ghalf,
+                                                  const int* __restrict__ gminus, int nhalf, double2* __restrict__ cp, size_t ldc,
+                                                  int overwrite)
+{
+  const int gl = blockIdx.x * 256 + threadIdx.x;
+  if (gl >= nhalf) return;
+  const size_t n = blockIdx.y;
+  const double2 pt = O[(2 * n) * ldu + gl], rq = O[(2 * n + 1) * ldu + gl];
+  double2* d = cp + n * ldc + ghalf[gl];
+  double2 v = overwrite ? make_double2(0.0, 0.0) : *d;
+  v.x += pt.x - rq.y; v.y += rq.x + pt.y;
+  *d = v;
+  if (gl > 0) {
+    d = cp + n * ldc + gminus[gl];
+    v = overwrite ? make_double2(0.0, 0.0) : *d;
+    v.x += pt.x + rq.y; v.y += rq.x - pt.y;
+    *d = v;
+  }
+}
+// one thread per (n, p): split-K reduce of the 2*nst real columns, E_nl partials, fs[2n][p] = wt/omega Re fnl, fs[2n+1][p] = .. Im
+__global__ void __launch_bounds__(256) k_fnl_finish_half(const double* __restrict__ wtp, int Mtot, const double* __restrict__ part, int Mp,
+                                                         int nst, int ksplit, const double* __restrict__ occ, double omega_inv,
+                                                         double* __restrict__ fs, double* __restrict__ eblk)
+{
+  __shared__ double red[256];
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nst * Mtot;
+  double e = 0.0;
+  if (idx < total) {
+    const int n = (int)(idx / Mtot), p = (int)(idx % Mtot);
+    const int ncols = 2 * nst;
+    const double fac = wtp[p] * omega_inv;
+    double fr = 0.0, fi = 0.0;
+    for (int ks = 0; ks < ksplit; ks++) {
+      fr += part[((size_t)ks * ncols + 2 * n) * Mp + p];
+      fi += part[((size_t)ks * ncols + 2 * n + 1) * Mp + p];
+    }
+    e = fac * occ[n] * (fr * fr + fi * fi);
+    fs[(size_t)(2 * n) * Mp + p] = fac * fr;
+    fs[(size_t)(2 * n + 1) * Mp + p] = fac * fi;
+  }
+  red[threadIdx.x] = e;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) eblk[blockIdx.x] = red[0];
+}
+
 }  // namespace qb200
 
 #include "nonlocal_3m.cuh"
@@ -402,6 +530,15 @@ struct qb200_nl {
   bool use3m;                                  // complex bases: Karatsuba 3-GEMM form (nonlocal_3m.cuh)
   int tile3m;                                  // 0: 512-thread CTAs (one per SM), 1: 256-thread CTAs (two per SM)
   size_t W_WP;                                 // row pitch W was last zero-filled for (3M pad rows must be zero)
+  // Gamma point with complex states (k = 0, force_complex_wf): real-function split over the half sphere
+  bool gamma_half;                             // available: lattice description given, k = 0, every G has its -G
+  bool gamma_off;                              // QB200_NL_GAMMA=0
+  int nhalf;                                   // (ngw + 1) / 2: G = 0 first, then one of every (G, -G) pair
+  const int *ghalf, *gminus;                   // device [nhalf]: index of G and of -G in the basis order
+  double *Wg, *Ug, *Og; size_t Wg_cap, Ug_cap, Og_cap;
+  bool Wg_valid;
+  bool sym_dirty, sym_ok;                      // twnl(-G) = (-1)^l twnl(G) verified for the current tables
+  int last_mode;                               // projector path of the last energy call: 0 real basis, 1 four-product, 2 three-product, 3 Gamma half sphere
 };
 
 static int nl_ensure(double** buf, size_t* cap, size_t elems)
@@ -448,6 +585,9 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   nl->use3m = !is_real;
   if (const char* e = getenv("QB200_NL_3M")) if (e[0] == '0') nl->use3m = false;
   nl->tile3m = 1; nl->W_WP = 0;
+  nl->gamma_half = false; nl->gamma_off = false; nl->nhalf = 0; nl->ghalf = nl->gminus = nullptr;
+  nl->Wg = nl->Ug = nl->Og = nullptr; nl->Wg_cap = nl->Ug_cap = nl->Og_cap = 0; nl->Wg_valid = false; nl->last_mode = 0; nl->sym_dirty = true; nl->sym_ok = false;
+  if (const char* e = getenv("QB200_NL_GAMMA")) if (e[0] == '0') nl->gamma_off = true;
   if (const char* e = getenv("QB200_NL_TILE")) nl->tile3m = atoi(e);
   cudaDeviceProp prop;
   QB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -487,7 +627,7 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   nl->sp.push_back(s);
   nl->ph.push_back(nullptr);
   nl->Mtot += s.M;
-  nl->ph_dirty = true; nl->wtp_dirty = true; nl->W_valid = false;
+  nl->ph_dirty = true; nl->wtp_dirty = true; nl->W_valid = false; nl->Wg_valid = false; nl->sym_dirty = true;
   return QB200_OK;
 }
 
@@ -512,7 +652,33 @@ extern "C" int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* 
   nl->lat.JT = 2 * (jmax[0] + jmax[1] + jmax[2]) + 3;
   for (int i = 0; i < 9; i++) nl->bvec[i] = b[i];
   for (int d = 0; d < 3; d++) nl->kcart[d] = kpoint[0] * b[d] + kpoint[1] * b[3 + d] + kpoint[2] * b[6 + d];
-  nl->ph_dirty = true; nl->W_valid = false;
+  nl->ph_dirty = true; nl->W_valid = false; nl->Wg_valid = false; nl->sym_dirty = true;
+  // Gamma point with complex states: pair every G with -G (possible iff k = 0 and the sphere is symmetric)
+  nl->gamma_half = false;
+  if (!nl->is_real && kpoint[0] == 0.0 && kpoint[1] == 0.0 && kpoint[2] == 0.0 && (ngw & 1)) {
+    const long long J0 = 2ll * jmax[0] + 1, J1 = 2ll * jmax[1] + 1, J2 = 2ll * jmax[2] + 1;
+    if (J0 * J1 * J2 < (1ll << 31)) {
+      std::vector<int> where((size_t)(J0 * J1 * J2), -1);
+      auto key = [&](int h, int k, int l) { return (size_t)(((long long)(h + jmax[0]) * J1 + (k + jmax[1])) * J2 + (l + jmax[2])); };
+      for (int i = 0; i < ngw; i++) where[key(idx[3 * (size_t)i], idx[3 * (size_t)i + 1], idx[3 * (size_t)i + 2])] = i;
+      std::vector<int> gh, gm;
+      gh.reserve(ngw / 2 + 1); gm.reserve(ngw / 2 + 1);
+      bool ok = where[key(0, 0, 0)] >= 0;
+      if (ok) { gh.push_back(where[key(0, 0, 0)]); gm.push_back(where[key(0, 0, 0)]); }
+      for (int i = 0; i < ngw && ok; i++) {
+        const int h = idx[3 * (size_t)i], k = idx[3 * (size_t)i + 1], l = idx[3 * (size_t)i + 2];
+        if (!(h > 0 || (h == 0 && (k > 0 || (k == 0 && l > 0))))) continue;       // one representative per pair
+        const int m = where[key(-h, -k, -l)];
+        if (m < 0) { ok = false; break; }
+        gh.push_back(i); gm.push_back(m);
+      }
+      if (ok && (int)gh.size() == (ngw + 1) / 2) {
+        const int *dh, *dm;
+        if ((rc = nl_upload(nl, gh.data(), gh.size(), &dh)) || (rc = nl_upload(nl, gm.data(), gm.size(), &dm))) return rc;
+        nl->ghalf = dh; nl->gminus = dm; nl->nhalf = (int)gh.size(); nl->gamma_half = true;
+      }
+    }
+  }
   return QB200_OK;
 }
 
@@ -535,6 +701,25 @@ static int nl_refresh_tables(qb200_nl* nl)
     }
     QB_CUDA(cudaMemcpyAsync(nl->wtp, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
     QB_CUDA(cudaStreamSynchronize(nl->stream));
+  }
+  if (nl->sym_dirty) {
+    nl->sym_dirty = false;
+    nl->sym_ok = false;
+    if (nl->gamma_half && !nl->gamma_off) {
+      unsigned long long* acc = nullptr;
+      QB_CUDA(cudaMalloc((void**)&acc, 2 * sizeof(unsigned long long)));
+      QB_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), nl->stream));
+      for (const NlSpecies& S : nl->sp) {
+        if (S.M <= 0) continue;
+        k_twnl_parity<<<dim3((nl->nhalf + 255) / 256, S.npr), 256, 0, nl->stream>>>(S, nl->ngw, nl->ghalf, nl->gminus, nl->nhalf, acc);
+        NL_LAUNCH_CHECK(nl);
+      }
+      double h[2] = { 0.0, 0.0 };
+      QB_CUDA(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, nl->stream));
+      QB_CUDA(cudaStreamSynchronize(nl->stream));
+      cudaFree(acc);
+      nl->sym_ok = h[0] <= 1e-12 * h[1];
+    }
   }
   if (!nl->ph_dirty) return QB200_OK;
   nl->ph_dirty = false;
@@ -561,7 +746,7 @@ extern "C" int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau)
   QB_CUDA(cudaSetDevice(nl->device));
   if (nl->sp[is].na > 0 && nl->sp[is].tau)
     QB_CUDA(cudaMemcpy(const_cast<double*>(nl->sp[is].tau), tau, 3 * (size_t)nl->sp[is].na * sizeof(double), cudaMemcpyHostToDevice));
-  nl->ph_dirty = true; nl->W_valid = false;
+  nl->ph_dirty = true; nl->W_valid = false; nl->Wg_valid = false;
   return QB200_OK;
 }
 
@@ -576,7 +761,7 @@ extern "C" int qb200_nl_set_workspace(qb200_nl* nl, long long bytes)
 {
   if (!nl || bytes < (1ll << 20)) { set_error("qb200_nl_set_workspace: bad argument"); return QB200_EINVAL; }
   nl->anl_budget = bytes;
-  nl->W_valid = false;
+  nl->W_valid = false; nl->Wg_valid = false;
   return QB200_OK;
 }
 
@@ -585,7 +770,7 @@ extern "C" int qb200_nl_destroy(qb200_nl* nl)
   if (!nl) return QB200_OK;
   cudaSetDevice(nl->device);
   for (void* p : nl->owned) cudaFree(p);
-  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W }) if (p) cudaFree(p);
+  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W, nl->Wg, nl->Ug, nl->Og }) if (p) cudaFree(p);
   delete nl;
   return QB200_OK;
 }
@@ -598,6 +783,7 @@ extern "C" long long qb200_nl_query(const qb200_nl* nl, int what)
     case 11: return nl->nchunks_last;
     case 12: return (long long)(nl->W_cap * sizeof(double));
     case 13: return nl->Mtot;
+    case 14: return nl->last_mode;
     default: return -1;
   }
 }
@@ -632,6 +818,76 @@ static void nl_chunking(const qb200_nl* nl, int* gchunk_out, int* nchunks_out)
 int qb200_nl_projectors(const qb200_nl* nl) { return nl->Mtot; }
 int qb200_nl_chunks(const qb200_nl* nl, int) { int g, n; nl_chunking(nl, &g, &n); return nl->Mtot > 0 ? n : 1; }
 
+// Gamma point, complex states: the projector contraction over the half sphere (kernels above).  occ already on the device,
+// enl_dev cleared by the caller, tables refreshed.
+static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c, int compute_hpsi, double* cp, int cont, int overwrite)
+{
+  int rc;
+  nl->last_mode = 3;
+  nl->nchunks_last = 1;
+  const int Mtot = nl->Mtot, nhalf = nl->nhalf, ngw = nl->ngw;
+  const int hpad = (nhalf + 15) / 16 * 16;
+  const size_t WP = 2 * (size_t)hpad, ldu = (size_t)hpad;
+  const int Mp = (Mtot + 1) & ~1;
+  const int nst2 = 2 * nst;
+  if (nl->Wg_cap < (size_t)Mtot * WP) nl->Wg_valid = false;
+  if ((rc = nl_ensure(&nl->Wg, &nl->Wg_cap, (size_t)Mtot * WP))) return rc;
+  if ((rc = nl_ensure(&nl->Ug, &nl->Ug_cap, 2 * ldu * nst2))) return rc;
+  if (compute_hpsi && (rc = nl_ensure(&nl->Og, &nl->Og_cap, 2 * ldu * nst2))) return rc;
+  if (!(nl->Wg_valid && (nl->cache_anl || cont))) {
+    prof_begin(7, nl->stream);
+    for (const NlSpecies& S : nl->sp) {
+      if (S.M <= 0) continue;
+      k_anl_gen_half<<<dim3((hpad + 127) / 128, S.na), 128, 0, nl->stream>>>(S, nl->lat, ngw, nl->kpgx, nl->ghalf, nhalf, hpad, nl->Wg, WP);
+      NL_LAUNCH_CHECK(nl);
+    }
+    prof_end(nl->stream);
+    nl->Wg_valid = true;
+  }
+  // split-K of k_fnl<1>: 128 x 128 tiles, one CTA per SM
+  const int mt = (Mtot + NL_TM - 1) / NL_TM, nt = (nst2 + NL_TN - 1) / NL_TN;
+  int ksplit = 1;
+  {
+    const int maxk = std::max(1, nhalf / 256);
+    double best = -1.0;
+    for (int k = 1; k <= std::min(maxk, 64); k++) {
+      const long ctas = (long)mt * nt * k;
+      const long waves = (ctas + nl->nsm - 1) / nl->nsm;
+      const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;
+      if (eff > best) { best = eff; ksplit = k; }
+    }
+  }
+  if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * nst2 * Mp))) return rc;
+  if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, (size_t)nst2 * Mp))) return rc;
+  if (Mp != Mtot) QB_CUDA(cudaMemsetAsync(nl->fs, 0, (size_t)nst2 * Mp * sizeof(double), nl->stream));
+  const size_t total = (size_t)nst * Mtot;
+  const int nblk = (int)((total + 255) / 256);
+  if ((rc = nl_ensure(&nl->eblk, &nl->eblk_cap, nblk))) return rc;
+  const dim3 gpm((nhalf + 255) / 256, nst);
+  prof_begin(3, nl->stream);
+  k_split_pm<<<gpm, 256, 0, nl->stream>>>((const double2*)c, ldc, nl->ghalf, nl->gminus, nhalf, (double2*)nl->Ug, ldu);
+  NL_LAUNCH_CHECK(nl);
+  int kper = (2 * nhalf + ksplit - 1) / ksplit;
+  kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
+  k_fnl<1><<<dim3(mt, nt, ksplit), NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, kper, (const double2*)nl->Ug, ldu, nst2, nl->part, Mp, Mtot, 0);
+  prof_end(nl->stream);
+  NL_LAUNCH_CHECK(nl);
+  prof_begin(4, nl->stream);
+  k_fnl_finish_half<<<nblk, 256, 0, nl->stream>>>(nl->wtp, Mtot, nl->part, Mp, nst, ksplit, nl->occ_dev, 1.0 / nl->omega, nl->fs, nl->eblk);
+  NL_LAUNCH_CHECK(nl);
+  k_sum_blocks<<<1, 256, 0, nl->stream>>>(nl->eblk, nblk, nl->enl_dev);
+  prof_end(nl->stream);
+  NL_LAUNCH_CHECK(nl);
+  if (!compute_hpsi) return QB200_OK;
+  prof_begin(5, nl->stream);
+  k_back<0><<<dim3((nhalf + 63) / 64, nt), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)nl->Og, ldu, nst2, 1);
+  NL_LAUNCH_CHECK(nl);
+  k_merge_pm<<<gpm, 256, 0, nl->stream>>>((const double2*)nl->Og, ldu, nl->ghalf, nl->gminus, nhalf, (double2*)cp, ldc, overwrite);
+  prof_end(nl->stream);
+  NL_LAUNCH_CHECK(nl);
+  return QB200_OK;
+}
+
 // device pointers; enl accumulated into nl->enl_dev.  flags bit 0 clear: a new call (enl zeroed, anl regenerated unless
 // cached); bit 0 set: a further block of states of the same call (enl keeps accumulating, a whole-sphere anl in W is
 // reused).  Bit 1: cp rows [0, ngw) are known to be zero and are WRITTEN instead of accumulated (H psi: first term).
@@ -645,7 +901,14 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
   const int Mtot = nl->Mtot;
   if (Mtot <= 0) return QB200_OK;
   if ((rc = nl_refresh_tables(nl))) return rc;
+  if (nl->gamma_half && !nl->gamma_off && nl->sym_ok) {
+    // whole half-sphere anl + the two half-sphere blocks must fit the workspace; otherwise the chunked sweeps below
+    const size_t hpad = ((size_t)nl->nhalf + 15) / 16 * 16;
+    const long long need = 8ll * (long long)Mtot * 2 * (long long)hpad;
+    if (need <= nl->anl_budget) return nl_energy_gamma_half(nl, ldc, nst, c, compute_hpsi, cp, cont, overwrite);
+  }
   const int real = nl->is_real;
+  nl->last_mode = real ? 0 : (nl->use3m ? 2 : 1);
   const int ncols = real ? nst : 2 * nst;
   const bool m3 = nl->use3m && !real;              // Karatsuba form (nonlocal_3m.cuh)
   const int RW = real ? Mtot : (m3 ? 24 * ((Mtot + 7) / 8) : 2 * Mtot);          // rows of W

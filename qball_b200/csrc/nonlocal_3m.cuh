@@ -71,9 +71,11 @@ __global__ void __launch_bounds__(128) k_anl_gen3(NlSpecies S, NlLattice L, int 
 template <int NWM, int NWN, int NSTG>
 __global__ void __launch_bounds__(32 * NWM * NWN, 512 / (32 * NWM * NWN))
 k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper, const double2* __restrict__ c, size_t ldc, int nst,
-       double* __restrict__ part, int Mp, int Mtot, int accumulate)
+       double* __restrict__ part, int Mp, int Mtot, int accumulate, int lower_only = 0)
 {
   typedef Fnl3Cfg<NWM, NWN, NSTG> C;
+  // lower_only (qb200_gram: the Hermitian overlap matrix): tiles that lie strictly above the diagonal are never read
+  if (lower_only && (int)blockIdx.x * C::MP + C::MP - 1 < (int)blockIdx.y * C::NT) return;
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / NWN, wn = warp - wm * NWN;
@@ -197,14 +199,15 @@ __global__ void __launch_bounds__(256) k_fnl_finish3(const double* __restrict__ 
 template <int NWM, int NWN, int NSTG>
 __global__ void __launch_bounds__(32 * NWM * NWN, 512 / (32 * NWM * NWN))
 k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount, const double* __restrict__ fs3, int FP3,
-        double2* __restrict__ cp, size_t ldc, int nst, int overwrite)
+        double2* __restrict__ cp, size_t ldc, int nst, int overwrite, int upper_tri = 0)
 {
   typedef Back3Cfg<NWM, NWN, NSTG> C;
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / NWN, wn = warp - wm * NWN;
   const int n0 = blockIdx.x * C::NT, gl0 = blockIdx.y * C::GT;
-  const int nstage = RW3 / N3_BK_KROWS;
+  // upper_tri (qb200_gram: the second operand L^-H is upper triangular): rows m > n0 + NT - 1 contribute nothing
+  const int nstage = upper_tri ? min(RW3 / N3_BK_KROWS, (n0 + C::NT + 7) / 8) : RW3 / N3_BK_KROWS;
   constexpr int ACH = C::GT / 2, ATOT = N3_BK_KROWS * ACH, BTOT = C::NT * 12;   // 16-byte copies per stage
   auto issue = [&](int st) {
     if (st < nstage) {

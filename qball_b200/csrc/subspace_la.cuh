@@ -370,13 +370,14 @@ int la_pack(qb200_la* la, const LaGeom& g, const double* c, size_t ldc, int gbeg
 }
 
 // part (+)= W^H x over one chunk
-int la_fnl(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, const double* x, size_t ldc, int nst, bool accumulate)
+int la_fnl(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, const double* x, size_t ldc, int nst, bool accumulate,
+           int lower_only = 0)
 {
   int kper = ((g.m3 ? 1 : 2) * gcount + g.ksplit - 1) / g.ksplit;
   kper = g.m3 ? (kper + N3_KS - 1) / N3_KS * N3_KS : (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
   dim3 g1(g.mt, g.nt, g.ksplit);
   prof_begin(3, la->stream);
-  if (g.m3) k_fnl3<4, 2, 2><<<g1, 256, Fnl3Cfg<4, 2, 2>::SMEM, la->stream>>>(W, g.WP, gbeg, gcount, kper, (const double2*)x, ldc, nst, la->part, g.Mp, g.nall, accumulate);
+  if (g.m3) k_fnl3<4, 2, 2><<<g1, 256, Fnl3Cfg<4, 2, 2>::SMEM, la->stream>>>(W, g.WP, gbeg, gcount, kper, (const double2*)x, ldc, nst, la->part, g.Mp, g.nall, accumulate, lower_only);
   else k_fnl<1><<<g1, NL_THREADS, FNL_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, kper, (const double2*)x, ldc, nst, la->part, g.Mp, g.nall, accumulate);
   prof_end(la->stream);
   LA_LAUNCH_CHECK(la);
@@ -384,10 +385,11 @@ int la_fnl(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount,
 }
 
 // y[rows of the chunk, :] (+)= W * fs
-int la_back(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, double* y, size_t ldc, int nst, int overwrite)
+int la_back(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount, double* y, size_t ldc, int nst, int overwrite,
+            int upper_tri = 0)
 {
   prof_begin(5, la->stream);
-  if (g.m3) k_back3<4, 2, 3><<<dim3(g.nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
+  if (g.m3) k_back3<4, 2, 3><<<dim3(g.nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite, upper_tri);
   else k_back<0><<<dim3((gcount + 63) / 64, g.nt), NL_THREADS, BK_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
   prof_end(la->stream);
   LA_LAUNCH_CHECK(la);
@@ -452,7 +454,7 @@ static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
   for (int ch = 0; ch < g.nchunks; ch++) {
     const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
     if ((rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
-    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, c, ldc, n, ch > 0))) return rc;
+    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, c, ldc, n, ch > 0, 1))) return rc;   // Hermitian: lower tiles only
   }
   const size_t total = (size_t)n * n;
   const int nblk = (int)((total + 255) / 256);
@@ -492,7 +494,7 @@ static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
     const int ch = g.nchunks - 1 - i;
     const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
     if (i > 0 && (rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
-    if ((rc = la_back(la, g, la->W, gbeg, gcount, c, ldc, n, 1))) return rc;
+    if ((rc = la_back(la, g, la->W, gbeg, gcount, c, ldc, n, 1, 1))) return rc;       // L^-H is upper triangular
   }
   return QB200_OK;
 }

@@ -416,3 +416,60 @@ def test_cuda_exponential_propagator_vs_oracle(host):
     cw1 = _dev(c)
     H.exponential(ft, nlp, cw1, occ, _dev(v), _dev(b["kpg2"]), dt1, order=order)
     assert relerr(cw1.cpu().numpy(), exp1) < TOL
+
+
+@pytest.mark.parametrize("name", ["forced_complex_ortho_al", "mgo216_shape_112cubed"])
+def test_cuda_projectors_gamma_half_sphere_mode(name, monkeypatch):
+    """complex states at k = 0 (force_complex_wf): the projector contraction runs over the half sphere as two real
+    functions per state (query 14 == 3); the Karatsuba path on the same inputs must agree, and so must H psi accumulated
+    into a non-zero block and a second call (cached positions)"""
+    g = load_golden(name)
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    cd = _dev(c)
+    nlp = H.NonLocalPotential(b, g["species"])
+    base = np.ascontiguousarray(c[::-1] * 0.5)                  # cp += ...: start from a non-zero block
+    cp = _dev(base)
+    enl = nlp.energy(cd, occ, True, cp)
+    assert nlp.query(14) == 3
+    assert abs(enl - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"]))
+    compare(g, "hnl", cp.cpu().numpy() - base)
+    cp2 = _dev(base)
+    assert nlp.energy(cd, occ, True, cp2) == enl                # deterministic
+    assert np.array_equal(cp2.cpu().numpy(), cp.cpu().numpy())
+    assert abs(nlp.energy(cd, occ, False) - enl) <= 1e-14 * max(1.0, abs(enl))
+    monkeypatch.setenv("QB200_NL_GAMMA", "0")
+    nlk = H.NonLocalPotential(b, g["species"])
+    cp3 = _dev(base)
+    enl3 = nlk.energy(cd, occ, True, cp3)
+    assert nlk.query(14) == 2
+    assert abs(enl3 - enl) <= 1e-12 * max(1.0, abs(enl))
+    assert relerr(cp3.cpu().numpy(), cp.cpu().numpy()) < 1e-12
+
+
+def test_cuda_projectors_kpoint_keeps_three_product_form():
+    g = load_golden("kpoint_cubic_au_oncv")
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    nlp = H.NonLocalPotential(b, g["species"])
+    nlp.energy(_dev(c), occ, False)
+    assert nlp.query(14) == 2
+
+
+def test_cuda_projectors_asymmetric_tables_use_general_path():
+    """the half-sphere form needs twnl(-G) = (-1)^l twnl(G); a table without that property (legal input of the ABI) must be
+    detected and go through the general complex path, matching the oracle"""
+    cell, ecut = (10, 0, 0, 0, 11, 0, 0, 0, 12), 5.0
+    b = P.make_basis(cell, ecut, (0, 0, 0), True)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, 6, ngw, False, seed=5)
+    occ = R.synth_occ(6, 5)
+    rng = np.random.default_rng(9)
+    species = [dict(na=2, npr=4, lproj=np.array([0, 1, 1, 1], dtype=np.int32), wt=np.array([0.9, -0.4, -0.4, -0.4]),
+                    twnl=rng.standard_normal((4, ngw)) * np.exp(-b["kpg2"] / 4.0)[None, :], tau=rng.uniform(0, 10, (2, 3)))]
+    enl_ref, h_ref = P.nl_energy(b, c, occ, species)
+    nlp = H.NonLocalPotential(b, species)
+    cp = _dev(np.zeros_like(c))
+    enl = nlp.energy(_dev(c), occ, True, cp)
+    assert nlp.query(14) == 2
+    assert abs(enl - enl_ref) <= 1e-10 * max(1.0, abs(enl_ref)) and relerr(cp.cpu().numpy(), h_ref) < TOL
