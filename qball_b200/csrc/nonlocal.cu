@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(256) k_sum_blocks(const double* __restrict__ e
 }
 
 // ------------------------------------------------------------------------------------------------ cp += anl * fs
-// grid (ceil(gcount/64), ceil(nst/128)): 128 output reals (64 plane waves of the chunk x re/im) x 128 states per CTA.
+// grid (ceil(nst/128), ceil(gcount/64)) -- state tiles fastest, so the CTAs that share a W tile run together and W streams
+// from HBM once (r1l ncu: 4.7 GB per launch with the plane-wave tiles fastest, W re-read by every state tile):
+// 128 output reals (64 plane waves of the chunk x re/im) x 128 states per CTA.
 // Reduction over the rows of W (32 per stage), read k-major: A[k = W row][row = 2*(g-gbeg)+{re,im}];
 // B[k][n] = fs[n][k], fs = wt/omega * fnl with row pitch FP = (IS_REAL ? Mp : 2*Mp) doubles, zero beyond RW.
 template <int IS_REAL>
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int gl0 = blockIdx.x * 64, n0 = blockIdx.y * NL_TN;
+  const int gl0 = blockIdx.y * 64, n0 = blockIdx.x * NL_TN;
   const int nstage = (RW + NL_KSTEP - 1) / NL_KSTEP;
   auto issue = [&](int st) {
     if (st < nstage) {
@@ -880,7 +882,7 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
   NL_LAUNCH_CHECK(nl);
   if (!compute_hpsi) return QB200_OK;
   prof_begin(5, nl->stream);
-  k_back<0><<<dim3((nhalf + 63) / 64, nt), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)nl->Og, ldu, nst2, 1);
+  k_back<0><<<dim3(nt, (nhalf + 63) / 64), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)nl->Og, ldu, nst2, 1);
   NL_LAUNCH_CHECK(nl);
   k_merge_pm<<<gpm, 256, 0, nl->stream>>>((const double2*)nl->Og, ldu, nl->ghalf, nl->gminus, nhalf, (double2*)cp, ldc, overwrite);
   prof_end(nl->stream);
@@ -985,7 +987,7 @@ int qb200_nl_energy_dev(qb200_nl* nl, int ldc, int nst, const double* c, const d
     const int ch = nchunks - 1 - i;
     const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
     if (i > 0 && (rc = nl_generate_chunk(nl, gbeg, gcount, gpad, WP))) return rc;   // (i == 0: still in W from sweep 1)
-    dim3 g2((gcount + 63) / 64, nt);
+    dim3 g2(nt, (gcount + 63) / 64);
     prof_begin(5, nl->stream);
     if (m3 && nl->tile3m == 1) k_back3<4, 2, 3><<<dim3(nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);
     else if (m3) k_back3<4, 4, 4><<<dim3(nt, (gcount + 63) / 64), 512, Back3Cfg<4, 4, 4>::SMEM, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, FP, (double2*)cp, ldc, nst, overwrite);

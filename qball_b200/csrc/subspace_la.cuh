@@ -390,7 +390,7 @@ int la_back(qb200_la* la, const LaGeom& g, const double* W, int gbeg, int gcount
 {
   prof_begin(5, la->stream);
   if (g.m3) k_back3<4, 2, 3><<<dim3(g.nt, (gcount + 63) / 64), 256, Back3Cfg<4, 2, 3>::SMEM, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite, upper_tri);
-  else k_back<0><<<dim3((gcount + 63) / 64, g.nt), NL_THREADS, BK_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
+  else k_back<0><<<dim3(g.nt, (gcount + 63) / 64), NL_THREADS, BK_SMEM_BYTES, la->stream>>>(W, g.WP, g.RW, gbeg, gcount, la->fs, g.FP, (double2*)y, ldc, nst, overwrite);
   prof_end(la->stream);
   LA_LAUNCH_CHECK(la);
   return QB200_OK;

@@ -473,3 +473,44 @@ def test_cuda_projectors_asymmetric_tables_use_general_path():
     enl = nlp.energy(_dev(c), occ, True, cp)
     assert nlp.query(14) == 2
     assert abs(enl - enl_ref) <= 1e-10 * max(1.0, abs(enl_ref)) and relerr(cp.cpu().numpy(), h_ref) < TOL
+
+
+def test_cuda_energy_after_fixed_tddft_steps_within_1e8_hartree():
+    """north_star: energies within 1e-8 Ha of the reference after a fixed TDDFT step count.  The terms this path owns --
+    E_kin + E_nl + integral(v rho) = sum_n occ_n <psi_n|H|psi_n>, plus E_nl alone and the electron count -- after 5
+    propagation steps (order-4 exponential, Hamiltonian frozen, real MgO-type projector tables from the fixture so that the
+    Gamma half-sphere projector form is the one exercised) against the same recurrence over the oracle."""
+    g = load_golden("forced_complex_ortho_al")
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), True)
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    grid = (g["np0"], g["np1"], g["np2"])
+    species, ngw = g["species"], b["ngw"]
+    v = 0.3 * v
+    dt, order, nsteps = 0.05, 4, 5
+    oft = P.FT(b, *grid)
+    cref = c.copy()
+    for _ in range(nsteps):
+        acc, op, f = cref.copy(), cref.copy(), 1.0 + 0.0j
+        for n in range(1, order + 1):
+            f *= -1j * dt / n
+            _, op = P.hpsi(b, oft, np.ascontiguousarray(op), v, occ, species)
+            acc += f * op
+        cref = acc
+    enl_ref, h_ref = P.hpsi(b, oft, np.ascontiguousarray(cref), v, occ, species)
+    e_ref = float(np.sum(occ * np.einsum("ng,ng->n", cref[:, :ngw].conj(), h_ref[:, :ngw]).real))
+    rho_ref = oft.compute_density(np.ascontiguousarray(cref), occ / b["omega"], np.zeros(oft.N))
+    ft = H.FourierTransform(b, *grid)
+    nlp = H.NonLocalPotential(b, species)
+    cd, vd, kd = _dev(c), _dev(v), _dev(b["kpg2"])
+    for _ in range(nsteps):
+        H.exponential(ft, nlp, cd, occ, vd, kd, dt, order=order)
+    assert nlp.query(14) == 3
+    out = torch.zeros_like(cd)
+    enl = H.hpsi(ft, nlp, cd, occ, vd, kd, out)
+    cg, hg = cd.cpu().numpy(), out.cpu().numpy()
+    e = float(np.sum(occ * np.einsum("ng,ng->n", cg[:, :ngw].conj(), hg[:, :ngw]).real))
+    rho = torch.zeros(oft.N, dtype=torch.float64, device="cuda")
+    H.compute_density(ft, cd, 1.0, occ, b["omega"], rho)
+    nel, nel_ref = float(rho.sum()) * b["omega"] / oft.N, float(rho_ref.sum()) * b["omega"] / oft.N
+    assert abs(e - e_ref) < 1e-8 and abs(enl - enl_ref) < 1e-8 and abs(nel - nel_ref) < 1e-8, (e - e_ref, enl - enl_ref, nel - nel_ref)
+    assert relerr(cg, cref) < TOL
