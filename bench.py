@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nst", type=int, default=0, help="states per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workspace-mb", type=int, default=0, help="qb200_plan_set_workspace (0: the library default)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -264,6 +265,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ft = H.FourierTransform(b, np0, np1, np2, device=local_rank, stream=stream)
     nlp = H.NonLocalPotential(b, species, device=local_rank, stream=stream)
+    if args.workspace_mb:
+        ft.set_workspace(args.workspace_mb << 20)
     with torch.cuda.stream(stream):
         c = torch.from_numpy(c_host).to(dev)
         v = torch.from_numpy(v_host).to(dev)

@@ -49,7 +49,8 @@ int qb200_plan_create(qb200_plan** plan, int device, int np0, int np1, int np2, 
 int qb200_plan_destroy(qb200_plan* plan);
 /* work on this CUDA stream (cudaStream_t as void*); default is the legacy default stream */
 int qb200_plan_set_stream(qb200_plan* plan, void* cuda_stream);
-/* bytes of device scratch for the column-form intermediate (default 256 MiB); bounds the number of states per batch */
+/* bytes of device scratch for the column-form intermediate (default 4 GiB when a plane fits in shared memory, 8 GiB
+ * otherwise; allocated for the states actually batched); bounds the number of states per batch */
 int qb200_plan_set_workspace(qb200_plan* plan, long long bytes);
 /* Host coefficient blocks and residency.  When `c` is a HOST pointer, qb200_hpsi and qb200_compute_density upload it
  * in blocks of states on a copy stream while earlier blocks are being computed (and qb200_hpsi downloads finished

@@ -579,7 +579,10 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     }
     if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
   }
-  p->ws_bytes = p->fused ? (256ll << 20) : (8ll << 30);
+  // fused path: batches of up to ~1100 MgO216 states -- whole blocks go through in one batch, so the persistent CTAs of
+  // the plane and z-column kernels pay their wave quantisation and prologue once (r1l sweep: 256 MiB 27.66 ms/step, 1 GiB 26.68,
+  // 4 GiB 26.33); the scratch is allocated for the units actually batched, never for the whole budget
+  p->ws_bytes = p->fused ? (4ll << 30) : (8ll << 30);
   if (const char* e = getenv("QB200_WORKSPACE_BYTES")) p->ws_bytes = atoll(e);
   configure_batch(p);
   *out = p;
