@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict_
     __syncthreads();                   // stage st has landed for everybody; everybody is done with stage st-1's buffer
     issue(st + NL_NSTAGE - 1);
     const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_RK;
-    warp_mma_stage<false>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
+    // the last row tile is mostly padding when RW is not a multiple of 128 (MgO216: 540 rows, 28 of 128 in the fifth
+    // tile): warps whose 32-row slab holds no row skip the tensor work, the others then own the pipe (warp-uniform test)
+    if (r0 + wm * 32 < RW && n0 + wn * 32 < nst) warp_mma_stage<false>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
   }
   const int ncols = IS_REAL ? nst : 2 * nst;
   const int r = lane >> 2, cq = lane & 3;

@@ -120,6 +120,7 @@ k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper,
     const double* As = nl_smem + (st % NSTG) * C::STAGE;
     const double* a0 = As + ((wm * 2) * 24 + r) * N3_APITCH + kq;
     const double* b0 = As + C::ASTAGE + (wn * 32 + r) * N3_BPITCH + 2 * kq;
+    if (p0 + wm * 16 >= Mtot || n0 + wn * 32 >= nst) continue;       // warp tile entirely in the padding (warp-uniform)
 #pragma unroll
     for (int k4 = 0; k4 < N3_KS / 4; k4++) {
       double a[3][2];
