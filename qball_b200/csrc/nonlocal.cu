@@ -308,10 +308,15 @@ __global__ void __launch_bounds__(256) k_sum_blocks(const double* __restrict__ e
 // 128 output reals (64 plane waves of the chunk x re/im) x 128 states per CTA.
 // Reduction over the rows of W (32 per stage), read k-major: A[k = W row][row = 2*(g-gbeg)+{re,im}];
 // B[k][n] = fs[n][k], fs = wt/omega * fnl with row pitch FP = (IS_REAL ? Mp : 2*Mp) doubles, zero beyond RW.
+// IS_REAL == 2: the half-sphere form of complex states at Gamma (see k_split_pm): columns (2n, 2n+1) carry (f_r, f_i) of state
+// n, rows (2g', 2g'+1) the (A, B) parts; the epilogue forms cp(G) (+)= (P - Q) + i (R + T), cp(-G) (+)= (P + Q) + i (R - T)
+// with P = sum A f_r, T = sum B f_r, R = sum A f_i, Q = sum B f_i directly from the accumulators (one lane exchange
+// between the A-row and the B-row of a plane wave) and stores them at ghalf[g'] / gminus[g'] of the sphere-ordered block.
 template <int IS_REAL>
 __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
                                                           const double* __restrict__ fs, int FP, double2* __restrict__ cp,
-                                                          size_t ldc, int nst, int overwrite)
+                                                          size_t ldc, int nst, int overwrite, const int* __restrict__ ghalf = nullptr,
+                                                          const int* __restrict__ gminus = nullptr)
 {
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,6 +356,29 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
     warp_mma_stage<true>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
   }
   const int r = lane >> 2, cq = lane & 3;
+  if (IS_REAL == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int row = wm * 32 + i * 8 + r;                   // even: A-row (P, R), odd: B-row (T, Q) of plane wave gl
+      const int gl = gl0 + (row >> 1);
+      const bool odd = row & 1;
+      const int gdst = gl < gcount ? (odd ? gminus[gl] : ghalf[gl]) : 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double mine0 = acc[i][j][0], mine1 = acc[i][j][1];
+        const double oth0 = __shfl_xor_sync(0xffffffffu, mine0, 4), oth1 = __shfl_xor_sync(0xffffffffu, mine1, 4);
+        const double Pv = odd ? oth0 : mine0, Rv = odd ? oth1 : mine1, Tv = odd ? mine0 : oth0, Qv = odd ? mine1 : oth1;
+        const int n2 = n0 + wn * 32 + j * 8 + 2 * cq;          // column pair (2n, 2n+1) of state n = n2 / 2
+        if (gl < gcount && n2 < nst && !(odd && gl == 0)) {   // G = 0 (gl == 0) has no partner
+          double2* dst = cp + (size_t)(n2 >> 1) * ldc + gdst;
+          double2 v = overwrite ? make_double2(0.0, 0.0) : *dst;
+          if (odd) { v.x += Pv + Qv; v.y += Rv - Tv; } else { v.x += Pv - Qv; v.y += Rv + Tv; }
+          *dst = v;
+        }
+      }
+    }
+    return;
+  }
   double* cpd = reinterpret_cast<double*>(cp);
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -363,7 +391,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
         const int g = gbeg + gl;
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
         double v = acc[i][j][e];
-        if (IS_REAL && g == 0 && (row & 1) == 0) v *= 2.0;    // W holds half of Re anl at G=0 (k_anl_gen)
+        if (IS_REAL == 1 && g == 0 && (row & 1) == 0) v *= 2.0;    // W holds half of Re anl at G=0 (k_anl_gen)
         if (gl < gcount && n < nst) {
           double* dst = cpd + 2 * ((size_t)n * ldc + g) + (row & 1);
           *dst = overwrite ? v : *dst + v;
@@ -379,8 +407,8 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
 //   Re fnl = sum_G [A,B].[Re(a+b),  Im(a-b)]          Im fnl = sum_G [A,B].[Im(a+b), -Re(a-b)]
 // -- two REAL dot products with the same real row (A_G, B_G): psi = psi_R + i psi_I is projected as two real functions,
 // 2 real MACs per (projector, state, plane wave) instead of the 3 of the Karatsuba form.  The back-projection is the
-// transposed statement.  k_split_pm / k_merge_pm convert between the sphere and the half-sphere blocks; the GEMMs are the
-// real-basis kernels k_fnl<1> / k_back<0> on 2*nst real "states" and ngw reals (= 2 * half sphere) per state.
+// transposed statement.  k_split_pm builds the half-sphere block, the epilogue of k_back<2> scatters back to the sphere; the GEMMs are the
+// real-basis kernels k_fnl<1> / k_back on 2*nst real "states" and ngw reals (= 2 * half sphere) per state.
 // grid (ceil(hpad/128), na): anl of the half sphere, W[p][2g'..2g'+1] = (A, B), g = ghalf[g']; columns >= nhalf zero
 __global__ void __launch_bounds__(128) k_anl_gen_half(NlSpecies S, NlLattice L, int ngw, const double* __restrict__ kpgx,
                                                       const int* __restrict__ ghalf, int nhalf, int hpad, double* __restrict__ W, size_t WP)
@@ -446,27 +474,6 @@ __global__ void __launch_bounds__(256) k_split_pm(const double2* __restrict__ c,
   if (gl > 0) b = c[n * ldc + gminus[gl]];
   U[(2 * n) * ldu + gl] = make_double2(a.x + b.x, a.y - b.y);
   U[(2 * n + 1) * ldu + gl] = make_double2(a.y + b.y, b.x - a.x);
-}
-// grid (ceil(nhalf/256), nst): O[2n][g'] = (P, T) = (sum A f_r, sum B f_r), O[2n+1][g'] = (R, Q) = (sum A f_i, sum B f_i)
-//   cp(G) (+)= (P - Q) + i (R + T) ;  cp(-G) (+)= (P + Q) + i (R - T)
-__global__ void __launch_bounds__(256) k_merge_pm(const double2* __restrict__ O, size_t ldu, const int* __restrict__ ghalf,
-                                                  const int* __restrict__ gminus, int nhalf, double2* __restrict__ cp, size_t ldc,
-                                                  int overwrite)
-{
-  const int gl = blockIdx.x * 256 + threadIdx.x;
-  if (gl >= nhalf) return;
-  const size_t n = blockIdx.y;
-  const double2 pt = O[(2 * n) * ldu + gl], rq = O[(2 * n + 1) * ldu + gl];
-  double2* d = cp + n * ldc + ghalf[gl];
-  double2 v = overwrite ? make_double2(0.0, 0.0) : *d;
-  v.x += pt.x - rq.y; v.y += rq.x + pt.y;
-  *d = v;
-  if (gl > 0) {
-    d = cp + n * ldc + gminus[gl];
-    v = overwrite ? make_double2(0.0, 0.0) : *d;
-    v.x += pt.x + rq.y; v.y += rq.x - pt.y;
-    *d = v;
-  }
 }
 // one thread per (n, p): split-K reduce of the 2*nst real columns, E_nl partials, fs[2n][p] = wt/omega Re fnl, fs[2n+1][p] = .. Im
 __global__ void __launch_bounds__(256) k_fnl_finish_half(const double* __restrict__ wtp, int Mtot, const double* __restrict__ part, int Mp,
@@ -539,7 +546,7 @@ struct qb200_nl {
   bool gamma_off;                              // QB200_NL_GAMMA=0
   int nhalf;                                   // (ngw + 1) / 2: G = 0 first, then one of every (G, -G) pair
   const int *ghalf, *gminus;                   // device [nhalf]: index of G and of -G in the basis order
-  double *Wg, *Ug, *Og; size_t Wg_cap, Ug_cap, Og_cap;
+  double *Wg, *Ug; size_t Wg_cap, Ug_cap;
   bool Wg_valid;
   bool sym_dirty, sym_ok;                      // twnl(-G) = (-1)^l twnl(G) verified for the current tables
   int last_mode;                               // projector path of the last energy call: 0 real basis, 1 four-product, 2 three-product, 3 Gamma half sphere
@@ -590,7 +597,7 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   if (const char* e = getenv("QB200_NL_3M")) if (e[0] == '0') nl->use3m = false;
   nl->tile3m = 1; nl->W_WP = 0;
   nl->gamma_half = false; nl->gamma_off = false; nl->nhalf = 0; nl->ghalf = nl->gminus = nullptr;
-  nl->Wg = nl->Ug = nl->Og = nullptr; nl->Wg_cap = nl->Ug_cap = nl->Og_cap = 0; nl->Wg_valid = false; nl->last_mode = 0; nl->sym_dirty = true; nl->sym_ok = false;
+  nl->Wg = nl->Ug = nullptr; nl->Wg_cap = nl->Ug_cap = 0; nl->Wg_valid = false; nl->last_mode = 0; nl->sym_dirty = true; nl->sym_ok = false;
   if (const char* e = getenv("QB200_NL_GAMMA")) if (e[0] == '0') nl->gamma_off = true;
   if (const char* e = getenv("QB200_NL_TILE")) nl->tile3m = atoi(e);
   cudaDeviceProp prop;
@@ -605,6 +612,7 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  QB_CUDA(cudaFuncSetAttribute(k_back<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
   QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 4, 3>::SMEM));
   QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 2, 2>::SMEM));
   QB_CUDA(cudaFuncSetAttribute(k_back3<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 4, 4>::SMEM));
@@ -774,7 +782,7 @@ extern "C" int qb200_nl_destroy(qb200_nl* nl)
   if (!nl) return QB200_OK;
   cudaSetDevice(nl->device);
   for (void* p : nl->owned) cudaFree(p);
-  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W, nl->Wg, nl->Ug, nl->Og }) if (p) cudaFree(p);
+  for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W, nl->Wg, nl->Ug }) if (p) cudaFree(p);
   delete nl;
   return QB200_OK;
 }
@@ -837,7 +845,6 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
   if (nl->Wg_cap < (size_t)Mtot * WP) nl->Wg_valid = false;
   if ((rc = nl_ensure(&nl->Wg, &nl->Wg_cap, (size_t)Mtot * WP))) return rc;
   if ((rc = nl_ensure(&nl->Ug, &nl->Ug_cap, 2 * ldu * nst2))) return rc;
-  if (compute_hpsi && (rc = nl_ensure(&nl->Og, &nl->Og_cap, 2 * ldu * nst2))) return rc;
   if (!(nl->Wg_valid && (nl->cache_anl || cont))) {
     prof_begin(7, nl->stream);
     for (const NlSpecies& S : nl->sp) {
@@ -884,9 +891,8 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
   NL_LAUNCH_CHECK(nl);
   if (!compute_hpsi) return QB200_OK;
   prof_begin(5, nl->stream);
-  k_back<0><<<dim3(nt, (nhalf + 63) / 64), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)nl->Og, ldu, nst2, 1);
-  NL_LAUNCH_CHECK(nl);
-  k_merge_pm<<<gpm, 256, 0, nl->stream>>>((const double2*)nl->Og, ldu, nl->ghalf, nl->gminus, nhalf, (double2*)cp, ldc, overwrite);
+  k_back<2><<<dim3(nt, (nhalf + 63) / 64), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)cp, ldc, nst2, overwrite,
+                                                                                    nl->ghalf, nl->gminus);
   prof_end(nl->stream);
   NL_LAUNCH_CHECK(nl);
   return QB200_OK;
