@@ -109,7 +109,11 @@ int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const 
  *   kpoint = Basis::kpoint(), in units of b0,b1,b2                                             (Basis.h:51)
  * With k+G = kpoint + h b0 + k b1 + l b2 the structure-factor phase exp(-i (k+G).tau) (comp_eigr / comp_anl,
  * NonLocalPotential.cc:1959-2036) factorises per direction; the kernels then read three small per-atom tables instead
- * of evaluating one FP64 sincos per (atom, G) and tile.  Same results to rounding (~1e-13 absolute in the phase). */
+ * of evaluating one FP64 sincos per (atom, G) and tile.  Same results to rounding (~1e-13 absolute in the phase).
+ * With this description, a COMPLEX basis at kpoint = 0 (force_complex_wf, the TDDFT configuration) whose tables satisfy
+ * twnl(-G) = (-1)^l twnl(G) (every table NonLocalPotential::update_twnl produces; verified on the device) is contracted
+ * over the half sphere: psi = psi_R + i psi_I as two real functions, a third fewer flops than the general complex path
+ * (qb200_nl_query(nl, 14) == 3 after an energy call; QB200_NL_GAMMA=0 disables it). */
 int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* b, const double* kpoint);
 /* atoms moved: new positions for species is (AtomSet::get_positions order) */
 int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau);
@@ -125,7 +129,9 @@ int qb200_nl_destroy(qb200_nl* nl);
 int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, int compute_hpsi, double* cp,
                     double* enl);
 long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call,
-                                                           12: bytes of the anl block, 13: projectors in total */
+                                                           12: bytes of the anl block, 13: projectors in total,
+                                                           14: form of the last call: 0 real basis, 1 complex 4-product,
+                                                               2 complex 3-product, 3 Gamma-point half sphere */
 
 /* ---- the whole H psi column block in the reference's order (EnergyFunctional.cc:1142-1153, 1500, 1675-1695):
  *      hpsi = 0 ; hpsi += V_nl psi ; hpsi += 0.5|k+G|^2 psi ; hpsi += FT[v FT^-1 psi].  nl may be NULL (no projectors).

@@ -142,6 +142,10 @@ class NonLocalPotential {
   void add_species(int na, int npr, const int* lproj, const double* wt, const double* twnl, const double* tau)
   { check(qb200_nl_add_species(nl_, na, npr, lproj, wt, twnl, tau), "qb200_nl_add_species"); }
   void set_positions(int is, const double* tau) { check(qb200_nl_set_positions(nl_, is, tau), "qb200_nl_set_positions"); }
+  // optional: idx = basis.idx_ptr() (3*ngw), b = { cell.b(0), cell.b(1), cell.b(2) } as 9 doubles, kpoint = basis.kpoint()
+  // in crystal units -> separable phase tables; complex states at k = 0 are then contracted over the half sphere
+  void set_lattice(const int* idx, const double* b, const double* kpoint)
+  { check(qb200_nl_set_lattice(nl_, idx, b, kpoint), "qb200_nl_set_lattice"); }
   // double energy(SlaterDet& sd, bool compute_hpsi, SlaterDet& dsd, ...) without forces/stress
   double energy(int mloc, int nstloc, const std::complex<double>* c, const double* occ_local, bool compute_hpsi,
                 std::complex<double>* cp)
