@@ -75,3 +75,37 @@ def test_cuda_current_vs_oracle_and_total(kpoint, fc, nst, ldpad):
     for d in range(3):
         assert abs(tot[d] - ref[d].sum() * b["omega"] / oft.N) < 1e-10 * max(1.0, abs(want[d]))
         assert abs(tot[d] - want[d]) < 1e-9 * max(1.0, abs(want[d]))
+
+
+@pytest.mark.gpu
+def test_cuda_current_properties_mgo216_full_size():
+    """BASELINE-size shape (MgO216: 112^3, ngw 73447): the integral of the current density equals -sum_n f_n <psi_n|k+G|psi_n>
+    (exact identity of the definition), j is odd under complex conjugation of the coefficients' mirror image
+    c(G) -> conj(c(-G)) (time reversal), which for a state with c(-G) = conj(c(G)) (a real function) means j = 0."""
+    import torch
+    from qball_b200 import host as H
+    cell, ecut, nst = (23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), 25.0, 5
+    b = P.make_basis(cell, ecut, (0, 0, 0), True)
+    grid = P.density_grid(cell, ecut)
+    N = grid[0] * grid[1] * grid[2]
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw, False, seed=51)
+    # make the last state a REAL function: c(-G) = conj(c(G))
+    idx = b["idx"]
+    where = {tuple(v): i for i, v in enumerate(idx.tolist())}
+    minus = np.array([where[(-h, -k, -l)] for h, k, l in idx.tolist()])
+    c[-1] = 0.5 * (c[-1] + np.conj(c[-1][minus]))
+    occ = np.array([2.0, 1.0, 0.0, 0.5, 2.0])
+    ft = H.FourierTransform(b, *grid)
+    cur = torch.zeros((3, N), dtype=torch.float64, device="cuda")
+    kd = torch.from_numpy(b["kpgx"]).cuda()
+    H.compute_current(ft, torch.from_numpy(c).cuda(), 1.0, occ, b["omega"], kd, cur)
+    tot = cur.sum(dim=1).cpu().numpy() * b["omega"] / N
+    want = np.array([-float(np.sum(occ[:, None] * np.abs(c) ** 2 * b["kpgx"][d][None, :])) for d in range(3)])
+    scale = float(np.sum(occ[:, None] * np.abs(c) ** 2 * np.sqrt(2 * b["kpg2"])[None, :]))
+    assert np.abs(tot - want).max() < 1e-10 * scale
+    # the real state alone carries no current
+    only = np.zeros(nst); only[-1] = 2.0
+    cur1 = torch.zeros((3, N), dtype=torch.float64, device="cuda")
+    H.compute_current(ft, torch.from_numpy(c).cuda(), 1.0, only, b["omega"], kd, cur1)
+    assert float(cur1.abs().max()) < 1e-10 * float(cur.abs().max())

@@ -145,3 +145,37 @@ def test_cuda_gram_singular_overlap_fails_loudly():
     with pytest.raises(capi.QB200Error):
         L.gram(cd)
     assert np.array_equal(cd.cpu().numpy(), c), "a failed factorisation must leave the block unchanged"
+
+
+@pytest.mark.gpu
+def test_cuda_subspace_la_properties_mgo216_full_size():
+    """BASELINE-size block (MgO216: ngw 73447, 768 complex states, 0.9 GB): size-independent properties of the subspace
+    algebra -- gram leaves orthonormal columns (and is idempotent on them), a = c^H Hc is returned as computed, and the
+    descent direction is orthogonal to the subspace: c^H (Hc - c a) = 0 for orthonormal c."""
+    import torch
+    from qball_b200 import host as H
+    cell, ecut, nst = (23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), 25.0, 768
+    b = P.make_basis(cell, ecut, (0, 0, 0), True)
+    assert b["ngw"] == 73447
+    c = torch.from_numpy(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, seed=41)).cuda()
+    hc = torch.from_numpy(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, seed=42)).cuda()
+    L = H.SubspaceLA(b)
+    L.gram(c)
+    eye = torch.eye(nst, dtype=torch.complex128, device="cuda")
+    s = c.conj() @ c.T                                       # (nst, ldc) blocks: s[m, n] = <c_m | c_n>
+    assert float((s - eye).abs().max()) < 1e-12
+    c2 = c.clone()
+    L.gram(c2)
+    assert float((c2 - c).abs().max()) < 1e-12 * float(c.abs().max())
+    a_want = (c.conj() @ hc.T).T.contiguous()                # row n = column n of a: a[m, n] = <c_m | hc_n>
+    a = torch.zeros((nst, nst), dtype=torch.complex128, device="cuda")
+    res = hc.clone()
+    L.residual(c, res, a)
+    scale = float(a_want.abs().max())
+    assert float((a - a_want).abs().max()) < 1e-11 * scale
+    assert float((c.conj() @ res.T).abs().max()) < 1e-11 * scale
+    # band-sharded form: the columns of a middle shard equal the same columns of the full result
+    lo, hi = 200, 331
+    part = hc[lo:hi].clone()
+    L.residual(c, part)
+    assert float((part - res[lo:hi]).abs().max()) < 1e-12 * float(res.abs().max())
