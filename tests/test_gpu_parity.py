@@ -514,3 +514,39 @@ def test_cuda_energy_after_fixed_tddft_steps_within_1e8_hartree():
     nel, nel_ref = float(rho.sum()) * b["omega"] / oft.N, float(rho_ref.sum()) * b["omega"] / oft.N
     assert abs(e - e_ref) < 1e-8 and abs(enl - enl_ref) < 1e-8 and abs(nel - nel_ref) < 1e-8, (e - e_ref, enl - enl_ref, nel - nel_ref)
     assert relerr(cg, cref) < TOL
+
+
+def test_cuda_gamma_half_sphere_host_blocks_sliced():
+    """the half-sphere projector form under the host-pointer pipeline: 259 complex states at k = 0 go through in slices of 64
+    (the anl matrix of the first slice is reused by the later ones); tables with the parity of real projectors
+    (l = 0: even in G, l = 1: odd); against the device-pointer path (one block) and the oracle"""
+    cell, ecut, nst = (11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0, 259
+    b = P.make_basis(cell, ecut, (0, 0, 0), True)
+    grid = P.density_grid(cell, ecut)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 2, False, seed=61)
+    v = R.synth_potential(*grid, seed=62)
+    occ = R.synth_occ(nst, nst - 7)
+    env = np.exp(-b["kpg2"] / 4.0)
+    twnl = np.stack([env, env * b["kpgx"][0], env * b["kpgx"][1], env * b["kpgx"][2]])
+    rng = np.random.default_rng(63)
+    species = [dict(na=5, npr=4, lproj=np.array([0, 1, 1, 1], dtype=np.int32), wt=np.array([1.3, -0.6, -0.6, -0.6]),
+                    twnl=np.ascontiguousarray(twnl), tau=rng.uniform(0, 11, (5, 3)))]
+    ft = H.FourierTransform(b, *grid)
+    nlp = H.NonLocalPotential(b, species)
+    out_d = _dev(np.zeros_like(c))
+    enl_d = H.hpsi(ft, nlp, _dev(c), occ, _dev(v), _dev(b["kpg2"]), out_d)
+    assert nlp.query(14) == 3
+    hc = torch.from_numpy(c.copy()).pin_memory()
+    hout = torch.zeros_like(hc).pin_memory()
+    enl_h = H.hpsi(ft, nlp, hc, occ, v, b["kpg2"], hout)
+    assert nlp.query(14) == 3
+    assert abs(enl_h - enl_d) <= 1e-12 * max(1.0, abs(enl_d))
+    assert relerr(hout.numpy(), out_d.cpu().numpy()) < 1e-12
+    assert np.all(hout.numpy()[:, ngw:] == 0)
+    sel = [0, 1, 130, nst - 2, nst - 1]
+    oft = P.FT(b, *grid)
+    enl_ref, _ = P.nl_energy(b, c, occ, species, compute_hpsi=False)
+    _, h_ref = P.hpsi(b, oft, np.ascontiguousarray(c[sel]), v, occ[sel], species)
+    assert abs(enl_h - enl_ref) <= 1e-10 * max(1.0, abs(enl_ref))
+    assert relerr(hout.numpy()[sel][:, :ngw], h_ref[:, :ngw]) < TOL
