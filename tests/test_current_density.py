@@ -109,3 +109,23 @@ def test_cuda_current_properties_mgo216_full_size():
     cur1 = torch.zeros((3, N), dtype=torch.float64, device="cuda")
     H.compute_current(ft, torch.from_numpy(c).cuda(), 1.0, only, b["omega"], kd, cur1)
     assert float(cur1.abs().max()) < 1e-10 * float(cur.abs().max())
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref/ref_driver not built (needs /root/reference)")
+@pytest.mark.parametrize("cell,ecut,kpoint,fc,nst", [
+    ((10, 0, 0, 0, 10, 0, 0, 0, 10), 6.0, (0, 0, 0), True, 4),
+    ((8, 0, 0, 2.0, 9, 0, -1.0, 0.5, 12), 5.0, (0.5, 0.5, 0.5), False, 3),
+    ((5.4, 5.4, 0, 0, 5.4, 5.4, 5.4, 0, 5.4), 8.0, (0.125, 0.25, 0.375), False, 2),
+])
+def test_oracle_current_vs_live_reference(cell, ecut, kpoint, fc, nst):
+    """the oracle against the reference's pair-form compute_density run live (shapes the fixtures do not cover:
+    triclinic and fcc cells, general k-points), plus the integral identity of the definition"""
+    r = R.run_reference(R.Case(cell=cell, ecut=ecut, kpoint=kpoint, force_complex=fc, nst=nst), seed=9, nocc=nst - 1)
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    ft = P.FT(b, r["np0"], r["np1"], r["np2"])
+    cur = P.compute_current(ft, r["c"], r["occ"] / r["omega"], r["kpgx"])
+    assert np.abs(cur - r["cur"]).max() < TOL * np.abs(r["cur"]).max()
+    ngw = b["ngw"]
+    tot = cur.sum(axis=1) * r["omega"] / ft.N
+    want = [-float(np.sum(r["occ"][:, None] * np.abs(r["c"][:, :ngw]) ** 2 * r["kpgx"][d][None, :])) for d in range(3)]
+    assert np.abs(tot - np.array(want)).max() < 1e-10 * max(1.0, np.abs(want).max())
