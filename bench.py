@@ -16,6 +16,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -26,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "hpsi_density_state_applies_per_s", "state-applies/s"
+_FP64_PEAK = {}          # device index -> (DMMA TFLOP/s, DFMA TFLOP/s), measured once per process
 
 WORKLOADS = {
     # name: cell, ecut (Ha), kpoint, force_complex, nst per GPU, species shape [(name, na, lproj)], note
@@ -125,17 +129,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
-    """times the reference's own SlaterDet::rs_mul_add / compute_density / NonLocalPotential::energy (oracle/_ref, the
-    UNMODIFIED reference compiled serially with its built-in FFT) on a bounded sample of the workload."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def reference_case(wl_name, nst_sample, tmp):
+    """the workload as a case of oracle/_ref/ref_driver: synthetic species files of the workload's projector shape
+    (oracle/synth_species.py; /root/reference and its pseudopotentials do not exist on the GPU box) and the same atom
+    positions as the GPU arm"""
     import refdrive as R
     import synth_species as S
     wl = WORKLOADS[wl_name]
-    threads = threads or os.cpu_count() or 1
-    if not R.have_ref():
-        return None
-    tmp = tempfile.mkdtemp(prefix="qbbench_")
     spfiles = {"mgo216": S.mgo_species, "au992": S.au_species, "si54p": S.si_species}.get(wl_name)
     species, atoms = [], []
     if spfiles:
@@ -147,8 +147,21 @@ def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
             for i in range(na):
                 atoms.append((f"{nm}{i}", nm, float(pos[o + i][0]), float(pos[o + i][1]), float(pos[o + i][2])))
             o += na
-    case = R.Case(cell=wl["cell"], ecut=wl["ecut"], kpoint=wl["kpoint"], force_complex=wl["force_complex"], nst=nst_sample,
+    return R.Case(cell=wl["cell"], ecut=wl["ecut"], kpoint=wl["kpoint"], force_complex=wl["force_complex"], nst=nst_sample,
                   species=species, atoms=atoms)
+
+
+def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
+    """times the reference's own SlaterDet::rs_mul_add / compute_density / NonLocalPotential::energy (oracle/_ref, the
+    UNMODIFIED reference compiled serially with its built-in FFT) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdrive as R
+    wl = WORKLOADS[wl_name]
+    threads = threads or os.cpu_count() or 1
+    if not R.have_ref():
+        return None
+    tmp = tempfile.mkdtemp(prefix="qbbench_")
+    case = reference_case(wl_name, nst_sample, tmp)
     prefix = os.path.join(tmp, "case")
     cf = os.path.join(tmp, "case.txt")
     with open(cf, "w") as f:
@@ -164,7 +177,74 @@ def run_reference_cpu(wl_name, nst_sample, nrep, threads=None):
     t = json.loads(line)
     per_rep = (t["t_nonlocal"] + t["t_kinetic"] + t["t_local"] + t["t_density"]) / nrep
     t.update(per_rep_s=per_rep, applies_per_s=nst_sample / per_rep, threads=threads)
+    shutil.rmtree(tmp, ignore_errors=True)
     return t
+
+
+def parity_vs_reference(wl_name, nst_sample, device, stream):
+    """The oracle as the CHECKER of the GPU arm on the benchmark's own configuration: the compiled reference
+    (oracle/_ref/ref_driver `run`) evaluates H psi, rho and E_nl for the first `nst_sample` states of the workload -- the
+    same seeded coefficients / potential / atom positions the CPU timing leg uses, all atoms' projector tables as the
+    reference's own NonLocalPotential::update_twnl builds them from the species files -- and the GPU path (C ABI) is run
+    on exactly those inputs and tables.  Returns max-norm relative errors (north_star gate: 1e-10)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import refdrive as R
+    from qball_b200 import host as H
+    if not R.have_ref():
+        return None
+    wl = WORKLOADS[wl_name]
+    tmp = tempfile.mkdtemp(prefix="qbparity_")
+    try:
+        t0 = time.perf_counter()
+        r = R.run_reference(reference_case(wl_name, nst_sample, tmp), seed=1, nocc=None, workdir=tmp,
+                            threads=os.cpu_count() or 1)        # v: seed + 6 = 7, as the timing leg
+        t_ref = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    b, _ = make_basis(wl["cell"], wl["ecut"], wl["kpoint"], wl["force_complex"])
+    assert b["ngw"] == r["ngw"] and np.array_equal(b["rod_h"], r["rod_h"]) and np.array_equal(b["idx"], r["idx"]), "basis tables differ from the reference's"
+    ft = H.FourierTransform(b, r["np0"], r["np1"], r["np2"], device=device, stream=stream)
+    nlp = H.NonLocalPotential(b, r["species"], device=device, stream=stream)
+    N = r["np0"] * r["np1"] * r["np2"]
+    dev = torch.device("cuda", device)
+    with torch.cuda.stream(stream):
+        cd = torch.from_numpy(r["c"]).to(dev)
+        vd = torch.from_numpy(r["v"]).to(dev)
+        out = torch.zeros_like(cd)
+        enl = H.hpsi(ft, nlp, cd, r["occ"], vd, torch.from_numpy(b["kpg2"]).to(dev), out)
+        rho = torch.zeros(N, dtype=torch.float64, device=dev)
+        H.compute_density(ft, cd, 1.0, r["occ"], r["omega"], rho)
+    torch.cuda.synchronize(dev)
+    hp, rh = out.cpu().numpy(), rho.cpu().numpy()
+    res = {"hpsi_relerr": float(np.abs(hp - r["hpsi"]).max() / np.abs(r["hpsi"]).max()),
+           "rho_relerr": float(np.abs(rh - r["rho"]).max() / np.abs(r["rho"]).max()),
+           "enl_abs": float(abs(enl - r["enl"])), "enl_rel": float(abs(enl - r["enl"]) / max(1.0, abs(r["enl"]))),
+           "enl": float(enl), "enl_reference": float(r["enl"]), "states": nst_sample,
+           "projector_rows": int(sum(s["na"] * s["npr"] for s in r["species"])), "projector_form": int(nlp.query(14)),
+           "reference_seconds": t_ref,
+           "what": f"first {nst_sample} states of the {wl_name} workload, all atoms' projectors: qb200_hpsi + qb200_compute_density "
+                   "against oracle/_ref/ref_driver (unmodified reference: NonLocalPotential::energy + kinetic + SlaterDet::rs_mul_add, "
+                   "SlaterDet::compute_density) on identical inputs and projector tables; tolerance 1e-10"}
+    res["ok"] = bool(res["hpsi_relerr"] < 1e-10 and res["rho_relerr"] < 1e-10 and res["enl_rel"] < 1e-10)
+    del ft, nlp, cd, vd, out, rho
+    torch.cuda.empty_cache()
+    return res
+
+
+def probe_cpu_fft_libraries():
+    """BASELINE.md tier B (the reference built against FFTW3) needs an FFTW3 on the box: probed, not assumed"""
+    import ctypes.util
+    found = {name: bool(ctypes.util.find_library(name)) for name in ("fftw3", "fftw3_omp", "fftw3_threads", "mkl_rt", "essl")}
+    found["note"] = "no FFTW3/MKL/ESSL on this image: tier B (reference + FFTW3) cannot be built; the CPU arm is the reference's built-in FFT" \
+        if not any(v for v in found.values() if isinstance(v, bool)) else "an FFT library is present: rebuild oracle/_ref with HAVE_FFTW3 for the tier-B arm"
+    return found
+
+
+def norm2_states(c, ngw, is_real):
+    """sum_G |c_G|^2 per state over the FULL sphere (real bases store half of it: G and -G, G = 0 once)"""
+    a = (c[:, :ngw].real ** 2 + c[:, :ngw].imag ** 2).sum(axis=1)
+    return 2.0 * a - c[:, 0].real ** 2 if is_real else a
 
 
 def main():
@@ -187,14 +267,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-mb", type=int, default=0, help="qb200_plan_set_workspace (0: the library default)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's states PER GPU (default); strong: the workload's states IN TOTAL, split over the GPUs")
+    ap.add_argument("--no-sub", action="store_true", help="skip the au992 / strong-scaling sub-records of the default run")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.nst:
         wl["nst"] = args.nst
+    if args.scaling == "strong":
+        wl["nst"] = max(1, wl["nst"] // int(os.environ.get("WORLD_SIZE", "1")))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric, unit = "hpsi_density_state_applies_per_s", "state-applies/s"
+    metric, unit = METRIC, UNIT
     config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}",
               "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if args.workload == "mgo216" else "L2 flushed by the c/Hpsi block sweep"}
 
@@ -254,6 +339,46 @@ def main():
         import datetime
         # every collective of this bench is short: a rank that dies must not hold the others for NCCL's default 10 minutes
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
+    out = run_ours(args, args.workload, wl, rank, world, local_rank, args.steps, args.warmup, extras=not args.no_e2e,
+                   scaling=args.scaling)
+    # ---------------------------------------------------------------- sub-records of the default run (the driver runs
+    # `bench.py --gpus N --steps K --warmup W` only): the other half of the metric (Au992 shape, fixed 64-state shard per
+    # GPU) and, at N > 1, MgO216 STRONG scaling (768 states in total, 768/N per GPU) next to the weak-scaling headline
+    if args.workload == "mgo216" and not args.nst and not args.no_sub and args.scaling == "weak":
+        keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "gpu_launches", "roofline",
+                "roofline_hbm", "roofline_local_path", "roofline_fp64", "kernel_ms_per_step", "shape", "parity", "enl", "e2e")
+        if world > 1:
+            wls = dict(WORKLOADS["mgo216"])
+            wls["nst"] = WORKLOADS["mgo216"]["nst"] // world
+            try:
+                sub = run_ours(args, "mgo216", wls, rank, world, local_rank, args.steps, args.warmup, extras=False, want_e2e=True,
+                               scaling="strong")
+                out["strong_scaling"] = {k: sub[k] for k in keep if k in sub}
+            except Exception as ex:  # noqa: BLE001
+                out["strong_scaling"] = {"error": str(ex)[:300]}
+        try:
+            sub = run_ours(args, "au992", dict(WORKLOADS["au992"]), rank, world, local_rank, max(3, min(args.steps, 4)), 1, extras=False)
+            out["au992"] = {k: sub[k] for k in keep if k in sub}
+        except Exception as ex:  # noqa: BLE001
+            out["au992"] = {"error": str(ex)[:300]}
+    if rank == 0:
+        emit(out)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, want_e2e=False, scaling="weak"):
+    """one measurement of the B200 arm on workload `wl` (per-GPU shard wl["nst"]); extras: the side measurements of the
+    headline record (TDDFT glue, cuFFT comparison, subspace LA, e2e, CPU baseline, parity against the reference)"""
+    import torch
+    import torch.distributed as dist
+    from qball_b200 import capi
+    from qball_b200 import host as H
+    dev = torch.device("cuda", local_rank)
+    metric, unit = METRIC, UNIT
+    config = {"workload": f"{wl_name}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}",
+              "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if wl["nst"] * 16 * 70000 > (200 << 20) else "L2 flushed by the c/Hpsi block sweep"}
     b, grid = make_basis(wl["cell"], wl["ecut"], wl["kpoint"], wl["force_complex"])
     np0, np1, np2 = grid
     N, ngw, nst = np0 * np1 * np2, b["ngw"], wl["nst"]
@@ -293,7 +418,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     sync_all()
     l0 = ft.launches() + nlp.launches()
@@ -304,7 +429,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         enl = step()
     with torch.cuda.stream(stream):
         e1.record(stream)
@@ -318,8 +443,30 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * nst * args.steps / (ms * 1e-3)
+    ms_per_step = ms / steps
+    value = world * nst * steps / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- integrity of the (all-reduced) density of the last step:
+    # integral of rho = sum_n occ_n ||c_n||^2 (ChargeDensity.cc:525), and at N > 1 the all-reduced rho against the
+    # rank-ordered sum of the per-rank densities gathered on every rank (NCCL's reduction order may differ: ~1e-16)
+    with torch.cuda.stream(stream):
+        nel = float(rho.sum().item()) * omega / N
+        want = torch.tensor([float(np.dot(occ, norm2_states(c_host, ngw, b["is_real"])))], dtype=torch.float64, device=dev)
+        rho_sum_err = None
+        if world > 1:
+            dist.all_reduce(want)
+            mine = torch.zeros(N, dtype=torch.float64, device=dev)
+            H.compute_density(ft, c, 1.0, occ, omega, mine)
+            parts = torch.empty((world, N), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(parts, mine)
+            tot = parts[0].clone()
+            for r in range(1, world):
+                tot += parts[r]
+            rho_sum_err = float(((rho - tot).abs().max() / tot.abs().max()).item())
+            del mine, parts, tot
+    integrity = {"nelectrons": nel, "sum_occ_norm2": float(want.item()), "nelectrons_relerr": abs(nel - float(want.item())) / float(want.item()),
+                 "allreduced_rho_vs_sum_of_rank_rhos_relerr": rho_sum_err}
+    integrity["ok"] = bool(integrity["nelectrons_relerr"] < 1e-10 and (rho_sum_err is None or rho_sum_err < 1e-12))
 
     # ---------------------------------------------------------------- roofline of the dominant kernels (live event times)
     peaks = {}
@@ -343,17 +490,17 @@ def main():
 
     def traffic_of(*keys):
         """launch-weighted mean DRAM bytes per launch over the kernels `keys` (None unless every one was captured)"""
-        if args.workload != "mgo216" or not all(k in ncu_traffic for k in keys):
+        if wl_name != "mgo216" or not all(k in ncu_traffic for k in keys):
             return None
         return sum(ncu_traffic[k]["dram_bytes_per_launch"] for k in keys) / len(keys)
 
     roofline_hbm = None
     if xy_n:
-        ach = xy_bytes_step * args.steps / (xy_ms * 1e-3) / 1e9
+        ach = xy_bytes_step * steps / (xy_ms * 1e-3) / 1e9
         roofline_hbm = {"kernel": "k_plane (fused xy stage)" if ft.fused() else "k_xrows+k_ycols (split xy stage)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": traffic_of("k_plane_s<0>", "k_plane_s<1>") if ft.fused() else None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": xy_bytes_step * args.steps / xy_n,
+                        "algorithmic_bytes_per_launch": xy_bytes_step * steps / xy_n,
                         "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
     # the whole local path (z columns + xy stage, both directions) against the HBM roofline with SURVEY.md section 8d's
     # per-unit algorithmic bytes: B_Hpsi = 48*ngw*cper + 64*nvec*np2 + 8*N, B_rho = 16*ngw + 32*nvec*np2 (+16*N per build)
@@ -362,10 +509,12 @@ def main():
     local_ms = prof["k_zcol_bwd"][0] + prof["xy_stage"][0] + prof["k_zcol_fwd"][0] + prof["k_rho_reduce"][0]
     roofline_local = None
     if local_ms > 0:
-        ach = local_bytes_step * args.steps / (local_ms * 1e-3) / 1e9
+        ach = local_bytes_step * steps / (local_ms * 1e-3) / 1e9
         roofline_local = {"kernel": "local path: k_zcol_bwd + xy stage + k_zcol_fwd (H psi local term + density)", "bound": "hbm",
                           "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                           "note": "xy stage is bound by the shared-memory and FP64 pipes (ncu: smem wavefronts 65%, FP64 45%, DRAM 7% of peak), not by HBM"}
+    if roofline_local is not None:
+        roofline_local["fp64_roof_note"] = "the butterflies of the local path execute ~0.18 TFLOP per MgO216 step; at the measured DFMA rate that is the second roof of this stage (see roofline_fp64.fp64_tflops_measured)"
     nl_flops_step = 0.0     # flops EXECUTED on the FP64 tensor pipe
     nl_zgemm_flops_step = 0.0   # the same contraction counted as the reference's zgemm/dgemm (8 / 2 flops per MAC)
     nl_mode = nlp.query(14)   # 0 real basis, 1 four-product, 2 three-product (Karatsuba), 3 Gamma-point half sphere (real-function split)
@@ -375,26 +524,37 @@ def main():
         nl_flops_step += per_mac * s["na"] * s["npr"] * ngw * nst
         nl_zgemm_flops_step += (8.0 if b["is_real"] else 16.0) * s["na"] * s["npr"] * ngw * nst
     nl_ms = prof["k_fnl"][0] + prof["k_back"][0]
-    fp64_peak = 37.0   # TFLOP/s nominal B200 FP64 (vector = DMMA); MEASURED_PEAKS.json has no FP64 entry
+    # FP64 ceiling: measured in this process by the library's DMMA / DFMA issue-rate loops (MEASURED_PEAKS.json holds no
+    # FP64 figure); the nominal B200 number is kept beside it
+    if local_rank not in _FP64_PEAK:
+        try:
+            _FP64_PEAK[local_rank] = capi.measure_fp64_peak(local_rank)
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"fp64 peak measurement failed: {ex}\n")
+            _FP64_PEAK[local_rank] = (None, None)
+    dmma_tf, dfma_tf = _FP64_PEAK[local_rank]
+    fp64_peak = dmma_tf if dmma_tf else 37.0
     roofline_fp64 = None
     if nl_ms > 0:
-        ach = nl_flops_step * args.steps / (nl_ms * 1e-3) / 1e12
+        ach = nl_flops_step * steps / (nl_ms * 1e-3) / 1e12
         roofline_fp64 = {"kernel": ("k_fnl3 + k_back3 (DMMA projector GEMMs, 3-product complex form: 12 flops per complex MAC)" if m3
                                     else "k_split_pm + k_fnl<1> + k_back<2> (DMMA projector GEMMs over the half sphere: complex states "
                                          "at Gamma projected as two real functions, 8 flops per complex MAC; the split pass and the scatter epilogue included in the time)"
                                     if nl_mode == 3 else "k_fnl + k_back (DMMA projector GEMMs)"), "bound": "tensor", "achieved": ach, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic_of("k_fnl3<4>", "k_back3<4>") if m3 else (traffic_of("k_split_pm", "k_fnl<1>", "k_back<2>") if nl_mode == 3 else None),
-                         "zgemm_equivalent_tflops": nl_zgemm_flops_step * args.steps / (nl_ms * 1e-3) / 1e12,
-                         "peak_source": "nominal FP64 37 TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)",
+                         "zgemm_equivalent_tflops": nl_zgemm_flops_step * steps / (nl_ms * 1e-3) / 1e12,
+                         "peak_source": ("measured in this run: qb200_measure_fp64_peak (DMMA m8n8k4 issue-rate loop on every SM)" if dmma_tf
+                                         else "nominal FP64 37 TFLOP/s (measurement failed)"),
+                         "fp64_tflops_measured": {"dmma": dmma_tf, "dfma": dfma_tf}, "fp64_tflops_nominal": 37.0,
                          "launches": prof["k_fnl"][1] + prof["k_back"][1]}
-    prof_ms = {k: round(vv[0] / args.steps, 4) for k, vv in prof.items()}
+    prof_ms = {k: round(vv[0] / steps, 4) for k, vv in prof.items()}
     dominant = max(prof.items(), key=lambda kv: kv[1][0])[0]
     roofline = roofline_fp64 if dominant in ("k_fnl", "k_back") and roofline_fp64 else roofline_hbm
 
     # ---------------------------------------------------------------- TDDFT propagation (configs[3]): one 4th-order Taylor
     # exponential exp(-i dt H) on the resident block = 4 H psi applications + axpy chain (ExponentialWavefunctionStepper.cc:51-149)
     tddft = None
-    if not b["is_real"] and not args.no_e2e:
+    if not b["is_real"] and extras:
         with torch.cuda.stream(stream):
             cprop = c.clone()
             H.exponential(ft, nlp, cprop, occ, v, kpg2, 0.02)        # warm-up (allocates the two work blocks)
@@ -426,7 +586,7 @@ def main():
     # local operator cp += FT[v FT^-1 c] per state on dense grids through torch.fft (cuFFT Z2Z 3-D, batched), coefficients
     # already scattered to the grid and no gather timed -- i.e. cuFFT is given LESS work than the fused path does
     cufft = None
-    if rank == 0 and not args.no_e2e:
+    if rank == 0 and extras:
         try:
             nb_c = max(1, min(nst, int((2 << 30) // (16 * N))))          # states per cuFFT batch (<= 2 GiB per buffer)
             with torch.cuda.stream(stream):
@@ -467,7 +627,7 @@ def main():
     # the PSD/PSDA descent direction a = c^H Hc, Hc -= c a (with band sharding: after an NCCL all-gather of the state
     # blocks -- the path's one exchange step) and SlaterDet::gram on this rank's block
     subspace = None
-    if not args.no_e2e:
+    if extras:
         try:
             la = H.SubspaceLA(b, device=local_rank, stream=stream)
             from qball_b200 import parallel as PAR
@@ -509,7 +669,7 @@ def main():
 
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI, copies inside
     e2e = None
-    if not args.no_e2e:
+    if extras or want_e2e:
         hc = torch.from_numpy(c_host).pin_memory()
         hv = torch.from_numpy(v_host).pin_memory()
         hk = torch.from_numpy(b["kpg2"]).pin_memory()
@@ -530,7 +690,7 @@ def main():
                 H.compute_density(ft, hc, 1.0, occ, omega, hrho)
             return e
 
-        ne = max(1, min(args.steps, 3))
+        ne = max(1, min(steps, 3))
         step_host()
         sync_all()
         t0 = time.perf_counter()
@@ -550,30 +710,40 @@ def main():
 
     # ---------------------------------------------------------------- cpu baseline (rank 0, N=1): the compiled reference
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {"mgo216": 16, "au992": 1, "sih4": 4, "si54p": 16}[args.workload]
+    parity = {"integrity": integrity}
+    if rank == 0 and world == 1 and extras and not args.no_cpu_baseline:
+        sample = {"mgo216": 16, "au992": 1, "sih4": 4, "si54p": 16}[wl_name]
         try:
-            tcpu = run_reference_cpu(args.workload, sample, 1)
+            pr = parity_vs_reference(wl_name, sample, local_rank, stream)
+            if pr:
+                parity.update(pr)
+        except Exception as ex:  # noqa: BLE001
+            parity["error"] = str(ex)[:300]
+            sys.stderr.write(f"parity leg failed: {ex}\n")
+        try:
+            tcpu = run_reference_cpu(wl_name, sample, 1)
         except Exception as ex:  # noqa: BLE001
             tcpu = None
             sys.stderr.write(f"cpu baseline failed: {ex}\n")
         if tcpu:
             cpu_baseline = {"value": tcpu["applies_per_s"], "unit": unit, "cores": tcpu["threads"], "kind": "reference",
-                            "sample": f"{sample} states of the {args.workload} shape, all projectors, one H psi + density pass; "
+                            "sample": f"{sample} states of the {wl_name} shape, all projectors, one H psi + density pass; "
                                       f"reference compiled serially with its built-in FFT (oracle/_ref), OMP threads = cores",
-                            "breakdown_s": {k: tcpu[k] for k in ("t_nonlocal", "t_kinetic", "t_local", "t_density")}}
+                            "breakdown_s": {k: tcpu[k] for k in ("t_nonlocal", "t_kinetic", "t_local", "t_density")},
+                            "fft_backend": "FFT_NOLIB (the reference's built-in cfftm, its slowest tier)",
+                            "tier_b_probe": probe_cpu_fft_libraries()}
 
-    if rank == 0:
-        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-               "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
-               "kernel_ms_per_step": prof_ms, "tddft": tddft, "subspace_la": subspace, "cufft_comparison": cufft, "enl": enl,
-               "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
-                         "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
-        emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+           "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_local_path": roofline_local, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline,
+           "parity": parity,
+           "kernel_ms_per_step": prof_ms, "tddft": tddft, "subspace_la": subspace, "cufft_comparison": cufft, "enl": enl,
+           "shape": {"ngw": ngw, "nvec": nvec, "grid": [np0, np1, np2], "nst_per_gpu": nst, "nprna": sum(s["na"] * s["npr"] for s in species),
+                     "fused_plane_path": ft.fused(), "states_per_batch": ft.batch()}}
+    del ft, nlp, c, v, hpsi, rho
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -192,6 +192,11 @@ int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info);
 int qb200_profile_enable(int on);
 int qb200_profile_read(double* ms, long long* count, int ncat);
 
+/* ---- device self-measurement for the FP64 roofline denominator (bench.py): out[0] = FP64 tensor (DMMA, mma.sync.m8n8k4.f64)
+ *      TFLOP/s, out[1] = plain DFMA TFLOP/s, issue-rate loops on every SM of `device` (~50 ms).  The reference has no
+ *      counterpart; MEASURED_PEAKS.json carries no FP64 figure. */
+int qb200_measure_fp64_peak(int device, double* out);
+
 #ifdef __cplusplus
 }
 #endif

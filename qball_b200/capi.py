@@ -71,6 +71,8 @@ def load():
     L.qb200_la_query.restype = ll
     L.qb200_residual.argtypes = [vp, i, i, dp, i, dp, dp]
     L.qb200_gram.argtypes = [vp, i, i, dp, ip]
+    L.qb200_measure_fp64_peak.argtypes = [i, C.POINTER(d)]
+    L.qb200_measure_fp64_peak.restype = i
     L.qb200_profile_enable.argtypes = [i]
     L.qb200_profile_read.argtypes = [C.POINTER(d), C.POINTER(ll), i]
     for name in ("qb200_profile_enable", "qb200_profile_read", "qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace", "qb200_plan_set_coefficient_tag",
@@ -111,6 +113,13 @@ def device_count() -> int:
 
 
 PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce", "k_anl_gen")
+
+
+def measure_fp64_peak(device: int = 0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) measured on `device` by the library's issue-rate loops"""
+    out = (C.c_double * 2)()
+    _check(load().qb200_measure_fp64_peak(int(device), out), "qb200_measure_fp64_peak")
+    return float(out[0]), float(out[1])
 
 
 def profile_enable(on: bool):

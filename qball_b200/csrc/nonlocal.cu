@@ -528,6 +528,8 @@ struct qb200_nl {
   NlLattice lat;
   double bvec[9], kcart[3];
   std::vector<double2*> ph;                    // per species phase tables
+  std::vector<int> ph_JT;                      // the NlLattice::JT each table was allocated for
+  std::vector<void*> lat_owned;                // uploads of the last qb200_nl_set_lattice (freed by the next one)
   bool ph_dirty;
   // concatenated projector list and the materialised anl chunk
   int Mtot;
@@ -561,11 +563,11 @@ static int nl_ensure(double** buf, size_t* cap, size_t elems)
   return QB200_OK;
 }
 
-template <class T> static int nl_upload(qb200_nl* nl, const T* h, size_t n, const T** d)
+template <class T> static int nl_upload(qb200_nl* nl, const T* h, size_t n, const T** d, bool lattice = false)
 {
   void* p = nullptr;
   QB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  nl->owned.push_back(p);
+  (lattice ? nl->lat_owned : nl->owned).push_back(p);
   if (n) QB_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
   *d = (const T*)p;
   return QB200_OK;
@@ -600,23 +602,27 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   nl->Wg = nl->Ug = nullptr; nl->Wg_cap = nl->Ug_cap = 0; nl->Wg_valid = false; nl->last_mode = 0; nl->sym_dirty = true; nl->sym_ok = false;
   if (const char* e = getenv("QB200_NL_GAMMA")) if (e[0] == '0') nl->gamma_off = true;
   if (const char* e = getenv("QB200_NL_TILE")) nl->tile3m = atoi(e);
+  // every failure after `new` destroys the object again (no leak on an early return)
+  auto fail = [nl](cudaError_t e, const char* what, int line) { const int rc = cuda_fail(e, what, __FILE__, line); qb200_nl_destroy(nl); return rc; };
+#define NL_CREATE_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(e__, #x, __LINE__); } while (0)
   cudaDeviceProp prop;
-  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  NL_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
   nl->nsm = prop.multiProcessorCount;
   const double* d;
   int rc = nl_upload(nl, kpgx, 3 * (size_t)ngw, &d);
   if (rc) { qb200_nl_destroy(nl); return rc; }
   nl->kpgx = const_cast<double*>(d);
-  QB_CUDA(cudaMalloc((void**)&nl->enl_dev, sizeof(double)));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_back<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 4, 3>::SMEM));
-  QB_CUDA(cudaFuncSetAttribute(k_fnl3<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 2, 2>::SMEM));
-  QB_CUDA(cudaFuncSetAttribute(k_back3<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 4, 4>::SMEM));
-  QB_CUDA(cudaFuncSetAttribute(k_back3<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 2, 3>::SMEM));
+  NL_CREATE_CUDA(cudaMalloc((void**)&nl->enl_dev, sizeof(double)));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_fnl<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_fnl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FNL_SMEM_BYTES));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_back<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_fnl3<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 4, 3>::SMEM));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_fnl3<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fnl3Cfg<4, 2, 2>::SMEM));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_back3<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 4, 4>::SMEM));
+  NL_CREATE_CUDA(cudaFuncSetAttribute(k_back3<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Back3Cfg<4, 2, 3>::SMEM));
+#undef NL_CREATE_CUDA
   *out = nl;
   return QB200_OK;
 }
@@ -638,6 +644,7 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   }
   nl->sp.push_back(s);
   nl->ph.push_back(nullptr);
+  nl->ph_JT.push_back(0);
   nl->Mtot += s.M;
   nl->ph_dirty = true; nl->wtp_dirty = true; nl->W_valid = false; nl->Wg_valid = false; nl->sym_dirty = true;
   return QB200_OK;
@@ -656,8 +663,13 @@ extern "C" int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* 
       planes[(size_t)d * ngw + i] = v;
       jmax[d] = std::max(jmax[d], std::abs(v));
     }
+  // a repeated call (cell or cutoff change) replaces the previous description: release its uploads first
+  QB_CUDA(cudaStreamSynchronize(nl->stream));
+  for (void* q : nl->lat_owned) cudaFree(q);
+  nl->lat_owned.clear();
+  nl->lat.idx = nullptr; nl->ghalf = nl->gminus = nullptr; nl->nhalf = 0;
   const int* dev;
-  int rc = nl_upload(nl, planes.data(), planes.size(), &dev);
+  int rc = nl_upload(nl, planes.data(), planes.size(), &dev, true);
   if (rc) return rc;
   nl->lat.idx = dev;
   for (int d = 0; d < 3; d++) nl->lat.jmax[d] = jmax[d];
@@ -686,7 +698,7 @@ extern "C" int qb200_nl_set_lattice(qb200_nl* nl, const int* idx, const double* 
       }
       if (ok && (int)gh.size() == (ngw + 1) / 2) {
         const int *dh, *dm;
-        if ((rc = nl_upload(nl, gh.data(), gh.size(), &dh)) || (rc = nl_upload(nl, gm.data(), gm.size(), &dm))) return rc;
+        if ((rc = nl_upload(nl, gh.data(), gh.size(), &dh, true)) || (rc = nl_upload(nl, gm.data(), gm.size(), &dm, true))) return rc;
         nl->ghalf = dh; nl->gminus = dm; nl->nhalf = (int)gh.size(); nl->gamma_half = true;
       }
     }
@@ -739,9 +751,10 @@ static int nl_refresh_tables(qb200_nl* nl)
   for (size_t is = 0; is < nl->sp.size(); is++) {
     NlSpecies& S = nl->sp[is];
     if (S.M <= 0) continue;
-    if (!nl->ph[is]) {
+    if (!nl->ph[is] || nl->ph_JT[is] < nl->lat.JT) {      // a later set_lattice may need longer tables (larger |h|,|k|,|l|)
+      if (nl->ph[is]) { cudaFree(nl->ph[is]); nl->ph[is] = nullptr; }
       QB_CUDA(cudaMalloc((void**)&nl->ph[is], (size_t)S.na * nl->lat.JT * sizeof(double2)));
-      nl->owned.push_back(nl->ph[is]);
+      nl->ph_JT[is] = nl->lat.JT;
     }
     const double* b = nl->bvec;
     k_phase_tables<<<S.na, 128, 0, nl->stream>>>(S, nl->lat, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8],
@@ -782,6 +795,8 @@ extern "C" int qb200_nl_destroy(qb200_nl* nl)
   if (!nl) return QB200_OK;
   cudaSetDevice(nl->device);
   for (void* p : nl->owned) cudaFree(p);
+  for (double2* p : nl->ph) if (p) cudaFree(p);
+  for (void* p : nl->lat_owned) cudaFree(p);
   for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W, nl->Wg, nl->Ug }) if (p) cudaFree(p);
   delete nl;
   return QB200_OK;

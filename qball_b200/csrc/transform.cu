@@ -292,7 +292,8 @@ static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t sme
   DevPlan& d = p->d;
   p->z2 = false;
   if (const char* e = getenv("QB200_Z2")) if (e[0] == '0') return QB200_OK;
-  if (d.np2 > 4095) return QB200_OK;
+  // zq packs (digit-reversed z) | (column << 12) in one int: 12 bits of z, 19 bits of column
+  if (d.np2 > 4095 || d.nvec >= (1 << 19)) return QB200_OK;
   int fb = 0, ff = 0;
   if (const char* e = getenv("QB200_ZB_COLS")) fb = atoi(e);
   if (const char* e = getenv("QB200_ZF_COLS")) ff = atoi(e);
@@ -433,7 +434,8 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   }
   // launch geometry
   cudaDeviceProp prop;
-  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  { const cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { const int rcp = cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__); qb200_plan_destroy(p); return rcp; } }
   p->max_smem = (int)prop.sharedMemPerBlockOptin;
   p->nsm = prop.multiProcessorCount;
   {

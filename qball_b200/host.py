@@ -128,8 +128,7 @@ class ChargeDensity:
         else:
             rhor[...] = 0.0
         compute_density(self.ft, c, weight, occ, self.omega, rhor)
-        if hasattr(rhor, "is_cuda"):
-            _par.allreduce_density(rhor, group)
+        _par.allreduce_density(rhor, group)                        # wfcontext->dsum('r', ...) (:309); host or device array
         nel = C.c_double(0.0)
         capi._check(self.ft._L.qb200_density_finish(self.vft._h, capi.ptr(rhor), self.omega, capi.ptr(rhog), C.byref(nel)),
                     "qb200_density_finish")
@@ -163,8 +162,7 @@ class CurrentDensity:
         else:
             cur[...] = 0.0
         compute_current(self.ft, c, weight, occ, self.omega, kpgx, cur)
-        if hasattr(cur, "is_cuda"):
-            _par.allreduce_density(cur, group)                     # wfcontext()->dsum('r', ...) (:90)
+        _par.allreduce_density(cur, group)                         # wfcontext()->dsum('r', ...) (:90); host or device array
         dv = self.omega / self.ft.np012()
         tot = cur.sum(dim=1) if hasattr(cur, "is_cuda") else cur.sum(axis=1)
         self.total_current = [float(dv * t) for t in tot]

@@ -9,6 +9,7 @@ rank needs ALL columns of c to form its columns of a = c^H (H c) and of c a -- a
 NVLink) replaces the reference's pzgemm communication over process columns."""
 from __future__ import annotations
 
+import numpy as np  # noqa: F401  (host arrays are accepted by allreduce_density)
 import torch
 import torch.distributed as dist
 
@@ -20,10 +21,22 @@ def state_block(nst: int, rank: int, world: int):
     return first, max(0, min(nb, nst - first))
 
 
-def allreduce_density(rho: torch.Tensor, group=None) -> torch.Tensor:
-    """wfcontext->dsum('r', np012loc, 1, rhor) over the state-column ranks"""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(rho, op=dist.ReduceOp.SUM, group=group)
+def allreduce_density(rho, group=None):
+    """wfcontext->dsum('r', np012loc, 1, rhor) over the state-column ranks (ChargeDensity.cc:309).  `rho` is a torch
+    tensor (CUDA or CPU) or a numpy HOST array (the C ABI stages host pointers, so host grids are a supported input and
+    must be summed over ranks exactly like device ones); reduced in place.  A host array under an NCCL-only process group
+    is staged through the current CUDA device."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return rho
+    t = rho if isinstance(rho, torch.Tensor) else torch.from_numpy(rho)      # shares memory with the numpy array
+    if not t.is_cuda and "gloo" not in str(dist.get_backend(group)).lower():
+        if not torch.cuda.is_available():
+            raise RuntimeError("allreduce_density: host array, but the process group has no CPU backend and no CUDA device")
+        d = t.cuda()
+        dist.all_reduce(d, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(d)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return rho
 
 

@@ -25,6 +25,18 @@ AL = EX + "/bulkal/TM_CAPW91_Al.xml"
 AU_ONCV = REF + "/testsuite/pseudopotentials/05_gold_oncv/Au_ONCV_PBE-1.0.xml"
 MG = EX + "/MgO216/Mg.xml"
 OX = EX + "/MgO216/O.xml"
+HY = EX + "/MgO216/H.xml"
+
+
+def sys_atoms(path):
+    """atom lines of a reference .sys file -> [(name, species, x, y, z)]"""
+    out = []
+    for line in open(path):
+        w = line.split()
+        if w and w[0] == "atom":
+            out.append((w[1], w[2], float(w[3]), float(w[4]), float(w[5])))
+    return out
+
 
 CASES = {
     # name: (Case, seed, nocc, mode, stride)
@@ -53,6 +65,14 @@ CASES = {
                                      atoms=[("Mg1", "magnesium", 0.0, 0.0, 0.0), ("Mg2", "magnesium", 3.85, 3.85, 0.0),
                                             ("Mg3", "magnesium", 11.55, 7.7, 3.85), ("O1", "oxygen", 3.85, 0.0, 0.0),
                                             ("O2", "oxygen", 0.0, 3.85, 0.0)]), 16, None, "sampled", 997),
+    # the benchmark's own projector regime: every atom of examples/MgO216/mg108o108h1.sys with the
+    # shipped Mg/O/H potentials (Mg 108 x 4 + O 108 x 1 = 540 projector rows in two species, H local only), 16 states
+    "mgo216_all_atoms_16st": (R.Case(cell=(23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), ecut=25.0, nst=16, force_complex=True,
+                                     species=[("magnesium", MG), ("oxygen", OX), ("hydrogen", HY)],
+                                     atoms=sys_atoms(EX + "/MgO216/mg108o108h1.sys")), 17, 14, "sampled", 2039),
+    # examples/bulkal/bulkal_kp3.i: fcc primitive cell, second k-point (0, 0, 1/3), 20 Ry, l <= 3 (lmax 3, llocal 2)
+    "bulkal_fcc_kpoint": (R.Case(cell=(-3.8, 0, 3.8, 0, 3.8, 3.8, -3.8, 3.8, 0), ecut=10.0, nst=6, kpoint=(0.0, 0.0, 0.3333333),
+                                 species=[("aluminum", AL)], atoms=[("Al1", "aluminum", 0.0, 0.0, 0.0)]), 18, 4, "full", 1),
 }
 
 
@@ -64,7 +84,10 @@ def checksum(a: np.ndarray) -> float:
 
 def main():
     outdir = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]          # fixture names to (re)generate; default: all
     for name, (case, seed, nocc, mode, stride) in CASES.items():
+        if only and name not in only:
+            continue
         r = R.run_reference(case, seed=seed, nocc=nocc)
         d = dict(mode=mode, stride=stride, seed=seed, nocc=-1 if nocc is None else nocc,
                  cell=np.array(case.cell, dtype=np.float64), ecut=case.ecut, kpoint=np.array(case.kpoint, dtype=np.float64),
@@ -84,7 +107,15 @@ def main():
         for i, s in enumerate(r["species"]):
             d[f"sp{i}_na"], d[f"sp{i}_npr"] = s["na"], s["npr"]
             d[f"sp{i}_lproj"], d[f"sp{i}_wt"], d[f"sp{i}_tau"] = s["lproj"], s["wt"], s["tau"]
-            d[f"sp{i}_twnl"] = s["twnl"].astype(np.float64)
+            tw = s["twnl"].astype(np.float64)
+            if full or tw.size < 70000:
+                d[f"sp{i}_twnl"] = tw
+            else:
+                # large tables: a cubic cell repeats every value many times (twnl = Y_lm(G) v_l(|G|)); store each row's
+                # distinct values + the index of every plane wave into them (bit-exact, ~20x smaller)
+                u, inv = np.unique(tw, return_inverse=True)
+                d[f"sp{i}_twnl_uniq"] = u
+                d[f"sp{i}_twnl_inv"] = inv.reshape(tw.shape).astype(np.uint32)
         keys = ["bwd0", "fwd0", "hloc", "rho", "hpsi"] + (["hnl"] if r["nsp"] else [])
         if r["is_real"] and case.nst >= 2:
             keys += ["bwdpair01", "fwdpair0", "fwdpair1"]

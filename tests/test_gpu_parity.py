@@ -550,3 +550,99 @@ def test_cuda_gamma_half_sphere_host_blocks_sliced():
     _, h_ref = P.hpsi(b, oft, np.ascontiguousarray(c[sel]), v, occ[sel], species)
     assert abs(enl_h - enl_ref) <= 1e-10 * max(1.0, abs(enl_ref))
     assert relerr(hout.numpy()[sel][:, :ngw], h_ref[:, :ngw]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ the benchmark's own regime
+@pytest.mark.parametrize("mode", ["half_sphere", "three_product", "host_pointers"])
+def test_cuda_mgo216_all_atoms_benchmark_projector_regime(mode, monkeypatch):
+    """examples/MgO216 as the benchmark runs it: every atom of mg108o108h1.sys with the shipped Mg/O/H potentials --
+    540 projector rows in two species (Mg 108 x 4 at row offset 0, O 108 x 1 at offset 432 > 128, H local only), i.e.
+    five 128-row M tiles with a padded last tile -- 16 complex states on the 112^3 grid, against the arrays the reference
+    itself produced (NonLocalPotential.cc:1909-2171 with its atom blocks of :1541; fixture mgo216_all_atoms_16st).
+    Half-sphere form (k_split_pm / k_fnl<1> / k_back<2>, W streamed once), the general 3-product form, and host pointers."""
+    if mode == "three_product":
+        monkeypatch.setenv("QB200_NL_GAMMA", "0")
+    _run_fixture("mgo216_all_atoms_16st", mode != "host_pointers", False, monkeypatch)
+    g = load_golden("mgo216_all_atoms_16st")
+    assert [s["na"] * s["npr"] for s in g["species"]] == [432, 108, 0]
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    nlp = H.NonLocalPotential(b, g["species"])
+    # a block wider than one 64-state GEMM tile: the fixture's 16 states repeated with different occupations; column n of
+    # V_nl psi must not depend on its neighbours and E_nl is additive over states
+    reps = 5
+    cw = _dev(np.concatenate([c] * reps))
+    occw = np.concatenate([occ * (1.0 + 0.25 * r) for r in range(reps)])
+    cp = torch.zeros_like(cw)
+    enl = nlp.energy(cw, occw, True, cp)
+    assert nlp.query(13) == 540 and nlp.query(14) == (2 if mode == "three_product" else 3)
+    want = g["enl"] * sum(1.0 + 0.25 * r for r in range(reps))
+    assert abs(enl - want) <= 1e-10 * abs(want)
+    got = cp.cpu().numpy()
+    for r in range(reps):
+        compare(g, "hnl", got[16 * r:16 * (r + 1)])
+
+
+def _many_atoms_species(b, rng, shapes):
+    """projector tables with the parity of real projectors (twnl(-G) = (-1)^l twnl(G)) for many atoms"""
+    kpg = np.sqrt(b["kpg2"])
+    out = []
+    for na, lproj in shapes:
+        rows = []
+        for i, l in enumerate(lproj):
+            ang = 1.0 if l == 0 else (b["kpgx"][i % 3] / np.maximum(kpg, 1e-12)) ** l
+            rows.append((1.0 + 0.07 * i) * np.exp(-b["kpg2"] / (3.0 + 0.2 * i)) * ang)
+        a = np.array(b["cell"], dtype=np.float64).reshape(3, 3)
+        out.append(dict(na=na, npr=len(lproj), lproj=np.array(lproj, dtype=np.int32),
+                        wt=rng.uniform(0.4, 1.6, len(lproj)) * np.where(np.array(lproj) == 1, -1.0, 1.0),
+                        twnl=np.ascontiguousarray(np.array(rows)), tau=rng.uniform(0, 1, (na, 3)) @ a))
+    return out
+
+
+@pytest.mark.parametrize("kpoint,fc", [((1e-7, 0.0, 0.0), False), ((0.0, 0.0, 0.0), True), ((0.0, 0.0, 0.0), False)])
+def test_cuda_projectors_many_rows_chunked_vs_oracle(kpoint, fc):
+    """the gold benchmark's projector regime in miniature: 710 projector rows (two species, row offset 360 of the second,
+    a multi-channel l <= 2 species), a workspace that forces >= 3 plane-wave chunks per sweep (the anl block is regenerated
+    in both sweeps), 40 states; complex basis at a tiny k (Au992's k = (1e-7,0,0), 3-product form), complex states at
+    Gamma (half-sphere form) and real states at Gamma, against the oracle (NonLocalPotential.cc:1909-2171)"""
+    cell, ecut, nst = (14, 0, 0, 0, 15, 0, 0, 0, 21), 7.0, 40
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    b["cell"] = cell
+    ngw = b["ngw"]
+    rng = np.random.default_rng(91)
+    species = _many_atoms_species(b, rng, [(90, [0, 1, 1, 1]), (35, [0, 0, 1, 1, 1, 2, 2, 2, 2, 2])])
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 1, b["is_real"], seed=92)
+    occ = R.synth_occ(nst, nst - 3)
+    enl_ref, h_ref = P.nl_energy(b, c, occ, species)
+    nlp = H.NonLocalPotential(b, species)
+    nlp.set_workspace(710 * 24 * (ngw // 4))            # about a quarter of the sphere per chunk
+    base = np.ascontiguousarray(0.25 * c[::-1])
+    cp = _dev(base)
+    enl = nlp.energy(_dev(c), occ, True, cp)
+    assert nlp.query(13) == 710 and nlp.query(11) >= 3, (nlp.query(13), nlp.query(11))
+    assert abs(enl - enl_ref) <= 1e-10 * max(1.0, abs(enl_ref)), (enl, enl_ref)
+    assert relerr(cp.cpu().numpy() - base, h_ref) < TOL
+    # unchunked on the same inputs: identical E_nl to rounding, and H psi through the whole-Hpsi entry point
+    nl1 = H.NonLocalPotential(b, species)
+    cp1 = _dev(base)
+    enl1 = nl1.energy(_dev(c), occ, True, cp1)
+    assert nl1.query(11) == 1 and abs(enl1 - enl) <= 1e-12 * max(1.0, abs(enl))
+    assert relerr(cp1.cpu().numpy(), cp.cpu().numpy()) < 1e-12
+
+
+def test_cuda_bulkal_fcc_kpoint_properties():
+    """examples/bulkal (bulkal_kp3.i): fcc primitive cell, k = (0, 0, 1/3), 20 Ry, 20^3 grid, Al with l <= 3; the arrays are
+    pinned by the reference fixture bulkal_fcc_kpoint (parametrised tests above); here the shape the survey records
+    (ngw 153, 37 rods) and H = H^dagger on the block"""
+    g = load_golden("bulkal_fcc_kpoint")
+    assert (g["np0"], g["np1"], g["np2"]) == (20, 20, 20) and g["ngw"] == 153 and g["nrods"] == 37 and not g["is_real"]
+    assert sorted(set(int(l) for l in g["species"][0]["lproj"])) == [0, 1, 3]      # lmax 3, llocal 2
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), False)
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    ft = H.FourierTransform(b, 20, 20, 20)
+    nlp = H.NonLocalPotential(b, g["species"])
+    cd = _dev(c)
+    out = torch.zeros_like(cd)
+    H.hpsi(ft, nlp, cd, occ, _dev(v), _dev(b["kpg2"]), out)
+    m = (cd[:, :g["ngw"]].conj() @ out[:, :g["ngw"]].T).cpu().numpy()
+    assert np.abs(m - m.conj().T).max() < 1e-11 * np.abs(m).max()

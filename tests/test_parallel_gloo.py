@@ -43,7 +43,10 @@ def _worker(rank, world, port, q):
                twnl=rng.standard_normal((4, b["ngw"])), tau=rng.uniform(0, 9, (2, 3)))]
     enl, _ = P.nl_energy(b, c, occ[first:first + n], sp)
     nel_local = float(rho.sum() * b["omega"] / ft.N)          # before the in-place all-reduce (ChargeDensity.cc:525-528)
+    rho_np = rho.copy()                                        # numpy HOST array: must be summed over ranks too
+    assert PAR.allreduce_density(rho_np) is rho_np
     rho_t = PAR.allreduce_density(torch.from_numpy(rho))
+    assert np.array_equal(rho_np, rho_t.numpy())
     enl_sum, nel = PAR.allreduce_scalars([enl, nel_local])
     if rank == 0:
         call = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=3)

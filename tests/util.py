@@ -34,8 +34,15 @@ def load_golden(name):
     g["mode"] = str(g["mode"])
     g["np0"], g["np1"], g["np2"] = (int(x) for x in g["grid"])
     g["is_real"] = bool(g["is_real"])
+    def twnl(i):
+        # large tables are stored as distinct values + per-plane-wave index (tests/golden/make_golden.py): bit-exact
+        if f"sp{i}_twnl" in g:
+            return g[f"sp{i}_twnl"]
+        return g[f"sp{i}_twnl_uniq"][g[f"sp{i}_twnl_inv"]]
+
     g["species"] = [dict(na=int(g[f"sp{i}_na"]), npr=int(g[f"sp{i}_npr"]), lproj=g[f"sp{i}_lproj"], wt=g[f"sp{i}_wt"],
-                         twnl=g[f"sp{i}_twnl"], tau=g[f"sp{i}_tau"]) for i in range(g["nsp"])]
+                         twnl=twnl(i).reshape(int(g[f"sp{i}_npr"]), g["ngw"]), tau=g[f"sp{i}_tau"].reshape(-1, 3))
+                    for i in range(g["nsp"])]
     return g
 
 
