@@ -21,8 +21,9 @@ from make_golden import CASES, R, checksum  # noqa: E402
 def main():
     outdir = os.path.join(HERE, "la")
     os.makedirs(outdir, exist_ok=True)
+    only = sys.argv[1:]          # fixture names to (re)generate; default: all "full" cases
     for name, (case, seed, nocc, mode, stride) in CASES.items():
-        if mode != "full":
+        if mode != "full" or (only and name not in only):
             continue
         r = R.run_reference(case, seed=seed, nocc=nocc)
         d = dict(resid=r["resid"], resid_a=r["resid_a"], gram=r["gram"], cur=r["cur"], hpsi_checksum=checksum(r["hpsi"]))
