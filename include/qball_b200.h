@@ -139,6 +139,18 @@ long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 
 int qb200_hpsi(qb200_plan* plan, qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* v,
                const double* kpg2, double* hpsi, double* enl);
 
+/* ---- kinetic-energy sums of EnergyFunctional::energy                               EnergyFunctional.cc:1155-1296
+ *      psi2sum[ig] = sum_n w[n] |c[ig,n]|^2 with w[n] = fac * occ[n] (host array of the nst LOCAL states; fac = 1 for a real
+ *      basis, 0.5 otherwise, :1184), then the 14 partial sums of :1225-1276 over this rank's plane waves:
+ *        tsum[0] = sum psi2sum*kpg2 (ekin), tsum[1..6] = sum 2 psi2sum*(xx,yy,zz,xy,yz,xz) (sigma_ekin; only if kpgx != NULL),
+ *        tsum[7] = sum psi2sum*fstress (econf; if fstress != NULL), tsum[8..13] = sum psi2sum*dfstress*(xx,..) (if both).
+ *      kpg2 = Basis::kpg2_ptr() (ngw), kpgx = Basis::kpgx_ptr(0) (3*ngw, component-major) or NULL,
+ *      fstress/dfstress = ConfinementPotential::fstress()/dfstress() or NULL.  psi2sum (ngw doubles) may be NULL.
+ *      tsum: 14 doubles, host or device.  The k-point weight, 1/weightsum and the dsum over ranks (:1281-1294) stay with the
+ *      caller.  A host block whose coefficient tag is unchanged is not uploaded again.  Deterministic. */
+int qb200_ekin_sums(qb200_plan* plan, int ldc, int nst, const double* c, const double* w, const double* kpg2,
+                    const double* kpgx, const double* fstress, const double* dfstress, double* psi2sum, double* tsum);
+
 /* ---- TDDFT propagator glue: ExponentialWavefunctionStepper::exponential(num_exp, dt1, dt2)
  *      (ExponentialWavefunctionStepper.cc:51-149) with the Hamiltonian frozen at v (the caller updates v between the
  *      exponentials of an ETRS/AETRS step): c <- sum_{N=0..order} (-i dt1 H)^N / N! c  (order 4 in the reference, :45);

@@ -123,6 +123,15 @@ inline double density_finish(FourierTransform& vft, const double* rho, double om
   return nel;
 }
 
+// kinetic-energy section of EnergyFunctional::energy (EnergyFunctional.cc:1155-1296) for one (spin, k-point):
+// w[n] = fac * occ[c.j(lj,jj)] per local state; fills psi2sum[ngw] (may be null) and tsum[14]
+inline void ekin_sums(FourierTransform& ft, int mloc, int nstloc, const std::complex<double>* c, const double* w,
+                      const double* kpg2, const double* kpgx, const double* fstress, const double* dfstress, double* psi2sum,
+                      double* tsum)
+{
+  check(qb200_ekin_sums(ft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), w, kpg2, kpgx, fstress, dfstress, psi2sum, tsum), "qb200_ekin_sums");
+}
+
 class NonLocalPotential;
 // ExponentialWavefunctionStepper::exponential with a frozen Hamiltonian (ExponentialWavefunctionStepper.cc:51-149); see
 // qb200_exponential.  Defined after NonLocalPotential below.

@@ -1,0 +1,166 @@
+// integration/qb200_shim.cc -- compiled INTO the reference (against its own headers) when Qball is built with -DUSE_QB200.
+// Forwards the seam functions of the H psi / density path to libqball_b200.so through include/qball_b200.hpp; see
+// qb200_shim.h and INTEGRATION.md.  Host blocks (ComplexMatrix::val, std::vector grids) are passed as HOST pointers: the
+// library stages them (pipelined uploads); nothing in the reference's data ownership changes.
+#include "qb200_shim.h"
+#include <qball_b200.hpp>
+#include <qball/Basis.h>
+#include <qball/AtomSet.h>
+#include <qball/SlaterDet.h>
+#include <qball/UnitCell.h>
+#include <math/matrix.h>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+using namespace std;
+
+namespace qb200_shim {
+
+static long long forwarded_ = 0;
+long long forwarded_calls() { return forwarded_; }
+// one line at exit so that a test (or a user) can see that the device path really carried the run
+static struct ExitReport {
+  ~ExitReport() { if (forwarded_ > 0) cout << " <!-- qb200_shim: " << forwarded_ << " seam calls forwarded to the device -->" << endl; }
+} exit_report_;
+
+static int device_id()
+{
+  const char* e = getenv("QB200_DEVICE");          // one rank per GPU: the launcher sets QB200_DEVICE=<local rank>
+  return e ? atoi(e) : 0;
+}
+
+bool enabled()
+{
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("QB200_SHIM");
+    state = (e && e[0] == '0') ? 0 : 1;
+    if (state == 1 && qb200_device_count() < 1) {
+      // built for the GPU path and not switched off: fail loudly, like the reference's MPI_Abort (FourierTransform.cc:696-700)
+      cerr << " qb200_shim: no CUDA device (set QB200_SHIM=0 to run the reference's CPU path)" << endl;
+      abort();
+    }
+    if (state == 1) cout << " <!-- qb200_shim: H psi / density path forwarded to libqball_b200 (" << qb200_version() << ") -->" << endl;
+  }
+  return state == 1;
+}
+
+// ---------------------------------------------------------------------------------------------- FourierTransform
+static map<const FourierTransform*, qb200::FourierTransform*>& ft_table()
+{
+  static map<const FourierTransform*, qb200::FourierTransform*> t;
+  return t;
+}
+
+void ft_attach(const FourierTransform* key, const Basis& basis, int np0, int np1, int np2)
+{
+  if (!enabled()) return;
+  if (basis.context().nprow() != 1) {
+    cerr << " qb200_shim: the GPU path is band-parallel: set nrowmax 1 (nprow = " << basis.context().nprow() << ")" << endl;
+    abort();
+  }
+  ft_table()[key] = new qb200::FourierTransform(qb200::BasisTables::from_basis(basis), np0, np1, np2, device_id());
+}
+
+void ft_detach(const FourierTransform* key)
+{
+  map<const FourierTransform*, qb200::FourierTransform*>::iterator it = ft_table().find(key);
+  if (it == ft_table().end()) return;
+  delete it->second;
+  ft_table().erase(it);
+}
+
+qb200::FourierTransform& ft_gpu(const FourierTransform* key)
+{
+  map<const FourierTransform*, qb200::FourierTransform*>::iterator it = ft_table().find(key);
+  if (it == ft_table().end()) { cerr << " qb200_shim: FourierTransform without a device plan" << endl; abort(); }
+  return *it->second;
+}
+
+// ---------------------------------------------------------------------------------------------- SlaterDet
+void rs_mul_add(const FourierTransform& ft, const ComplexMatrix& c, int nstloc, const double* v, ComplexMatrix& cp)
+{
+  forwarded_++;
+  qb200::rs_mul_add(ft_gpu(&ft), c.mloc(), nstloc, c.cvalptr(), v, cp.valptr());
+}
+
+void compute_density(const FourierTransform& ft, const ComplexMatrix& c, int nstloc, const vector<double>& occ, double weight,
+                     double omega, double* rho)
+{
+  forwarded_++;
+  vector<double> occ_loc(nstloc > 0 ? nstloc : 1, 0.0);
+  int n = 0;
+  for (int lj = 0; lj < c.nblocks(); lj++)
+    for (int jj = 0; jj < c.nbs(lj); jj++, n++) occ_loc[n] = occ[c.j(lj, jj)];                 // SlaterDet.cc:912
+  qb200::compute_density(ft_gpu(&ft), c.mloc(), nstloc, c.cvalptr(), weight, &occ_loc[0], omega, rho);
+}
+
+// ---------------------------------------------------------------------------------------------- NonLocalPotential
+static map<const NonLocalPotential*, qb200::NonLocalPotential*>& nl_table()
+{
+  static map<const NonLocalPotential*, qb200::NonLocalPotential*> t;
+  return t;
+}
+
+void nl_invalidate(const NonLocalPotential* key)
+{
+  map<const NonLocalPotential*, qb200::NonLocalPotential*>::iterator it = nl_table().find(key);
+  if (it == nl_table().end()) return;
+  delete it->second;
+  nl_table().erase(it);
+}
+
+double nl_energy(const NonLocalPotential* key, const Basis& basis, AtomSet& atoms, int nsp, const vector<int>& na,
+                 const vector<int>& npr, const vector<vector<int> >& lproj, const vector<vector<double> >& wt,
+                 const vector<vector<double> >& twnl, SlaterDet& sd, bool compute_hpsi, SlaterDet& dsd)
+{
+  forwarded_++;
+  vector<vector<double> > tau;
+  atoms.get_positions(tau, true);                                                                // NonLocalPotential.cc:1544
+  qb200::NonLocalPotential* g = 0;
+  map<const NonLocalPotential*, qb200::NonLocalPotential*>::iterator it = nl_table().find(key);
+  if (it != nl_table().end()) g = it->second;
+  else {
+    g = new qb200::NonLocalPotential(basis.localsize(), basis.real(), basis.cell().volume(), basis.kpgx_ptr(0), device_id());
+    const UnitCell& uc = basis.cell();
+    const D3vector kp = basis.kpoint();
+    const double b[9] = { uc.b(0).x, uc.b(0).y, uc.b(0).z, uc.b(1).x, uc.b(1).y, uc.b(1).z, uc.b(2).x, uc.b(2).y, uc.b(2).z };
+    const double k[3] = { kp.x, kp.y, kp.z };
+    g->set_lattice(basis.idx_ptr(), b, k);
+    const double zero3[3] = { 0.0, 0.0, 0.0 };
+    for (int is = 0; is < nsp; is++) {          // every species keeps its index; local-only species contribute no rows
+      const bool nl = npr[is] > 0 && na[is] > 0;
+      g->add_species(nl ? na[is] : 0, nl ? npr[is] : 0, nl ? &lproj[is][0] : 0, nl ? &wt[is][0] : 0, nl ? &twnl[is][0] : 0,
+                     nl ? &tau[is][0] : zero3);
+    }
+    nl_table()[key] = g;
+  }
+  for (int is = 0; is < nsp; is++)
+    if (npr[is] > 0 && na[is] > 0) g->set_positions(is, &tau[is][0]);                            // atoms may have moved
+  const ComplexMatrix& c = sd.c();
+  const vector<double>& occ = sd.occ();
+  vector<double> occ_loc(sd.nstloc() > 0 ? sd.nstloc() : 1, 0.0);
+  int n = 0;
+  for (int lj = 0; lj < c.nblocks(); lj++)
+    for (int jj = 0; jj < c.nbs(lj); jj++, n++) occ_loc[n] = occ[c.j(lj, jj)];                 // NonLocalPotential.cc:2115
+  return g->energy(c.mloc(), sd.nstloc(), c.cvalptr(), &occ_loc[0], compute_hpsi, compute_hpsi ? dsd.c().valptr() : 0);
+}
+
+// ---------------------------------------------------------------------------------------------- EnergyFunctional (ekin)
+bool psi2sum(const FourierTransform* ft, const ComplexMatrix& c, const double* occ_global, double fac, const double* kpg2,
+             vector<double>& out)
+{
+  if (!enabled() || !ft) return false;
+  forwarded_++;
+  const int nloc = c.nloc();
+  vector<double> w(nloc > 0 ? nloc : 1, 0.0);
+  int n = 0;
+  for (int lj = 0; lj < c.nblocks(); lj++)
+    for (int jj = 0; jj < c.nbs(lj); jj++, n++) w[n] = fac * occ_global[c.j(lj, jj)];           // EnergyFunctional.cc:1214-1221
+  double tsum[14];
+  qb200::ekin_sums(ft_gpu(ft), c.mloc(), nloc, c.cvalptr(), &w[0], kpg2, 0, 0, 0, &out[0], tsum);
+  return true;
+}
+
+}  // namespace qb200_shim

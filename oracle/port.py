@@ -56,6 +56,7 @@ def lib():
         L.qbo_rs_mul_add.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
         L.qbo_compute_density.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp]
         L.qbo_kinetic_add.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_ekin_sums.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]
         L.qbo_nl_energy_species.restype = C.c_double
         L.qbo_nl_energy_species.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp,
                                             dp, C.c_double, C.c_int, C.c_int, dp]
@@ -169,6 +170,17 @@ def kinetic_add(kpg2, c, cp):
     nst, ldc = c.shape
     lib().qbo_kinetic_add(kpg2.shape[0], ldc, nst, _d(np.ascontiguousarray(kpg2)), _d(c), _d(cp))
     return cp
+
+
+def ekin_sums(kpg2, c, occ, is_real, kpgx=None, fstress=None, dfstress=None):
+    """EnergyFunctional.cc:1155-1296 for one (spin, k-point): returns (tsum[14], psi2sum[ngw])"""
+    nst, ldc = c.shape
+    ngw = kpg2.shape[0]
+    tsum, p2 = np.zeros(14), np.zeros(ngw)
+    opt = lambda a: None if a is None else _d(np.ascontiguousarray(a, dtype=np.float64))  # noqa: E731
+    lib().qbo_ekin_sums(ngw, ldc, nst, _d(c), _d(np.ascontiguousarray(occ, dtype=np.float64)), C.c_double(1.0 if is_real else 0.5),
+                        _d(np.ascontiguousarray(kpg2)), opt(kpgx), opt(fstress), opt(dfstress), _d(p2), _d(tsum))
+    return tsum, p2
 
 
 def nl_energy(b: dict, c, occ, species, compute_hpsi=True, cp=None):

@@ -494,6 +494,38 @@ void qbo_kinetic_add(int ngw, int ldc, int nst, const double* kpg2, const double
     }
 }
 
+/* kinetic-energy section of EnergyFunctional::energy (EnergyFunctional.cc:1155-1296) for one (spin, k-point):
+ * psi2sum[ig] = fac * sum_n occ[n] |c[ig,n]|^2 (:1209-1223), then the 14 partial sums tsum[] of :1225-1276 (the stress
+ * sums only if kpgx != NULL, the confinement sums only if fstress / dfstress != NULL).  Same loop order as the reference. */
+void qbo_ekin_sums(int ngw, int ldc, int nst, const double* c, const double* occ, double fac, const double* kpg2,
+                   const double* kpgx, const double* fstress, const double* dfstress, double* psi2sum, double* tsum)
+{
+  for (int ig = 0; ig < ngw; ig++) psi2sum[ig] = 0.0;
+  for (int n = 0; n < nst; n++)
+    for (int ig = 0; ig < ngw; ig++) {
+      const double re = c[2*((size_t)n*ldc + ig)], im = c[2*((size_t)n*ldc + ig)+1];
+      psi2sum[ig] += fac * occ[n] * (re*re + im*im);                                     /* :1219-1221 */
+    }
+  for (int k = 0; k < 14; k++) tsum[k] = 0.0;
+  for (int ig = 0; ig < ngw; ig++) {
+    const double p2 = psi2sum[ig];
+    tsum[0] += p2 * kpg2[ig];                                                            /* :1230 */
+    if (kpgx) {
+      const double x = kpgx[ig], y = kpgx[ngw + ig], z = kpgx[2*(size_t)ngw + ig], f = 2.0 * p2;   /* :1232-1247 */
+      tsum[1] += f*x*x; tsum[2] += f*y*y; tsum[3] += f*z*z; tsum[4] += f*x*y; tsum[5] += f*y*z; tsum[6] += f*x*z;
+    }
+  }
+  if (fstress)
+    for (int ig = 0; ig < ngw; ig++) {
+      const double p2 = psi2sum[ig];
+      tsum[7] += p2 * fstress[ig];                                                       /* :1258 */
+      if (kpgx && dfstress) {
+        const double x = kpgx[ig], y = kpgx[ngw + ig], z = kpgx[2*(size_t)ngw + ig], f = p2 * dfstress[ig];  /* :1260-1273 */
+        tsum[8] += f*x*x; tsum[9] += f*y*y; tsum[10] += f*z*z; tsum[11] += f*x*y; tsum[12] += f*y*z; tsum[13] += f*x*z;
+      }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ NonLocalPotential */
 double qbo_nl_energy_species(int ngw, int ldc, int nst, const double* c, const double* occ, int is_real, int na, int npr,
                              const int* lproj, const double* wt, const double* twnl, const double* tau,

@@ -71,6 +71,8 @@ def load():
     L.qb200_la_query.restype = ll
     L.qb200_residual.argtypes = [vp, i, i, dp, i, dp, dp]
     L.qb200_gram.argtypes = [vp, i, i, dp, ip]
+    L.qb200_ekin_sums.argtypes = [vp, i, i, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.qb200_ekin_sums.restype = i
     L.qb200_measure_fp64_peak.argtypes = [i, C.POINTER(d)]
     L.qb200_measure_fp64_peak.restype = i
     L.qb200_profile_enable.argtypes = [i]

@@ -302,3 +302,118 @@ extern "C" int qb200_compute_current(qb200_plan* p, int ldc, int nst, const doub
   if (curhost || chost) QB_CUDA(cudaStreamSynchronize(p->stream));
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ kinetic energy sums (K22)
+// EnergyFunctional::energy, "kinetic energy" section (/root/reference/src/qball/EnergyFunctional.cc:1155-1296):
+//   psi2sum[ig] = sum_n w[n] |c[ig,n]|^2                  (:1209-1223; w[n] = fac * occ[n], fac = 1 real basis / 0.5 complex)
+//   tsum[0]     = sum_ig psi2sum * kpg2                   (:1230)          -> ekin
+//   tsum[1..6]  = sum_ig 2 psi2sum * (xx, yy, zz, xy, yz, xz) of k+G       (:1232-1247, compute_stress)
+//   tsum[7]     = sum_ig psi2sum * fstress                (:1258)          -> econf
+//   tsum[8..13] = sum_ig psi2sum * dfstress * (xx, yy, zz, xy, yz, xz)     (:1260-1273)
+// One pass over the block (HBM-bound: 16 ldc nst bytes), states summed in index order per plane wave, then one CTA
+// reduces the 14 weighted sums in a fixed order: deterministic.  The k-point weight, the division by weightsum and the
+// dsum over ranks (:1281-1294) stay with the caller (qb200_allreduce_scalars).
+__global__ void __launch_bounds__(256) k_psi2sum(const double2* __restrict__ c, size_t ldc, int ngw, int nst, const double* __restrict__ w,
+                                                 double* __restrict__ psi2sum)
+{
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= ngw) return;
+  double s = 0.0;
+  const double2* p = c + ig;
+#pragma unroll 4
+  for (int n = 0; n < nst; n++) {
+    const double2 a = p[(size_t)n * ldc];
+    s += w[n] * (a.x * a.x + a.y * a.y);
+  }
+  psi2sum[ig] = s;
+}
+
+__global__ void __launch_bounds__(1024) k_ekin_sums(const double* __restrict__ psi2sum, int ngw, const double* __restrict__ kpg2,
+                                                    const double* __restrict__ kpgx, const double* __restrict__ fstress,
+                                                    const double* __restrict__ dfstress, double* __restrict__ tsum)
+{
+  __shared__ double red[1024];
+  double t[14];
+#pragma unroll
+  for (int k = 0; k < 14; k++) t[k] = 0.0;
+  for (int ig = threadIdx.x; ig < ngw; ig += 1024) {
+    const double p2 = psi2sum[ig];
+    t[0] += p2 * kpg2[ig];
+    double xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
+    if (kpgx) {
+      const double x = kpgx[ig], y = kpgx[ngw + ig], z = kpgx[2 * (size_t)ngw + ig];
+      xx = x * x; yy = y * y; zz = z * z; xy = x * y; yz = y * z; xz = x * z;
+      const double f = 2.0 * p2;
+      t[1] += f * xx; t[2] += f * yy; t[3] += f * zz; t[4] += f * xy; t[5] += f * yz; t[6] += f * xz;
+    }
+    if (fstress) t[7] += p2 * fstress[ig];
+    if (kpgx && dfstress) {
+      const double f = p2 * dfstress[ig];
+      t[8] += f * xx; t[9] += f * yy; t[10] += f * zz; t[11] += f * xy; t[12] += f * yz; t[13] += f * xz;
+    }
+  }
+  for (int k = 0; k < 14; k++) {
+    red[threadIdx.x] = t[k];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) tsum[k] = red[0];
+    __syncthreads();
+  }
+}
+
+extern "C" int qb200_ekin_sums(qb200_plan* p, int ldc, int nst, const double* c, const double* w, const double* kpg2,
+                               const double* kpgx, const double* fstress, const double* dfstress, double* psi2sum, double* tsum)
+{
+  if (!p || !c || !w || !kpg2 || !tsum || nst < 0 || ldc < p->d.ngw) { set_error("qb200_ekin_sums: bad argument"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(p->device));
+  const int ngw = p->d.ngw;
+  const size_t blk = 2 * (size_t)ldc * nst;
+  int rc;
+  for (int k = 0; k < 14; k++) tsum[k] = 0.0;
+  if (nst == 0) { if (psi2sum && !is_device_ptr(psi2sum)) for (int i = 0; i < ngw; i++) psi2sum[i] = 0.0; return QB200_OK; }
+  // device views: c (resident copy reused under an unchanged coefficient tag), the per-plane-wave tables, the weights
+  const double* cd = c;
+  if (!is_device_ptr(c)) {
+    if ((rc = ensure_buf(&p->st_c, &p->st_c_cap, blk))) return rc;
+    if (!plan_resident(p, c, ldc, nst)) {
+      p->res_ptr = nullptr;
+      QB_CUDA(cudaMemcpyAsync(p->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      plan_mark_resident(p, c, ldc, nst);
+    }
+    cd = p->st_c;
+  }
+  // work: psi2sum[ngw] | tsum[14] | w[nst] | host tables staged behind (kpg2, kpgx[3], fstress, dfstress as needed)
+  const bool hk = !is_device_ptr(kpg2), hx = kpgx && !is_device_ptr(kpgx), hf = fstress && !is_device_ptr(fstress),
+             hd = dfstress && !is_device_ptr(dfstress);
+  const size_t need = (size_t)ngw + 16 + nst + (size_t)ngw * ((hk ? 1 : 0) + (hx ? 3 : 0) + (hf ? 1 : 0) + (hd ? 1 : 0));
+  if ((rc = ensure_buf(&p->st_f, &p->st_f_cap, need))) return rc;
+  double* ps = p->st_f;
+  double* ts = ps + ngw;
+  double* wd = ts + 16;
+  double* nxt = wd + nst;
+  auto stage = [&](const double* h, size_t n, bool host, const double** dptr) -> int {
+    if (!h) { *dptr = nullptr; return QB200_OK; }
+    if (!host) { *dptr = h; return QB200_OK; }
+    QB_CUDA(cudaMemcpyAsync(nxt, h, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    *dptr = nxt; nxt += n;
+    return QB200_OK;
+  };
+  const double *kd, *xd, *fd, *dd;
+  if ((rc = stage(kpg2, ngw, hk, &kd)) || (rc = stage(kpgx, 3 * (size_t)ngw, hx, &xd)) || (rc = stage(fstress, ngw, hf, &fd)) ||
+      (rc = stage(dfstress, ngw, hd, &dd))) return rc;
+  QB_CUDA(cudaMemcpyAsync(wd, w, nst * sizeof(double), cudaMemcpyDefault, p->stream));
+  k_psi2sum<<<(ngw + 255) / 256, 256, 0, p->stream>>>((const double2*)cd, (size_t)ldc, ngw, nst, wd, ps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_psi2sum launch", __FILE__, __LINE__);
+  k_ekin_sums<<<1, 1024, 0, p->stream>>>(ps, ngw, kd, xd, fd, dd, ts);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_ekin_sums launch", __FILE__, __LINE__);
+  p->launches += 2;
+  QB_CUDA(cudaMemcpyAsync(tsum, ts, 14 * sizeof(double), cudaMemcpyDefault, p->stream));
+  if (psi2sum) QB_CUDA(cudaMemcpyAsync(psi2sum, ps, ngw * sizeof(double), cudaMemcpyDefault, p->stream));
+  QB_CUDA(cudaStreamSynchronize(p->stream));
+  return QB200_OK;
+}

@@ -242,6 +242,20 @@ def hpsi(ft: FourierTransform, nlp, c, occ, v, kpg2, out) -> float:
     return enl.value
 
 
+def ekin_sums(ft: FourierTransform, c, occ, is_real: bool, kpg2, kpgx=None, fstress=None, dfstress=None, want_psi2sum=False):
+    """the kinetic-energy section of EnergyFunctional::energy (EnergyFunctional.cc:1155-1296) for one (spin, k-point):
+    returns tsum[14] (tsum[0] = ekin partial before the k-point weight, tsum[7] = econf, the rest the stress sums) and,
+    optionally, psi2sum[ngw].  fac = 1 for a real basis (G and -G), 0.5 otherwise (:1184)."""
+    nst, ldc = _block_dims(c)
+    w = np.ascontiguousarray((1.0 if is_real else 0.5) * np.asarray(occ, dtype=np.float64))
+    assert w.shape[0] == nst
+    tsum = np.zeros(14)
+    p2 = np.zeros(ft.ngw()) if want_psi2sum else None
+    capi._check(ft._L.qb200_ekin_sums(ft._h, ldc, nst, capi.ptr(c), capi.ptr(w), capi.ptr(kpg2), capi.ptr(kpgx), capi.ptr(fstress),
+                                      capi.ptr(dfstress), capi.ptr(p2), capi.ptr(tsum)), "qb200_ekin_sums")
+    return (tsum, p2) if want_psi2sum else tsum
+
+
 def exponential(ft: FourierTransform, nlp, c, occ, v, kpg2, dt1: float, dt2: float = 0.0, c2=None, order: int = 4):
     """ExponentialWavefunctionStepper::exponential(num_exp, dt1, dt2) with a frozen Hamiltonian
     (ExponentialWavefunctionStepper.cc:51-149): c <- sum_N (-i dt1 H)^N/N! c in place; c2 (optional) <- the dt2 series."""

@@ -646,3 +646,34 @@ def test_cuda_bulkal_fcc_kpoint_properties():
     H.hpsi(ft, nlp, cd, occ, _dev(v), _dev(b["kpg2"]), out)
     m = (cd[:, :g["ngw"]].conj() @ out[:, :g["ngw"]].T).cpu().numpy()
     assert np.abs(m - m.conj().T).max() < 1e-11 * np.abs(m).max()
+
+
+@pytest.mark.parametrize("kpoint,fc,host", [((0, 0, 0), False, False), ((0.1, 0.2, 0.3), False, True), ((0, 0, 0), True, False)])
+def test_cuda_ekin_sums_vs_oracle(kpoint, fc, host):
+    """kinetic-energy section of EnergyFunctional::energy (EnergyFunctional.cc:1155-1296): psi2sum and the 14 partial sums
+    (ekin, sigma_ekin, econf, sigma_econf) against the oracle's loop-for-loop restatement; trace(sigma_ekin sums) = 2 ekin"""
+    cell, ecut, nst = (10, 0, 0, 0.5, 11, 0, 0, 0, 12), 6.0, 37
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    grid = P.density_grid(cell, ecut)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 3, b["is_real"], seed=81)
+    occ = R.synth_occ(nst, nst - 4)
+    rng = np.random.default_rng(82)
+    fstress, dfstress = rng.uniform(0, 1, ngw), rng.uniform(-1, 1, ngw)
+    ft = H.FourierTransform(b, *grid)
+    w = (lambda a: np.ascontiguousarray(a)) if host else _dev
+    t_ref, p2_ref = P.ekin_sums(b["kpg2"], c, occ, b["is_real"], kpgx=b["kpgx"], fstress=fstress, dfstress=dfstress)
+    t, p2 = H.ekin_sums(ft, w(c), occ, b["is_real"], w(b["kpg2"]), w(b["kpgx"]), w(fstress), w(dfstress), want_psi2sum=True)
+    assert relerr(p2, p2_ref) < 1e-13
+    assert np.abs(t - t_ref).max() < 1e-12 * np.abs(t_ref).max(), (t, t_ref)
+    assert abs(t[1] + t[2] + t[3] - 2.0 * t[0]) < 1e-12 * abs(t[0])
+    # energy only: no stress / confinement tables
+    t0 = H.ekin_sums(ft, w(c), occ, b["is_real"], w(b["kpg2"]))
+    assert abs(t0[0] - t_ref[0]) < 1e-12 * abs(t_ref[0]) and np.all(t0[1:] == 0.0)
+    # E_kin of the block equals the kinetic part of sum_n occ_n <psi_n|H psi_n> (real basis: G and -G)
+    kin = np.zeros_like(c)
+    P.kinetic_add(b["kpg2"], c, kin)
+    e = np.einsum("ng,ng->n", c[:, :ngw].conj(), kin[:, :ngw]).real
+    if b["is_real"]:
+        e = 2.0 * e - (c[:, 0].conj() * kin[:, 0]).real
+    assert abs(t0[0] - float(np.dot(occ, e))) < 1e-12 * abs(t0[0])
