@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "hpsi_density_state_applies_per_s", "state-applies/s"
+_COMM = {}               # the process's qb200 communicator (N > 1), shared by the sub-records
 _FP64_PEAK = {}          # device index -> (DMMA TFLOP/s, DFMA TFLOP/s), measured once per process
 
 WORKLOADS = {
@@ -401,15 +402,20 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
         scal = torch.zeros(2, dtype=torch.float64, device=dev)
     omega = b["omega"]
 
+    # N > 1: the collectives of the C ABI itself (NCCL inside libqball_b200.so; torch.distributed is only the rendezvous)
+    comm = _COMM.get("comm")
+    if world > 1 and comm is None:
+        from qball_b200 import parallel as PAR
+        comm = _COMM["comm"] = PAR.Communicator.from_torch_distributed(local_rank)
+
     def step():
         with torch.cuda.stream(stream):
             enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
             rho.zero_()
             H.compute_density(ft, c, 1.0, occ, omega, rho)
             if world > 1:
-                scal[0] = enl
-                dist.all_reduce(rho)          # ChargeDensity.cc:309 dsum('r') over state columns
-                dist.all_reduce(scal)         # NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519
+                comm.allreduce_rho(rho, stream)              # ChargeDensity.cc:309 dsum('r') over state columns
+                enl = comm.allreduce_scalars([enl])[0]       # NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519
         return enl
 
     def sync_all():

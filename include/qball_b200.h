@@ -204,6 +204,25 @@ int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info);
 int qb200_profile_enable(int on);
 int qb200_profile_read(double* ms, long long* count, int ncat);
 
+/* ---- the path's collectives over the GPUs of one box (band parallelism, nprow = 1, one rank per GPU), NCCL inside:
+ *      qb200_allreduce_rho      replaces  wfcontext->dsum('r', np012loc, 1, &rhor[ispin][0], np012loc)      ChargeDensity.cc:309
+ *      qb200_allreduce_scalars  replaces  ctxt_.dsum('r',1,1,&enl,1)   NonLocalPotential.cc:2629,
+ *                                         wfcontext()->dsum(14,1,&sum[0],14)  EnergyFunctional.cc:1294 and the nelectrons
+ *                                         dsum of ChargeDensity.cc:528 (pack them into one call: {E_nl, tsum[14], integral of rho})
+ *      Setup: rank 0 calls qb200_comm_get_unique_id, the caller broadcasts the 128 bytes out of band (MPI_Bcast over the
+ *      reference's own communicator), every rank calls qb200_comm_init(device = its GPU, id, rank, nranks).
+ *      rho: n doubles, DEVICE pointer (summed in place, enqueued on `stream` like a kernel launch) or HOST pointer (staged,
+ *      synchronous).  vals: a short HOST array.  NCCL is loaded at run time (libnccl.so.2); without it these calls return
+ *      QB200_EUNSUPPORTED and everything else keeps working. */
+#define QB200_UNIQUE_ID_BYTES 128
+typedef struct qb200_comm qb200_comm;
+int qb200_comm_get_unique_id(void* id /* QB200_UNIQUE_ID_BYTES */);
+int qb200_comm_init(qb200_comm** comm, int device, const void* id, int rank, int nranks);
+int qb200_comm_destroy(qb200_comm* comm);
+long long qb200_comm_query(const qb200_comm* comm, int what);   /* 0 rank, 1 nranks, 2 NCCL version code */
+int qb200_allreduce_rho(qb200_comm* comm, double* rho, long long n, void* cuda_stream);
+int qb200_allreduce_scalars(qb200_comm* comm, double* vals, int n);
+
 /* ---- device self-measurement for the FP64 roofline denominator (bench.py): out[0] = FP64 tensor (DMMA, mma.sync.m8n8k4.f64)
  *      TFLOP/s, out[1] = plain DFMA TFLOP/s, issue-rate loops on every SM of `device` (~50 ms).  The reference has no
  *      counterpart; MEASURED_PEAKS.json carries no FP64 figure. */

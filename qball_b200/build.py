@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libqball_b200.so")
-SOURCES = ["transform.cu", "plane.cu", "nonlocal.cu", "hpsi.cu", "diag.cu"]
+SOURCES = ["transform.cu", "plane.cu", "nonlocal.cu", "hpsi.cu", "diag.cu", "comm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(r.stdout + r.stderr)
     if failed:
         raise RuntimeError(f"nvcc failed; see {log}")
-    cmd = [nvcc, "-shared", "-o", LIB] + [o for _, o, _, _ in results] + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB] + [o for _, o, _, _ in results] + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, "a") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

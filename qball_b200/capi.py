@@ -73,6 +73,15 @@ def load():
     L.qb200_gram.argtypes = [vp, i, i, dp, ip]
     L.qb200_ekin_sums.argtypes = [vp, i, i, dp, dp, dp, dp, dp, dp, dp, dp]
     L.qb200_ekin_sums.restype = i
+    L.qb200_comm_get_unique_id.argtypes = [vp]
+    L.qb200_comm_init.argtypes = [C.POINTER(vp), i, vp, i, i]
+    L.qb200_comm_destroy.argtypes = [vp]
+    L.qb200_comm_query.argtypes = [vp, i]
+    L.qb200_comm_query.restype = ll
+    L.qb200_allreduce_rho.argtypes = [vp, dp, ll, vp]
+    L.qb200_allreduce_scalars.argtypes = [vp, dp, i]
+    for name in ("qb200_comm_get_unique_id", "qb200_comm_init", "qb200_comm_destroy", "qb200_allreduce_rho", "qb200_allreduce_scalars"):
+        getattr(L, name).restype = i
     L.qb200_measure_fp64_peak.argtypes = [i, C.POINTER(d)]
     L.qb200_measure_fp64_peak.restype = i
     L.qb200_profile_enable.argtypes = [i]

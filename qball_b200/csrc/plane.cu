@@ -2,6 +2,7 @@
 // Own translation unit: the __noinline__ radix passes are shared by all kernels of a translation unit and compiled
 // for the tightest register budget among them; here that is 65536/448 = 144 registers (128 elsewhere).
 #include "plane_static.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace qb200 {
@@ -59,8 +60,10 @@ template <class K> static int opt_in(K kernel, int bytes)
 
 int plane_opt_in(qb200_plan* p)
 {
-  const int bytes = (int)p->smem_plane;
-  if (bytes <= 48 * 1024) return QB200_OK;
+  if ((int)p->smem_plane <= 48 * 1024) return QB200_OK;
+  // per-kernel attribute shared by every plan of the process (wavefunction basis, density basis, ...): always the device
+  // maximum, so that a later plan with a smaller plane cannot undercut an earlier one
+  const int bytes = std::max((int)p->smem_plane, p->max_smem);
   if (p->static_shape == 1) {
     int rc;
     if ((rc = opt_in(k_plane_s<OP_HPSI, ShapeMgO216>, bytes)) || (rc = opt_in(k_plane_s<OP_DENSITY, ShapeMgO216>, bytes)) ||

@@ -131,9 +131,16 @@ void plan_mark_resident(qb200_plan* p, const void* c, int ldc, int nst)
   p->res_ptr = c; p->res_ldc = ldc; p->res_nst = nst; p->res_tag = p->next_tag;
 }
 
+// The attribute is per KERNEL, not per plan: two plans of one process (the wavefunction basis and the density basis of the
+// same run) need different amounts for the same kernel, and the later, smaller request would undercut the earlier plan's
+// launches ("invalid argument").  So every opt-in asks for the device's maximum; a launch still takes only what it needs.
 template <class K> static int opt_in_smem(K kernel, size_t bytes)
 {
-  if (bytes > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (bytes <= 48 * 1024) return QB200_OK;
+  int dev = 0, mx = 0;
+  QB_CUDA(cudaGetDevice(&dev));
+  QB_CUDA(cudaDeviceGetAttribute(&mx, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(mx, (int)bytes)));
   return QB200_OK;
 }
 

@@ -64,3 +64,68 @@ def allgather_states(c_local: torch.Tensor, nst: int, group=None) -> torch.Tenso
     # complex tensors travel as their (re, im) doubles
     dist.all_gather_into_tensor(torch.view_as_real(out), torch.view_as_real(send.contiguous()), group=group)
     return out[:nst]
+
+
+class Communicator:
+    """qb200_comm: the NCCL communicator INSIDE libqball_b200.so (include/qball_b200.h, "collectives"), the object a C++
+    caller gets.  The 128-byte unique id is produced by rank 0 and handed to the other ranks out of band -- here through
+    torch.distributed's object broadcast (the reference would MPI_Bcast it over its own communicator)."""
+
+    def __init__(self, device: int, rank: int, nranks: int, unique_id: bytes):
+        import ctypes as C
+        from . import capi
+        self._L = capi.load()
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        h = C.c_void_p()
+        capi._check(self._L.qb200_comm_init(C.byref(h), int(device), C.cast(buf, C.c_void_p), int(rank), int(nranks)), "qb200_comm_init")
+        self._h, self.rank, self.nranks = h, rank, nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import capi
+        buf = C.create_string_buffer(128)
+        capi._check(capi.load().qb200_comm_get_unique_id(C.cast(buf, C.c_void_p)), "qb200_comm_get_unique_id")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None):
+        """one communicator over the ranks of an initialised torch.distributed group (rank 0's id broadcast as an object)"""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(device, rank, world, box[0])
+
+    def nccl_version(self) -> int:
+        return int(self._L.qb200_comm_query(self._h, 2))
+
+    def allreduce_rho(self, rho, stream=None):
+        """ChargeDensity.cc:309: sum of rho(r) over the state-column ranks, in place; device tensor (asynchronous on `stream`,
+        default: torch's current stream) or host numpy array (staged, synchronous)"""
+        from . import capi
+        n = int(rho.numel()) if hasattr(rho, "numel") else int(rho.size)
+        s = 0
+        if hasattr(rho, "is_cuda") and rho.is_cuda:
+            st = stream if stream is not None else torch.cuda.current_stream(rho.device)
+            s = st.cuda_stream if hasattr(st, "cuda_stream") else int(st)
+        capi._check(self._L.qb200_allreduce_rho(self._h, capi.ptr(rho), n, s), "qb200_allreduce_rho")
+        return rho
+
+    def allreduce_scalars(self, values):
+        """NonLocalPotential.cc:2629 / EnergyFunctional.cc:1294 / ChargeDensity.cc:528: one small sum over the ranks"""
+        from . import capi
+        a = np.ascontiguousarray(np.array(list(values), dtype=np.float64))
+        capi._check(self._L.qb200_allreduce_scalars(self._h, capi.ptr(a), int(a.size)), "qb200_allreduce_scalars")
+        return [float(x) for x in a]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qb200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -677,3 +677,27 @@ def test_cuda_ekin_sums_vs_oracle(kpoint, fc, host):
     if b["is_real"]:
         e = 2.0 * e - (c[:, 0].conj() * kin[:, 0]).real
     assert abs(t0[0] - float(np.dot(occ, e))) < 1e-12 * abs(t0[0])
+
+
+def test_cuda_plans_of_different_shared_memory_need_coexist():
+    """regression (found by running the reference itself through the shim, examples/sih4): the wavefunction plan and the
+    density-basis plan of one run share the plane kernels but need different amounts of dynamic shared memory; the
+    opt-in is per kernel, so the plan created LATER (smaller need) must not undercut launches of the earlier one"""
+    cell, ecut = (14, 0, 0, 0, 14, 0, 0, 0, 14), 18.0
+    b = P.make_basis(cell, ecut, (0, 0, 0), False)
+    vb = P.make_basis(cell, 4.0 * ecut, (0, 0, 0), False)
+    grid = P.density_grid(cell, ecut)
+    assert grid == (60, 60, 60)
+    N = 60 ** 3
+    vft = H.FourierTransform(vb, *grid)          # larger column table in shared memory
+    ft = H.FourierTransform(b, *grid)            # created second, needs less
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal(N) + 0j
+    want = P.FT(vb, *grid).forward(f.copy())
+    got = np.zeros(vb["ngw"], dtype=np.complex128)
+    vft.forward(f.copy(), got)
+    assert relerr(got, want) < TOL
+    c = R.synth_coefficients(b["kpg2"], ecut, 2, b["ngw"], True, seed=3)
+    fr = np.zeros(N, dtype=np.complex128)
+    ft.backward(np.ascontiguousarray(c[0, :b["ngw"]]), fr)
+    assert relerr(fr, P.FT(b, *grid).backward(np.ascontiguousarray(c[0, :b["ngw"]]))) < TOL
