@@ -223,6 +223,21 @@ long long qb200_comm_query(const qb200_comm* comm, int what);   /* 0 rank, 1 nra
 int qb200_allreduce_rho(qb200_comm* comm, double* rho, long long n, void* cuda_stream);
 int qb200_allreduce_scalars(qb200_comm* comm, double* vals, int n);
 
+/* ---- the rest of PSDAWavefunctionStepper::update after the descent direction (qb200_residual), so that the wavefunction
+ *      block stays on the device between two H psi evaluations          PSDAWavefunctionStepper.cc:93-225 (real), :281-395
+ *      with Preconditioner::apply(sd, ispin, ikp, -1.0)                   Preconditioner.cc:118-139
+ *        dc[ig,n] *= -precdiag[ig] (ig < ngw; precdiag = Preconditioner::diag(ispin, ikp), Preconditioner.cc:47-90)
+ *        extrapolate != 0 (every call but the first after a reset, extrapolate_[ispin][ikp]):
+ *          a = sum occ_n f (f - f_last), b = sum occ_n (f - f_last)^2 over the local columns (real basis: G and -G counted,
+ *          G = 0 once), summed over the ranks of `comm` (may be NULL: one rank); theta = -a/b; theta < -1 -> 0; min(2, theta)
+ *          c <- c + theta (c - c_last) + f + theta (f - f_last)
+ *        extrapolate == 0: c <- c + f.        In both cases c_last <- old c, dc_last <- f.
+ *      c, dc, c_last, dc_last: ldc x nst DEVICE blocks (wf_, dwf, wf_last_, dwf_last_); occ: host, the nst local occupations;
+ *      precdiag: ngw doubles, host or device.  *theta (may be NULL) receives -a/b before clipping (the value the reference
+ *      prints).  The orthogonalisation that follows in the reference (SlaterDet::gram) is qb200_gram. */
+int qb200_psda_update(qb200_la* la, qb200_comm* comm, int ldc, int nst, double* c, double* dc, double* c_last, double* dc_last,
+                      const double* occ, const double* precdiag, int extrapolate, double* theta);
+
 /* ---- device self-measurement for the FP64 roofline denominator (bench.py): out[0] = FP64 tensor (DMMA, mma.sync.m8n8k4.f64)
  *      TFLOP/s, out[1] = plain DFMA TFLOP/s, issue-rate loops on every SM of `device` (~50 ms).  The reference has no
  *      counterpart; MEASURED_PEAKS.json carries no FP64 figure. */

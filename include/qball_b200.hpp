@@ -202,6 +202,17 @@ class SubspaceLA {
   // SlaterDet::gram(): c <- c L^-H with c^H c = L L^H.  A singular overlap aborts like the reference's potrf.
   void gram(int mloc, int n, std::complex<double>* c)
   { int info = 0; check(qb200_gram(la_, mloc, n, reinterpret_cast<double*>(c), &info), "qb200_gram"); }
+  // the rest of PSDAWavefunctionStepper::update on device-resident blocks (see qb200_psda_update); returns theta (unclipped)
+  double psda_update(qb200_comm* comm, int mloc, int nstloc, std::complex<double>* c, std::complex<double>* dc,
+                     std::complex<double>* c_last, std::complex<double>* dc_last, const double* occ_local, const double* precdiag,
+                     bool extrapolate)
+  {
+    double theta = 0.0;
+    check(qb200_psda_update(la_, comm, mloc, nstloc, reinterpret_cast<double*>(c), reinterpret_cast<double*>(dc),
+                            reinterpret_cast<double*>(c_last), reinterpret_cast<double*>(dc_last), occ_local, precdiag,
+                            extrapolate ? 1 : 0, &theta), "qb200_psda_update");
+    return theta;
+  }
   qb200_la* handle() const { return la_; }
 
  private:

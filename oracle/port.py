@@ -56,6 +56,8 @@ def lib():
         L.qbo_rs_mul_add.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
         L.qbo_compute_density.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp]
         L.qbo_kinetic_add.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+        L.qbo_psda_update.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int]
+        L.qbo_psda_update.restype = C.c_double
         L.qbo_ekin_sums.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]
         L.qbo_nl_energy_species.restype = C.c_double
         L.qbo_nl_energy_species.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp,
@@ -181,6 +183,21 @@ def ekin_sums(kpg2, c, occ, is_real, kpgx=None, fstress=None, dfstress=None):
     lib().qbo_ekin_sums(ngw, ldc, nst, _d(c), _d(np.ascontiguousarray(occ, dtype=np.float64)), C.c_double(1.0 if is_real else 0.5),
                         _d(np.ascontiguousarray(kpg2)), opt(kpgx), opt(fstress), opt(dfstress), _d(p2), _d(tsum))
     return tsum, p2
+
+
+def preconditioner_diag(kpg2, ecutprec, fstress=None):
+    """Preconditioner::update (Preconditioner.cc:47-90): diag[ig] = 0.5/max(e, ecutprec), e = 0.5 (|k+G|^2 [+ fstress])"""
+    e = 0.5 * (kpg2 + (0.0 if fstress is None else fstress))
+    return np.where(e < ecutprec, 0.5 / ecutprec, 0.5 / np.maximum(e, 1e-300))
+
+
+def psda_update(ngw, is_real, c, dc, c_last, dc_last, occ, precdiag, extrapolate):
+    """in place; returns theta before clipping"""
+    nst, ldc = c.shape
+    L = lib()
+    L.qbo_psda_update.restype = C.c_double
+    return float(L.qbo_psda_update(ngw, ldc, nst, int(is_real), _d(c), _d(dc), _d(c_last), _d(dc_last),
+                                   _d(np.ascontiguousarray(occ, dtype=np.float64)), _d(np.ascontiguousarray(precdiag)), int(extrapolate)))
 
 
 def nl_energy(b: dict, c, occ, species, compute_hpsi=True, cp=None):

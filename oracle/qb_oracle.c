@@ -526,6 +526,54 @@ void qbo_ekin_sums(int ngw, int ldc, int nst, const double* c, const double* occ
     }
 }
 
+/* PSDAWavefunctionStepper::update after the descent direction (PSDAWavefunctionStepper.cc:93-225 real, :281-395 complex)
+ * with Preconditioner::apply(sd, ispin, ikp, -1.0) (Preconditioner.cc:118-139), one rank.  Returns theta before clipping. */
+double qbo_psda_update(int ngw, int ldc, int nst, int is_real, double* c, double* dc, double* c_last, double* dc_last,
+                       const double* occ, const double* precdiag, int extrapolate)
+{
+  for (int n = 0; n < nst; n++)                                                    /* Preconditioner.cc:127-137 */
+    for (int i = 0; i < ngw; i++) {
+      dc[2*((size_t)n*ldc + i)]   *= -1.0 * precdiag[i];
+      dc[2*((size_t)n*ldc + i)+1] *= -1.0 * precdiag[i];
+    }
+  const size_t n2 = 2 * (size_t)ldc * nst;
+  double theta_raw = 0.0;
+  if (extrapolate) {
+    double a = 0.0, b = 0.0;
+    for (int n = 0; n < nst; n++)
+      for (size_t i = 0; i < 2 * (size_t)ldc; i++) {                                /* :124-136 / :334-341 */
+        const double f = dc[i + 2*(size_t)ldc*n], df = f - dc_last[i + 2*(size_t)ldc*n];
+        a += occ[n] * f * df;
+        b += occ[n] * df * df;
+      }
+    if (is_real) {                                                                  /* :146-173 */
+      a *= 2.0; b *= 2.0;
+      for (int n = 0; n < nst; n++) {
+        const size_t i = 2 * (size_t)ldc * n;
+        const double f0 = dc[i], f1 = dc[i+1], d0 = f0 - dc_last[i], d1 = f1 - dc_last[i+1];
+        a -= occ[n] * (f0*d0 + f1*d1);
+        b -= occ[n] * (d0*d0 + d1*d1);
+      }
+    }
+    double theta = 0.0;
+    if (b != 0.0) theta = -a / b;                                                   /* :182-183 */
+    theta_raw = theta;
+    if (theta < -1.0) theta = 0.0;                                                  /* :188-191 */
+    if (theta > 2.0) theta = 2.0;
+    for (size_t i = 0; i < n2; i++) {                                               /* :196-209 */
+      const double x = c[i], xbar = x + theta * (x - c_last[i]);
+      const double f = dc[i], fbar = f + theta * (f - dc_last[i]);
+      c[i] = xbar + fbar; c_last[i] = x; dc_last[i] = f;
+    }
+  } else {
+    for (size_t i = 0; i < n2; i++) {                                               /* :212-221 */
+      const double x = c[i], f = dc[i];
+      c[i] = x + f; c_last[i] = x; dc_last[i] = f;
+    }
+  }
+  return theta_raw;
+}
+
 /* ------------------------------------------------------------------------------------------------ NonLocalPotential */
 double qbo_nl_energy_species(int ngw, int ldc, int nst, const double* c, const double* occ, int is_real, int na, int npr,
                              const int* lproj, const double* wt, const double* twnl, const double* tau,

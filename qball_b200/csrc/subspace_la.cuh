@@ -549,3 +549,135 @@ extern "C" int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info)
   }
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ PSDA wavefunction update
+// The rest of PSDAWavefunctionStepper::update after the descent direction (PSDAWavefunctionStepper.cc:93-225 real basis,
+// :281-395 complex) with Preconditioner::apply(sd, ispin, ikp, -1.0) (Preconditioner.cc:118-139), so that between two H psi
+// evaluations the wavefunction block never leaves the device:
+//   dc[ig,n] *= -precdiag[ig]                              for ig < ngw            (padding rows untouched)
+//   extrapolate:  a = sum_n occ_n sum_i f (f - f_last),  b = sum_n occ_n sum_i (f - f_last)^2   over the 2*ldc doubles of
+//                 every local column (real basis: both doubled and the G = 0 row subtracted once, :146-173),
+//                 summed over the ranks (dsum over the sd context, :177 / :343);  theta = -a/b, theta < -1 -> 0, min(2, theta)
+//   c <- c + theta (c - c_last) + f + theta (f - f_last);  c_last <- old c;  dc_last <- f         (:192-209 / :362-379)
+//   no extrapolation (first call after a reset): c <- c + f, c_last <- old c, dc_last <- f          (:211-221)
+// Partial sums: one (a, b) pair per CTA in a fixed layout, reduced by one warp in index order: deterministic.
+__global__ void __launch_bounds__(256) k_psda_prec_dots(double2* __restrict__ dc, const double2* __restrict__ dc_last, size_t ldc, int ngw,
+                                                        const double* __restrict__ precdiag, const double* __restrict__ occ,
+                                                        int is_real, int want_dots, double* __restrict__ part)
+{
+  // grid (ceil(ldc/256), nst): one state per blockIdx.y
+  __shared__ double ra[256], rb[256];
+  const int n = blockIdx.y;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (i < ldc) {
+    double2 f = dc[(size_t)n * ldc + i];
+    if (i < (size_t)ngw) {
+      const double k = -precdiag[i];
+      f.x *= k; f.y *= k;
+      dc[(size_t)n * ldc + i] = f;
+    }
+    if (want_dots) {
+      const double2 l = dc_last[(size_t)n * ldc + i];
+      const double dx = f.x - l.x, dy = f.y - l.y;
+      double w = occ[n];
+      if (is_real) w *= (i == 0 ? 1.0 : 2.0);            // G and -G; the G = 0 row counted once (:146-173)
+      a = w * (f.x * dx + f.y * dy);
+      b = w * (dx * dx + dy * dy);
+    }
+  }
+  if (!want_dots) return;
+  ra[threadIdx.x] = a; rb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { ra[threadIdx.x] += ra[threadIdx.x + s]; rb[threadIdx.x] += rb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const size_t blk = (size_t)n * gridDim.x + blockIdx.x;
+    part[2 * blk] = ra[0]; part[2 * blk + 1] = rb[0];
+  }
+}
+__global__ void __launch_bounds__(1024) k_psda_sum_ab(const double* __restrict__ part, size_t nblk, double* __restrict__ ab)
+{
+  __shared__ double ra[1024], rb[1024];
+  double a = 0.0, b = 0.0;
+  for (size_t i = threadIdx.x; i < nblk; i += 1024) { a += part[2 * i]; b += part[2 * i + 1]; }
+  ra[threadIdx.x] = a; rb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { ra[threadIdx.x] += ra[threadIdx.x + s]; rb[threadIdx.x] += rb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { ab[0] = ra[0]; ab[1] = rb[0]; }
+}
+__global__ void __launch_bounds__(256) k_psda_apply(size_t n2, double theta, double* __restrict__ c, const double* __restrict__ dc,
+                                                    double* __restrict__ c_last, double* __restrict__ dc_last, int extrapolate)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = c[i], f = dc[i];
+    double xn;
+    if (extrapolate) {
+      const double xbar = x + theta * (x - c_last[i]);
+      const double fbar = f + theta * (f - dc_last[i]);
+      xn = xbar + fbar;
+    } else {
+      xn = x + f;
+    }
+    c[i] = xn; c_last[i] = x; dc_last[i] = f;
+  }
+}
+
+extern "C" int qb200_psda_update(qb200_la* la, qb200_comm* comm, int ldc, int nst, double* c, double* dc, double* c_last,
+                                 double* dc_last, const double* occ, const double* precdiag, int extrapolate, double* theta_out)
+{
+  if (!la || !c || !dc || !c_last || !dc_last || !occ || !precdiag || nst < 0 || ldc < la->ngw) { set_error("qb200_psda_update: bad argument"); return QB200_EINVAL; }
+  if (theta_out) *theta_out = 0.0;
+  if (nst == 0 && !comm) return QB200_OK;
+  if (nst > 0 && (!is_device_ptr(c) || !is_device_ptr(dc) || !is_device_ptr(c_last) || !is_device_ptr(dc_last))) {
+    set_error("qb200_psda_update: the four blocks must be device-resident (this call exists to keep the stepper on the device)");
+    return QB200_EINVAL;
+  }
+  QB_CUDA(cudaSetDevice(la->device));
+  int rc;
+  const int gx = (ldc + 255) / 256;
+  const size_t nblk = (size_t)gx * nst;
+  // work: part[2*nblk] | ab[2] | occ[nst] | precdiag[ngw] (if host)
+  const bool hp = !is_device_ptr(precdiag);
+  if ((rc = nl_ensure(&la->part, &la->part_cap, 2 * nblk + 2 + nst + (hp ? la->ngw : 0) + 8))) return rc;
+  double* part = la->part;
+  double* ab = part + 2 * nblk;
+  double* occd = ab + 2;
+  const double* pd = precdiag;
+  QB_CUDA(cudaMemcpyAsync(occd, occ, (size_t)nst * sizeof(double), cudaMemcpyDefault, la->stream));
+  if (hp) {
+    double* q = occd + nst;
+    QB_CUDA(cudaMemcpyAsync(q, precdiag, (size_t)la->ngw * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    pd = q;
+  }
+  double h_ab[2] = { 0.0, 0.0 };
+  if (nst > 0) {
+    k_psda_prec_dots<<<dim3(gx, nst), 256, 0, la->stream>>>((double2*)dc, (const double2*)dc_last, (size_t)ldc, la->ngw, pd, occd, la->is_real,
+                                                            extrapolate ? 1 : 0, part);
+    LA_LAUNCH_CHECK(la);
+    if (extrapolate) {
+      k_psda_sum_ab<<<1, 1024, 0, la->stream>>>(part, nblk, ab);
+      LA_LAUNCH_CHECK(la);
+      QB_CUDA(cudaMemcpyAsync(h_ab, ab, 2 * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+      QB_CUDA(cudaStreamSynchronize(la->stream));
+    }
+  }
+  double theta = 0.0;
+  if (extrapolate) {
+    if (comm && (rc = qb200_allreduce_scalars(comm, h_ab, 2))) return rc;          // dsum over the sd context (:177, :343)
+    if (h_ab[1] != 0.0) theta = -h_ab[0] / h_ab[1];
+    if (theta_out) *theta_out = theta;                                             // the value the reference prints before clipping
+    if (theta < -1.0) theta = 0.0;
+    theta = std::min(2.0, theta);
+  }
+  if (nst > 0) {
+    k_psda_apply<<<148 * 8, 256, 0, la->stream>>>(2 * (size_t)ldc * nst, theta, c, dc, c_last, dc_last, extrapolate ? 1 : 0);
+    LA_LAUNCH_CHECK(la);
+  }
+  return QB200_OK;
+}

@@ -297,6 +297,18 @@ class SubspaceLA:
         capi._check(self._L.qb200_residual(self._h, ldc, nall, capi.ptr(c), nst, capi.ptr(hc), capi.ptr(a)), "qb200_residual")
         return hc
 
+    def psda_update(self, c, dc, c_last, dc_last, occ, precdiag, extrapolate: bool, comm=None) -> float:
+        """the rest of PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:93-225, 281-395) on device-resident
+        blocks: dc <- -K dc; Anderson extrapolation with theta from the occupation-weighted dot products (summed over the
+        ranks of `comm`, a parallel.Communicator); c, c_last, dc_last updated in place.  Returns theta before clipping."""
+        nst, ldc = _block_dims(c)
+        occ = np.ascontiguousarray(occ, dtype=np.float64)
+        th = C.c_double(0.0)
+        capi._check(self._L.qb200_psda_update(self._h, comm._h if comm is not None else None, ldc, nst, capi.ptr(c), capi.ptr(dc),
+                                              capi.ptr(c_last), capi.ptr(dc_last), capi.ptr(occ), capi.ptr(precdiag),
+                                              int(bool(extrapolate)), C.byref(th)), "qb200_psda_update")
+        return th.value
+
     def gram(self, c):
         """c <- c L^-H with c^H c = L L^H, in place"""
         nst, ldc = _block_dims(c)

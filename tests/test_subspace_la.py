@@ -179,3 +179,80 @@ def test_cuda_subspace_la_properties_mgo216_full_size():
     part = hc[lo:hi].clone()
     L.residual(c, part)
     assert float((part - res[lo:hi]).abs().max()) < 1e-12 * float(res.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kpoint,fc", [((0, 0, 0), False), ((0.1, 0.2, 0.3), False), ((0, 0, 0), True)])
+def test_cuda_psda_update_vs_oracle(kpoint, fc):
+    """the rest of PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:93-225, 281-395) with Preconditioner::apply
+    (Preconditioner.cc:118-139): first call without extrapolation, second with Anderson's theta, a third with a direction
+    that drives theta into the clipped range; every block (c, dc, c_last, dc_last) against the oracle's restatement"""
+    import torch
+    cell, ecut, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 6.0, 9
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    ngw, ldc = b["ngw"], b["ngw"] + 3
+    occ = R.synth_occ(nst, nst - 2)
+    prec = P.preconditioner_diag(b["kpg2"], 2.0)
+    la = H.SubspaceLA(b)
+    blocks = [R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=s) for s in (91, 92)]
+    c_ref, cl_ref, dl_ref = blocks[0].copy(), np.zeros_like(blocks[0]), np.zeros_like(blocks[0])
+    cd, cld, dld = (torch.from_numpy(a.copy()).cuda() for a in (c_ref, cl_ref, dl_ref))
+    for it, (seed, scale) in enumerate([(93, 0.3), (94, 0.25), (95, -4.0)]):
+        dc = scale * R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=seed)
+        dcd = torch.from_numpy(dc.copy()).cuda()
+        th_ref = P.psda_update(ngw, b["is_real"], c_ref, dc, cl_ref, dl_ref, occ, prec, it > 0)
+        th = la.psda_update(cd, dcd, cld, dld, occ, prec if it % 2 == 0 else torch.from_numpy(prec).cuda(), it > 0)
+        assert abs(th - th_ref) <= 1e-11 * max(1.0, abs(th_ref)), (it, th, th_ref)
+        for got, want in ((cd, c_ref), (dcd, dc), (cld, cl_ref), (dld, dl_ref)):
+            assert relerr(got.cpu().numpy(), want) < 1e-12
+        assert np.all(cd.cpu().numpy()[:, ngw:] == c_ref[:, ngw:])
+
+
+@pytest.mark.gpu
+def test_cuda_scf_iterations_stay_on_device_vs_oracle():
+    """three electronic iterations as BOSampleStepper drives them with wf_dyn PSDA -- H psi -> a = c^H Hc, Hc -= c a ->
+    preconditioner + Anderson update -> SlaterDet::gram -> density -- with the block resident on the device throughout
+    (only v goes in, rho / E_nl / E_kin / theta come out), against the same sequence over the oracle"""
+    import torch
+    cell, ecut, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 6.0, 6
+    b = P.make_basis(cell, ecut, (0, 0, 0), False)
+    grid = P.density_grid(cell, ecut)
+    ngw = b["ngw"]
+    N = grid[0] * grid[1] * grid[2]
+    occ = R.synth_occ(nst, nst)
+    v = 0.2 * R.synth_potential(*grid, seed=97)
+    prec = P.preconditioner_diag(b["kpg2"], 2.0)
+    rng = np.random.default_rng(98)
+    species = [dict(na=2, npr=4, lproj=np.array([0, 1, 1, 1], dtype=np.int32), wt=np.array([0.9, -0.4, -0.4, -0.4]),
+                    twnl=rng.standard_normal((4, ngw)) * np.exp(-b["kpg2"] / 4.0)[None, :], tau=rng.uniform(0, 10, (2, 3)))]
+    c0 = R.synth_coefficients(b["kpg2"], ecut, nst, ngw, True, seed=96)
+    c0 = P.gram(c0, True)                                                 # orthonormal start (SlaterDet::gram)
+    # oracle sequence
+    oft = P.FT(b, *grid)
+    c, cl, dl = c0.copy(), np.zeros_like(c0), np.zeros_like(c0)
+    ref = []
+    for it in range(3):
+        enl, hc = P.hpsi(b, oft, np.ascontiguousarray(c), v, occ, species)
+        ekin = P.ekin_sums(b["kpg2"], c, occ, True)[0][0]
+        hc, _ = P.residual(np.ascontiguousarray(c), hc, True)
+        th = P.psda_update(ngw, True, c, hc, cl, dl, occ, prec, it > 0)
+        c = P.gram(c, True)
+        rho = oft.compute_density(np.ascontiguousarray(c), occ / b["omega"], np.zeros(N))
+        ref.append((enl, ekin, th, rho.copy(), c.copy()))
+    # device sequence: the coefficient block is uploaded once and never read back inside the loop
+    ft, nlp, la = H.FourierTransform(b, *grid), H.NonLocalPotential(b, species), H.SubspaceLA(b)
+    cd = torch.from_numpy(c0.copy()).cuda()
+    cld, dld, hd = torch.zeros_like(cd), torch.zeros_like(cd), torch.zeros_like(cd)
+    kd = torch.from_numpy(b["kpg2"]).cuda()
+    for it in range(3):
+        enl = H.hpsi(ft, nlp, cd, occ, v, kd, hd)                           # v: host array in
+        ekin = H.ekin_sums(ft, cd, occ, True, kd)[0]
+        la.residual(cd, hd)
+        th = la.psda_update(cd, hd, cld, dld, occ, prec, it > 0)
+        la.gram(cd)
+        rho = np.zeros(N)
+        H.compute_density(ft, cd, 1.0, occ, b["omega"], rho)                # rho: host array out
+        e_ref, k_ref, t_ref, r_ref, c_ref = ref[it]
+        assert abs(enl - e_ref) < 1e-10 * max(1.0, abs(e_ref)) and abs(ekin - k_ref) < 1e-10 * abs(k_ref)
+        assert abs(th - t_ref) < 1e-8 * max(1.0, abs(t_ref)), (it, th, t_ref)
+        assert relerr(rho, r_ref) < TOL and relerr(cd.cpu().numpy(), c_ref) < TOL
