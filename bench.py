@@ -37,9 +37,9 @@ WORKLOADS = {
     "mgo216": dict(cell=(23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), ecut=25.0, kpoint=(0, 0, 0), force_complex=True, nst=768,
                    species=[("Mg", 108, [0, 1, 1, 1]), ("O", 108, [0])],
                    note="examples/MgO216 (timing_nr512.i: 50 Ry, force_complex_wf ON, 768 states, 112^3 grid)"),
-    "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=64,
+    "au992": dict(cell=(30.84, 0, 0, 0, 30.84, 0, 0, 0, 119.505), ecut=65.0, kpoint=(1e-7, 0, 0), force_complex=False, nst=256,
                   species=[("Au", 992, [0, 1, 1, 1])],
-                  note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 64 states (the full 10118-state job holds ~1265 per GPU on 8)"),
+                  note="examples/gold_benchmark N=992-equivalent cell (252x252x896 grid); per-GPU shard of 256 states (the 5456-state job of BASELINE.json holds 682 per GPU on 8, the 10118-state job of the shipped Au_PBE.xml 1265; c + H psi of 256 states = 23 GB)"),
     "si54p": dict(cell=(0, 15.525, 15.525, 15.525, 0, 15.525, 15.525, 15.525, 0), ecut=32.5, kpoint=(0, 0, 0), force_complex=False, nst=109,
                   species=[("Si", 54, [0, 1, 1, 1])],
                   note="examples/si54p as a Gamma-point real-wavefunction case (65 Ry, 126^3 grid, 109 states, 216 projectors; SURVEY.md 8d)"),
@@ -384,7 +384,11 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     np0, np1, np2 = grid
     N, ngw, nst = np0 * np1 * np2, b["ngw"], wl["nst"]
     from qball_b200 import synth as R
-    c_host = R.synth_coefficients(b["kpg2"], wl["ecut"], nst, ngw, b["is_real"], seed=1, first_state=rank * nst)
+    # the block is synthesised directly in HBM (bit-identical to the numpy generator the CPU arm and the fixtures use);
+    # a host copy exists only where a host-pointer leg needs one
+    need_host_block = extras or want_e2e
+    c_dev0 = R.synth_coefficients_torch(b["kpg2"], wl["ecut"], nst, ngw, b["is_real"], seed=1, first_state=rank * nst, device=dev)
+    c_host = c_dev0.cpu().numpy() if need_host_block else None
     v_host = R.synth_potential(np0, np1, np2, 7)
     occ = R.synth_occ(nst, nst - max(1, nst // 64))
     species = synth_species(b, wl)
@@ -394,7 +398,7 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     if args.workspace_mb:
         ft.set_workspace(args.workspace_mb << 20)
     with torch.cuda.stream(stream):
-        c = torch.from_numpy(c_host).to(dev)
+        c = c_dev0
         v = torch.from_numpy(v_host).to(dev)
         kpg2 = torch.from_numpy(b["kpg2"]).to(dev)
         hpsi = torch.zeros_like(c)
@@ -457,7 +461,10 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     # rank-ordered sum of the per-rank densities gathered on every rank (NCCL's reduction order may differ: ~1e-16)
     with torch.cuda.stream(stream):
         nel = float(rho.sum().item()) * omega / N
-        want = torch.tensor([float(np.dot(occ, norm2_states(c_host, ngw, b["is_real"])))], dtype=torch.float64, device=dev)
+        nrm = (c[:, :ngw].real ** 2 + c[:, :ngw].imag ** 2).sum(dim=1)
+        if b["is_real"]:
+            nrm = 2.0 * nrm - c[:, 0].real ** 2           # half sphere stored: G and -G, G = 0 once
+        want = (torch.from_numpy(np.asarray(occ, dtype=np.float64)).to(dev) * nrm).sum().reshape(1)
         rho_sum_err = None
         if world > 1:
             dist.all_reduce(want)

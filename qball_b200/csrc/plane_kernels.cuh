@@ -27,6 +27,7 @@ struct MidArgs {
   double facu;
   int np0;
   int zero_imag;
+  int exp;
 };
 
 // The middle pass of the y direction on a block of columns: element (line, j) at base[line + j*estride].
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(448, 1) k_plane2(const __grid_constant__ DevPl
       a.v = v + (size_t)z * np01 + c0;
       a.rho = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + c0;
       a.f = f + (size_t)unit * N + (size_t)z * np01 + c0;
-      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag;
+      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag; a.exp = 0;
       mid_pass_any<OP>(rl, g, blk, nc, pitch, np1, yrev, a, nf == 1, keepy);
       if ((OP == OP_HPSI || OP == OP_FWD) && nf > 1) {
         g.sync();

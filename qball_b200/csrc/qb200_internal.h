@@ -36,6 +36,7 @@ struct DevPlan {
   int nyrev_c;                         // 16-byte slots reserved for the yrev table in shared memory
   int ncolpos_c;                       // 16-byte slots for the colpos table in shared memory (0: read it from global)
   int stage_per;                       // plane kernel: column values per group staged ahead in dead rows (0: off)
+  int exp;                             // QB200_EXP: timing experiments that BREAK results (bit 0 no rho reduction, 1 no v load, 2 no fill/scatter)
   const int *yrev;                     // natural y index of the first element of segment seg of the y mid pass
   const int *colpos;                   // per column iv: kp*pitch0 + (digit-reversed x position of hp)
   const int *colhk;                    // per column iv: hp + np0*kp

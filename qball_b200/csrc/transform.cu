@@ -557,6 +557,8 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     const int per = (((d.nvec + ngrp - 1) / ngrp) + 7) / 8 * 8;
     d.stage_per = (per <= d.kskip * 8 && ngrp * 8 <= np0) ? per : 0;
     if (const char* e = getenv("QB200_NO_STAGE")) if (e[0] == '1') d.stage_per = 0;
+    d.exp = 0;
+    if (const char* e = getenv("QB200_EXP")) d.exp = atoi(e);      // timing experiments only: results are wrong when set
   }
   p->static_shape = 0;
   if (p->fused) {

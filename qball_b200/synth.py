@@ -48,3 +48,38 @@ def synth_occ(nst, nocc=None):
     if nocc < nst:
         occ[nocc - 1] = 1.25
     return occ
+
+
+def _splitmix_uniform_torch(seed: int, start: int, count: int, device):
+    """the same stream as splitmix_uniform, evaluated with torch int64 arithmetic (wrapping multiply, logical shifts
+    emulated by masking) on `device`: bit-identical doubles, so blocks of any size can be synthesised in HBM directly"""
+    import torch
+
+    def s64(x):                         # uint64 constant -> the int64 with the same bits
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def lsr(z, k):
+        return torch.bitwise_and(torch.bitwise_right_shift(z, k), (1 << (64 - k)) - 1)
+
+    z = (torch.arange(start, start + count, dtype=torch.int64, device=device) + seed) * s64(0x9E3779B97F4A7C15)
+    z = torch.bitwise_xor(z, lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = torch.bitwise_xor(z, lsr(z, 27)) * s64(0x94D049BB133111EB)
+    z = torch.bitwise_xor(z, lsr(z, 31))
+    return lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
+
+
+def synth_coefficients_torch(kpg2, ecut, nst, ldc, is_real, seed=1, first_state=0, device="cpu"):
+    """synth_coefficients on a torch device (same values to the last bit up to the exp() of the damping factor, which is
+    taken from numpy): returns an (nst, ldc) complex128 tensor"""
+    import torch
+    ngw = int(kpg2.shape[0])
+    damp = torch.from_numpy(np.exp(-np.asarray(kpg2) / (0.5 * ecut))).to(device)
+    c = torch.zeros((nst, ldc), dtype=torch.complex128, device=device)
+    cr = torch.view_as_real(c)
+    for n in range(nst):
+        u = _splitmix_uniform_torch(seed, 2 * ngw * (first_state + n), 2 * ngw, device)
+        cr[n, :ngw, 0] = (u[0::2] - 0.5) * damp
+        cr[n, :ngw, 1] = (u[1::2] - 0.5) * damp
+    if is_real:
+        cr[:, 0, 1] = 0.0
+    return c

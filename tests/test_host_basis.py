@@ -59,3 +59,15 @@ def test_c_abi_library_exports_every_declared_symbol():
         s = (ctypes.c_int * 1)(3)
         rc = L.qb200_plan_create(ctypes.byref(h), 0, 8, 8, 8, 1, z, z, z, s, 0, 0, 0)
         assert rc < 0 and L.qb200_last_error()
+
+
+def test_device_side_synthetic_block_is_bit_identical_to_the_numpy_generator():
+    """bench.py synthesises the coefficient block directly in HBM (torch int64 splitmix); it must be the same block the
+    CPU arm, the fixtures and the parity leg generate with numpy"""
+    from qball_b200 import basis as B
+    from qball_b200 import synth as S
+    b = B.make_basis((9, 0, 0, 0, 10, 0, 0, 0, 11), 5.0, (0, 0, 0), False)
+    for is_real, first in ((b["is_real"], 0), (False, 7)):
+        a = S.synth_coefficients(b["kpg2"], 5.0, 4, b["ngw"] + 2, is_real, seed=3, first_state=first)
+        t = S.synth_coefficients_torch(b["kpg2"], 5.0, 4, b["ngw"] + 2, is_real, seed=3, first_state=first).numpy()
+        assert np.array_equal(a, t)

@@ -188,6 +188,7 @@ def test_cuda_psda_update_vs_oracle(kpoint, fc):
     (Preconditioner.cc:118-139): first call without extrapolation, second with Anderson's theta, a third with a direction
     that drives theta into the clipped range; every block (c, dc, c_last, dc_last) against the oracle's restatement"""
     import torch
+    from qball_b200 import host as H
     cell, ecut, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 6.0, 9
     b = P.make_basis(cell, ecut, kpoint, fc)
     ngw, ldc = b["ngw"], b["ngw"] + 3
@@ -214,6 +215,7 @@ def test_cuda_scf_iterations_stay_on_device_vs_oracle():
     preconditioner + Anderson update -> SlaterDet::gram -> density -- with the block resident on the device throughout
     (only v goes in, rho / E_nl / E_kin / theta come out), against the same sequence over the oracle"""
     import torch
+    from qball_b200 import host as H
     cell, ecut, nst = (10, 0, 0, 0, 11, 0, 0, 0, 12), 6.0, 6
     b = P.make_basis(cell, ecut, (0, 0, 0), False)
     grid = P.density_grid(cell, ecut)
