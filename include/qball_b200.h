@@ -95,6 +95,20 @@ int qb200_compute_density(qb200_plan* plan, int ldc, int nst, const double* c, c
  *      grid; rho: N doubles; rhog: vbasis ngw complex; nelectrons may be NULL. */
 int qb200_density_finish(qb200_plan* vplan, const double* rho, double omega, double* rhog, double* nelectrons);
 
+/* ---- v(r) producers on the density basis: EnergyFunctional::update_vhxc                 EnergyFunctional.cc:353-975
+ *      with XCPotential::update (XCPotential.cc:104-460) and the unpolarized LDA (Perdew-Zunger / Ceperley-Alder,
+ *      LDAFunctional.cc:96-161) or PBE (PBEFunctional.cc:196-291) functional; one spin, no ESM / NLCC / enthalpy term:
+ *        v_r = v_xc[rho, grad rho] + FT^-1[ vion_local_g + 4 pi (rhog/omega + rhopst) g2i ]
+ *        energies[0] = exc, [1] = eps (electrons x local ionic potential), [2] = ehart
+ *      vplan: the plan of the density basis (vbasis_) on the density grid; rhor: N doubles (cd_.rhor[0]); rhog: ng complex
+ *      (cd_.rhog[0] = FT[omega rho]); gx = vbasis.gx_ptr(0) (3*ng, component-major; only read for PBE); g2i = vbasis.g2i_ptr();
+ *      vion_local_g, rhopst: ng complex (EnergyFunctional members, rebuilt when atoms move); v_r: N doubles, OUTPUT;
+ *      rhogt (may be NULL): ng complex, receives rhoelg + rhopst (needed by forces / stress).  Host or device pointers. */
+#define QB200_XC_LDA 0
+#define QB200_XC_PBE 1
+int qb200_update_vhxc(qb200_plan* vplan, int xc, const double* rhor, const double* rhog, const double* gx, const double* g2i,
+                      const double* vion_local_g, const double* rhopst, double omega, double* v_r, double* rhogt, double* energies);
+
 /* ---- NonLocalPotential::energy, norm-conserving branch                 NonLocalPotential.cc:1909-2171, 2628-2643
  *      Projector tables are the outputs of the reference's host setup (NonLocalPotential::init/update_twnl,
  *      NonLocalPotential.cc:76-1522) and AtomSet::get_positions.  One qb200_nl per NonLocalPotential object. */

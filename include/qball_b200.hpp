@@ -123,6 +123,15 @@ inline double density_finish(FourierTransform& vft, const double* rho, double om
   return nel;
 }
 
+// EnergyFunctional::update_vhxc + XCPotential::update on the density-basis transform (see qb200_update_vhxc); energies = exc, eps, ehart
+inline void update_vhxc(FourierTransform& vft, int xc, const double* rhor, const std::complex<double>* rhog, const double* gx,
+                        const double* g2i, const std::complex<double>* vion_local_g, const std::complex<double>* rhopst, double omega,
+                        double* v_r, std::complex<double>* rhogt, double* energies)
+{
+  check(qb200_update_vhxc(vft.plan(), xc, rhor, reinterpret_cast<const double*>(rhog), gx, g2i, reinterpret_cast<const double*>(vion_local_g),
+                          reinterpret_cast<const double*>(rhopst), omega, v_r, reinterpret_cast<double*>(rhogt), energies), "qb200_update_vhxc");
+}
+
 // kinetic-energy section of EnergyFunctional::energy (EnergyFunctional.cc:1155-1296) for one (spin, k-point):
 // w[n] = fac * occ[c.j(lj,jj)] per local state; fills psi2sum[ngw] (may be null) and tsum[14]
 inline void ekin_sums(FourierTransform& ft, int mloc, int nstloc, const std::complex<double>* c, const double* w,

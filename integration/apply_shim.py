@@ -93,6 +93,27 @@ def patch_energy_functional(s):
             "#endif\n")
     s = insert_before(s, r"^[ \t]*for \( int lj=0; lj < c\.nblocks\(\); lj\+\+ \)", code, "EnergyFunctional psi2sum loop",
                       after_regex=r"compute psi2sum\(G\) = fac \* sum_G occ\(n\) psi2\(n,G\)")
+    # update_vhxc: one spin, LDA / PBE, none of the special branches -> the whole function on the device
+    code = ("#ifdef USE_QB200\n"
+            "  if (qb200_shim::enabled() && wf_.nspin() == 1 && !s_.ctrl.ultrasoft && !s_.ctrl.nlcc && s_.ctrl.esm_bc == \"\" &&\n"
+            "      s_.ctrl.enthalpy_pressure == 0.0 && !s_.ctrl.tddft_involved && s_.ctrl.vdw != \"D3\" && s_.ctrl.stress != \"ON\" &&\n"
+            "      (s_.ctrl.xc == \"LDA\" || s_.ctrl.xc == \"PBE\")) {\n"
+            "    const int ngloc_q = vbasis_->localsize();\n"
+            "    const double omega_q = wf_.cell().volume();\n"
+            "    double en_q[3];\n"
+            "    qb200_shim::update_vhxc(vft, s_.ctrl.xc == \"PBE\" ? 1 : 0, &cd_.rhor[0][0], &cd_.rhog[0][0], vbasis_->gx_ptr(0), vbasis_->g2i_ptr(),\n"
+            "                            &vion_local_g[0], &rhopst[0], omega_q, &v_r[0][0], &rhogt[0], en_q);\n"
+            "    const double *const g2i_q = vbasis_->g2i_ptr();\n"
+            "    for ( int ig = 0; ig < ngloc_q; ig++ ) {          // members other parts of energy() read (forces: :1715-1722)\n"
+            "      rhoelg[ig] = cd_.rhog[0][ig] / omega_q;\n"
+            "      vlocal_g[ig] = vion_local_g[ig] + 4.0 * M_PI * rhogt[ig] * g2i_q[ig];\n"
+            "    }\n"
+            "    exc_ = en_q[0]; eps_ = en_q[1]; ehart_ = en_q[2];\n"
+            "    epv_ = 0.0; evdw_ = 0.0; sigma_vdw = 0.0;\n"
+            "    return;\n"
+            "  }\n"
+            "#endif\n")
+    s = insert_after_open_brace(s, r"^void EnergyFunctional::update_vhxc\(void\)", code, "EnergyFunctional::update_vhxc")
     return s
 
 

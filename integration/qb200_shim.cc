@@ -163,4 +163,13 @@ bool psi2sum(const FourierTransform* ft, const ComplexMatrix& c, const double* o
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------- EnergyFunctional (v(r))
+void update_vhxc(const FourierTransform* vft, int xc, const double* rhor, const complex<double>* rhog, const double* gx,
+                 const double* g2i, const complex<double>* vion_local_g, const complex<double>* rhopst, double omega,
+                 double* v_r, complex<double>* rhogt, double* energies)
+{
+  forwarded_++;
+  qb200::update_vhxc(ft_gpu(vft), xc, rhor, rhog, gx, g2i, vion_local_g, rhopst, omega, v_r, rhogt, energies);
+}
+
 }  // namespace qb200_shim

@@ -39,6 +39,10 @@ void nl_invalidate(const NonLocalPotential* key);      // update_twnl rebuilt th
 // EnergyFunctional::energy, psi2sum loop (EnergyFunctional.cc:1209-1223): returns true when psi2sum was filled on the device
 bool psi2sum(const FourierTransform* ft, const ComplexMatrix& c, const double* occ_global, double fac, const double* kpg2,
              std::vector<double>& psi2sum);
+// EnergyFunctional::update_vhxc (EnergyFunctional.cc:353-975) for one spin, LDA (xc 0) / PBE (xc 1); energies = exc, eps, ehart
+void update_vhxc(const FourierTransform* vft, int xc, const double* rhor, const std::complex<double>* rhog, const double* gx,
+                 const double* g2i, const std::complex<double>* vion_local_g, const std::complex<double>* rhopst, double omega,
+                 double* v_r, std::complex<double>* rhogt, double* energies);
 // counters for the tests: calls forwarded to the device since start
 long long forwarded_calls();
 

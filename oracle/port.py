@@ -185,6 +185,38 @@ def ekin_sums(kpg2, c, occ, is_real, kpgx=None, fstress=None, dfstress=None):
     return tsum, p2
 
 
+def xc_lda(rho):
+    rho = np.ascontiguousarray(rho, dtype=np.float64)
+    e, v = np.zeros_like(rho), np.zeros_like(rho)
+    lib().qbo_xc_lda(C.c_size_t(rho.size), _d(rho), _d(e), _d(v))
+    return e, v
+
+
+def xc_pbe(rho, grad):
+    rho, grad = np.ascontiguousarray(rho, dtype=np.float64), np.ascontiguousarray(grad, dtype=np.float64)
+    e, v1, v2 = np.zeros_like(rho), np.zeros_like(rho), np.zeros_like(rho)
+    lib().qbo_xc_pbe(C.c_size_t(rho.size), _d(rho), _d(grad), _d(e), _d(v1), _d(v2))
+    return e, v1, v2
+
+
+def g2i_of(b):
+    """Basis::g2i (k = 0 basis): 1/|G|^2, 0 at G = 0"""
+    g2 = np.asarray(b["kpg2"])
+    return np.where(g2 > 0.0, 1.0 / np.where(g2 > 0.0, g2, 1.0), 0.0)
+
+
+def update_vhxc(vft, vb, xc, rhor, rhog, vion, rhopst):
+    """EnergyFunctional::update_vhxc for one spin on the density basis vb (k = 0: gx = kpgx): returns (v_r, [exc, eps, ehart])"""
+    N = vft.N
+    v_r, en = np.zeros(N), np.zeros(3)
+    cc = lambda a: np.ascontiguousarray(a, dtype=np.complex128)  # noqa: E731
+    L = lib()
+    L.qbo_update_vhxc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 6 + [C.c_double] + [C.POINTER(C.c_double)] * 2
+    L.qbo_update_vhxc(vft.h, int(xc), int(vb["ngw"]), int(vb["is_real"]), _d(np.ascontiguousarray(rhor)), _d(cc(rhog)),
+                      _d(np.ascontiguousarray(vb["kpgx"])), _d(g2i_of(vb)), _d(cc(vion)), _d(cc(rhopst)), C.c_double(vb["omega"]), _d(v_r), _d(en))
+    return v_r, en
+
+
 def preconditioner_diag(kpg2, ecutprec, fstress=None):
     """Preconditioner::update (Preconditioner.cc:47-90): diag[ig] = 0.5/max(e, ecutprec), e = 0.5 (|k+G|^2 [+ fstress])"""
     e = 0.5 * (kpg2 + (0.0 if fstress is None else fstress))

@@ -574,6 +574,141 @@ double qbo_psda_update(int ngw, int ldc, int nst, int is_real, double* c, double
   return theta_raw;
 }
 
+/* ------------------------------------------------------------------------------------------------ XC functionals, update_vhxc */
+/* LDAFunctional::xc_unpolarized (functionals/LDAFunctional.cc:96-161): Perdew-Zunger / Ceperley-Alder, unpolarized */
+void qbo_xc_lda(size_t n, const double* rho, double* exc, double* vxc)
+{
+  const double c1 = 0.6203504908994001, c3 = -0.610887057711;
+  const double A = 0.0311, B = -0.048, b1 = 1.0529, b2 = 0.3334, G = -0.1423;
+  const double D = G / (1.0 + b1 + b2) - B;                                                   /* :119-120 */
+  const double C = -A - D - G * ((b1/2.0 + b2) / ((1.0+b1+b2)*(1.0+b1+b2)));
+  for (size_t i = 0; i < n; i++) {
+    double ee = 0.0, vv = 0.0;
+    const double rh = rho[i];
+    if (rh > 0.0) {
+      const double ro13 = cbrt(rh), rs = c1 / ro13;
+      const double vx = c3 / rs, ex = 0.75 * vx;                                              /* :133-134 */
+      double ec, vc;
+      if (rs < 1.0) {                                                                         /* :137-144 */
+        const double logrs = log(rs);
+        ec = A * logrs + B + C * rs * logrs + D * rs;
+        vc = A * logrs + (B - A / 3.0) + (2.0/3.0) * C * rs * logrs + ((2.0 * D - C) / 3.0) * rs;
+      } else {                                                                                /* :146-153 */
+        const double sqrtrs = sqrt(rs), den = 1.0 + b1 * sqrtrs + b2 * rs;
+        ec = G / den;
+        vc = ec * (1.0 + (7.0/6.0) * b1 * sqrtrs + (4.0/3.0) * b2 * rs) / den;
+      }
+      ee = ex + ec; vv = vx + vc;
+    }
+    exc[i] = ee; vxc[i] = vv;
+  }
+}
+
+static void gcor2(double a, double a1, double b1, double b2, double b3, double b4, double rtrs, double* gg, double* ggrs)
+{                                                                                             /* PBEFunctional.cc:482-492 */
+  const double q0 = -2.0 * a * (1.0 + a1 * rtrs * rtrs);
+  const double q1 = 2.0 * a * rtrs * (b1 + rtrs * (b2 + rtrs * (b3 + rtrs * b4)));
+  const double q2 = log(1.0 + 1.0 / q1);
+  *gg = q0 * q2;
+  const double q3 = a * (b1 / rtrs + 2.0 * b2 + rtrs * (3.0 * b3 + 4.0 * b4 * rtrs));
+  *ggrs = -2.0 * a * a1 * q2 - q0 * q3 / (q1 * (1.0 + q1));
+}
+
+/* PBEFunctional::excpbe (functionals/PBEFunctional.cc:196-291), unpolarized; grad = |grad rho| */
+void qbo_xc_pbe(size_t n, const double* rho_, const double* grad_, double* exc, double* vxc1, double* vxc2)
+{
+  const double third = 1.0/3.0, third4 = 4.0/3.0;
+  const double ax = -0.7385587663820224058, um = 0.2195149727645171, uk = 0.804, ul = um / uk;
+  const double pi32third = 3.09366772628014, alpha = 1.91915829267751, seven_sixth = 7.0/6.0, four_over_pi = 1.27323954473516;
+  const double gamma = 0.03109069086965489, bet = 0.06672455060314922, delt = bet / gamma;
+  for (size_t i = 0; i < n; i++) {
+    const double rho = rho_[i], grad = grad_[i];
+    exc[i] = 0.0; vxc1[i] = 0.0; vxc2[i] = 0.0;
+    if (rho < 1.e-18) continue;                                                               /* :219-221 */
+    const double rh13 = pow(rho, third), exunif = ax * rh13, fk = pi32third * rh13;
+    const double s = grad / (2.0 * fk * rho), s2 = s * s, p0 = 1.0 + ul * s2, fxpbe = 1.0 + uk - uk / p0;
+    const double ex = exunif * fxpbe, fs = 2.0 * uk * ul / (p0 * p0);
+    const double vx1 = third4 * exunif * (fxpbe - s2 * fs), vx2 = -exunif * fs / (rho * 4.0 * fk * fk);   /* :246-247 */
+    const double rs = alpha / fk, twoks = 2.0 * sqrt(four_over_pi * fk), t = grad / (twoks * rho), rtrs = sqrt(rs);
+    double ec, ecrs;
+    gcor2(0.0310907, 0.2137, 7.5957, 3.5876, 1.6382, 0.49294, rtrs, &ec, &ecrs);
+    const double vc = ec - rs * ecrs * third;
+    const double pon = -ec / gamma, b = delt / (exp(pon) - 1.0), b2 = b * b, t2 = t * t, t4 = t2 * t2;
+    const double q4 = 1.0 + b * t2, q5 = q4 + b2 * t4, h = gamma * log(1.0 + delt * q4 * t2 / q5);
+    const double t6 = t4 * t2, rsthrd = rs * third, fac = delt / b + 1.0, bec = b2 * fac / bet;
+    const double q8 = q5 * q5 + delt * q4 * q5 * t2, q9 = 1.0 + 2.0 * b * t2;
+    const double hb = -bet * b * t6 * (2.0 + b * t2) / q8, hrs = -rsthrd * hb * bec * ecrs, ht = 2.0 * bet * q9 / q8;
+    const double vc1 = vc + h + hrs - t2 * ht * seven_sixth, vc2 = -ht / (rho * twoks * twoks);
+    exc[i] = ex + ec + h; vxc1[i] = vx1 + vc1; vxc2[i] = vx2 + vc2;                           /* :288-290 */
+  }
+}
+
+/* EnergyFunctional::update_vhxc (EnergyFunctional.cc:353-975) with XCPotential::update (XCPotential.cc:104-460): one spin, no
+ * NLCC / ESM / enthalpy / TDDFT-split density.  ft: the density-basis transform.  xc: 0 LDA, 1 PBE.  energies: exc, eps, ehart.
+ * The reference's own sequence of transforms (GGA: 3 backward, then per direction forward / i G_j / backward). */
+void qbo_update_vhxc(qbo_ft* ft, int xc, int ng, int is_real, const double* rhor, const double* rhog, const double* gx,
+                     const double* g2i, const double* vion, const double* rhopst, double omega, double* v_r, double* energies)
+{
+  const size_t N = (size_t)ft->np0 * ft->np1 * ft->np2;
+  const double omega_inv = 1.0 / omega, fpi = 4.0 * M_PI;
+  double* tmpr = (double*)malloc(2 * N * sizeof(double));
+  double* tmp1 = (double*)malloc(2 * (size_t)ng * sizeof(double));
+  double* exc = (double*)malloc(N * sizeof(double));
+  double* v1 = (double*)malloc(N * sizeof(double));
+  for (size_t i = 0; i < N; i++) v_r[i] = 0.0;                                                /* :382-384 */
+  double esum = 0.0;
+  if (xc == 0) {                                                                              /* XCPotential.cc:133-175 */
+    qbo_xc_lda(N, rhor, exc, v1);
+    for (size_t i = 0; i < N; i++) { esum += rhor[i] * exc[i]; v_r[i] += v1[i]; }
+  } else {
+    double* gr = (double*)malloc(3 * N * sizeof(double));
+    double* gmod = (double*)malloc(N * sizeof(double));
+    double* v2 = (double*)malloc(N * sizeof(double));
+    double* vxctmp = (double*)malloc(N * sizeof(double));
+    for (int j = 0; j < 3; j++) {                                                             /* :200-214 */
+      for (int ig = 0; ig < ng; ig++) {
+        const double g = omega_inv * gx[(size_t)j * ng + ig];
+        tmp1[2*ig] = -g * rhog[2*ig+1]; tmp1[2*ig+1] = g * rhog[2*ig];
+      }
+      qbo_backward(ft, tmp1, tmpr);
+      for (size_t i = 0; i < N; i++) gr[(size_t)j * N + i] = tmpr[2*i];
+    }
+    for (size_t i = 0; i < N; i++) gmod[i] = sqrt(gr[i]*gr[i] + gr[N+i]*gr[N+i] + gr[2*N+i]*gr[2*N+i]);   /* PBEFunctional.cc:101-103 */
+    qbo_xc_pbe(N, rhor, gmod, exc, v1, v2);
+    for (int j = 0; j < 3; j++) {                                                             /* XCPotential.cc:262-285 */
+      for (size_t i = 0; i < N; i++) { tmpr[2*i] = gr[(size_t)j * N + i] * v2[i]; tmpr[2*i+1] = 0.0; }
+      qbo_forward(ft, tmpr, tmp1);
+      for (int ig = 0; ig < ng; ig++) {
+        const double g = gx[(size_t)j * ng + ig], re = tmp1[2*ig], im = tmp1[2*ig+1];
+        tmp1[2*ig] = -g * im; tmp1[2*ig+1] = g * re;
+      }
+      qbo_backward(ft, tmp1, tmpr);
+      for (size_t i = 0; i < N; i++) vxctmp[i] = (j == 0 ? 0.0 : vxctmp[i]) + tmpr[2*i];
+    }
+    for (size_t i = 0; i < N; i++) { esum += rhor[i] * exc[i]; v_r[i] += v1[i] + vxctmp[i]; }  /* :397-410 */
+    free(gr); free(gmod); free(v2); free(vxctmp);
+  }
+  energies[0] = esum * omega / (double)N;                                                     /* :170, :452 */
+  /* eps (EnergyFunctional.cc:447-465) and ehart, vlocal_g (:487-518) */
+  double eps = 0.0, ehsum = 0.0;
+  for (int ig = 0; ig < ng; ig++) {
+    const double rx = omega_inv * rhog[2*ig], ry = omega_inv * rhog[2*ig+1];
+    eps += rx * vion[2*ig] + ry * vion[2*ig+1];
+  }
+  if (is_real) eps = 2.0 * eps - (omega_inv * rhog[0] * vion[0] + omega_inv * rhog[1] * vion[1]);
+  energies[1] = eps * omega;
+  for (int ig = 0; ig < ng; ig++) {
+    const double tx = omega_inv * rhog[2*ig] + rhopst[2*ig], ty = omega_inv * rhog[2*ig+1] + rhopst[2*ig+1];
+    ehsum += (tx*tx + ty*ty) * g2i[ig];
+    tmp1[2*ig] = vion[2*ig] + fpi * tx * g2i[ig];
+    tmp1[2*ig+1] = vion[2*ig+1] + fpi * ty * g2i[ig];
+  }
+  energies[2] = (is_real ? 1.0 : 0.5) * omega * fpi * ehsum;
+  qbo_backward(ft, tmp1, tmpr);                                                               /* :931-939 */
+  for (size_t i = 0; i < N; i++) v_r[i] += tmpr[2*i];
+  free(tmpr); free(tmp1); free(exc); free(v1);
+}
+
 /* ------------------------------------------------------------------------------------------------ NonLocalPotential */
 double qbo_nl_energy_species(int ngw, int ldc, int nst, const double* c, const double* occ, int is_real, int na, int npr,
                              const int* lproj, const double* wt, const double* twnl, const double* tau,

@@ -54,6 +54,8 @@
 #include <qball/Timer.h>
 #include <qball/VectorPotential.h>
 #include <math/matrix.h>
+#include <functionals/LDAFunctional.h>
+#include <functionals/PBEFunctional.h>
 // the driver needs the projector tables (twnl, wt, lproj), which are private members of NonLocalPotential;
 // every header it includes is already included above, so only that one class is affected.
 #define private public
@@ -84,6 +86,27 @@ int main(int argc, char** argv)
   if (argc < 3) { fprintf(stderr, "usage: ref_driver basis|run|time <case.txt> [nrep]\n"); return 1; }
   const string mode = argv[1];
   MPI_Init(&argc, &argv);
+  if (mode == "xc") {
+    // ref_driver xc <prefix>: the reference's own LDAFunctional / PBEFunctional (unpolarized) on the points of
+    // <prefix>.in_rho.f64 (n doubles) and <prefix>.in_grad.f64 (3n doubles, component-major); dumps exc, vxc1 (, vxc2)
+    const string pre = argv[2];
+    FILE* f = fopen((pre + ".in_rho.f64").c_str(), "rb");
+    if (!f) { perror("in_rho"); return 2; }
+    fseek(f, 0, SEEK_END); const size_t n = ftell(f) / sizeof(double); fclose(f);
+    vector<vector<double> > rhoe(1, vector<double>(n));
+    vector<double> grad(3 * n);
+    slurp(pre + ".in_rho.f64", &rhoe[0][0], n * sizeof(double));
+    slurp(pre + ".in_grad.f64", &grad[0], 3 * n * sizeof(double));
+    { LDAFunctional lda(rhoe); lda.setxc();
+      dump(pre + ".lda_exc.f64", lda.exc, n * sizeof(double)); dump(pre + ".lda_vxc.f64", lda.vxc1, n * sizeof(double)); }
+    { PBEFunctional pbe(rhoe);
+      for (int j = 0; j < 3; j++) memcpy(pbe.grad_rho[j], &grad[j * n], n * sizeof(double));
+      pbe.setxc();
+      dump(pre + ".pbe_exc.f64", pbe.exc, n * sizeof(double)); dump(pre + ".pbe_vxc1.f64", pbe.vxc1, n * sizeof(double));
+      dump(pre + ".pbe_vxc2.f64", pbe.vxc2, n * sizeof(double)); }
+    MPI_Finalize();
+    return 0;
+  }
   {
   double a[9] = {0}; double ecut = 0, kp[3] = {0,0,0}; int force_complex = 0; int grid[3] = {0,0,0}; int nst = 1;
   vector<pair<string,string> > species; vector<AtomLine> atomlines; string out = "case";

@@ -82,6 +82,8 @@ def load():
     L.qb200_allreduce_scalars.argtypes = [vp, dp, i]
     for name in ("qb200_comm_get_unique_id", "qb200_comm_init", "qb200_comm_destroy", "qb200_allreduce_rho", "qb200_allreduce_scalars"):
         getattr(L, name).restype = i
+    L.qb200_update_vhxc.argtypes = [vp, i, dp, dp, dp, dp, dp, dp, d, dp, dp, dp]
+    L.qb200_update_vhxc.restype = i
     L.qb200_psda_update.argtypes = [vp, vp, i, i, dp, dp, dp, dp, dp, dp, i, C.POINTER(d)]
     L.qb200_psda_update.restype = i
     L.qb200_measure_fp64_peak.argtypes = [i, C.POINTER(d)]

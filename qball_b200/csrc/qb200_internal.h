@@ -103,6 +103,7 @@ struct qb200_plan {
   std::vector<cudaEvent_t> evs;
   const void* res_ptr; int res_ldc, res_nst; long long res_tag, next_tag;
   double *ex_a, *ex_b, *ex_c2; size_t ex_a_cap, ex_b_cap, ex_c2_cap;   // work blocks of qb200_exponential
+  double* vh; size_t vh_cap;                                            // work of qb200_update_vhxc (vhxc.cuh)
 };
 
 namespace qb200 {

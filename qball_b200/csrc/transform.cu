@@ -352,6 +352,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
   p->st_c_cap = p->st_cp_cap = p->st_v_cap = p->st_f_cap = p->st_kpg2_cap = 0;
   p->launches = 0;
   p->ex_a = p->ex_b = p->ex_c2 = nullptr; p->ex_a_cap = p->ex_b_cap = p->ex_c2_cap = 0;
+  p->vh = nullptr; p->vh_cap = 0;
   p->s_in = p->s_out = nullptr; p->res_ptr = nullptr; p->res_ldc = p->res_nst = 0; p->res_tag = p->next_tag = 0;
   DevPlan& d = p->d;
   d.np0 = np0; d.np1 = np1; d.np2 = np2; d.nrods = nrods; d.is_real = is_real ? 1 : 0;
@@ -608,7 +609,7 @@ extern "C" int qb200_plan_destroy(qb200_plan* p)
   for (cudaEvent_t e : p->evs) cudaEventDestroy(e);
   if (p->s_in) cudaStreamDestroy(p->s_in);
   if (p->s_out) cudaStreamDestroy(p->s_out);
-  for (double* q : { p->zt, p->w, p->rho_part, p->fac_dev, p->st_c, p->st_cp, p->st_v, p->st_f, p->st_kpg2, p->ex_a, p->ex_b, p->ex_c2 })
+  for (double* q : { p->zt, p->w, p->rho_part, p->fac_dev, p->st_c, p->st_cp, p->st_v, p->st_f, p->st_kpg2, p->ex_a, p->ex_b, p->ex_c2, p->vh })
     if (q) cudaFree(q);
   delete p;
   return QB200_OK;
@@ -1005,3 +1006,5 @@ extern "C" int qb200_density_finish(qb200_plan* pv, const double* rho, double om
   if (nelectrons) *nelectrons = nel;
   return QB200_OK;
 }
+
+#include "vhxc.cuh"

@@ -136,6 +136,20 @@ class ChargeDensity:
         return nel.value
 
 
+XC_LDA, XC_PBE = 0, 1
+
+
+def update_vhxc(vft: FourierTransform, xc: int, rhor, rhog, gx, g2i, vion_local_g, rhopst, omega: float, v_r, rhogt=None):
+    """EnergyFunctional::update_vhxc (EnergyFunctional.cc:353-975) with XCPotential::update (XCPotential.cc:104-460) for one
+    spin on the density-basis transform `vft`: v_r (output) = v_xc + FT^-1[vion_local_g + 4 pi (rhog/omega + rhopst) g2i];
+    returns (exc, eps, ehart).  xc: XC_LDA or XC_PBE (gx = vbasis.gx_ptr(0), only read for PBE)."""
+    en = np.zeros(3)
+    capi._check(vft._L.qb200_update_vhxc(vft._h, int(xc), capi.ptr(rhor), capi.ptr(rhog), capi.ptr(gx), capi.ptr(g2i),
+                                         capi.ptr(vion_local_g), capi.ptr(rhopst), float(omega), capi.ptr(v_r), capi.ptr(rhogt),
+                                         capi.ptr(en)), "qb200_update_vhxc")
+    return float(en[0]), float(en[1]), float(en[2])
+
+
 def compute_current(ft: FourierTransform, c, weight: float, occ, omega: float, kpgx, cur):
     """the per-(spin, k-point) body of CurrentDensity::update_current (CurrentDensity.cc:64-88):
     cur[idir] += -Im sum_n weight*occ_n/omega conj(psi_n) FT^-1[i kpgx_idir c_n]; cur: (3, N) doubles, accumulated."""
