@@ -210,6 +210,14 @@ int qb200_residual(qb200_la* la, int ldc, int nall, const double* c, int nst, do
  * non-positive-definite overlap returns QB200_EINVAL with *info = order of the failing minor and leaves c unchanged. */
 int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info);
 
+/* ---- Wavefunction::diag(dwf, eigvec), one (spin, k-point), norm-conserving                     Wavefunction.cc:1510-1715
+ *      h = c^H (H c) (real bases: 2 c^T (H c) minus the rank-1 term of real row 0, :1538-1539); w = eigenvalues of h from its
+ *      lower triangle, ascending (syevd / heevd 'l', :1604, :1682; sd->set_eig(w)); eigvec != 0: c <- c z with z the
+ *      eigenvectors (:1606-1609, :1684-1688).  The reference calls (Sca)LAPACK; here: parallel cyclic Jacobi on the device
+ *      + the FP64 tensor-core GEMM for c z.  c: ldc x nst (all states on this rank), overwritten only if eigvec; hc = H c,
+ *      ldc x nst (read only); w: nst doubles, HOST; sweeps (may be NULL): Jacobi sweeps used. */
+int qb200_diag(qb200_la* la, int ldc, int nst, double* c, const double* hc, int eigvec, double* w, int* sweeps);
+
 /* ---- optional per-kernel timing (CUDA events on the launching stream, recorded around every launch while enabled).
  *      categories: 0 k_zcol_bwd, 1 xy stage (k_plane, or k_xrows+k_ycols), 2 k_zcol_fwd, 3 k_fnl, 4 k_fnl_finish+sum,
  *      5 k_back, 6 k_rho_reduce, 7 k_anl_gen.  qb200_profile_read synchronises, ADDS elapsed milliseconds and launch counts of the

@@ -211,6 +211,9 @@ class SubspaceLA {
   // SlaterDet::gram(): c <- c L^-H with c^H c = L L^H.  A singular overlap aborts like the reference's potrf.
   void gram(int mloc, int n, std::complex<double>* c)
   { int info = 0; check(qb200_gram(la_, mloc, n, reinterpret_cast<double*>(c), &info), "qb200_gram"); }
+  // Wavefunction::diag: w (n doubles, host) = eigenvalues of c^H (H c), ascending; eigvec: c <- c z
+  void diag(int mloc, int n, std::complex<double>* c, const std::complex<double>* hc, bool eigvec, double* w)
+  { check(qb200_diag(la_, mloc, n, reinterpret_cast<double*>(c), reinterpret_cast<const double*>(hc), eigvec ? 1 : 0, w, 0), "qb200_diag"); }
   // the rest of PSDAWavefunctionStepper::update on device-resident blocks (see qb200_psda_update); returns theta (unclipped)
   double psda_update(qb200_comm* comm, int mloc, int nstloc, std::complex<double>* c, std::complex<double>* dc,
                      std::complex<double>* c_last, std::complex<double>* dc_last, const double* occ_local, const double* precdiag,

@@ -275,6 +275,25 @@ def residual(c, hc, is_real):
     return out, a
 
 
+def subspace_h(c, hc, is_real):
+    """h = c^H (H c) as Wavefunction::diag forms it (Wavefunction.cc:1538-1539 real: gemm('t','n',2.0) + ger(-1.0); :1641
+    complex: gemm('c','n',1.0)); h[m, n], numpy"""
+    ngw_rows = c.shape[1]
+    if is_real:
+        cr = np.ascontiguousarray(c).view(np.float64).reshape(c.shape[0], 2 * ngw_rows)
+        hr = np.ascontiguousarray(hc).view(np.float64).reshape(hc.shape[0], 2 * ngw_rows)
+        return 2.0 * cr @ hr.T - np.outer(cr[:, 0], hr[:, 0])
+    return c.conj() @ hc.T
+
+
+def diag(c, hc, is_real):
+    """eigenvalues of h from its lower triangle, ascending (syevd / heevd 'l', Wavefunction.cc:1604, 1682) and the
+    eigenvectors z (columns); LAPACK through numpy, as the reference calls LAPACK"""
+    h = subspace_h(c, hc, is_real)
+    w, z = np.linalg.eigh(h, UPLO="L")
+    return w, z, h
+
+
 def gram(c, is_real):
     """SlaterDet::gram (SlaterDet.cc:1043-1143): Cholesky orthonormalisation, returns the new (nst, ldc) block"""
     nst, ldc = c.shape

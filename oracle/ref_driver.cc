@@ -284,6 +284,9 @@ int main(int argc, char** argv)
       am.ger(-1.0,c_proxy,0,cp_proxy,0);
       cp_proxy.gemm('n','n',-1.0,c_proxy,am,1.0);
       dump(out + ".resid_a.f64", am.cvalptr(), (size_t)nst*nst*sizeof(double));
+      { // Wavefunction::diag (Wavefunction.cc:1538-1539, 1612): eigenvalues of the same h through the reference's syevd('l')
+        DoubleMatrix hd(am); valarray<double> w(hd.m()); hd.syevd('l', w);
+        dump(out + ".diag_w.f64", &w[0], nst*sizeof(double)); }
     } else {
       ComplexMatrix& c_proxy = sd.c();
       ComplexMatrix& cpm = dsd.c();
@@ -291,6 +294,9 @@ int main(int argc, char** argv)
       am.gemm('c','n',1.0,c_proxy,cpm,0.0);
       cpm.gemm('n','n',-1.0,c_proxy,am,1.0);
       dump(out + ".resid_a.f64", am.cvalptr(), (size_t)nst*nst*sizeof(complex<double>));
+      { // Wavefunction::diag (Wavefunction.cc:1641, 1693): eigenvalues of the same h through the reference's heev('l')
+        ComplexMatrix hd(am); valarray<double> w(hd.m()); hd.heev('l', w);
+        dump(out + ".diag_w.f64", &w[0], nst*sizeof(double)); }
     }
     dump(out + ".resid.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
   }

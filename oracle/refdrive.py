@@ -106,6 +106,8 @@ def run_reference(case: Case, seed: int = 1, nocc: int | None = None, workdir: s
     r["enl"] = float(_load(prefix, "enl.f64", np.float64)[0])
     r["resid"] = _load(prefix, "resid.f64", np.complex128).reshape(case.nst, b["mloc"])
     r["resid_a"] = _load(prefix, "resid_a.f64", np.float64 if b["is_real"] else np.complex128).reshape(case.nst, case.nst)
+    if os.path.exists(prefix + ".diag_w.f64"):
+        r["diag_w"] = _load(prefix, "diag_w.f64", np.float64)
     r["cur"] = _load(prefix, "cur.f64", np.float64).reshape(3, N)
     r["gram"] = _load(prefix, "gram.f64", np.complex128).reshape(case.nst, b["mloc"])
     sp = []

@@ -84,6 +84,8 @@ def load():
         getattr(L, name).restype = i
     L.qb200_update_vhxc.argtypes = [vp, i, dp, dp, dp, dp, dp, dp, d, dp, dp, dp]
     L.qb200_update_vhxc.restype = i
+    L.qb200_diag.argtypes = [vp, i, i, dp, dp, i, dp, ip]
+    L.qb200_diag.restype = i
     L.qb200_psda_update.argtypes = [vp, vp, i, i, dp, dp, dp, dp, dp, dp, i, C.POINTER(d)]
     L.qb200_psda_update.restype = i
     L.qb200_measure_fp64_peak.argtypes = [i, C.POINTER(d)]

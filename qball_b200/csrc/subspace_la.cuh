@@ -681,3 +681,244 @@ extern "C" int qb200_psda_update(qb200_la* la, qb200_comm* comm, int ldc, int ns
   }
   return QB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ subspace diagonalisation
+// Wavefunction::diag (/root/reference/src/qball/Wavefunction.cc:1510-1715), norm-conserving, one (spin, k-point):
+//   h = c^H (H c)                 (complex: h.gemm('c','n',1.0,c,cp,0.0) :1641; real: gemm('t','n',2.0) + ger(-1.0) :1538-1539)
+//   w = eigenvalues of h, ascending, from its LOWER triangle (syevd / heevd 'l', :1604, :1682)
+//   eigvec: z = eigenvectors, c <- c z (:1606-1609, :1684-1688)
+// The reference calls LAPACK; here the n x n Hermitian problem is solved on the device by a parallel cyclic Jacobi method
+// (round-robin ordering: n/2 disjoint rotations per step, n - 1 steps per sweep, quadratic convergence, every rotation unitary
+// to rounding -- eigenvalues accurate to a few ulp of ||h||), and c z reuses the FP64 tensor-core GEMM of qb200_gram.
+// Eigenvectors of degenerate eigenvalues and the phase of every eigenvector are as arbitrary as LAPACK's.
+namespace qb200 {
+
+// A (ne x ne, column-major) <- Hermitian matrix defined by the lower triangle of S (n x n); padding row / column ne - 1 zero
+__global__ void __launch_bounds__(256) k_jac_init(const double2* __restrict__ S, int n, int ne, double2* __restrict__ A, double2* __restrict__ Z)
+{
+  const size_t idx = blockIdx.x * (size_t)256 + threadIdx.x;
+  if (idx >= (size_t)ne * ne) return;
+  const int col = (int)(idx / ne), row = (int)(idx % ne);
+  double2 v = make_double2(0.0, 0.0);
+  if (row < n && col < n) {
+    if (row > col) v = S[(size_t)col * n + row];
+    else if (row < col) { const double2 t = S[(size_t)row * n + col]; v = make_double2(t.x, -t.y); }
+    else v = make_double2(S[(size_t)col * n + row].x, 0.0);
+  }
+  A[idx] = v;
+  Z[idx] = make_double2(row == col ? 1.0 : 0.0, 0.0);
+}
+
+// round-robin pairing of step `step` (0 .. ne-2): player 0 fixed, the others rotate
+__device__ __forceinline__ void jac_pair(int k, int step, int ne, int& p, int& q)
+{
+  const int m = ne - 1;
+  int a = (k == 0) ? m : ((step + k) % m);
+  int b = (step + m - k) % m;
+  p = min(a, b); q = max(a, b);
+}
+
+struct JacRot { double c, s, ex, ey; };     // J[p,p] = J[q,q] = c, J[p,q] = s e^{i phi}, J[q,p] = -s e^{-i phi}; (ex, ey) = e^{i phi}
+
+// one CTA per pair: rotation from (A[p,p], A[q,q], A[p,q]), then the COLUMN operation A <- A J, Z <- Z J on columns p, q
+__global__ void __launch_bounds__(256) k_jac_cols(double2* __restrict__ A, double2* __restrict__ Z, int ne, int step, JacRot* __restrict__ rot)
+{
+  int p, q;
+  jac_pair(blockIdx.x, step, ne, p, q);
+  __shared__ JacRot R;
+  if (threadIdx.x == 0) {
+    const double app = A[(size_t)p * ne + p].x, aqq = A[(size_t)q * ne + q].x;
+    const double2 apq = A[(size_t)q * ne + p];                    // element (row p, column q)
+    const double mod = hypot(apq.x, apq.y);
+    JacRot r;
+    if (mod <= 1e-300 || mod * mod <= 1e-34 * fabs(app * aqq)) { r.c = 1.0; r.s = 0.0; r.ex = 1.0; r.ey = 0.0; }
+    else {
+      const double tau = (aqq - app) / (2.0 * mod);
+      const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+      r.c = 1.0 / sqrt(1.0 + t * t); r.s = t * r.c; r.ex = apq.x / mod; r.ey = apq.y / mod;
+    }
+    R = r; rot[blockIdx.x] = r;
+  }
+  __syncthreads();
+  const double c = R.c, s = R.s, ex = R.ex, ey = R.ey;
+  if (s == 0.0) return;
+  for (int i = threadIdx.x; i < 2 * ne; i += 256) {
+    double2* M = i < ne ? A : Z;
+    const int r = i < ne ? i : i - ne;
+    const double2 xp = M[(size_t)p * ne + r], xq = M[(size_t)q * ne + r];
+    // new_p = c xp - s e^{-i phi} xq ; new_q = s e^{i phi} xp + c xq
+    const double2 eq = make_double2(ex * xq.x + ey * xq.y, ex * xq.y - ey * xq.x);      // e^{-i phi} xq
+    const double2 ep = make_double2(ex * xp.x - ey * xp.y, ex * xp.y + ey * xp.x);      // e^{+i phi} xp
+    M[(size_t)p * ne + r] = make_double2(c * xp.x - s * eq.x, c * xp.y - s * eq.y);
+    M[(size_t)q * ne + r] = make_double2(s * ep.x + c * xq.x, s * ep.y + c * xq.y);
+  }
+}
+// ROW operation A <- J^H A for all pairs: thread (column r, pair k)
+__global__ void __launch_bounds__(256) k_jac_rows(double2* __restrict__ A, int ne, int step, const JacRot* __restrict__ rot)
+{
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= ne) return;
+  int p, q;
+  jac_pair(blockIdx.y, step, ne, p, q);
+  const JacRot R = rot[blockIdx.y];
+  if (R.s == 0.0) return;
+  const double c = R.c, s = R.s, ex = R.ex, ey = R.ey;
+  const double2 xp = A[(size_t)r * ne + p], xq = A[(size_t)r * ne + q];
+  // new_p = c xp - s e^{i phi} xq ; new_q = s e^{-i phi} xp + c xq
+  const double2 eq = make_double2(ex * xq.x - ey * xq.y, ex * xq.y + ey * xq.x);
+  const double2 ep = make_double2(ex * xp.x + ey * xp.y, ex * xp.y - ey * xp.x);
+  double2 np_ = make_double2(c * xp.x - s * eq.x, c * xp.y - s * eq.y);
+  double2 nq_ = make_double2(s * ep.x + c * xq.x, s * ep.y + c * xq.y);
+  if (r == p) { np_.y = 0.0; }                   // the diagonal stays real, the annihilated pair exactly zero
+  if (r == q) { nq_.y = 0.0; np_ = make_double2(0.0, 0.0); }
+  if (r == p) nq_ = make_double2(0.0, 0.0);
+  A[(size_t)r * ne + p] = np_;
+  A[(size_t)r * ne + q] = nq_;
+}
+// sums[0] = sum_{i != j} |a_ij|^2, sums[1] = sum |a_ij|^2 (one CTA, fixed order)
+__global__ void __launch_bounds__(1024) k_jac_off(const double2* __restrict__ A, int ne, double* __restrict__ sums)
+{
+  __shared__ double ro[1024], rt[1024];
+  double o = 0.0, t = 0.0;
+  for (size_t i = threadIdx.x; i < (size_t)ne * ne; i += 1024) {
+    const double2 a = A[i];
+    const double v = a.x * a.x + a.y * a.y;
+    t += v;
+    if ((int)(i / ne) != (int)(i % ne)) o += v;
+  }
+  ro[threadIdx.x] = o; rt[threadIdx.x] = t;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { ro[threadIdx.x] += ro[threadIdx.x + s]; rt[threadIdx.x] += rt[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sums[0] = ro[0]; sums[1] = rt[0]; }
+}
+__global__ void __launch_bounds__(256) k_jac_diag(const double2* __restrict__ A, int ne, int n, double* __restrict__ w)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) w[i] = A[(size_t)i * ne + i].x;
+}
+// second operand of c z: T[m, col] = Z[m, perm[col]] in the layout la_back reads (cf. k_gram_operand)
+template <int IS_REAL>
+__global__ void __launch_bounds__(256) k_diag_operand(const double2* __restrict__ Z, int ne, int n, const int* __restrict__ perm, double* __restrict__ fs, int FP)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const int col = (int)(idx / n), m = (int)(idx % n);
+  const double2 t = Z[(size_t)perm[col] * ne + m];
+  if (IS_REAL) fs[(size_t)col * FP + m] = t.x;
+  else {
+    double* o = fs + (size_t)col * FP + (m >> 3) * 24 + (m & 7);
+    o[0] = t.x; o[8] = t.y; o[16] = t.x + t.y;
+  }
+}
+
+}  // namespace qb200
+
+static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc, int eigvec, double* w_host, int* sweeps_out)
+{
+  int rc;
+  const LaGeom g = la_geometry(la, n, n, false, ldc);
+  la->nchunks_last = g.nchunks;
+  if ((rc = la_prepare_W(la, g))) return rc;
+  const int ncols = la->is_real ? n : 2 * n;
+  const int ne = (n + 1) & ~1;
+  if ((rc = nl_ensure(&la->part, &la->part_cap, (size_t)g.ksplit * ncols * g.Mp))) return rc;
+  if ((rc = nl_ensure(&la->fs, &la->fs_cap, (size_t)n * g.FP))) return rc;
+  if ((rc = nl_ensure(&la->S, &la->S_cap, 2 * (size_t)ne * ne + 8))) return rc;
+  if ((rc = nl_ensure(&la->X, &la->X_cap, 2 * (size_t)ne * ne))) return rc;
+  // Dinv doubles as the small work area: A (ne x ne) | rot[ne/2] | sums[2] | w[n] | perm[n]
+  const size_t rot_d = (sizeof(JacRot) * (size_t)(ne / 2) + 7) / 8;
+  if ((rc = nl_ensure(&la->Dinv, &la->Dinv_cap, 2 * (size_t)ne * ne + rot_d + 2 + n + (n + 1) / 2 + 8))) return rc;
+  const int ngw = la->ngw;
+  // S = c^H (H c)
+  for (int ch = 0; ch < g.nchunks; ch++) {
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, hc, ldc, n, ch > 0, 0))) return rc;
+  }
+  const size_t total = (size_t)n * n;
+  const int nblk = (int)((total + 255) / 256);
+  if (la->is_real) k_la_finish<1, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)hc, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
+  else k_la_finish<0, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)hc, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
+  LA_LAUNCH_CHECK(la);
+  double2* A = (double2*)la->Dinv;
+  double2* Z = (double2*)la->X;
+  JacRot* rot = (JacRot*)(la->Dinv + 2 * (size_t)ne * ne);
+  double* sums = la->Dinv + 2 * (size_t)ne * ne + rot_d;
+  double* wd = sums + 2;
+  int* perm_d = (int*)(wd + n);
+  k_jac_init<<<(int)(((size_t)ne * ne + 255) / 256), 256, 0, la->stream>>>((const double2*)la->S, n, ne, A, Z);
+  LA_LAUNCH_CHECK(la);
+  int sweeps = 0;
+  const int maxsweep = 30;                                  // the reference's own jacobi() uses the same cap (Wavefunction.cc:1594)
+  for (; sweeps < maxsweep; sweeps++) {
+    double h[2];
+    k_jac_off<<<1, 1024, 0, la->stream>>>(A, ne, sums);
+    LA_LAUNCH_CHECK(la);
+    QB_CUDA(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, la->stream));
+    QB_CUDA(cudaStreamSynchronize(la->stream));
+    if (!(h[0] > 1e-30 * h[1])) break;                      // off-diagonal norm below 1e-15 ||h||
+    for (int step = 0; step < ne - 1; step++) {
+      k_jac_cols<<<ne / 2, 256, 0, la->stream>>>(A, Z, ne, step, rot);
+      k_jac_rows<<<dim3((ne + 255) / 256, ne / 2), 256, 0, la->stream>>>(A, ne, step, rot);
+      la->launches += 2;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return qb200::cuda_fail(e, "jacobi sweep", __FILE__, __LINE__);
+  }
+  if (sweeps_out) *sweeps_out = sweeps;
+  k_jac_diag<<<(n + 255) / 256, 256, 0, la->stream>>>(A, ne, n, wd);
+  LA_LAUNCH_CHECK(la);
+  std::vector<double> w(n);
+  QB_CUDA(cudaMemcpyAsync(w.data(), wd, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+  QB_CUDA(cudaStreamSynchronize(la->stream));
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; i++) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return w[a] < w[b]; });        // ascending, as LAPACK
+  for (int i = 0; i < n; i++) w_host[i] = w[perm[i]];
+  if (!eigvec) return QB200_OK;
+  QB_CUDA(cudaMemcpyAsync(perm_d, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, la->stream));
+  if (g.FP != (g.m3 ? 3 * n : n)) QB_CUDA(cudaMemsetAsync(la->fs, 0, (size_t)n * g.FP * sizeof(double), la->stream));
+  if (la->is_real) k_diag_operand<1><<<nblk, 256, 0, la->stream>>>(Z, ne, n, perm_d, la->fs, g.FP);
+  else k_diag_operand<0><<<nblk, 256, 0, la->stream>>>(Z, ne, n, perm_d, la->fs, g.FP);
+  LA_LAUNCH_CHECK(la);
+  // c <- c z from the packed copy, chunk by chunk (a chunk's rows of c are overwritten only after they were packed)
+  for (int i = 0; i < g.nchunks; i++) {
+    const int ch = g.nchunks - 1 - i;
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if (i > 0 && (rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_back(la, g, la->W, gbeg, gcount, c, ldc, n, 1, 0))) return rc;
+  }
+  QB_CUDA(cudaStreamSynchronize(la->stream));     // perm (host vector) was uploaded asynchronously
+  return QB200_OK;
+}
+
+extern "C" int qb200_diag(qb200_la* la, int ldc, int nst, double* c, const double* hc, int eigvec, double* w, int* sweeps)
+{
+  if (sweeps) *sweeps = 0;
+  if (!la || !c || !hc || !w || nst < 0 || ldc < la->ngw) { set_error("qb200_diag: bad argument"); return QB200_EINVAL; }
+  if (nst == 0) return QB200_OK;
+  if (is_device_ptr(w)) { set_error("qb200_diag: w is a host array (valarray<double> in the reference)"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(la->device));
+  int rc;
+  const size_t cb = 2 * (size_t)ldc * nst;
+  double* cd = c; const double* hd = hc;
+  if (!is_device_ptr(c)) {
+    if ((rc = nl_ensure(&la->st_c, &la->st_c_cap, cb))) return rc;
+    QB_CUDA(cudaMemcpyAsync(la->st_c, c, cb * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    cd = la->st_c;
+  }
+  if (!is_device_ptr(hc)) {
+    if ((rc = nl_ensure(&la->st_x, &la->st_x_cap, cb))) return rc;
+    QB_CUDA(cudaMemcpyAsync(la->st_x, hc, cb * sizeof(double), cudaMemcpyHostToDevice, la->stream));
+    hd = la->st_x;
+  }
+  if ((rc = la_diag_dev(la, ldc, nst, cd, hd, eigvec, w, sweeps))) return rc;
+  if (eigvec && cd != c) {
+    QB_CUDA(cudaMemcpyAsync(c, cd, cb * sizeof(double), cudaMemcpyDeviceToHost, la->stream));
+    QB_CUDA(cudaStreamSynchronize(la->stream));
+  }
+  return QB200_OK;
+}

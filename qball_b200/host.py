@@ -311,6 +311,15 @@ class SubspaceLA:
         capi._check(self._L.qb200_residual(self._h, ldc, nall, capi.ptr(c), nst, capi.ptr(hc), capi.ptr(a)), "qb200_residual")
         return hc
 
+    def diag(self, c, hc, eigvec: bool = True):
+        """Wavefunction::diag (Wavefunction.cc:1510-1715): eigenvalues (ascending) of c^H (H c); eigvec: c <- c z in place.
+        Returns (w, sweeps)."""
+        nst, ldc = _block_dims(c)
+        w = np.zeros(nst)
+        sw = C.c_int(0)
+        capi._check(self._L.qb200_diag(self._h, ldc, nst, capi.ptr(c), capi.ptr(hc), int(bool(eigvec)), capi.ptr(w), C.byref(sw)), "qb200_diag")
+        return w, sw.value
+
     def psda_update(self, c, dc, c_last, dc_last, occ, precdiag, extrapolate: bool, comm=None) -> float:
         """the rest of PSDAWavefunctionStepper::update (PSDAWavefunctionStepper.cc:93-225, 281-395) on device-resident
         blocks: dc <- -K dc; Anderson extrapolation with theta from the occupation-weighted dot products (summed over the

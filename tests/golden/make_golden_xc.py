@@ -42,7 +42,7 @@ def run_reference(rho, grad):
 def main():
     rho, grad = points()
     out = run_reference(rho, grad)
-    fn = os.path.join(HERE, "xc_points.npz")
+    fn = os.path.join(HERE, "xc", "xc_points.npz")
     np.savez_compressed(fn, rho=rho, grad=grad, **out)
     print(f"xc_points: {rho.size} points -> {os.path.getsize(fn) / 1024:.0f} KiB")
 

@@ -258,3 +258,61 @@ def test_cuda_scf_iterations_stay_on_device_vs_oracle():
         assert abs(enl - e_ref) < 1e-10 * max(1.0, abs(e_ref)) and abs(ekin - k_ref) < 1e-10 * abs(k_ref)
         assert abs(th - t_ref) < 1e-8 * max(1.0, abs(t_ref)), (it, th, t_ref)
         assert relerr(rho, r_ref) < TOL and relerr(cd.cpu().numpy(), c_ref) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_oracle_diag_matches_reference_fixture(name):
+    """eigenvalues of psi^H (H psi): the oracle (LAPACK via numpy on the reference's formula) against the reference's own
+    syevd / heev('l') calls (tests/golden/la/*.npz diag_w, Wavefunction.cc:1538-1539, 1612, 1641, 1693)"""
+    g, b, c = _inputs(name)
+    la = _la_golden(name)
+    hpsi = g["hpsi"].reshape(c.shape)
+    w, _, _ = P.diag(c, hpsi, g["is_real"])
+    assert np.abs(w - la["diag_w"]).max() <= 1e-12 * max(1.0, np.abs(la["diag_w"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names("full"))
+def test_cuda_diag_vs_reference_fixture(name):
+    import torch
+    from qball_b200 import host as H
+    g, b, c = _inputs(name)
+    la_g = _la_golden(name)
+    hpsi = np.ascontiguousarray(g["hpsi"].reshape(c.shape))
+    la = H.SubspaceLA(b)
+    w, sweeps = la.diag(c.copy(), hpsi, eigvec=False)                       # host pointers
+    assert np.abs(w - la_g["diag_w"]).max() <= 1e-10 * max(1.0, np.abs(la_g["diag_w"]).max()), (w, la_g["diag_w"])
+    assert 1 <= sweeps < 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kpoint,fc,nst", [((0, 0, 0), False, 37), ((0.1, 0.2, 0.3), False, 130), ((0, 0, 0), True, 64)])
+def test_cuda_diag_eigenpairs_vs_oracle(kpoint, fc, nst):
+    """Wavefunction::diag with eigenvectors at sizes that cross the GEMM tiles (odd n included): eigenvalues against LAPACK
+    (the oracle) to 1e-10; the rotated block c z: z unitary, z^H h z = diag(w), and the subspace unchanged"""
+    import torch
+    from qball_b200 import host as H
+    cell, ecut = (10, 0, 0, 0, 11, 0, 0, 0, 12), 6.0
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    ngw, ldc = b["ngw"], b["ngw"] + 2
+    c = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=71), b["is_real"])
+    hc = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=72)
+    # a Hermitian "H c": symmetrise the subspace matrix through hc <- hc + c (h^H - h)/2 is not needed: diag reads the LOWER
+    # triangle only (LAPACK 'l'), so any hc defines a Hermitian problem -- exactly what the reference solves
+    w_ref, z_ref, h = P.diag(c, hc, b["is_real"])
+    la = H.SubspaceLA(b)
+    cd = torch.from_numpy(c.copy()).cuda()
+    w, sweeps = la.diag(cd, torch.from_numpy(hc).cuda(), eigvec=True)
+    assert np.abs(w - w_ref).max() <= 1e-10 * np.abs(w_ref).max(), np.abs(w - w_ref).max()
+    cn = cd.cpu().numpy()
+    assert np.all(cn[:, ngw:] == 0)
+    # z implied by c_new = c z (c orthonormal): z = S(c, c_new), with the reference's real-basis inner product
+    z = P.subspace_h(c, cn, b["is_real"])
+    hl = np.tril(h) + np.tril(h, -1).conj().T                              # the matrix LAPACK 'l' sees
+    n = nst
+    assert np.abs(z.conj().T @ z - np.eye(n)).max() < 1e-11
+    assert np.abs(z.conj().T @ hl @ z - np.diag(w)).max() < 1e-10 * np.abs(w_ref).max()
+    # eigenvalues only: the block is left untouched
+    cd2 = torch.from_numpy(c.copy()).cuda()
+    w2, _ = la.diag(cd2, torch.from_numpy(hc).cuda(), eigvec=False)
+    assert np.array_equal(cd2.cpu().numpy(), c) and np.abs(w2 - w).max() <= 1e-13 * np.abs(w).max()

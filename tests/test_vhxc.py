@@ -1,7 +1,7 @@
 """v(r) producers on the density basis: EnergyFunctional::update_vhxc (EnergyFunctional.cc:353-975)
 with XCPotential::update (XCPotential.cc:104-460) and the unpolarized LDA / PBE functionals.
 CPU: the oracle's functionals against golden vectors produced by the reference's own LDAFunctional / PBEFunctional
-(tests/golden/xc_points.npz, bit-exact) and live against the compiled reference; properties of the oracle's update_vhxc.
+(tests/golden/xc/xc_points.npz, bit-exact) and live against the compiled reference; properties of the oracle's update_vhxc.
 GPU: qb200_update_vhxc through the C ABI against the oracle.  (The reference-level pin is tests/test_reference_shim.py:
 the reference's own SCF runs with update_vhxc forwarded to the device reproduce every printed energy to 1e-8 Ha.)"""
 import os
@@ -15,7 +15,7 @@ from util import GOLDEN, TOL, relerr
 
 
 def _xc_fixture():
-    z = np.load(os.path.join(GOLDEN, "xc_points.npz"))
+    z = np.load(os.path.join(GOLDEN, "xc", "xc_points.npz"))
     return {k: z[k] for k in z.files}
 
 
