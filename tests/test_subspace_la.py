@@ -308,7 +308,7 @@ def test_cuda_diag_eigenpairs_vs_oracle(kpoint, fc, nst):
     assert np.all(cn[:, ngw:] == 0)
     # z implied by c_new = c z (c orthonormal): z = S(c, c_new), with the reference's real-basis inner product
     z = P.subspace_h(c, cn, b["is_real"])
-    hl = np.tril(h) + np.tril(h, -1).conj().T                              # the matrix LAPACK 'l' sees
+    hl = np.tril(h, -1) + np.tril(h, -1).conj().T + np.diag(np.diag(h).real)   # the matrix LAPACK 'l' sees (real diagonal)
     n = nst
     assert np.abs(z.conj().T @ z - np.eye(n)).max() < 1e-11
     assert np.abs(z.conj().T @ hl @ z - np.diag(w)).max() < 1e-10 * np.abs(w_ref).max()
