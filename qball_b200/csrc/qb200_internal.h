@@ -80,6 +80,7 @@ struct qb200_plan {
   size_t smem_xr[2], smem_yc[4];       // dynamic shared memory of k_xrows2<+1/-1>, k_ycols2<OP>
   bool z2;                             // second-generation z-column kernels in use
   int z_static;                        // 0 run-time shape, 1 compiled 112-plane shape (MgO216)
+  int z_threads;                       // threads per CTA of the v2 z kernels (256, or 128 with four CTAs per SM)
   size_t smem_zb[2], smem_zf[2];       // their dynamic shared memory, [MODE_SINGLE], [MODE_PAIR]
   int zslots_b[2], zslots_f[2];        // resident CTAs on the whole device
   long long ws_bytes;

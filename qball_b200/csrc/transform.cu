@@ -227,7 +227,10 @@ static int ensure_work(qb200_plan* p, int units)
 typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;
 typedef qb200::SplitShape<126, 126, 29, 68, 29, 68, 16, 8> ShapeSi54p;    // examples/si54p at 65 Ry: 126^3 grid, |h|,|k| <= 28
 typedef qb200::ZShape<112, 29, 26, 60> ZbMgO216;   // examples/MgO216: 112 planes, |l| <= 25; 29 / 22 columns per tile fill one wave
-typedef qb200::ZShape<112, 22, 26, 60> ZfMgO216;   // examples/gold_benchmark: 252 x 252 x 896 grid
+typedef qb200::ZShape<112, 22, 26, 60> ZfMgO216;
+// the same shape in CTAs of 128 threads with tiles half as wide (four resident CTAs per SM instead of two; QB200_Z_THREADS=128)
+typedef qb200::ZShape<112, 15, 26, 60> ZbMgO216n;
+typedef qb200::ZShape<112, 11, 26, 60> ZfMgO216n;   // examples/gold_benchmark: 252 x 252 x 896 grid
 
 template <class S> static bool split_shape_matches(const qb200::DevPlan& d, int hmax, int rowb)
 {
@@ -280,7 +283,7 @@ bool z2_pick(const qb200_plan* p, const std::vector<int>& first, bool fwd, size_
     }
     const size_t need = c.smem[d.is_real ? MODE_PAIR : MODE_SINGLE];
     if (need > (size_t)p->max_smem) continue;
-    c.ctas = (int)std::min<size_t>(2, smem_sm / (need + 1024));
+    c.ctas = (int)std::min<size_t>(p->z_threads == 128 ? 4 : 2, smem_sm / (need + 1024));
     if (c.ctas < 1) continue;
     const long slots = (long)p->nsm * c.ctas;
     const long nzb = (d.nrods + c.rb - 1) / c.rb;
@@ -302,6 +305,8 @@ static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t sme
   // zq packs (digit-reversed z) | (column << 12) in one int: 12 bits of z, 19 bits of column
   if (d.np2 > 4095 || d.nvec >= (1 << 19)) return QB200_OK;
   int fb = 0, ff = 0;
+  p->z_threads = 256;
+  if (const char* e = getenv("QB200_Z_THREADS")) if (atoi(e) == 128) p->z_threads = 128;
   if (const char* e = getenv("QB200_ZB_COLS")) fb = atoi(e);
   if (const char* e = getenv("QB200_ZF_COLS")) ff = atoi(e);
   // compiled shape (MgO216's 112 planes): its tile widths are fixed at compile time
@@ -310,6 +315,7 @@ static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t sme
     const char* ns = getenv("QB200_NO_STATIC");
     if (!(ns && ns[0] == '1') && !d.is_real && d.np2 == ZbMgO216::NP2 && lmax < ZbMgO216::ZSPLIT && fb == 0 && ff == 0) {
       p->z_static = 1; fb = ZbMgO216::CB; ff = ZfMgO216::CB;
+      if (p->z_threads == 128) { fb = ZbMgO216n::CB; ff = ZfMgO216n::CB; }
     }
   }
   Z2Choice b, f;
@@ -321,12 +327,13 @@ static int configure_z2(qb200_plan* p, const std::vector<int>& first, size_t sme
   if ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, DynZ>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_bwd2<MODE_PAIR, DynZ>, p->smem_zb[1])) ||
       (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, DynZ>, p->smem_zf[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_PAIR, DynZ>, p->smem_zf[1]))) return rc;
   if (p->z_static == 1 &&
-      ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, ZbMgO216>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, ZfMgO216>, p->smem_zf[0])))) return rc;
+      ((rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, ZbMgO216>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, ZfMgO216>, p->smem_zf[0])) ||
+       (rc = opt_in_smem(k_zcol_bwd2<MODE_SINGLE, ZbMgO216n>, p->smem_zb[0])) || (rc = opt_in_smem(k_zcol_fwd2<MODE_SINGLE, ZfMgO216n>, p->smem_zf[0])))) return rc;
   int n = 0;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_SINGLE, DynZ>, 256, p->smem_zb[0])); p->zslots_b[0] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_PAIR, DynZ>, 256, p->smem_zb[1])); p->zslots_b[1] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_SINGLE, DynZ>, 256, p->smem_zf[0])); p->zslots_f[0] = std::max(1, n) * p->nsm;
-  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_PAIR, DynZ>, 256, p->smem_zf[1])); p->zslots_f[1] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_SINGLE, DynZ>, p->z_threads, p->smem_zb[0])); p->zslots_b[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_bwd2<MODE_PAIR, DynZ>, p->z_threads, p->smem_zb[1])); p->zslots_b[1] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_SINGLE, DynZ>, p->z_threads, p->smem_zf[0])); p->zslots_f[0] = std::max(1, n) * p->nsm;
+  QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zcol_fwd2<MODE_PAIR, DynZ>, p->z_threads, p->smem_zf[1])); p->zslots_f[1] = std::max(1, n) * p->nsm;
   p->z2 = true;
   return QB200_OK;
 }
@@ -680,9 +687,11 @@ static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int
   prof_begin(0, p->stream);
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zb_rb, p->zslots_b[mode], nunits);
-    if (mode == MODE_PAIR) k_zcol_bwd2<MODE_PAIR, DynZ><<<g2, 256, p->smem_zb[1], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
-    else if (p->z_static == 1) k_zcol_bwd2<MODE_SINGLE, ZbMgO216><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
-    else k_zcol_bwd2<MODE_SINGLE, DynZ><<<g2, 256, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    const int zt = p->z_threads;
+    if (mode == MODE_PAIR) k_zcol_bwd2<MODE_PAIR, DynZ><<<g2, zt, p->smem_zb[1], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else if (p->z_static == 1 && zt == 128) k_zcol_bwd2<MODE_SINGLE, ZbMgO216n><<<g2, zt, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else if (p->z_static == 1) k_zcol_bwd2<MODE_SINGLE, ZbMgO216><<<g2, zt, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
+    else k_zcol_bwd2<MODE_SINGLE, DynZ><<<g2, zt, p->smem_zb[0], p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits);
   }
   else if (mode == MODE_PAIR) k_zcol_bwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
   else k_zcol_bwd<MODE_SINGLE><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt);
@@ -699,12 +708,15 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
   prof_begin(2, p->stream);
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zf_rb, p->zslots_f[mode], nunits);
+    const int zt = p->z_threads;
     if (mode == MODE_PAIR)
-      k_zcol_fwd2<MODE_PAIR, DynZ><<<g2, 256, p->smem_zf[1], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+      k_zcol_fwd2<MODE_PAIR, DynZ><<<g2, zt, p->smem_zf[1], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+    else if (p->z_static == 1 && zt == 128)
+      k_zcol_fwd2<MODE_SINGLE, ZfMgO216n><<<g2, zt, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
     else if (p->z_static == 1)
-      k_zcol_fwd2<MODE_SINGLE, ZfMgO216><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+      k_zcol_fwd2<MODE_SINGLE, ZfMgO216><<<g2, zt, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
     else
-      k_zcol_fwd2<MODE_SINGLE, DynZ><<<g2, 256, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
+      k_zcol_fwd2<MODE_SINGLE, DynZ><<<g2, zt, p->smem_zf[0], p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale, nunits);
   }
   else if (mode == MODE_PAIR)
     k_zcol_fwd<MODE_PAIR><<<g, 256, p->smem_z, p->stream>>>(p->d, (const cplx*)p->zt, (cplx*)out, ldc, accumulate, kpg2, (const cplx*)cin, scale);
