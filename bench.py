@@ -24,6 +24,7 @@ import threading
 import time
 
 import numpy as np
+from ctypes import byref as C_byref, c_double as C_double
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -761,32 +762,76 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
                     cw, cl, dl = c.clone(), torch.zeros_like(c), torch.zeros_like(c)
                     la2.gram(cw) if world == 1 else None
                 prec = np.where(0.5 * b["kpg2"] < 4.0, 0.5 / 4.0, 0.5 / np.maximum(0.5 * b["kpg2"], 1e-300))   # Preconditioner.cc:47-90, ecutprec 8 Ry
+                # the density basis (k = 0, 4 ecut: ChargeDensity.cc:77-81) and Gaussian stand-ins for the ionic tables
+                from qball_b200 import basis as BB
+                vb = BB.make_basis(wl["cell"], 4.0 * wl["ecut"], (0, 0, 0), False)
+                vft = H.FourierTransform(vb, np0, np1, np2, device=local_rank, stream=stream)
+                g2 = vb["kpg2"]
+                with torch.cuda.stream(stream):
+                    g2i_d = torch.from_numpy(np.where(g2 > 0, 1.0 / np.where(g2 > 0, g2, 1.0), 0.0)).to(dev)
+                    gx_d = torch.from_numpy(np.ascontiguousarray(vb["kpgx"])).to(dev)
+                    vion_d = torch.from_numpy((-(40.0 / omega) * np.exp(-0.35 * g2)).astype(np.complex128)).to(dev)
+                    rhops_d = torch.from_numpy((-(float(np.sum(occ)) * world / omega) * np.exp(-0.16 * g2)).astype(np.complex128)).to(dev)
+                    rhog_d = torch.zeros(vb["ngw"], dtype=torch.complex128, device=dev)
+                    vscf = v.clone()
                 it = [0]
+                parts = {}
 
                 def scf_step():
+                    t = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
                     with torch.cuda.stream(stream):
-                        e = H.hpsi(ft, nlp, cw, occ, hv, kpg2, hpsi)
-                        H.ekin_sums(ft, cw, occ, b["is_real"], kpg2)
-                        call = PAR.allgather_states(cw, world * nst) if world > 1 else cw
-                        la2.residual(call, hpsi)
-                        la2.psda_update(cw, hpsi, cl, dl, occ, prec, it[0] > 0, comm if world > 1 else None)
-                        if world == 1:
-                            la2.gram(cw)
+                        t[0].record(stream)
                         rho.zero_()
                         H.compute_density(ft, cw, 1.0, occ, omega, rho)
                         if world > 1:
                             comm.allreduce_rho(rho, stream)
-                        hrho.copy_(rho, non_blocking=True)
+                        nel = C_double()
+                        capi._check(ft._L.qb200_density_finish(vft._h, capi.ptr(rho), omega, capi.ptr(rhog_d), C_byref(nel)), "qb200_density_finish")
+                        t[1].record(stream)
+                        en = H.update_vhxc(vft, H.XC_LDA, rho, rhog_d, gx_d, g2i_d, vion_d, rhops_d, omega, vscf)     # rho -> v(r), on the device
+                        t[2].record(stream)
+                        e = H.hpsi(ft, nlp, cw, occ, vscf, kpg2, hpsi)
+                        ek = H.ekin_sums(ft, cw, occ, b["is_real"], kpg2)[0]
+                        t[3].record(stream)
+                        call = PAR.allgather_states(cw, world * nst) if world > 1 else cw
+                        la2.residual(call, hpsi)
+                        t[4].record(stream)
+                        la2.psda_update(cw, hpsi, cl, dl, occ, prec, it[0] > 0, comm if world > 1 else None)
+                        t[5].record(stream)
+                        if world == 1:
+                            la2.gram(cw)
+                        t[6].record(stream)
                     stream.synchronize()
                     it[0] += 1
-                    return e
+                    for k, (a, bb) in {"density+rhog": (0, 1), "update_vhxc": (1, 2), "hpsi+ekin": (2, 3), "residual": (3, 4),
+                                       "psda_update": (4, 5), "gram": (5, 6)}.items():
+                        parts[k] = parts.get(k, 0.0) + t[a].elapsed_time(t[bb])
+                    return e, ek, en, nel.value
 
                 ns = 3
+                scf_step()
+                parts.clear()
                 dts = timed(scf_step, ns)
+                nsteps_timed = ns + 1           # timed() runs one untimed call first; parts accumulate over all of them
                 scf_iter = {"ms_per_iteration": dts / ns * 1e3, "state_applies_per_s": world * nst * ns / dts, "iterations": ns,
-                            "what": "H psi + E_kin + residual (a = c^H Hc, Hc -= c a) + preconditioned Anderson update (qb200_psda_update)"
-                                    + (" + SlaterDet::gram" if world == 1 else " (band-sharded: all-gather of c for the residual; the distributed Cholesky is not built, gram skipped)")
-                                    + " + density; wavefunction resident in HBM throughout, v in / rho out through pinned host buffers"}
+                            "parts_ms": {k: vv / nsteps_timed for k, vv in parts.items()},
+                            "pcie_bytes_per_iteration": 8 * 24,
+                            "what": "one electronic iteration of BOSampleStepper / PSDA with NOTHING but scalars crossing PCIe: density + rho(G) "
+                                    "(qb200_compute_density, qb200_density_finish) -> v(r) (qb200_update_vhxc, LDA) -> H psi + E_kin -> residual -> "
+                                    "preconditioned Anderson update (qb200_psda_update)"
+                                    + (" -> SlaterDet::gram" if world == 1 else " (band-sharded: all-gather of c for the residual; the distributed Cholesky is not built, gram skipped)")}
+                # Wavefunction::diag of the block (eigenvalues + rotation), timed once
+                if world == 1:
+                    with torch.cuda.stream(stream):
+                        td0, td1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        H.hpsi(ft, nlp, cw, occ, vscf, kpg2, hpsi)
+                        td0.record(stream)
+                        wd, sweeps = la2.diag(cw, hpsi, eigvec=True)
+                        td1.record(stream)
+                    stream.synchronize()
+                    scf_iter["diag_ms"] = td0.elapsed_time(td1)
+                    scf_iter["diag_jacobi_sweeps"] = sweeps
+                del vft, g2i_d, gx_d, vion_d, rhops_d, rhog_d, vscf
                 del la2, cw, cl, dl
             except Exception as ex:  # noqa: BLE001
                 scf_iter = {"error": str(ex)[:300]}
