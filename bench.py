@@ -516,6 +516,17 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
                         "traffic": traffic_of("k_plane_s<0>", "k_plane_s<1>") if ft.fused() else None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": xy_bytes_step * steps / xy_n,
                         "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
+        # the stage is bound ON CHIP before it is bound by HBM: the other two roofs, from the committed ncu
+        # --set full capture of this command (profiles/ncu_traffic.json; static evidence, not measured in this run)
+        if ft.fused() and wl_name == "mgo216":
+            onchip = {k: {"fp64_pipe_active_frac": ncu_traffic[k].get("fp64_pipe_active_pct", 0.0) / 100.0,
+                          "smem_pipe_wavefronts_per_cycle": ncu_traffic[k].get("smem_wavefronts_per_cycle_per_sm"),
+                          "dram_bytes_per_launch": ncu_traffic[k]["dram_bytes_per_launch"]}
+                      for k in ("k_plane_s<0>", "k_plane_s<1>") if k in ncu_traffic and "fp64_pipe_active_pct" in ncu_traffic[k]}
+            if onchip:
+                roofline_hbm["on_chip_roofs"] = {"kernels": onchip, "source": "profiles/ncu_traffic.json (ncu --set full of this command)",
+                                                 "note": "FP64 issue floor of the stage: ~6.1 ms per step at the measured DFMA rate against 13.1 ms "
+                                                         "measured; shared-memory pipe 0.6-0.7 wavefronts per cycle per SM; the two overlap by ~10 % (DESIGN.md section 7)"}
     # the whole local path (z columns + xy stage, both directions) against the HBM roofline with SURVEY.md section 8d's
     # per-unit algorithmic bytes: B_Hpsi = 48*ngw*cper + 64*nvec*np2 + 8*N, B_rho = 16*ngw + 32*nvec*np2 (+16*N per build)
     cper = 2 if b["is_real"] else 1

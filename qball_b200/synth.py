@@ -68,18 +68,22 @@ def _splitmix_uniform_torch(seed: int, start: int, count: int, device):
     return lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
 
 
-def synth_coefficients_torch(kpg2, ecut, nst, ldc, is_real, seed=1, first_state=0, device="cpu"):
+def synth_coefficients_torch(kpg2, ecut, nst, ldc, is_real, seed=1, first_state=0, device="cpu", block=64):
     """synth_coefficients on a torch device (same values to the last bit up to the exp() of the damping factor, which is
-    taken from numpy): returns an (nst, ldc) complex128 tensor"""
+    taken from numpy): returns an (nst, ldc) complex128 tensor.  Generated `block` states at a time (a dozen tensor ops per
+    block, so that a profiler's launch list is not flooded with per-state helper kernels)."""
     import torch
     ngw = int(kpg2.shape[0])
     damp = torch.from_numpy(np.exp(-np.asarray(kpg2) / (0.5 * ecut))).to(device)
     c = torch.zeros((nst, ldc), dtype=torch.complex128, device=device)
     cr = torch.view_as_real(c)
-    for n in range(nst):
-        u = _splitmix_uniform_torch(seed, 2 * ngw * (first_state + n), 2 * ngw, device)
-        cr[n, :ngw, 0] = (u[0::2] - 0.5) * damp
-        cr[n, :ngw, 1] = (u[1::2] - 0.5) * damp
+    for n0 in range(0, nst, block):
+        nb = min(block, nst - n0)
+        # the counters of state n are 2*ngw*(first_state + n) + [0, 2*ngw): contiguous over a block of states
+        u = _splitmix_uniform_torch(seed, 2 * ngw * (first_state + n0), 2 * ngw * nb, device).view(nb, ngw, 2)
+        cr[n0:n0 + nb, :ngw, 0] = (u[:, :, 0] - 0.5) * damp
+        cr[n0:n0 + nb, :ngw, 1] = (u[:, :, 1] - 0.5) * damp
+        del u
     if is_real:
         cr[:, 0, 1] = 0.0
     return c

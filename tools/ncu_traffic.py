@@ -17,11 +17,25 @@ for rep in sys.argv[1:]:
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[h.index(k)].replace(",", "")) * UNIT[units[h.index(k)]]
         e = out.setdefault(key, {"dram_bytes_per_launch": 0.0, "launches": 0, "grid": int(r[h.index("launch__grid_size")].replace(",", "")),
-                                 "source": []})
+                                 "source": [], "fp64_pipe_active_pct": 0.0, "tensor_pipe_active_pct": 0.0, "smem_wavefronts_per_cycle_per_sm": 0.0,
+                                 "duration_ms": 0.0})
         e["dram_bytes_per_launch"] += tot
         e["launches"] += 1
+
+        def num(k):
+            return float(r[h.index(k)].replace(",", "") or 0) if k in h else 0.0
+
+        e["fp64_pipe_active_pct"] += num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+        e["tensor_pipe_active_pct"] += num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        cyc, nsm = num("sm__cycles_elapsed.max"), 148.0
+        if cyc > 0:
+            e["smem_wavefronts_per_cycle_per_sm"] += num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / (cyc * nsm)
+        dur = num("gpu__time_duration.sum")
+        du = units[h.index("gpu__time_duration.sum")] if "gpu__time_duration.sum" in h else "ms"
+        e["duration_ms"] += dur * {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(du, 1.0)
         if rep not in e["source"]:
             e["source"].append(rep)
 for e in out.values():
-    e["dram_bytes_per_launch"] /= e["launches"]
+    for k in ("dram_bytes_per_launch", "fp64_pipe_active_pct", "tensor_pipe_active_pct", "smem_wavefronts_per_cycle_per_sm", "duration_ms"):
+        e[k] /= e["launches"]
 print(json.dumps(out, indent=1))
