@@ -2,6 +2,8 @@
 // Own translation unit: the __noinline__ radix passes are shared by all kernels of a translation unit and compiled
 // for the tightest register budget among them; here that is 65536/448 = 144 registers (128 elsewhere).
 #include "plane_static.cuh"
+#include "plane_tmem.cuh"
+#include <cmath>
 #include <algorithm>
 #include <cstdlib>
 
@@ -52,6 +54,46 @@ int plane_select_static(const qb200_plan* p, int hmax)
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-memory kernel
+// k_plane_t (plane_tmem.cuh) exists for the compiled MgO216 geometry; QB200_PLANE_T=0 keeps k_plane_s
+typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32, 113> ShapeMgO216t;
+#define QB200_T_NYW 8
+#define QB200_T_NXW 8
+#define QB200_T_K1SPLIT 7
+#define QB200_T_ARGS ShapeMgO216t, QB200_T_NYW, QB200_T_NXW, QB200_T_K1SPLIT
+
+bool plane_t_wanted(const qb200_plan* p)
+{
+  if (const char* e = getenv("QB200_PLANE_T")) if (e[0] == '0') return false;
+  typedef ShapeMgO216t T;
+  const DevPlan& d = p->d;
+  return p->fused && p->static_shape == 2 && d.np0 == T::NP0 && d.np1 == T::NP1 && d.ksplit == T::YSPLIT && d.kskip == T::YSKIP;
+}
+int plane_t_pitch() { return ShapeMgO216t::PITCH; }
+void plane_t_xrange(int* xsplit, int* xskip) { *xsplit = ShapeMgO216t::XSPLIT; *xskip = ShapeMgO216t::XSKIP; }
+
+int plane_t_setup(qb200_plan* p)
+{
+  typedef ShapeMgO216t T;
+  p->plane_t = false;
+  p->smem_plane_t = plane_t_smem<T>(p->d.nvec, p->d.ntzero);
+  if (p->smem_plane_t + 64 > (size_t)p->max_smem) return QB200_OK;      // does not fit: k_plane_s stays
+  // W_112^{b k1} for the thread-per-column passes (long double, as the packed tables)
+  double tw[2 * 7 * 16];
+  const long double twopi = 6.283185307179586476925286766559005768L;
+  for (int b = 0; b < 7; b++)
+    for (int k1 = 0; k1 < 16; k1++) {
+      const int e = (b * k1) % T::NP1;
+      tw[2 * (16 * b + k1)] = (double)cosl(twopi * e / T::NP1);
+      tw[2 * (16 * b + k1) + 1] = (double)sinl(twopi * e / T::NP1);
+    }
+  QB_CUDA(cudaMemcpyToSymbol(c_ytw, tw, sizeof(tw)));
+  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, QB200_T_ARGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, QB200_T_ARGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+  p->plane_t = true;
+  return QB200_OK;
+}
+
 template <class K> static int opt_in(K kernel, int bytes)
 {
   QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -90,6 +132,14 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
 {
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
+  if (p->plane_t && (op == OP_HPSI || op == OP_DENSITY)) {
+    constexpr int NT = (QB200_T_NYW + QB200_T_NXW) * 32;
+    if (op == OP_HPSI) k_plane_t<OP_HPSI, QB200_T_ARGS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    else k_plane_t<OP_DENSITY, QB200_T_ARGS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_plane_t launch", __FILE__, __LINE__);
+    return QB200_OK;
+  }
   if (p->static_shape == 1) {
     typedef ShapeMgO216 S;
     switch (op) {

@@ -50,6 +50,10 @@ struct DevPlan {
   const int *yq;                       // natural y index held by position q after the y DIF transform
   // warp-owned plane kernel (k_plane_w): columns sorted by owner warp: staged address | plane position << 16, column index
   const int *wown, *wown_iv, *wown_start;
+  // tensor-memory plane kernel (k_plane_t, plane_tmem.cuh): 16-bit positions in a buffer of kept rows only
+  const unsigned short *tpos;          // per column iv: (kept-row index)*pitch + digit-reversed x position
+  const unsigned short *tzero;         // positions inside the non-zero x range of a kept row that no column covers
+  int ntzero;
 };
 
 enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
@@ -65,6 +69,10 @@ int plane_select_static(const qb200_plan* p, int hmax);
 int plane_preferred_gthreads(int np0, int np1, int ksplit, int kskip);
 int plane_preferred_pitch(int np0, int np1, int ksplit, int kskip);
 int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, const double* fac, int nunits, int zero_imag);
+bool plane_t_wanted(const qb200_plan* p);      // the compiled shape has a tensor-memory kernel and it is not switched off
+int plane_t_pitch();
+void plane_t_xrange(int* xsplit, int* xskip);
+int plane_t_setup(qb200_plan* p);              // after d.tpos / d.tzero are uploaded: shared memory, constants, opt-in
 }
 
 struct qb200_plan {
@@ -98,6 +106,8 @@ struct qb200_plan {
   int nsm;
   int plane_threads;
   int static_shape;                    // plane.cu: 0 generic kernel, > 0 compiled shape index
+  bool plane_t;                        // H psi / density planes run k_plane_t (y direction in tensor memory)
+  size_t smem_plane_t;
   // pipelined host-pointer paths (hpsi.cu, qb200_compute_density): copy streams + events, and the identity of the host
   // coefficient block whose device copy sits in st_c (qb200_plan_set_coefficient_tag)
   cudaStream_t s_in, s_out;

@@ -200,7 +200,8 @@ static void plan_split(const qb200_plan* p, int remaining, int maxG, int* nb_out
       const long rounds = ((long)np2 * G + nsm - 1) / nsm;
       const long upg = (nb + G - 1) / G;
       // a CTA pays ~0.4 unit-times of prologue (tables, first exposed fill) before its first unit
-      const double eff = ((double)nb * np2 / nsm) / ((double)rounds * (upg + 0.4));
+      // (the tensor-memory kernel is a two-stage pipeline over the units: one more unit-time to fill and drain)
+      const double eff = ((double)nb * np2 / nsm) / ((double)rounds * (upg + (p->plane_t ? 1.2 : 0.4)));
       if (eff > best * (1.0 + 1e-9)) { best = eff; bnb = nb; bG = G; }
     }
   *nb_out = bnb; *G_out = bG;
@@ -597,6 +598,25 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       p->smem_plane += (size_t)d.ncolpos_c * 16;
     }
     if ((rc = plane_opt_in(p))) { qb200_plan_destroy(p); return rc; }
+    // tensor-memory kernel of the compiled shape: positions in a buffer that holds the kept rows only
+    p->plane_t = false;
+    if (plane_t_wanted(p) && d.nvec <= 65535) {
+      const int tp = plane_t_pitch();
+      int xs, xk;
+      plane_t_xrange(&xs, &xk);
+      std::vector<unsigned short> tpos(d.nvec), tzero;
+      std::vector<char> covered((size_t)d.nkeep * tp, 0);
+      for (int iv = 0; iv < d.nvec; iv++) {
+        const int hp = colhk[iv] % np0, kp = colhk[iv] / np0, jr = kp < d.ksplit ? kp : kp - d.kskip;
+        tpos[iv] = (unsigned short)(jr * tp + xpos[hp]);
+        covered[tpos[iv]] = 1;
+      }
+      for (int jr = 0; jr < d.nkeep; jr++)
+        for (int hp = 0; hp < np0; hp++)
+          if ((hp < xs || hp >= xs + xk) && !covered[(size_t)jr * tp + xpos[hp]]) tzero.push_back((unsigned short)(jr * tp + xpos[hp]));
+      d.ntzero = (int)tzero.size();
+      if ((rc = upload(p, tpos, &d.tpos)) || (rc = upload(p, tzero, &d.tzero)) || (rc = plane_t_setup(p))) { qb200_plan_destroy(p); return rc; }
+    }
   }
   // fused path: batches of up to ~1100 MgO216 states -- whole blocks go through in one batch, so the persistent CTAs of
   // the plane and z-column kernels pay their wave quantisation and prologue once (r1l sweep: 256 MiB 27.66 ms/step, 1 GiB 26.68,
@@ -662,6 +682,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 14: return p->split2 ? 1 : 0;
     case 15: return p->split_static;
     case 16: return p->z_static;
+    case 17: return p->plane_t ? 1 : 0;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;

@@ -99,7 +99,16 @@ def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
     b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
     assert ft.query(10) == 2, "MgO216 plan did not select the compiled shape (one warp per column block)"
+    assert ft.query(17) == 1, "MgO216 plan did not select the tensor-memory plane kernel (k_plane_t)"
     del ft
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+    # the shared-memory-only kernel of the same compiled shape (k_plane_s)
+    monkeypatch.setenv("QB200_PLANE_T", "0")
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(10) == 2 and ft.query(17) == 0
+    del ft
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+    monkeypatch.delenv("QB200_PLANE_T")
     monkeypatch.setenv("QB200_NO_STATIC", "1")
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
     assert ft.query(10) == 0
