@@ -59,7 +59,7 @@ int plane_select_static(const qb200_plan* p, int hmax)
 typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32, 113> ShapeMgO216t;
 #define QB200_T_NYW 8
 #define QB200_T_NXW 8
-#define QB200_T_K1SPLIT 7
+#define QB200_T_K1SPLIT 8
 #define QB200_T_ARGS ShapeMgO216t, QB200_T_NYW, QB200_T_NXW, QB200_T_K1SPLIT
 
 bool plane_t_wanted(const qb200_plan* p)

@@ -95,7 +95,9 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
   cplx* stg = A0 + 2 * ABUF;
   unsigned short* tpos = reinterpret_cast<unsigned short*>(stg + nvp);
   unsigned short* tzero = tpos + nvp;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (the shuffle tells the compiler that the warp index -- and every role, loop bound and TMEM address derived from it -- is
+  // warp-uniform: they live in uniform registers, no R2UR per tcgen05 instruction)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int z = blockIdx.x, G = gridDim.y;
   const size_t N = (size_t)np01 * P.np2;
 
@@ -161,9 +163,10 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       if (OP == OP_DENSITY) bar_arrive_n(BAR_DONE + (i & 1), NT);   // the kept rows are consumed: the buffer is free again
       // pass 2: for each k1 the 7-point transform over b -> psi(x, y = k1 + 16 k2, z); pointwise work; way back to slots (., k1)
       double vn[7];
+      const double* vp = vz + (size_t)klo * np0;
       if (OP == OP_HPSI) {
 #pragma unroll
-        for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vz + (size_t)(klo + 16 * k2) * np0);
+        for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
       }
 #pragma unroll 1
       for (int k1 = klo; k1 < khi; k1++) {
@@ -171,16 +174,21 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
         if (OP == OP_HPSI) {
 #pragma unroll
           for (int k2 = 0; k2 < 7; k2++) vv[k2] = vn[k2];
-          const int kn = min(k1 + 1, khi - 1);
+          if (k1 + 1 < khi) vp += np0;              // (the last iteration re-reads its own row: no branch around the loads)
 #pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vz + (size_t)(kn + 16 * k2) * np0);
+          for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
         }
         cplx t[7];
         Tmem<1, 7>::ld(t, t0 + 4 * k1, 64);
         Dft<7, +1>::run(t);
         if (OP == OP_HPSI) {
+          if (zero_imag) {
 #pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y = zero_imag ? 0.0 : t[k2].y * vv[k2]; }
+            for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y = 0.0; }
+          } else {
+#pragma unroll
+            for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y *= vv[k2]; }
+          }
           Dft<7, -1>::run(t);
 #pragma unroll
           for (int b = 1; b < 7; b++) { const double2 w = c_ytw[16 * b + k1]; t[b] = cmul_s<-1>(t[b], w.x, w.y); }
