@@ -129,7 +129,7 @@ def device_count() -> int:
     return load().qb200_device_count()
 
 
-PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce", "k_anl_gen")
+PROFILE_CATEGORIES = ("k_zcol_bwd", "xy_stage", "k_zcol_fwd", "k_fnl", "k_fnl_finish", "k_back", "k_rho_reduce", "k_anl_gen", "xy_density")
 
 
 def measure_fp64_peak(device: int = 0):

@@ -57,10 +57,9 @@ int plane_select_static(const qb200_plan* p, int hmax)
 // ------------------------------------------------------------------------------------------------ tensor-memory kernel
 // k_plane_t (plane_tmem.cuh) exists for the compiled MgO216 geometry; QB200_PLANE_T=0 keeps k_plane_s
 typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32, 113> ShapeMgO216t;
-#define QB200_T_NYW 8
-#define QB200_T_NXW 8
-#define QB200_T_K1SPLIT 8
-#define QB200_T_ARGS ShapeMgO216t, QB200_T_NYW, QB200_T_NXW, QB200_T_K1SPLIT
+// warps (Y, X) per operation: the density build has no way back, so its x direction needs half the warps
+#define QB200_T_HPSI ShapeMgO216t, 8, 8
+#define QB200_T_DENS ShapeMgO216t, 12, 4
 
 bool plane_t_wanted(const qb200_plan* p)
 {
@@ -88,8 +87,8 @@ int plane_t_setup(qb200_plan* p)
       tw[2 * (16 * b + k1) + 1] = (double)sinl(twopi * e / T::NP1);
     }
   QB_CUDA(cudaMemcpyToSymbol(c_ytw, tw, sizeof(tw)));
-  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, QB200_T_ARGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
-  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, QB200_T_ARGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, QB200_T_HPSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, QB200_T_DENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
   p->plane_t = true;
   return QB200_OK;
 }
@@ -133,9 +132,9 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
   if (p->plane_t && (op == OP_HPSI || op == OP_DENSITY)) {
-    constexpr int NT = (QB200_T_NYW + QB200_T_NXW) * 32;
-    if (op == OP_HPSI) k_plane_t<OP_HPSI, QB200_T_ARGS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
-    else k_plane_t<OP_DENSITY, QB200_T_ARGS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    constexpr int NT = 512;
+    if (op == OP_HPSI) k_plane_t<OP_HPSI, QB200_T_HPSI><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    else k_plane_t<OP_DENSITY, QB200_T_DENS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_plane_t launch", __FILE__, __LINE__);
     return QB200_OK;

@@ -13,7 +13,8 @@
 //     trip  y-transform(+1) -> v(r) multiply or |psi|^2 -> y-transform(-1)  need NO exchange between threads: inputs come
 //     from the kept rows (lanes read consecutive x: conflict-free), every intermediate moves registers <-> TMEM, twiddles
 //     are warp-uniform constants.  The two warps of a lane quarter split the butterflies of a pass (b = 0..3 | 4..6 for the
-//     radix-16 passes, k1 split for the radix-7 pass) and meet at a 64-thread named barrier between passes.
+//     radix-16 passes, k1 split for the radix-7 pass) and meet at a named barrier of their own between passes (H psi: two warps
+//     per quarter and 8 X warps; density, which has no way back: three per quarter and 4 X warps).
 //
 // The y direction was 2/3 of the shared-memory wavefronts of k_plane_s (three passes over the full 112 x 112 plane, plus
 // per-thread twiddle loads); here it costs two reads/writes of the kept rows.  The shared-memory pipe (X warps) and the FP64
@@ -73,13 +74,13 @@ template <class SH> QB200_HD constexpr size_t plane_t_smem(int nvec, int nzero)
 
 enum { BAR_X = 1, BAR_FULL = 2, BAR_DONE = 4, BAR_PAIR = 6 };
 
-template <int OP, class SH, int NYW, int NXW, int K1SPLIT>
+template <int OP, class SH, int NYW, int NXW>
 __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
                                                                  double* __restrict__ rho_part, const double* __restrict__ fac, int nunits,
                                                                  int zero_imag)
 {
   static_assert(OP == OP_HPSI || OP == OP_DENSITY, "k_plane_t: H psi and density only");
-  static_assert(SH::NP1 == 112 && NYW == 8, "thread-per-column y passes are written for 112 = 16 x 7 with two warps per TMEM lane quarter");
+  static_assert(SH::NP1 == 112 && NYW % 4 == 0 && NYW >= 4 && NYW <= 16, "thread-per-column y passes are written for 112 = 16 x 7, MW = NYW/4 warps per TMEM lane quarter");
   static_assert(SH::NP0 <= 4 * 28, "28 columns per lane quarter");
   constexpr FftDesc FX = make_fft_desc(SH::NP0);
   constexpr int np0 = SH::NP0, np1 = SH::NP1, pitch = SH::PITCH, np01 = np0 * np1, NK = SH::NKEEP;
@@ -125,8 +126,9 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
     const uint32_t t0 = tbase + ((uint32_t)(q * 32) << 16);
     const bool act = lane < 28 && 28 * q + lane < np0;
     const int xc = min(28 * q + lane, np0 - 1);
-    const int blo = m ? 4 : 0, bhi = m ? 7 : 4;
-    const int klo = m ? K1SPLIT : 0, khi = m ? 16 : K1SPLIT;
+    constexpr int MW = NYW / 4;                    // warps that share a lane quarter split the butterflies of every pass
+    const int blo = (7 * m) / MW, bhi = (7 * (m + 1)) / MW;
+    const int klo = (16 * m) / MW, khi = (16 * (m + 1)) / MW;
     constexpr unsigned MASK = zmask(16, 7, SH::YSPLIT, SH::YSKIP);
     const double* vz = v + (size_t)z * np01 + xc;
     double* rz = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + xc;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       }
       tmem_wait_st();
       tmem_fence_before();
-      bar_sync_n(BAR_PAIR + q, 64);
+      bar_sync_n(BAR_PAIR + q, 32 * MW);
       tmem_fence_after();
       if (OP == OP_DENSITY) bar_arrive_n(BAR_DONE + (i & 1), NT);   // the kept rows are consumed: the buffer is free again
       // pass 2: for each k1 the 7-point transform over b -> psi(x, y = k1 + 16 k2, z); pointwise work; way back to slots (., k1)
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       if (OP == OP_HPSI) {
         tmem_wait_st();
         tmem_fence_before();
-        bar_sync_n(BAR_PAIR + q, 64);
+        bar_sync_n(BAR_PAIR + q, 32 * MW);
         tmem_fence_after();
         // pass 3: for each b the 16-point transform over k1 -> the kept rows y = 7a + b
 #pragma unroll 1
