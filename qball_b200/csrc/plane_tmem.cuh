@@ -27,39 +27,12 @@
 #pragma once
 #include "plane_static.cuh"
 #include "tmem_ops.cuh"
+#include "async_ops.cuh"
 
 namespace qb200 {
 
 // c_ytw[16 b + k1] = W_112^{b k1} (cos, sin), filled by plane_t_setup (plane.cu)
 __constant__ double2 c_ytw[7 * 16];
-
-__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
-{
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-// TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
-}
 
 // dynamic shared memory of k_plane_t (bytes); the same rule on the host (plane.cu)
 template <class SH> QB200_HD constexpr size_t plane_t_smem(int nvec, int nzero)

@@ -73,6 +73,11 @@ bool plane_t_wanted(const qb200_plan* p);      // the compiled shape has a tenso
 int plane_t_pitch();
 void plane_t_xrange(int* xsplit, int* xskip);
 int plane_t_setup(qb200_plan* p);              // after d.tpos / d.tzero are uploaded: shared memory, constants, opt-in
+// zcol_tmem.cu: z-column kernels with one thread per column in tensor memory (complex bases on the compiled 112-plane shape)
+bool zcol_t_wanted(const qb200_plan* p, int lmax);
+int zcol_t_setup(qb200_plan* p, const std::vector<int>& rod_first);
+int launch_zbwd_t(qb200_plan* p, const double* c, size_t ldc, int nunits);
+int launch_zfwd_t(qb200_plan* p, double* out, size_t ldc, int nunits, int accumulate, const double* kpg2, const double* cin, double scale);
 }
 
 struct qb200_plan {
@@ -108,6 +113,9 @@ struct qb200_plan {
   int static_shape;                    // plane.cu: 0 generic kernel, > 0 compiled shape index
   bool plane_t;                        // H psi / density planes run k_plane_t (y direction in tensor memory)
   size_t smem_plane_t;
+  bool zcol_t;                         // MODE_SINGLE z columns run k_zcol_bwd_t / k_zcol_fwd_t (zcol_tmem.cu)
+  int zt_cmax, zt_nblk;                // coefficients of the longest 128-column block, number of blocks
+  size_t smem_zt_b, smem_zt_f;
   // pipelined host-pointer paths (hpsi.cu, qb200_compute_density): copy streams + events, and the identity of the host
   // coefficient block whose device copy sits in st_c (qb200_plan_set_coefficient_tag)
   cudaStream_t s_in, s_out;

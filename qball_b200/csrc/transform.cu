@@ -475,6 +475,8 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     int lmax = 0;
     for (int r = 0; r < nrods; r++) lmax = std::max(lmax, std::max(std::abs(lmin[r]), std::abs(lmin[r] + size[r] - 1)));
     if ((rc = configure_z2(p, first, prop.sharedMemPerMultiprocessor, lmax))) { qb200_plan_destroy(p); return rc; }
+    p->zcol_t = false;
+    if (p->z2 && zcol_t_wanted(p, lmax) && (rc = zcol_t_setup(p, first))) { qb200_plan_destroy(p); return rc; }
   }
   const size_t pitch2 = (size_t)(np2 | 1);
   int ncolmax = (int)std::min<size_t>(32, (80 * 1024) / (pitch2 * 16));
@@ -687,6 +689,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 15: return p->split_static;
     case 16: return p->z_static;
     case 17: return p->plane_t ? 1 : 0;
+    case 18: return p->zcol_t ? 1 : 0;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;
@@ -710,6 +713,13 @@ static int launch_zbwd(qb200_plan* p, int mode, const double* c, size_t ldc, int
 {
   dim3 g(nzblocks(p), nunits);
   prof_begin(0, p->stream);
+  if (p->zcol_t && mode == MODE_SINGLE) {
+    const int rc = launch_zbwd_t(p, c, ldc, nunits);
+    prof_end(p->stream);
+    if (rc) return rc;
+    p->launches++;
+    return QB200_OK;
+  }
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zb_rb, p->zslots_b[mode], nunits);
     const int zt = p->z_threads;
@@ -731,6 +741,13 @@ static int launch_zfwd(qb200_plan* p, int mode, double* out, size_t ldc, int nun
   dim3 g(nzblocks(p), nunits);
   const double scale = 1.0 / ((double)p->d.np0 * p->d.np1 * p->d.np2);
   prof_begin(2, p->stream);
+  if (p->zcol_t && mode == MODE_SINGLE) {
+    const int rc = launch_zfwd_t(p, out, ldc, nunits, accumulate, kpg2, cin, scale);
+    prof_end(p->stream);
+    if (rc) return rc;
+    p->launches++;
+    return QB200_OK;
+  }
   if (p->z2) {
     const dim3 g2 = z2_grid(p, p->d.zf_rb, p->zslots_f[mode], nunits);
     const int zt = p->z_threads;

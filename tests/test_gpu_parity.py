@@ -109,6 +109,16 @@ def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
     del ft
     _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
     monkeypatch.delenv("QB200_PLANE_T")
+    # the z-column kernels: tensor-memory form by default (k_zcol_bwd_t / k_zcol_fwd_t), the shared-memory tiles (v2) otherwise
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(18) == 1, "MgO216 plan did not select the tensor-memory z-column kernels"
+    del ft
+    monkeypatch.setenv("QB200_ZCOL_T", "0")
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    assert ft.query(18) == 0 and ft.query(16) == 1
+    del ft
+    _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+    monkeypatch.delenv("QB200_ZCOL_T")
     monkeypatch.setenv("QB200_NO_STATIC", "1")
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
     assert ft.query(10) == 0
