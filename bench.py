@@ -509,11 +509,13 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
         return sum(ncu_traffic[k]["dram_bytes_per_launch"] for k in keys) / len(keys)
 
     roofline_hbm = None
+    # the plane kernel that ran: k_plane_t (y direction in tensor memory; plan query 17) or k_plane_s
+    plane_keys = ("k_plane_t<0>", "k_plane_t<1>") if ft.query(17) == 1 else ("k_plane_s<0>", "k_plane_s<1>")
     if xy_n:
         ach = xy_bytes_step * steps / (xy_ms * 1e-3) / 1e9
         roofline_hbm = {"kernel": "k_plane (fused xy stage)" if ft.fused() else "k_xrows+k_ycols (split xy stage)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": traffic_of("k_plane_s<0>", "k_plane_s<1>") if ft.fused() else None, "peak_source": peak_src,
+                        "traffic": traffic_of(*plane_keys) if ft.fused() else None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": xy_bytes_step * steps / xy_n,
                         "launches": xy_n, "avg_launch_ms": xy_ms / xy_n}
         # the stage is bound ON CHIP before it is bound by HBM: the other two roofs, from the committed ncu
@@ -522,11 +524,11 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
             onchip = {k: {"fp64_pipe_active_frac": ncu_traffic[k].get("fp64_pipe_active_pct", 0.0) / 100.0,
                           "smem_pipe_wavefronts_per_cycle": ncu_traffic[k].get("smem_wavefronts_per_cycle_per_sm"),
                           "dram_bytes_per_launch": ncu_traffic[k]["dram_bytes_per_launch"]}
-                      for k in ("k_plane_s<0>", "k_plane_s<1>") if k in ncu_traffic and "fp64_pipe_active_pct" in ncu_traffic[k]}
+                      for k in plane_keys if k in ncu_traffic and "fp64_pipe_active_pct" in ncu_traffic[k]}
             if onchip:
                 roofline_hbm["on_chip_roofs"] = {"kernels": onchip, "source": "profiles/ncu_traffic.json (ncu --set full of this command)",
-                                                 "note": "FP64 issue floor of the stage: ~6.1 ms per step at the measured DFMA rate against 13.1 ms "
-                                                         "measured; shared-memory pipe 0.6-0.7 wavefronts per cycle per SM; the two overlap by ~10 % (DESIGN.md section 7)"}
+                                                 "note": "the stage is bound by FP64 issue: ~6 ms per step of butterflies at the measured DFMA rate "
+                                                         "(k_plane_t keeps the y direction in tensor memory, so the shared-memory pipe is no longer a roof; DESIGN.md section 4)"}
     # the whole local path (z columns + xy stage, both directions) against the HBM roofline with SURVEY.md section 8d's
     # per-unit algorithmic bytes: B_Hpsi = 48*ngw*cper + 64*nvec*np2 + 8*N, B_rho = 16*ngw + 32*nvec*np2 (+16*N per build)
     cper = 2 if b["is_real"] else 1
@@ -537,7 +539,7 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
         ach = local_bytes_step * steps / (local_ms * 1e-3) / 1e9
         roofline_local = {"kernel": "local path: k_zcol_bwd + xy stage + k_zcol_fwd (H psi local term + density)", "bound": "hbm",
                           "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                          "note": "xy stage is bound by the shared-memory and FP64 pipes (ncu: smem wavefronts 65%, FP64 45%, DRAM 7% of peak), not by HBM"}
+                          "note": "xy stage is bound by FP64 issue (ncu: FP64 pipe 64-66 % active, DRAM 11 % of peak), the z-column kernels by HBM (5.3-5.8 TB/s)"}
     if roofline_local is not None:
         roofline_local["fp64_roof_note"] = "the butterflies of the local path execute ~0.18 TFLOP per MgO216 step; at the measured DFMA rate that is the second roof of this stage (see roofline_fp64.fp64_tflops_measured)"
     nl_flops_step = 0.0     # flops EXECUTED on the FP64 tensor pipe
