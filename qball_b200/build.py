@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libqball_b200.so")
-SOURCES = ["transform.cu", "plane.cu", "zcol_tmem.cu", "nonlocal.cu", "hpsi.cu", "diag.cu", "comm.cu"]
+SOURCES = ["transform.cu", "plane.cu", "zcol_tmem.cu", "ycols_tmem.cu", "nonlocal.cu", "hpsi.cu", "diag.cu", "comm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

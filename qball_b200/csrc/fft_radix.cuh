@@ -47,6 +47,10 @@ template<> struct Roots<11> {
   static __device__ __forceinline__ double c(int k) { constexpr double t[11] = { 1.0, 0.84125353283118116886, 0.41541501300188642553, -0.14231483827328514044, -0.65486073394528506406, -0.95949297361449738989, -0.95949297361449738989, -0.65486073394528506406, -0.14231483827328514044, 0.41541501300188642553, 0.84125353283118116886 }; return t[k]; }
   static __device__ __forceinline__ double s(int k) { constexpr double t[11] = { 0.0, 0.54064081745559758211, 0.90963199535451837141, 0.98982144188093273238, 0.75574957435425828377, 0.28173255684142969771, -0.28173255684142969771, -0.75574957435425828377, -0.98982144188093273238, -0.90963199535451837141, -0.54064081745559758211 }; return t[k]; }
 };
+template<> struct Roots<14> {
+  static __device__ __forceinline__ double c(int k) { constexpr double t[14] = { 1.0, 0.90096886790241912624, 0.62348980185873353053, 0.22252093395631440429, -0.22252093395631440429, -0.62348980185873353053, -0.90096886790241912624, -1.0, -0.90096886790241912624, -0.62348980185873353053, -0.22252093395631440429, 0.22252093395631440429, 0.62348980185873353053, 0.90096886790241912624 }; return t[k]; }
+  static __device__ __forceinline__ double s(int k) { constexpr double t[14] = { 0.0, 0.43388373911755812048, 0.78183148246802980871, 0.97492791218182360702, 0.97492791218182360702, 0.78183148246802980871, 0.43388373911755812048, 0.0, -0.43388373911755812048, -0.78183148246802980871, -0.97492791218182360702, -0.97492791218182360702, -0.78183148246802980871, -0.43388373911755812048 }; return t[k]; }
+};
 template<> struct Roots<16> {
   static __device__ __forceinline__ double c(int k) { constexpr double t[16] = { 1.0, 0.92387953251128675613, 0.7071067811865475244, 0.38268343236508977173, 0.0, -0.38268343236508977173, -0.7071067811865475244, -0.92387953251128675613, -1.0, -0.92387953251128675613, -0.7071067811865475244, -0.38268343236508977173, 0.0, 0.38268343236508977173, 0.7071067811865475244, 0.92387953251128675613 }; return t[k]; }
   static __device__ __forceinline__ double s(int k) { constexpr double t[16] = { 0.0, 0.38268343236508977173, 0.7071067811865475244, 0.92387953251128675613, 1.0, 0.92387953251128675613, 0.7071067811865475244, 0.38268343236508977173, 0.0, -0.38268343236508977173, -0.7071067811865475244, -0.92387953251128675613, -1.0, -0.92387953251128675613, -0.7071067811865475244, -0.38268343236508977173 }; return t[k]; }
@@ -147,5 +151,6 @@ template <int A, int B, int S> struct DftComposite {
 template <int S> struct Dft<8, S> : DftComposite<2, 4, S> {};
 template <int S> struct Dft<9, S> : DftComposite<3, 3, S> {};
 template <int S> struct Dft<16, S> : DftComposite<4, 4, S> {};
+template <int S> struct Dft<14, S> : DftComposite<2, 7, S> {};   // thread-private passes of the tensor-memory kernels (126 = 9 x 14)
 
 }  // namespace qb200

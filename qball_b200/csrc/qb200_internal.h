@@ -78,6 +78,9 @@ bool zcol_t_wanted(const qb200_plan* p, int lmax);
 int zcol_t_setup(qb200_plan* p, const std::vector<int>& rod_first);
 int launch_zbwd_t(qb200_plan* p, const double* c, size_t ldc, int nunits);
 int launch_zfwd_t(qb200_plan* p, double* out, size_t ldc, int nunits, int accumulate, const double* kpg2, const double* cin, double scale);
+// ycols_tmem.cu: y stage of the split xy path with the column in tensor memory (compiled 126 / 252 plane heights)
+int ycols_t_setup(qb200_plan* p);
+int launch_ycols_t(qb200_plan* p, int op, const double* v, const double* fac, int nunits, int zero_imag);
 }
 
 struct qb200_plan {
@@ -116,6 +119,7 @@ struct qb200_plan {
   bool zcol_t;                         // MODE_SINGLE z columns run k_zcol_bwd_t / k_zcol_fwd_t (zcol_tmem.cu)
   int zt_cmax, zt_nblk;                // coefficients of the longest 128-column block, number of blocks
   size_t smem_zt_b, smem_zt_f;
+  int ycols_t;                         // split path: 0 k_ycols2, 1 k_ycols_t on 126-row planes (si54p), 2 on 252-row planes (Au992)
   // pipelined host-pointer paths (hpsi.cu, qb200_compute_density): copy streams + events, and the identity of the host
   // coefficient block whose device copy sits in st_c (qb200_plan_set_coefficient_tag)
   cudaStream_t s_in, s_out;

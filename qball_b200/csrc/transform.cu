@@ -551,6 +551,8 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
       qb200_plan_destroy(p); return rc;
     }
   }
+  p->ycols_t = 0;
+  if ((rc = ycols_t_setup(p))) { qb200_plan_destroy(p); return rc; }
   // plane kernel geometry: groups of gthreads threads own blocks of 8 rows / 8 columns (fft_group.cuh); pick the number of
   // groups (<= 7 x 64 = 448 threads so that the radix-16 pass keeps its ~112 registers) that needs the fewest rounds
   {
@@ -690,6 +692,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 16: return p->z_static;
     case 17: return p->plane_t ? 1 : 0;
     case 18: return p->zcol_t ? 1 : 0;
+    case 19: return p->ycols_t;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;
@@ -778,8 +781,14 @@ static int launch_split(qb200_plan* p, dim3 gr, dim3 gy, const double* v, double
     k_xrows2<+1, SH><<<gr, 256, p->smem_xr[0], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
     QB_LAUNCH_CHECK(p);
   }
-  k_ycols2<OP, SH><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
-  QB_LAUNCH_CHECK(p);
+  if (p->ycols_t && (OP == OP_HPSI || OP == OP_DENSITY)) {
+    const int rc = launch_ycols_t(p, OP, v, fac, nunits, zero_imag);
+    if (rc) return rc;
+    p->launches++;
+  } else {
+    k_ycols2<OP, SH><<<gy, 256, p->smem_yc[OP], p->stream>>>(d, (cplx*)p->w, v, (cplx*)f, p->rho_part, fac, nunits, zero_imag);
+    QB_LAUNCH_CHECK(p);
+  }
   if (OP == OP_HPSI || OP == OP_FWD) {
     k_xrows2<-1, SH><<<gr, 256, p->smem_xr[1], p->stream>>>(d, (cplx*)p->zt, (cplx*)p->w, p->xr_rowb, p->xr_smax, nunits);
     QB_LAUNCH_CHECK(p);

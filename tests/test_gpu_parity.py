@@ -302,6 +302,7 @@ def test_properties_au992_full_size_split_path(monkeypatch):
         ft = H.FourierTransform(b, *grid)
         ft.set_workspace(2 << 30)
         assert not ft.fused() and ft.query(14) == 1 and ft.query(15) == (1 if mode == "static" else 0)
+        assert ft.query(19) == (2 if mode == "static" else 0)      # static: y stage with two TMEM lanes per 252-point column
         h = torch.zeros_like(cd)
         H.rs_mul_add(ft, cd, vd, h, kpg2=_dev(b["kpg2"]))
         rho = torch.zeros(N, dtype=torch.float64, device="cuda")
@@ -325,7 +326,7 @@ def test_properties_au992_full_size_split_path(monkeypatch):
     assert relerr(res["static"][1], res["generic"][1]) < 1e-12
 
 
-@pytest.mark.parametrize("compiled", [True, False])
+@pytest.mark.parametrize("compiled", [True, "smem", False])
 def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     """examples/si54p as a Gamma-point real-wavefunction case (fcc-type cell 2 x 15.525, 65 Ry, 126^3 grid,
     ngw 33114): planes of 126 x 127 x 16 B exceed shared memory, so this runs the real-basis pair path (+ odd tail)
@@ -333,6 +334,8 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     checked against the oracle on the same seeded inputs."""
     if not compiled:
         monkeypatch.setenv("QB200_NO_STATIC", "1")
+    if compiled == "smem":      # the compiled shape with the shared-memory y stage (k_ycols2) instead of the tensor-memory one
+        monkeypatch.setenv("QB200_YCOLS_T", "0")
     a = 15.525
     cell, ecut = (0, a, a, a, 0, a, a, a, 0), 32.5
     b = P.make_basis(cell, ecut, (0, 0, 0), False)
@@ -345,6 +348,7 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     oft = P.FT(b, *grid)
     ft = H.FourierTransform(b, *grid)
     assert not ft.fused() and ft.query(14) == 1 and ft.query(11) == 1 and ft.query(15) == (2 if compiled else 0)
+    assert ft.query(19) == (1 if compiled is True else 0), "y stage: k_ycols_t (column in tensor memory) only for the compiled shape"
     want = oft.rs_mul_add(c, v, np.zeros_like(c))
     P.kinetic_add(b["kpg2"], c, want)
     got = _dev(np.zeros_like(c))
