@@ -16,9 +16,10 @@
 //     the odd ones that of v; only rows y < 56 or y >= 196 are non-zero, so u[y'] and v[y'] are ONE input each (no add):
 //     both lanes read the same kept rows, the "odd" lane multiplies by +-W_252^{y'}.  On the way back
 //     Y[y'] = u'[y'] + W^{-y'} v'[y'] (rows y < 126), Y[y'+126] = u'[y'] - W^{-y'} v'[y'] is one lane exchange (shuffle).
-// Work items (unit, plane z, block of columns) are dealt to one persistent CTA per SM; for the density every (z, block) has
-// ONE owner CTA that walks the units in order, so the L2 reductions (red.global.add.f64) to an address are applied in a
-// fixed order: deterministic, as in the other density kernels.
+// Every (plane z, block of columns) has ONE owner CTA (persistent, one per SM) that walks the units in order.  The density is
+// accumulated in shared memory over all units of a launch (acc[y][column], 127 KB: each point has one owner thread) and added to
+// rho once per launch -- one read-modify-write per point and batch instead of one L2 reduction per point and state; fixed
+// order, deterministic, as in the other density kernels.
 #include "qb200_internal.h"
 #include "plane_static.cuh"
 #include "tmem_ops.cuh"
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
   constexpr unsigned MASK = zmask(9, 14, YS::KSPLIT, YS::KSKIP);
   constexpr int MW = 4;                                             // warps per TMEM lane quarter
   __shared__ uint32_t tmem_slot;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* acc = reinterpret_cast<double*>(smraw);                  // DENSITY: [np1][COLS]
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (warp == 0) tmem_alloc512(&tmem_slot);
   tmem_fence_before();
@@ -75,7 +78,11 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
     const bool act = cl < YS::COLS && x < np0;
     const int xc = min(x, np0 - 1);
     const double* vz = v + (size_t)z * np01 + xc;
-    double* rz = rho_part + (size_t)z * np01 + xc;
+    if (OP == OP_DENSITY) {
+      __syncthreads();                                             // the previous slot's write-out is done with acc
+      for (int i = tid; i < np1 * YS::COLS; i += 512) acc[i] = 0.0;
+      __syncthreads();
+    }
     for (int unit = 0; unit < nunits; unit++) {
       double facu = 0.0;
       if (OP == OP_DENSITY) { facu = fac[unit]; if (!(facu > 0.0)) continue; }
@@ -140,8 +147,7 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
 #pragma unroll
           for (int k2 = 0; k2 < 14; k2++) {
             const int k = k1 + 9 * k2, y = PAIR ? 2 * k + role : k;
-            const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)y * np0), "d"(val) : "memory");
+            acc[y * YS::COLS + cl] += facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);    // this thread owns (y, cl) in every unit
           }
         }
       }
@@ -183,6 +189,15 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
         }
       }
     }
+    if (OP == OP_DENSITY) {
+      __syncthreads();
+      double* rz = rho_part + (size_t)z * np01 + (size_t)xb * YS::COLS;
+      const int ncol = min(YS::COLS, np0 - xb * YS::COLS);
+      for (int i = tid; i < np1 * YS::COLS; i += 512) {
+        const int y = i / YS::COLS, c = i - y * YS::COLS;
+        if (c < ncol) rz[(size_t)y * np0 + c] += acc[i];
+      }
+    }
   }
   tmem_fence_before();
   __syncthreads();
@@ -217,6 +232,8 @@ int ycols_t_setup(qb200_plan* p)
   for (int y = 0; y < 126; y++) { t252[2 * y] = (double)cosl(twopi * y / 252); t252[2 * y + 1] = (double)sinl(twopi * y / 252); }
   QB_CUDA(cudaMemcpyToSymbol(c_w126, t126, sizeof(t126)));
   QB_CUDA(cudaMemcpyToSymbol(c_w252, t252, sizeof(t252)));
+  QB_CUDA(cudaFuncSetAttribute(k_ycols_t<OP_DENSITY, YtSi54p>, cudaFuncAttributeMaxDynamicSharedMemorySize, YtSi54p::NP1 * YtSi54p::COLS * 8));
+  QB_CUDA(cudaFuncSetAttribute(k_ycols_t<OP_DENSITY, YtAu992>, cudaFuncAttributeMaxDynamicSharedMemorySize, YtAu992::NP1 * YtAu992::COLS * 8));
   p->ycols_t = shape;
   return QB200_OK;
 }
@@ -229,10 +246,10 @@ int launch_ycols_t(qb200_plan* p, int op, const double* v, const double* fac, in
   const int grid = std::min(p->nsm, nslots);
   if (p->ycols_t == 1) {
     if (op == OP_HPSI) k_ycols_t<OP_HPSI, YtSi54p><<<grid, 512, 0, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
-    else k_ycols_t<OP_DENSITY, YtSi54p><<<grid, 512, 0, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
+    else k_ycols_t<OP_DENSITY, YtSi54p><<<grid, 512, (size_t)YtSi54p::NP1 * YtSi54p::COLS * 8, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
   } else {
     if (op == OP_HPSI) k_ycols_t<OP_HPSI, YtAu992><<<grid, 512, 0, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
-    else k_ycols_t<OP_DENSITY, YtAu992><<<grid, 512, 0, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
+    else k_ycols_t<OP_DENSITY, YtAu992><<<grid, 512, (size_t)YtAu992::NP1 * YtAu992::COLS * 8, p->stream>>>(d, w, v, p->rho_part, fac, nunits, zero_imag);
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_ycols_t launch", __FILE__, __LINE__);
