@@ -57,9 +57,13 @@ int plane_select_static(const qb200_plan* p, int hmax)
 // ------------------------------------------------------------------------------------------------ tensor-memory kernel
 // k_plane_t (plane_tmem.cuh) exists for the compiled MgO216 geometry; QB200_PLANE_T=0 keeps k_plane_s
 typedef PlaneShape<112, 112, 26, 60, 26, 60, 14, 32, 113> ShapeMgO216t;
-// warps (Y, X) per operation: the density build has no way back, so its x direction needs half the warps
-#define QB200_T_HPSI ShapeMgO216t, 8, 8
-#define QB200_T_DENS ShapeMgO216t, 12, 4
+// warps (Y, X) per operation; QB200_T_HPSI / QB200_T_DENS = index into the lists below selects the alternative geometry.
+// Measured (MgO216, profiles/r2t6_plane_t_warp_configs.txt): H psi 6.11 ms with (8, 8), 6.21 with (12, 8) at 96 registers;
+// density 3.30 ms with (12, 4), 3.31 (8, 8), 3.34 (12, 8), 3.44 (12, 6): the kernel is bound by instruction issue (FP64 pipe
+// 68 % + 21 % other instructions), not by the Y warps' critical path, so more warps do not help
+#define QB200_T_HPSI_LIST(F) F(0, 8, 8) F(1, 12, 8)
+#define QB200_T_DENS_LIST(F) F(0, 12, 4) F(1, 8, 8)
+static int t_cfg(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
 
 bool plane_t_wanted(const qb200_plan* p)
 {
@@ -87,8 +91,10 @@ int plane_t_setup(qb200_plan* p)
       tw[2 * (16 * b + k1) + 1] = (double)sinl(twopi * e / T::NP1);
     }
   QB_CUDA(cudaMemcpyToSymbol(c_ytw, tw, sizeof(tw)));
-  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, QB200_T_HPSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
-  QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, QB200_T_DENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+#define QB200_T_OPTIN_H(i, ny, nx) QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, ShapeMgO216t, ny, nx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+#define QB200_T_OPTIN_D(i, ny, nx) QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
+  QB200_T_HPSI_LIST(QB200_T_OPTIN_H)
+  QB200_T_DENS_LIST(QB200_T_OPTIN_D)
   p->plane_t = true;
   return QB200_OK;
 }
@@ -132,9 +138,11 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
   if (p->plane_t && (op == OP_HPSI || op == OP_DENSITY)) {
-    constexpr int NT = 512;
-    if (op == OP_HPSI) k_plane_t<OP_HPSI, QB200_T_HPSI><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
-    else k_plane_t<OP_DENSITY, QB200_T_DENS><<<grid, NT, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    const int cfg = t_cfg(op == OP_HPSI ? "QB200_T_HPSI" : "QB200_T_DENS");
+#define QB200_T_LAUNCH_H(i, ny, nx) if (op == OP_HPSI && cfg == i) k_plane_t<OP_HPSI, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+#define QB200_T_LAUNCH_D(i, ny, nx) if (op == OP_DENSITY && cfg == i) k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
+    QB200_T_HPSI_LIST(QB200_T_LAUNCH_H)
+    QB200_T_DENS_LIST(QB200_T_LAUNCH_D)
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_plane_t launch", __FILE__, __LINE__);
     return QB200_OK;
