@@ -137,7 +137,7 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
 {
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
-  if (p->plane_t && (op == OP_HPSI || op == OP_DENSITY)) {
+  if (p->plane_t && (op == OP_DENSITY || (op == OP_HPSI && !zero_imag))) {
     const int cfg = t_cfg(op == OP_HPSI ? "QB200_T_HPSI" : "QB200_T_DENS");
 #define QB200_T_LAUNCH_H(i, ny, nx) if (op == OP_HPSI && cfg == i) k_plane_t<OP_HPSI, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
 #define QB200_T_LAUNCH_D(i, ny, nx) if (op == OP_DENSITY && cfg == i) k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);

@@ -137,37 +137,21 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       tmem_fence_after();
       if (OP == OP_DENSITY) bar_arrive_n(BAR_DONE + (i & 1), NT);   // the kept rows are consumed: the buffer is free again
       // pass 2: for each k1 the 7-point transform over b -> psi(x, y = k1 + 16 k2, z); pointwise work; way back to slots (., k1)
-      double vn[7];
+      // (H psi: v(r) of the NEXT k1 is loaded while the current one is transformed; the loop is unrolled by two with the two
+      //  register sets swapping roles, so the prefetch costs no register moves)
       const double* vp = vz + (size_t)klo * np0;
-      if (OP == OP_HPSI) {
-#pragma unroll
-        for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
-      }
-#pragma unroll 1
-      for (int k1 = klo; k1 < khi; k1++) {
-        double vv[7];
-        if (OP == OP_HPSI) {
-#pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) vv[k2] = vn[k2];
-          if (k1 + 1 < khi) vp += np0;              // (the last iteration re-reads its own row: no branch around the loads)
-#pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) vn[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
-        }
+      auto pass2 = [&](int k1, const double (&vv)[7]) {
         cplx t[7];
         Tmem<1, 7>::ld(t, t0 + 4 * k1, 64);
         Dft<7, +1>::run(t);
         if (OP == OP_HPSI) {
-          if (zero_imag) {
+          // (the odd tail of a real basis, whose imaginary part is dropped here -- SlaterDet.cc:1014-1023 -- runs k_plane_s)
 #pragma unroll
-            for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y = 0.0; }
-          } else {
-#pragma unroll
-            for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y *= vv[k2]; }
-          }
+          for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y *= vv[k2]; }
           Dft<7, -1>::run(t);
 #pragma unroll
           for (int b = 1; b < 7; b++) { const double2 w = c_ytw[16 * b + k1]; t[b] = cmul_s<-1>(t[b], w.x, w.y); }
-          Tmem<1, 7>::st(t0 + 4 * k1, t, 64);
+          Tmem<1, 7>::st2(t0 + 4 * k1, t, 64);
         } else {
           // fire-and-forget reductions at the L2, one owner per address (CTA (z, gy) owns plane z of partial gy), applied in
           // unit order: deterministic (as k_plane_s)
@@ -178,6 +162,25 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
               asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)(k1 + 16 * k2) * np0), "d"(val) : "memory");
             }
           }
+        }
+      };
+      auto loadv = [&](double (&vv)[7]) {
+        if (OP == OP_HPSI) {
+#pragma unroll
+          for (int k2 = 0; k2 < 7; k2++) vv[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
+        }
+      };
+      double va[7], vb[7];
+      loadv(va);
+#pragma unroll 1
+      for (int k1 = klo; k1 < khi; k1 += 2) {
+        if (k1 + 1 < khi) vp += np0;                // (the last iteration re-reads its own row: no branch around the loads)
+        loadv(vb);
+        pass2(k1, va);
+        if (k1 + 1 < khi) {
+          if (k1 + 2 < khi) vp += np0;
+          loadv(va);
+          pass2(k1 + 1, vb);
         }
       }
       if (OP == OP_HPSI) {
