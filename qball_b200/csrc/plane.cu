@@ -95,6 +95,18 @@ int plane_t_setup(qb200_plan* p)
 #define QB200_T_OPTIN_D(i, ny, nx) QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
   QB200_T_HPSI_LIST(QB200_T_OPTIN_H)
   QB200_T_DENS_LIST(QB200_T_OPTIN_D)
+  // density with the CTA's rho plane in shared memory (k_plane_td): opt-in (QB200_T_DENS_SMEM=1).  Measured 3.53 ms against 3.29 ms
+  // for the L2 reductions of k_plane_t<DENSITY> (MgO216): the reductions were not the limit, and single-buffering the kept rows
+  // to make room for the plane costs more than they did
+  p->plane_td = false;
+  p->smem_plane_td = plane_td_smem<T>(p->d.nvec);
+  {
+    const char* e = getenv("QB200_T_DENS_SMEM");
+    if (e && e[0] == '1' && p->smem_plane_td + 64 <= (size_t)p->max_smem) {
+      QB_CUDA((cudaFuncSetAttribute(k_plane_td<ShapeMgO216t, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_td)));
+      p->plane_td = true;
+    }
+  }
   p->plane_t = true;
   return QB200_OK;
 }
@@ -138,6 +150,12 @@ int launch_plane(qb200_plan* p, int op, dim3 grid, const double* v, double* f, c
   const DevPlan& d = p->d;
   cplx* zt = (cplx*)p->zt;
   if (p->plane_t && (op == OP_DENSITY || (op == OP_HPSI && !zero_imag))) {
+    if (op == OP_DENSITY && p->plane_td) {
+      k_plane_td<ShapeMgO216t, 8, 8><<<grid, 512, p->smem_plane_td, p->stream>>>(d, zt, p->rho_part, fac, nunits);
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_plane_td launch", __FILE__, __LINE__);
+      return QB200_OK;
+    }
     const int cfg = t_cfg(op == OP_HPSI ? "QB200_T_HPSI" : "QB200_T_DENS");
 #define QB200_T_LAUNCH_H(i, ny, nx) if (op == OP_HPSI && cfg == i) k_plane_t<OP_HPSI, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);
 #define QB200_T_LAUNCH_D(i, ny, nx) if (op == OP_DENSITY && cfg == i) k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx><<<grid, (ny + nx) * 32, p->smem_plane_t, p->stream>>>(d, zt, v, p->rho_part, fac, nunits, zero_imag);

@@ -259,4 +259,144 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
   if (warp == 0) tmem_dealloc512(tbase);
 }
 
+// ------------------------------------------------------------------------------------------------ density, rho in shared memory
+// k_plane_td<SH, NYW, NXW>: the density build of k_plane_t with the CTA's plane of rho_part ACCUMULATED IN SHARED MEMORY over
+// all its units (one read-modify-write of global memory per point and CTA instead of one L2 reduction per point and state:
+// 1.08 G red.global.add.f64 per MgO216 launch).  The 100 KB plane takes the place of the second buffer of kept rows: the kept
+// rows are single-buffered, which costs little here -- the y direction needs them only in its first pass (they are free again
+// while the radix-7 pass and the |psi|^2 accumulation run, and that is when the X warps scatter and transform the next unit).
+template <class SH> QB200_HD constexpr size_t plane_td_smem(int nvec)
+{
+  constexpr FftDesc FX = make_fft_desc(SH::NP0);
+  return (size_t)((FX.twsize + 7) & ~7) * 16 + (size_t)SH::NKEEP * SH::PITCH * 16 + (size_t)((nvec + 7) & ~7) * 16 + (size_t)SH::NP0 * SH::NP1 * 8;
+}
+
+template <class SH, int NYW, int NXW>
+__global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_td(const __grid_constant__ DevPlan P, const cplx* __restrict__ zt, double* __restrict__ rho_part,
+                                                                  const double* __restrict__ fac, int nunits)
+{
+  static_assert(SH::NP1 == 112 && NYW % 4 == 0 && NYW >= 4 && NYW <= 16, "thread-per-column y passes are written for 112 = 16 x 7");
+  constexpr FftDesc FX = make_fft_desc(SH::NP0);
+  constexpr int np0 = SH::NP0, np1 = SH::NP1, pitch = SH::PITCH, np01 = np0 * np1, NK = SH::NKEEP;
+  constexpr int NYT = NYW * 32, NXT = NXW * 32, NT = NYT + NXT;
+  constexpr int ABUF = NK * pitch;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar;
+  const int nvec = P.nvec, nvp = (nvec + 7) & ~7, nzero = P.ntzero;
+  cplx* tw0 = reinterpret_cast<cplx*>(smraw);
+  cplx* A = tw0 + ((FX.twsize + 7) & ~7);
+  cplx* stg = A + ABUF;
+  double* acc = reinterpret_cast<double*>(stg + nvp);
+  const unsigned short* __restrict__ tpos = P.tpos;
+  const unsigned short* __restrict__ tzero = P.tzero;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int z = blockIdx.x, G = gridDim.y;
+  const size_t N = (size_t)np01 * P.np2;
+  if (warp == 0) tmem_alloc512(&tmem_slot);
+  if (tid == 32) mbar_init(&mbar, 1);
+  for (int i = tid; i < FX.twsize; i += NT) tw0[i] = P.tw0p[i];
+  for (int i = tid; i < ABUF; i += NT) A[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < np01; i += NT) acc[i] = 0.0;
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  const uint32_t tbase = tmem_slot;
+  auto next_unit = [&](int u) {
+    u += G;
+    while (u < nunits && !(fac[u] > 0.0)) u += G;
+    return u;
+  };
+  const int first = next_unit((int)blockIdx.y - G);
+  if (warp < NYW) {
+    const int q = warp & 3, m = warp >> 2;
+    const uint32_t t0 = tbase + ((uint32_t)(q * 32) << 16);
+    const bool act = lane < 28 && 28 * q + lane < np0;
+    const int xc = min(28 * q + lane, np0 - 1);
+    constexpr int MW = NYW / 4;
+    const int blo = (7 * m) / MW, bhi = (7 * (m + 1)) / MW;
+    const int klo = (16 * m) / MW, khi = (16 * (m + 1)) / MW;
+    constexpr unsigned MASK = zmask(16, 7, SH::YSPLIT, SH::YSKIP);
+    const cplx* Ax = A + xc;
+    double* ax = acc + xc;
+    for (int unit = first; unit < nunits; unit = next_unit(unit)) {
+      const double facu = fac[unit];
+      bar_sync_n(BAR_FULL, NT);
+#pragma unroll 1
+      for (int b = blo; b < bhi; b++) {
+        cplx x[16];
+#pragma unroll
+        for (int a = 0; a < 16; a++) {
+          const int c = zclass(a, 7, SH::YSPLIT, SH::YSKIP);
+          if (c == 0) continue;
+          const int y = 7 * a + b;
+          const int row = (7 * a + 6 < SH::YSPLIT) ? y : ((7 * a >= SH::YSPLIT + SH::YSKIP) ? y - SH::YSKIP : (y < SH::YSPLIT ? y : y - SH::YSKIP));
+          if (c == 1) x[a] = Ax[row * pitch];
+          else x[a] = (y < SH::YSPLIT || y >= SH::YSPLIT + SH::YSKIP) ? Ax[row * pitch] : make_double2(0.0, 0.0);
+        }
+        DftM<16, +1, MASK>::run(x);
+        if (b != 0) {
+#pragma unroll
+          for (int k1 = 1; k1 < 16; k1++) { const double2 w = c_ytw[16 * b + k1]; x[k1] = cmul_s<+1>(x[k1], w.x, w.y); }
+        }
+        Tmem<16>::st(t0 + 64 * b, x);
+      }
+      tmem_wait_st();
+      tmem_fence_before();
+      bar_sync_n(BAR_PAIR + q, 32 * MW);
+      tmem_fence_after();
+      bar_arrive_n(BAR_DONE, NT);                  // the kept rows are consumed: the X warps may bring the next unit
+#pragma unroll 1
+      for (int k1 = klo; k1 < khi; k1++) {
+        cplx t[7];
+        Tmem<1, 7>::ld(t, t0 + 4 * k1, 64);
+        Dft<7, +1>::run(t);
+        if (act) {                                 // this thread owns (y = k1 + 16 k2, x) in every unit of the CTA
+#pragma unroll
+          for (int k2 = 0; k2 < 7; k2++) ax[(k1 + 16 * k2) * np0] += facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
+        }
+      }
+      // (the other warps of the quarter finish their share of pass 2 before pass 1 of the next unit overwrites the slots)
+      tmem_fence_before();
+      bar_sync_n(BAR_PAIR + q, 32 * MW);
+      tmem_fence_after();
+    }
+  } else {
+    const int xt = tid - NYT;
+    auto xsync = []() { bar_sync_n(BAR_X, NXT); };
+    const uint32_t row_bytes = (uint32_t)nvec * 16u;
+    uint32_t sphase = 0;
+    if (xt == 0 && first < nunits) {
+      mbar_expect_tx(&mbar, row_bytes);
+      bulk_g2s(stg, zt + ((size_t)first * P.np2 + z) * nvec, row_bytes, &mbar);
+    }
+    int i = 0;
+    for (int unit = first; unit < nunits; i++) {
+      const int nxt = next_unit(unit);
+      mbar_wait(&mbar, sphase);
+      sphase ^= 1u;
+      if (i > 0) {
+        bar_sync_n(BAR_DONE, NT);                  // the Y warps have read the kept rows of the unit before
+        for (int j = xt; j < nzero; j += NXT) A[tzero[j]] = make_double2(0.0, 0.0);
+      }
+      for (int j = xt; j < nvec; j += NXT) A[tpos[j]] = stg[j];
+      xsync();
+      if (xt == 0 && nxt < nunits) {
+        mbar_expect_tx(&mbar, row_bytes);
+        bulk_g2s(stg, zt + ((size_t)nxt * P.np2 + z) * nvec, row_bytes, &mbar);
+      }
+      dit_s<+1, np0, 1, NK, DenseRowsW<pitch>, SH::XSPLIT, SH::XSKIP, true, false, FX.nf - 1>(xt, NXT, A, tw0, xsync);
+      __threadfence_block();
+      bar_arrive_n(BAR_FULL, NT);
+      unit = nxt;
+    }
+    if (i > 0) bar_sync_n(BAR_DONE, NT);
+  }
+  tmem_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc512(tbase);
+  double* rz = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01;
+  for (int i = tid; i < np01; i += NT) rz[i] += acc[i];
+}
+
 }  // namespace qb200

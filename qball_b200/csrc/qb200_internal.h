@@ -116,6 +116,8 @@ struct qb200_plan {
   int static_shape;                    // plane.cu: 0 generic kernel, > 0 compiled shape index
   bool plane_t;                        // H psi / density planes run k_plane_t (y direction in tensor memory)
   size_t smem_plane_t;
+  bool plane_td;                       // density planes run k_plane_td (rho plane accumulated in shared memory)
+  size_t smem_plane_td;
   bool zcol_t;                         // MODE_SINGLE z columns run k_zcol_bwd_t / k_zcol_fwd_t (zcol_tmem.cu)
   int zt_cmax, zt_nblk;                // coefficients of the longest 128-column block, number of blocks
   size_t smem_zt_b, smem_zt_f;

@@ -198,6 +198,7 @@ static void plan_split(const qb200_plan* p, int remaining, int maxG, int* nb_out
   const int nbmax = std::min(p->batch, remaining);
   if (!p->fused) { *nb_out = nbmax; *G_out = 1; return; }
   double best = -1.0; int bnb = nbmax, bG = 1;
+  if (const char* e = getenv("QB200_PLANE_G")) { const int G = atoi(e); if (G >= 1) { *nb_out = nbmax; *G_out = std::min(std::min(G, maxG), nbmax); return; } }
   const int nbmin = (nbmax == remaining) ? nbmax : std::max(1, (3 * nbmax) / 4);   // the last batch takes what is left
   for (int nb = nbmax; nb >= nbmin; nb--)
     for (int G = 1; G <= std::min(maxG, nb); G++) {

@@ -42,9 +42,9 @@ __device__ __forceinline__ ZItem zitem(const DevPlan& P, int it, int nblk)
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// grid (#SMs), block 256 (two warps per TMEM lane quarter).  smem: stage[2][cmax] complex
-template <class ZS>
-__global__ void __launch_bounds__(256, 1) k_zcol_bwd_t(const __grid_constant__ DevPlan P, const cplx* __restrict__ c, size_t ldc,
+// grid (#SMs), block 128*MW (MW warps per TMEM lane quarter).  smem: stage[2][cmax] complex
+template <class ZS, int MW>
+__global__ void __launch_bounds__(128 * MW, 1) k_zcol_bwd_t(const __grid_constant__ DevPlan P, const cplx* __restrict__ c, size_t ldc,
                                                        cplx* __restrict__ zt, int nunits, int nblk, int cmax)
 {
   static_assert(ZS::NP2 == 112, "thread-per-column passes are written for 112 = 16 x 7");
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(256, 1) k_zcol_bwd_t(const __grid_constant__ D
   const uint32_t tbase = tmem_slot;
   const int q = warp & 3, m = warp >> 2;
   const uint32_t t0 = tbase + ((uint32_t)(q * 32) << 16);
-  constexpr int MW = 2;
   const int blo = (7 * m) / MW, bhi = (7 * (m + 1)) / MW, klo = (16 * m) / MW, khi = (16 * (m + 1)) / MW;
   constexpr unsigned MASK = zmask(16, 7, ZS::ZSPLIT, ZS::ZSKIP);
   const int nitems = nunits * nblk;
@@ -266,7 +265,8 @@ int zcol_t_setup(qb200_plan* p, const std::vector<int>& first)
       tw[2 * (16 * b + k1) + 1] = (double)sinl(twopi * e / ZtMgO216::NP2);
     }
   QB_CUDA(cudaMemcpyToSymbol(c_ztw, tw, sizeof(tw)));
-  QB_CUDA(cudaFuncSetAttribute(k_zcol_bwd_t<ZtMgO216>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_zt_b));
+  QB_CUDA((cudaFuncSetAttribute(k_zcol_bwd_t<ZtMgO216, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_zt_b)));
+  QB_CUDA((cudaFuncSetAttribute(k_zcol_bwd_t<ZtMgO216, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_zt_b)));
   QB_CUDA(cudaFuncSetAttribute(k_zcol_fwd_t<ZtMgO216>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_zt_f));
   p->zcol_t = true;
   return QB200_OK;
@@ -275,7 +275,9 @@ int zcol_t_setup(qb200_plan* p, const std::vector<int>& first)
 int launch_zbwd_t(qb200_plan* p, const double* c, size_t ldc, int nunits)
 {
   const int nitems = nunits * p->zt_nblk;
-  k_zcol_bwd_t<ZtMgO216><<<std::min(p->nsm, nitems), 256, p->smem_zt_b, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits, p->zt_nblk, p->zt_cmax);
+  static const int mw = [] { const char* e = getenv("QB200_ZB_MW"); return e ? atoi(e) : 2; }();
+  if (mw == 4) k_zcol_bwd_t<ZtMgO216, 4><<<std::min(p->nsm, nitems), 512, p->smem_zt_b, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits, p->zt_nblk, p->zt_cmax);
+  else k_zcol_bwd_t<ZtMgO216, 2><<<std::min(p->nsm, nitems), 256, p->smem_zt_b, p->stream>>>(p->d, (const cplx*)c, ldc, (cplx*)p->zt, nunits, p->zt_nblk, p->zt_cmax);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_zcol_bwd_t launch", __FILE__, __LINE__);
   return QB200_OK;
