@@ -177,6 +177,45 @@ def test_cuda_vs_oracle_seeded(cell, ecut, kpoint, fc, nst, ldpad):
     assert relerr(rho.cpu().numpy(), rho_want) < TOL
 
 
+@pytest.mark.parametrize("fc,nst,ldpad", [(True, 7, 3), (False, 5, 0)])
+def test_cuda_mgo216_shape_vs_oracle_seeded(fc, nst, ldpad):
+    """the benchmark's grid (MgO216 cell, 50 Ry, 112^3) through the tensor-memory kernels against the oracle on seeded inputs:
+    complex states with a padded leading dimension, zero occupations (units the density kernel skips) and a workspace of
+    three units per batch; and the Gamma-point REAL basis on the same grid (pairs through k_plane_t, the odd tail with its
+    imaginary part dropped through k_plane_s, z columns through the shared-memory tiles)"""
+    cell, ecut = (23.1, 0, 0, 0, 23.1, 0, 0, 0, 23.1), 25.0
+    b = P.make_basis(cell, ecut, (0, 0, 0), fc)
+    grid = P.density_grid(cell, ecut)
+    assert grid == (112, 112, 112) and b["is_real"] == (not fc)
+    ldc = b["ngw"] + ldpad
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, b["is_real"], seed=15)
+    v = R.synth_potential(*grid, seed=19)
+    occ = R.synth_occ(nst, nst - 1)
+    occ[1] = 0.0
+    oft = P.FT(b, *grid)
+    ft = H.FourierTransform(b, *grid)
+    assert ft.query(17) == 1 and ft.query(18) == (1 if fc else 0)
+    ft.set_workspace(3 * ft.nvec() * grid[2] * 16)
+    want = oft.rs_mul_add(c, v, np.zeros_like(c))
+    P.kinetic_add(b["kpg2"], c, want)
+    got = _dev(np.zeros_like(c))
+    H.rs_mul_add(ft, _dev(c), _dev(v), got, kpg2=_dev(b["kpg2"]))
+    got = got.cpu().numpy()
+    assert relerr(got[:, :b["ngw"]], want[:, :b["ngw"]]) < TOL
+    assert np.all(got[:, b["ngw"]:] == 0)
+    rho_want = oft.compute_density(c, occ / b["omega"], np.full(oft.N, 0.25))
+    rho = _dev(np.full(oft.N, 0.25))
+    H.compute_density(ft, _dev(c), 1.0, occ, b["omega"], rho)
+    assert relerr(rho.cpu().numpy(), rho_want) < TOL
+    # the same calls with host pointers (sliced, pipelined uploads)
+    goth = np.zeros_like(c)
+    H.rs_mul_add(ft, c, v, goth, kpg2=b["kpg2"])
+    assert relerr(goth[:, :b["ngw"]], want[:, :b["ngw"]]) < TOL
+    rhoh = np.full(oft.N, 0.25)
+    H.compute_density(ft, c, 1.0, occ, b["omega"], rhoh)
+    assert relerr(rhoh, rho_want) < TOL
+
+
 def test_properties_mgo216_full_size():
     """BASELINE-size shape (MgO216: 112^3, ngw 73447): size-independent properties -- fwd(bwd(c)) = c, Parseval,
     linearity of H_loc, integral of rho = sum of occupations times norms."""
