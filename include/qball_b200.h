@@ -142,6 +142,22 @@ int qb200_nl_destroy(qb200_nl* nl);
  * The row-sum of enl over G-row ranks (NonLocalPotential.cc:2629) is the identity with nprow = 1. */
 int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, int compute_hpsi, double* cp,
                     double* enl);
+/* ---- Ultrasoft beta.psi path.  The object is created as above with, per species, the reference's
+ * betag tables -- twnl[lm*ngw + ig] = beta_b(|k+G|) * Y_lm(k+G), lproj[lm] = l of channel lm, wt unused -- as
+ * SlaterDet::calc_betag fills them before the (-i)^l factor (src/qball/SlaterDet.cc:2006-2127; an input like twnl).  Complex
+ * bases only: ultrasoft potentials force complex states (SlaterDet.cc:57-58); QB200_EUNSUPPORTED otherwise.
+ * Projector order p: species in the order added, then atom, then channel (ia*npr + lm), M = total number.
+ *   qb200_nl_betapsi : betapsi[n*M + p] = sum_G conj(anl_p(G)) c_n(G), anl = betag * (-i)^l * exp(-i (k+G).tau)
+ *                      replaces SlaterDet::calc_betapsi (SlaterDet.cc:2130-2263)
+ *   qb200_nl_add_beta: cp_n(G) += sum_p anl_p(G) f[n*M + p]            the gemm of SlaterDet::calc_spsi (:2565) and of the
+ *                      ultrasoft H psi (NonLocalPotential.cc:1554-1906) with the caller's coupling already applied to f
+ *   qb200_nl_spsi    : spsi = c + sum anl_p (q betapsi)_p / omega; qmat = per species, in order, the dense symmetric npr x npr
+ *                      matrix built from the (lm1, lm2, qaug) triples of SlaterDet::calc_spsi (:2536-2549); betapsi (optional,
+ *                      may be NULL) receives <beta|psi>.  replaces SlaterDet::calc_spsi (SlaterDet.cc:2426-2570)
+ * c, cp, spsi: ldc x nst complex blocks, host or device; betapsi, f: nst x M complex, host or device; qmat: host or device. */
+int qb200_nl_betapsi(qb200_nl* nl, int ldc, int nst, const double* c, double* betapsi);
+int qb200_nl_add_beta(qb200_nl* nl, int ldc, int nst, const double* f, double* cp);
+int qb200_nl_spsi(qb200_nl* nl, int ldc, int nst, const double* c, const double* qmat, double* spsi, double* betapsi);
 long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call,
                                                            12: bytes of the anl block, 13: projectors in total,
                                                            14: form of the last call: 0 real basis, 1 complex 4-product,

@@ -301,3 +301,57 @@ def gram(c, is_real):
     info = lib().qbo_gram(ldc, nst, int(is_real), _d(out))
     assert info == 0, f"gram: leading minor {info} not positive definite"
     return out
+
+
+# --------------------------------------------------------------------------------------------- ultrasoft beta.psi (row f4)
+def us_anl(b: dict, s: dict):
+    """betag with the structure factor: anl[ia*npr + lm, ig] = betag_lm(ig) * (-i)^l * exp(-i (k+G).tau_ia)
+    (SlaterDet::calc_betag, SlaterDet.cc:2006-2127, and the phase of calc_betapsi's !highmem branch, :2222-2236)"""
+    kpgx = np.asarray(b["kpgx"], dtype=np.float64)                       # (3, ngw)
+    il = np.array([1.0, -1.0j, -1.0, 1.0j])[np.asarray(s["lproj"]) & 3]     # (-i)^l
+    arg = np.asarray(s["tau"]) @ kpgx                                     # (na, ngw)
+    ph = np.cos(arg) - 1j * np.sin(arg)
+    bg = np.asarray(s["twnl"]) * il[:, None]                              # (npr, ngw)
+    return (ph[:, None, :] * bg[None, :, :]).reshape(s["na"] * s["npr"], -1)
+
+
+def us_qmatrix(s: dict):
+    """dense symmetric coupling of one species from its (lm1, lm2, qaug) triples (the loop of SlaterDet::calc_spsi,
+    SlaterDet.cc:2536-2549: bpsum[lm1] += q * bp[lm2]; and the transposed term when lm1 != lm2)"""
+    q = np.zeros((s["npr"], s["npr"]))
+    for a, bb, v in zip(s["lm1"], s["lm2"], s["qaug"]):
+        q[a, bb] += v
+        if a != bb:
+            q[bb, a] += v
+    return q
+
+
+def us_betapsi(b: dict, c, species):
+    """SlaterDet::calc_betapsi (SlaterDet.cc:2130-2263, complex basis): betapsi[n, p] = sum_G conj(anl_p(G)) c_n(G);
+    species concatenated, p = ia*npr + lm inside a species"""
+    ngw = b["ngw"]
+    return np.concatenate([c[:, :ngw] @ np.conj(us_anl(b, s)).T for s in species], axis=1)
+
+
+def us_add_beta(b: dict, f, species, cp):
+    """cp_n(G) += sum_p anl_p(G) f[n, p] (the gemm of SlaterDet::calc_spsi, SlaterDet.cc:2565)"""
+    ngw, off = b["ngw"], 0
+    for s in species:
+        m = s["na"] * s["npr"]
+        cp[:, :ngw] += f[:, off:off + m] @ us_anl(b, s)
+        off += m
+    return cp
+
+
+def us_spsi(b: dict, c, species):
+    """SlaterDet::calc_spsi (SlaterDet.cc:2426-2570): S psi = psi + sum_{a,nm} beta_n q_nm <beta_m|psi> / omega"""
+    bp = us_betapsi(b, c, species)
+    f = np.zeros_like(bp)
+    off = 0
+    for s in species:
+        q = us_qmatrix(s)
+        m = s["na"] * s["npr"]
+        blk = bp[:, off:off + m].reshape(-1, s["na"], s["npr"])
+        f[:, off:off + m] = (blk @ q.T).reshape(-1, m) / b["omega"]
+        off += m
+    return us_add_beta(b, f, species, c.copy()), bp

@@ -132,7 +132,7 @@ int main(int argc, char** argv)
   UnitCell cell(D3vector(a[0],a[1],a[2]), D3vector(a[3],a[4],a[5]), D3vector(a[6],a[7],a[8]));
   D3vector kpoint(kp[0],kp[1],kp[2]);
 
-  SlaterDet sd(ctxt, colctxt, ctxtsq, kpoint, false, force_complex != 0);
+  SlaterDet sd(ctxt, colctxt, ctxtsq, kpoint, mode == "us", force_complex != 0);   // (ultrasoft forces complex states, SlaterDet.cc:57-58)
   sd.set_nblocks(1,1);
   sd.resize(cell, cell, ecut, nst);
   const Basis& basis = sd.basis();
@@ -179,6 +179,51 @@ int main(int argc, char** argv)
     Atom* at = new Atom(atomlines[i].name, atomlines[i].species,
                         D3vector(atomlines[i].x, atomlines[i].y, atomlines[i].z), D3vector(0,0,0));
     atoms.addAtom(at);
+  }
+  if (mode == "us") {
+    // ---- the ultrasoft beta.psi path.  SlaterDet::init_usfns (SlaterDet.cc:103-197) runs calc_betag
+    //      (:2006-2127), calc_betapsi (:2130-2263), Species::calc_qnmg -> set_qaug, calc_spsi (:2426-2570) on the given states
+    vector<complex<double> > cin((size_t)mloc*nst);
+    slurp(out + ".in_c.f64", &cin[0], cin.size()*sizeof(complex<double>));
+    memcpy(sd.c().valptr(), &cin[0], cin.size()*sizeof(complex<double>));
+    sd.init_usfns(&atoms);
+    vector<vector<double> > tau; atoms.get_positions(tau, true);
+    for (int is = 0; is < atoms.nsp(); is++) {
+      Species* s = atoms.species_list[is];
+      if (!s->ultrasoft()) { fprintf(stderr, "species %d is not ultrasoft\n", is); return 3; }
+      char tag[32]; snprintf(tag, sizeof tag, ".us%d", is);
+      const int na = atoms.na(is), nlm = s->nbetalm(), nq = s->nqtot();
+      int h[4] = { na, nlm, nq, 0 };
+      dump(out + tag + ".hdr.i32", h, sizeof h);
+      vector<int> l(nlm), lm1(nq), lm2(nq);
+      for (int lm = 0; lm < nlm; lm++) l[lm] = s->betalm_l(lm);
+      for (int qi = 0; qi < nq; qi++) { lm1[qi] = s->qnm_lm1(qi); lm2[qi] = s->qnm_lm2(qi); }
+      dump(out + tag + ".l.i32", &l[0], nlm*sizeof(int));
+      dump(out + tag + ".lm1.i32", &lm1[0], nq*sizeof(int));
+      dump(out + tag + ".lm2.i32", &lm2[0], nq*sizeof(int));
+      // betag without the structure factor (the !highmem branch): bval * ylm * (-i)^l -> the real table bval * ylm
+      const complex<double>* bg = sd.betag(is)->cvalptr();
+      const int bg_mloc = sd.betag(is)->mloc();
+      vector<double> tw((size_t)nlm*ngw);
+      for (int lm = 0; lm < nlm; lm++) {
+        const complex<double> il = l[lm] == 0 ? complex<double>(1,0) : l[lm] == 1 ? complex<double>(0,-1) : l[lm] == 2 ? complex<double>(-1,0) : complex<double>(0,1);
+        for (int ig = 0; ig < ngw; ig++) tw[(size_t)lm*ngw + ig] = real(bg[(size_t)lm*bg_mloc + ig] / il);
+      }
+      dump(out + tag + ".betag.f64", &tw[0], tw.size()*sizeof(double));
+      dump(out + tag + ".tau.f64", &tau[is][0], 3*na*sizeof(double));
+      vector<complex<double> > qnm; vector<double> qaug;
+      s->calc_qnmg(const_cast<Basis*>(&basis), qnm, qaug);
+      dump(out + tag + ".qaug.f64", &qaug[0], nq*sizeof(double));
+      // betapsi: (na*nlm) x nst, element (ia*nlm + lm, n)
+      const ComplexMatrix* bp = sd.betapsi(is);
+      vector<complex<double> > bpo((size_t)nst*na*nlm);
+      for (int n = 0; n < nst; n++)
+        for (int i = 0; i < na*nlm; i++) bpo[(size_t)n*na*nlm + i] = bp->cvalptr()[(size_t)n*bp->mloc() + i];
+      dump(out + tag + ".betapsi.f64", &bpo[0], bpo.size()*sizeof(complex<double>));
+    }
+    dump(out + ".spsi.f64", sd.spsi().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+    MPI_Finalize();
+    return 0;
   }
   NonLocalPotential* nlp = 0;
   if (!species.empty()) {

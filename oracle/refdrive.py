@@ -123,3 +123,37 @@ def run_reference(case: Case, seed: int = 1, nocc: int | None = None, workdir: s
         r["hnl"] = _load(prefix, "hnl.f64", np.complex128).reshape(case.nst, b["mloc"])
     assert r["bwd0"].shape[0] == N
     return r
+
+
+def run_reference_us(case: Case, seed: int = 1, workdir: str | None = None, threads: int = 8) -> dict:
+    """SURVEY section 8 row f4 (ultrasoft beta.psi path): ``ref_driver us`` = the reference's own SlaterDet::init_usfns
+    (calc_betag, calc_betapsi, Species::calc_qnmg -> set_qaug, calc_spsi) on seeded coefficients.  Returns the basis, the
+    coefficients, per species the betag tables (without (-i)^l and without the structure factor), l per channel, the
+    (lm1, lm2, qaug) triples, positions and betapsi; and spsi."""
+    assert have_ref(), "oracle/_ref/ref_driver missing: run `make -C oracle ref` where /root/reference exists"
+    tmp = workdir or tempfile.mkdtemp(prefix="qbrefus_")
+    prefix = os.path.join(tmp, "case")
+    cf = os.path.join(tmp, "case.txt")
+    with open(cf, "w") as f:
+        f.write(case.text(prefix))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    subprocess.run([REF_DRIVER, "basis", cf], check=True, env=env, stdout=subprocess.DEVNULL)
+    b = read_basis(prefix)
+    c = synth_coefficients(b["kpg2"], case.ecut, case.nst, b["mloc"], b["is_real"], seed)
+    c.tofile(prefix + ".in_c.f64")
+    subprocess.run([REF_DRIVER, "us", cf], check=True, env=env, stdout=subprocess.DEVNULL)
+    r = dict(b)
+    r["c"] = c
+    sp = []
+    for i in range(b["nsp"]):
+        h = _load(prefix, f"us{i}.hdr.i32", np.int32)
+        na, nlm, nq = int(h[0]), int(h[1]), int(h[2])
+        sp.append(dict(na=na, npr=nlm, lproj=_load(prefix, f"us{i}.l.i32", np.int32),
+                       twnl=_load(prefix, f"us{i}.betag.f64", np.float64).reshape(nlm, b["ngw"]),
+                       tau=_load(prefix, f"us{i}.tau.f64", np.float64).reshape(na, 3),
+                       lm1=_load(prefix, f"us{i}.lm1.i32", np.int32), lm2=_load(prefix, f"us{i}.lm2.i32", np.int32),
+                       qaug=_load(prefix, f"us{i}.qaug.f64", np.float64),
+                       betapsi=_load(prefix, f"us{i}.betapsi.f64", np.complex128).reshape(case.nst, na * nlm)))
+    r["species"] = sp
+    r["spsi"] = _load(prefix, "spsi.f64", np.complex128).reshape(case.nst, b["mloc"])
+    return r

@@ -1052,6 +1052,251 @@ extern "C" int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, 
   return QB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ ultrasoft beta.psi path
+// SlaterDet::calc_betapsi (SlaterDet.cc:2130-2263) and the gemms of SlaterDet::calc_spsi (:2426-2570)
+// are the projector contraction and the back-projection WITHOUT the diagonal weights of the norm-conserving form: betapsi =
+// anl^H c, S psi = psi + anl (q betapsi) / omega with the species' symmetric coupling q between the channels of one atom.
+// The tables are the reference's betag (beta_b(|k+G|) Y_lm(k+G), SlaterDet::calc_betag :2006-2127; an INPUT like twnl) given
+// to qb200_nl_add_species with lproj = l of the channel; the structure factor and (-i)^l are applied as for anl.  Ultrasoft
+// potentials force complex states (SlaterDet.cc:57-58), so these entry points require a complex basis; they run the
+// 4-product DMMA kernels (k_anl_gen<0>, k_fnl<0>, k_back<0>), plane-wave chunk by chunk.
+__global__ void __launch_bounds__(256) k_us_collect(const double* __restrict__ part, int Mp, int nst, int ksplit, int Mtot, double* __restrict__ bp)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nst * Mtot) return;
+  const int n = (int)(idx / Mtot), p = (int)(idx % Mtot);
+  double fr = 0.0, fi = 0.0;
+  for (int ks = 0; ks < ksplit; ks++) {                     // fixed order: deterministic
+    fr += part[((size_t)ks * 2 * nst + 2 * n) * Mp + p];
+    fi += part[((size_t)ks * 2 * nst + 2 * n + 1) * Mp + p];
+  }
+  bp[2 * idx] = fr;
+  bp[2 * idx + 1] = fi;
+}
+// fs[n][p] (pitch Mp complex, zero pad) = f[n][p]
+__global__ void __launch_bounds__(256) k_us_pack(const double2* __restrict__ f, int Mtot, int nst, int Mp, double2* __restrict__ fs)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nst * Mp) return;
+  const int n = (int)(idx / Mp), p = (int)(idx % Mp);
+  fs[idx] = p < Mtot ? f[(size_t)n * Mtot + p] : make_double2(0.0, 0.0);
+}
+// f[n][p] = omega_inv * sum_lm' q_species(p)[lm(p)][lm'] bp[n][atom block of p + lm'];  meta[4p..] = block start, npr, q offset, lm
+__global__ void __launch_bounds__(256) k_us_couple(const double2* __restrict__ bp, int Mtot, int nst, const int* __restrict__ meta,
+                                                   const double* __restrict__ q, double omega_inv, double2* __restrict__ f)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nst * Mtot) return;
+  const int n = (int)(idx / Mtot), p = (int)(idx % Mtot);
+  const int b0 = meta[4 * p], npr = meta[4 * p + 1], qo = meta[4 * p + 2], lm = meta[4 * p + 3];
+  const double2* b = bp + (size_t)n * Mtot + b0;
+  const double* qr = q + qo + (size_t)lm * npr;
+  double fr = 0.0, fi = 0.0;
+  for (int j = 0; j < npr; j++) { fr += qr[j] * b[j].x; fi += qr[j] * b[j].y; }
+  f[idx] = make_double2(omega_inv * fr, omega_inv * fi);
+}
+
+static int nl_us_check(qb200_nl* nl, const char* who)
+{
+  if (nl->is_real) { set_error(std::string(who) + ": ultrasoft projectors need a complex basis (SlaterDet.cc:57-58)"); return QB200_EUNSUPPORTED; }
+  return QB200_OK;
+}
+static void nl_us_chunking(const qb200_nl* nl, int* gchunk, int* nchunks)
+{
+  long long gmax = nl->anl_budget / std::max(32ll * nl->Mtot, 1ll);
+  gmax = std::max(512ll, (gmax / 512) * 512);
+  *gchunk = (int)std::min<long long>(gmax, ((long long)nl->ngw + 15) / 16 * 16);
+  *nchunks = (nl->ngw + *gchunk - 1) / *gchunk;
+}
+static int nl_us_gen(qb200_nl* nl, int gbeg, int gcount, int gpad, size_t WP)
+{
+  for (const NlSpecies& S : nl->sp) {
+    if (S.M <= 0) continue;
+    k_anl_gen<0><<<dim3((gpad + 127) / 128, S.na), 128, 0, nl->stream>>>(S, nl->lat, nl->ngw, nl->kpgx, gbeg, gcount, gpad, nl->W, WP);
+    NL_LAUNCH_CHECK(nl);
+  }
+  return QB200_OK;
+}
+// bp_dev[nst][Mtot] complex (device) = anl^H c
+static int nl_us_project(qb200_nl* nl, int ldc, int nst, const double* c, double* bp_dev)
+{
+  int rc;
+  if ((rc = nl_refresh_tables(nl))) return rc;
+  const int Mtot = nl->Mtot, RW = 2 * Mtot, Mp = (Mtot + 1) & ~1, ngw = nl->ngw;
+  int gchunk, nchunks;
+  nl_us_chunking(nl, &gchunk, &nchunks);
+  const size_t WP = 2 * (size_t)gchunk;
+  if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
+  nl->W_valid = false; nl->W_WP = 0;                                     // W is rewritten in the 4-product layout
+  const int mt = (RW + NL_TM - 1) / NL_TM, nt = (nst + NL_TN - 1) / NL_TN;
+  int ksplit = 1;
+  {
+    const int maxk = std::max(1, std::min(gchunk, ngw) / 512);
+    double best = -1.0;
+    for (int k = 1; k <= std::min(maxk, 64); k++) {
+      const long ctas = (long)mt * nt * k, waves = (ctas + nl->nsm - 1) / nl->nsm;
+      const double eff = (double)ctas / (double)(waves * nl->nsm) - 0.002 * k;
+      if (eff > best) { best = eff; ksplit = k; }
+    }
+  }
+  if ((rc = nl_ensure(&nl->part, &nl->part_cap, (size_t)ksplit * 2 * nst * Mp))) return rc;
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = nl_us_gen(nl, gbeg, gcount, gpad, WP))) return rc;
+    int kper = (2 * gcount + ksplit - 1) / ksplit;
+    kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
+    k_fnl<0><<<dim3(mt, nt, ksplit), NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, kper, (const double2*)c, ldc, nst, nl->part, Mp, Mtot, ch > 0);
+    NL_LAUNCH_CHECK(nl);
+  }
+  const size_t total = (size_t)nst * Mtot;
+  k_us_collect<<<(unsigned)((total + 255) / 256), 256, 0, nl->stream>>>(nl->part, Mp, nst, ksplit, Mtot, bp_dev);
+  NL_LAUNCH_CHECK(nl);
+  return QB200_OK;
+}
+// cp (device) += anl f, f_dev[nst][Mtot] complex (device)
+static int nl_us_backproject(qb200_nl* nl, int ldc, int nst, const double* f_dev, double* cp)
+{
+  int rc;
+  if ((rc = nl_refresh_tables(nl))) return rc;
+  const int Mtot = nl->Mtot, RW = 2 * Mtot, Mp = (Mtot + 1) & ~1, ngw = nl->ngw;
+  int gchunk, nchunks;
+  nl_us_chunking(nl, &gchunk, &nchunks);
+  const size_t WP = 2 * (size_t)gchunk;
+  if ((rc = nl_ensure(&nl->W, &nl->W_cap, (size_t)RW * WP))) return rc;
+  nl->W_valid = false; nl->W_WP = 0;
+  if ((rc = nl_ensure(&nl->fs, &nl->fs_cap, (size_t)nst * 2 * Mp))) return rc;
+  k_us_pack<<<(unsigned)(((size_t)nst * Mp + 255) / 256), 256, 0, nl->stream>>>((const double2*)f_dev, Mtot, nst, Mp, (double2*)nl->fs);
+  NL_LAUNCH_CHECK(nl);
+  const int nt = (nst + NL_TN - 1) / NL_TN;
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int gbeg = ch * gchunk, gcount = std::min(gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = nl_us_gen(nl, gbeg, gcount, gpad, WP))) return rc;
+    k_back<0><<<dim3(nt, (gcount + 63) / 64), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->W, WP, RW, gbeg, gcount, nl->fs, 2 * Mp, (double2*)cp, ldc, nst, 0);
+    NL_LAUNCH_CHECK(nl);
+  }
+  return QB200_OK;
+}
+
+// small device scratch of the ultrasoft entry points (freed with the object through `owned`)
+static int nl_us_scratch(qb200_nl* nl, size_t bytes, void** out)
+{
+  void* d = nullptr;
+  QB_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  *out = d;
+  return QB200_OK;
+}
+
+extern "C" int qb200_nl_betapsi(qb200_nl* nl, int ldc, int nst, const double* c, double* betapsi)
+{
+  if (!nl || !c || !betapsi || nst < 0 || ldc < nl->ngw) { set_error("qb200_nl_betapsi: bad argument"); return QB200_EINVAL; }
+  int rc;
+  if ((rc = nl_us_check(nl, "qb200_nl_betapsi"))) return rc;
+  if (nst == 0 || nl->Mtot == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(nl->device));
+  const size_t blk = 2 * (size_t)ldc * nst, nbp = 2 * (size_t)nst * nl->Mtot;
+  const double* cd = c;
+  if (!is_device_ptr(c)) {
+    if ((rc = nl_ensure(&nl->st_c, &nl->st_c_cap, blk))) return rc;
+    QB_CUDA(cudaMemcpyAsync(nl->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
+    cd = nl->st_c;
+  }
+  void* bpd = betapsi;
+  const bool bhost = !is_device_ptr(betapsi);
+  if (bhost && (rc = nl_us_scratch(nl, nbp * sizeof(double), &bpd))) return rc;
+  rc = nl_us_project(nl, ldc, nst, cd, (double*)bpd);
+  if (!rc && bhost) { const cudaError_t e = cudaMemcpyAsync(betapsi, bpd, nbp * sizeof(double), cudaMemcpyDeviceToHost, nl->stream); if (e != cudaSuccess) rc = cuda_fail(e, "copy", __FILE__, __LINE__); }
+  const cudaError_t es = cudaStreamSynchronize(nl->stream);
+  if (bhost) cudaFree(bpd);
+  if (!rc && es != cudaSuccess) rc = cuda_fail(es, "qb200_nl_betapsi", __FILE__, __LINE__);
+  return rc;
+}
+
+extern "C" int qb200_nl_add_beta(qb200_nl* nl, int ldc, int nst, const double* f, double* cp)
+{
+  if (!nl || !f || !cp || nst < 0 || ldc < nl->ngw) { set_error("qb200_nl_add_beta: bad argument"); return QB200_EINVAL; }
+  int rc;
+  if ((rc = nl_us_check(nl, "qb200_nl_add_beta"))) return rc;
+  if (nst == 0 || nl->Mtot == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(nl->device));
+  const size_t blk = 2 * (size_t)ldc * nst, nbp = 2 * (size_t)nst * nl->Mtot;
+  void* fd = const_cast<double*>(f);
+  const bool fhost = !is_device_ptr(f);
+  if (fhost) {
+    if ((rc = nl_us_scratch(nl, nbp * sizeof(double), &fd))) return rc;
+    QB_CUDA(cudaMemcpyAsync(fd, f, nbp * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
+  }
+  double* cpd = cp;
+  if (!is_device_ptr(cp)) {
+    if ((rc = nl_ensure(&nl->st_cp, &nl->st_cp_cap, blk))) return rc;
+    QB_CUDA(cudaMemcpyAsync(nl->st_cp, cp, blk * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
+    cpd = nl->st_cp;
+  }
+  rc = nl_us_backproject(nl, ldc, nst, (const double*)fd, cpd);
+  if (!rc && cpd != cp) { const cudaError_t e = cudaMemcpyAsync(cp, cpd, blk * sizeof(double), cudaMemcpyDeviceToHost, nl->stream); if (e != cudaSuccess) rc = cuda_fail(e, "copy", __FILE__, __LINE__); }
+  const cudaError_t es = cudaStreamSynchronize(nl->stream);
+  if (fhost) cudaFree(fd);
+  if (!rc && es != cudaSuccess) rc = cuda_fail(es, "qb200_nl_add_beta", __FILE__, __LINE__);
+  return rc;
+}
+
+extern "C" int qb200_nl_spsi(qb200_nl* nl, int ldc, int nst, const double* c, const double* qmat, double* spsi, double* betapsi)
+{
+  if (!nl || !c || !qmat || !spsi || nst < 0 || ldc < nl->ngw) { set_error("qb200_nl_spsi: bad argument"); return QB200_EINVAL; }
+  int rc;
+  if ((rc = nl_us_check(nl, "qb200_nl_spsi"))) return rc;
+  if (nst == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(nl->device));
+  const size_t blk = 2 * (size_t)ldc * nst, nbp = 2 * (size_t)nst * nl->Mtot;
+  const double* cd = c;
+  if (!is_device_ptr(c)) {
+    if ((rc = nl_ensure(&nl->st_c, &nl->st_c_cap, blk))) return rc;
+    QB_CUDA(cudaMemcpyAsync(nl->st_c, c, blk * sizeof(double), cudaMemcpyHostToDevice, nl->stream));
+    cd = nl->st_c;
+  }
+  double* sd = spsi;
+  if (!is_device_ptr(spsi)) {
+    if ((rc = nl_ensure(&nl->st_cp, &nl->st_cp_cap, blk))) return rc;
+    sd = nl->st_cp;
+  }
+  QB_CUDA(cudaMemcpyAsync(sd, cd, blk * sizeof(double), cudaMemcpyDeviceToDevice, nl->stream));   // spsi_ = c_  (SlaterDet.cc:2438)
+  if (nl->Mtot > 0) {
+    // per-projector description of the coupling and the species' q matrices
+    std::vector<int> meta(4 * (size_t)nl->Mtot);
+    size_t qo = 0;
+    for (const NlSpecies& S : nl->sp) {
+      for (int ia = 0; ia < S.na; ia++)
+        for (int lm = 0; lm < S.npr; lm++) {
+          const size_t p = (size_t)S.poff + (size_t)ia * S.npr + lm;
+          meta[4 * p] = S.poff + ia * S.npr; meta[4 * p + 1] = S.npr; meta[4 * p + 2] = (int)qo; meta[4 * p + 3] = lm;
+        }
+      qo += (size_t)S.npr * S.npr;
+    }
+    void *md = nullptr, *qd = nullptr, *bpd = nullptr, *fd = nullptr;
+    if ((rc = nl_us_scratch(nl, meta.size() * sizeof(int), &md)) || (rc = nl_us_scratch(nl, qo * sizeof(double), &qd)) ||
+        (rc = nl_us_scratch(nl, nbp * sizeof(double), &bpd)) || (rc = nl_us_scratch(nl, nbp * sizeof(double), &fd))) {
+      for (void* q : { md, qd, bpd, fd }) if (q) cudaFree(q);
+      return rc;
+    }
+    cudaMemcpyAsync(md, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, nl->stream);
+    cudaMemcpyAsync(qd, qmat, qo * sizeof(double), cudaMemcpyDefault, nl->stream);
+    rc = nl_us_project(nl, ldc, nst, cd, (double*)bpd);
+    if (!rc) {
+      const size_t total = (size_t)nst * nl->Mtot;
+      k_us_couple<<<(unsigned)((total + 255) / 256), 256, 0, nl->stream>>>((const double2*)bpd, nl->Mtot, nst, (const int*)md, (const double*)qd, 1.0 / nl->omega, (double2*)fd);
+      nl->launches++;
+      rc = nl_us_backproject(nl, ldc, nst, (const double*)fd, sd);
+    }
+    if (!rc && betapsi) cudaMemcpyAsync(betapsi, bpd, nbp * sizeof(double), cudaMemcpyDefault, nl->stream);
+    const cudaError_t es = cudaStreamSynchronize(nl->stream);
+    for (void* q : { md, qd, bpd, fd }) cudaFree(q);
+    if (!rc && es != cudaSuccess) rc = cuda_fail(es, "qb200_nl_spsi", __FILE__, __LINE__);
+    if (rc) return rc;
+  }
+  if (sd != spsi) QB_CUDA(cudaMemcpyAsync(spsi, sd, blk * sizeof(double), cudaMemcpyDeviceToHost, nl->stream));
+  QB_CUDA(cudaStreamSynchronize(nl->stream));
+  return QB200_OK;
+}
+
 double* qb200_nl_enl_dev(qb200_nl* nl) { return nl->enl_dev; }
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s) { cudaStream_t o = nl->stream; nl->stream = s; return o; }
 

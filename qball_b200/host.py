@@ -233,6 +233,30 @@ class NonLocalPotential:
                                             C.byref(enl)), "qb200_nl_energy")
         return enl.value
 
+    # ---- ultrasoft beta.psi path: the object was built from the reference's betag tables
+    #      (species[i]["twnl"] = beta_b(|k+G|) Y_lm(k+G), "lproj" = l per channel, "wt" unused)
+    def nproj(self): return int(self._L.qb200_nl_query(self._h, 13))
+
+    def betapsi(self, c, out):
+        """SlaterDet::calc_betapsi (SlaterDet.cc:2130-2263): out[n, p] = <beta_p|psi_n>, p = species, atom, channel"""
+        nst, ldc = _block_dims(c)
+        capi._check(self._L.qb200_nl_betapsi(self._h, ldc, nst, capi.ptr(c), capi.ptr(out)), "qb200_nl_betapsi")
+        return out
+
+    def add_beta(self, f, cp):
+        """cp_n(G) += sum_p beta_p(G) f[n, p] (the gemm of SlaterDet::calc_spsi, SlaterDet.cc:2565)"""
+        nst, ldc = _block_dims(cp)
+        capi._check(self._L.qb200_nl_add_beta(self._h, ldc, nst, capi.ptr(f), capi.ptr(cp)), "qb200_nl_add_beta")
+        return cp
+
+    def spsi(self, c, qmats, out, betapsi=None):
+        """SlaterDet::calc_spsi (SlaterDet.cc:2426-2570): out = c + sum beta (q <beta|psi>) / omega; qmats = list of the species'
+        dense symmetric npr x npr coupling matrices"""
+        nst, ldc = _block_dims(c)
+        q = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64).ravel() for m in qmats]))
+        capi._check(self._L.qb200_nl_spsi(self._h, ldc, nst, capi.ptr(c), capi.ptr(q), capi.ptr(out), capi.ptr(betapsi)), "qb200_nl_spsi")
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.qb200_nl_destroy(self._h)
