@@ -173,6 +173,20 @@ class NonLocalPotential {
                           reinterpret_cast<double*>(cp), &enl), "qb200_nl_energy");
     return enl;
   }
+  // ---- ultrasoft beta.psi path.  The object holds, per ultrasoft species, the betag tables of
+  // SlaterDet::calc_betag (twnl[lm*ngw + ig] = beta_b(|k+G|) Y_lm(k+G), lproj[lm] = l, wt unused); complex bases only.
+  // void SlaterDet::calc_betapsi(): betapsi[n*M + p], p = species, atom, channel (SlaterDet.cc:2130-2263)
+  void betapsi(int mloc, int nstloc, const std::complex<double>* c, std::complex<double>* betapsi)
+  { check(qb200_nl_betapsi(nl_, mloc, nstloc, reinterpret_cast<const double*>(c), reinterpret_cast<double*>(betapsi)), "qb200_nl_betapsi"); }
+  // cp += sum_p beta_p f_p: the gemm of calc_spsi (SlaterDet.cc:2565) / of the ultrasoft H psi with the caller's coupling in f
+  void add_beta(int mloc, int nstloc, const std::complex<double>* f, std::complex<double>* cp)
+  { check(qb200_nl_add_beta(nl_, mloc, nstloc, reinterpret_cast<const double*>(f), reinterpret_cast<double*>(cp)), "qb200_nl_add_beta"); }
+  // void SlaterDet::calc_spsi(): spsi = c + sum beta (q <beta|psi>) / omega (SlaterDet.cc:2426-2570); qmat = per species the
+  // dense symmetric npr x npr matrix of its (lm1, lm2, qaug) triples; betapsi may be null
+  void spsi(int mloc, int nstloc, const std::complex<double>* c, const double* qmat, std::complex<double>* spsi,
+            std::complex<double>* betapsi = 0)
+  { check(qb200_nl_spsi(nl_, mloc, nstloc, reinterpret_cast<const double*>(c), qmat, reinterpret_cast<double*>(spsi),
+                        reinterpret_cast<double*>(betapsi)), "qb200_nl_spsi"); }
   qb200_nl* handle() const { return nl_; }
 
  private:
