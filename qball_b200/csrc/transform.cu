@@ -230,7 +230,7 @@ static int ensure_work(qb200_plan* p, int units)
   return QB200_OK;
 }
 
-typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 12> ShapeAu992;
+typedef qb200::SplitShape<252, 252, 56, 140, 56, 140, 16, 8> ShapeAu992;
 typedef qb200::SplitShape<126, 126, 29, 68, 29, 68, 16, 8> ShapeSi54p;    // examples/si54p at 65 Ry: 126^3 grid, |h|,|k| <= 28
 typedef qb200::ZShape<112, 29, 26, 60> ZbMgO216;   // examples/MgO216: 112 planes, |l| <= 25; 29 / 22 columns per tile fill one wave
 typedef qb200::ZShape<112, 22, 26, 60> ZfMgO216;
@@ -512,8 +512,7 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     const size_t rowbytes = (size_t)d.pitch0 * 16;
     int rowb = (int)std::min<size_t>(d.nkeep, std::max<size_t>(1, (40 * 1024) / rowbytes));
     if (rowb > 8) rowb = 8;
-    // 252-wide rows (gold benchmark): 12 rows per CTA -- fewer barriers per row, still two resident CTAs (2 x 12 x 4 KB double-buffered)
-    if (np0 == 252 && d.nkeep >= 12) rowb = 12;
+    // (12 rows per CTA for the 252-wide rows of the gold benchmark, compiled in: xy 73.8 ms against 72.5 ms per 64 states -- no gain)
     if (const char* e = getenv("QB200_XR_ROWB")) { const int r = atoi(e); if (r >= 1 && r <= d.nkeep) rowb = r; }
     int smax = 4;
     for (int jr0 = 0; jr0 < d.nkeep; jr0 += rowb) smax = std::max(smax, rowstart[std::min(jr0 + rowb, d.nkeep)] - rowstart[jr0]);
