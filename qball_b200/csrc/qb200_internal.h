@@ -81,6 +81,12 @@ int launch_zfwd_t(qb200_plan* p, double* out, size_t ldc, int nunits, int accumu
 // ycols_tmem.cu: y stage of the split xy path with the column in tensor memory (compiled 126 / 252 plane heights)
 int ycols_t_setup(qb200_plan* p);
 int launch_ycols_t(qb200_plan* p, int op, const double* v, const double* fac, int nunits, int zero_imag);
+// ycols_tmem.cu: the whole xy stage of a 126 x 126 plane in one kernel (kept rows in shared memory, columns in tensor memory)
+bool plane_f_wanted(const qb200_plan* p, int hmax);
+int plane_f_pitch();
+void plane_f_xrange(int* xsplit, int* xskip);
+int plane_f_setup(qb200_plan* p);
+int launch_plane_f(qb200_plan* p, int op, dim3 grid, const double* v, const double* fac, int nunits);
 }
 
 struct qb200_plan {
@@ -121,6 +127,8 @@ struct qb200_plan {
   bool zcol_t;                         // MODE_SINGLE z columns run k_zcol_bwd_t / k_zcol_fwd_t (zcol_tmem.cu)
   int zt_cmax, zt_nblk;                // coefficients of the longest 128-column block, number of blocks
   size_t smem_zt_b, smem_zt_f;
+  bool plane_f;                        // planes too large for k_plane_t's two buffers but whose kept rows fit once: k_plane_f (si54p)
+  size_t smem_plane_f;
   int ycols_t;                         // split path: 0 k_ycols2, 1 k_ycols_t on 126-row planes (si54p), 2 on 252-row planes (Au992)
   // pipelined host-pointer paths (hpsi.cu, qb200_compute_density): copy streams + events, and the identity of the host
   // coefficient block whose device copy sits in st_c (qb200_plan_set_coefficient_tag)

@@ -196,7 +196,7 @@ static void plan_split(const qb200_plan* p, int remaining, int maxG, int* nb_out
 {
   const int np2 = p->d.np2, nsm = std::max(1, p->nsm);
   const int nbmax = std::min(p->batch, remaining);
-  if (!p->fused) { *nb_out = nbmax; *G_out = 1; return; }
+  if (!p->fused && !p->plane_f) { *nb_out = nbmax; *G_out = 1; return; }
   double best = -1.0; int bnb = nbmax, bG = 1;
   if (const char* e = getenv("QB200_PLANE_G")) { const int G = atoi(e); if (G >= 1) { *nb_out = nbmax; *G_out = std::min(std::min(G, maxG), nbmax); return; } }
   const int nbmin = (nbmax == remaining) ? nbmax : std::max(1, (3 * nbmax) / 4);   // the last batch takes what is left
@@ -580,6 +580,24 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     d.exp = 0;
     if (const char* e = getenv("QB200_EXP")) d.exp = atoi(e);      // timing experiments only: results are wrong when set
   }
+  // 16-bit positions in a buffer that holds the kept rows only (pitch tp): per column its (kept row, digit-reversed x), and the
+  // positions inside the non-zero x range [0,xs) + [xs+xk,np0) of a kept row that no column covers (they must read as zero)
+  auto build_kept_row_tables = [&](int tp, int xs, int xk) -> int {
+    std::vector<unsigned short> tpos(d.nvec), tzero;
+    std::vector<char> covered((size_t)d.nkeep * tp, 0);
+    for (int iv = 0; iv < d.nvec; iv++) {
+      const int hp = colhk[iv] % np0, kp = colhk[iv] / np0, jr = kp < d.ksplit ? kp : kp - d.kskip;
+      tpos[iv] = (unsigned short)(jr * tp + xpos[hp]);
+      covered[tpos[iv]] = 1;
+    }
+    for (int jr = 0; jr < d.nkeep; jr++)
+      for (int hp = 0; hp < np0; hp++)
+        if ((hp < xs || hp >= xs + xk) && !covered[(size_t)jr * tp + xpos[hp]]) tzero.push_back((unsigned short)(jr * tp + xpos[hp]));
+    d.ntzero = (int)tzero.size();
+    int r;
+    if ((r = upload(p, tpos, &d.tpos)) || (r = upload(p, tzero, &d.tzero))) return r;
+    return QB200_OK;
+  };
   p->static_shape = 0;
   if (p->fused) {
     int hmax = 0;
@@ -612,21 +630,20 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     // tensor-memory kernel of the compiled shape: positions in a buffer that holds the kept rows only
     p->plane_t = false;
     if (plane_t_wanted(p) && d.nvec <= 65535) {
-      const int tp = plane_t_pitch();
       int xs, xk;
       plane_t_xrange(&xs, &xk);
-      std::vector<unsigned short> tpos(d.nvec), tzero;
-      std::vector<char> covered((size_t)d.nkeep * tp, 0);
-      for (int iv = 0; iv < d.nvec; iv++) {
-        const int hp = colhk[iv] % np0, kp = colhk[iv] / np0, jr = kp < d.ksplit ? kp : kp - d.kskip;
-        tpos[iv] = (unsigned short)(jr * tp + xpos[hp]);
-        covered[tpos[iv]] = 1;
-      }
-      for (int jr = 0; jr < d.nkeep; jr++)
-        for (int hp = 0; hp < np0; hp++)
-          if ((hp < xs || hp >= xs + xk) && !covered[(size_t)jr * tp + xpos[hp]]) tzero.push_back((unsigned short)(jr * tp + xpos[hp]));
-      d.ntzero = (int)tzero.size();
-      if ((rc = upload(p, tpos, &d.tpos)) || (rc = upload(p, tzero, &d.tzero)) || (rc = plane_t_setup(p))) { qb200_plan_destroy(p); return rc; }
+      if ((rc = build_kept_row_tables(plane_t_pitch(), xs, xk)) || (rc = plane_t_setup(p))) { qb200_plan_destroy(p); return rc; }
+    }
+  }
+  // planes whose kept rows fit shared memory once (si54p 126 x 126): the whole xy stage in one kernel (k_plane_f)
+  p->plane_f = false;
+  if (!p->fused) {
+    int hmax = 0;
+    for (int r = 0; r < nrods; r++) hmax = std::max(hmax, std::abs(rod_h[r]));
+    if (plane_f_wanted(p, hmax)) {
+      int xs, xk;
+      plane_f_xrange(&xs, &xk);
+      if ((rc = build_kept_row_tables(plane_f_pitch(), xs, xk)) || (rc = plane_f_setup(p))) { qb200_plan_destroy(p); return rc; }
     }
   }
   // fused path: batches of up to ~1100 MgO216 states -- whole blocks go through in one batch, so the persistent CTAs of
@@ -696,6 +713,7 @@ extern "C" long long qb200_plan_query(const qb200_plan* p, int what)
     case 17: return p->plane_t ? 1 : 0;
     case 18: return p->zcol_t ? 1 : 0;
     case 19: return p->ycols_t;
+    case 20: return p->plane_f ? 1 : 0;
     case 12: return p->d.zb_cb;
     case 13: return p->d.zf_cb;
     default: return -1;
@@ -811,6 +829,16 @@ static int launch_xy(qb200_plan* p, int nunits, const double* v, double* f, cons
     if (OP == OP_DENSITY) prof_begin(8, p->stream);      // (category 8: the density launches of category 1)
     prof_begin(1, p->stream);
     const int rc = launch_plane(p, OP, g, v, f, fac, nunits, zero_imag);
+    prof_end(p->stream);
+    if (rc) return rc;
+    p->launches++;
+    return QB200_OK;
+  }
+  if (p->plane_f && !zero_imag && (OP == OP_HPSI || OP == OP_DENSITY)) {
+    dim3 g(d.np2, std::max(1, std::min(ngroups, nunits)));
+    if (OP == OP_DENSITY) prof_begin(8, p->stream);
+    prof_begin(1, p->stream);
+    const int rc = launch_plane_f(p, OP, g, v, fac, nunits);
     prof_end(p->stream);
     if (rc) return rc;
     p->launches++;
@@ -1034,7 +1062,7 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
     if ((rc = ensure_work(p, nb))) return rc;
     if (upload_c) QB_CUDA(cudaStreamWaitEvent(p->stream, p->evs[1 + ib], 0));
     if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
-    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, p->fused ? G : 1, 0))) return rc;
+    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, (p->fused || p->plane_f) ? G : 1, 0))) return rc;
     b0 += nb;
   }
   prof_begin(6, p->stream);

@@ -204,6 +204,185 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
   if (warp == 0) tmem_dealloc512(tbase);
 }
 
+// ------------------------------------------------------------------------------------------------ fused plane kernel, 126 x 126
+// k_plane_f<OP, FS>: the WHOLE xy stage of a 126 x 126 plane (si54p) in one kernel, with no intermediate in HBM: the plane
+// (254 KB) does not fit shared memory, its kept rows do (58 x 127 x 16 B = 118 KB), and the y direction needs no more than
+// that because its columns live in tensor memory (the passes of k_ycols_t, reading the kept rows from shared memory instead
+// of `w`).  Per unit: TMA bulk copy of the plane row (one unit ahead) -> scatter -> pruned x-DIT (compiled passes of
+// plane_static.cuh, all 16 warps) -> y round trip in TMEM (all 16 warps, four per lane quarter) -> pruned x-DIF -> gather.
+// Single-buffered: the two directions alternate (k_plane_t overlaps them on two buffers; 2 x 118 KB do not fit).
+// grid (np2, G) persistent over the units gy, gy+G, ...; block 512.
+template <int NP0_, int NP1_, int XSPLIT_, int YSPLIT_> struct FShape {
+  static constexpr int NP0 = NP0_, NP1 = NP1_, XSPLIT = XSPLIT_, XSKIP = NP0_ - 2 * XSPLIT_, YSPLIT = YSPLIT_, YSKIP = NP1_ - 2 * YSPLIT_;
+  static constexpr int NKEEP = 2 * YSPLIT_, PITCH = NP0_ | 1;
+  static_assert(NP1_ == 126 && NP0_ <= 126, "thread-per-column y passes are written for 126 = 9 x 14, one plane per 128 TMEM lanes");
+};
+typedef FShape<126, 126, 29, 29> FsSi54p;
+
+template <class FS> QB200_HD constexpr size_t plane_f_smem(int nvec, int nzero)
+{
+  constexpr FftDesc FX = make_fft_desc(FS::NP0);
+  return (size_t)((FX.twsize + 7) & ~7) * 16 + (size_t)FS::NKEEP * FS::PITCH * 16 + (size_t)((nvec + 7) & ~7) * 16 +
+         (size_t)((nvec + 7) & ~7) * 2 + (size_t)((nzero + 7) & ~7) * 2;
+}
+
+template <int OP, class FS>
+__global__ void __launch_bounds__(512, 1) k_plane_f(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
+                                                    double* __restrict__ rho_part, const double* __restrict__ fac, int nunits)
+{
+  static_assert(OP == OP_HPSI || OP == OP_DENSITY, "k_plane_f: H psi and density only");
+  constexpr FftDesc FX = make_fft_desc(FS::NP0);
+  constexpr int np0 = FS::NP0, np1 = FS::NP1, np01 = np0 * np1, pitch = FS::PITCH, NK = FS::NKEEP, NT = 512;
+  constexpr unsigned MASK = zmask(9, 14, FS::YSPLIT, FS::YSKIP);
+  constexpr int MW = 4;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar;
+  const int nvec = P.nvec, nvp = (nvec + 7) & ~7, nzero = P.ntzero;
+  cplx* tw0 = reinterpret_cast<cplx*>(smraw);
+  cplx* A = tw0 + ((FX.twsize + 7) & ~7);
+  cplx* stg = A + NK * pitch;
+  unsigned short* tpos = reinterpret_cast<unsigned short*>(stg + nvp);
+  unsigned short* tzero = tpos + nvp;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int z = blockIdx.x, G = gridDim.y;
+  const size_t N = (size_t)np01 * P.np2;
+  if (warp == 0) tmem_alloc512(&tmem_slot);
+  if (tid == 32) mbar_init(&mbar, 1);
+  for (int i = tid; i < FX.twsize; i += NT) tw0[i] = P.tw0p[i];
+  for (int i = tid; i < nvec; i += NT) tpos[i] = P.tpos[i];
+  for (int i = tid; i < nzero; i += NT) tzero[i] = P.tzero[i];
+  for (int i = tid; i < NK * pitch; i += NT) A[i] = make_double2(0.0, 0.0);
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const int q = warp & 3, m = warp >> 2;
+  const uint32_t t0 = tbase + ((uint32_t)(q * 32) << 16);
+  const int blo = (14 * m) / MW, bhi = (14 * (m + 1)) / MW, klo = (9 * m) / MW, khi = (9 * (m + 1)) / MW;
+  const int cl = 32 * q + lane;
+  const bool act = cl < np0;
+  const int xc = min(cl, np0 - 1);
+  const double* vz = v + (size_t)z * np01 + xc;
+  double* rz = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + xc;
+  cplx* Ax = A + xc;
+  auto csync = []() { __syncthreads(); };
+  auto next_unit = [&](int u) {
+    u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    return u;
+  };
+  const uint32_t row_bytes = (uint32_t)nvec * 16u;
+  uint32_t sphase = 0;
+  int unit = next_unit((int)blockIdx.y - G);
+  if (tid == 0 && unit < nunits) {
+    mbar_expect_tx(&mbar, row_bytes);
+    bulk_g2s(stg, zt + ((size_t)unit * P.np2 + z) * nvec, row_bytes, &mbar);
+  }
+  for (; unit < nunits;) {
+    const int nxt = next_unit(unit);
+    double facu = 0.0;
+    if (OP == OP_DENSITY) facu = fac[unit];
+    cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
+    mbar_wait(&mbar, sphase);
+    sphase ^= 1u;
+    __syncthreads();                               // everybody has left the previous unit (kept rows, TMEM slots)
+    for (int j = tid; j < nzero; j += NT) A[tzero[j]] = make_double2(0.0, 0.0);
+    for (int j = tid; j < nvec; j += NT) A[tpos[j]] = stg[j];
+    __syncthreads();
+    if (tid == 0 && nxt < nunits) {
+      mbar_expect_tx(&mbar, row_bytes);
+      bulk_g2s(stg, zt + ((size_t)nxt * P.np2 + z) * nvec, row_bytes, &mbar);
+    }
+    // x direction: kept rows, digit-reversed (zeros outside the sphere's h range) -> natural
+    dit_s<+1, np0, 1, NK, DenseRowsW<pitch>, FS::XSPLIT, FS::XSKIP, true, false, FX.nf - 1>(tid, NT, A, tw0, csync);
+    __syncthreads();
+    // y pass 1: 9-point transforms over a of the kept rows y = 14a + b, twiddle -> slots (b, .)
+#pragma unroll 1
+    for (int b = blo; b < bhi; b++) {
+      cplx xin[9];
+#pragma unroll
+      for (int a = 0; a < 9; a++) {
+        const int c = zclass(a, 14, FS::YSPLIT, FS::YSKIP);
+        if (c == 0) continue;
+        const int yp = 14 * a + b;
+        const bool kept = c == 1 || yp < FS::YSPLIT || yp >= FS::YSPLIT + FS::YSKIP;
+        const int jr = (14 * a + 13 < FS::YSPLIT) ? yp : ((14 * a >= FS::YSPLIT + FS::YSKIP) ? yp - FS::YSKIP : (yp < FS::YSPLIT ? yp : yp - FS::YSKIP));
+        xin[a] = kept ? Ax[jr * pitch] : make_double2(0.0, 0.0);
+      }
+      DftM<9, +1, MASK>::run(xin);
+      if (b != 0) {
+#pragma unroll
+        for (int k1 = 1; k1 < 9; k1++) { const double2 tw = c_w126[9 * b + k1]; xin[k1] = cmul_s<+1>(xin[k1], tw.x, tw.y); }
+      }
+      Tmem<8>::st(t0 + 36 * b, xin);
+      Tmem<1>::st(t0 + 36 * b + 32, xin + 8);
+    }
+    tmem_wait_st();
+    tmem_fence_before();
+    bar_sync_n(1 + q, 32 * MW);
+    tmem_fence_after();
+    // y pass 2: 14-point transforms over b -> psi(x, y = k1 + 9 k2, z); pointwise work; way back
+#pragma unroll 1
+    for (int k1 = klo; k1 < khi; k1++) {
+      cplx t[14];
+      Tmem<1, 14>::ld(t, t0 + 4 * k1, 36);
+      Dft<14, +1>::run(t);
+      if (OP == OP_HPSI) {
+#pragma unroll
+        for (int k2 = 0; k2 < 14; k2++) {
+          const double vv = __ldg(vz + (size_t)(k1 + 9 * k2) * np0);
+          t[k2].x *= vv;
+          t[k2].y *= vv;
+        }
+        Dft<14, -1>::run(t);
+#pragma unroll
+        for (int b = 1; b < 14; b++) { const double2 tw = c_w126[9 * b + k1]; t[b] = cmul_s<-1>(t[b], tw.x, tw.y); }
+        Tmem<1, 14>::st(t0 + 4 * k1, t, 36);
+      } else if (act) {
+#pragma unroll
+        for (int k2 = 0; k2 < 14; k2++) {
+          const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
+          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)(k1 + 9 * k2) * np0), "d"(val) : "memory");
+        }
+      }
+    }
+    if (OP == OP_HPSI) {
+      tmem_wait_st();
+      tmem_fence_before();
+      bar_sync_n(1 + q, 32 * MW);
+      tmem_fence_after();
+      // y pass 3: 9-point transforms over k1 -> the kept rows y = 14a + b
+#pragma unroll 1
+      for (int b = blo; b < bhi; b++) {
+        cplx xo[9];
+        Tmem<8>::ld(xo, t0 + 36 * b);
+        Tmem<1>::ld(xo + 8, t0 + 36 * b + 32);
+        Dft<9, -1>::run(xo);
+        if (act) {
+#pragma unroll
+          for (int a = 0; a < 9; a++) {
+            const int c = zclass(a, 14, FS::YSPLIT, FS::YSKIP);
+            if (c == 0) continue;
+            const int yp = 14 * a + b;
+            const bool kept = c == 1 || yp < FS::YSPLIT || yp >= FS::YSPLIT + FS::YSKIP;
+            const int jr = (14 * a + 13 < FS::YSPLIT) ? yp : ((14 * a >= FS::YSPLIT + FS::YSKIP) ? yp - FS::YSKIP : (yp < FS::YSPLIT ? yp : yp - FS::YSKIP));
+            if (kept) Ax[jr * pitch] = xo[a];
+          }
+        }
+      }
+      __syncthreads();
+      dif_s<-1, np0, 1, NK, DenseRowsW<pitch>, FS::XSPLIT, FS::XSKIP, false, true, 0, FX.nf - 1>(tid, NT, A, tw0, csync);
+      __syncthreads();
+      for (int j = tid; j < nvec; j += NT) ztrow[j] = A[tpos[j]];
+    }
+    unit = nxt;
+  }
+  tmem_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc512(tbase);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int ycols_t_shape(const qb200_plan* p)
 {
@@ -235,6 +414,37 @@ int ycols_t_setup(qb200_plan* p)
   QB_CUDA(cudaFuncSetAttribute(k_ycols_t<OP_DENSITY, YtSi54p>, cudaFuncAttributeMaxDynamicSharedMemorySize, YtSi54p::NP1 * YtSi54p::COLS * 8));
   QB_CUDA(cudaFuncSetAttribute(k_ycols_t<OP_DENSITY, YtAu992>, cudaFuncAttributeMaxDynamicSharedMemorySize, YtAu992::NP1 * YtAu992::COLS * 8));
   p->ycols_t = shape;
+  return QB200_OK;
+}
+
+// fused 126 x 126 plane kernel (k_plane_f): QB200_PLANE_F=0 keeps the split path
+bool plane_f_wanted(const qb200_plan* p, int hmax)
+{
+  if (const char* e = getenv("QB200_PLANE_F")) if (e[0] == '0') return false;
+  if (const char* e = getenv("QB200_NO_STATIC")) if (e[0] == '1') return false;
+  if (const char* e = getenv("QB200_FORCE_SPLIT")) if (e[0] == '1') return false;
+  const DevPlan& d = p->d;
+  typedef FsSi54p F;
+  return !p->fused && d.np0 == F::NP0 && d.np1 == F::NP1 && d.ksplit == F::YSPLIT && d.nkeep == F::NKEEP && hmax < F::XSPLIT && d.nvec <= 65535;
+}
+int plane_f_pitch() { return FsSi54p::PITCH; }
+void plane_f_xrange(int* xsplit, int* xskip) { *xsplit = FsSi54p::XSPLIT; *xskip = FsSi54p::XSKIP; }
+int plane_f_setup(qb200_plan* p)
+{
+  p->plane_f = false;
+  p->smem_plane_f = plane_f_smem<FsSi54p>(p->d.nvec, p->d.ntzero);
+  if (p->smem_plane_f + 64 > (size_t)p->max_smem || !p->ycols_t) return QB200_OK;      // (the constants are set by ycols_t_setup)
+  QB_CUDA((cudaFuncSetAttribute(k_plane_f<OP_HPSI, FsSi54p>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_f)));
+  QB_CUDA((cudaFuncSetAttribute(k_plane_f<OP_DENSITY, FsSi54p>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_f)));
+  p->plane_f = true;
+  return QB200_OK;
+}
+int launch_plane_f(qb200_plan* p, int op, dim3 grid, const double* v, const double* fac, int nunits)
+{
+  if (op == OP_HPSI) k_plane_f<OP_HPSI, FsSi54p><<<grid, 512, p->smem_plane_f, p->stream>>>(p->d, (cplx*)p->zt, v, p->rho_part, fac, nunits);
+  else k_plane_f<OP_DENSITY, FsSi54p><<<grid, 512, p->smem_plane_f, p->stream>>>(p->d, (cplx*)p->zt, v, p->rho_part, fac, nunits);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_plane_f launch", __FILE__, __LINE__);
   return QB200_OK;
 }
 

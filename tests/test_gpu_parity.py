@@ -365,7 +365,7 @@ def test_properties_au992_full_size_split_path(monkeypatch):
     assert relerr(res["static"][1], res["generic"][1]) < 1e-12
 
 
-@pytest.mark.parametrize("compiled", [True, "smem", False])
+@pytest.mark.parametrize("compiled", [True, "ycols", "smem", False])
 def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     """examples/si54p as a Gamma-point real-wavefunction case (fcc-type cell 2 x 15.525, 65 Ry, 126^3 grid,
     ngw 33114): planes of 126 x 127 x 16 B exceed shared memory, so this runs the real-basis pair path (+ odd tail)
@@ -375,6 +375,8 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
         monkeypatch.setenv("QB200_NO_STATIC", "1")
     if compiled == "smem":      # the compiled shape with the shared-memory y stage (k_ycols2) instead of the tensor-memory one
         monkeypatch.setenv("QB200_YCOLS_T", "0")
+    if compiled == "ycols":     # the split path with the tensor-memory y stage (k_ycols_t) instead of the one-kernel xy stage (k_plane_f)
+        monkeypatch.setenv("QB200_PLANE_F", "0")
     a = 15.525
     cell, ecut = (0, a, a, a, 0, a, a, a, 0), 32.5
     b = P.make_basis(cell, ecut, (0, 0, 0), False)
@@ -387,7 +389,8 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     oft = P.FT(b, *grid)
     ft = H.FourierTransform(b, *grid)
     assert not ft.fused() and ft.query(14) == 1 and ft.query(11) == 1 and ft.query(15) == (2 if compiled else 0)
-    assert ft.query(19) == (1 if compiled is True else 0), "y stage: k_ycols_t (column in tensor memory) only for the compiled shape"
+    assert ft.query(19) == (1 if compiled in (True, "ycols") else 0), "y stage: k_ycols_t (column in tensor memory) only for the compiled shape"
+    assert ft.query(20) == (1 if compiled is True else 0), "xy stage in one kernel (k_plane_f) for the compiled 126 x 126 shape"
     want = oft.rs_mul_add(c, v, np.zeros_like(c))
     P.kinetic_add(b["kpg2"], c, want)
     got = _dev(np.zeros_like(c))
