@@ -47,6 +47,41 @@ template <class SH> QB200_HD constexpr size_t plane_t_smem(int nvec, int nzero)
 
 enum { BAR_X = 1, BAR_FULL = 2, BAR_DONE = 4, BAR_PAIR = 6 };
 
+// Good-Thomas (prime-factor) index maps of the thread-per-column y passes of k_plane_t: 16 and 7 are coprime, so with
+//   y = (7a + 16b) mod 112,  k = (49 k1 + 64 k2) mod 112      (49 = 7 * (7^-1 mod 16), 64 = 16 * (16^-1 mod 7))
+// W_112^{y k} = W_16^{a k1} W_7^{b k2} exactly: a 16 x 7 two-dimensional transform with NO twiddle factors between the passes
+// (the Cooley-Tukey maps y = 7a + b, k = k1 + 16 k2 cost 105 + 96 complex multiplications and their table fetches per column
+// and round trip).  Residue class b is a compile-time constant in passes 1 and 3, so the kept rows of a butterfly (its zero
+// inputs / unused outputs) and their shared-memory offsets are constants too.
+template <class SH, int B> struct YGT {
+  static QB200_HD constexpr int y(int a) { return (7 * a + 16 * B) % 112; }
+  static QB200_HD constexpr bool kept(int a) { return y(a) < SH::YSPLIT || y(a) >= SH::YSPLIT + SH::YSKIP; }
+  static QB200_HD constexpr int row(int a) { return y(a) < SH::YSPLIT ? y(a) : y(a) - SH::YSKIP; }
+  static QB200_HD constexpr unsigned mask() { unsigned m = 0; for (int a = 0; a < 16; a++) if (kept(a)) m |= 1u << a; return m; }
+};
+// pass 1 of class B: kept rows y(a) of the column -> 16-point transform over a -> TMEM slots (B, k1)
+template <class SH, int B> __device__ __forceinline__ void y_pass1_gt(const cplx* __restrict__ Ax, uint32_t t0)
+{
+  typedef YGT<SH, B> M;
+  cplx x[16];
+#pragma unroll
+  for (int a = 0; a < 16; a++) if (M::kept(a)) x[a] = Ax[M::row(a) * SH::PITCH];
+  DftM<16, +1, M::mask()>::run(x);
+  Tmem<16>::st(t0 + 64 * B, x);
+}
+// pass 3 of class B: slots (B, k1) -> 16-point transform over k1 -> the kept rows y(a)
+template <class SH, int B> __device__ __forceinline__ void y_pass3_gt(cplx* __restrict__ Ax, uint32_t t0, bool act)
+{
+  typedef YGT<SH, B> M;
+  cplx x[16];
+  Tmem<16>::ld(x, t0 + 64 * B);
+  Dft<16, -1>::run(x);
+  if (act) {
+#pragma unroll
+    for (int a = 0; a < 16; a++) if (M::kept(a)) Ax[M::row(a) * SH::PITCH] = x[a];
+  }
+}
+
 template <int OP, class SH, int NYW, int NXW>
 __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_constant__ DevPlan P, cplx* __restrict__ zt, const double* __restrict__ v,
                                                                  double* __restrict__ rho_part, const double* __restrict__ fac, int nunits,
@@ -111,35 +146,22 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       double facu = 0.0;
       if (OP == OP_DENSITY) facu = fac[unit];
       bar_sync_n(BAR_FULL + (i & 1), NT);          // the X warps finished the x transform of this unit
-      // pass 1: for each residue b the 16-point transform over a of the kept rows y = 7a + b, twiddle, -> TMEM slots (b, .)
-#pragma unroll 1
-      for (int b = blo; b < bhi; b++) {
-        cplx x[16];
-#pragma unroll
-        for (int a = 0; a < 16; a++) {
-          const int c = zclass(a, 7, SH::YSPLIT, SH::YSKIP);
-          if (c == 0) continue;
-          const int y = 7 * a + b;
-          const int row = (7 * a + 6 < SH::YSPLIT) ? y : ((7 * a >= SH::YSPLIT + SH::YSKIP) ? y - SH::YSKIP : (y < SH::YSPLIT ? y : y - SH::YSKIP));
-          if (c == 1) x[a] = A[row * pitch];
-          else x[a] = (y < SH::YSPLIT || y >= SH::YSPLIT + SH::YSKIP) ? A[row * pitch] : make_double2(0.0, 0.0);
-        }
-        DftM<16, +1, MASK>::run(x);
-        if (b != 0) {
-#pragma unroll
-          for (int k1 = 1; k1 < 16; k1++) { const double2 w = c_ytw[16 * b + k1]; x[k1] = cmul_s<+1>(x[k1], w.x, w.y); }
-        }
-        Tmem<16>::st(t0 + 64 * b, x);
-      }
+      // pass 1: for each residue class b the 16-point transform over a of the kept rows y = (7a + 16b) mod 112 -> TMEM slots (b, .)
+#define QB200_Y1(B) if (B >= blo && B < bhi) y_pass1_gt<SH, B>(A, t0);
+      QB200_Y1(0) QB200_Y1(1) QB200_Y1(2) QB200_Y1(3) QB200_Y1(4) QB200_Y1(5) QB200_Y1(6)
+#undef QB200_Y1
       tmem_wait_st();
       tmem_fence_before();
       bar_sync_n(BAR_PAIR + q, 32 * MW);
       tmem_fence_after();
       if (OP == OP_DENSITY) bar_arrive_n(BAR_DONE + (i & 1), NT);   // the kept rows are consumed: the buffer is free again
-      // pass 2: for each k1 the 7-point transform over b -> psi(x, y = k1 + 16 k2, z); pointwise work; way back to slots (., k1)
-      // (H psi: v(r) of the NEXT k1 is loaded while the current one is transformed; the loop is unrolled by two with the two
-      //  register sets swapping roles, so the prefetch costs no register moves)
-      const double* vp = vz + (size_t)klo * np0;
+      // pass 2: for each k1 the 7-point transform over b -> psi(x, y, z) at y = (49 k1 + 64 k2) mod 112; pointwise work; way back
+      // to slots (., k1).  (H psi: v(r) of the NEXT k1 is loaded while the current one is transformed; the loop is unrolled by two
+      // with the two register sets swapping roles, so the prefetch costs no register moves)
+      auto yrow = [](int k1, int k2) {               // warp-uniform: (49 k1 + 64 k2) mod 112
+        int k = (49 * k1) % 112 + (64 * k2) % 112;
+        return k >= 112 ? k - 112 : k;
+      };
       auto pass2 = [&](int k1, const double (&vv)[7]) {
         cplx t[7];
         Tmem<1, 7>::ld(t, t0 + 4 * k1, 64);
@@ -149,8 +171,6 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
 #pragma unroll
           for (int k2 = 0; k2 < 7; k2++) { t[k2].x *= vv[k2]; t[k2].y *= vv[k2]; }
           Dft<7, -1>::run(t);
-#pragma unroll
-          for (int b = 1; b < 7; b++) { const double2 w = c_ytw[16 * b + k1]; t[b] = cmul_s<-1>(t[b], w.x, w.y); }
           Tmem<1, 7>::st2(t0 + 4 * k1, t, 64);
         } else {
           // fire-and-forget reductions at the L2, one owner per address (CTA (z, gy) owns plane z of partial gy), applied in
@@ -159,27 +179,25 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
 #pragma unroll
             for (int k2 = 0; k2 < 7; k2++) {
               const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
-              asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)(k1 + 16 * k2) * np0), "d"(val) : "memory");
+              asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)yrow(k1, k2) * np0), "d"(val) : "memory");
             }
           }
         }
       };
-      auto loadv = [&](double (&vv)[7]) {
+      auto loadv = [&](int k1, double (&vv)[7]) {
         if (OP == OP_HPSI) {
 #pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) vv[k2] = __ldg(vp + (size_t)(16 * k2) * np0);
+          for (int k2 = 0; k2 < 7; k2++) vv[k2] = __ldg(vz + (size_t)yrow(k1, k2) * np0);
         }
       };
       double va[7], vb[7];
-      loadv(va);
+      loadv(klo, va);
 #pragma unroll 1
       for (int k1 = klo; k1 < khi; k1 += 2) {
-        if (k1 + 1 < khi) vp += np0;                // (the last iteration re-reads its own row: no branch around the loads)
-        loadv(vb);
+        loadv(min(k1 + 1, khi - 1), vb);           // (the last iteration re-reads its own rows: no branch around the loads)
         pass2(k1, va);
         if (k1 + 1 < khi) {
-          if (k1 + 2 < khi) vp += np0;
-          loadv(va);
+          loadv(min(k1 + 2, khi - 1), va);
           pass2(k1 + 1, vb);
         }
       }
@@ -188,24 +206,10 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
         tmem_fence_before();
         bar_sync_n(BAR_PAIR + q, 32 * MW);
         tmem_fence_after();
-        // pass 3: for each b the 16-point transform over k1 -> the kept rows y = 7a + b
-#pragma unroll 1
-        for (int b = blo; b < bhi; b++) {
-          cplx x[16];
-          Tmem<16>::ld(x, t0 + 64 * b);
-          Dft<16, -1>::run(x);
-          if (act) {
-#pragma unroll
-            for (int a = 0; a < 16; a++) {
-              const int c = zclass(a, 7, SH::YSPLIT, SH::YSKIP);
-              if (c == 0) continue;
-              const int y = 7 * a + b;
-              const int row = (7 * a + 6 < SH::YSPLIT) ? y : ((7 * a >= SH::YSPLIT + SH::YSKIP) ? y - SH::YSKIP : (y < SH::YSPLIT ? y : y - SH::YSKIP));
-              if (c == 1) A[row * pitch] = x[a];
-              else if (y < SH::YSPLIT || y >= SH::YSPLIT + SH::YSKIP) A[row * pitch] = x[a];
-            }
-          }
-        }
+        // pass 3: for each residue class b the 16-point transform over k1 -> the kept rows y = (7a + 16b) mod 112
+#define QB200_Y3(B) if (B >= blo && B < bhi) y_pass3_gt<SH, B>(A0 + (i & 1) * ABUF + xc, t0, act);
+        QB200_Y3(0) QB200_Y3(1) QB200_Y3(2) QB200_Y3(3) QB200_Y3(4) QB200_Y3(5) QB200_Y3(6)
+#undef QB200_Y3
         __threadfence_block();
         bar_arrive_n(BAR_DONE + (i & 1), NT);      // the X warps may take the buffer for the way back
       }
