@@ -91,6 +91,9 @@ int plane_t_setup(qb200_plan* p)
       tw[2 * (16 * b + k1) + 1] = (double)sinl(twopi * e / T::NP1);
     }
   QB_CUDA(cudaMemcpyToSymbol(c_ytw, tw, sizeof(tw)));
+  int yrow[16 * 8] = { 0 };
+  for (int k1 = 0; k1 < 16; k1++) for (int k2 = 0; k2 < 7; k2++) yrow[8 * k1 + k2] = ((49 * k1 + 64 * k2) % T::NP1) * T::NP0;
+  QB_CUDA(cudaMemcpyToSymbol(c_yrow, yrow, sizeof(yrow)));
 #define QB200_T_OPTIN_H(i, ny, nx) QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_HPSI, ShapeMgO216t, ny, nx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
 #define QB200_T_OPTIN_D(i, ny, nx) QB_CUDA(cudaFuncSetAttribute(k_plane_t<OP_DENSITY, ShapeMgO216t, ny, nx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_plane_t));
   QB200_T_HPSI_LIST(QB200_T_OPTIN_H)

@@ -33,6 +33,8 @@ namespace qb200 {
 
 // c_ytw[16 b + k1] = W_112^{b k1} (cos, sin), filled by plane_t_setup (plane.cu)
 __constant__ double2 c_ytw[7 * 16];
+// c_yrow[8 k1 + k2] = (49 k1 + 64 k2) mod 112: the row of output (k1, k2) of the Good-Thomas passes (below), times np0
+__constant__ int c_yrow[16 * 8];
 
 // dynamic shared memory of k_plane_t (bytes); the same rule on the host (plane.cu)
 template <class SH> QB200_HD constexpr size_t plane_t_smem(int nvec, int nzero)
@@ -158,10 +160,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       // pass 2: for each k1 the 7-point transform over b -> psi(x, y, z) at y = (49 k1 + 64 k2) mod 112; pointwise work; way back
       // to slots (., k1).  (H psi: v(r) of the NEXT k1 is loaded while the current one is transformed; the loop is unrolled by two
       // with the two register sets swapping roles, so the prefetch costs no register moves)
-      auto yrow = [](int k1, int k2) {               // warp-uniform: (49 k1 + 64 k2) mod 112
-        int k = (49 * k1) % 112 + (64 * k2) % 112;
-        return k >= 112 ? k - 112 : k;
-      };
+      auto yrow = [](int k1, int k2) { return c_yrow[8 * k1 + k2]; };   // warp-uniform: ((49 k1 + 64 k2) mod 112) * np0
       auto pass2 = [&](int k1, const double (&vv)[7]) {
         cplx t[7];
         Tmem<1, 7>::ld(t, t0 + 4 * k1, 64);
@@ -179,7 +178,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
 #pragma unroll
             for (int k2 = 0; k2 < 7; k2++) {
               const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
-              asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)yrow(k1, k2) * np0), "d"(val) : "memory");
+              asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + yrow(k1, k2)), "d"(val) : "memory");
             }
           }
         }
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
       auto loadv = [&](int k1, double (&vv)[7]) {
         if (OP == OP_HPSI) {
 #pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) vv[k2] = __ldg(vz + (size_t)yrow(k1, k2) * np0);
+          for (int k2 = 0; k2 < 7; k2++) vv[k2] = __ldg(vz + yrow(k1, k2));
         }
       };
       double va[7], vb[7];
