@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(128) k_anl_gen(NlSpecies S, NlLattice L, int n
 }
 
 // one stage of the warp tile: acc[i][j] += A(32 x 32 reals) * B(32 x 32 reals)
-template <bool A_KMAJOR>
+// k4 steps [K4A, K4B) of one stage (the whole stage by default): the kernels run the first steps, then issue the copies of the
+// stage after next, then the rest -- right after the stage barrier the tensor pipe gets work at once instead of idling while
+// all 16 warps compute copy addresses (ncu: 11 % of the samples of k_fnl<1> sat behind that barrier)
+template <bool A_KMAJOR, int K4A = 0, int K4B = NL_KSTEP / 4>
 __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][4][2],
                                                int lane, int wm, int wn)
 {
@@ -165,7 +168,7 @@ __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, co
   const double* a0 = A_KMAJOR ? As + kq * NL_PITCH_KR + wm * 32 + r : As + (wm * 32 + r) * NL_PITCH + kq;
   const double* b0 = Bs + (wn * 32 + r) * NL_PITCH + kq;
 #pragma unroll
-  for (int k4 = 0; k4 < NL_KSTEP / 4; k4++) {
+  for (int k4 = K4A; k4 < K4B; k4++) {
     double a[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) a[i] = A_KMAJOR ? a0[k4 * 4 * NL_PITCH_KR + i * 8] : a0[i * 8 * NL_PITCH + k4 * 4];
@@ -221,11 +224,13 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict_
   for (int st = 0; st < nstage; st++) {
     nl_cp_wait_group<NL_NSTAGE - 2>();
     __syncthreads();                   // stage st has landed for everybody; everybody is done with stage st-1's buffer
-    issue(st + NL_NSTAGE - 1);
     const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_RK;
     // the last row tile is mostly padding when RW is not a multiple of 128 (MgO216: 540 rows, 28 of 128 in the fifth
     // tile): warps whose 32-row slab holds no row skip the tensor work, the others then own the pipe (warp-uniform test)
-    if (r0 + wm * 32 < RW && n0 + wn * 32 < nst) warp_mma_stage<false>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
+    const bool work = r0 + wm * 32 < RW && n0 + wn * 32 < nst;
+    if (work) warp_mma_stage<false, 0, 2>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
+    issue(st + NL_NSTAGE - 1);
+    if (work) warp_mma_stage<false, 2, NL_KSTEP / 4>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
   }
   const int ncols = IS_REAL ? nst : 2 * nst;
   const int r = lane >> 2, cq = lane & 3;
@@ -351,9 +356,10 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
   for (int st = 0; st < nstage; st++) {
     nl_cp_wait_group<NL_NSTAGE - 2>();
     __syncthreads();
-    issue(st + NL_NSTAGE - 1);
     const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_KR;
-    warp_mma_stage<true>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
+    warp_mma_stage<true, 0, 2>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
+    issue(st + NL_NSTAGE - 1);
+    warp_mma_stage<true, 2, NL_KSTEP / 4>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
   }
   const int r = lane >> 2, cq = lane & 3;
   if (IS_REAL == 2) {
