@@ -116,13 +116,16 @@ k_fnl3(const double* __restrict__ W3, size_t WP, int gbeg, int gcount, int kper,
   for (int st = 0; st < nstage; st++) {
     nl_cp_wait_group<NSTG - 2>();
     __syncthreads();
-    issue(st + NSTG - 1);
     const double* As = nl_smem + (st % NSTG) * C::STAGE;
     const double* a0 = As + ((wm * 2) * 24 + r) * N3_APITCH + kq;
     const double* b0 = As + C::ASTAGE + (wn * 32 + r) * N3_BPITCH + 2 * kq;
-    if (p0 + wm * 16 >= Mtot || n0 + wn * 32 >= nst) continue;       // warp tile entirely in the padding (warp-uniform)
+    const bool work = !(p0 + wm * 16 >= Mtot || n0 + wn * 32 >= nst);   // false: warp tile entirely in the padding (warp-uniform)
+    // the first step of the stage runs BEFORE the copies of the stage after next are issued: the tensor pipe gets work right
+    // after the barrier instead of idling while every warp computes copy addresses (cf. warp_mma_stage in nonlocal.cu)
 #pragma unroll
     for (int k4 = 0; k4 < N3_KS / 4; k4++) {
+      if (k4 == 1) issue(st + NSTG - 1);
+      if (!work) continue;
       double a[3][2];
 #pragma unroll
       for (int q = 0; q < 3; q++)
@@ -244,7 +247,6 @@ k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount,
   for (int st = 0; st < nstage; st++) {
     nl_cp_wait_group<NSTG - 2>();
     __syncthreads();
-    issue(st + NSTG - 1);
     const double* As = nl_smem + (st % NSTG) * C::STAGE;
     const double* a0 = As + kq * C::APITCH + wm * 16 + r;
     const double* b0 = As + C::ASTAGE + (wn * 32 + r) * N3_BK_BPITCH + kq;
@@ -252,6 +254,7 @@ k_back3(const double* __restrict__ W3, size_t WP, int RW3, int gbeg, int gcount,
     for (int q = 0; q < 3; q++)
 #pragma unroll
       for (int k4 = 0; k4 < 2; k4++) {
+        if (q == 0 && k4 == 1) issue(st + NSTG - 1);      // after the first step of the stage (see k_fnl3)
         double a[2], b[4];
 #pragma unroll
         for (int i = 0; i < 2; i++) a[i] = a0[(q * 8 + k4 * 4) * C::APITCH + i * 8];
