@@ -109,6 +109,11 @@ def test_cuda_mgo216_compiled_shape_and_generic_kernel(monkeypatch):
     del ft
     _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
     monkeypatch.delenv("QB200_PLANE_T")
+    # opt-in variants of k_plane_t: the density with its rho plane in shared memory (k_plane_td), the other warp geometries
+    for var, val in (("QB200_T_DENS_SMEM", "1"), ("QB200_T_DENS", "1"), ("QB200_T_HPSI", "1")):
+        monkeypatch.setenv(var, val)
+        _run_fixture("mgo216_shape_112cubed", True, False, monkeypatch)
+        monkeypatch.delenv(var)
     # the z-column kernels: tensor-memory form by default (k_zcol_bwd_t / k_zcol_fwd_t), the shared-memory tiles (v2) otherwise
     ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
     assert ft.query(18) == 1, "MgO216 plan did not select the tensor-memory z-column kernels"
