@@ -24,7 +24,7 @@ struct MidArgs {
   const double* v;      // v + z*np01 + c0          (OP_HPSI)
   double* rho;          // rho_part plane + c0      (OP_DENSITY)
   cplx* f;              // f plane + c0             (OP_BWD / OP_FWD)
-  double facu;
+  double facu, facv;    // weights of |Re psi|^2 and |Im psi|^2 (equal unless the unit is a pair of real states)
   int np0;
   int zero_imag;
   int exp;
@@ -76,7 +76,7 @@ __device__ __noinline__ void mid_pass(Grp g, cplx* base, int nlines, int estride
       } else if (OP == OP_DENSITY) {
         double* rp = a.rho + g0;
 #pragma unroll
-        for (int j = 0; j < R; j++) rp[j * ystep] = vv[j] + a.facu * (x[j].x * x[j].x + x[j].y * x[j].y);
+        for (int j = 0; j < R; j++) rp[j * ystep] = vv[j] + (a.facu * x[j].x * x[j].x + a.facv * x[j].y * x[j].y);
       } else if (OP == OP_BWD) {
         cplx* fp = a.f + g0;
 #pragma unroll
@@ -167,15 +167,15 @@ __global__ void __launch_bounds__(448, 1) k_plane2(const __grid_constant__ DevPl
   };
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   int unit = next_unit((int)blockIdx.y - G);
   if (per && unit < nunits) stage(unit);
   for (; unit < nunits;) {
     const int nxt = next_unit(unit);
-    double facu = 0.0;
-    if (OP == OP_DENSITY) facu = fac[unit];
+    double facu = 0.0, facv = 0.0;
+    if (OP == OP_DENSITY) { facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
     cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
     if (per) cp_async_wait_all();
     __syncthreads();   // tables / staged values visible; the previous unit's readers are done with the plane
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(448, 1) k_plane2(const __grid_constant__ DevPl
       a.v = v + (size_t)z * np01 + c0;
       a.rho = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + c0;
       a.f = f + (size_t)unit * N + (size_t)z * np01 + c0;
-      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag; a.exp = 0;
+      a.facu = facu; a.facv = facv; a.np0 = np0; a.zero_imag = zero_imag; a.exp = 0;
       mid_pass_any<OP>(rl, g, blk, nc, pitch, np1, yrev, a, nf == 1, keepy);
       if ((OP == OP_HPSI || OP == OP_FWD) && nf > 1) {
         g.sync();

@@ -198,12 +198,12 @@ __device__ __forceinline__ void mid_s(int tid, int nthr, cplx* blk, int nlines, 
         if (a.exp & 1) {          // timing experiment: no reductions (one dependent store keeps the arithmetic alive)
           double acc = 0.0;
 #pragma unroll
-          for (int j = 0; j < R; j++) acc += a.facu * (x[j].x * x[j].x + x[j].y * x[j].y);
+          for (int j = 0; j < R; j++) acc += a.facu * x[j].x * x[j].x + a.facv * x[j].y * x[j].y;
           if (acc == 1.2345e300) rp[0] = acc;
         } else
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          const double val = a.facu * (x[j].x * x[j].x + x[j].y * x[j].y);
+          const double val = a.facu * x[j].x * x[j].x + a.facv * x[j].y * x[j].y;
           asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rp + j * YSTEP), "d"(val) : "memory");
         }
       } else if (OP == OP_BWD) {
@@ -262,15 +262,15 @@ __global__ void __launch_bounds__(SH::NTHR, 1) k_plane_s(const __grid_constant__
   };
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   int unit = next_unit((int)blockIdx.y - G);
   if (per && unit < nunits) stage(unit);
   for (; unit < nunits;) {
     const int nxt = next_unit(unit);
-    double facu = 0.0;
-    if (OP == OP_DENSITY) facu = fac[unit];
+    double facu = 0.0, facv = 0.0;
+    if (OP == OP_DENSITY) { facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
     cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
     if (per) cp_async_wait_all();
     __syncthreads();
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(SH::NTHR, 1) k_plane_s(const __grid_constant__
       a.v = v + (size_t)z * np01 + c0;
       a.rho = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + c0;
       a.f = f + (size_t)unit * N + (size_t)z * np01 + c0;
-      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag; a.exp = P.exp;
+      a.facu = facu; a.facv = facv; a.np0 = np0; a.zero_imag = zero_imag; a.exp = P.exp;
       mid_s<OP, SH>(gtid, SH::GT, blk, nc, a);
       if constexpr ((OP == OP_HPSI || OP == OP_FWD) && FY.nf > 1) {
         gsync();
@@ -390,15 +390,15 @@ __global__ void __launch_bounds__(SH::NTHR, 1) k_plane_w(const __grid_constant__
   };
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   int unit = next_unit((int)blockIdx.y - G);
   if (per && unit < nunits) stage(unit);
   for (; unit < nunits;) {
     const int nxt = next_unit(unit);
-    double facu = 0.0;
-    if (OP == OP_DENSITY) facu = fac[unit];
+    double facu = 0.0, facv = 0.0;
+    if (OP == OP_DENSITY) { facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
     cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
     if (per) cp_async_wait_all();
     __syncthreads();                 // tables / every warp's staged values visible; the plane is free
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(SH::NTHR, 1) k_plane_w(const __grid_constant__
       a.v = v + (size_t)z * np01 + c0;
       a.rho = rho_part + (size_t)blockIdx.y * N + (size_t)z * np01 + c0;
       a.f = f + (size_t)unit * N + (size_t)z * np01 + c0;
-      a.facu = facu; a.np0 = np0; a.zero_imag = zero_imag; a.exp = 0;
+      a.facu = facu; a.facv = facv; a.np0 = np0; a.zero_imag = zero_imag; a.exp = 0;
       mid_s<OP, SH>(lane, 32, blk, QB200_BLOCK_LINES, a);
       if constexpr ((OP == OP_HPSI || OP == OP_FWD) && FY.nf > 1) {
         __syncwarp();

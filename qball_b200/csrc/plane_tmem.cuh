@@ -125,7 +125,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
 
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   const int first = next_unit((int)blockIdx.y - G);
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
     int i = 0;
     for (int unit = first; unit < nunits; unit = next_unit(unit), i++) {
       cplx* A = A0 + (i & 1) * ABUF + xc;
-      double facu = 0.0;
-      if (OP == OP_DENSITY) facu = fac[unit];
+      double facu = 0.0, facv = 0.0;
+      if (OP == OP_DENSITY) { facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
       bar_sync_n(BAR_FULL + (i & 1), NT);          // the X warps finished the x transform of this unit
       // pass 1: for each residue class b the 16-point transform over a of the kept rows y = (7a + 16b) mod 112 -> TMEM slots (b, .)
 #define QB200_Y1(B) if (B >= blo && B < bhi) y_pass1_gt<SH, B>(A, t0);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_t(const __grid_co
           if (act) {
 #pragma unroll
             for (int k2 = 0; k2 < 7; k2++) {
-              const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
+              const double val = facu * t[k2].x * t[k2].x + facv * t[k2].y * t[k2].y;
               asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + yrow(k1, k2)), "d"(val) : "memory");
             }
           }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_td(const __grid_c
   const uint32_t tbase = tmem_slot;
   auto next_unit = [&](int u) {
     u += G;
-    while (u < nunits && !(fac[u] > 0.0)) u += G;
+    while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   const int first = next_unit((int)blockIdx.y - G);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_td(const __grid_c
     const cplx* Ax = A + xc;
     double* ax = acc + xc;
     for (int unit = first; unit < nunits; unit = next_unit(unit)) {
-      const double facu = fac[unit];
+      const double facu = fac_first(fac, unit), facv = fac_second(P, fac, unit);
       bar_sync_n(BAR_FULL, NT);
 #pragma unroll 1
       for (int b = blo; b < bhi; b++) {
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__((NYW + NXW) * 32, 1) k_plane_td(const __grid_c
         Dft<7, +1>::run(t);
         if (act) {                                 // this thread owns (y = k1 + 16 k2, x) in every unit of the CTA
 #pragma unroll
-          for (int k2 = 0; k2 < 7; k2++) ax[(k1 + 16 * k2) * np0] += facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
+          for (int k2 = 0; k2 < 7; k2++) ax[(k1 + 16 * k2) * np0] += facu * t[k2].x * t[k2].x + facv * t[k2].y * t[k2].y;
         }
       }
       // (the other warps of the quarter finish their share of pass 2 before pass 1 of the next unit overwrites the slots)

@@ -54,9 +54,25 @@ struct DevPlan {
   const unsigned short *tpos;          // per column iv: (kept-row index)*pitch + digit-reversed x position
   const unsigned short *tzero;         // positions inside the non-zero x range of a kept row that no column covers
   int ntzero;
+  // density of Gamma-point REAL bases: a unit is a PAIR of states transformed as psi_1 + i psi_2 (SlaterDet.cc:858-899), whose
+  // weights are fac[unit] (real part) and fac[unit + fac2off] (imaginary part); 0: one state per unit, one weight
+  int fac2off;
 };
 
 enum { MODE_SINGLE = 0, MODE_PAIR = 1 };
+#ifdef __CUDACC__
+// weights of a density unit: only positive weights contribute (SlaterDet.cc:856, 905: states with zero occupation are skipped)
+__device__ __forceinline__ bool fac_active(const DevPlan& P, const double* __restrict__ fac, int u)
+{
+  return fac[u] > 0.0 || (P.fac2off && fac[u + P.fac2off] > 0.0);
+}
+__device__ __forceinline__ double fac_first(const double* __restrict__ fac, int u) { const double f = fac[u]; return f > 0.0 ? f : 0.0; }
+__device__ __forceinline__ double fac_second(const DevPlan& P, const double* __restrict__ fac, int u)
+{
+  const double f = fac[u + P.fac2off];          // fac2off == 0: the same weight for both parts (|psi|^2 of a complex state)
+  return f > 0.0 ? f : 0.0;
+}
+#endif
 enum { OP_HPSI = 0, OP_DENSITY = 1, OP_BWD = 2, OP_FWD = 3 };
 
 }  // namespace qb200
@@ -113,6 +129,7 @@ struct qb200_plan {
   size_t w_units;
   double* rho_part; size_t rho_part_elems;
   double* fac_dev; size_t fac_cap;
+  std::vector<double> fac_host;        // host weights regrouped for pair units before their one upload
   // staging for host-pointer calls
   double *st_c, *st_cp, *st_v, *st_f, *st_kpg2; size_t st_c_cap, st_cp_cap, st_v_cap, st_f_cap, st_kpg2_cap;
   long long launches;

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256, 2) k_ycols2(const __grid_constant__ DevPl
   const FastDiv dnx(nx);
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   auto issue = [&](int u) {
@@ -202,12 +202,12 @@ __global__ void __launch_bounds__(256, 2) k_ycols2(const __grid_constant__ DevPl
         tile[q * pitch + xl] = t;
       }
     } else if (OP == OP_DENSITY) {
-      const double facu = fac[unit];
+      const double facu = fac_first(fac, unit), facv = fac_second(P, fac, unit);
       for (int e = tid; e < np1 * nx; e += nthr) {
         int xl;
         const int q = dnx.div(e, xl);
         const cplx t = tile[q * pitch + xl];
-        acc[q * xb + xl] += facu * (t.x * t.x + t.y * t.y);     // same thread owns the same (q, xl) for every unit
+        acc[q * xb + xl] += facu * t.x * t.x + facv * t.y * t.y;     // same thread owns the same (q, xl) for every unit
       }
     } else if (OP == OP_BWD) {
       cplx* fz = f + (size_t)unit * N + (size_t)z * np01 + x0;

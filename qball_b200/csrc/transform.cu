@@ -1032,38 +1032,68 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   if ((rc = stage_in(p, rho, N, &p->st_v, &p->st_v_cap, &rd_c))) return rc;
   double* rd = const_cast<double*>(rd_c);
   if ((rc = ensure(&p->fac_dev, &p->fac_cap, nst))) return rc;
-  QB_CUDA(cudaMemcpyAsync(p->fac_dev, fac, nst * sizeof(double), cudaMemcpyDefault, p->stream));
-  // groups: exclusive owners of a partial density each; enough CTAs to fill the machine
+  // Real bases at Gamma: two states per transform, psi_1 + i psi_2 (the packing of FourierTransform.cc:555-581 that
+  // SlaterDet.cc:858-885 applies to the density: rho += fac1 Re^2 + fac2 Im^2), the odd last state alone (:886-903).
+  // fac_dev then holds [first weights | second weights | the odd state's weight].  QB200_DENSITY_PAIRS=0: one state per transform.
+  const bool pairs_on = !(getenv("QB200_DENSITY_PAIRS") && atoi(getenv("QB200_DENSITY_PAIRS")) == 0);
+  const int npair = (d.is_real && pairs_on) ? nst / 2 : 0;
+  if (npair && !is_device_ptr(fac)) {
+    p->fac_host.resize(nst);
+    for (int u = 0; u < npair; u++) { p->fac_host[u] = fac[2 * u]; p->fac_host[npair + u] = fac[2 * u + 1]; }
+    if (nst % 2) p->fac_host[2 * npair] = fac[nst - 1];
+    QB_CUDA(cudaMemcpyAsync(p->fac_dev, p->fac_host.data(), nst * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  } else if (npair) {
+    QB_CUDA(cudaMemcpy2DAsync(p->fac_dev, sizeof(double), fac, 2 * sizeof(double), sizeof(double), npair, cudaMemcpyDeviceToDevice, p->stream));
+    QB_CUDA(cudaMemcpy2DAsync(p->fac_dev + npair, sizeof(double), fac + 1, 2 * sizeof(double), sizeof(double), npair, cudaMemcpyDeviceToDevice, p->stream));
+    if (nst % 2) QB_CUDA(cudaMemcpyAsync(p->fac_dev + 2 * npair, fac + nst - 1, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+  } else {
+    QB_CUDA(cudaMemcpyAsync(p->fac_dev, fac, nst * sizeof(double), cudaMemcpyDefault, p->stream));
+  }
+  // batches of units (a unit = one state or one pair); groups: exclusive owners of a partial density each; enough CTAs to
+  // fill the machine
+  struct Batch { int state0, nunits, spu, facoff, G; };
+  std::vector<Batch> batches;
   const int maxG = 16;
-  int ngroups = 1, nbatches = 0;
-  for (int b0 = 0; b0 < nst;) { int nb, G; plan_split(p, nst - b0, maxG, &nb, &G); ngroups = std::max(ngroups, G); b0 += nb; nbatches++; }
+  int ngroups = 1;
+  auto add_batches = [&](int state0, int nunits, int spu, int facoff) {
+    for (int b0 = 0; b0 < nunits;) {
+      int nb, G;
+      plan_split(p, nunits - b0, maxG, &nb, &G);
+      ngroups = std::max(ngroups, G);
+      batches.push_back({state0 + b0 * spu, nb, spu, facoff + b0, G});
+      b0 += nb;
+    }
+  };
+  if (npair) {
+    add_batches(0, npair, 2, 0);
+    if (nst % 2) add_batches(nst - 1, 1, 1, 2 * npair);
+  } else {
+    add_batches(0, nst, 1, 0);
+  }
   if (upload_c) {
     cudaEvent_t ev;
     if ((rc = plan_event(p, 0, &ev))) return rc;
     QB_CUDA(cudaEventRecord(ev, p->stream));              // st_c may still be read by earlier work on the plan's stream
     QB_CUDA(cudaStreamWaitEvent(p->s_in, ev, 0));
-    int ib = 0;
-    for (int b0 = 0; b0 < nst; ib++) {
-      int nb, G;
-      plan_split(p, nst - b0, maxG, &nb, &G);
-      const size_t off = 2 * (size_t)b0 * ldc, cnt = 2 * (size_t)nb * ldc;
+    for (size_t ib = 0; ib < batches.size(); ib++) {
+      const Batch& b = batches[ib];
+      const size_t off = 2 * (size_t)b.state0 * ldc, cnt = 2 * (size_t)b.nunits * b.spu * ldc;
       QB_CUDA(cudaMemcpyAsync(p->st_c + off, c + off, cnt * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
-      if ((rc = plan_event(p, 1 + ib, &ev))) return rc;
+      if ((rc = plan_event(p, 1 + (int)ib, &ev))) return rc;
       QB_CUDA(cudaEventRecord(ev, p->s_in));
-      b0 += nb;
     }
   }
   if ((rc = ensure(&p->rho_part, &p->rho_part_elems, (size_t)ngroups * N))) return rc;
   QB_CUDA(cudaMemsetAsync(p->rho_part, 0, (size_t)ngroups * N * sizeof(double), p->stream));
-  int ib = 0;
-  for (int b0 = 0; b0 < nst; ib++) {
-    int nb, G;
-    plan_split(p, nst - b0, maxG, &nb, &G);
-    if ((rc = ensure_work(p, nb))) return rc;
+  for (size_t ib = 0; ib < batches.size(); ib++) {
+    const Batch& b = batches[ib];
+    if ((rc = ensure_work(p, b.nunits))) return rc;
     if (upload_c) QB_CUDA(cudaStreamWaitEvent(p->stream, p->evs[1 + ib], 0));
-    if ((rc = launch_zbwd(p, MODE_SINGLE, cd + 2 * (size_t)b0 * ldc, ldc, nb))) return rc;
-    if ((rc = launch_xy<OP_DENSITY>(p, nb, nullptr, nullptr, p->fac_dev + b0, (p->fused || p->plane_f) ? G : 1, 0))) return rc;
-    b0 += nb;
+    if ((rc = launch_zbwd(p, b.spu == 2 ? MODE_PAIR : MODE_SINGLE, cd + 2 * (size_t)b.state0 * ldc, ldc, b.nunits))) return rc;
+    p->d.fac2off = b.spu == 2 ? npair : 0;               // (the plan descriptor travels by value with each launch)
+    rc = launch_xy<OP_DENSITY>(p, b.nunits, nullptr, nullptr, p->fac_dev + b.facoff, (p->fused || p->plane_f) ? b.G : 1, 0);
+    p->d.fac2off = 0;
+    if (rc) return rc;
   }
   prof_begin(6, p->stream);
   k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256, 2) k_ycols(const __grid_constant__ DevPla
   const int u0 = blockIdx.z * units_per_group;
   const int u1 = min(u0 + units_per_group, nunits);
   for (int unit = u0; unit < u1; unit++) {
-    double facu = 0.0;
-    if (OP == OP_DENSITY) { facu = fac[unit]; if (!(facu > 0.0)) continue; }
+    double facu = 0.0, facv = 0.0;
+    if (OP == OP_DENSITY) { if (!fac_active(P, fac, unit)) continue; facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
     cplx* wz = w + ((size_t)unit * P.np2 + z) * P.nkeep * np0 + x0;
     __syncthreads();
     if (OP != OP_FWD) {
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256, 2) k_ycols(const __grid_constant__ DevPla
       for (int e = threadIdx.x; e < np1 * nx; e += blockDim.x) {
         const int xl = e % nx, y = e / nx;
         const cplx t = sm[y * xb + xl];
-        rz[(size_t)y * np0 + xl] += facu * (t.x * t.x + t.y * t.y);
+        rz[(size_t)y * np0 + xl] += facu * t.x * t.x + facv * t.y * t.y;
       }
     } else if (OP == OP_BWD) {
       cplx* fz = f + (size_t)unit * N + (size_t)z * np01 + x0;

@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
       __syncthreads();
     }
     for (int unit = 0; unit < nunits; unit++) {
-      double facu = 0.0;
-      if (OP == OP_DENSITY) { facu = fac[unit]; if (!(facu > 0.0)) continue; }
+      double facu = 0.0, facv = 0.0;
+      if (OP == OP_DENSITY) { if (!fac_active(P, fac, unit)) continue; facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
       cplx* wz = w + ((size_t)unit * P.np2 + z) * NK * np0 + xc;
       // the previous item's pass 3 (other warps of the quarter) is done with the TMEM slots
       tmem_fence_before();
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(512, 1) k_ycols_t(const __grid_constant__ DevP
 #pragma unroll
           for (int k2 = 0; k2 < 14; k2++) {
             const int k = k1 + 9 * k2, y = PAIR ? 2 * k + role : k;
-            acc[y * YS::COLS + cl] += facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);    // this thread owns (y, cl) in every unit
+            acc[y * YS::COLS + cl] += facu * t[k2].x * t[k2].x + facv * t[k2].y * t[k2].y;    // this thread owns (y, cl) in every unit
           }
         }
       }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(512, 1) k_plane_f(const __grid_constant__ DevP
   auto csync = []() { __syncthreads(); };
   auto next_unit = [&](int u) {
     u += G;
-    if (OP == OP_DENSITY) while (u < nunits && !(fac[u] > 0.0)) u += G;
+    if (OP == OP_DENSITY) while (u < nunits && !fac_active(P, fac, u)) u += G;
     return u;
   };
   const uint32_t row_bytes = (uint32_t)nvec * 16u;
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(512, 1) k_plane_f(const __grid_constant__ DevP
   }
   for (; unit < nunits;) {
     const int nxt = next_unit(unit);
-    double facu = 0.0;
-    if (OP == OP_DENSITY) facu = fac[unit];
+    double facu = 0.0, facv = 0.0;
+    if (OP == OP_DENSITY) { facu = fac_first(fac, unit); facv = fac_second(P, fac, unit); }
     cplx* ztrow = zt + ((size_t)unit * P.np2 + z) * nvec;
     mbar_wait(&mbar, sphase);
     sphase ^= 1u;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(512, 1) k_plane_f(const __grid_constant__ DevP
       } else if (act) {
 #pragma unroll
         for (int k2 = 0; k2 < 14; k2++) {
-          const double val = facu * (t[k2].x * t[k2].x + t[k2].y * t[k2].y);
+          const double val = facu * t[k2].x * t[k2].x + facv * t[k2].y * t[k2].y;
           asm volatile("red.global.add.f64 [%0], %1;" ::"l"(rz + (size_t)(k1 + 9 * k2) * np0), "d"(val) : "memory");
         }
       }

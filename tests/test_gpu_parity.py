@@ -409,6 +409,33 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     assert relerr(rho.cpu().numpy(), rho_want) < TOL
 
 
+@pytest.mark.parametrize("nst,host", [(9, False), (8, True), (1, False)])
+def test_cuda_density_of_real_states_in_pairs(nst, host, monkeypatch):
+    """Gamma-point real bases: the density transforms two states at once as psi_1 + i psi_2 and adds fac1 Re^2 + fac2 Im^2
+    (the form of SlaterDet.cc:858-885; the odd last state alone, :886-903).  Checked against the oracle's one-state-at-a-time
+    sum (SlaterDet.cc:906-924, the branch the reference runs) and against this library with QB200_DENSITY_PAIRS=0, with pairs
+    whose first, second or both weights are zero, several batches of pair units, device and host pointers."""
+    cell, ecut = (11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0
+    b = P.make_basis(cell, ecut, (0, 0, 0), False)
+    grid = P.density_grid(cell, ecut)
+    assert b["is_real"]
+    ldc = b["ngw"] + 2
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, True, seed=71)
+    occ = np.array([2.0, 0.0, 0.0, 1.5, 0.0, 0.0, 1.0, 2.0, 0.75])[:nst]
+    oft = P.FT(b, *grid)
+    rho_want = oft.compute_density(c, occ / b["omega"], np.full(oft.N, 0.5))
+    res = {}
+    for pairs in ("1", "0"):
+        monkeypatch.setenv("QB200_DENSITY_PAIRS", pairs)
+        ft = H.FourierTransform(b, *grid)
+        ft.set_workspace(2 * ft.nvec() * grid[2] * 16)   # two units per batch
+        rho = np.full(oft.N, 0.5) if host else _dev(np.full(oft.N, 0.5))
+        H.compute_density(ft, c if host else _dev(c), 1.0, occ, b["omega"], rho)
+        res[pairs] = rho if host else rho.cpu().numpy()
+        assert relerr(res[pairs], rho_want) < TOL
+    assert relerr(res["1"], res["0"]) < 1e-12
+
+
 @pytest.mark.parametrize("kpoint,host", [((0, 0, 0), False), ((0.25, 0, 0.5), True)])
 def test_cuda_update_density_tail_vs_oracle(kpoint, host):
     """ChargeDensity::update_density (ChargeDensity.cc:276-551, norm-conserving, one k-point): rho(r), the integral
