@@ -158,6 +158,31 @@ int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const doubl
 int qb200_nl_betapsi(qb200_nl* nl, int ldc, int nst, const double* c, double* betapsi);
 int qb200_nl_add_beta(qb200_nl* nl, int ldc, int nst, const double* f, double* cp);
 int qb200_nl_spsi(qb200_nl* nl, int ldc, int nst, const double* c, const double* qmat, double* spsi, double* betapsi);
+/* ---- Ultrasoft potentials, the rest: the ultrasoft branch of NonLocalPotential::energy
+ * (src/qball/NonLocalPotential.cc:1554-1752; forces :1754-1900 stay with the caller) and the augmentation charges of
+ * ChargeDensity::update_density (src/qball/ChargeDensity.cc:312-465).  Same object as above (betag tables per species).
+ * Further inputs, all produced by the reference's host setup like twnl / betag:
+ *   qb200_nl_us_set_density_basis: the density basis cdbasis_ / vbasis_ (complex at k = 0 for ultrasoft runs,
+ *       ChargeDensity.cc:75): ngv = localsize(), vkpgx = kpgx_ptr(0) (3*ngv, component-major).  Before set_species.
+ *   qb200_nl_us_set_species: species `is` (order of qb200_nl_add_species): nq = Species::nqtot() pairs of channels
+ *       lm1[q] = qnm_lm1(q), lm2[q] = qnm_lm2(q), dzero[q] = Species::dzero(q), qnmg[q*ngv + ig] = Q_q(G) complex as
+ *       Species::calc_qnmg(cdbasis_, .) returns it (NonLocalPotential.cc:2719, ChargeDensity.cc:793; no structure factor).
+ *   qb200_nl_us_energy: D^I_q = dzero_q + sum_G Re(conj(exp(-i G.tau_I) Q_q(G)) veff(G))          (:1607-1636)
+ *       *enl = sum_n occ_n/omega sum_{I,q} mult_q dzero_q Re(conj(bp_n[I,lm1]) bp_n[I,lm2])          (:1639-1665)
+ *       compute_hpsi: cp_n += sum_{I,lm} beta^I_lm(G) (1/omega) sum_lm' D^I[lm,lm'] bp_n[I,lm']      (:1667-1750)
+ *       veff: ngv complex (veff_g of EnergyFunctional.cc:924-927), only read when compute_hpsi; occ: nst doubles.
+ *   qb200_nl_us_augment_density: rho += Re FT^-1[ sum_{I,q} Q_q(G) summat[I,q] exp(-i G.tau_I)/omega ],
+ *       summat[I,q] = sum_n fac_n mult_q conj(bp_n[I,lm1]) bp_n[I,lm2], fac_n = weight*occ_n/omega as for
+ *       qb200_compute_density; vplan = the plan of the density basis on the density grid; *uscharge (may be NULL) receives
+ *       the integral the reference prints (:441-446).  The term is a sum over states, so a band-sharded caller adds each
+ *       rank's part to its partial rho before qb200_allreduce_rho (the reference sums summat over the ranks instead, :373-375).
+ * Pointers host or device.  Complex bases only (QB200_EUNSUPPORTED otherwise). */
+int qb200_nl_us_set_density_basis(qb200_nl* nl, int ngv, const double* vkpgx);
+int qb200_nl_us_set_species(qb200_nl* nl, int is, int nq, const int* lm1, const int* lm2, const double* dzero, const double* qnmg);
+int qb200_nl_us_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, const double* veff, int compute_hpsi,
+                       double* cp, double* enl);
+int qb200_nl_us_augment_density(qb200_nl* nl, qb200_plan* vplan, int ldc, int nst, const double* c, const double* fac, double* rho,
+                                double* uscharge);
 long long qb200_nl_query(const qb200_nl* nl, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call,
                                                            12: bytes of the anl block, 13: projectors in total,
                                                            14: form of the last call: 0 real basis, 1 complex 4-product,

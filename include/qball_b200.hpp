@@ -187,6 +187,29 @@ class NonLocalPotential {
             std::complex<double>* betapsi = 0)
   { check(qb200_nl_spsi(nl_, mloc, nstloc, reinterpret_cast<const double*>(c), qmat, reinterpret_cast<double*>(spsi),
                         reinterpret_cast<double*>(betapsi)), "qb200_nl_spsi"); }
+  // ---- the rest of the ultrasoft path: tables of NonLocalPotential::update_usfns / ChargeDensity::update_usfns
+  // (Species::calc_qnmg on the density basis, NonLocalPotential.cc:2719, ChargeDensity.cc:793), then the ultrasoft branch of
+  // NonLocalPotential::energy (:1554-1752, no forces) and the augmentation charges of ChargeDensity::update_density (:312-465)
+  void us_set_density_basis(int ngv, const double* vkpgx)
+  { check(qb200_nl_us_set_density_basis(nl_, ngv, vkpgx), "qb200_nl_us_set_density_basis"); }
+  void us_set_species(int is, int nq, const int* lm1, const int* lm2, const double* dzero, const std::complex<double>* qnmg)
+  { check(qb200_nl_us_set_species(nl_, is, nq, lm1, lm2, dzero, reinterpret_cast<const double*>(qnmg)), "qb200_nl_us_set_species"); }
+  double us_energy(int mloc, int nstloc, const std::complex<double>* c, const double* occ_local, const std::complex<double>* veff,
+                   bool compute_hpsi, std::complex<double>* cp)
+  {
+    double enl = 0.0;
+    check(qb200_nl_us_energy(nl_, mloc, nstloc, reinterpret_cast<const double*>(c), occ_local, reinterpret_cast<const double*>(veff),
+                             compute_hpsi ? 1 : 0, reinterpret_cast<double*>(cp), &enl), "qb200_nl_us_energy");
+    return enl;
+  }
+  // fac[n] = weight * occ[n] / omega as for compute_density; vft = the transform of the density basis; returns the integrated charge
+  double us_augment_density(FourierTransform& vft, int mloc, int nstloc, const std::complex<double>* c, const double* fac, double* rho)
+  {
+    double q = 0.0;
+    check(qb200_nl_us_augment_density(nl_, vft.plan(), mloc, nstloc, reinterpret_cast<const double*>(c), fac, rho, &q),
+          "qb200_nl_us_augment_density");
+    return q;
+  }
   qb200_nl* handle() const { return nl_; }
 
  private:

@@ -355,3 +355,72 @@ def us_spsi(b: dict, c, species):
         f[:, off:off + m] = (blk @ q.T).reshape(-1, m) / b["omega"]
         off += m
     return us_add_beta(b, f, species, c.copy()), bp
+
+
+def us_pair_matrix(s: dict, values):
+    """dense symmetric npr x npr matrix from per-q values along the species' (lm1, lm2) pairs"""
+    m = np.zeros((s["npr"], s["npr"]))
+    for a, bb, v in zip(s["lm1"], s["lm2"], values):
+        m[a, bb] = v
+        m[bb, a] = v
+    return m
+
+
+def us_dmat(s: dict, vkpgx, veff):
+    """D_nm^I = D_nm^0 + sum_G Re( conj(sf_I(G) Q_nm(G)) veff(G) ) on the density basis (NonLocalPotential.cc:1607-1636,
+    !highmem branch; sf_I(G) = exp(-i G.tau_I), :2724-2731).  Returns (na, nq)."""
+    arg = np.asarray(s["tau"]) @ np.asarray(vkpgx)                       # (na, ngv)
+    sf = np.cos(arg) - 1j * np.sin(arg)
+    u = np.conj(sf) * np.asarray(veff)[None, :]                           # (na, ngv)
+    return np.real(u @ np.conj(np.asarray(s["qnmg"])).T) + np.asarray(s["dzero"])[None, :]
+
+
+def us_energy(b: dict, c, occ, species, vkpgx, veff, compute_hpsi=True):
+    """ultrasoft branch of NonLocalPotential::energy (NonLocalPotential.cc:1554-1752, no forces):
+    E_nl = sum_n occ_n/omega sum_{I,q} mult_q dzero_q Re(conj(bp[I,lm1]) bp[I,lm2]),
+    H psi_n += sum_{I,lm} beta^I_lm (1/omega) sum_lm' D^I[lm,lm'] bp_n[I,lm']."""
+    bp = us_betapsi(b, c, species)
+    occ = np.asarray(occ, dtype=np.float64)
+    enl, off = 0.0, 0
+    f = np.zeros_like(bp)
+    for s in species:
+        m = s["na"] * s["npr"]
+        blk = bp[:, off:off + m].reshape(-1, s["na"], s["npr"])           # (nst, na, npr)
+        d0 = us_pair_matrix(s, s["dzero"])
+        enl += float(np.einsum("n,nia,ab,nib->", occ, np.conj(blk), d0, blk).real) / b["omega"]
+        if compute_hpsi:
+            dm = us_dmat(s, vkpgx, veff)
+            for ia in range(s["na"]):
+                f[:, off + ia * s["npr"]:off + (ia + 1) * s["npr"]] = blk[:, ia, :] @ us_pair_matrix(s, dm[ia]).T / b["omega"]
+        off += m
+    hp = us_add_beta(b, f, species, np.zeros_like(c)) if compute_hpsi else None
+    return enl, hp, bp
+
+
+def us_summat(s: dict, bp_species, fac):
+    """summat[I, q] = sum_n fac_n mult_q conj(bp_n[I,lm1]) bp_n[I,lm2], fac_n = weight occ_n / omega (ChargeDensity.cc:352-368)"""
+    blk = np.asarray(bp_species).reshape(-1, s["na"], s["npr"])
+    mult = np.where(np.asarray(s["lm1"]) == np.asarray(s["lm2"]), 1.0, 2.0)
+    return np.einsum("n,niq,niq->iq", np.asarray(fac, dtype=np.float64), np.conj(blk[:, :, s["lm1"]]), blk[:, :, s["lm2"]]) * mult[None, :]
+
+
+def us_rhog(b: dict, c, fac, species, vkpgx):
+    """rhogus(G) = sum_{I,q} Q_q(G) summat[I,q] exp(-i G.tau_I) / omega (ChargeDensity.cc:397-428 with sfactloc_ of :800-820)"""
+    bp = us_betapsi(b, c, species)
+    rg = np.zeros(np.asarray(vkpgx).shape[1], dtype=np.complex128)
+    off = 0
+    for s in species:
+        m = s["na"] * s["npr"]
+        sm = us_summat(s, bp[:, off:off + m], fac)                        # (na, nq)
+        arg = np.asarray(s["tau"]) @ np.asarray(vkpgx)
+        sf = (np.cos(arg) - 1j * np.sin(arg)) / b["omega"]
+        rg += np.einsum("iq,qg,ig->g", sm, np.asarray(s["qnmg"]), sf)
+        off += m
+    return rg
+
+
+def us_augment_density(b: dict, vft: "FT", c, fac, species, vkpgx, rho):
+    """rho += Re FT^-1[rhogus] (ChargeDensity.cc:437-456); returns (rho, uscharge = sum Re(.) omega / N)"""
+    r = vft.backward(us_rhog(b, c, fac, species, vkpgx)).real
+    rho += r
+    return rho, float(r.sum()) * b["omega"] / r.size

@@ -15,6 +15,8 @@
 // The kinetic term of EnergyFunctional::energy (EnergyFunctional.cc:1675-1690) lives inside a function that needs a
 // whole Sample; its three-line loop is restated here in the same order (clear -> nonlocal -> kinetic -> local).
 //
+//   NonLocalPotential::energy (ultrasoft branch) src/qball/NonLocalPotential.cc:1554-1906   } mode `usx`: through a
+//   ChargeDensity::update_density (augmentation) src/qball/ChargeDensity.cc:312-465         } Sample, as the application does
 // usage:  ref_driver basis <case.txt>     dump basis / grid tables to <out>.*
 //         ref_driver run   <case.txt>     read <out>.in_c.f64, <out>.in_v.f64, <out>.in_occ.f64 ; dump results
 //
@@ -53,6 +55,9 @@
 #include <qball/UnitCell.h>
 #include <qball/Timer.h>
 #include <qball/VectorPotential.h>
+#include <qball/Sample.h>
+#include <qball/Wavefunction.h>
+#include <qball/ChargeDensity.h>
 #include <math/matrix.h>
 #include <functionals/LDAFunctional.h>
 #include <functionals/PBEFunctional.h>
@@ -132,6 +137,118 @@ int main(int argc, char** argv)
   UnitCell cell(D3vector(a[0],a[1],a[2]), D3vector(a[3],a[4],a[5]), D3vector(a[6],a[7],a[8]));
   D3vector kpoint(kp[0],kp[1],kp[2]);
 
+  if (mode == "usx") {
+    // ---- SURVEY section 8 row f4, remainder: the ultrasoft branch of NonLocalPotential::energy (D_nm^I from veff(G) and
+    //      Q_nm(G), E_nl, H psi; NonLocalPotential.cc:1554-1752) and the augmentation charges of ChargeDensity::update_density
+    //      (ChargeDensity.cc:312-465), both run by the reference's own classes on a Sample set up the way SpeciesCmd / RunCmd do
+    //      (ultrasoft flag on ctrl and wf, allocation through randomize), with the coefficients and occupations overwritten.
+    Sample* s = new Sample(ctxt);
+    s->ctrl.ecutden = 0.0; s->ctrl.ultrasoft = true; s->ctrl.nlcc = false; s->ctrl.tddft_involved = false; s->ctrl.extra_memory = 0;
+    s->atoms.set_cell(cell);
+    for (size_t i = 0; i < species.size(); i++) {
+      SpeciesReader rd(ctxt);
+      Species* sp = new Species(ctxt, species[i].first);
+      rd.readSpecies(*sp, species[i].second);
+      rd.bcastSpecies(*sp);
+      s->atoms.addSpecies(sp, species[i].first);
+      if (!sp->ultrasoft()) { fprintf(stderr, "species %zu is not ultrasoft\n", i); return 3; }
+    }
+    for (size_t i = 0; i < atomlines.size(); i++)
+      s->atoms.addAtom(new Atom(atomlines[i].name, atomlines[i].species, D3vector(atomlines[i].x, atomlines[i].y, atomlines[i].z), D3vector(0,0,0)));
+    s->wf.set_ultrasoft(true);
+    s->wf.set_cell(cell);
+    s->wf.set_ecut(ecut);
+    s->wf.set_nel(2*nst);
+    s->wf.set_nspin(1);
+    if (kp[0] != 0.0 || kp[1] != 0.0 || kp[2] != 0.0) s->wf.add_kpoint(kpoint, 1.0);   // the first added k-point replaces the default one (Wavefunction.cc:1049-1055)
+    s->wf.randomize_us(0.01, s->atoms, false);          // allocates, as RunCmd.cc:111-112 does (Wavefunction.cc:1116-1137)
+    SlaterDet* sd = s->wf.sd(0,0);
+    if (sd->nst() != nst || sd->basis().real()) { fprintf(stderr, "usx: unexpected wavefunction (nst %d, real %d)\n", sd->nst(), (int)sd->basis().real()); return 3; }
+    const Basis& basis = sd->basis();
+    const int ngw = basis.localsize(), mloc = sd->c().mloc();
+    vector<complex<double> > cin((size_t)mloc*nst);
+    vector<double> occ(nst);
+    slurp(out + ".in_c.f64", &cin[0], cin.size()*sizeof(complex<double>));
+    slurp(out + ".in_occ.f64", &occ[0], nst*sizeof(double));
+    memcpy(sd->c().valptr(), &cin[0], cin.size()*sizeof(complex<double>));
+    sd->set_occ(occ);
+    ChargeDensity cd(*s);
+    Basis* vb = cd.vbasis();
+    const int ngv = vb->localsize();
+    const int gr[3] = { cd.vft()->np0(), cd.vft()->np1(), cd.vft()->np2() };
+    const size_t N = cd.vft()->np012loc();
+    // the density without the augmentation charges: the reference's own SlaterDet::compute_density on the same grid
+    vector<double> rho_nc(N, 0.0);
+    sd->compute_density(*cd.ft(0,0), 1.0, &rho_nc[0]);
+    sd->init_usfns(&s->atoms);
+    cd.update_usfns();
+    cd.update_density();
+    { int hdr[8] = { gr[0], gr[1], gr[2], ngv, vb->nrod_loc(), vb->real() ? 1 : 0, ngw, mloc };
+      dump(out + ".usx.hdr.i32", hdr, sizeof hdr);
+      vector<int> rods(4*vb->nrod_loc());
+      const int nr = vb->nrod_loc();
+      for (int i = 0; i < nr; i++) { rods[i] = vb->rod_h(i); rods[nr+i] = vb->rod_k(i); rods[2*nr+i] = vb->rod_lmin(i); rods[3*nr+i] = vb->rod_size(i); }
+      dump(out + ".usx.vrods.i32", &rods[0], rods.size()*sizeof(int));
+      int mm[2] = { vb->idxmin(1), vb->idxmax(1) };
+      dump(out + ".usx.vidxmm.i32", mm, sizeof mm);
+      dump(out + ".usx.vkpgx.f64", vb->kpgx_ptr(0), 3*(size_t)ngv*sizeof(double));
+      dump(out + ".usx.vg2.f64", vb->g2_ptr(), (size_t)ngv*sizeof(double)); }
+    dump(out + ".usx.rho_nc.f64", &rho_nc[0], N*sizeof(double));
+    dump(out + ".usx.rho.f64", &cd.rhor[0][0], N*sizeof(double));
+    double nel = cd.nelectrons();
+    dump(out + ".usx.nel.f64", &nel, sizeof nel);
+    // a seeded effective potential on the density basis (an input of NonLocalPotential::energy; EnergyFunctional.cc:924-927)
+    vector<complex<double> > veff(ngv);
+    { const double* g2 = vb->g2_ptr();
+      for (int ig = 0; ig < ngv; ig++) {
+        const double ph = 0.37*ig + 1.3*g2[ig];
+        veff[ig] = 0.8*exp(-0.15*g2[ig]) * complex<double>(cos(ph), sin(ph));
+      } }
+    dump(out + ".usx.veff.f64", &veff[0], (size_t)ngv*sizeof(complex<double>));
+    NonLocalPotential nlp(s->atoms, sd->context(), basis, 0, false);
+    nlp.update_usfns(*sd, vb);
+    SlaterDet dsd(*sd); dsd.c().clear();
+    vector<vector<double> > fion; valarray<double> sigma(6);
+    const double enl = nlp.energy(*sd, true, dsd, false, fion, false, sigma, veff);
+    dump(out + ".usx.enl.f64", &enl, sizeof enl);
+    dump(out + ".usx.hnl.f64", dsd.c().cvalptr(), (size_t)mloc*nst*sizeof(complex<double>));
+    vector<vector<double> > tau; s->atoms.get_positions(tau, true);
+    for (int is = 0; is < s->atoms.nsp(); is++) {
+      Species* sp = s->atoms.species_list[is];
+      char tag[32]; snprintf(tag, sizeof tag, ".usx%d", is);
+      const int na = s->atoms.na(is), nlm = sp->nbetalm(), nq = sp->nqtot();
+      int h[4] = { na, nlm, nq, 0 };
+      dump(out + tag + ".hdr.i32", h, sizeof h);
+      vector<int> l(nlm), lm1(nq), lm2(nq);
+      vector<double> dzero(nq);
+      for (int lm = 0; lm < nlm; lm++) l[lm] = sp->betalm_l(lm);
+      for (int qi = 0; qi < nq; qi++) { lm1[qi] = sp->qnm_lm1(qi); lm2[qi] = sp->qnm_lm2(qi); dzero[qi] = sp->dzero(qi); }
+      dump(out + tag + ".l.i32", &l[0], nlm*sizeof(int));
+      dump(out + tag + ".lm1.i32", &lm1[0], nq*sizeof(int));
+      dump(out + tag + ".lm2.i32", &lm2[0], nq*sizeof(int));
+      dump(out + tag + ".dzero.f64", &dzero[0], nq*sizeof(double));
+      const complex<double>* bg = sd->betag(is)->cvalptr();
+      const int bg_mloc = sd->betag(is)->mloc();
+      vector<double> tw((size_t)nlm*ngw);
+      for (int lm = 0; lm < nlm; lm++) {
+        const complex<double> il = l[lm] == 0 ? complex<double>(1,0) : l[lm] == 1 ? complex<double>(0,-1) : l[lm] == 2 ? complex<double>(-1,0) : complex<double>(0,1);
+        for (int ig = 0; ig < ngw; ig++) tw[(size_t)lm*ngw + ig] = real(bg[(size_t)lm*bg_mloc + ig] / il);
+      }
+      dump(out + tag + ".betag.f64", &tw[0], tw.size()*sizeof(double));
+      dump(out + tag + ".tau.f64", &tau[is][0], 3*na*sizeof(double));
+      // Q_nm(G) on the density basis: the table both NonLocalPotential::update_usfns (:2719) and ChargeDensity::update_usfns (:793) take
+      vector<complex<double> > qnm; vector<double> qaug;
+      sp->calc_qnmg(vb, qnm, qaug);
+      dump(out + tag + ".qnmg.f64", &qnm[0], (size_t)nq*ngv*sizeof(complex<double>));
+      const ComplexMatrix* bp = sd->betapsi(is);
+      vector<complex<double> > bpo((size_t)nst*na*nlm);
+      for (int n = 0; n < nst; n++)
+        for (int i = 0; i < na*nlm; i++) bpo[(size_t)n*na*nlm + i] = bp->cvalptr()[(size_t)n*bp->mloc() + i];
+      dump(out + tag + ".betapsi.f64", &bpo[0], bpo.size()*sizeof(complex<double>));
+    }
+    MPI_Finalize();
+    return 0;
+  }
   SlaterDet sd(ctxt, colctxt, ctxtsq, kpoint, mode == "us", force_complex != 0);   // (ultrasoft forces complex states, SlaterDet.cc:57-58)
   sd.set_nblocks(1,1);
   sd.resize(cell, cell, ecut, nst);

@@ -157,3 +157,55 @@ def run_reference_us(case: Case, seed: int = 1, workdir: str | None = None, thre
     r["species"] = sp
     r["spsi"] = _load(prefix, "spsi.f64", np.complex128).reshape(case.nst, b["mloc"])
     return r
+
+
+def run_reference_usx(case: Case, seed: int = 1, occ=None, workdir: str | None = None, threads: int = 8) -> dict:
+    """SURVEY section 8 row f4, remainder: ``ref_driver usx`` = the reference's own ultrasoft branch of
+    NonLocalPotential::energy (NonLocalPotential.cc:1554-1752) and the augmentation charges of
+    ChargeDensity::update_density (ChargeDensity.cc:312-465) on a Sample set up as the application does, with seeded
+    coefficients, the given occupations and a seeded effective potential veff(G) on the density basis.  Returns the
+    wavefunction basis, the density basis (forced complex at k = 0 for ultrasoft potentials, ChargeDensity.cc:75), per species
+    the betag tables / channels / (lm1, lm2, dzero) / Q_nm(G) on the density basis / positions / betapsi, and the results:
+    rho_nc (no augmentation), rho (with), nelectrons, veff, enl, hnl."""
+    assert have_ref(), "oracle/_ref/ref_driver missing: run `make -C oracle ref` where /root/reference exists"
+    tmp = workdir or tempfile.mkdtemp(prefix="qbrefusx_")
+    prefix = os.path.join(tmp, "case")
+    cf = os.path.join(tmp, "case.txt")
+    with open(cf, "w") as f:
+        f.write(case.text(prefix))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    subprocess.run([REF_DRIVER, "basis", cf], check=True, env=env, stdout=subprocess.DEVNULL)
+    b = read_basis(prefix)
+    c = synth_coefficients(b["kpg2"], case.ecut, case.nst, b["mloc"], b["is_real"], seed)
+    occ = np.full(case.nst, 2.0) if occ is None else np.asarray(occ, dtype=np.float64)
+    c.tofile(prefix + ".in_c.f64")
+    occ.tofile(prefix + ".in_occ.f64")
+    subprocess.run([REF_DRIVER, "usx", cf], check=True, env=env, stdout=subprocess.DEVNULL)
+    r = dict(b)
+    h = _load(prefix, "usx.hdr.i32", np.int32)
+    assert int(h[6]) == b["ngw"] and int(h[7]) == b["mloc"]
+    ngv, nvr = int(h[3]), int(h[4])
+    vr = _load(prefix, "usx.vrods.i32", np.int32).reshape(4, nvr)
+    mm = _load(prefix, "usx.vidxmm.i32", np.int32)
+    r.update(c=c, occ=occ, vgrid=(int(h[0]), int(h[1]), int(h[2])), ngv=ngv, v_is_real=bool(h[5]),
+             v_rod_h=vr[0].copy(), v_rod_k=vr[1].copy(), v_rod_lmin=vr[2].copy(), v_rod_size=vr[3].copy(),
+             v_idxmin1=int(mm[0]), v_idxmax1=int(mm[1]),
+             vkpgx=_load(prefix, "usx.vkpgx.f64", np.float64).reshape(3, ngv), vg2=_load(prefix, "usx.vg2.f64", np.float64),
+             rho_nc=_load(prefix, "usx.rho_nc.f64", np.float64), rho=_load(prefix, "usx.rho.f64", np.float64),
+             nelectrons=float(_load(prefix, "usx.nel.f64", np.float64)[0]), veff=_load(prefix, "usx.veff.f64", np.complex128),
+             enl=float(_load(prefix, "usx.enl.f64", np.float64)[0]),
+             hnl=_load(prefix, "usx.hnl.f64", np.complex128).reshape(case.nst, b["mloc"]))
+    sp = []
+    for i in range(b["nsp"]):
+        hh = _load(prefix, f"usx{i}.hdr.i32", np.int32)
+        na, nlm, nq = int(hh[0]), int(hh[1]), int(hh[2])
+        sp.append(dict(na=na, npr=nlm, nq=nq, lproj=_load(prefix, f"usx{i}.l.i32", np.int32),
+                       twnl=_load(prefix, f"usx{i}.betag.f64", np.float64).reshape(nlm, b["ngw"]),
+                       tau=_load(prefix, f"usx{i}.tau.f64", np.float64).reshape(na, 3),
+                       lm1=_load(prefix, f"usx{i}.lm1.i32", np.int32), lm2=_load(prefix, f"usx{i}.lm2.i32", np.int32),
+                       dzero=_load(prefix, f"usx{i}.dzero.f64", np.float64),
+                       qnmg=_load(prefix, f"usx{i}.qnmg.f64", np.complex128).reshape(nq, ngv),
+                       betapsi=_load(prefix, f"usx{i}.betapsi.f64", np.complex128).reshape(case.nst, na * nlm),
+                       wt=np.zeros(nlm)))
+    r["species"] = sp
+    return r

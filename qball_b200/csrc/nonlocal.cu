@@ -518,7 +518,21 @@ __global__ void __launch_bounds__(256) k_fnl_finish_half(const double* __restric
 
 using namespace qb200;
 
+// augmentation tables of the ultrasoft entry points (ultrasoft.cuh)
+struct UsSpeciesDev {
+  int nq;
+  const int *lm1, *lm2;      // [nq] channels of pair q
+  const double* dzero;       // [nq] D^0
+  const double2* qnm;        // [nq][ngv] Q_q(G) on the density basis
+};
+struct UsTables {
+  int ngv = 0;
+  const double* vkpgx = nullptr;                 // device [3][ngv]
+  std::vector<UsSpeciesDev> sp;                  // per species of the object (nq == 0: not set)
+};
+
 struct qb200_nl {
+  UsTables* us;
   int device;
   cudaStream_t stream;
   int ngw, is_real;
@@ -588,6 +602,7 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   if (device < 0 || device >= ndev) { set_error("qb200_nl_create: no such CUDA device"); return QB200_ENODEV; }
   QB_CUDA(cudaSetDevice(device));
   qb200_nl* nl = new qb200_nl();
+  nl->us = nullptr;
   nl->device = device; nl->stream = 0; nl->ngw = ngw; nl->is_real = is_real ? 1 : 0; nl->omega = omega;
   nl->part = nl->fs = nl->eblk = nl->occ_dev = nl->enl_dev = nl->st_c = nl->st_cp = nullptr;
   nl->part_cap = nl->fs_cap = nl->eblk_cap = nl->occ_cap = nl->st_c_cap = nl->st_cp_cap = 0;
@@ -804,6 +819,7 @@ extern "C" int qb200_nl_destroy(qb200_nl* nl)
   for (double2* p : nl->ph) if (p) cudaFree(p);
   for (void* p : nl->lat_owned) cudaFree(p);
   for (double* p : { nl->part, nl->fs, nl->eblk, nl->occ_dev, nl->enl_dev, nl->st_c, nl->st_cp, nl->wtp, nl->W, nl->Wg, nl->Ug }) if (p) cudaFree(p);
+  delete nl->us;
   delete nl;
   return QB200_OK;
 }
@@ -1302,6 +1318,8 @@ extern "C" int qb200_nl_spsi(qb200_nl* nl, int ldc, int nst, const double* c, co
   QB_CUDA(cudaStreamSynchronize(nl->stream));
   return QB200_OK;
 }
+
+#include "ultrasoft.cuh"
 
 double* qb200_nl_enl_dev(qb200_nl* nl) { return nl->enl_dev; }
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s) { cudaStream_t o = nl->stream; nl->stream = s; return o; }

@@ -249,6 +249,43 @@ class NonLocalPotential:
         capi._check(self._L.qb200_nl_add_beta(self._h, ldc, nst, capi.ptr(f), capi.ptr(cp)), "qb200_nl_add_beta")
         return cp
 
+    def us_set_tables(self, vkpgx, species):
+        """the augmentation tables of the ultrasoft energy branch / augmentation charges: vkpgx = kpgx of the density basis
+        (3 x ngv), species = per species a dict with lm1, lm2 (Species::qnm_lm1/2), dzero (Species::dzero) and qnmg (nq x ngv
+        complex, Species::calc_qnmg on the density basis; NonLocalPotential.cc:2719, ChargeDensity.cc:793)"""
+        vk = np.ascontiguousarray(vkpgx, dtype=np.float64)
+        ngv = vk.shape[1]
+        capi._check(self._L.qb200_nl_us_set_density_basis(self._h, ngv, capi.ptr(vk)), "qb200_nl_us_set_density_basis")
+        for i, s in enumerate(species):
+            lm1 = np.ascontiguousarray(s["lm1"], dtype=np.int32)
+            lm2 = np.ascontiguousarray(s["lm2"], dtype=np.int32)
+            dz = np.ascontiguousarray(s["dzero"], dtype=np.float64)
+            q = np.ascontiguousarray(s["qnmg"], dtype=np.complex128)
+            assert q.shape == (lm1.shape[0], ngv)
+            capi._check(self._L.qb200_nl_us_set_species(self._h, i, int(lm1.shape[0]), lm1.ctypes.data_as(capi.C.POINTER(capi.C.c_int)),
+                                                        lm2.ctypes.data_as(capi.C.POINTER(capi.C.c_int)), capi.ptr(dz), capi.ptr(q)),
+                        "qb200_nl_us_set_species")
+
+    def us_energy(self, c, occ, veff=None, compute_hpsi=False, cp=None) -> float:
+        """ultrasoft branch of NonLocalPotential::energy (NonLocalPotential.cc:1554-1752): returns E_nl; compute_hpsi: cp +=
+        beta (D^I <beta|psi>) / omega with D^I = D^0 + sum_G Re(conj(sf_I Q) veff)"""
+        nst, ldc = _block_dims(c)
+        o = np.ascontiguousarray(occ, dtype=np.float64)
+        e = np.zeros(1)
+        capi._check(self._L.qb200_nl_us_energy(self._h, ldc, nst, capi.ptr(c), capi.ptr(o), capi.ptr(veff), int(bool(compute_hpsi)),
+                                               capi.ptr(cp), capi.ptr(e)), "qb200_nl_us_energy")
+        return float(e[0])
+
+    def us_augment_density(self, vft, c, weight: float, occ, omega: float, rho) -> float:
+        """augmentation charges of ChargeDensity::update_density (ChargeDensity.cc:312-465): rho += Re FT^-1[rhogus] on the
+        density-basis transform `vft`; returns the integrated augmentation charge the reference prints"""
+        nst, ldc = _block_dims(c)
+        fac = np.ascontiguousarray((weight / omega) * np.asarray(occ, dtype=np.float64))
+        q = np.zeros(1)
+        capi._check(self._L.qb200_nl_us_augment_density(self._h, vft._h, ldc, nst, capi.ptr(c), capi.ptr(fac), capi.ptr(rho), capi.ptr(q)),
+                    "qb200_nl_us_augment_density")
+        return float(q[0])
+
     def spsi(self, c, qmats, out, betapsi=None):
         """SlaterDet::calc_spsi (SlaterDet.cc:2426-2570): out = c + sum beta (q <beta|psi>) / omega; qmats = list of the species'
         dense symmetric npr x npr coupling matrices"""

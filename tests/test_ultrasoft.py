@@ -110,3 +110,107 @@ def test_cuda_ultrasoft_needs_complex_basis():
     c = np.zeros((1, b["ngw"]), dtype=np.complex128)
     with pytest.raises(capi.QB200Error):
         nlp.betapsi(c, np.zeros((1, 1), dtype=np.complex128))
+
+
+# ------------------------------------------------------------------------------------------------ the rest of row f4
+# the ultrasoft branch of NonLocalPotential::energy (NonLocalPotential.cc:1554-1752) and the augmentation charges of
+# ChargeDensity::update_density (ChargeDensity.cc:312-465); fixtures tests/golden/usx/*.npz from the reference's own classes on a
+# Sample (tests/golden/make_golden_usx.py)
+USX = os.path.join(HERE, "golden", "usx")
+XNAMES = sorted(f[:-4] for f in os.listdir(USX) if f.endswith(".npz"))
+
+
+def loadx(name):
+    z = np.load(os.path.join(USX, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    cell, ecut = tuple(g["cell"]), float(g["ecut"])
+    b = P.make_basis(cell, ecut, tuple(g["kpoint"]), True)
+    vb = P.make_basis(cell, 4.0 * ecut, (0, 0, 0), True)        # ChargeDensity.cc:75-80: complex at k = 0 for ultrasoft runs
+    assert b["ngw"] == int(g["ngw"]) and vb["ngw"] == int(g["ngv"]) and P.density_grid(cell, ecut) == tuple(g["vgrid"])
+    sp = [dict(na=int(g[f"sp{i}_na"]), npr=int(g[f"sp{i}_npr"]), nq=int(g[f"sp{i}_nq"]), lproj=g[f"sp{i}_lproj"], twnl=g[f"sp{i}_twnl"],
+               tau=g[f"sp{i}_tau"], lm1=g[f"sp{i}_lm1"], lm2=g[f"sp{i}_lm2"], dzero=g[f"sp{i}_dzero"], qnmg=g[f"sp{i}_qnmg"],
+               betapsi=g[f"sp{i}_betapsi"], wt=np.zeros(int(g[f"sp{i}_npr"]))) for i in range(int(g["nsp"]))]
+    c = R.synth_coefficients(b["kpg2"], ecut, int(g["nst"]), int(g["mloc"]), False, int(g["seed"]))
+    return g, b, vb, sp, c
+
+
+@pytest.mark.parametrize("name", XNAMES)
+def test_oracle_ultrasoft_energy_and_augmentation_vs_reference_fixture(name):
+    """the numpy restatement (oracle/port.py us_energy / us_augment_density) against what the reference's
+    NonLocalPotential::energy and ChargeDensity::update_density produced"""
+    g, b, vb, sp, c = loadx(name)
+    ngw = b["ngw"]
+    enl, hp, bp = P.us_energy(b, c, g["occ"], sp, vb["kpgx"], g["veff"])
+    assert relerr(bp, np.concatenate([s["betapsi"] for s in sp], axis=1)) < 1e-13
+    assert abs(enl - float(g["enl"])) < 1e-13 * abs(float(g["enl"]))
+    assert relerr(hp[:, :ngw], g["hnl"][:, :ngw]) < 1e-13
+    vft = P.FT(vb, *(int(x) for x in g["vgrid"]))
+    rho, usq = P.us_augment_density(b, vft, c, g["occ"] / b["omega"], sp, vb["kpgx"], g["rho_nc"].copy())
+    assert relerr(rho, g["rho"]) < 1e-13
+    assert np.abs(g["rho"] - g["rho_nc"]).max() > 0.1 * np.abs(g["rho"]).max()       # the augmentation part is not small here
+    assert abs(rho.sum() * b["omega"] / rho.size - float(g["nelectrons"])) < 1e-11
+
+
+def test_oracle_ultrasoft_energy_vs_live_reference():
+    if not R.have_ref() or not os.path.isdir("/root/reference"):
+        pytest.skip("compiled reference not present")
+    case = R.Case(cell=(9, 0, 0, 0, 8, 0, 0.4, 0, 8.5), ecut=4.0, kpoint=(0.0, 0.5, 0.0), nst=2,
+                  species=[("carbon", "/root/reference/testsuite/pseudopotentials/04_ultrasoft_carbon/carbon.xml")],
+                  atoms=[("C1", "carbon", 1.0, -2.0, 0.5)])
+    r = R.run_reference_usx(case, seed=11, occ=[2.0, 0.3])
+    enl, hp, _ = P.us_energy(r, r["c"], r["occ"], r["species"], r["vkpgx"], r["veff"])
+    assert abs(enl - r["enl"]) < 1e-13 * abs(r["enl"]) and relerr(hp[:, :r["ngw"]], r["hnl"][:, :r["ngw"]]) < 1e-13
+    vb = P.make_basis(case.cell, 4.0 * case.ecut, (0, 0, 0), True)
+    rho, _ = P.us_augment_density(r, P.FT(vb, *r["vgrid"]), r["c"], r["occ"] / r["omega"], r["species"], r["vkpgx"], r["rho_nc"].copy())
+    assert relerr(rho, r["rho"]) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", XNAMES)
+@pytest.mark.parametrize("host", [False, True])
+def test_cuda_ultrasoft_energy_and_augmentation_vs_reference_fixture(name, host):
+    """qb200_nl_us_energy / qb200_nl_us_augment_density through the C ABI against the reference's arrays (E_nl, H psi with the
+    atom-dependent D^I built from veff(G) and Q_nm(G), rho with the augmentation charges), device and host pointers, whole
+    sphere and a workspace that forces several plane-wave chunks"""
+    import torch
+    from qball_b200 import host as H
+    g, b, vb, sp, c = loadx(name)
+    ngw, nst = b["ngw"], c.shape[0]
+    wrap = (lambda a: np.ascontiguousarray(a)) if host else (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda())
+    back = (lambda a: a) if host else (lambda t: t.cpu().numpy())
+    vgrid = tuple(int(x) for x in g["vgrid"])
+    for ws in (None, 1 << 20):
+        nlp = H.NonLocalPotential(b, sp)
+        if ws:
+            nlp.set_workspace(ws)
+        nlp.us_set_tables(vb["kpgx"], sp)
+        e0 = nlp.us_energy(wrap(c), g["occ"])                               # energy only
+        assert abs(e0 - float(g["enl"])) < TOL * abs(float(g["enl"]))
+        cp0 = 0.25 * c
+        cp = wrap(cp0.copy())
+        e1 = nlp.us_energy(wrap(c), g["occ"], wrap(g["veff"]), True, cp)    # H psi on top of a non-zero cp
+        assert e1 == e0
+        assert relerr(back(cp)[:, :ngw] - cp0[:, :ngw], g["hnl"][:, :ngw]) < TOL
+        assert np.all(back(cp)[:, ngw:] == cp0[:, ngw:])
+        # density: SlaterDet::compute_density on the wavefunction basis, then the augmentation charges on the density basis
+        ft = H.FourierTransform(b, *vgrid)
+        vft = H.FourierTransform(vb, *vgrid)
+        rho = wrap(np.zeros(vgrid[0] * vgrid[1] * vgrid[2]))
+        H.compute_density(ft, wrap(c), 1.0, g["occ"], b["omega"], rho)
+        assert relerr(back(rho), g["rho_nc"]) < TOL
+        usq = nlp.us_augment_density(vft, wrap(c), 1.0, g["occ"], b["omega"], rho)
+        assert relerr(back(rho), g["rho"]) < TOL
+        want_q = (g["rho"] - g["rho_nc"]).sum() * b["omega"] / g["rho"].size
+        assert abs(usq - want_q) < 1e-10 * max(1.0, abs(want_q))
+        assert abs(back(rho).sum() * b["omega"] / g["rho"].size - float(g["nelectrons"])) < 1e-10
+        nlp.close()
+
+
+@pytest.mark.gpu
+def test_cuda_ultrasoft_energy_needs_tables():
+    from qball_b200 import capi, host as H
+    g, b, vb, sp, c = loadx(XNAMES[0])
+    nlp = H.NonLocalPotential(b, sp)
+    with pytest.raises(capi.QB200Error):
+        nlp.us_energy(c, g["occ"])
+    nlp.close()
