@@ -117,6 +117,20 @@ int qb200_nl_create(qb200_nl** nl, int device, int ngw, int is_real, double omeg
 /* add species: na atoms, npr projectors, lproj[npr], wt[npr], twnl[npr*ngw] (twnl[is][ipr*ngw+ig]), tau[3*na] */
 int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const double* wt, const double* twnl,
                          const double* tau);
+/* NonLocalPotential::update_twnl on the device for a Kleinman-Bylander species (nquad == 0; NonLocalPotential.cc:261-1522, the
+ * twnl part -- the stress derivatives dtwnl stay with the caller): twnl[ipr*ngw + ig] = Y_lm(k+G) * v(|k+G|), real spherical
+ * harmonics in the reference's order and normalisation, v from the species' radial cubic splines (Species::dvnlg,
+ * Species.cc:1492-1505; splintd, spline.cc:126-156).  After a cell change the caller refreshes kpgx (a new object) or the
+ * tables with this call instead of shipping npr*ngw doubles.
+ *   mproj[ipr]   = m of projector ipr (iprojlm[is][l][m][ic] == ipr, NonLocalPotential.cc:219-233), 0 <= m <= 2 l
+ *   tabproj[ipr] = index of its radial table, one per (l, channel): vnlg / vnlg_spl [ntab][nknots] = the y_ / y2_ arrays of
+ *                  Species::projectors_g_[l][ic] on the knots gspl[nknots] (the first nknots of Species::gspl_; enough knots to
+ *                  cover max |k+G| suffice), gcut = the LAST knot of the full table (beyond it v = 0, Species.cc:1495)
+ * qb200_nl_add_species accepts twnl == NULL for a species whose table is filled this way.  All pointers here are host pointers.
+ * qb200_nl_get_twnl copies the table of species `is` (npr*ngw doubles) back, host or device destination. */
+int qb200_nl_update_twnl(qb200_nl* nl, int is, const int* mproj, const int* tabproj, int ntab, int nknots, const double* gspl,
+                         double gcut, const double* vnlg, const double* vnlg_spl);
+int qb200_nl_get_twnl(qb200_nl* nl, int is, double* twnl);
 /* optional, before the first energy call: the integer description of the plane waves.
  *   idx    = Basis::idx_ptr(): 3*ngw ints, (h,k,l) of plane wave ig at idx[3*ig + 0..2]      (Basis.cc:672-674)
  *   b      = reciprocal lattice vectors UnitCell::b(0), b(1), b(2) as 9 doubles (b[3*i + xyz]) (Basis.cc:711-713)

@@ -160,6 +160,13 @@ class NonLocalPotential {
   void add_species(int na, int npr, const int* lproj, const double* wt, const double* twnl, const double* tau)
   { check(qb200_nl_add_species(nl_, na, npr, lproj, wt, twnl, tau), "qb200_nl_add_species"); }
   void set_positions(int is, const double* tau) { check(qb200_nl_set_positions(nl_, is, tau), "qb200_nl_set_positions"); }
+  // void NonLocalPotential::update_twnl(compute_stress = false) for Kleinman-Bylander species `is` (NonLocalPotential.cc:261-1522):
+  // mproj / tabproj = m and radial-table index of every projector (iprojlm), tables = y_ / y2_ of Species::projectors_g_[l][ic] on
+  // the knots gspl, gcut = the last knot of the full table.  add_species may then be given twnl = 0.
+  void update_twnl(int is, const int* mproj, const int* tabproj, int ntab, int nknots, const double* gspl, double gcut,
+                   const double* vnlg, const double* vnlg_spl)
+  { check(qb200_nl_update_twnl(nl_, is, mproj, tabproj, ntab, nknots, gspl, gcut, vnlg, vnlg_spl), "qb200_nl_update_twnl"); }
+  void get_twnl(int is, double* twnl) { check(qb200_nl_get_twnl(nl_, is, twnl), "qb200_nl_get_twnl"); }
   // optional: idx = basis.idx_ptr() (3*ngw), b = { cell.b(0), cell.b(1), cell.b(2) } as 9 doubles, kpoint = basis.kpoint()
   // in crystal units -> separable phase tables; complex states at k = 0 are then contracted over the half sphere
   void set_lattice(const int* idx, const double* b, const double* kpoint)

@@ -424,3 +424,51 @@ def us_augment_density(b: dict, vft: "FT", c, fac, species, vkpgx, rho):
     r = vft.backward(us_rhog(b, c, fac, species, vkpgx)).real
     rho += r
     return rho, float(r.sum()) * b["omega"] / r.size
+
+
+def update_twnl(kpgx, lproj, mproj, tabproj, gspl, vnlg, vnlg_spl, gcut=None):
+    """NonLocalPotential::update_twnl for a Kleinman-Bylander species (NonLocalPotential.cc:261-1522, the twnl part, no stress
+    derivatives): twnl[ipr, ig] = Y_lm(k+G) v(|k+G|), v = the species' radial cubic spline (Species::dvnlg, Species.cc:1492-1505:
+    0 beyond the last knot; splintd, spline.cc:126-156), real spherical harmonics in the reference's order and normalisation
+    (l=0 :334, l=1 :466-470, l=2 :712-747, l=3 :1126-1140).  kpgx: (3, ngw).  Arithmetic in the reference's order."""
+    kpgx = np.asarray(kpgx, dtype=np.float64)
+    x, y, z = kpgx[0], kpgx[1], kpgx[2]
+    kpg = np.sqrt(x * x + y * y + z * z)                 # Basis::update_g: kpg_ = sqrt(kpg2_) (Basis.cc:733-737)
+    with np.errstate(divide="ignore"):
+        gi = np.where(kpg > 0.0, 1.0 / kpg, 0.0)
+    gspl = np.asarray(gspl, dtype=np.float64)
+    gcut = float(gspl[-1]) if gcut is None else float(gcut)
+    n = gspl.shape[0]
+    khi = np.clip(np.searchsorted(gspl, kpg, side="right"), 1, n - 1)   # first knot > x (the bisection of spline.cc:135-142)
+    klo = khi - 1
+    h = gspl[khi] - gspl[klo]
+    a = (gspl[khi] - kpg) / h
+    bb = (kpg - gspl[klo]) / h
+    pi = np.pi
+    fpi = 4.0 * pi
+    s14pi, s34pi, s54pi, s3 = np.sqrt(1.0 / fpi), np.sqrt(3.0 / fpi), np.sqrt(5.0 / fpi), np.sqrt(3.0)
+    s74pi, s2132pi, s3532pi, s1054pi = np.sqrt(7.0 / fpi), np.sqrt(21.0 / (32. * pi)), np.sqrt(35.0 / (32. * pi)), np.sqrt(105.0 / fpi)
+    gi2 = gi * gi
+    gi3 = gi2 * gi
+    xx, yy, zz = x * x * gi2, y * y * gi2, z * z * gi2
+    xy, yz, xz = x * y * gi2, y * z * gi2, x * z * gi2
+    ylm = {
+        (0, 0): s14pi,
+        (1, 0): s34pi * x * gi, (1, 1): s34pi * y * gi, (1, 2): s34pi * z * gi,
+        (2, 0): s54pi * 0.5 * (3.0 * zz - 1.0), (2, 1): s54pi * 0.5 * s3 * (xx - yy), (2, 2): s54pi * s3 * xy,
+        (2, 3): s54pi * s3 * yz, (2, 4): s54pi * s3 * xz,
+        (3, 0): s74pi * 0.5 * z * gi * (5.0 * zz - 3.0), (3, 1): s2132pi * x * gi * (5.0 * zz - 1.0),
+        (3, 2): s2132pi * y * gi * (5.0 * zz - 1.0), (3, 3): s1054pi * x * y * z * gi3,
+        (3, 4): s1054pi * 0.5 * z * gi * (xx - yy), (3, 5): s3532pi * x * gi * (xx - 3.0 * yy),
+        (3, 6): s3532pi * y * gi * (3.0 * xx - yy),
+    }
+    out = np.zeros((len(lproj), kpg.shape[0]))
+    vcache = {}
+    for ipr, (l, m, t) in enumerate(zip(lproj, mproj, tabproj)):
+        t = int(t)
+        if t not in vcache:
+            ya, y2a = np.asarray(vnlg[t]), np.asarray(vnlg_spl[t])
+            v = a * ya[klo] + bb * ya[khi] + h * h * (1.0 / 6.0) * ((a * a * a - a) * y2a[klo] + (bb * bb * bb - bb) * y2a[khi])
+            vcache[t] = np.where(kpg > gcut, 0.0, v)
+        out[ipr] = ylm[(int(l), int(m))] * vcache[t]
+    return out

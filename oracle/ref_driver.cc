@@ -44,6 +44,10 @@
 #include <cstdio>
 #include <cstring>
 #include <omp.h>
+// the driver needs tables that are private members of the reference's classes (NonLocalPotential: twnl, wt, lproj, iprojlm;
+// Species / Spline: the radial spline tables behind Species::dvnlg).  Every standard header is included above, so only the
+// reference's own classes are affected (access specifiers do not change the layout).
+#define private public
 #include <qball/Basis.h>
 #include <qball/FourierTransform.h>
 #include <qball/SlaterDet.h>
@@ -61,9 +65,6 @@
 #include <math/matrix.h>
 #include <functionals/LDAFunctional.h>
 #include <functionals/PBEFunctional.h>
-// the driver needs the projector tables (twnl, wt, lproj), which are private members of NonLocalPotential;
-// every header it includes is already included above, so only that one class is affected.
-#define private public
 #include <qball/NonLocalPotential.h>
 #undef private
 using namespace std;
@@ -355,6 +356,33 @@ int main(int argc, char** argv)
       dump(out + tag + ".wt.f64", nlp->npr[is] ? &nlp->wt[is][0] : 0, nlp->npr[is]*sizeof(double));
       dump(out + tag + ".twnl.f64", nlp->npr[is] ? &nlp->twnl[is][0] : 0, (size_t)nlp->npr[is]*ngw*sizeof(double));
       dump(out + tag + ".tau.f64", &tau[is][0], 3*nlp->na[is]*sizeof(double));
+      // what NonLocalPotential::update_twnl (NonLocalPotential.cc:261-1522) builds twnl FROM, for
+      // Kleinman-Bylander species (nquad == 0): per projector its m and its radial table (l, channel), the tables being the
+      // species' cubic splines behind Species::dvnlg (Species.cc:1492-1505; spline.cc:126-156)
+      Species* s = atoms.species_list[is];
+      int kb[4] = { nlp->nquad[is], s->ndft_, 0, 0 };
+      if (nlp->npr[is] > 0 && nlp->nquad[is] == 0) {
+        vector<int> mproj(nlp->npr[is], -1), tproj(nlp->npr[is], -1);
+        vector<double> ytab, y2tab;
+        int ntab = 0;
+        for (int l = 0; l <= nlp->lmax[is]; l++) {
+          if (l == nlp->lloc[is]) continue;
+          for (int ic = 0; ic < s->nchannels(); ic++) {
+            const Spline& sp = s->projectors_g_[l][ic];
+            ytab.insert(ytab.end(), sp.y_.begin(), sp.y_.end());
+            y2tab.insert(y2tab.end(), sp.y2_.begin(), sp.y2_.end());
+            for (int m = 0; m < 2*l+1; m++) { const int ipr = nlp->iprojlm[is][l][m][ic]; mproj[ipr] = m; tproj[ipr] = ntab; }
+            ntab++;
+          }
+        }
+        kb[2] = ntab;
+        dump(out + tag + ".kb_m.i32", &mproj[0], mproj.size()*sizeof(int));
+        dump(out + tag + ".kb_tab.i32", &tproj[0], tproj.size()*sizeof(int));
+        dump(out + tag + ".kb_gspl.f64", &s->gspl_[0], s->ndft_*sizeof(double));
+        dump(out + tag + ".kb_y.f64", &ytab[0], ytab.size()*sizeof(double));
+        dump(out + tag + ".kb_y2.f64", &y2tab[0], y2tab.size()*sizeof(double));
+      }
+      dump(out + tag + ".kb.i32", kb, sizeof kb);
     }
   }
 

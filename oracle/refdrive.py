@@ -118,6 +118,14 @@ def run_reference(case: Case, seed: int = 1, nocc: int | None = None, workdir: s
                        wt=_load(prefix, f"sp{i}.wt.f64", np.float64),
                        twnl=_load(prefix, f"sp{i}.twnl.f64", np.float64).reshape(npr, b["ngw"]),
                        tau=_load(prefix, f"sp{i}.tau.f64", np.float64).reshape(na, 3)))
+        kb = _load(prefix, f"sp{i}.kb.i32", np.int32)
+        sp[-1]["nquad"] = int(kb[0])
+        if npr > 0 and int(kb[0]) == 0:      # Kleinman-Bylander: the radial spline tables update_twnl builds twnl from (row a11)
+            ndft, ntab = int(kb[1]), int(kb[2])
+            sp[-1].update(mproj=_load(prefix, f"sp{i}.kb_m.i32", np.int32), tabproj=_load(prefix, f"sp{i}.kb_tab.i32", np.int32),
+                          gspl=_load(prefix, f"sp{i}.kb_gspl.f64", np.float64),
+                          vnlg=_load(prefix, f"sp{i}.kb_y.f64", np.float64).reshape(ntab, ndft),
+                          vnlg_spl=_load(prefix, f"sp{i}.kb_y2.f64", np.float64).reshape(ntab, ndft))
     r["species"] = sp
     if b["nsp"]:
         r["hnl"] = _load(prefix, "hnl.f64", np.complex128).reshape(case.nst, b["mloc"])

@@ -657,11 +657,18 @@ extern "C" int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lp
   s.na = na; s.npr = npr; s.M = na * npr; s.poff = nl->Mtot;
   s.lproj = nullptr; s.wt = nullptr; s.twnl = nullptr; s.tau = nullptr; s.ph = nullptr;
   if (s.M > 0) {
-    if (!lproj || !wt || !twnl || !tau) { set_error("qb200_nl_add_species: null table"); return QB200_EINVAL; }
+    if (!lproj || !wt || !tau) { set_error("qb200_nl_add_species: null table"); return QB200_EINVAL; }
     for (int i = 0; i < npr; i++) if (lproj[i] < 0 || lproj[i] > 3) { set_error("qb200_nl_add_species: l > 3 unsupported (as in the reference)"); return QB200_EUNSUPPORTED; }
     int rc;
-    if ((rc = nl_upload(nl, lproj, npr, &s.lproj)) || (rc = nl_upload(nl, wt, npr, &s.wt)) ||
-        (rc = nl_upload(nl, twnl, (size_t)npr * nl->ngw, &s.twnl)) || (rc = nl_upload(nl, tau, 3 * (size_t)na, &s.tau))) return rc;
+    if ((rc = nl_upload(nl, lproj, npr, &s.lproj)) || (rc = nl_upload(nl, wt, npr, &s.wt)) || (rc = nl_upload(nl, tau, 3 * (size_t)na, &s.tau))) return rc;
+    if (twnl) { if ((rc = nl_upload(nl, twnl, (size_t)npr * nl->ngw, &s.twnl))) return rc; }
+    else {                                     // no table yet: qb200_nl_update_twnl fills it on the device
+      void* t = nullptr;
+      QB_CUDA(cudaMalloc(&t, (size_t)npr * nl->ngw * sizeof(double)));
+      nl->owned.push_back(t);
+      QB_CUDA(cudaMemset(t, 0, (size_t)npr * nl->ngw * sizeof(double)));
+      s.twnl = (const double*)t;
+    }
   }
   nl->sp.push_back(s);
   nl->ph.push_back(nullptr);
@@ -793,6 +800,109 @@ extern "C" int qb200_nl_set_positions(qb200_nl* nl, int is, const double* tau)
   if (nl->sp[is].na > 0 && nl->sp[is].tau)
     QB_CUDA(cudaMemcpy(const_cast<double*>(nl->sp[is].tau), tau, 3 * (size_t)nl->sp[is].na * sizeof(double), cudaMemcpyHostToDevice));
   nl->ph_dirty = true; nl->W_valid = false; nl->Wg_valid = false;
+  return QB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ update_twnl (row a11)
+// NonLocalPotential::update_twnl for a Kleinman-Bylander species (NonLocalPotential.cc:261-1522, the twnl part):
+// twnl[ipr][ig] = Y_lm(k+G) v(|k+G|); v = the species' radial cubic spline (Species::dvnlg, Species.cc:1492-1505: zero beyond the
+// last knot of the FULL table, gcut; splintd, spline.cc:126-156), real spherical harmonics in the reference's order and
+// normalisation (l=0 :334, l=1 :466-470, l=2 :712-747, l=3 :1126-1140).  One thread per plane wave, every projector of the species.
+namespace qb200 {
+__global__ void __launch_bounds__(128) k_twnl_kb(int ngw, const double* __restrict__ kpgx, int npr, const int* __restrict__ lproj,
+                                                 const int* __restrict__ mproj, const int* __restrict__ tabproj, int nknots,
+                                                 const double* __restrict__ gspl, double gcut, const double* __restrict__ ya,
+                                                 const double* __restrict__ y2a, double* __restrict__ twnl)
+{
+  const int ig = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ig >= ngw) return;
+  const double x = kpgx[ig], y = kpgx[ngw + ig], z = kpgx[2 * (size_t)ngw + ig];
+  const double g = sqrt(x * x + y * y + z * z);
+  const double gi = g > 0.0 ? 1.0 / g : 0.0;                             // Basis.cc:737
+  int klo = 0, khi = nknots - 1;
+  while (khi - klo > 1) { const int k = (khi + klo) >> 1; if (gspl[k] > g) khi = k; else klo = k; }
+  const double h = gspl[khi] - gspl[klo], a = (gspl[khi] - g) / h, b = (g - gspl[klo]) / h;
+  const double a3 = a * a * a - a, b3 = b * b * b - b, h26 = h * h * (1.0 / 6.0);
+  const double pi = 3.14159265358979323846, fpi = 4.0 * pi;
+  const double s14pi = sqrt(1.0 / fpi), s34pi = sqrt(3.0 / fpi), s54pi = sqrt(5.0 / fpi), s3 = sqrt(3.0), s74pi = sqrt(7.0 / fpi),
+               s2132pi = sqrt(21.0 / (32. * pi)), s3532pi = sqrt(35.0 / (32. * pi)), s1054pi = sqrt(105.0 / fpi);
+  const double gi2 = gi * gi, gi3 = gi2 * gi;
+  const double xx = x * x * gi2, yy = y * y * gi2, zz = z * z * gi2, xy = x * y * gi2, yz = y * z * gi2, xz = x * z * gi2;
+  int tlast = -1;
+  double v = 0.0;
+  for (int ipr = 0; ipr < npr; ipr++) {
+    const int t = tabproj[ipr];
+    if (t != tlast) {
+      const double* Y = ya + (size_t)t * nknots;
+      const double* Y2 = y2a + (size_t)t * nknots;
+      v = g > gcut ? 0.0 : a * Y[klo] + b * Y[khi] + h26 * (a3 * Y2[klo] + b3 * Y2[khi]);
+      tlast = t;
+    }
+    double ylm = 0.0;
+    switch (lproj[ipr] * 8 + mproj[ipr]) {
+      case 0: ylm = s14pi; break;
+      case 8: ylm = s34pi * x * gi; break;
+      case 9: ylm = s34pi * y * gi; break;
+      case 10: ylm = s34pi * z * gi; break;
+      case 16: ylm = s54pi * 0.5 * (3.0 * zz - 1.0); break;
+      case 17: ylm = s54pi * 0.5 * s3 * (xx - yy); break;
+      case 18: ylm = s54pi * s3 * xy; break;
+      case 19: ylm = s54pi * s3 * yz; break;
+      case 20: ylm = s54pi * s3 * xz; break;
+      case 24: ylm = s74pi * 0.5 * z * gi * (5.0 * zz - 3.0); break;
+      case 25: ylm = s2132pi * x * gi * (5.0 * zz - 1.0); break;
+      case 26: ylm = s2132pi * y * gi * (5.0 * zz - 1.0); break;
+      case 27: ylm = s1054pi * x * y * z * gi3; break;
+      case 28: ylm = s1054pi * 0.5 * z * gi * (xx - yy); break;
+      case 29: ylm = s3532pi * x * gi * (xx - 3.0 * yy); break;
+      case 30: ylm = s3532pi * y * gi * (3.0 * xx - yy); break;
+    }
+    twnl[(size_t)ipr * ngw + ig] = ylm * v;
+  }
+}
+}  // namespace qb200
+
+extern "C" int qb200_nl_update_twnl(qb200_nl* nl, int is, const int* mproj, const int* tabproj, int ntab, int nknots, const double* gspl,
+                                    double gcut, const double* vnlg, const double* vnlg_spl)
+{
+  if (!nl || is < 0 || is >= (int)nl->sp.size() || !mproj || !tabproj || ntab < 1 || nknots < 2 || !gspl || !vnlg || !vnlg_spl) {
+    set_error("qb200_nl_update_twnl: bad argument"); return QB200_EINVAL;
+  }
+  const NlSpecies& S = nl->sp[is];
+  if (S.npr == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(nl->device));
+  std::vector<int> l(S.npr);
+  QB_CUDA(cudaMemcpy(l.data(), S.lproj, S.npr * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < S.npr; i++)
+    if (tabproj[i] < 0 || tabproj[i] >= ntab || mproj[i] < 0 || mproj[i] > 2 * l[i]) { set_error("qb200_nl_update_twnl: projector description out of range"); return QB200_EINVAL; }
+  for (int k = 1; k < nknots; k++) if (!(gspl[k] > gspl[k - 1])) { set_error("qb200_nl_update_twnl: knots must increase (spline.cc:145)"); return QB200_EINVAL; }
+  void *dm = nullptr, *dt = nullptr, *dg = nullptr, *dy = nullptr, *dy2 = nullptr;
+  auto fail = [&](int rc) { for (void* q : { dm, dt, dg, dy, dy2 }) if (q) cudaFree(q); return rc; };
+  const size_t tb = (size_t)ntab * nknots * sizeof(double);
+  if (cudaMalloc(&dm, S.npr * sizeof(int)) || cudaMalloc(&dt, S.npr * sizeof(int)) || cudaMalloc(&dg, nknots * sizeof(double)) ||
+      cudaMalloc(&dy, tb) || cudaMalloc(&dy2, tb)) { set_error("qb200_nl_update_twnl: out of device memory"); return fail(QB200_ENOMEM); }
+  cudaMemcpyAsync(dm, mproj, S.npr * sizeof(int), cudaMemcpyHostToDevice, nl->stream);
+  cudaMemcpyAsync(dt, tabproj, S.npr * sizeof(int), cudaMemcpyHostToDevice, nl->stream);
+  cudaMemcpyAsync(dg, gspl, nknots * sizeof(double), cudaMemcpyHostToDevice, nl->stream);
+  cudaMemcpyAsync(dy, vnlg, tb, cudaMemcpyHostToDevice, nl->stream);
+  cudaMemcpyAsync(dy2, vnlg_spl, tb, cudaMemcpyHostToDevice, nl->stream);
+  k_twnl_kb<<<(nl->ngw + 127) / 128, 128, 0, nl->stream>>>(nl->ngw, nl->kpgx, S.npr, S.lproj, (const int*)dm, (const int*)dt, nknots, (const double*)dg, gcut,
+                                                           (const double*)dy, (const double*)dy2, const_cast<double*>(S.twnl));
+  nl->launches++;
+  const cudaError_t e = cudaStreamSynchronize(nl->stream);
+  fail(0);
+  if (e != cudaSuccess) return cuda_fail(e, "qb200_nl_update_twnl", __FILE__, __LINE__);
+  nl->W_valid = false; nl->Wg_valid = false; nl->sym_dirty = true;      // every materialised anl is stale
+  return QB200_OK;
+}
+
+// the species' projector table as it sits on the device (npr * ngw doubles), for checks and for callers that keep a host copy
+extern "C" int qb200_nl_get_twnl(qb200_nl* nl, int is, double* twnl)
+{
+  if (!nl || is < 0 || is >= (int)nl->sp.size() || !twnl) { set_error("qb200_nl_get_twnl: bad argument"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(nl->device));
+  QB_CUDA(cudaStreamSynchronize(nl->stream));
+  if (nl->sp[is].npr > 0) QB_CUDA(cudaMemcpy(twnl, nl->sp[is].twnl, (size_t)nl->sp[is].npr * nl->ngw * sizeof(double), cudaMemcpyDefault));
   return QB200_OK;
 }
 

@@ -206,7 +206,7 @@ class NonLocalPotential:
         for s in species:
             lproj, lp = capi._iarr(s["lproj"])
             wt = np.ascontiguousarray(s["wt"], dtype=np.float64)
-            twnl = np.ascontiguousarray(s["twnl"], dtype=np.float64)
+            twnl = None if s.get("twnl") is None else np.ascontiguousarray(s["twnl"], dtype=np.float64)   # None: update_twnl() fills it
             tau = np.ascontiguousarray(s["tau"], dtype=np.float64)
             capi._check(L.qb200_nl_add_species(h, int(s["na"]), int(s["npr"]), lp, capi.ptr(wt), capi.ptr(twnl), capi.ptr(tau)),
                         "qb200_nl_add_species")
@@ -223,6 +223,24 @@ class NonLocalPotential:
     def set_positions(self, isp: int, tau):
         tau = np.ascontiguousarray(tau, dtype=np.float64)
         capi._check(self._L.qb200_nl_set_positions(self._h, isp, capi.ptr(tau)), "qb200_nl_set_positions")
+
+    def update_twnl(self, isp: int, mproj, tabproj, gspl, vnlg, vnlg_spl, gcut=None):
+        """NonLocalPotential::update_twnl for Kleinman-Bylander species `isp` on the device (NonLocalPotential.cc:261-1522, the twnl
+        part): mproj / tabproj = m and radial-table index of every projector, gspl / vnlg / vnlg_spl = knots, values and second
+        derivatives of the species' radial splines (Species::projectors_g_), gcut = last knot of the full table"""
+        m, mp = capi._iarr(mproj)
+        t, tp = capi._iarr(tabproj)
+        g = np.ascontiguousarray(gspl, dtype=np.float64)
+        y = np.ascontiguousarray(vnlg, dtype=np.float64)
+        y2 = np.ascontiguousarray(vnlg_spl, dtype=np.float64)
+        assert y.ndim == 2 and y.shape == y2.shape and y.shape[1] == g.shape[0]
+        capi._check(self._L.qb200_nl_update_twnl(self._h, int(isp), mp, tp, int(y.shape[0]), int(g.shape[0]), capi.ptr(g),
+                                                 float(g[-1] if gcut is None else gcut), capi.ptr(y), capi.ptr(y2)), "qb200_nl_update_twnl")
+
+    def get_twnl(self, isp: int, npr: int, ngw: int):
+        out = np.zeros((npr, ngw))
+        capi._check(self._L.qb200_nl_get_twnl(self._h, int(isp), capi.ptr(out)), "qb200_nl_get_twnl")
+        return out
 
     def energy(self, c, occ, compute_hpsi: bool, cp=None) -> float:
         """energy(sd, compute_hpsi, dsd, ...): returns enl; cp += V_nl psi when compute_hpsi."""
