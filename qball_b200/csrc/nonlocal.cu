@@ -188,12 +188,19 @@ __device__ __forceinline__ void warp_mma_stage(const double* __restrict__ As, co
 template <int IS_REAL>
 __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
                                                          int kper, const double2* __restrict__ c, size_t ldc, int nst,
-                                                         double* __restrict__ part, int Mp, int Mtot, int accumulate)
+                                                         double* __restrict__ part, int Mp, int Mtot, int accumulate,
+                                                         int tn = NL_TN)
 {
+  // tn (a multiple of 32, <= NL_TN): columns per CTA.  A block whose column count is not a multiple of 128 is cut into EQUAL
+  // tiles (192 columns: 2 x 96 instead of 128 + 64), so every CTA keeps the same number of warps busy
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int r0 = blockIdx.x * NL_TM, n0 = blockIdx.y * NL_TN;
+  // warp tile (wm, wn) of the 4 x 4: skewed so that the warps of one tile row AND those of one tile column sit on four different
+  // SM sub-partitions (warp % 4) -- when a row or a column of warp tiles has no work (padding), every FP64 tensor pipe keeps
+  // three busy warps instead of one pipe idling
+  const int wm = warp >> 2, wn = (warp + wm) & 3;
+  const int r0 = blockIdx.x * NL_TM, n0 = blockIdx.y * tn;
+  const int nend = min(nst, n0 + tn);
   const int kbeg = blockIdx.z * kper, kend = min(kbeg + kper, 2 * gcount);
   const int nstage = (kend - kbeg + NL_KSTEP - 1) / NL_KSTEP;
   // this thread's 4+4 copies per stage: row (tid>>4) + 32 i, 16-byte chunk (tid & 15) of the stage's 32 reals
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict_
         const int row = crow + 32 * i;
         const bool aok = kok && r0 + row < RW;
         nl_cp16(As + row * NL_PITCH + 2 * cch, W + (aok ? (size_t)(r0 + row) * WP + k : 0), aok);
-        const bool bok = kok && n0 + row < nst;
+        const bool bok = kok && n0 + row < nend;
         nl_cp16(Bs + row * NL_PITCH + 2 * cch, c + (bok ? (size_t)(n0 + row) * ldc + gbeg + (k >> 1) : 0), bok);
       }
     }
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict_
     const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_RK;
     // the last row tile is mostly padding when RW is not a multiple of 128 (MgO216: 540 rows, 28 of 128 in the fifth
     // tile): warps whose 32-row slab holds no row skip the tensor work, the others then own the pipe (warp-uniform test)
-    const bool work = r0 + wm * 32 < RW && n0 + wn * 32 < nst;
+    const bool work = r0 + wm * 32 < RW && n0 + wn * 32 < nend;
     if (work) warp_mma_stage<false, 0, 2>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
     issue(st + NL_NSTAGE - 1);
     if (work) warp_mma_stage<false, 2, NL_KSTEP / 4>(As, As + NL_TM * NL_PITCH, acc, lane, wm, wn);
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_fnl(const double* __restrict_
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
         const int p = IS_REAL ? row : (row >> 1);
         const int col = IS_REAL ? n : 2 * n + (row & 1);
-        if (p < Mtot && n < nst) {
+        if (p < Mtot && n < nend) {
           double* dst = part + ((size_t)blockIdx.z * ncols + col) * Mp + p;
           *dst = accumulate ? *dst + acc[i][j][e] : acc[i][j][e];
         }
@@ -321,12 +328,14 @@ template <int IS_REAL>
 __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict__ W, size_t WP, int RW, int gbeg, int gcount,
                                                           const double* __restrict__ fs, int FP, double2* __restrict__ cp,
                                                           size_t ldc, int nst, int overwrite, const int* __restrict__ ghalf = nullptr,
-                                                          const int* __restrict__ gminus = nullptr)
+                                                          const int* __restrict__ gminus = nullptr, int tn = NL_TN)
 {
   extern __shared__ __align__(16) double nl_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int gl0 = blockIdx.y * 64, n0 = blockIdx.x * NL_TN;
+  const int wm = warp >> 2, wn = (warp + wm) & 3;                // skewed as in k_fnl
+  const int gl0 = blockIdx.y * 64, n0 = blockIdx.x * tn;         // tn: equal column tiles, as in k_fnl
+  const int nend = min(nst, n0 + tn);
+  const bool work = n0 + wn * 32 < nend;                         // (warp-uniform) this warp's 32 columns hold a state
   const int nstage = (RW + NL_KSTEP - 1) / NL_KSTEP;
   auto issue = [&](int st) {
     if (st < nstage) {
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
         nl_cp16(As + kr * NL_PITCH_KR + 2 * gc, W + (aok ? (size_t)(k0 + kr) * WP + 2 * (size_t)(gl0 + gc) : 0), aok);
         // B: 128 states x 16 chunks of 2 reals
         const int nl = ci >> 4, ch = ci & 15;
-        const bool bok = n0 + nl < nst && k0 + 2 * ch < FP;
+        const bool bok = n0 + nl < nend && k0 + 2 * ch < FP;
         nl_cp16(Bs + nl * NL_PITCH + 2 * ch, fs + (bok ? (size_t)(n0 + nl) * FP + k0 + 2 * ch : 0), bok);
       }
     }
@@ -357,9 +366,9 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
     nl_cp_wait_group<NL_NSTAGE - 2>();
     __syncthreads();
     const double* As = nl_smem + (st % NL_NSTAGE) * NL_STAGE_KR;
-    warp_mma_stage<true, 0, 2>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
+    if (work) warp_mma_stage<true, 0, 2>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
     issue(st + NL_NSTAGE - 1);
-    warp_mma_stage<true, 2, NL_KSTEP / 4>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
+    if (work) warp_mma_stage<true, 2, NL_KSTEP / 4>(As, As + NL_KSTEP * NL_PITCH_KR, acc, lane, wm, wn);
   }
   const int r = lane >> 2, cq = lane & 3;
   if (IS_REAL == 2) {
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
         const double oth0 = __shfl_xor_sync(0xffffffffu, mine0, 4), oth1 = __shfl_xor_sync(0xffffffffu, mine1, 4);
         const double Pv = odd ? oth0 : mine0, Rv = odd ? oth1 : mine1, Tv = odd ? mine0 : oth0, Qv = odd ? mine1 : oth1;
         const int n2 = n0 + wn * 32 + j * 8 + 2 * cq;          // column pair (2n, 2n+1) of state n = n2 / 2
-        if (gl < gcount && n2 < nst && !(odd && gl == 0)) {   // G = 0 (gl == 0) has no partner
+        if (gl < gcount && n2 < nend && !(odd && gl == 0)) {  // G = 0 (gl == 0) has no partner
           double2* dst = cp + (size_t)(n2 >> 1) * ldc + gdst;
           double2 v = overwrite ? make_double2(0.0, 0.0) : *dst;
           if (odd) { v.x += Pv + Qv; v.y += Rv - Tv; } else { v.x += Pv - Qv; v.y += Rv + Tv; }
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(NL_THREADS, 1) k_back(const double* __restrict
         const int n = n0 + wn * 32 + j * 8 + 2 * cq + e;
         double v = acc[i][j][e];
         if (IS_REAL == 1 && g == 0 && (row & 1) == 0) v *= 2.0;    // W holds half of Re anl at G=0 (k_anl_gen)
-        if (gl < gcount && n < nst) {
+        if (gl < gcount && n < nend) {
           double* dst = cpd + 2 * ((size_t)n * ldc + g) + (row & 1);
           *dst = overwrite ? v : *dst + v;
         }
@@ -613,9 +622,11 @@ extern "C" int qb200_nl_create(qb200_nl** out, int device, int ngw, int is_real,
   nl->W = nullptr; nl->W_cap = 0; nl->W_valid = false; nl->nchunks_last = 0;
   nl->anl_budget = 8ll << 30;
   if (const char* e = getenv("QB200_ANL_BYTES")) nl->anl_budget = std::max(1ll << 20, atoll(e));
-  // off by default: like the reference (comp_anl in every energy call) each call regenerates anl (~1 % of the call)
-  nl->cache_anl = false;
-  if (const char* e = getenv("QB200_ANL_CACHE")) nl->cache_anl = e[0] == '1';
+  // a whole-sphere anl block stays valid until positions, tables, lattice or workspace change (each of those calls
+  // invalidates it): the next energy call reuses it instead of regenerating it (QB200_ANL_CACHE=0: regenerate every call,
+  // as the reference's comp_anl does)
+  nl->cache_anl = true;
+  if (const char* e = getenv("QB200_ANL_CACHE")) nl->cache_anl = e[0] != '0';
   nl->use3m = !is_real;
   if (const char* e = getenv("QB200_NL_3M")) if (e[0] == '0') nl->use3m = false;
   nl->tile3m = 1; nl->W_WP = 0;
@@ -1003,9 +1014,13 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
     nl->Wg_valid = true;
   }
   // split-K of k_fnl<1>: 128 x 128 tiles, one CTA per SM
-  const int mt = (Mtot + NL_TM - 1) / NL_TM, nt = (nst2 + NL_TN - 1) / NL_TN;
+  // equal column tiles: 2*nst = 192 real columns run as 2 x 96, not 128 + 64 (QB200_NL_TN=0: full tiles and a remainder)
+  int nt = (nst2 + NL_TN - 1) / NL_TN, tn = NL_TN;
+  { const char* e = getenv("QB200_NL_TN"); if (!(e && atoi(e) == 0)) { tn = std::min(NL_TN, ((nst2 + nt - 1) / nt + 31) / 32 * 32); nt = (nst2 + tn - 1) / tn; } }
+  const int mt = (Mtot + NL_TM - 1) / NL_TM;
   int ksplit = 1;
-  {
+  if (const char* e = getenv("QB200_NL_KSPLIT")) ksplit = std::max(1, std::min(64, atoi(e)));
+  else {
     const int maxk = std::max(1, nhalf / 256);
     double best = -1.0;
     for (int k = 1; k <= std::min(maxk, 64); k++) {
@@ -1027,7 +1042,7 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
   NL_LAUNCH_CHECK(nl);
   int kper = (2 * nhalf + ksplit - 1) / ksplit;
   kper = (kper + NL_KSTEP - 1) / NL_KSTEP * NL_KSTEP;
-  k_fnl<1><<<dim3(mt, nt, ksplit), NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, kper, (const double2*)nl->Ug, ldu, nst2, nl->part, Mp, Mtot, 0);
+  k_fnl<1><<<dim3(mt, nt, ksplit), NL_THREADS, FNL_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, kper, (const double2*)nl->Ug, ldu, nst2, nl->part, Mp, Mtot, 0, tn);
   prof_end(nl->stream);
   NL_LAUNCH_CHECK(nl);
   prof_begin(4, nl->stream);
@@ -1039,7 +1054,7 @@ static int nl_energy_gamma_half(qb200_nl* nl, int ldc, int nst, const double* c,
   if (!compute_hpsi) return QB200_OK;
   prof_begin(5, nl->stream);
   k_back<2><<<dim3(nt, (nhalf + 63) / 64), NL_THREADS, BK_SMEM_BYTES, nl->stream>>>(nl->Wg, WP, Mtot, 0, nhalf, nl->fs, Mp, (double2*)cp, ldc, nst2, overwrite,
-                                                                                    nl->ghalf, nl->gminus);
+                                                                                    nl->ghalf, nl->gminus, tn);
   prof_end(nl->stream);
   NL_LAUNCH_CHECK(nl);
   return QB200_OK;

@@ -1036,7 +1036,31 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
   // SlaterDet.cc:858-885 applies to the density: rho += fac1 Re^2 + fac2 Im^2), the odd last state alone (:886-903).
   // fac_dev then holds [first weights | second weights | the odd state's weight].  QB200_DENSITY_PAIRS=0: one state per transform.
   const bool pairs_on = !(getenv("QB200_DENSITY_PAIRS") && atoi(getenv("QB200_DENSITY_PAIRS")) == 0);
-  const int npair = (d.is_real && pairs_on) ? nst / 2 : 0;
+  int npair = (d.is_real && pairs_on) ? nst / 2 : 0;
+  if (npair) {
+    // The packing needs what the reference guarantees for real bases: Im c_n(G=0) = 0 (SlaterDet.cc:2776-2779).  A state whose
+    // G = 0 coefficient carries an imaginary part would leak it into its partner's density at first order, while the
+    // one-state transform the reference runs (:906-924) sees it at second order only -- such a block takes the reference's branch.
+    bool heads_real = true;
+    if (chost) {
+      for (int n = 0; n < nst && heads_real; n++) {
+        const double* col = c + 2 * (size_t)n * ldc;
+        double ref = 0.0;
+        for (int i = 0; i < std::min(64, d.ngw); i++) ref = std::max(ref, std::max(std::fabs(col[2 * i]), std::fabs(col[2 * i + 1])));
+        if (std::fabs(col[1]) > 1e-13 * ref) heads_real = false;
+      }
+    } else {
+      int* flag = reinterpret_cast<int*>(p->fac_dev);          // (fac_dev is filled after this check)
+      int h = 0;
+      QB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), p->stream));
+      k_gamma_heads<<<(nst + 127) / 128, 128, 0, p->stream>>>((const cplx*)c, (size_t)ldc, d.ngw, nst, flag);
+      QB_LAUNCH_CHECK(p);
+      QB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      QB_CUDA(cudaStreamSynchronize(p->stream));
+      heads_real = h == 0;
+    }
+    if (!heads_real) npair = 0;
+  }
   if (npair && !is_device_ptr(fac)) {
     p->fac_host.resize(nst);
     for (int u = 0; u < npair; u++) { p->fac_host[u] = fac[2 * u]; p->fac_host[npair + u] = fac[2 * u + 1]; }

@@ -259,6 +259,18 @@ __global__ void __launch_bounds__(256, 2) k_ycols(const __grid_constant__ DevPla
   }
 }
 
+// flag[0] |= 1 when some state's G = 0 coefficient (row 0 of its column) has an imaginary part that is not rounding noise
+// next to the largest of the column's first rows: |Im c_n(0)| > 1e-13 max_{i < 64} |c_n(i)|_inf.  One thread per state.
+__global__ void k_gamma_heads(const cplx* __restrict__ c, size_t ldc, int ngw, int nst, int* __restrict__ flag)
+{
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nst) return;
+  const cplx* col = c + (size_t)n * ldc;
+  double ref = 0.0;
+  for (int i = 0; i < min(64, ngw); i++) ref = fmax(ref, fmax(fabs(col[i].x), fabs(col[i].y)));
+  if (fabs(col[0].y) > 1e-13 * ref) atomicOr(flag, 1);
+}
+
 // rho[i] += sum_g part[g][i], fixed order
 __global__ void k_rho_reduce(double* __restrict__ rho, const double* __restrict__ part, size_t N, int ngroups)
 {

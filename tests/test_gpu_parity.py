@@ -409,18 +409,22 @@ def test_cuda_vs_oracle_si54p_shape_gamma_real(compiled, monkeypatch):
     assert relerr(rho.cpu().numpy(), rho_want) < TOL
 
 
-@pytest.mark.parametrize("nst,host", [(9, False), (8, True), (1, False)])
-def test_cuda_density_of_real_states_in_pairs(nst, host, monkeypatch):
+@pytest.mark.parametrize("nst,host,imag_head", [(9, False, False), (8, True, False), (1, False, False), (6, False, True), (6, True, True)])
+def test_cuda_density_of_real_states_in_pairs(nst, host, imag_head, monkeypatch):
     """Gamma-point real bases: the density transforms two states at once as psi_1 + i psi_2 and adds fac1 Re^2 + fac2 Im^2
     (the form of SlaterDet.cc:858-885; the odd last state alone, :886-903).  Checked against the oracle's one-state-at-a-time
     sum (SlaterDet.cc:906-924, the branch the reference runs) and against this library with QB200_DENSITY_PAIRS=0, with pairs
-    whose first, second or both weights are zero, several batches of pair units, device and host pointers."""
+    whose first, second or both weights are zero, several batches of pair units, device and host pointers.  imag_head: a state
+    whose G = 0 coefficient has an imaginary part (outside the reference's invariant for real bases, SlaterDet.cc:2776-2779)
+    would leak it into its partner at first order -- such a block must take the one-state branch and still match the oracle."""
     cell, ecut = (11, 0, 0, 0, 12, 0, 0, 0, 13), 6.0
     b = P.make_basis(cell, ecut, (0, 0, 0), False)
     grid = P.density_grid(cell, ecut)
     assert b["is_real"]
     ldc = b["ngw"] + 2
     c = R.synth_coefficients(b["kpg2"], ecut, nst, ldc, True, seed=71)
+    if imag_head:
+        c[3, 0] += 1e-3j * abs(c[3, 0])
     occ = np.array([2.0, 0.0, 0.0, 1.5, 0.0, 0.0, 1.0, 2.0, 0.75])[:nst]
     oft = P.FT(b, *grid)
     rho_want = oft.compute_density(c, occ / b["omega"], np.full(oft.N, 0.5))
