@@ -773,7 +773,10 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
                 la2 = H.SubspaceLA(b, device=local_rank, stream=stream)
                 with torch.cuda.stream(stream):
                     cw, cl, dl = c.clone(), torch.zeros_like(c), torch.zeros_like(c)
-                    la2.gram(cw) if world == 1 else None
+                    if world == 1:
+                        la2.gram(cw)
+                    else:                     # band-sharded SlaterDet::gram: overlap columns -> sum over ranks -> replicated Cholesky
+                        la2.gram_sharded(comm, PAR.allgather_states(cw, world * nst), rank * nst, nst, cw)
                 prec = np.where(0.5 * b["kpg2"] < 4.0, 0.5 / 4.0, 0.5 / np.maximum(0.5 * b["kpg2"], 1e-300))   # Preconditioner.cc:47-90, ecutprec 8 Ry
                 # the density basis (k = 0, 4 ecut: ChargeDensity.cc:77-81) and Gaussian stand-ins for the ionic tables
                 from qball_b200 import basis as BB
@@ -813,6 +816,8 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
                         t[5].record(stream)
                         if world == 1:
                             la2.gram(cw)
+                        else:
+                            la2.gram_sharded(comm, PAR.allgather_states(cw, world * nst), rank * nst, nst, cw)
                         t[6].record(stream)
                     stream.synchronize()
                     it[0] += 1
@@ -832,7 +837,9 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
                             "what": "one electronic iteration of BOSampleStepper / PSDA with NOTHING but scalars crossing PCIe: density + rho(G) "
                                     "(qb200_compute_density, qb200_density_finish) -> v(r) (qb200_update_vhxc, LDA) -> H psi + E_kin -> residual -> "
                                     "preconditioned Anderson update (qb200_psda_update)"
-                                    + (" -> SlaterDet::gram" if world == 1 else " (band-sharded: all-gather of c for the residual; the distributed Cholesky is not built, gram skipped)")}
+                                    " -> SlaterDet::gram"
+                                    + ("" if world == 1 else " (band-sharded: NCCL all-gather of c for the residual and for gram; gram = overlap columns per rank, "
+                                       "qb200_allreduce_rho of the overlap, Cholesky replicated on every rank, own columns of c L^-H: qb200_gram_sharded)")}
                 # Wavefunction::diag of the block (eigenvalues + rotation), timed once
                 if world == 1:
                     with torch.cuda.stream(stream):

@@ -264,6 +264,17 @@ int qb200_residual(qb200_la* la, int ldc, int nall, const double* c, int nst, do
  * c: ldc x nst (all states on this rank), orthonormalised in place.  info (may be NULL): LAPACK potrf's info; a
  * non-positive-definite overlap returns QB200_EINVAL with *info = order of the failing minor and leaves c unchanged. */
 int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info);
+/* SlaterDet::gram with the states sharded over ranks (the reference's distributed herk / potrf / trsm, SlaterDet.cc:1043-1143,
+ * restated for band sharding with nprow = 1).  c_all: the gathered ldc x nall block (as for qb200_residual); this rank owns the
+ * columns [first, first + nst); c_local (ldc x nst; may be those columns of c_all) receives the orthonormalised states.
+ *   qb200_gram_overlap: S (nall x nall complex, column-major) = 0 except this rank's columns S[:, first..] = c_all^H c_local
+ *   (sum S over the ranks: every entry has one non-zero contributor)
+ *   qb200_gram_apply  : Cholesky S = L L^H (replicated on every rank), c_local <- c_all (L^-H)[:, first..]
+ *   qb200_gram_sharded: the three steps with the sum done by qb200_allreduce_rho on `comm` (NULL allowed when nst == nall)
+ * Device pointers only.  info as for qb200_gram. */
+int qb200_gram_overlap(qb200_la* la, int ldc, int nall, const double* c_all, int first, int nst, double* S);
+int qb200_gram_apply(qb200_la* la, int ldc, int nall, const double* c_all, const double* S, int first, int nst, double* c_local, int* info);
+int qb200_gram_sharded(qb200_la* la, struct qb200_comm* comm, int ldc, int nall, const double* c_all, int first, int nst, double* c_local, int* info);
 
 /* ---- Wavefunction::diag(dwf, eigvec), one (spin, k-point), norm-conserving                     Wavefunction.cc:1510-1715
  *      h = c^H (H c) (real bases: 2 c^T (H c) minus the rank-1 term of real row 0, :1538-1539); w = eigenvalues of h from its

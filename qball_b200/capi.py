@@ -80,6 +80,9 @@ def load():
     L.qb200_la_query.restype = ll
     L.qb200_residual.argtypes = [vp, i, i, dp, i, dp, dp]
     L.qb200_gram.argtypes = [vp, i, i, dp, ip]
+    L.qb200_gram_overlap.argtypes = [vp, i, i, dp, i, i, dp]
+    L.qb200_gram_apply.argtypes = [vp, i, i, dp, dp, i, i, dp, ip]
+    L.qb200_gram_sharded.argtypes = [vp, vp, i, i, dp, i, i, dp, ip]
     L.qb200_ekin_sums.argtypes = [vp, i, i, dp, dp, dp, dp, dp, dp, dp, dp]
     L.qb200_ekin_sums.restype = i
     L.qb200_comm_get_unique_id.argtypes = [vp]
@@ -105,7 +108,7 @@ def load():
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_density_finish", "qb200_nl_create", "qb200_nl_add_species",
                  "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_set_workspace", "qb200_nl_destroy", "qb200_nl_energy", "qb200_nl_betapsi", "qb200_nl_add_beta", "qb200_nl_spsi", "qb200_nl_update_twnl", "qb200_nl_get_twnl", "qb200_nl_us_set_density_basis", "qb200_nl_us_set_species", "qb200_nl_us_energy", "qb200_nl_us_augment_density", "qb200_hpsi", "qb200_exponential",
-                 "qb200_compute_current", "qb200_la_create", "qb200_la_set_stream", "qb200_la_set_workspace", "qb200_la_destroy", "qb200_residual", "qb200_gram"):
+                 "qb200_compute_current", "qb200_la_create", "qb200_la_set_stream", "qb200_la_set_workspace", "qb200_la_destroy", "qb200_residual", "qb200_gram", "qb200_gram_overlap", "qb200_gram_apply", "qb200_gram_sharded"):
         getattr(L, name).restype = i
     _lib = L
     return L

@@ -215,6 +215,22 @@ __global__ void __launch_bounds__(256) k_gram_operand(const double2* __restrict_
   }
 }
 
+// the same for the columns [first, first + ncol) of T only (band-sharded gram: this rank's states)
+template <int IS_REAL>
+__global__ void __launch_bounds__(256) k_gram_operand_cols(const double2* __restrict__ X, int n, int first, int ncol, double* __restrict__ fs, int FP)
+{
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)ncol * n) return;
+  const int cl = (int)(idx / n), m = (int)(idx % n), col = first + cl;
+  double2 t = make_double2(0.0, 0.0);
+  if (m <= col) { const double2 x = X[(size_t)m * n + col]; t = make_double2(x.x, -x.y); }
+  if (IS_REAL) fs[(size_t)cl * FP + m] = t.x;
+  else {
+    double* o = fs + (size_t)cl * FP + (m >> 3) * 24 + (m & 7);
+    o[0] = t.x; o[8] = t.y; o[16] = t.x + t.y;
+  }
+}
+
 }  // namespace qb200
 
 using namespace qb200;
@@ -227,6 +243,7 @@ struct qb200_la {
   double *W, *part, *fs; size_t W_cap, part_cap, fs_cap;
   size_t W_WP;                                  // pitch W was last zero-filled for (3M pad rows must be zero)
   double *S, *X, *Dinv; size_t S_cap, X_cap, Dinv_cap;
+  double* Ssh; size_t Ssh_cap;                  // band-sharded gram: the overlap columns before / after the sum over ranks
   double *st_c, *st_x, *st_a; size_t st_c_cap, st_x_cap, st_a_cap;
   int* info_dev;
   long long launches;
@@ -247,6 +264,7 @@ extern "C" int qb200_la_create(qb200_la** out, int device, int ngw, int is_real)
   la->budget = 8ll << 30;
   if (const char* e = getenv("QB200_LA_BYTES")) la->budget = std::max(1ll << 20, atoll(e));
   la->W = la->part = la->fs = la->S = la->X = la->Dinv = la->st_c = la->st_x = la->st_a = nullptr;
+  la->Ssh = nullptr; la->Ssh_cap = 0;
   la->W_cap = la->part_cap = la->fs_cap = la->S_cap = la->X_cap = la->Dinv_cap = la->st_c_cap = la->st_x_cap = la->st_a_cap = 0;
   la->W_WP = 0; la->launches = 0; la->nchunks_last = 0; la->info_dev = nullptr;
   cudaDeviceProp prop;
@@ -279,7 +297,7 @@ extern "C" int qb200_la_destroy(qb200_la* la)
 {
   if (!la) return QB200_OK;
   cudaSetDevice(la->device);
-  for (double* p : { la->W, la->part, la->fs, la->S, la->X, la->Dinv, la->st_c, la->st_x, la->st_a }) if (p) cudaFree(p);
+  for (double* p : { la->W, la->part, la->fs, la->S, la->X, la->Dinv, la->Ssh, la->st_c, la->st_x, la->st_a }) if (p) cudaFree(p);
   if (la->info_dev) cudaFree(la->info_dev);
   delete la;
   return QB200_OK;
@@ -432,6 +450,29 @@ static int la_residual_dev(qb200_la* la, int ldc, int nall, const double* c, int
   return QB200_OK;
 }
 
+// la->S (n x n, lower triangle read) = L L^H, blocked right-looking, Dinv[k] = L_kk^-1; then la->X = L^-1
+static int la_factor(qb200_la* la, int n)
+{
+  const int nblkd = (n + LA_NB - 1) / LA_NB;
+  double2* S = (double2*)la->S; double2* Dinv = (double2*)la->Dinv;
+  const dim3 tb(LA_NB, LA_NB);
+  for (int k = 0; k < nblkd; k++) {
+    const int k0 = k * LA_NB;
+    k_potrf_diag<<<1, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB, la->info_dev);
+    LA_LAUNCH_CHECK(la);
+    const int nt = nblkd - k - 1;
+    if (nt > 0) {
+      k_potrf_panel<<<nt, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB);
+      LA_LAUNCH_CHECK(la);
+      k_potrf_trail<<<dim3(nt, nt), tb, 0, la->stream>>>(S, n, k0);
+      LA_LAUNCH_CHECK(la);
+    }
+  }
+  k_trtri_cols<<<nblkd, tb, 0, la->stream>>>(S, n, Dinv, (double2*)la->X);
+  LA_LAUNCH_CHECK(la);
+  return QB200_OK;
+}
+
 static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
 {
   int rc;
@@ -462,24 +503,7 @@ static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
   if (la->is_real) k_la_finish<1, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)c, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
   else k_la_finish<0, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, n, n, g.ksplit, (const double2*)c, (const double2*)c, ldc, nullptr, nullptr, 0, (double2*)la->S, n);
   LA_LAUNCH_CHECK(la);
-  // S = L L^H (lower), blocked right-looking; Dinv[k] = L_kk^-1
-  double2* S = (double2*)la->S; double2* Dinv = (double2*)la->Dinv;
-  const dim3 tb(LA_NB, LA_NB);
-  for (int k = 0; k < nblkd; k++) {
-    const int k0 = k * LA_NB;
-    k_potrf_diag<<<1, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB, la->info_dev);
-    LA_LAUNCH_CHECK(la);
-    const int nt = nblkd - k - 1;
-    if (nt > 0) {
-      k_potrf_panel<<<nt, tb, 0, la->stream>>>(S, n, k0, Dinv + (size_t)k * LA_NB * LA_NB);
-      LA_LAUNCH_CHECK(la);
-      k_potrf_trail<<<dim3(nt, nt), tb, 0, la->stream>>>(S, n, k0);
-      LA_LAUNCH_CHECK(la);
-    }
-  }
-  // X = L^-1, then the GEMM operand T = L^-H
-  k_trtri_cols<<<nblkd, tb, 0, la->stream>>>(S, n, Dinv, (double2*)la->X);
-  LA_LAUNCH_CHECK(la);
+  if ((rc = la_factor(la, n))) return rc;
   if (la->is_real) k_gram_operand<1><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, la->fs, g.FP);
   else k_gram_operand<0><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, la->fs, g.FP);
   prof_end(la->stream);
@@ -548,6 +572,103 @@ extern "C" int qb200_gram(qb200_la* la, int ldc, int nst, double* c, int* info)
     QB_CUDA(cudaStreamSynchronize(la->stream));
   }
   return QB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ band-sharded gram
+// SlaterDet::gram with the states distributed over process columns (the reference's pzherk / pzpotrf / pztrsm on the
+// square context, SlaterDet.cc:1043-1143), restated for band sharding with nprow = 1:
+//   (1) overlap : this rank's columns S[:, first .. first+nst) = c_all^H c_local        (1/P of the herk)
+//   (2) sum of the column blocks over the ranks (every other entry of a rank's S is zero: the sum is a gather)
+//   (3) apply   : Cholesky S = L L^H and L^-1 on every rank (replicated, as cheap as on one GPU), then
+//                 c_local <- c_all T[:, first .. first+nst), T = L^-H                  (1/P of the trsm)
+// c_all: the gathered ldc x nall block (as for qb200_residual), device pointer; c_local: ldc x nst, device pointer, may be
+// the rank's own columns inside c_all.
+static int la_gram_check(qb200_la* la, const char* who, int ldc, int nall, const double* c_all, int first, int nst)
+{
+  if (!la || !c_all || nall < 1 || nst < 0 || first < 0 || first + nst > nall || ldc < la->ngw) { set_error(std::string(who) + ": bad argument"); return QB200_EINVAL; }
+  if (!is_device_ptr(c_all)) { set_error(std::string(who) + ": device pointers only (the gathered block lives on the device)"); return QB200_EINVAL; }
+  return QB200_OK;
+}
+
+extern "C" int qb200_gram_overlap(qb200_la* la, int ldc, int nall, const double* c_all, int first, int nst, double* S)
+{
+  int rc;
+  if ((rc = la_gram_check(la, "qb200_gram_overlap", ldc, nall, c_all, first, nst))) return rc;
+  if (!S || !is_device_ptr(S)) { set_error("qb200_gram_overlap: S must be a device pointer (nall x nall complex)"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(la->device));
+  QB_CUDA(cudaMemsetAsync(S, 0, 2 * (size_t)nall * nall * sizeof(double), la->stream));
+  if (nst == 0) return QB200_OK;
+  const LaGeom g = la_geometry(la, nall, nst, false, ldc);
+  la->nchunks_last = g.nchunks;
+  if ((rc = la_prepare_W(la, g))) return rc;
+  const int ncols = la->is_real ? nst : 2 * nst;
+  if ((rc = nl_ensure(&la->part, &la->part_cap, (size_t)g.ksplit * ncols * g.Mp))) return rc;
+  const double* x = c_all + 2 * (size_t)first * ldc;
+  for (int ch = 0; ch < g.nchunks; ch++) {
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, la->ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = la_pack(la, g, c_all, ldc, gbeg, gcount, gpad))) return rc;
+    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, x, ldc, nst, ch > 0))) return rc;
+  }
+  const size_t total = (size_t)nst * nall;
+  const int nblk = (int)((total + 255) / 256);
+  double2* Sc = (double2*)S + (size_t)first * nall;
+  if (la->is_real) k_la_finish<1, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, nall, nst, g.ksplit, (const double2*)c_all, (const double2*)x, ldc, nullptr, nullptr, 0, Sc, nall);
+  else k_la_finish<0, 1><<<nblk, 256, 0, la->stream>>>(la->part, g.Mp, nall, nst, g.ksplit, (const double2*)c_all, (const double2*)x, ldc, nullptr, nullptr, 0, Sc, nall);
+  LA_LAUNCH_CHECK(la);
+  return QB200_OK;
+}
+
+extern "C" int qb200_gram_apply(qb200_la* la, int ldc, int nall, const double* c_all, const double* S, int first, int nst, double* c_local, int* info)
+{
+  if (info) *info = 0;
+  int rc;
+  if ((rc = la_gram_check(la, "qb200_gram_apply", ldc, nall, c_all, first, nst))) return rc;
+  if (!S || !is_device_ptr(S) || (nst > 0 && (!c_local || !is_device_ptr(c_local)))) { set_error("qb200_gram_apply: device pointers only"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(la->device));
+  const int n = nall, nblkd = (n + LA_NB - 1) / LA_NB;
+  const LaGeom g = la_geometry(la, nall, std::max(nst, 1), false, ldc);
+  la->nchunks_last = g.nchunks;
+  if ((rc = la_prepare_W(la, g))) return rc;
+  if ((rc = nl_ensure(&la->fs, &la->fs_cap, (size_t)std::max(nst, 1) * g.FP))) return rc;
+  if ((rc = nl_ensure(&la->S, &la->S_cap, 2 * (size_t)n * n))) return rc;
+  if ((rc = nl_ensure(&la->X, &la->X_cap, 2 * (size_t)n * n))) return rc;
+  if ((rc = nl_ensure(&la->Dinv, &la->Dinv_cap, 2 * (size_t)nblkd * LA_NB * LA_NB))) return rc;
+  QB_CUDA(cudaMemcpyAsync(la->S, S, 2 * (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, la->stream));   // the factorisation is in place
+  QB_CUDA(cudaMemsetAsync(la->fs, 0, (size_t)std::max(nst, 1) * g.FP * sizeof(double), la->stream));
+  QB_CUDA(cudaMemsetAsync(la->X, 0, 2 * (size_t)n * n * sizeof(double), la->stream));
+  QB_CUDA(cudaMemsetAsync(la->info_dev, 0, sizeof(int), la->stream));
+  if ((rc = la_factor(la, n))) return rc;
+  if (nst > 0) {
+    const int nblk = (int)(((size_t)nst * n + 255) / 256);
+    if (la->is_real) k_gram_operand_cols<1><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, first, nst, la->fs, g.FP);
+    else k_gram_operand_cols<0><<<nblk, 256, 0, la->stream>>>((const double2*)la->X, n, first, nst, la->fs, g.FP);
+    LA_LAUNCH_CHECK(la);
+  }
+  int h_info = 0;
+  QB_CUDA(cudaMemcpyAsync(&h_info, la->info_dev, sizeof(int), cudaMemcpyDeviceToHost, la->stream));
+  QB_CUDA(cudaStreamSynchronize(la->stream));
+  if (info) *info = h_info;
+  if (h_info != 0) { set_error("qb200_gram_apply: overlap matrix not positive definite (potrf info > 0)"); return QB200_EINVAL; }
+  for (int i = 0; i < g.nchunks && nst > 0; i++) {
+    const int ch = g.nchunks - 1 - i;
+    const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, la->ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
+    if ((rc = la_pack(la, g, c_all, ldc, gbeg, gcount, gpad))) return rc;     // (a chunk's rows are packed before c_local, which may alias them, is written)
+    if ((rc = la_back(la, g, la->W, gbeg, gcount, c_local, ldc, nst, 1))) return rc;
+  }
+  return QB200_OK;
+}
+
+extern "C" int qb200_gram_sharded(qb200_la* la, qb200_comm* comm, int ldc, int nall, const double* c_all, int first, int nst, double* c_local, int* info)
+{
+  if (info) *info = 0;
+  int rc;
+  if ((rc = la_gram_check(la, "qb200_gram_sharded", ldc, nall, c_all, first, nst))) return rc;
+  if (!comm && nst != nall) { set_error("qb200_gram_sharded: a communicator is needed when the rank does not hold every state"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(la->device));
+  if ((rc = nl_ensure(&la->Ssh, &la->Ssh_cap, 2 * (size_t)nall * nall))) return rc;
+  if ((rc = qb200_gram_overlap(la, ldc, nall, c_all, first, nst, la->Ssh))) return rc;
+  if (comm && (rc = qb200_allreduce_rho(comm, la->Ssh, 2ll * nall * nall, (void*)la->stream))) return rc;
+  return qb200_gram_apply(la, ldc, nall, c_all, la->Ssh, first, nst, c_local, info);
 }
 
 // ------------------------------------------------------------------------------------------------ PSDA wavefunction update

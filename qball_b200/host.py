@@ -418,6 +418,29 @@ class SubspaceLA:
         capi._check(self._L.qb200_gram(self._h, ldc, nst, capi.ptr(c), C.byref(info)), "qb200_gram")
         return c
 
+    def gram_overlap(self, c_all, first: int, nst: int, S):
+        """band-sharded gram, step 1: S (nall x nall complex, device) = 0 but this rank's columns c_all^H c_all[first:first+nst]"""
+        nall, ldc = _block_dims(c_all)
+        capi._check(self._L.qb200_gram_overlap(self._h, ldc, nall, capi.ptr(c_all), int(first), int(nst), capi.ptr(S)), "qb200_gram_overlap")
+        return S
+
+    def gram_apply(self, c_all, S, first: int, nst: int, c_local):
+        """band-sharded gram, step 3: c_local <- c_all (L^-H)[:, first:first+nst] with the summed overlap S = L L^H"""
+        nall, ldc = _block_dims(c_all)
+        info = C.c_int(0)
+        capi._check(self._L.qb200_gram_apply(self._h, ldc, nall, capi.ptr(c_all), capi.ptr(S), int(first), int(nst), capi.ptr(c_local),
+                                             C.byref(info)), "qb200_gram_apply")
+        return c_local
+
+    def gram_sharded(self, comm, c_all, first: int, nst: int, c_local):
+        """SlaterDet::gram over band-sharded states: overlap columns -> sum over the ranks of `comm` -> replicated Cholesky -> this
+        rank's orthonormalised columns (SlaterDet.cc:1043-1143 with the states distributed over process columns)"""
+        nall, ldc = _block_dims(c_all)
+        info = C.c_int(0)
+        capi._check(self._L.qb200_gram_sharded(self._h, comm._h if comm is not None else None, ldc, nall, capi.ptr(c_all), int(first),
+                                               int(nst), capi.ptr(c_local), C.byref(info)), "qb200_gram_sharded")
+        return c_local
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.qb200_la_destroy(self._h)

@@ -51,6 +51,16 @@ def _worker(rank, world, port, q):
     comm.allreduce_rho(rho_host)                             # host pointer, staged
     enl_sum, nel = comm.allreduce_scalars([enl, nel_local])
     torch.cuda.synchronize()
+    # SlaterDet::gram over the sharded states: gathered block -> overlap columns -> sum over ranks -> replicated Cholesky -> own columns
+    call_h = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=3)
+    la = H.SubspaceLA(b, device=rank)
+    c_all = torch.from_numpy(call_h).cuda()
+    c_loc = torch.zeros_like(cd)
+    la.gram_sharded(comm, c_all, first, n, c_loc)
+    want = P.gram(call_h, b["is_real"])[first:first + n]
+    gerr = torch.tensor([float(np.abs(c_loc.cpu().numpy() - want).max() / np.abs(want).max()) if n else 0.0], dtype=torch.float64)
+    dist.all_reduce(gerr, op=dist.ReduceOp.MAX)
+    la.close()
     if rank == 0:
         call = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=3)
         oft = P.FT(b, *grid)
@@ -58,7 +68,7 @@ def _worker(rank, world, port, q):
         enl_all, _ = P.nl_energy(b, call, occ, sp, compute_hpsi=False)
         sc = np.abs(rho_all).max()
         q.put((float(np.abs(rho.cpu().numpy() - rho_all).max() / sc), float(np.abs(rho_host - rho_all).max() / sc),
-               abs(enl_sum - enl_all) / max(1.0, abs(enl_all)), abs(nel - rho_all.sum() * b["omega"] / N)))
+               abs(enl_sum - enl_all) / max(1.0, abs(enl_all)), abs(nel - rho_all.sum() * b["omega"] / N), float(gerr[0])))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -78,4 +88,4 @@ def test_c_abi_collectives_band_sharded_density(world):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res[0] < 1e-10 and res[1] < 1e-10 and res[2] < 1e-10 and res[3] < 1e-9, res
+    assert res[0] < 1e-10 and res[1] < 1e-10 and res[2] < 1e-10 and res[3] < 1e-9 and res[4] < 1e-10, res

@@ -135,6 +135,50 @@ def test_cuda_la_vs_oracle(kpoint, fc, nst, nloc, ldpad, ws):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kpoint,fc,nst,shards,ws", [((0, 0, 0), False, 11, (4, 4, 3), None), ((0.1, 0.2, 0.3), False, 70, (35, 35), 1 << 20),
+                                                      ((0, 0, 0), True, 9, (9,), None), ((0.25, 0, 0), False, 6, (0, 6), None)])
+def test_cuda_gram_band_sharded_vs_oracle(kpoint, fc, nst, shards, ws):
+    """SlaterDet::gram with the states sharded over ranks (qb200_gram_overlap -> sum over ranks -> qb200_gram_apply), the ranks
+    played one after the other on one GPU: every rank's columns must equal those of the oracle's gram of the whole block (and of
+    qb200_gram); real and complex bases, uneven shards, an empty shard, a workspace that forces several plane-wave chunks"""
+    import torch
+    from qball_b200 import host as H
+    cell, ecut = (9, 0, 0, 0, 10, 0, 0, 0, 11), 6.0
+    b = P.make_basis(cell, ecut, kpoint, fc)
+    ngw = b["ngw"]
+    c = R.synth_coefficients(b["kpg2"], ecut, nst, ngw + 3, b["is_real"], seed=41)
+    want = P.gram(c, b["is_real"])
+    la = H.SubspaceLA(b)
+    if ws:
+        la.set_workspace(ws)
+    call = _dev(c)
+    S = torch.zeros((nst, nst), dtype=torch.complex128, device="cuda")
+    first = 0
+    for n in shards:                                  # step 1 on every "rank", step 2 = the sum
+        Sr = torch.full((nst, nst), 7.0, dtype=torch.complex128, device="cuda")
+        la.gram_overlap(call, first, n, Sr)
+        S += Sr
+        first += n
+    assert first == nst
+    if ws:
+        assert la.query(11) > 1
+    first = 0
+    for n in shards:                                  # step 3 on every "rank"
+        out = torch.zeros((max(n, 1), ngw + 3), dtype=torch.complex128, device="cuda")
+        la.gram_apply(call, S, first, n, out)
+        if n:
+            got = out.cpu().numpy()[:n]
+            assert relerr(got[:, :ngw], want[first:first + n, :ngw]) < TOL
+            assert np.all(got[:, ngw:] == 0)
+        first += n
+    # the one-call form with every state on one rank needs no communicator and may write in place
+    c2 = _dev(c)
+    la.gram_sharded(None, c2, 0, nst, c2)
+    assert relerr(c2.cpu().numpy()[:, :ngw], want[:, :ngw]) < TOL
+    la.close()
+
+
+@pytest.mark.gpu
 def test_cuda_gram_singular_overlap_fails_loudly():
     from qball_b200 import capi, host as H
     b = P.make_basis((9, 0, 0, 0, 9, 0, 0, 0, 9), 4.0, (0.2, 0, 0), False)
