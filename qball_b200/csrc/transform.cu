@@ -275,7 +275,12 @@ bool z2_pick(const qb200_plan* p, const std::vector<int>& first, bool fwd, size_
   const int per = d.is_real ? 2 : 1;
   bool found = false;
   Z2Choice best = {};
-  for (int cb = 32; cb >= 8; cb--) {
+  // tiles of at least 8 columns (128-byte runs of a zt row); very long columns (the 896 planes of the gold benchmark: 14 KB per
+  // column) only fit 3-4 per tile next to the staging buffers -- still faster than the first-generation kernels (Au992, 64
+  // states: z stages 33.2 -> 25.9 ms).  QB200_Z2_MINCB overrides.
+  int cbmin = d.np2 > 512 ? std::max(per, 3) : 8;
+  if (const char* e = getenv("QB200_Z2_MINCB")) cbmin = std::max(per, atoi(e));
+  for (int cb = 32; cb >= cbmin; cb--) {
     if (cb % per) continue;
     if (force_cb > 0 && cb != force_cb) continue;
     Z2Choice c;
@@ -480,7 +485,12 @@ extern "C" int qb200_plan_create(qb200_plan** out, int device, int np0, int np1,
     if (p->z2 && zcol_t_wanted(p, lmax) && (rc = zcol_t_setup(p, first))) { qb200_plan_destroy(p); return rc; }
   }
   const size_t pitch2 = (size_t)(np2 | 1);
-  int ncolmax = (int)std::min<size_t>(32, (80 * 1024) / (pitch2 * 16));
+  // columns per CTA of the first-generation z kernels: two CTAs per SM (2 x 104 KB), and an EVEN number of columns so that
+  // the runs of a zt row a CTA writes / reads are whole 32-byte sectors (long columns: 6 x 16 B = 96 B for the 896 planes of
+  // the gold benchmark instead of 5 x 16 B = 80 B straddling sectors; QB200_Z1_COLS overrides)
+  int ncolmax = (int)std::min<size_t>(32, (104 * 1024) / (pitch2 * 16));
+  if (ncolmax > 2) ncolmax &= ~1;
+  if (const char* e = getenv("QB200_Z1_COLS")) { const int v = atoi(e); if (v >= 1 && v <= 32) ncolmax = v; }
   if (ncolmax < (is_real ? 2 : 1)) ncolmax = is_real ? 2 : 1;
   d.rb = is_real ? std::max(1, ncolmax / 2) : ncolmax;
   const int zcols = is_real ? 2 * d.rb : d.rb;
