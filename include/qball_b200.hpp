@@ -269,6 +269,14 @@ class SubspaceLA {
                             extrapolate ? 1 : 0, &theta), "qb200_psda_update");
     return theta;
   }
+  // SlaterDet::gram with band-sharded states (device pointers): c_all = gathered mloc x nall block, this rank's columns
+  // [first, first + nstloc) -> c_local; comm sums the overlap columns over the ranks (may be null when nstloc == nall)
+  void gram_sharded(qb200_comm* comm, int mloc, int nall, const std::complex<double>* c_all, int first, int nstloc, std::complex<double>* c_local)
+  {
+    int info = 0;
+    check(qb200_gram_sharded(la_, comm, mloc, nall, reinterpret_cast<const double*>(c_all), first, nstloc, reinterpret_cast<double*>(c_local), &info),
+          "qb200_gram_sharded");
+  }
   qb200_la* handle() const { return la_; }
 
  private:
