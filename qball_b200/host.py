@@ -120,14 +120,17 @@ class ChargeDensity:
         self.omega = float(omega)
         self.nelectrons = 0.0
 
-    def update_density(self, c, occ, rhor, rhog, weight: float = 1.0, group=None) -> float:
-        """rhor (N doubles) and rhog (vbasis ngw complex) are outputs; returns nelectrons (total_electronic_charge)"""
+    def update_density(self, c, occ, rhor, rhog, weight: float = 1.0, group=None, ultrasoft=None) -> float:
+        """rhor (N doubles) and rhog (vbasis ngw complex) are outputs; returns nelectrons (total_electronic_charge).
+        ultrasoft: a NonLocalPotential holding the betag / Q_nm(G) tables -- adds the augmentation charges (:312-465; here before
+        the sum over ranks: the term is a sum over states, the reference sums its coefficient matrix over the ranks instead)"""
         from . import parallel as _par
         if hasattr(rhor, "zero_"):
             rhor.zero_()
         else:
             rhor[...] = 0.0
         compute_density(self.ft, c, weight, occ, self.omega, rhor)
+        self.uscharge = ultrasoft.us_augment_density(self.vft, c, weight, occ, self.omega, rhor) if ultrasoft is not None else 0.0
         _par.allreduce_density(rhor, group)                        # wfcontext->dsum('r', ...) (:309); host or device array
         nel = C.c_double(0.0)
         capi._check(self.ft._L.qb200_density_finish(self.vft._h, capi.ptr(rhor), self.omega, capi.ptr(rhog), C.byref(nel)),

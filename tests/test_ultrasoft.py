@@ -203,6 +203,12 @@ def test_cuda_ultrasoft_energy_and_augmentation_vs_reference_fixture(name, host)
         want_q = (g["rho"] - g["rho_nc"]).sum() * b["omega"] / g["rho"].size
         assert abs(usq - want_q) < 1e-10 * max(1.0, abs(want_q))
         assert abs(back(rho).sum() * b["omega"] / g["rho"].size - float(g["nelectrons"])) < 1e-10
+        # the same through the ChargeDensity mirror: rho, rho(G) and the electron count the reference reports
+        cdm = H.ChargeDensity(ft, vb, b["omega"])
+        rho2, rhog = wrap(np.zeros_like(g["rho"])), wrap(np.zeros(vb["ngw"], dtype=np.complex128))
+        nel = cdm.update_density(wrap(c), g["occ"], rho2, rhog, ultrasoft=nlp)
+        assert relerr(back(rho2), g["rho"]) < TOL and abs(nel - float(g["nelectrons"])) < 1e-10 and abs(cdm.uscharge - want_q) < 1e-10
+        assert abs(back(rhog)[np.argmin(vb["kpg2"])].real - float(g["nelectrons"])) < 1e-9     # rho(G = 0) = omega * mean(rho) = nel
         nlp.close()
 
 
