@@ -249,7 +249,8 @@ int qb200_la_set_stream(qb200_la* la, void* cuda_stream);
 /* bytes the packed copy of the wavefunction block may take (default 8 GiB); larger blocks are swept in plane-wave chunks */
 int qb200_la_set_workspace(qb200_la* la, long long bytes);
 int qb200_la_destroy(qb200_la* la);
-long long qb200_la_query(const qb200_la* la, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call */
+long long qb200_la_query(const qb200_la* la, int what); /* 9: kernels launched, 11: plane-wave chunks of the last call,
+                                                           13: the last qb200_diag replayed its Jacobi sweeps from a CUDA graph */
 /* descent direction of the SD / PSD / PSDA wavefunction steppers:
  *   complex:  a.gemm('c','n',1.0,c,cp,0.0); cp.gemm('n','n',-1.0,c,a,1.0)       PSDAWavefunctionStepper.cc:264-277
  *   real:     a.gemm('t','n',2.0,c,cp,0.0); a.ger(-1.0,c,0,cp,0); cp.gemm('n','n',-1.0,c,a,1.0)          :65-84

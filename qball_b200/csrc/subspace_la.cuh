@@ -243,6 +243,7 @@ struct qb200_la {
   double *W, *part, *fs; size_t W_cap, part_cap, fs_cap;
   size_t W_WP;                                  // pitch W was last zero-filled for (3M pad rows must be zero)
   double *S, *X, *Dinv; size_t S_cap, X_cap, Dinv_cap;
+  bool jacobi_graph;                            // the last qb200_diag replayed its sweeps from a CUDA graph
   double* Ssh; size_t Ssh_cap;                  // band-sharded gram: the overlap columns before / after the sum over ranks
   double *st_c, *st_x, *st_a; size_t st_c_cap, st_x_cap, st_a_cap;
   int* info_dev;
@@ -264,7 +265,7 @@ extern "C" int qb200_la_create(qb200_la** out, int device, int ngw, int is_real)
   la->budget = 8ll << 30;
   if (const char* e = getenv("QB200_LA_BYTES")) la->budget = std::max(1ll << 20, atoll(e));
   la->W = la->part = la->fs = la->S = la->X = la->Dinv = la->st_c = la->st_x = la->st_a = nullptr;
-  la->Ssh = nullptr; la->Ssh_cap = 0;
+  la->Ssh = nullptr; la->Ssh_cap = 0; la->jacobi_graph = false;
   la->W_cap = la->part_cap = la->fs_cap = la->S_cap = la->X_cap = la->Dinv_cap = la->st_c_cap = la->st_x_cap = la->st_a_cap = 0;
   la->W_WP = 0; la->launches = 0; la->nchunks_last = 0; la->info_dev = nullptr;
   cudaDeviceProp prop;
@@ -310,6 +311,7 @@ extern "C" long long qb200_la_query(const qb200_la* la, int what)
     case 9: return la->launches;
     case 11: return la->nchunks_last;
     case 12: return (long long)(la->W_cap * sizeof(double));
+    case 13: return la->jacobi_graph ? 1 : 0;
     default: return -1;
   }
 }
@@ -974,6 +976,30 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
   LA_LAUNCH_CHECK(la);
   int sweeps = 0;
   const int maxsweep = 30;                                  // the reference's own jacobi() uses the same cap (Wavefunction.cc:1594)
+  // A sweep is 2 (ne - 1) tiny launches: launch-bound.  On a capturable stream the sweep is captured ONCE into a CUDA graph and
+  // replayed for every sweep (same pointers, same step sequence); the legacy default stream cannot be captured and launches
+  // directly.  QB200_JACOBI_GRAPH=0: direct launches everywhere.
+  auto sweep = [&]() {
+    for (int step = 0; step < ne - 1; step++) {
+      k_jac_cols<<<ne / 2, 256, 0, la->stream>>>(A, Z, ne, step, rot);
+      k_jac_rows<<<dim3((ne + 255) / 256, ne / 2), 256, 0, la->stream>>>(A, ne, step, rot);
+    }
+  };
+  cudaGraphExec_t gexec = nullptr;
+  {
+    const char* e = getenv("QB200_JACOBI_GRAPH");
+    const bool want = !(e && e[0] == '0') && ne > 32 && la->stream != 0 && la->stream != cudaStreamLegacy;
+    if (want && cudaStreamBeginCapture(la->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      sweep();
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamEndCapture(la->stream, &graph) == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+        cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();                                   // a failed capture leaves no sticky error; the direct path takes over
+    }
+  }
+  la->jacobi_graph = gexec != nullptr;
   for (; sweeps < maxsweep; sweeps++) {
     double h[2];
     k_jac_off<<<1, 1024, 0, la->stream>>>(A, ne, sums);
@@ -981,14 +1007,17 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
     QB_CUDA(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, la->stream));
     QB_CUDA(cudaStreamSynchronize(la->stream));
     if (!(h[0] > 1e-30 * h[1])) break;                      // off-diagonal norm below 1e-15 ||h||
-    for (int step = 0; step < ne - 1; step++) {
-      k_jac_cols<<<ne / 2, 256, 0, la->stream>>>(A, Z, ne, step, rot);
-      k_jac_rows<<<dim3((ne + 255) / 256, ne / 2), 256, 0, la->stream>>>(A, ne, step, rot);
-      la->launches += 2;
+    if (gexec) {
+      const cudaError_t eg = cudaGraphLaunch(gexec, la->stream);
+      if (eg != cudaSuccess) { cudaGraphExecDestroy(gexec); return qb200::cuda_fail(eg, "jacobi sweep (graph)", __FILE__, __LINE__); }
+    } else {
+      sweep();
     }
+    la->launches += 2 * (ne - 1);
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return qb200::cuda_fail(e, "jacobi sweep", __FILE__, __LINE__);
+    if (e != cudaSuccess) { if (gexec) cudaGraphExecDestroy(gexec); return qb200::cuda_fail(e, "jacobi sweep", __FILE__, __LINE__); }
   }
+  if (gexec) { cudaStreamSynchronize(la->stream); cudaGraphExecDestroy(gexec); }
   if (sweeps_out) *sweeps_out = sweeps;
   k_jac_diag<<<(n + 255) / 256, 256, 0, la->stream>>>(A, ne, n, wd);
   LA_LAUNCH_CHECK(la);

@@ -330,6 +330,32 @@ def test_cuda_diag_vs_reference_fixture(name):
 
 
 @pytest.mark.gpu
+def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream():
+    """on a capturable stream the 2 (n - 1) launches of a Jacobi sweep are captured once and replayed (the legacy default
+    stream launches directly): same eigenvalues and rotated states as the direct path"""
+    import torch
+    from qball_b200 import host as H
+    cell, ecut, nst = (10, 0, 0, 0, 9, 0, 0, 0, 11), 6.0, 70
+    b = P.make_basis(cell, ecut, (0.2, 0.1, 0.0), False)
+    c = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, 61), False)
+    hc = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, 62) + c * (1.0 + b["kpg2"])[None, :]
+    res = {}
+    for mode in ("graph", "direct"):
+        st = torch.cuda.Stream() if mode == "graph" else None
+        la = H.SubspaceLA(b, stream=st)
+        with torch.cuda.stream(st) if st is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            cd, hd = _dev(c), _dev(hc)
+            torch.cuda.synchronize()
+            w, _ = la.diag(cd, hd)
+            torch.cuda.synchronize()
+        assert la.query(13) == (1 if mode == "graph" else 0)
+        res[mode] = (np.asarray(w).copy(), cd.cpu().numpy().copy())
+        la.close()
+    assert np.allclose(res["graph"][0], res["direct"][0], rtol=0, atol=1e-12 * np.abs(res["direct"][0]).max())
+    assert relerr(res["graph"][1], res["direct"][1]) < 1e-10
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("kpoint,fc,nst", [((0, 0, 0), False, 37), ((0.1, 0.2, 0.3), False, 130), ((0, 0, 0), True, 64)])
 def test_cuda_diag_eigenpairs_vs_oracle(kpoint, fc, nst):
     """Wavefunction::diag with eigenvectors at sizes that cross the GEMM tiles (odd n included): eigenvalues against LAPACK
