@@ -563,6 +563,19 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
             _FP64_PEAK[local_rank] = (None, None)
     dmma_tf, dfma_tf = _FP64_PEAK[local_rank]
     fp64_peak = dmma_tf if dmma_tf else 37.0
+    # FP64 issue roof of the xy stage, live: the kernels' FP64 warp-instruction counts are a property of the code (per unit, from the
+    # committed ncu capture of this command); the time and the DFMA issue rate (2 flops per lane-instruction) are measured in this run
+    if roofline_hbm is not None and ft.fused() and wl_name == "mgo216" and dfma_tf:
+        try:
+            inst = sum(ncu_traffic[k]["fp64_warp_inst_per_launch"] / ncu_traffic[k]["units_per_launch"] * n_
+                       for k, n_ in ((plane_keys[0], nunits_h), (plane_keys[1], nst)))
+            lane_rate = inst * 32.0 * steps / (xy_ms * 1e-3)
+            peak_rate = dfma_tf * 1e12 / 2.0
+            roofline_hbm["fp64_issue"] = {"bound": "fp64 instruction issue", "achieved": lane_rate / 1e12, "peak": peak_rate / 1e12,
+                                          "unit": "T lane-instructions/s", "frac": lane_rate / peak_rate, "fp64_warp_instructions_per_step": inst,
+                                          "source": "instruction counts per unit from profiles/ncu_traffic.json (ncu of this command); time and DFMA rate measured in this run"}
+        except Exception:  # noqa: BLE001
+            pass
     roofline_fp64 = None
     if nl_ms > 0:
         ach = nl_flops_step * steps / (nl_ms * 1e-3) / 1e12
