@@ -244,6 +244,7 @@ struct qb200_la {
   size_t W_WP;                                  // pitch W was last zero-filled for (3M pad rows must be zero)
   double *S, *X, *Dinv; size_t S_cap, X_cap, Dinv_cap;
   bool jacobi_graph;                            // the last qb200_diag replayed its sweeps from a CUDA graph
+  bool jacobi_blocked;                          // the last qb200_diag ran the blocked Jacobi method
   double* Ssh; size_t Ssh_cap;                  // band-sharded gram: the overlap columns before / after the sum over ranks
   double *st_c, *st_x, *st_a; size_t st_c_cap, st_x_cap, st_a_cap;
   int* info_dev;
@@ -265,7 +266,7 @@ extern "C" int qb200_la_create(qb200_la** out, int device, int ngw, int is_real)
   la->budget = 8ll << 30;
   if (const char* e = getenv("QB200_LA_BYTES")) la->budget = std::max(1ll << 20, atoll(e));
   la->W = la->part = la->fs = la->S = la->X = la->Dinv = la->st_c = la->st_x = la->st_a = nullptr;
-  la->Ssh = nullptr; la->Ssh_cap = 0; la->jacobi_graph = false;
+  la->Ssh = nullptr; la->Ssh_cap = 0; la->jacobi_graph = false; la->jacobi_blocked = false;
   la->W_cap = la->part_cap = la->fs_cap = la->S_cap = la->X_cap = la->Dinv_cap = la->st_c_cap = la->st_x_cap = la->st_a_cap = 0;
   la->W_WP = 0; la->launches = 0; la->nchunks_last = 0; la->info_dev = nullptr;
   cudaDeviceProp prop;
@@ -312,6 +313,7 @@ extern "C" long long qb200_la_query(const qb200_la* la, int what)
     case 11: return la->nchunks_last;
     case 12: return (long long)(la->W_cap * sizeof(double));
     case 13: return la->jacobi_graph ? 1 : 0;
+    case 14: return la->jacobi_blocked ? 1 : 0;
     default: return -1;
   }
 }
@@ -898,12 +900,15 @@ __global__ void __launch_bounds__(256) k_jac_rows(double2* __restrict__ A, int n
   A[(size_t)r * ne + p] = np_;
   A[(size_t)r * ne + q] = nq_;
 }
-// sums[0] = sum_{i != j} |a_ij|^2, sums[1] = sum |a_ij|^2 (one CTA, fixed order)
-__global__ void __launch_bounds__(1024) k_jac_off(const double2* __restrict__ A, int ne, double* __restrict__ sums)
+// sums[0] = sum_{i != j} |a_ij|^2, sums[1] = sum |a_ij|^2: every CTA reduces a fixed slice to part[2 b], part[2 b + 1]; the last
+// stage (one CTA) adds the partials in index order -- deterministic
+__global__ void __launch_bounds__(1024) k_jac_off(const double2* __restrict__ A, int ne, double* __restrict__ part)
 {
   __shared__ double ro[1024], rt[1024];
   double o = 0.0, t = 0.0;
-  for (size_t i = threadIdx.x; i < (size_t)ne * ne; i += 1024) {
+  const size_t total = (size_t)ne * ne, per = (total + gridDim.x - 1) / gridDim.x;
+  const size_t i0 = blockIdx.x * per, i1 = i0 + per < total ? i0 + per : total;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += 1024) {
     const double2 a = A[i];
     const double v = a.x * a.x + a.y * a.y;
     t += v;
@@ -915,13 +920,205 @@ __global__ void __launch_bounds__(1024) k_jac_off(const double2* __restrict__ A,
     if (threadIdx.x < s) { ro[threadIdx.x] += ro[threadIdx.x + s]; rt[threadIdx.x] += rt[threadIdx.x + s]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { sums[0] = ro[0]; sums[1] = rt[0]; }
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = ro[0]; part[2 * blockIdx.x + 1] = rt[0]; }
+}
+__global__ void k_jac_off_sum(const double* __restrict__ part, int nb, double* __restrict__ sums)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double o = 0.0, t = 0.0;
+    for (int b = 0; b < nb; b++) { o += part[2 * b]; t += part[2 * b + 1]; }
+    sums[0] = o; sums[1] = t;
+  }
 }
 __global__ void __launch_bounds__(256) k_jac_diag(const double2* __restrict__ A, int ne, int n, double* __restrict__ w)
 {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) w[i] = A[(size_t)i * ne + i].x;
 }
+// ---- blocked Jacobi: the matrix in blocks of BJ_NB; a step pairs the blocks round-robin, one CTA diagonalises each 2 BJ_NB x
+// 2 BJ_NB pivot [A_PP A_PQ; A_QP A_QQ] completely in shared memory (cyclic Jacobi, no launches) and hands back its unitary U; two
+// small GEMM kernels then apply U to the block columns of A and Z and U^H to the block rows of A.  A sweep is 3 (nblk - 1) launches
+// instead of 2 (n - 1), and the sequential chain of rotation steps runs at shared-memory latency instead of launch latency.
+constexpr int BJ_NB = 32, BJ_M = 2 * BJ_NB, BJ_LD = BJ_M + 1, BJ_PT = 1024;
+static_assert(BJ_PT == 32 * BJ_NB, "one warp per pair of a pivot step");
+constexpr size_t BJ_PIVOT_SMEM = 2 * (size_t)BJ_M * BJ_LD * sizeof(double2) + BJ_NB * sizeof(JacRot) + 2 * BJ_PT * sizeof(double);
+constexpr size_t BJ_APPLY_SMEM = 2 * (size_t)BJ_M * BJ_LD * sizeof(double2);
+
+__device__ __forceinline__ int bj_global(int k, int P, int Q) { return k < BJ_NB ? P * BJ_NB + k : Q * BJ_NB + (k - BJ_NB); }
+
+// grid (nblk/2), BJ_PT threads.  U[pair][col j][row k] (BJ_M x BJ_M, column-major, dense).  inner_max: cyclic sweeps over the pivot
+// (the outer sweeps finish what a pivot leaves: 3 keep the quadratic convergence, a fully converged pivot costs 4x the time)
+__global__ void __launch_bounds__(BJ_PT) k_bj_pivot(const double2* __restrict__ A, int ne, int nblk, int step, double2* __restrict__ Ubuf,
+                                                    double2* __restrict__ Mbuf, int inner_max)
+{
+  extern __shared__ __align__(16) unsigned char bj_raw[];
+  double2* M = reinterpret_cast<double2*>(bj_raw);          // M[col * BJ_LD + row]
+  double2* U = M + BJ_M * BJ_LD;
+  JacRot* rot = reinterpret_cast<JacRot*>(U + BJ_M * BJ_LD);
+  double* red = reinterpret_cast<double*>(rot + BJ_NB);      // [2][BJ_PT]
+  int P, Q;
+  jac_pair(blockIdx.x, step, nblk, P, Q);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < BJ_M * BJ_M; e += BJ_PT) {
+    const int col = e / BJ_M, row = e % BJ_M;
+    const int gr = bj_global(row, P, Q), gc = bj_global(col, P, Q);
+    double2 v;
+    if (row > col) v = A[(size_t)gc * ne + gr];                                  // the lower triangle defines the Hermitian block
+    else if (row < col) { const double2 t = A[(size_t)gr * ne + gc]; v = make_double2(t.x, -t.y); }
+    else v = make_double2(A[(size_t)gc * ne + gr].x, 0.0);
+    M[col * BJ_LD + row] = v;
+    U[col * BJ_LD + row] = make_double2(row == col ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  for (int sw = 0; sw < inner_max; sw++) {
+    // off-diagonal and total norm of the pivot (fixed order)
+    double o = 0.0, t = 0.0;
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_PT) {
+      const int col = e / BJ_M, row = e % BJ_M;
+      const double2 a = M[col * BJ_LD + row];
+      const double v = a.x * a.x + a.y * a.y;
+      t += v;
+      if (row != col) o += v;
+    }
+    red[tid] = o; red[BJ_PT + tid] = t;
+    __syncthreads();
+    for (int k = BJ_PT / 2; k > 0; k >>= 1) {
+      if (tid < k) { red[tid] += red[tid + k]; red[BJ_PT + tid] += red[BJ_PT + tid + k]; }
+      __syncthreads();
+    }
+    const bool done = !(red[0] > 1e-32 * red[BJ_PT]);
+    __syncthreads();
+    if (done) break;
+    // one warp per pair of the step (32 warps, 32 pairs): every lane derives the rotation from the pair's own three elements
+    // (broadcast reads), the warp applies it to its two columns of M and U, and after the barrier to its two rows of M -- the
+    // rotation stays in registers, two barriers per step
+    const int wp = tid >> 5, lane = tid & 31;
+    for (int st = 0; st < BJ_M - 1; st++) {
+      // the 32 rotations of the step by ONE warp (lane = pair): 32 warps deriving them redundantly would put ~300 dependent FP64
+      // instructions per warp on the FP64 pipe and make the step pipe-bound
+      if (wp == 0) {
+        int p0, q0;
+        jac_pair(lane, st, BJ_M, p0, q0);
+        const double app = M[p0 * BJ_LD + p0].x, aqq = M[q0 * BJ_LD + q0].x;
+        const double2 apq = M[q0 * BJ_LD + p0];               // element (row p, column q)
+        const double mod = sqrt(apq.x * apq.x + apq.y * apq.y);
+        JacRot r;
+        r.c = 1.0; r.s = 0.0; r.ex = 1.0; r.ey = 0.0;
+        if (!(mod <= 1e-150 || mod * mod <= 1e-34 * fabs(app * aqq))) {
+          const double imod = 1.0 / mod;
+          const double tau = 0.5 * (aqq - app) * imod;
+          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          r.c = rsqrt(1.0 + tt * tt); r.s = tt * r.c; r.ex = apq.x * imod; r.ey = apq.y * imod;
+        }
+        rot[lane] = r;
+      }
+      __syncthreads();
+      int p, q;
+      jac_pair(wp, st, BJ_M, p, q);
+      const JacRot R = rot[wp];
+      const double rc_ = R.c, rs = R.s, ex = R.ex, ey = R.ey;
+      if (rs != 0.0) {
+#pragma unroll
+        for (int i = lane; i < 2 * BJ_M; i += 32) {           // column operation: columns p, q of M and of U
+          double2* X = i < BJ_M ? M : U;
+          const int r = i < BJ_M ? i : i - BJ_M;
+          const double2 xp = X[p * BJ_LD + r], xq = X[q * BJ_LD + r];
+          const double2 eq = make_double2(ex * xq.x + ey * xq.y, ex * xq.y - ey * xq.x);      // e^{-i phi} xq
+          const double2 ep = make_double2(ex * xp.x - ey * xp.y, ex * xp.y + ey * xp.x);      // e^{+i phi} xp
+          X[p * BJ_LD + r] = make_double2(rc_ * xp.x - rs * eq.x, rc_ * xp.y - rs * eq.y);
+          X[q * BJ_LD + r] = make_double2(rs * ep.x + rc_ * xq.x, rs * ep.y + rc_ * xq.y);
+        }
+      }
+      __syncthreads();
+      if (rs != 0.0) {
+#pragma unroll
+        for (int r = lane; r < BJ_M; r += 32) {               // row operation: rows p, q of M
+          const double2 xp = M[r * BJ_LD + p], xq = M[r * BJ_LD + q];
+          const double2 eq = make_double2(ex * xq.x - ey * xq.y, ex * xq.y + ey * xq.x);
+          const double2 ep = make_double2(ex * xp.x + ey * xp.y, ex * xp.y - ey * xp.x);
+          double2 np_ = make_double2(rc_ * xp.x - rs * eq.x, rc_ * xp.y - rs * eq.y);
+          double2 nq_ = make_double2(rs * ep.x + rc_ * xq.x, rs * ep.y + rc_ * xq.y);
+          if (r == p) { np_.y = 0.0; nq_ = make_double2(0.0, 0.0); }
+          if (r == q) { nq_.y = 0.0; np_ = make_double2(0.0, 0.0); }
+          M[r * BJ_LD + p] = np_;
+          M[r * BJ_LD + q] = nq_;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  double2* Uo = Ubuf + (size_t)blockIdx.x * BJ_M * BJ_M;
+  double2* Mo = Mbuf + (size_t)blockIdx.x * BJ_M * BJ_M;      // the diagonalised pivot: real diagonal, exact zeros where annihilated
+  for (int e = tid; e < BJ_M * BJ_M; e += BJ_PT) {
+    Uo[e] = U[(e / BJ_M) * BJ_LD + (e % BJ_M)];
+    Mo[e] = M[(e / BJ_M) * BJ_LD + (e % BJ_M)];
+  }
+}
+
+// ROWOP == 0: X[:, PQ] <- X[:, PQ] U for a tile of 64 rows (X = A, and Z when blockIdx.z == 1)
+// ROWOP == 1: A[PQ, :] <- U^H A[PQ, :] for a tile of 64 columns
+// grid (nblk/2, ne/64, ROWOP ? 1 : 2), 256 threads: thread -> 4 x 4 outputs
+template <int ROWOP>
+__global__ void __launch_bounds__(256) k_bj_apply(double2* __restrict__ A, double2* __restrict__ Z, int ne, int nblk, int step,
+                                                  const double2* __restrict__ Ubuf, const double2* __restrict__ Mbuf)
+{
+  extern __shared__ __align__(16) unsigned char bj_raw[];
+  double2* T = reinterpret_cast<double2*>(bj_raw);          // T[k * BJ_LD + x]: x = row (column op) or column (row op) inside the tile
+  double2* Cc = T + BJ_M * BJ_LD;                           // Cc[k * BJ_LD + j] = coefficient of input k in output j
+  int P, Q;
+  jac_pair(blockIdx.x, step, nblk, P, Q);
+  double2* X = (!ROWOP && blockIdx.z == 1) ? Z : A;
+  const int x0 = blockIdx.y * BJ_M, tid = threadIdx.x;
+  const double2* U = Ubuf + (size_t)blockIdx.x * BJ_M * BJ_M;
+  for (int e = tid; e < BJ_M * BJ_M; e += 256) {
+    const int a = e / BJ_M, b = e % BJ_M;
+    if (!ROWOP) {
+      T[a * BJ_LD + b] = X[(size_t)bj_global(a, P, Q) * ne + x0 + b];            // k = a (pivot column), x = b (row): contiguous in b
+      Cc[b * BJ_LD + a] = U[(size_t)a * BJ_M + b];                                 // U[col j = a][row k = b] -> Cc[k][j]
+    } else {
+      T[b * BJ_LD + a] = X[(size_t)(x0 + a) * ne + bj_global(b, P, Q)];          // x = a (column), k = b (pivot row): contiguous in b
+      const double2 u = U[(size_t)a * BJ_M + b];                                   // U[col i = a][row k = b]: coefficient conj(U[k][i])
+      Cc[b * BJ_LD + a] = make_double2(u.x, -u.y);
+    }
+  }
+  __syncthreads();
+  const int j0 = (tid >> 4) * 4, xx0 = (tid & 15) * 4;
+  double2 acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int x = 0; x < 4; x++) acc[j][x] = make_double2(0.0, 0.0);
+  for (int k = 0; k < BJ_M; k++) {
+    double2 t[4], c[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) t[x] = T[k * BJ_LD + xx0 + x];
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = Cc[k * BJ_LD + j0 + j];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        acc[j][x].x += c[j].x * t[x].x - c[j].y * t[x].y;
+        acc[j][x].y += c[j].x * t[x].y + c[j].y * t[x].x;
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      if (!ROWOP) X[(size_t)bj_global(j0 + j, P, Q) * ne + x0 + xx0 + x] = acc[j][x];
+      else {
+        // the pivot block itself takes the values the pivot kernel reached in shared memory (U^H M U up to rounding): its
+        // annihilated elements are EXACTLY zero, as in the element-wise method -- without this the off-diagonal norm of a
+        // large matrix stalls at the rounding noise of the block GEMMs
+        const int col = x0 + xx0 + x, cb = col / BJ_NB;
+        double2 v = acc[j][x];
+        if (cb == P || cb == Q) v = Mbuf[(size_t)blockIdx.x * BJ_M * BJ_M + (size_t)((cb == P ? 0 : BJ_NB) + col % BJ_NB) * BJ_M + j0 + j];
+        X[(size_t)col * ne + bj_global(j0 + j, P, Q)] = v;
+      }
+    }
+}
+
 // second operand of c z: T[m, col] = Z[m, perm[col]] in the layout la_back reads (cf. k_gram_operand)
 template <int IS_REAL>
 __global__ void __launch_bounds__(256) k_diag_operand(const double2* __restrict__ Z, int ne, int n, const int* __restrict__ perm, double* __restrict__ fs, int FP)
@@ -946,14 +1143,21 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
   la->nchunks_last = g.nchunks;
   if ((rc = la_prepare_W(la, g))) return rc;
   const int ncols = la->is_real ? n : 2 * n;
-  const int ne = (n + 1) & ~1;
-  if ((rc = nl_ensure(&la->part, &la->part_cap, (size_t)g.ksplit * ncols * g.Mp))) return rc;
+  // blocked Jacobi (default): the matrix padded to an even number of 32 x 32 blocks; QB200_JACOBI_BLOCK=0: the element-wise
+  // parallel cyclic Jacobi (two launches per rotation step), padded to an even order
+  bool blocked = true;
+  if (const char* e = getenv("QB200_JACOBI_BLOCK")) blocked = e[0] != '0';
+  const int bj_nblk = (((n + BJ_NB - 1) / BJ_NB) + 1) & ~1;
+  const int ne = blocked ? bj_nblk * BJ_NB : (n + 1) & ~1;
+  if ((rc = nl_ensure(&la->part, &la->part_cap, std::max<size_t>((size_t)g.ksplit * ncols * g.Mp, 256)))) return rc;   // (>= the off-norm partials)
   if ((rc = nl_ensure(&la->fs, &la->fs_cap, (size_t)n * g.FP))) return rc;
   if ((rc = nl_ensure(&la->S, &la->S_cap, 2 * (size_t)ne * ne + 8))) return rc;
   if ((rc = nl_ensure(&la->X, &la->X_cap, 2 * (size_t)ne * ne))) return rc;
-  // Dinv doubles as the small work area: A (ne x ne) | rot[ne/2] | sums[2] | w[n] | perm[n]
+  // Dinv doubles as the small work area: A (ne x ne) | rot[ne/2] | sums[2] | w[n] | perm[n] | U of every pivot (blocked)
   const size_t rot_d = (sizeof(JacRot) * (size_t)(ne / 2) + 7) / 8;
-  if ((rc = nl_ensure(&la->Dinv, &la->Dinv_cap, 2 * (size_t)ne * ne + rot_d + 2 + n + (n + 1) / 2 + 8))) return rc;
+  const size_t small_d = (rot_d + 2 + n + (n + 1) / 2 + 8 + 1) & ~(size_t)1;
+  const size_t ubuf_d = blocked ? 2 * (size_t)(bj_nblk / 2) * BJ_M * BJ_M : 0;     // U of every pivot; the same again for the diagonalised pivots
+  if ((rc = nl_ensure(&la->Dinv, &la->Dinv_cap, 2 * (size_t)ne * ne + small_d + 2 * ubuf_d))) return rc;
   const int ngw = la->ngw;
   // S = c^H (H c)
   for (int ch = 0; ch < g.nchunks; ch++) {
@@ -986,7 +1190,38 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
     }
   };
   cudaGraphExec_t gexec = nullptr;
-  {
+  const int JAC_OFF_CTAS = 64;                                // (la->part, free between the two GEMMs, holds the 128 partial sums)
+  la->jacobi_blocked = blocked;
+  if (blocked) {
+    double2* Ubuf = (double2*)(la->Dinv + 2 * (size_t)ne * ne + small_d);
+    double2* Mbuf = Ubuf + ubuf_d / 2;
+    // cyclic sweeps over a pivot per visit: ONE (measured, 768 states: 67.8 ms against 99.7 / 126.1 ms with two / three -- the
+    // number of outer sweeps stays the same, 11; the element-wise method with a graph: 133 ms); a single pivot = the whole
+    // matrix is converged inside the kernel
+    int bj_inner = bj_nblk == 2 ? 12 : 1;
+    if (const char* e = getenv("QB200_BJ_INNER")) bj_inner = std::max(1, atoi(e));
+    QB_CUDA(cudaFuncSetAttribute(k_bj_pivot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_PIVOT_SMEM));
+    QB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
+    QB_CUDA(cudaFuncSetAttribute(k_bj_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
+    la->jacobi_graph = false;
+    for (; sweeps < maxsweep; sweeps++) {
+      double h[2];
+      k_jac_off<<<JAC_OFF_CTAS, 1024, 0, la->stream>>>(A, ne, la->part);
+      k_jac_off_sum<<<1, 32, 0, la->stream>>>(la->part, JAC_OFF_CTAS, sums);
+      LA_LAUNCH_CHECK(la);
+      QB_CUDA(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, la->stream));
+      QB_CUDA(cudaStreamSynchronize(la->stream));
+      if (!(h[0] > 1e-30 * h[1])) break;                    // off-diagonal norm below 1e-15 ||h||
+      for (int step = 0; step < bj_nblk - 1; step++) {
+        k_bj_pivot<<<bj_nblk / 2, BJ_PT, BJ_PIVOT_SMEM, la->stream>>>(A, ne, bj_nblk, step, Ubuf, Mbuf, bj_inner);
+        k_bj_apply<0><<<dim3(bj_nblk / 2, ne / BJ_M, 2), 256, BJ_APPLY_SMEM, la->stream>>>(A, Z, ne, bj_nblk, step, Ubuf, Mbuf);
+        k_bj_apply<1><<<dim3(bj_nblk / 2, ne / BJ_M, 1), 256, BJ_APPLY_SMEM, la->stream>>>(A, Z, ne, bj_nblk, step, Ubuf, Mbuf);
+        la->launches += 3;
+      }
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return qb200::cuda_fail(e, "blocked jacobi sweep", __FILE__, __LINE__);
+    }
+  } else {
     const char* e = getenv("QB200_JACOBI_GRAPH");
     const bool want = !(e && e[0] == '0') && ne > 32 && la->stream != 0 && la->stream != cudaStreamLegacy;
     if (want && cudaStreamBeginCapture(la->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -999,10 +1234,11 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
       cudaGetLastError();                                   // a failed capture leaves no sticky error; the direct path takes over
     }
   }
-  la->jacobi_graph = gexec != nullptr;
-  for (; sweeps < maxsweep; sweeps++) {
+  if (!blocked) la->jacobi_graph = gexec != nullptr;
+  for (; !blocked && sweeps < maxsweep; sweeps++) {
     double h[2];
-    k_jac_off<<<1, 1024, 0, la->stream>>>(A, ne, sums);
+    k_jac_off<<<JAC_OFF_CTAS, 1024, 0, la->stream>>>(A, ne, la->part);
+    k_jac_off_sum<<<1, 32, 0, la->stream>>>(la->part, JAC_OFF_CTAS, sums);
     LA_LAUNCH_CHECK(la);
     QB_CUDA(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, la->stream));
     QB_CUDA(cudaStreamSynchronize(la->stream));

@@ -330,11 +330,12 @@ def test_cuda_diag_vs_reference_fixture(name):
 
 
 @pytest.mark.gpu
-def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream():
-    """on a capturable stream the 2 (n - 1) launches of a Jacobi sweep are captured once and replayed (the legacy default
-    stream launches directly): same eigenvalues and rotated states as the direct path"""
+def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream(monkeypatch):
+    """the element-wise cyclic Jacobi (QB200_JACOBI_BLOCK=0): on a capturable stream the 2 (n - 1) launches of a sweep are
+    captured once and replayed (the legacy default stream launches directly): same eigenvalues and rotated states"""
     import torch
     from qball_b200 import host as H
+    monkeypatch.setenv("QB200_JACOBI_BLOCK", "0")
     cell, ecut, nst = (10, 0, 0, 0, 9, 0, 0, 0, 11), 6.0, 70
     b = P.make_basis(cell, ecut, (0.2, 0.1, 0.0), False)
     c = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, 61), False)
@@ -353,6 +354,41 @@ def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream():
         la.close()
     assert np.allclose(res["graph"][0], res["direct"][0], rtol=0, atol=1e-12 * np.abs(res["direct"][0]).max())
     assert relerr(res["graph"][1], res["direct"][1]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kpoint,nst", [((0, 0, 0), 5), ((0.2, 0.1, 0.0), 64), ((0.2, 0.1, 0.0), 97), ((0, 0, 0), 200)])
+def test_cuda_diag_blocked_and_cyclic_jacobi_agree(kpoint, nst, monkeypatch):
+    """the blocked Jacobi method (default: 64 x 64 pivots diagonalised in shared memory, block rotations applied as small GEMMs)
+    against the element-wise cyclic Jacobi and against numpy's eigvalsh of the same subspace matrix: orders below one block,
+    exactly one pivot, an odd number of blocks (padding block), real and complex bases"""
+    from qball_b200 import host as H
+    cell, ecut = (10, 0, 0, 0, 9, 0, 0, 0, 11), 7.0
+    b = P.make_basis(cell, ecut, kpoint, False)
+    c = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], 71), b["is_real"])
+    hc = R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], 72) + c * (1.0 + b["kpg2"])[None, :]
+    w_ref = np.linalg.eigvalsh(np.tril(P.subspace_h(c, hc, b["is_real"])) + np.tril(P.subspace_h(c, hc, b["is_real"]), -1).conj().T)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QB200_JACOBI_BLOCK", mode)
+        la = H.SubspaceLA(b)
+        cd, hd = _dev(c), _dev(hc)
+        w, sweeps = la.diag(cd, hd)
+        assert la.query(14) == int(mode) and 1 <= sweeps < 30
+        scale = np.abs(w_ref).max()
+        assert np.abs(np.asarray(w) - w_ref).max() < 1e-12 * scale
+        # the rotated states diagonalise H in the subspace: c'^H (H c') = diag(w), with H c' = (H c) z
+        res[mode] = (np.asarray(w).copy(), cd.cpu().numpy().copy())
+        la.close()
+    # eigenvectors agree up to phases where the eigenvalues are well separated: compare the projectors c' c'^H through |<a|b>|
+    gap = np.min(np.diff(res["1"][0])) / np.abs(w_ref).max()
+    if gap > 1e-6:
+        a_, b_ = res["1"][1][:, :b["ngw"]], res["0"][1][:, :b["ngw"]]
+        if b["is_real"]:
+            ov = np.abs(2.0 * np.einsum("ng,ng->n", np.conj(a_), b_).real - a_[:, 0].real * b_[:, 0].real)
+        else:
+            ov = np.abs(np.einsum("ng,ng->n", np.conj(a_), b_))
+        assert np.abs(ov - 1.0).max() < 1e-8
 
 
 @pytest.mark.gpu
