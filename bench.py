@@ -282,7 +282,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric, unit = METRIC, UNIT
-    config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}",
+    config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; one NCCL all-reduce per step carries rho(r) and E_nl (no host synchronisation inside the step)" if world > 1 else ""),
               "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if args.workload == "mgo216" else "L2 flushed by the c/Hpsi block sweep",
               "anl": "the materialised projector block anl(G) depends on the atomic positions only and is kept across the steps (positions fixed, as over the SCF iterations of one ionic step); QB200_ANL_CACHE=0 regenerates it in every call like the reference's comp_anl (+0.08 ms per MgO216 step)"}
 
@@ -380,7 +380,7 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     from qball_b200 import host as H
     dev = torch.device("cuda", local_rank)
     metric, unit = METRIC, UNIT
-    config = {"workload": f"{wl_name}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}",
+    config = {"workload": f"{wl_name}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; one NCCL all-reduce per step carries rho(r) and E_nl (no host synchronisation inside the step)" if world > 1 else ""),
               "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if wl["nst"] * 16 * 70000 > (200 << 20) else "L2 flushed by the c/Hpsi block sweep",
               "anl": "the materialised projector block anl(G) depends on the atomic positions only and is kept across the steps (positions fixed, as over the SCF iterations of one ionic step); QB200_ANL_CACHE=0 regenerates it in every call like the reference's comp_anl (+0.08 ms per MgO216 step)"}
     b, grid = make_basis(wl["cell"], wl["ecut"], wl["kpoint"], wl["force_complex"])
@@ -405,7 +405,8 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
         v = torch.from_numpy(v_host).to(dev)
         kpg2 = torch.from_numpy(b["kpg2"]).to(dev)
         hpsi = torch.zeros_like(c)
-        rho = torch.zeros(N, dtype=torch.float64, device=dev)
+        rho_ext = torch.zeros(N + 8, dtype=torch.float64, device=dev)     # rho(r) and, behind it, the scalars that ride in the same all-reduce
+        rho = rho_ext[:N]
         scal = torch.zeros(2, dtype=torch.float64, device=dev)
     omega = b["omega"]
 
@@ -417,12 +418,19 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
 
     def step():
         with torch.cuda.stream(stream):
-            enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
-            rho.zero_()
-            H.compute_density(ft, c, 1.0, occ, omega, rho)
-            if world > 1:
-                comm.allreduce_rho(rho, stream)              # ChargeDensity.cc:309 dsum('r') over state columns
-                enl = comm.allreduce_scalars([enl])[0]       # NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519
+            if world == 1:
+                enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
+                rho.zero_()
+                H.compute_density(ft, c, 1.0, occ, omega, rho)
+            else:
+                # no host synchronisation inside the step: E_nl stays on the device, is placed behind rho(r), and ONE all-reduce
+                # carries both (ChargeDensity.cc:309 dsum('r') of rho; NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519 for E_nl)
+                H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi, want_enl=False)
+                rho_ext.zero_()
+                H.compute_density(ft, c, 1.0, occ, omega, rho)
+                nlp.last_enl(rho_ext[N:N + 1])
+                comm.allreduce_rho(rho_ext, stream)
+                enl = None
         return enl
 
     def sync_all():
@@ -447,6 +455,8 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     with torch.cuda.stream(stream):
         e1.record(stream)
     sync_all()
+    if world > 1:
+        enl = float(rho_ext[N].item())          # the all-reduced E_nl of the last step, read after the timed region
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     capi.profile_enable(False)

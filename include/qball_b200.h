@@ -156,6 +156,11 @@ int qb200_nl_destroy(qb200_nl* nl);
  * The row-sum of enl over G-row ranks (NonLocalPotential.cc:2629) is the identity with nprow = 1. */
 int qb200_nl_energy(qb200_nl* nl, int ldc, int nst, const double* c, const double* occ, int compute_hpsi, double* cp,
                     double* enl);
+/* E_nl of the last qb200_nl_energy / qb200_hpsi call.  A caller that passes enl = NULL to those calls gets no host
+ * synchronisation from them; the energy stays in a device scalar that this call copies out: to a DEVICE address without
+ * synchronising (on the object's stream; e.g. behind the density, so that one qb200_allreduce_rho carries rho and E_nl --
+ * the fused small all-reduce of NonLocalPotential.cc:2629 / ChargeDensity.cc:309), or to a HOST address (synchronous). */
+int qb200_nl_last_enl(qb200_nl* nl, double* enl);
 /* ---- Ultrasoft beta.psi path.  The object is created as above with, per species, the reference's
  * betag tables -- twnl[lm*ngw + ig] = beta_b(|k+G|) * Y_lm(k+G), lproj[lm] = l of channel lm, wt unused -- as
  * SlaterDet::calc_betag fills them before the (-i)^l factor (src/qball/SlaterDet.cc:2006-2127; an input like twnl).  Complex

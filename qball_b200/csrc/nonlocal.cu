@@ -1447,6 +1447,22 @@ extern "C" int qb200_nl_spsi(qb200_nl* nl, int ldc, int nst, const double* c, co
 #include "ultrasoft.cuh"
 
 double* qb200_nl_enl_dev(qb200_nl* nl) { return nl->enl_dev; }
+
+// E_nl of the last qb200_nl_energy / qb200_hpsi call (the device scalar the kernels summed into).  A DEVICE destination is
+// written on the object's stream without synchronising -- for callers that passed enl = NULL and reduce the energy on the
+// device, e.g. appended to the density buffer so that ONE all-reduce carries rho and E_nl; a HOST destination synchronises.
+extern "C" int qb200_nl_last_enl(qb200_nl* nl, double* enl)
+{
+  if (!nl || !enl) { set_error("qb200_nl_last_enl: bad argument"); return QB200_EINVAL; }
+  QB_CUDA(cudaSetDevice(nl->device));
+  if (is_device_ptr(enl)) {
+    QB_CUDA(cudaMemcpyAsync(enl, nl->enl_dev, sizeof(double), cudaMemcpyDeviceToDevice, nl->stream));
+  } else {
+    QB_CUDA(cudaMemcpyAsync(enl, nl->enl_dev, sizeof(double), cudaMemcpyDeviceToHost, nl->stream));
+    QB_CUDA(cudaStreamSynchronize(nl->stream));
+  }
+  return QB200_OK;
+}
 cudaStream_t qb200_nl_swap_stream(qb200_nl* nl, cudaStream_t s) { cudaStream_t o = nl->stream; nl->stream = s; return o; }
 
 // the subspace dense linear algebra on the same GEMM kernels (qb200_residual, qb200_gram)

@@ -227,6 +227,15 @@ class NonLocalPotential:
         tau = np.ascontiguousarray(tau, dtype=np.float64)
         capi._check(self._L.qb200_nl_set_positions(self._h, isp, capi.ptr(tau)), "qb200_nl_set_positions")
 
+    def last_enl(self, out=None):
+        """E_nl of the last energy / hpsi call: into a device tensor (1 double, asynchronous) or returned as a float (synchronous)"""
+        if out is not None:
+            capi._check(self._L.qb200_nl_last_enl(self._h, capi.ptr(out)), "qb200_nl_last_enl")
+            return out
+        e = np.zeros(1)
+        capi._check(self._L.qb200_nl_last_enl(self._h, capi.ptr(e)), "qb200_nl_last_enl")
+        return float(e[0])
+
     def update_twnl(self, isp: int, mproj, tabproj, gspl, vnlg, vnlg_spl, gcut=None):
         """NonLocalPotential::update_twnl for Kleinman-Bylander species `isp` on the device (NonLocalPotential.cc:261-1522, the twnl
         part): mproj / tabproj = m and radial-table index of every projector, gspl / vnlg / vnlg_spl = knots, values and second
@@ -327,15 +336,16 @@ class NonLocalPotential:
             pass
 
 
-def hpsi(ft: FourierTransform, nlp, c, occ, v, kpg2, out) -> float:
+def hpsi(ft: FourierTransform, nlp, c, occ, v, kpg2, out, want_enl: bool = True):
     """The H psi block of EnergyFunctional::energy(compute_hpsi=true) (EnergyFunctional.cc:1142-1153,1500,1675-1695):
-    out = V_nl c + 0.5|k+G|^2 c + FT[v FT^-1 c]; returns enl."""
+    out = V_nl c + 0.5|k+G|^2 c + FT[v FT^-1 c]; returns enl.  want_enl=False: no host synchronisation, E_nl stays on the
+    device (NonLocalPotential.last_enl) and None is returned."""
     nst, ldc = _block_dims(c)
     occ = np.ascontiguousarray(occ, dtype=np.float64)
     enl = C.c_double(0.0)
     capi._check(ft._L.qb200_hpsi(ft._h, nlp._h if nlp is not None else None, ldc, nst, capi.ptr(c), capi.ptr(occ), capi.ptr(v),
-                                 capi.ptr(kpg2), capi.ptr(out), C.byref(enl)), "qb200_hpsi")
-    return enl.value
+                                 capi.ptr(kpg2), capi.ptr(out), C.byref(enl) if want_enl else None), "qb200_hpsi")
+    return enl.value if want_enl else None
 
 
 def ekin_sums(ft: FourierTransform, c, occ, is_real: bool, kpg2, kpgx=None, fstress=None, dfstress=None, want_psi2sum=False):

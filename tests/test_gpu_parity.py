@@ -780,6 +780,25 @@ def test_cuda_ekin_sums_vs_oracle(kpoint, fc, host):
     assert abs(t0[0] - float(np.dot(occ, e))) < 1e-12 * abs(t0[0])
 
 
+def test_cuda_hpsi_without_host_synchronisation_keeps_enl_on_the_device():
+    """qb200_hpsi with enl = NULL does not synchronise; qb200_nl_last_enl hands the energy out afterwards -- to a device address
+    (behind the density, so that one all-reduce carries rho and E_nl) or to the host; same value as the synchronous call"""
+    g = load_golden("kpoint_cubic_au_oncv")
+    b = P.make_basis(g["cell"], g["ecut"], tuple(g["kpoint"]), bool(g["force_complex"]))
+    c, v, occ = regen_inputs(g, b["kpg2"])
+    ft = H.FourierTransform(b, g["np0"], g["np1"], g["np2"])
+    nlp = H.NonLocalPotential(b, g["species"])
+    cd, vd, kd = _dev(c), _dev(v), _dev(b["kpg2"])
+    out1, out2 = _dev(np.zeros_like(c)), _dev(np.zeros_like(c))
+    e_sync = H.hpsi(ft, nlp, cd, occ, vd, kd, out1)
+    assert H.hpsi(ft, nlp, cd, occ, vd, kd, out2, want_enl=False) is None
+    N = g["np0"] * g["np1"] * g["np2"]
+    ext = torch.zeros(N + 8, dtype=torch.float64, device="cuda")
+    nlp.last_enl(ext[N:N + 1])
+    assert nlp.last_enl() == e_sync and float(ext[N].item()) == e_sync and abs(e_sync - g["enl"]) <= 1e-10 * max(1.0, abs(g["enl"]))
+    assert torch.equal(out1, out2)
+
+
 def test_cuda_plans_of_different_shared_memory_need_coexist():
     """regression (found by running the reference itself through the shim, examples/sih4): the wavefunction plan and the
     density-basis plan of one run share the plane kernels but need different amounts of dynamic shared memory; the
