@@ -1180,50 +1180,44 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
   LA_LAUNCH_CHECK(la);
   int sweeps = 0;
   const int maxsweep = 30;                                  // the reference's own jacobi() uses the same cap (Wavefunction.cc:1594)
-  // A sweep is 2 (ne - 1) tiny launches: launch-bound.  On a capturable stream the sweep is captured ONCE into a CUDA graph and
-  // replayed for every sweep (same pointers, same step sequence); the legacy default stream cannot be captured and launches
-  // directly.  QB200_JACOBI_GRAPH=0: direct launches everywhere.
-  auto sweep = [&]() {
-    for (int step = 0; step < ne - 1; step++) {
-      k_jac_cols<<<ne / 2, 256, 0, la->stream>>>(A, Z, ne, step, rot);
-      k_jac_rows<<<dim3((ne + 255) / 256, ne / 2), 256, 0, la->stream>>>(A, ne, step, rot);
-    }
-  };
-  cudaGraphExec_t gexec = nullptr;
-  const int JAC_OFF_CTAS = 64;                                // (la->part, free between the two GEMMs, holds the 128 partial sums)
   la->jacobi_blocked = blocked;
+  double2 *Ubuf = nullptr, *Mbuf = nullptr;
+  int bj_inner = 1;
   if (blocked) {
-    double2* Ubuf = (double2*)(la->Dinv + 2 * (size_t)ne * ne + small_d);
-    double2* Mbuf = Ubuf + ubuf_d / 2;
+    Ubuf = (double2*)(la->Dinv + 2 * (size_t)ne * ne + small_d);
+    Mbuf = Ubuf + ubuf_d / 2;
     // cyclic sweeps over a pivot per visit: ONE (measured, 768 states: 67.8 ms against 99.7 / 126.1 ms with two / three -- the
     // number of outer sweeps stays the same, 11; the element-wise method with a graph: 133 ms); a single pivot = the whole
     // matrix is converged inside the kernel
-    int bj_inner = bj_nblk == 2 ? 12 : 1;
+    bj_inner = bj_nblk == 2 ? 12 : 1;
     if (const char* e = getenv("QB200_BJ_INNER")) bj_inner = std::max(1, atoi(e));
     QB_CUDA(cudaFuncSetAttribute(k_bj_pivot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_PIVOT_SMEM));
     QB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
     QB_CUDA(cudaFuncSetAttribute(k_bj_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
-    la->jacobi_graph = false;
-    for (; sweeps < maxsweep; sweeps++) {
-      double h[2];
-      k_jac_off<<<JAC_OFF_CTAS, 1024, 0, la->stream>>>(A, ne, la->part);
-      k_jac_off_sum<<<1, 32, 0, la->stream>>>(la->part, JAC_OFF_CTAS, sums);
-      LA_LAUNCH_CHECK(la);
-      QB_CUDA(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, la->stream));
-      QB_CUDA(cudaStreamSynchronize(la->stream));
-      if (!(h[0] > 1e-30 * h[1])) break;                    // off-diagonal norm below 1e-15 ||h||
+  }
+  const int launches_per_sweep = blocked ? 3 * (bj_nblk - 1) : 2 * (ne - 1);
+  auto sweep = [&]() {
+    if (blocked) {
       for (int step = 0; step < bj_nblk - 1; step++) {
         k_bj_pivot<<<bj_nblk / 2, BJ_PT, BJ_PIVOT_SMEM, la->stream>>>(A, ne, bj_nblk, step, Ubuf, Mbuf, bj_inner);
         k_bj_apply<0><<<dim3(bj_nblk / 2, ne / BJ_M, 2), 256, BJ_APPLY_SMEM, la->stream>>>(A, Z, ne, bj_nblk, step, Ubuf, Mbuf);
         k_bj_apply<1><<<dim3(bj_nblk / 2, ne / BJ_M, 1), 256, BJ_APPLY_SMEM, la->stream>>>(A, Z, ne, bj_nblk, step, Ubuf, Mbuf);
-        la->launches += 3;
       }
-      const cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return qb200::cuda_fail(e, "blocked jacobi sweep", __FILE__, __LINE__);
+    } else {
+      for (int step = 0; step < ne - 1; step++) {
+        k_jac_cols<<<ne / 2, 256, 0, la->stream>>>(A, Z, ne, step, rot);
+        k_jac_rows<<<dim3((ne + 255) / 256, ne / 2), 256, 0, la->stream>>>(A, ne, step, rot);
+      }
     }
-  } else {
+  };
+  // A sweep is a fixed sequence of small launches (same pointers, same steps every sweep): on a capturable stream it is
+  // captured ONCE into a CUDA graph and replayed, which also takes the host's launch jitter out of the loop; the legacy
+  // default stream cannot be captured and launches directly.  QB200_JACOBI_GRAPH=0: direct launches everywhere.
+  cudaGraphExec_t gexec = nullptr;
+  const int JAC_OFF_CTAS = 64;                                // (la->part, free between the two GEMMs, holds the 128 partial sums)
+  {
     const char* e = getenv("QB200_JACOBI_GRAPH");
-    const bool want = !(e && e[0] == '0') && ne > 32 && la->stream != 0 && la->stream != cudaStreamLegacy;
+    const bool want = !(e && e[0] == '0') && launches_per_sweep > 8 && la->stream != 0 && la->stream != cudaStreamLegacy;
     if (want && cudaStreamBeginCapture(la->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       sweep();
       cudaGraph_t graph = nullptr;
@@ -1234,8 +1228,8 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
       cudaGetLastError();                                   // a failed capture leaves no sticky error; the direct path takes over
     }
   }
-  if (!blocked) la->jacobi_graph = gexec != nullptr;
-  for (; !blocked && sweeps < maxsweep; sweeps++) {
+  la->jacobi_graph = gexec != nullptr;
+  for (; sweeps < maxsweep; sweeps++) {
     double h[2];
     k_jac_off<<<JAC_OFF_CTAS, 1024, 0, la->stream>>>(A, ne, la->part);
     k_jac_off_sum<<<1, 32, 0, la->stream>>>(la->part, JAC_OFF_CTAS, sums);
@@ -1249,7 +1243,7 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
     } else {
       sweep();
     }
-    la->launches += 2 * (ne - 1);
+    la->launches += launches_per_sweep;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { if (gexec) cudaGraphExecDestroy(gexec); return qb200::cuda_fail(e, "jacobi sweep", __FILE__, __LINE__); }
   }

@@ -330,12 +330,13 @@ def test_cuda_diag_vs_reference_fixture(name):
 
 
 @pytest.mark.gpu
-def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream(monkeypatch):
-    """the element-wise cyclic Jacobi (QB200_JACOBI_BLOCK=0): on a capturable stream the 2 (n - 1) launches of a sweep are
+@pytest.mark.parametrize("blocked", ["1", "0"])
+def test_cuda_diag_sweeps_from_a_cuda_graph_on_a_user_stream(blocked, monkeypatch):
+    """on a capturable stream the launches of a Jacobi sweep (blocked: 3 per block step; element-wise: 2 per rotation step) are
     captured once and replayed (the legacy default stream launches directly): same eigenvalues and rotated states"""
     import torch
     from qball_b200 import host as H
-    monkeypatch.setenv("QB200_JACOBI_BLOCK", "0")
+    monkeypatch.setenv("QB200_JACOBI_BLOCK", blocked)
     cell, ecut, nst = (10, 0, 0, 0, 9, 0, 0, 0, 11), 6.0, 70
     b = P.make_basis(cell, ecut, (0.2, 0.1, 0.0), False)
     c = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], False, 61), False)
