@@ -282,7 +282,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric, unit = METRIC, UNIT
-    config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; one NCCL all-reduce per step carries rho(r) and E_nl (no host synchronisation inside the step)" if world > 1 else ""),
+    config = {"workload": f"{args.workload}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; strong-scaling run: one NCCL all-reduce per step carries rho(r) and E_nl, no host synchronisation inside the step" if world > 1 and args.scaling == "strong" else ""),
               "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if args.workload == "mgo216" else "L2 flushed by the c/Hpsi block sweep",
               "anl": "the materialised projector block anl(G) depends on the atomic positions only and is kept across the steps (positions fixed, as over the SCF iterations of one ionic step); QB200_ANL_CACHE=0 regenerates it in every call like the reference's comp_anl (+0.08 ms per MgO216 step)"}
 
@@ -380,7 +380,7 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     from qball_b200 import host as H
     dev = torch.device("cuda", local_rank)
     metric, unit = METRIC, UNIT
-    config = {"workload": f"{wl_name}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; one NCCL all-reduce per step carries rho(r) and E_nl (no host synchronisation inside the step)" if world > 1 else ""),
+    config = {"workload": f"{wl_name}: {wl['note']}", "states_per_gpu": wl["nst"], "sharding": f"band x{world}" + ("; strong-scaling run: one NCCL all-reduce per step carries rho(r) and E_nl, no host synchronisation inside the step" if world > 1 and scaling == "strong" else ""),
               "l2": "inputs larger than L2 (coefficient block >> 126 MB)" if wl["nst"] * 16 * 70000 > (200 << 20) else "L2 flushed by the c/Hpsi block sweep",
               "anl": "the materialised projector block anl(G) depends on the atomic positions only and is kept across the steps (positions fixed, as over the SCF iterations of one ionic step); QB200_ANL_CACHE=0 regenerates it in every call like the reference's comp_anl (+0.08 ms per MgO216 step)"}
     b, grid = make_basis(wl["cell"], wl["ecut"], wl["kpoint"], wl["force_complex"])
@@ -416,12 +416,26 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
         from qball_b200 import parallel as PAR
         comm = _COMM["comm"] = PAR.Communicator.from_torch_distributed(local_rank)
 
+    # N > 1, two ways to run the step's collectives (A/B on one 8-GPU box, tools/gpu_n_ab.sh, profiles/r2z3_allreduce_ab_8gpu.txt):
+    #  * E_nl returned to the host by qb200_hpsi, then qb200_allreduce_rho + qb200_allreduce_scalars (two host synchronisations per step);
+    #  * fused: no host synchronisation, E_nl placed behind rho(r) on the device (qb200_nl_last_enl) and ONE all-reduce.
+    # Fused wins where the step is short (96 states per GPU: 2.83 against 3.01 ms at 8 GPUs; 2 GPUs, 768 states: 19.32 against
+    # 19.51-19.62 ms) and loses at 8 GPUs with long steps (768 states per GPU: 20.6-21.1 against 19.59 ms; cause not identified
+    # within the round's GPU budget), so it is the default of the strong-scaling run only; QB200_BENCH_FUSED_ALLREDUCE=0/1 overrides.
+    fused_allreduce = os.environ.get("QB200_BENCH_FUSED_ALLREDUCE", "1" if scaling == "strong" else "0") == "1"
+
     def step():
         with torch.cuda.stream(stream):
             if world == 1:
                 enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
                 rho.zero_()
                 H.compute_density(ft, c, 1.0, occ, omega, rho)
+            elif not fused_allreduce:
+                enl = H.hpsi(ft, nlp, c, occ, v, kpg2, hpsi)
+                rho.zero_()
+                H.compute_density(ft, c, 1.0, occ, omega, rho)
+                comm.allreduce_rho(rho, stream)
+                enl = comm.allreduce_scalars([enl])[0]
             else:
                 # no host synchronisation inside the step: E_nl stays on the device, is placed behind rho(r), and ONE all-reduce
                 # carries both (ChargeDensity.cc:309 dsum('r') of rho; NonLocalPotential.cc:2629 / EnergyFunctional.cc:1519 for E_nl)
@@ -455,7 +469,7 @@ def run_ours(args, wl_name, wl, rank, world, local_rank, steps, warmup, extras, 
     with torch.cuda.stream(stream):
         e1.record(stream)
     sync_all()
-    if world > 1:
+    if world > 1 and enl is None:
         enl = float(rho_ext[N].item())          # the all-reduced E_nl of the last step, read after the timed region
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
