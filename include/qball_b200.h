@@ -117,7 +117,7 @@ int qb200_nl_create(qb200_nl** nl, int device, int ngw, int is_real, double omeg
 /* add species: na atoms, npr projectors, lproj[npr], wt[npr], twnl[npr*ngw] (twnl[is][ipr*ngw+ig]), tau[3*na] */
 int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const double* wt, const double* twnl,
                          const double* tau);
-/* NonLocalPotential::update_twnl on the device for a Kleinman-Bylander species (nquad == 0; NonLocalPotential.cc:261-1522, the
+/* NonLocalPotential::update_twnl on the device; first for a Kleinman-Bylander species (nquad == 0; NonLocalPotential.cc:261-1522, the
  * twnl part -- the stress derivatives dtwnl stay with the caller): twnl[ipr*ngw + ig] = Y_lm(k+G) * v(|k+G|), real spherical
  * harmonics in the reference's order and normalisation, v from the species' radial cubic splines (Species::dvnlg,
  * Species.cc:1492-1505; splintd, spline.cc:126-156).  After a cell change the caller refreshes kpgx (a new object) or the
@@ -130,6 +130,10 @@ int qb200_nl_add_species(qb200_nl* nl, int na, int npr, const int* lproj, const 
  * qb200_nl_get_twnl copies the table of species `is` (npr*ngw doubles) back, host or device destination. */
 int qb200_nl_update_twnl(qb200_nl* nl, int is, const int* mproj, const int* tabproj, int ntab, int nknots, const double* gspl,
                          double gcut, const double* vnlg, const double* vnlg_spl);
+/* the same for a semi-local species (nquad > 0; NonLocalPotential.cc:366-419, 500-600, 800-960, 1230-1345): projector
+ * ipr = iquad + nquad*ilm has twnl[ipr*ngw + ig] = Y_lm(k+G) * 4 pi j_l(|k+G| r) r at its quadrature radius
+ * rproj[ipr] = rquad[is][iquad] (NonLocalPotential.cc:150-200); mproj[ipr] = m.  Host pointers. */
+int qb200_nl_update_twnl_semilocal(qb200_nl* nl, int is, const int* mproj, const double* rproj);
 int qb200_nl_get_twnl(qb200_nl* nl, int is, double* twnl);
 /* optional, before the first energy call: the integer description of the plane waves.
  *   idx    = Basis::idx_ptr(): 3*ngw ints, (h,k,l) of plane wave ig at idx[3*ig + 0..2]      (Basis.cc:672-674)

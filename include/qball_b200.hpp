@@ -166,6 +166,11 @@ class NonLocalPotential {
   void update_twnl(int is, const int* mproj, const int* tabproj, int ntab, int nknots, const double* gspl, double gcut,
                    const double* vnlg, const double* vnlg_spl)
   { check(qb200_nl_update_twnl(nl_, is, mproj, tabproj, ntab, nknots, gspl, gcut, vnlg, vnlg_spl), "qb200_nl_update_twnl"); }
+  // semi-local species (nquad > 0): mproj[ipr] = m, rproj[ipr] = rquad[is][iquad] of projector ipr = iquad + nquad*ilm
+  void update_twnl_semilocal(int is, const int* mproj, const double* rproj)
+  { check(qb200_nl_update_twnl_semilocal(nl_, is, mproj, rproj), "qb200_nl_update_twnl_semilocal"); }
+  // E_nl of the last energy / hpsi call (enl = 0 there: no host synchronisation); device destination: asynchronous
+  void last_enl(double* enl) { check(qb200_nl_last_enl(nl_, enl), "qb200_nl_last_enl"); }
   void get_twnl(int is, double* twnl) { check(qb200_nl_get_twnl(nl_, is, twnl), "qb200_nl_get_twnl"); }
   // optional: idx = basis.idx_ptr() (3*ngw), b = { cell.b(0), cell.b(1), cell.b(2) } as 9 doubles, kpoint = basis.kpoint()
   // in crystal units -> separable phase tables; complex states at k = 0 are then contracted over the half sphere

@@ -472,3 +472,56 @@ def update_twnl(kpgx, lproj, mproj, tabproj, gspl, vnlg, vnlg_spl, gcut=None):
             vcache[t] = np.where(kpg > gcut, 0.0, v)
         out[ipr] = ylm[(int(l), int(m))] * vcache[t]
     return out
+
+
+def _ylm_table(kpgx):
+    """real spherical harmonics of update_twnl (reference order and normalisation) for every plane wave: dict (l, m) -> array"""
+    kpgx = np.asarray(kpgx, dtype=np.float64)
+    x, y, z = kpgx[0], kpgx[1], kpgx[2]
+    kpg = np.sqrt(x * x + y * y + z * z)
+    with np.errstate(divide="ignore"):
+        gi = np.where(kpg > 0.0, 1.0 / kpg, 0.0)
+    pi = np.pi
+    fpi = 4.0 * pi
+    s14pi, s34pi, s54pi, s3 = np.sqrt(1.0 / fpi), np.sqrt(3.0 / fpi), np.sqrt(5.0 / fpi), np.sqrt(3.0)
+    s74pi, s2132pi, s3532pi, s1054pi = np.sqrt(7.0 / fpi), np.sqrt(21.0 / (32. * pi)), np.sqrt(35.0 / (32. * pi)), np.sqrt(105.0 / fpi)
+    gi2 = gi * gi
+    gi3 = gi2 * gi
+    xx, yy, zz = x * x * gi2, y * y * gi2, z * z * gi2
+    xy, yz, xz = x * y * gi2, y * z * gi2, x * z * gi2
+    return kpg, gi, {
+        (0, 0): s14pi + 0.0 * kpg,
+        (1, 0): s34pi * x * gi, (1, 1): s34pi * y * gi, (1, 2): s34pi * z * gi,
+        (2, 0): s54pi * 0.5 * (3.0 * zz - 1.0), (2, 1): s54pi * 0.5 * s3 * (xx - yy), (2, 2): s54pi * s3 * xy,
+        (2, 3): s54pi * s3 * yz, (2, 4): s54pi * s3 * xz,
+        (3, 0): s74pi * 0.5 * z * gi * (5.0 * zz - 3.0), (3, 1): s2132pi * x * gi * (5.0 * zz - 1.0),
+        (3, 2): s2132pi * y * gi * (5.0 * zz - 1.0), (3, 3): s1054pi * x * y * z * gi3,
+        (3, 4): s1054pi * 0.5 * z * gi * (xx - yy), (3, 5): s3532pi * x * gi * (xx - 3.0 * yy),
+        (3, 6): s3532pi * y * gi * (3.0 * xx - yy),
+    }
+
+
+def update_twnl_semilocal(kpgx, lproj, mproj, rproj):
+    """NonLocalPotential::update_twnl for a semi-local species (nquad > 0; NonLocalPotential.cc:366-419 l=0, :500-600 l=1,
+    :800-960 l=2, :1230-1345 l=3; no stress derivatives): twnl[ipr, ig] = Y_lm(k+G) 4 pi j_l(|k+G| r) r at the projector's
+    quadrature radius r, spherical Bessel functions written with sin / cos as the reference does (l = 0: 4 pi sin(qr)/q, and
+    4 pi r at q = 0; l >= 1: 0 at q r = 0)."""
+    kpg, gi, ylm = _ylm_table(kpgx)
+    fpi = 4.0 * np.pi
+    out = np.zeros((len(lproj), kpg.shape[0]))
+    for ipr, (l, m, r) in enumerate(zip(lproj, mproj, rproj)):
+        l, m, r = int(l), int(m), float(r)
+        zz = kpg * r
+        with np.errstate(divide="ignore", invalid="ignore"):
+            zi = np.where(zz != 0.0, 1.0 / zz, 0.0)
+            s, c = np.sin(zz), np.cos(zz)
+            if l == 0:
+                v = np.where((gi == 0.0) & (kpg == 0.0), fpi * r, fpi * np.sin(kpg * r) * gi)
+            elif l == 1:
+                v = np.where(zz != 0.0, fpi * ((s * zi - c) * zi) * r, 0.0)
+            elif l == 2:
+                v = np.where(zz != 0.0, fpi * (((3.0 * zi * zi - 1.0) * s - 3.0 * zi * c) * zi) * r, 0.0)
+            else:
+                v = np.where(zz != 0.0, fpi * ((15.0 * zi * zi - 6.0) * zi * zi * s - (15.0 * zi * zi - 1.0) * zi * c) * r, 0.0)
+        out[ipr] = ylm[(l, m)] * v
+    return out

@@ -382,6 +382,20 @@ int main(int argc, char** argv)
         dump(out + tag + ".kb_y.f64", &ytab[0], ytab.size()*sizeof(double));
         dump(out + tag + ".kb_y2.f64", &y2tab[0], y2tab.size()*sizeof(double));
       }
+      if (nlp->npr[is] > 0 && nlp->nquad[is] > 0) {
+        // semi-local species (nquad > 0): projector ipr = iquad + nquad * ilm (NonLocalPotential.cc:234-249); per projector its m
+        // and the quadrature radius its radial function 4 pi j_l(|k+G| r) r is taken at
+        vector<int> mproj(nlp->npr[is], -1);
+        vector<double> rproj(nlp->npr[is], 0.0);
+        int ilm = 0;
+        for (int l = 0; l <= nlp->lmax[is]; l++) {
+          if (l == nlp->lloc[is]) continue;
+          for (int m = 0; m < 2*l+1; m++, ilm++)
+            for (int iq = 0; iq < nlp->nquad[is]; iq++) { const int ipr = iq + nlp->nquad[is]*ilm; mproj[ipr] = m; rproj[ipr] = nlp->rquad[is][iq]; }
+        }
+        dump(out + tag + ".sl_m.i32", &mproj[0], mproj.size()*sizeof(int));
+        dump(out + tag + ".sl_r.f64", &rproj[0], rproj.size()*sizeof(double));
+      }
       dump(out + tag + ".kb.i32", kb, sizeof kb);
     }
   }

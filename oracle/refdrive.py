@@ -120,6 +120,8 @@ def run_reference(case: Case, seed: int = 1, nocc: int | None = None, workdir: s
                        tau=_load(prefix, f"sp{i}.tau.f64", np.float64).reshape(na, 3)))
         kb = _load(prefix, f"sp{i}.kb.i32", np.int32)
         sp[-1]["nquad"] = int(kb[0])
+        if npr > 0 and int(kb[0]) > 0:       # semi-local: per projector m and the quadrature radius (row a11)
+            sp[-1].update(mproj=_load(prefix, f"sp{i}.sl_m.i32", np.int32), rproj=_load(prefix, f"sp{i}.sl_r.f64", np.float64))
         if npr > 0 and int(kb[0]) == 0:      # Kleinman-Bylander: the radial spline tables update_twnl builds twnl from (row a11)
             ndft, ntab = int(kb[1]), int(kb[2])
             sp[-1].update(mproj=_load(prefix, f"sp{i}.kb_m.i32", np.int32), tabproj=_load(prefix, f"sp{i}.kb_tab.i32", np.int32),

@@ -65,6 +65,7 @@ def load():
     L.qb200_nl_last_enl.argtypes = [vp, dp]
     L.qb200_nl_update_twnl.argtypes = [vp, i, ip, ip, i, i, dp, d, dp, dp]
     L.qb200_nl_get_twnl.argtypes = [vp, i, dp]
+    L.qb200_nl_update_twnl_semilocal.argtypes = [vp, i, ip, dp]
     L.qb200_nl_us_set_density_basis.argtypes = [vp, i, dp]
     L.qb200_nl_us_set_species.argtypes = [vp, i, i, ip, ip, dp, dp]
     L.qb200_nl_us_energy.argtypes = [vp, i, i, dp, dp, dp, i, dp, dp]
@@ -108,7 +109,7 @@ def load():
     for name in ("qb200_profile_enable", "qb200_profile_read", "qb200_plan_create", "qb200_plan_destroy", "qb200_plan_set_stream", "qb200_plan_set_workspace", "qb200_plan_set_coefficient_tag",
                  "qb200_fft_backward", "qb200_fft_forward", "qb200_fft_backward_pair", "qb200_fft_forward_pair",
                  "qb200_rs_mul_add", "qb200_compute_density", "qb200_density_finish", "qb200_nl_create", "qb200_nl_add_species",
-                 "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_set_workspace", "qb200_nl_destroy", "qb200_nl_energy", "qb200_nl_betapsi", "qb200_nl_add_beta", "qb200_nl_spsi", "qb200_nl_last_enl", "qb200_nl_update_twnl", "qb200_nl_get_twnl", "qb200_nl_us_set_density_basis", "qb200_nl_us_set_species", "qb200_nl_us_energy", "qb200_nl_us_augment_density", "qb200_hpsi", "qb200_exponential",
+                 "qb200_nl_set_positions", "qb200_nl_set_lattice", "qb200_nl_set_stream", "qb200_nl_set_workspace", "qb200_nl_destroy", "qb200_nl_energy", "qb200_nl_betapsi", "qb200_nl_add_beta", "qb200_nl_spsi", "qb200_nl_last_enl", "qb200_nl_update_twnl", "qb200_nl_update_twnl_semilocal", "qb200_nl_get_twnl", "qb200_nl_us_set_density_basis", "qb200_nl_us_set_species", "qb200_nl_us_energy", "qb200_nl_us_augment_density", "qb200_hpsi", "qb200_exponential",
                  "qb200_compute_current", "qb200_la_create", "qb200_la_set_stream", "qb200_la_set_workspace", "qb200_la_destroy", "qb200_residual", "qb200_gram", "qb200_gram_overlap", "qb200_gram_apply", "qb200_gram_sharded"):
         getattr(L, name).restype = i
     _lib = L

@@ -907,6 +907,84 @@ extern "C" int qb200_nl_update_twnl(qb200_nl* nl, int is, const int* mproj, cons
   return QB200_OK;
 }
 
+// Semi-local species (nquad > 0; NonLocalPotential.cc:366-419 l = 0, :500-600 l = 1, :800-960 l = 2, :1230-1345 l = 3): projector
+// ipr = iquad + nquad * ilm carries twnl[ipr][ig] = Y_lm(k+G) 4 pi j_l(|k+G| r_iquad) r_iquad, the spherical Bessel functions written
+// with sin / cos as the reference writes them (l = 0: 4 pi sin(q r) / q, 4 pi r at q = 0; l >= 1: 0 at q r = 0).
+namespace qb200 {
+__global__ void __launch_bounds__(128) k_twnl_sl(int ngw, const double* __restrict__ kpgx, int npr, const int* __restrict__ lproj,
+                                                 const int* __restrict__ mproj, const double* __restrict__ rproj, double* __restrict__ twnl)
+{
+  const int ig = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ig >= ngw) return;
+  const double x = kpgx[ig], y = kpgx[ngw + ig], z = kpgx[2 * (size_t)ngw + ig];
+  const double g = sqrt(x * x + y * y + z * z);
+  const double gi = g > 0.0 ? 1.0 / g : 0.0;
+  const double pi = 3.14159265358979323846, fpi = 4.0 * pi;
+  const double s14pi = sqrt(1.0 / fpi), s34pi = sqrt(3.0 / fpi), s54pi = sqrt(5.0 / fpi), s3 = sqrt(3.0), s74pi = sqrt(7.0 / fpi),
+               s2132pi = sqrt(21.0 / (32. * pi)), s3532pi = sqrt(35.0 / (32. * pi)), s1054pi = sqrt(105.0 / fpi);
+  const double gi2 = gi * gi, gi3 = gi2 * gi;
+  const double xx = x * x * gi2, yy = y * y * gi2, zz = z * z * gi2, xy = x * y * gi2, yz = y * z * gi2, xz = x * z * gi2;
+  for (int ipr = 0; ipr < npr; ipr++) {
+    const int l = lproj[ipr];
+    const double r = rproj[ipr], zr = g * r;
+    double sn, cs;
+    sincos(zr, &sn, &cs);
+    double v = 0.0;
+    if (l == 0) v = g == 0.0 ? fpi * r : fpi * sn * gi;
+    else if (zr != 0.0) {
+      const double zi = 1.0 / zr;
+      if (l == 1) v = fpi * ((sn * zi - cs) * zi) * r;
+      else if (l == 2) v = fpi * (((3.0 * zi * zi - 1.0) * sn - 3.0 * zi * cs) * zi) * r;
+      else v = fpi * ((15.0 * zi * zi - 6.0) * zi * zi * sn - (15.0 * zi * zi - 1.0) * zi * cs) * r;
+    }
+    double ylm = 0.0;
+    switch (l * 8 + mproj[ipr]) {
+      case 0: ylm = s14pi; break;
+      case 8: ylm = s34pi * x * gi; break;
+      case 9: ylm = s34pi * y * gi; break;
+      case 10: ylm = s34pi * z * gi; break;
+      case 16: ylm = s54pi * 0.5 * (3.0 * zz - 1.0); break;
+      case 17: ylm = s54pi * 0.5 * s3 * (xx - yy); break;
+      case 18: ylm = s54pi * s3 * xy; break;
+      case 19: ylm = s54pi * s3 * yz; break;
+      case 20: ylm = s54pi * s3 * xz; break;
+      case 24: ylm = s74pi * 0.5 * z * gi * (5.0 * zz - 3.0); break;
+      case 25: ylm = s2132pi * x * gi * (5.0 * zz - 1.0); break;
+      case 26: ylm = s2132pi * y * gi * (5.0 * zz - 1.0); break;
+      case 27: ylm = s1054pi * x * y * z * gi3; break;
+      case 28: ylm = s1054pi * 0.5 * z * gi * (xx - yy); break;
+      case 29: ylm = s3532pi * x * gi * (xx - 3.0 * yy); break;
+      case 30: ylm = s3532pi * y * gi * (3.0 * xx - yy); break;
+    }
+    twnl[(size_t)ipr * ngw + ig] = ylm * v;
+  }
+}
+}  // namespace qb200
+
+extern "C" int qb200_nl_update_twnl_semilocal(qb200_nl* nl, int is, const int* mproj, const double* rproj)
+{
+  if (!nl || is < 0 || is >= (int)nl->sp.size() || !mproj || !rproj) { set_error("qb200_nl_update_twnl_semilocal: bad argument"); return QB200_EINVAL; }
+  const NlSpecies& S = nl->sp[is];
+  if (S.npr == 0) return QB200_OK;
+  QB_CUDA(cudaSetDevice(nl->device));
+  std::vector<int> l(S.npr);
+  QB_CUDA(cudaMemcpy(l.data(), S.lproj, S.npr * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < S.npr; i++)
+    if (mproj[i] < 0 || mproj[i] > 2 * l[i] || !(rproj[i] >= 0.0)) { set_error("qb200_nl_update_twnl_semilocal: projector description out of range"); return QB200_EINVAL; }
+  void *dm = nullptr, *dr = nullptr;
+  auto fail = [&](int rc) { for (void* q : { dm, dr }) if (q) cudaFree(q); return rc; };
+  if (cudaMalloc(&dm, S.npr * sizeof(int)) || cudaMalloc(&dr, S.npr * sizeof(double))) { set_error("qb200_nl_update_twnl_semilocal: out of device memory"); return fail(QB200_ENOMEM); }
+  cudaMemcpyAsync(dm, mproj, S.npr * sizeof(int), cudaMemcpyHostToDevice, nl->stream);
+  cudaMemcpyAsync(dr, rproj, S.npr * sizeof(double), cudaMemcpyHostToDevice, nl->stream);
+  k_twnl_sl<<<(nl->ngw + 127) / 128, 128, 0, nl->stream>>>(nl->ngw, nl->kpgx, S.npr, S.lproj, (const int*)dm, (const double*)dr, const_cast<double*>(S.twnl));
+  nl->launches++;
+  const cudaError_t e = cudaStreamSynchronize(nl->stream);
+  fail(0);
+  if (e != cudaSuccess) return cuda_fail(e, "qb200_nl_update_twnl_semilocal", __FILE__, __LINE__);
+  nl->W_valid = false; nl->Wg_valid = false; nl->sym_dirty = true;
+  return QB200_OK;
+}
+
 // the species' projector table as it sits on the device (npr * ngw doubles), for checks and for callers that keep a host copy
 extern "C" int qb200_nl_get_twnl(qb200_nl* nl, int is, double* twnl)
 {

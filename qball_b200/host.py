@@ -249,6 +249,13 @@ class NonLocalPotential:
         capi._check(self._L.qb200_nl_update_twnl(self._h, int(isp), mp, tp, int(y.shape[0]), int(g.shape[0]), capi.ptr(g),
                                                  float(g[-1] if gcut is None else gcut), capi.ptr(y), capi.ptr(y2)), "qb200_nl_update_twnl")
 
+    def update_twnl_semilocal(self, isp: int, mproj, rproj):
+        """NonLocalPotential::update_twnl for semi-local species `isp` (nquad > 0) on the device: mproj / rproj = m and quadrature
+        radius of every projector (ipr = iquad + nquad * ilm)"""
+        m, mp = capi._iarr(mproj)
+        r = np.ascontiguousarray(rproj, dtype=np.float64)
+        capi._check(self._L.qb200_nl_update_twnl_semilocal(self._h, int(isp), mp, capi.ptr(r)), "qb200_nl_update_twnl_semilocal")
+
     def get_twnl(self, isp: int, npr: int, ngw: int):
         out = np.zeros((npr, ngw))
         capi._check(self._L.qb200_nl_get_twnl(self._h, int(isp), capi.ptr(out)), "qb200_nl_get_twnl")

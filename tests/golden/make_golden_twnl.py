@@ -20,9 +20,34 @@ import make_golden as MG  # noqa: E402
 NAMES = ["gamma_triclinic_si_h", "kpoint_cubic_au_oncv", "forced_complex_ortho_al", "bulkal_fcc_kpoint", "mgo216_shape_112cubed"]
 
 
+PP = "/root/reference/share/pseudopotentials/quantum-simulation.org/hscv/pbe/"
+# semi-local species (nquad = 8): Yb (lmax 3, llocal 3: l = 0, 1, 2 projectors, 72 in all), Zr (lmax 2, llocal 0: l = 1, 2; 64);
+# a k-point in a triclinic cell and the Gamma point (the q = 0 row of the l = 0 Bessel function).  These cases are not in the
+# main fixtures, so the reference's tables are stored here with the basis parameters.
+SEMILOCAL = {
+    "semilocal_yb_kpoint": R.Case(cell=(8.2, 0, 0, 0.4, 7.9, 0, 0.2, -0.3, 8.8), ecut=4.0, kpoint=(0.1, 0.0, -0.2), nst=2, species=[("ytterbium", PP + "Yb_HSCV_PBE-1.0.xml")],
+                                  atoms=[("Yb1", "ytterbium", 0.3, 0.2, -0.1), ("Yb2", "ytterbium", 3.9, 4.1, 3.7)]),
+    "semilocal_yb_gamma": R.Case(cell=(8.2, 0, 0, 0, 7.9, 0, 0, 0, 8.8), ecut=4.0, nst=2, species=[("ytterbium", PP + "Yb_HSCV_PBE-1.0.xml")],
+                                 atoms=[("Yb1", "ytterbium", 0.3, 0.2, -0.1)]),
+    "semilocal_zr_kpoint": R.Case(cell=(8.2, 0, 0, 0.4, 7.9, 0, 0.2, -0.3, 8.8), ecut=4.0, kpoint=(0.1, 0.0, -0.2), nst=2, species=[("zirconium", PP + "Zr_HSCV_PBE-1.1.xml")],
+                                  atoms=[("Zr1", "zirconium", 0.3, 0.2, -0.1)]),
+}
+
+
 def main():
     outdir = os.path.join(HERE, "twnl")
     os.makedirs(outdir, exist_ok=True)
+    sl = os.path.join(HERE, "twnl_semilocal")
+    os.makedirs(sl, exist_ok=True)
+    for name, case in SEMILOCAL.items():
+        r = R.run_reference(case, seed=5)
+        s = r["species"][0]
+        assert s["nquad"] > 0
+        fn = os.path.join(sl, name + ".npz")
+        np.savez_compressed(fn, cell=np.array(case.cell, dtype=np.float64), ecut=case.ecut, kpoint=np.array(case.kpoint), ngw=r["ngw"], omega=r["omega"],
+                            na=s["na"], npr=s["npr"], nquad=s["nquad"], lproj=s["lproj"], wt=s["wt"], tau=s["tau"], mproj=s["mproj"], rproj=s["rproj"],
+                            twnl=s["twnl"], seed=5, nst=case.nst, mloc=r["mloc"], enl=r["enl"], hnl_checksum=float(np.abs(r["hnl"]).sum()))
+        print(f"{name}: npr {s['npr']} ngw {r['ngw']} -> {os.path.getsize(fn) / 1024:.0f} KiB")
     for name in NAMES:
         case, seed, nocc, mode, stride = MG.CASES[name]
         r = R.run_reference(case, seed=seed, nocc=nocc)

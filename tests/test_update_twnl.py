@@ -101,3 +101,68 @@ def test_cuda_update_twnl_rejects_bad_descriptions():
     with pytest.raises(capi.QB200Error):
         nlp.update_twnl(0, t["sp0_mproj"], t["sp0_tabproj"], t["sp0_gspl"][::-1].copy(), t["sp0_vnlg"], t["sp0_vnlg_spl"])
     nlp.close()
+
+
+# ---- semi-local species (nquad > 0): twnl = Y_lm(k+G) 4 pi j_l(|k+G| r_iquad) r_iquad; fixtures tests/golden/twnl_semilocal/*.npz
+SL = os.path.join(HERE, "golden", "twnl_semilocal")
+SLNAMES = sorted(f[:-4] for f in os.listdir(SL) if f.endswith(".npz"))
+
+
+def load_sl(name):
+    z = np.load(os.path.join(SL, name + ".npz"))
+    t = {k: z[k] for k in z.files}
+    b = P.make_basis(tuple(t["cell"]), float(t["ecut"]), tuple(t["kpoint"]), False)
+    assert b["ngw"] == int(t["ngw"])
+    return t, b
+
+
+@pytest.mark.parametrize("name", SLNAMES)
+def test_oracle_update_twnl_semilocal_vs_reference_tables(name):
+    """the numpy restatement against the reference's tables for the shipped semi-local potentials (Yb: l = 0, 1, 2; Zr: l = 1, 2;
+    8 quadrature radii each): equal to the last bits (sin / cos of numpy and of libm may differ by an ulp)"""
+    t, b = load_sl(name)
+    got = P.update_twnl_semilocal(b["kpgx"], t["lproj"], t["mproj"], t["rproj"])
+    assert relerr(got, t["twnl"]) < 1e-15
+
+
+def test_oracle_update_twnl_semilocal_l3_is_the_spherical_bessel_function():
+    """no shipped semi-local potential has l = 3 projectors: the restatement's j_3 (NonLocalPotential.cc:1305-1313) against scipy"""
+    from scipy.special import spherical_jn
+    t, b = load_sl(SLNAMES[0])
+    r = 1.7
+    got = P.update_twnl_semilocal(b["kpgx"], [3] * 7, list(range(7)), [r] * 7)
+    q = np.sqrt((b["kpgx"] ** 2).sum(axis=0))
+    _, _, ylm = P._ylm_table(b["kpgx"])
+    for m in range(7):
+        want = ylm[(3, m)] * 4.0 * np.pi * spherical_jn(3, q * r) * r
+        big = q * r > 0.5                      # the sin / cos form loses digits at small arguments (as the reference's does)
+        assert np.abs(got[m][big] - want[big]).max() < 1e-11 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SLNAMES)
+def test_cuda_update_twnl_semilocal_vs_reference_tables(name):
+    """qb200_nl_update_twnl_semilocal fills the tables on the device; read back they match the reference's, and E_nl computed
+    from them matches the reference's NonLocalPotential::energy on the fixture's seeded states"""
+    import torch
+    import refdrive as R
+    from qball_b200 import host as H
+    t, b = load_sl(name)
+    sp = dict(na=int(t["na"]), npr=int(t["npr"]), lproj=t["lproj"], wt=t["wt"], tau=t["tau"].reshape(-1, 3), twnl=None)
+    nlp = H.NonLocalPotential(b, [sp])
+    nlp.update_twnl_semilocal(0, t["mproj"], t["rproj"])
+    # (the sin / cos form of j_l cancels at small q r, in the reference as here: an ulp of sincos is worth ~1e-12 of the table)
+    assert relerr(nlp.get_twnl(0, sp["npr"], b["ngw"]), t["twnl"]) < 1e-11
+    c = R.synth_coefficients(b["kpg2"], float(t["ecut"]), int(t["nst"]), int(t["mloc"]), b["is_real"], int(t["seed"]))
+    occ = R.synth_occ(int(t["nst"]), None)
+    cd = torch.from_numpy(c).cuda()
+    cp = torch.zeros_like(cd)
+    enl = nlp.energy(cd, occ, True, cp)
+    assert abs(enl - float(t["enl"])) <= 1e-10 * max(1.0, abs(float(t["enl"])))
+    assert abs(float(np.abs(cp.cpu().numpy()).sum()) - float(t["hnl_checksum"])) <= 1e-9 * float(t["hnl_checksum"])
+    # l = 3 (no shipped potential): the device against the restatement
+    l3 = dict(na=1, npr=7, lproj=np.full(7, 3, dtype=np.int32), wt=np.ones(7), tau=np.zeros((1, 3)), twnl=None)
+    n3 = H.NonLocalPotential(b, [l3])
+    n3.update_twnl_semilocal(0, np.arange(7), np.full(7, 1.7))
+    assert relerr(n3.get_twnl(0, 7, b["ngw"]), P.update_twnl_semilocal(b["kpgx"], [3] * 7, list(range(7)), [1.7] * 7)) < 1e-11
+    nlp.close(); n3.close()
