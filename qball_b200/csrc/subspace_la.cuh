@@ -329,7 +329,9 @@ struct LaGeom {
 };
 
 // nall "projector" rows, nst columns; in_place: real bases read the block itself as W (no copy, one chunk)
-LaGeom la_geometry(const qb200_la* la, int nall, int nst, bool in_place, size_t ldc)
+// lower_only: the first GEMM computes a Hermitian matrix and its CTAs above the diagonal exit at once (k_fnl3) -- the split-K
+// that fills the SMs is chosen for the tiles that actually work
+LaGeom la_geometry(const qb200_la* la, int nall, int nst, bool in_place, size_t ldc, bool lower_only = false)
 {
   LaGeom g;
   g.m3 = !la->is_real;
@@ -355,8 +357,14 @@ LaGeom la_geometry(const qb200_la* la, int nall, int nst, bool in_place, size_t 
   g.ksplit = 1;
   const int maxk = std::max(1, std::min(g.gchunk, ngw) / 512);
   double best = -1.0;
+  long tiles = (long)g.mt * g.nt;
+  if (lower_only && g.m3) {
+    tiles = 0;
+    for (int bx = 0; bx < g.mt; bx++)
+      for (int by = 0; by < g.nt; by++) if (!(bx * 64 + 63 < by * 64)) tiles++;
+  }
   for (int k = 1; k <= std::min(maxk, 64); k++) {
-    const long ctas = (long)g.mt * g.nt * k;
+    const long ctas = tiles * k;
     const long waves = (ctas + slots - 1) / slots;
     const double eff = (double)ctas / (double)(waves * slots) - 0.002 * k;
     if (eff > best) { best = eff; g.ksplit = k; }
@@ -481,7 +489,7 @@ static int la_gram_dev(qb200_la* la, int ldc, int nst, double* c, int* info)
 {
   int rc;
   const int n = nst;
-  const LaGeom g = la_geometry(la, n, n, false, ldc);
+  const LaGeom g = la_geometry(la, n, n, false, ldc, true);
   la->nchunks_last = g.nchunks;
   if ((rc = la_prepare_W(la, g))) return rc;
   const int ncols = la->is_real ? n : 2 * n;
@@ -1139,7 +1147,7 @@ __global__ void __launch_bounds__(256) k_diag_operand(const double2* __restrict_
 static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc, int eigvec, double* w_host, int* sweeps_out)
 {
   int rc;
-  const LaGeom g = la_geometry(la, n, n, false, ldc);
+  const LaGeom g = la_geometry(la, n, n, false, ldc, true);   // h is read from its lower triangle (syevd / heevd 'l')
   la->nchunks_last = g.nchunks;
   if ((rc = la_prepare_W(la, g))) return rc;
   const int ncols = la->is_real ? n : 2 * n;
@@ -1163,7 +1171,7 @@ static int la_diag_dev(qb200_la* la, int ldc, int n, double* c, const double* hc
   for (int ch = 0; ch < g.nchunks; ch++) {
     const int gbeg = ch * g.gchunk, gcount = std::min(g.gchunk, ngw - gbeg), gpad = (gcount + 15) / 16 * 16;
     if ((rc = la_pack(la, g, c, ldc, gbeg, gcount, gpad))) return rc;
-    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, hc, ldc, n, ch > 0, 0))) return rc;
+    if ((rc = la_fnl(la, g, la->W, gbeg, gcount, hc, ldc, n, ch > 0, 1))) return rc;
   }
   const size_t total = (size_t)n * n;
   const int nblk = (int)((total + 255) / 256);
