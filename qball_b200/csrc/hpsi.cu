@@ -55,9 +55,17 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
     cd = p->st_c;
     if (upload_c) p->res_ptr = nullptr;
   }
+  cudaEvent_t ev_v = nullptr;
   if (!is_device_ptr(v)) {
-    if ((rc = ensure_buf(&p->st_v, &p->st_v_cap, N))) return rc;
-    QB_CUDA(cudaMemcpyAsync(p->st_v, v, N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    // v(r) from the host rides on the copy stream under the projector contraction (the first term of H psi does not read it);
+    // the local term of the first block waits for it
+    if ((rc = ensure_buf(&p->st_v, &p->st_v_cap, N)) || (rc = plan_copy_streams(p))) return rc;
+    cudaEvent_t e0;
+    if ((rc = plan_event(p, 100, &e0)) || (rc = plan_event(p, 101, &ev_v))) return rc;
+    QB_CUDA(cudaEventRecord(e0, p->stream));              // st_v may still be read by earlier work on the plan's stream
+    QB_CUDA(cudaStreamWaitEvent(p->s_in, e0, 0));
+    QB_CUDA(cudaMemcpyAsync(p->st_v, v, N * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+    QB_CUDA(cudaEventRecord(ev_v, p->s_in));
     vd = p->st_v;
   }
   if (kpg2 && !is_device_ptr(kpg2)) {
@@ -104,6 +112,7 @@ extern "C" int qb200_hpsi(qb200_plan* p, qb200_nl* nl, int ldc, int nst, const d
       qb200_nl_swap_stream(nl, saved);
       return rc;
     }
+    if (ev_v && b == 0) QB_CUDA(cudaStreamWaitEvent(p->stream, ev_v, 0));
     if ((rc = qb200_rs_mul_add_dev(p, ldc, nb, cd + off, vd, kd, od + off))) {                       // kinetic + sd.rs_mul_add(...)
       if (nl) qb200_nl_swap_stream(nl, saved);
       return rc;

@@ -1039,7 +1039,14 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
     cd = p->st_c;
     if (upload_c) { p->res_ptr = nullptr; if ((rc = plan_copy_streams(p))) return rc; }
   }
-  if ((rc = stage_in(p, rho, N, &p->st_v, &p->st_v_cap, &rd_c))) return rc;
+  // a host rho (the caller's running sum: rho += ...) is uploaded on the copy stream under the transforms -- only the final
+  // reduction reads it -- after the coefficient blocks, which are needed first
+  const bool rhost = !is_device_ptr(rho);
+  cudaEvent_t ev_rho = nullptr;
+  if (rhost) {
+    if ((rc = ensure(&p->st_v, &p->st_v_cap, N)) || (rc = plan_copy_streams(p))) return rc;
+    rd_c = p->st_v;
+  } else rd_c = rho;
   double* rd = const_cast<double*>(rd_c);
   if ((rc = ensure(&p->fac_dev, &p->fac_cap, nst))) return rc;
   // Real bases at Gamma: two states per transform, psi_1 + i psi_2 (the packing of FourierTransform.cc:555-581 that
@@ -1117,6 +1124,14 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
       QB_CUDA(cudaEventRecord(ev, p->s_in));
     }
   }
+  if (rhost) {
+    cudaEvent_t e0;
+    if ((rc = plan_event(p, 102, &e0)) || (rc = plan_event(p, 103, &ev_rho))) return rc;
+    QB_CUDA(cudaEventRecord(e0, p->stream));              // st_v may still be read by earlier work on the plan's stream
+    QB_CUDA(cudaStreamWaitEvent(p->s_in, e0, 0));
+    QB_CUDA(cudaMemcpyAsync(p->st_v, rho, N * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+    QB_CUDA(cudaEventRecord(ev_rho, p->s_in));
+  }
   if ((rc = ensure(&p->rho_part, &p->rho_part_elems, (size_t)ngroups * N))) return rc;
   QB_CUDA(cudaMemsetAsync(p->rho_part, 0, (size_t)ngroups * N * sizeof(double), p->stream));
   for (size_t ib = 0; ib < batches.size(); ib++) {
@@ -1129,6 +1144,7 @@ extern "C" int qb200_compute_density(qb200_plan* p, int ldc, int nst, const doub
     p->d.fac2off = 0;
     if (rc) return rc;
   }
+  if (ev_rho) QB_CUDA(cudaStreamWaitEvent(p->stream, ev_rho, 0));
   prof_begin(6, p->stream);
   k_rho_reduce<<<std::min<size_t>((N + 255) / 256, 148 * 8), 256, 0, p->stream>>>(rd, p->rho_part, N, ngroups);
   prof_end(p->stream);
