@@ -112,3 +112,57 @@ def test_band_sharded_residual_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] == 0.0 and res[1] < 1e-13, res
+
+
+def _worker_gram(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import port as P
+    import refdrive as R
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    errs = []
+    for kpoint, nst in (((0.25, 0, 0), 5), ((0, 0, 0), 7)):           # complex basis (blocks 3 + 2) and real basis (blocks 4 + 3)
+        cell, ecut = (9, 0, 0, 0, 9, 0, 0, 0, 10), 4.0
+        b = P.make_basis(cell, ecut, kpoint)
+        first, n = PAR.state_block(nst, rank, world)
+        c = R.synth_coefficients(b["kpg2"], ecut, n, b["ngw"], b["is_real"], seed=3, first_state=first)
+        call = PAR.allgather_states(torch.from_numpy(c), nst).numpy()            # the gathered block qb200_gram_sharded takes
+        # step 1 (qb200_gram_overlap): this rank's columns of S = c_all^H c_local, every other entry zero
+        S = np.zeros((nst, nst), dtype=np.complex128)
+        S[:, first:first + n] = P.subspace_h(call, c, b["is_real"])               # same product as the overlap: h with Hc := c
+        # step 2 (qb200_allreduce_rho on the nall x nall block): every entry has one non-zero contributor
+        St = torch.from_numpy(np.ascontiguousarray(S).view(np.float64).copy())
+        dist.all_reduce(St)
+        S = St.numpy().view(np.complex128).reshape(nst, nst)
+        # step 3 (qb200_gram_apply): Cholesky replicated, own columns of c_all L^-H
+        Lc = np.linalg.cholesky(np.tril(S) + np.tril(S, -1).conj().T)
+        T = np.linalg.inv(Lc).conj().T                                             # L^-H, upper triangular
+        mine = (T[:, first:first + n].T @ call)                                    # rows = this rank's new states
+        want = P.gram(R.synth_coefficients(b["kpg2"], ecut, nst, b["ngw"], b["is_real"], seed=3), b["is_real"])[first:first + n]
+        errs.append(float(np.abs(mine - want).max() / np.abs(want).max()) if n else 0.0)
+    e = torch.tensor(errs, dtype=torch.float64)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put(tuple(float(x) for x in e))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_sharded_gram_world2():
+    """SlaterDet::gram over sharded states as qb200_gram_sharded runs it: overlap columns of the rank's block -> sum over the
+    ranks -> Cholesky on every rank -> the rank's columns of c L^-H; the pieces reassemble the single-rank gram (numpy stands in
+    for the device kernels; the collectives are the real ones)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30400 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker_gram, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert max(res) < 1e-12, res
